@@ -1,0 +1,153 @@
+"""ctypes bindings for the CPU checkers (TEST INFRASTRUCTURE ONLY).
+
+`oracle()`  -> oracle/libmauve_oracle.so : our C restatement (oracle/mauve_oracle.c)
+`ref()`     -> oracle/_ref/libmauve_ref.so : the reference's own sources compiled in place
+               (only present where oracle/Makefile.ref was run; tests skip when absent).
+Nothing under mauve_b200/ imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "libmauve_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libmauve_ref.so")
+
+
+class Match3(C.Structure):
+    _fields_ = [("len", C.c_int64), ("s0", C.c_int64), ("s1", C.c_int64)]
+
+
+_cache = {}
+
+
+def _proto(lib, prefix):
+    u64, p = C.c_uint64, C.c_void_p
+    g = lambda n: getattr(lib, prefix + n)
+    g("get_seed").restype = u64
+    g("get_seed").argtypes = [C.c_int, C.c_int]
+    g("default_seed_weight").restype = C.c_uint
+    g("default_seed_weight").argtypes = [u64]
+    g("seed_length").argtypes = [u64]
+    g("seed_weight").argtypes = [u64]
+    g("sml_build").restype = C.c_longlong
+    g("sml_build").argtypes = [C.c_char_p, u64, u64, p, p]
+    g("find_mums").restype = C.c_longlong
+    g("find_mums").argtypes = [C.c_char_p, u64, C.c_char_p, u64, u64, C.c_int, C.POINTER(C.POINTER(Match3)), p]
+    g("free").argtypes = [p]
+    g("nw_align").restype = C.c_longlong
+    g("hmm_params").argtypes = [C.c_double] * 4 + [p]
+    g("hmm_run").argtypes = [C.c_char_p, u64, p, p, p]
+
+
+def oracle(build=True):
+    if "o" not in _cache:
+        if build and (not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(
+                os.path.join(ROOT, "oracle", "mauve_oracle.c"))):
+            subprocess.check_call(["make", "-s", "-f", os.path.join(ROOT, "oracle", "Makefile")])
+        lib = C.CDLL(ORACLE_SO)
+        _proto(lib, "orc_")
+        lib.orc_nw_align.argtypes = [C.c_char_p, C.c_uint, C.c_char_p, C.c_uint, C.c_void_p, C.c_void_p]
+        lib.orc_hmm_encode.restype = C.c_longlong
+        lib.orc_hmm_encode.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_void_p]
+        lib.orc_pack.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p]
+        lib.orc_packed_words.restype = C.c_uint64
+        lib.orc_packed_words.argtypes = [C.c_uint64]
+        _cache["o"] = lib
+    return _cache["o"]
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    if "r" not in _cache:
+        lib = C.CDLL(REF_SO)
+        _proto(lib, "ref_")
+        lib.ref_nw_align.argtypes = [C.c_char_p, C.c_uint, C.c_char_p, C.c_uint, C.c_void_p]
+        _cache["r"] = lib
+    return _cache["r"]
+
+
+class Checker:
+    """Uniform python face over either library (prefix 'orc_' or 'ref_')."""
+
+    def __init__(self, lib, prefix):
+        self.lib, self.prefix = lib, prefix
+
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def get_seed(self, weight, rank):
+        return int(self._f("get_seed")(weight, rank))
+
+    def default_seed_weight(self, avg_len):
+        return int(self._f("default_seed_weight")(avg_len))
+
+    def seed_length(self, seed):
+        return int(self._f("seed_length")(seed))
+
+    def seed_weight(self, seed):
+        return int(self._f("seed_weight")(seed))
+
+    def sml_build(self, seq: bytes, seed: int):
+        n = len(seq)
+        L = self.seed_length(seed)
+        m = max(n - L + 1, 0)
+        pos = np.zeros(max(m, 1), dtype=np.uint32)
+        mer = np.zeros(max(m, 1), dtype=np.uint64)
+        r = self._f("sml_build")(seq, n, seed, pos.ctypes.data, mer.ctypes.data)
+        if r < 0:
+            raise RuntimeError("sml_build failed")
+        return pos[:r], mer[:r]
+
+    def find_mums(self, s0: bytes, s1: bytes, seed: int, rule: int = 0):
+        out = C.POINTER(Match3)()
+        stats = np.zeros(4, dtype=np.uint64)
+        n = self._f("find_mums")(s0, len(s0), s1, len(s1), seed, rule, C.byref(out), stats.ctypes.data)
+        if n < 0:
+            raise RuntimeError("find_mums failed")
+        if n:
+            arr = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_int64)), shape=(n, 3)).copy()
+        else:
+            arr = np.zeros((0, 3), dtype=np.int64)
+        self._f("free")(out)
+        return arr, stats
+
+    def nw_align(self, a: bytes, b: bytes):
+        buf = np.zeros(len(a) + len(b) + 1, dtype=np.uint8)
+        if self.prefix == "orc_":
+            score = C.c_int64(0)
+            n = self.lib.orc_nw_align(a, len(a), b, len(b), buf.ctypes.data, C.byref(score))
+            sc = score.value
+        else:
+            n = self.lib.ref_nw_align(a, len(a), b, len(b), buf.ctypes.data)
+            sc = None
+        if n < 0:
+            raise RuntimeError("nw_align failed")
+        return buf[:n].tobytes(), sc
+
+    def hmm_params(self, gc=0.5, go_h=0.0, go_u=0.0, pct_id=0.0):
+        out = np.zeros(21, dtype=np.float64)
+        self._f("hmm_params")(gc, go_h, go_u, pct_id, out.ctypes.data)
+        return out
+
+    def hmm_run(self, sym: bytes, params):
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        pred = np.zeros(max(len(sym), 1), dtype=np.uint8)
+        post = np.zeros(max(len(sym), 1), dtype=np.float64)
+        r = self._f("hmm_run")(sym, len(sym), params.ctypes.data, pred.ctypes.data, post.ctypes.data)
+        if r != 0:
+            raise RuntimeError("hmm_run failed")
+        return pred[:len(sym)].tobytes(), post[:len(sym)]
+
+
+def oracle_checker():
+    return Checker(oracle(), "orc_")
+
+
+def ref_checker():
+    return Checker(ref(), "ref_")
