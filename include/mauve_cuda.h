@@ -1,0 +1,153 @@
+/*
+ * mauve_cuda.h -- C ABI of libmauve_cuda.so: the B200 (sm_100a) implementation of
+ * progressiveMauve's anchoring hot path.
+ *
+ * The reference (Wyss/mauve-py, mauve/src/libMems) has no FFI today: everything on this
+ * path is a C++ virtual call inside one process.  Each entry point below states the
+ * reference interface it replaces (paths relative to /root/reference/mauve/src/;
+ * LM = libMems/libMems, MU = muscle/libMUSCLE).  INTEGRATION.md shows the C++ adapter
+ * classes a maintainer adds on the reference side to bind them.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function returns 0
+ * on success and a negative MCU_E* code on failure; mcu_last_error() gives the text for
+ * the calling thread.  Host buffers are caller-owned; buffers returned through `**out`
+ * are library-owned until mcu_free().  There is NO CPU fallback: if no CUDA device is
+ * usable every compute entry point fails with MCU_ENODEV.
+ */
+#ifndef MAUVE_CUDA_H_
+#define MAUVE_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define MCU_OK 0
+#define MCU_ENODEV (-1)   /* no CUDA device / driver */
+#define MCU_ECUDA (-2)    /* CUDA runtime error (see mcu_last_error) */
+#define MCU_EINVAL (-3)   /* bad argument (seed pattern, sizes, NULL pointer) */
+#define MCU_EGAP (-4)     /* '-' in a genome sequence: the reference throws (LM/SortedMerList.cpp:433-437) */
+#define MCU_ENOMEM (-5)
+#define MCU_EALPHA (-6)   /* DP input outside ACGT (integer-exact kernel only) */
+
+/* One ungapped match, exactly the fields of a reference match-list row
+ * (LM/MatchList.h:617-662 WriteList: length, start0, start1; 1-based, start1 < 0 = reverse strand). */
+typedef struct mcu_match {
+    int64_t len;
+    int64_t start0;
+    int64_t start1;
+} mcu_match;
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+/* Selects the CUDA device for the calling process (one process per GPU). */
+int mcu_init(int device);
+void mcu_shutdown(void);
+const char* mcu_last_error(void);
+void mcu_free(void* p);
+/* Pinned host buffers for callers that want overlap-capable transfers. */
+int mcu_host_alloc(void** out, uint64_t bytes);
+void mcu_host_free(void* p);
+
+/* ---- seed patterns: LM/SeedMasks.h:298-321 getSeed, :389-401 getDefaultSeedWeight,
+ *      :335-373 getSeedLength/getSeedWeight (host-side table logic, no device work) -------- */
+#define MCU_SOLID_SEED 0x7fffffff
+#define MCU_CODING_SEED 3
+uint64_t mcu_get_seed(int weight, int seed_rank);
+unsigned mcu_default_seed_weight(uint64_t avg_sequence_length);
+int mcu_seed_length(uint64_t seed);
+int mcu_seed_weight(uint64_t seed);
+
+/* ---- sorted mer list: replaces mems::DNAMemorySML::Create (LM/MemorySML.cpp:45-60:
+ *      SortedMerList::Create + FillDnaSeedSML/FillDnaSML + std::sort(bmer_lessthan)) and the
+ *      data MemorySML::Read / operator[] recompute (LM/MemorySML.cpp:62-94).
+ *      seq: n ASCII bases.  Outputs (each optional, may be NULL):
+ *        pos_out[n-L+1]    positions in sorted order (ties position-ascending)
+ *        mer_out[n-L+1]    bmer::mer of each rank (canonical seed left-aligned | strand bit)
+ *        packed_out[ceil(n/16)+2]  2-bit sequence exactly as SortedMerList::sequence
+ *      *sml_len_out = n-L+1 (0 when n < L).                                                  */
+int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed,
+                  uint32_t* pos_out, uint64_t* mer_out, uint32_t* packed_out, uint64_t* sml_len_out);
+
+/* ---- seed-match enumeration + extension: replaces MemHash::FindMatches(MatchList&)
+ *      (LM/MemHash.cpp:109-127) for two genomes, i.e. MatchFinder::SearchRange
+ *      (LM/MatchFinder.cpp:172-340) -> EnumerateMatches (LM/PairwiseMatchFinder.cpp:37-71 for
+ *      rule 0; LM/MemHash.cpp:139-162 with tolerances 0/1 for rule 1) -> HashMatch/SetDirection
+ *      (:167-203) -> AddHashEntry (:209-251) -> ExtendMatch (LM/MatchFinder.h:218-374)
+ *      -> GetMatchList (LM/MemHash.h:183-203).  Rows come back in the reference's list order.
+ *      stats (optional, 8 x uint64): [0] seed pairs (unique in both genomes), [1] matches,
+ *      [2] collisions = [0]-[1] (MemHash::MemCollisionCount), [3] 1 if some join run exceeds
+ *      MER_REPEAT_LIMIT=1000 (the reference's skip-ahead branch, LM/MatchFinder.cpp:253-277,
+ *      is not reproduced; such runs never produce seed pairs), [4..7] reserved.                */
+#define MCU_RULE_PAIRWISE 0
+#define MCU_RULE_MEMHASH 1
+int mcu_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule,
+                  mcu_match** out, uint64_t* n_out, uint64_t* stats);
+
+/* ---- device-resident session (measurement + multi-GPU sharding) -------------------------
+ * Same computation as mcu_find_mums, split so the timed region can start with both genomes
+ * already in HBM.  shard_index/shard_count partition the seed-key space by canonical-key
+ * prefix: each rank keeps only keys in its range; the per-rank match lists are
+ * merged by mcu_merge_matches on rank 0.                                                    */
+typedef struct mcu_session mcu_session;
+int mcu_session_create(mcu_session** out);
+void mcu_session_destroy(mcu_session* s);
+/* H2D of both genomes (async on the session stream, then synchronised). */
+int mcu_session_upload(mcu_session* s, const char* seq0, uint64_t n0, const char* seq1, uint64_t n1);
+/* pack + seedgen + sort + join + extend + order on the session stream.  stage_ms (optional,
+ * 8 floats, CUDA-event times): [0] pack, [1] seedgen, [2] sort, [3] join, [4] extend,
+ * [5] order, [6] total, [7] sort passes run.  Leaves the ordered match list on the device.  */
+int mcu_session_run(mcu_session* s, uint64_t seed, int shard_index, int shard_count,
+                    float* stage_ms, uint64_t* stats);
+/* number of matches produced by the last run */
+uint64_t mcu_session_match_count(const mcu_session* s);
+/* D2H copy of the match list into caller memory (n = mcu_session_match_count). */
+int mcu_session_download(mcu_session* s, mcu_match* out);
+/* device pointer to the match rows (3 x int64 each) for NCCL gathers by the host language */
+const void* mcu_session_matches_device(const mcu_session* s);
+/* kernels launched by this session since creation (bench.py's gpu_launches claim) */
+uint64_t mcu_session_launch_count(const mcu_session* s);
+/* Rank-0 merge of per-shard lists gathered into one device or host array: sorts into the
+ * reference list order and drops the duplicates that shards produce for one maximal match
+ * (the distributed form of AddHashEntry's containment check).  in_device != 0 means `rows`
+ * is a device pointer.  Result in library-owned host memory (*out, *n_out).               */
+int mcu_merge_matches(const mcu_match* rows, uint64_t n, int in_device, mcu_match** out, uint64_t* n_out);
+
+/* ---- gapped DP: replaces muscle::GlobalAlign (MU/glbalign.cpp:69-81 -> NWSmall
+ *      MU/nwsmall.cpp:500-670 + BitTraceBack MU/bittraceback.cpp:138-) for batches of
+ *      two single-sequence ACGT profiles (the 2-genome case).
+ *      a/b: concatenated sequences; a_off/b_off: n+1 offsets.  path_off (n+1, input): where each
+ *      problem's path goes in path_out (capacity la+lb per problem).  Outputs: path_out edge
+ *      types 'M','D','I' first-to-last edge (PWPath order), path_len[n], score[n] (max of
+ *      MAB/DAB/IAB -- NWSmall itself returns 0).  gcups_ms (optional): device time in ms.     */
+int mcu_nw_batch(uint64_t n, const char* a, const uint64_t* a_off, const char* b, const uint64_t* b_off,
+                 const uint64_t* path_off, char* path_out, uint32_t* path_len, int64_t* score, float* device_ms);
+/* counters of the last mcu_nw_batch call (5 x uint64): [0] DP cells (sum la*lb), [1] forward kernel
+ * launches, [2] traceback-side launches, [3] sub-batches, [4] traceback bytes of the largest one */
+void mcu_nw_last_stats(uint64_t* out5);
+
+/* ---- HomologyHMM: replaces run() (LM/HomologyHMM/homologymain.cc:24-62 = Forward
+ *      homology.cc:307-394 + Backward :400-547 + posterior threshold 0.9) for a batch of
+ *      symbol strings over '1'..'8' (encoder: LM/Islands.h:90-155).
+ *      params: 21 doubles in struct Params order (homology.h:169-177): iStartHomologous,
+ *      iGoHomologous, iGoUnrelated, iGoStopFromUnrelated, iGoStopFromHomologous,
+ *      aEmitHomologous[8], aEmitUnrelated[8].  sym/off: concatenated strings + n+1 offsets.
+ *      pred_out: 'H'/'N' per column; post_out (optional): posterior of "homologous".        */
+int mcu_hmm_params(double gc_content, double go_homologous, double go_unrelated, double pct_identity, double* params_out);
+int mcu_hmm_batch(uint64_t n, const char* sym, const uint64_t* off, const double* params,
+                  char* pred_out, double* post_out, float* device_ms);
+
+/* ---- test hooks (exercise single kernels through the ABI) -------------------------------- */
+/* stable LSD radix sort of (key,val) pairs on the low `bits` bits; key_bytes is 4 or 8 */
+int mcu_test_sort_pairs(void* keys, uint32_t* vals, uint64_t n, int key_bytes, int bits);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAUVE_CUDA_H_ */

@@ -1,0 +1,94 @@
+"""ctypes binding of the C ABI declared in include/mauve_cuda.h (libmauve_cuda.so).
+
+There is no CPU fallback anywhere in this package: if the shared library is missing the import
+of `lib()` raises, and if no sm_100 device is usable every compute call raises McuError
+(MCU_ENODEV).  Nothing here imports or executes anything under oracle/.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmauve_cuda.so")
+
+MCU_OK, MCU_ENODEV, MCU_ECUDA, MCU_EINVAL, MCU_EGAP, MCU_ENOMEM, MCU_EALPHA = 0, -1, -2, -3, -4, -5, -6
+SOLID_SEED = 0x7FFFFFFF
+CODING_SEED = 3
+RULE_PAIRWISE, RULE_MEMHASH = 0, 1
+
+# every symbol include/mauve_cuda.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "mcu_init", "mcu_shutdown", "mcu_last_error", "mcu_free", "mcu_host_alloc", "mcu_host_free",
+    "mcu_get_seed", "mcu_default_seed_weight", "mcu_seed_length", "mcu_seed_weight",
+    "mcu_sml_build", "mcu_find_mums",
+    "mcu_session_create", "mcu_session_destroy", "mcu_session_upload", "mcu_session_run",
+    "mcu_session_match_count", "mcu_session_download", "mcu_session_matches_device",
+    "mcu_session_launch_count", "mcu_merge_matches",
+    "mcu_nw_batch", "mcu_nw_last_stats", "mcu_hmm_params", "mcu_hmm_batch", "mcu_test_sort_pairs",
+]
+
+
+class McuError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("libmauve_cuda error %d: %s" % (code, text))
+        self.code = code
+
+
+class Match(C.Structure):
+    _fields_ = [("len", C.c_int64), ("start0", C.c_int64), ("start1", C.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libmauve_cuda.so (building is __graft_entry__.build()'s job); raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    u64, vp, i32 = C.c_uint64, C.c_void_p, C.c_int
+    L.mcu_init.argtypes = [i32]
+    L.mcu_shutdown.restype = None
+    L.mcu_last_error.restype = C.c_char_p
+    L.mcu_free.argtypes = [vp]
+    L.mcu_free.restype = None
+    L.mcu_host_alloc.argtypes = [C.POINTER(vp), u64]
+    L.mcu_host_free.argtypes = [vp]
+    L.mcu_host_free.restype = None
+    L.mcu_get_seed.argtypes = [i32, i32]
+    L.mcu_get_seed.restype = u64
+    L.mcu_default_seed_weight.argtypes = [u64]
+    L.mcu_default_seed_weight.restype = C.c_uint
+    L.mcu_seed_length.argtypes = [u64]
+    L.mcu_seed_weight.argtypes = [u64]
+    L.mcu_sml_build.argtypes = [vp, u64, u64, vp, vp, vp, C.POINTER(u64)]
+    L.mcu_find_mums.argtypes = [vp, u64, vp, u64, u64, i32, C.POINTER(C.POINTER(Match)), C.POINTER(u64), vp]
+    L.mcu_session_create.argtypes = [C.POINTER(vp)]
+    L.mcu_session_destroy.argtypes = [vp]
+    L.mcu_session_destroy.restype = None
+    L.mcu_session_upload.argtypes = [vp, vp, u64, vp, u64]
+    L.mcu_session_run.argtypes = [vp, u64, i32, i32, vp, vp]
+    L.mcu_session_match_count.argtypes = [vp]
+    L.mcu_session_match_count.restype = u64
+    L.mcu_session_download.argtypes = [vp, vp]
+    L.mcu_session_matches_device.argtypes = [vp]
+    L.mcu_session_matches_device.restype = vp
+    L.mcu_session_launch_count.argtypes = [vp]
+    L.mcu_session_launch_count.restype = u64
+    L.mcu_merge_matches.argtypes = [vp, u64, i32, C.POINTER(C.POINTER(Match)), C.POINTER(u64)]
+    L.mcu_nw_batch.argtypes = [u64, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
+    L.mcu_nw_last_stats.argtypes = [vp]
+    L.mcu_nw_last_stats.restype = None
+    L.mcu_hmm_params.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, vp]
+    L.mcu_hmm_batch.argtypes = [u64, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
+    L.mcu_test_sort_pairs.argtypes = [vp, vp, u64, i32, i32]
+    _lib = L
+    return L
+
+
+def check(code):
+    if code != MCU_OK:
+        raise McuError(code, (lib().mcu_last_error() or b"").decode("utf-8", "replace"))

@@ -1,0 +1,613 @@
+// Anchoring pipeline kernels (sm_100a).  Reference semantics cited per kernel; LM = libMems/libMems.
+//
+// Data layout in HBM (per session):
+//   ascii[g]   n_g bytes                      input genome g
+//   packed[g]  ceil(n_g/16)+2 u32             2-bit, MSB-first per word, 2 zero pad words (SortedMerList::sequence)
+//   keys/vals  (n_0-L+1)+(n_1-L+1) pairs x2   key = canon(2w bits)<<2 | genome<<1 | strand ; val = position
+//   partner    u32 per genome-0 position      genome-1 position of the unique seed pair starting there
+//   flags      u8 per genome-0 position       bit0 = unique seed pair, bit1 = reverse strand
+//   cand       u32 list                       seeds that may be the leftmost unique seed of their match
+//   matches    mcu_match rows                 raw, then ordered into the reference list order
+#include "anchor.cuh"
+
+namespace mcu {
+
+// =========================================================================================
+// pack2bit: SortedMerList::translate32 (LM/SortedMerList.cpp:425-460) with the BasicDNATable
+// (:29-47): A=0, C/B/Y=1, G/S/K=2, T=3, anything else 0; '-' is an error (:433-437).
+// One thread -> one 32-bit word (16 bases), 128-bit coalesced loads.  HBM-bound: 1 B read +
+// 0.25 B written per base.
+// =========================================================================================
+__device__ __forceinline__ u32 base_code(u32 c, u32& gap)
+{
+    // 2-bit code per letter index (c & 31): C=3,B=2,Y=25 -> 1 ; G=7,S=19,K=11 -> 2 ; T=20 -> 3
+    const u64 TABLE = (1ull << 6) | (1ull << 4) | (1ull << 50) | (2ull << 14) | (2ull << 38) | (2ull << 22) | (3ull << 40);
+    gap |= (c == (u32)'-');
+    u32 u = c & 0xDFu;
+    return (u - 65u) < 26u ? (u32)((TABLE >> (2 * (c & 31u))) & 3ull) : 0u;
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const u8* __restrict__ seq, u64 n, u32* __restrict__ packed, u64 words_total, u32* __restrict__ err)
+{
+    u32 gap = 0;
+    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < words_total; w += (u64)gridDim.x * blockDim.x) {
+        u64 base = w * 16;
+        u32 v = 0;
+        if (base + 16 <= n) {
+            uint4 q = __ldg((const uint4*)(seq + base));
+            u32 qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    u32 c = (qq[k] >> (8 * b)) & 255u;
+                    v |= base_code(c, gap) << (30 - 2 * (4 * k + b));
+                }
+            }
+        } else if (base < n) {
+            for (u32 j = 0; base + j < n; ++j) v |= base_code(seq[base + j], gap) << (30 - 2 * j);
+        }
+        packed[w] = v;
+    }
+    if (gap) atomicOr(err, 1u);
+}
+
+// =========================================================================================
+// seedgen: for every position p in [0, n-L+1): canonical spaced seed + strand flag =
+// SortedMerList::GetSeedMer (:726-762), RevCompMer (:597-614), GetDnaSeedMer (:764-769),
+// FillDnaSeedSML (:771-783) / FillDnaSML (:617-723, same values for solid seeds).
+// Emits key = canon<<2 | genome<<1 | strand (order-isomorphic to bmer::mer per genome, with the
+// genome bit placed so that one sort of both genomes also groups the join key `canon`), and
+// accumulates the digit histograms of all radix passes on the fly (so the sort never re-reads
+// the keys for counting).  Coalesced: thread t of a block handles position base+t.
+// HBM traffic: 0.25 B/base packed read (L1/L2 served) + sizeof(K)+4 written.
+// =========================================================================================
+template <typename K>
+__global__ void __launch_bounds__(256) seedgen_kernel(const u32* __restrict__ packed, u64 npos, SeedParams sp, u32 genome,
+                                                     K* __restrict__ keys, u32* __restrict__ vals, u64 out_base,
+                                                     u64* __restrict__ hist, int passes, int sharded, u64 canon_lo, u64 canon_hi,
+                                                     unsigned long long* __restrict__ out_counter)
+{
+    extern __shared__ u32 sh_hist[];  // passes*256
+    for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 rounds = (npos + stride - 1) / stride;
+    for (u64 r = 0; r < rounds; ++r) {
+        u64 p = r * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+        bool live = p < npos;
+        u64 key = 0;
+        if (live) {
+            u64 f = extract_seed(load_mer32(packed, p), sp);
+            u64 rc = revcomp_seed(f, sp.w);
+            u32 strand = rc < f;  // GetDnaSeedMer: forward wins ties (f < rc|1)
+            u64 canon = strand ? rc : f;
+            key = (canon << 2) | (genome << 1) | strand;
+            if (sharded) live = canon >= canon_lo && canon < canon_hi;
+        }
+        u64 slot = out_base + p;
+        if (sharded) {  // unordered compaction (tie order is irrelevant for match finding)
+            u32 m = __ballot_sync(0xffffffffu, live);
+            u64 wbase = 0;
+            if (lane == 0 && m) wbase = atomicAdd(out_counter, (unsigned long long)__popc(m));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            slot = out_base + wbase + __popc(m & lanemask_lt());
+        }
+        if (live) {
+            keys[slot] = (K)key;
+            vals[slot] = (u32)p;
+            for (int q = 0; q < passes; ++q) atomicAdd(&sh_hist[q * 256 + (u32)((key >> (8 * q)) & 255)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * 256; i += blockDim.x)
+        if (sh_hist[i]) atomicAdd((unsigned long long*)&hist[i], (unsigned long long)sh_hist[i]);
+}
+
+// keys -> bmer::mer values (canonical seed left-aligned in 64 bits | strand bit) for MemorySML::Read
+template <typename K>
+__global__ void keys_to_mers_kernel(const K* __restrict__ keys, u64 n, int w, u64* __restrict__ mers)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 k = keys[i];
+        mers[i] = ((k >> 2) << (64 - 2 * w)) | (k & 1);
+    }
+}
+
+// =========================================================================================
+// join: MatchFinder::SearchRange (LM/MatchFinder.cpp:172-340) merges the sorted lists on
+// mer & seed_mask and hands every equal-key run to EnumerateMatches; for two genomes both
+// PairwiseMatchFinder::EnumerateMatches (LM/PairwiseMatchFinder.cpp:37-71) and MemHash's
+// (LM/MemHash.cpp:139-162, tolerances 0/1) keep exactly the runs with one occurrence in each
+// genome.  In the combined sorted array such a run is "g0 entry immediately followed by a g1
+// entry with the same canon, different canon on both sides" -- a purely local test.
+// Output = HashMatch + SetDirection (LM/MemHash.cpp:167-203) in array form: partner[p0] = p1,
+// flags[p0] = 1 | rev<<1.  HBM traffic: sizeof(K) per pair (neighbours come from L1) + 4 B per
+// seed pair read + 5 B written.
+// counters: [0] seed pairs, [1] repeat-limit flag.
+// =========================================================================================
+template <typename K>
+__global__ void __launch_bounds__(256) join_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, u64 n,
+                                                  u32* __restrict__ partner, u8* __restrict__ flags,
+                                                  unsigned long long* __restrict__ counters)
+{
+    u32 found = 0, repeat = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        K k = keys[i];
+        K canon = k >> 2;
+        if (i + 1000 < n && (keys[i + 1000] >> 2) == canon) repeat = 1;  // run longer than MER_REPEAT_LIMIT
+        if ((k >> 1) & 1) continue;    // a pair starts at its genome-0 entry
+        if (i + 1 >= n) continue;
+        K k1 = keys[i + 1];
+        if ((k1 >> 2) != canon || !((k1 >> 1) & 1)) continue;
+        if (i > 0 && (keys[i - 1] >> 2) == canon) continue;
+        if (i + 2 < n && (keys[i + 2] >> 2) == canon) continue;
+        u32 p0 = vals[i], p1 = vals[i + 1];
+        u32 rev = (u32)((k ^ k1) & 1);
+        partner[p0] = p1;
+        flags[p0] = (u8)(1u | (rev << 1));
+        ++found;
+    }
+    // block reduce
+    __shared__ u32 s_found, s_rep;
+    if (threadIdx.x == 0) { s_found = 0; s_rep = 0; }
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) found += __shfl_down_sync(0xffffffffu, found, o);
+    repeat = __any_sync(0xffffffffu, repeat);
+    if ((threadIdx.x & 31) == 0) {
+        if (found) atomicAdd(&s_found, found);
+        if (repeat) s_rep = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_found) atomicAdd(&counters[0], (unsigned long long)s_found);
+        if (s_rep) atomicMax(&counters[1], 1ull);
+    }
+}
+
+// =========================================================================================
+// candidate filter: a seed whose left neighbour on the same diagonal is also a unique seed
+// pair cannot be the leftmost unique seed of its match -> drop it with two byte loads.
+// This is the bulk of AddHashEntry's "already contained" rejections (LM/MemHash.cpp:215-220):
+// 2.7 M seed pairs -> ~30 k candidates on MDS42.  counters[2] = number of candidates.
+// =========================================================================================
+__global__ void __launch_bounds__(256) candidate_kernel(const u32* __restrict__ partner, const u8* __restrict__ flags, u64 npos0,
+                                                       u32* __restrict__ cand, unsigned long long* __restrict__ counters)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 rounds = (npos0 + stride - 1) / stride;
+    for (u64 r = 0; r < rounds; ++r) {
+        u64 p = r * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+        bool is_cand = false;
+        if (p < npos0) {
+            u32 f = flags[p];
+            if (f & 1) {
+                is_cand = true;
+                if (p > 0) {
+                    u32 fl = flags[p - 1];
+                    if ((fl & 1) && fl == f) {
+                        u32 p1 = partner[p], q1 = partner[p - 1];
+                        // same diagonal: forward p1-1, reverse p1+1
+                        if ((f & 2) ? (q1 == p1 + 1) : (q1 + 1 == p1)) is_cand = false;
+                    }
+                }
+            }
+        }
+        u32 m = __ballot_sync(0xffffffffu, is_cand);
+        if (m) {
+            u64 base = 0;
+            if (lane == 0) base = atomicAdd(&counters[2], (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (is_cand) cand[base + __popc(m & lanemask_lt())] = (u32)p;
+        }
+    }
+}
+
+// =========================================================================================
+// extend: MatchFinder::ExtendMatch (LM/MatchFinder.h:218-374) + the containment dedupe of
+// MemHash::AddHashEntry (LM/MemHash.cpp:209-251), in closed form:
+// on the seed's diagonal a "hit" at offset t is spaced-seed equality of the two genomes with
+// the strand relation of the seed (forward: f0 == f1; reverse: f0 == revcomp(f1) and f0 not
+// its own reverse complement -- the parity test of :281-303); the match is the maximal chain
+// of hits with gaps <= L containing the seed, clipped to valid seed positions (:248-257).
+// One warp per candidate: lanes probe the L offsets beyond the current end, ballot, jump to
+// the farthest hit.  While walking left, meeting another unique seed pair of the same diagonal
+// means this candidate is not the leftmost one of its match -> abandon (exactly one emitter
+// per match).  counters[3] = number of matches.
+// =========================================================================================
+struct ExtendArgs {
+    const u32* g0;
+    const u32* g1;
+    u64 npos0, npos1;
+    const u32* partner;
+    const u8* flags;
+    const u32* cand;
+    u64 ncand;
+    mcu_match* out;
+    unsigned long long* counters;
+};
+
+__device__ __forceinline__ bool probe_hit(const ExtendArgs& a, const SeedParams& sp, bool rev, i64 d, i64 t, i64& other)
+{
+    if (t < 0 || t >= (i64)a.npos0) return false;
+    other = rev ? d - t : t + d;
+    if (other < 0 || other >= (i64)a.npos1) return false;
+    u64 f0 = extract_seed(load_mer32(a.g0, (u64)t), sp);
+    u64 x1 = extract_seed(load_mer32(a.g1, (u64)other), sp);
+    if (!rev) return f0 == x1;
+    if (f0 != revcomp_seed(x1, sp.w)) return false;
+    return f0 != revcomp_seed(f0, sp.w);
+}
+
+__global__ void __launch_bounds__(256) extend_kernel(ExtendArgs a, SeedParams sp)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u64 warp_global = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const i64 L = sp.L;
+    for (u64 c = warp_global; c < a.ncand; c += nwarps) {
+        const i64 t0 = a.cand[c];
+        const bool rev = (a.flags[t0] >> 1) & 1;
+        const i64 p1 = a.partner[t0];
+        const i64 d = rev ? t0 + p1 : p1 - t0;
+        // ---- walk left ----
+        i64 cur = t0;
+        bool abandoned = false;
+        while (true) {
+            i64 t = cur - 1 - (i64)lane, other = 0;
+            bool h = (i64)lane < L && probe_hit(a, sp, rev, d, t, other);
+            bool uniq = h && (a.flags[t] & 1) && (i64)a.partner[t] == other;
+            if (__any_sync(0xffffffffu, uniq)) { abandoned = true; break; }
+            u32 hits = __ballot_sync(0xffffffffu, h);
+            if (!hits) break;
+            cur -= 32 - __clz(hits);  // farthest hit: highest lane = largest distance
+        }
+        if (abandoned) continue;
+        const i64 lo = cur;
+        // ---- walk right ----
+        cur = t0;
+        while (true) {
+            i64 t = cur + 1 + (i64)lane, other = 0;
+            bool h = (i64)lane < L && probe_hit(a, sp, rev, d, t, other);
+            u32 hits = __ballot_sync(0xffffffffu, h);
+            if (!hits) break;
+            cur += 32 - __clz(hits);
+        }
+        const i64 hi = cur;
+        if (lane == 0) {
+            u64 slot = atomicAdd(&a.counters[3], 1ull);
+            mcu_match m;
+            m.len = hi - lo + L;
+            m.start0 = lo + 1;
+            m.start1 = rev ? -((d - hi) + 1) : lo + d + 1;
+            a.out[slot] = m;
+        }
+    }
+}
+
+// =========================================================================================
+// order: MemHash::GetMatchList (LM/MemHash.h:183-203) walks buckets 0..39999
+// (bucket = generalized offset mod 40000, LM/MemHash.cpp:213, offset per
+// MatchHashEntry::CalculateOffset LM/MatchHashEntry.cpp:141-160); inside a bucket entries are
+// kept sorted by strict_start_lessthan_ptr (LM/MatchHashEntry.cpp:48-67; stored entries have
+// m_mersize == 0 because the copy goes through operator=, :112-120).
+// Two stable LSD sorts: secondary key (genome-1 start as compared there), then bucket|start0.
+// =========================================================================================
+__global__ void order_keys_kernel(const mcu_match* __restrict__ rows, u64 n, int s0_bits, u64* __restrict__ primary, u64* __restrict__ secondary,
+                                  u32* __restrict__ idx)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        mcu_match m = rows[i];
+        i64 off = m.start1 - m.start0 - (m.start1 < 0 ? m.len : 0);
+        i64 b = ((off % 40000) + 40000) % 40000;
+        u64 s1 = m.start1 < 0 ? (u64)(-m.start1 + m.len) : (u64)m.start1;
+        primary[i] = ((u64)b << s0_bits) | (u64)m.start0;
+        secondary[i] = (s1 << 1) | (m.start1 < 0 ? 1u : 0u);
+        idx[i] = (u32)i;
+    }
+}
+
+__global__ void gather_u64_kernel(const u64* __restrict__ src, const u32* __restrict__ idx, u64 n, u64* __restrict__ dst)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+
+__global__ void gather_rows_kernel(const mcu_match* __restrict__ src, const u32* __restrict__ idx, u64 n, mcu_match* __restrict__ dst)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+
+// =========================================================================================
+// host side
+// =========================================================================================
+static int grid_for(u64 n, int block, int per_sm)
+{
+    u64 want = div_up(n, (u64)block);
+    u64 cap = (u64)sm_count() * per_sm;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+static int bit_length(u64 x)
+{
+    int b = 0;
+    while (x) { ++b; x >>= 1; }
+    return b;
+}
+
+int session_init(Session& s)
+{
+    MCU_TRY(ensure_device());
+    MCU_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) MCU_CUDA(cudaEventCreate(&s.ev[i]));
+    MCU_CUDA(cudaHostAlloc((void**)&s.h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    MCU_TRY(s.counters.reserve(8 * sizeof(unsigned long long)));
+    s.ok = true;
+    return MCU_OK;
+}
+
+void session_destroy(Session& s)
+{
+    if (!s.ok) return;
+    cudaStreamSynchronize(s.stream);
+    DevBuf* bufs[] = {&s.ascii[0], &s.ascii[1], &s.packed[0], &s.packed[1], &s.keys_a, &s.keys_b, &s.vals_a, &s.vals_b,
+                      &s.partner, &s.flags, &s.cand, &s.raw_matches, &s.ord_keys_a, &s.ord_keys_b, &s.ord_vals_a, &s.ord_vals_b,
+                      &s.matches, &s.counters, &s.radix.hist, &s.radix.status, &s.radix.counters};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(s.ev[i]);
+    if (s.h_counters) cudaFreeHost(s.h_counters);
+    cudaStreamDestroy(s.stream);
+    s.ok = false;
+}
+
+int session_upload(Session& s, const char* seq0, u64 n0, const char* seq1, u64 n1)
+{
+    const char* seq[2] = {seq0, seq1};
+    u64 n[2] = {n0, n1};
+    for (int g = 0; g < 2; ++g) {
+        if (n[g] && !seq[g]) { set_error("session_upload: NULL sequence"); return MCU_EINVAL; }
+        if (n[g] >= 0xFFFFFFFFull) { set_error("sequence longer than the reference's 32-bit position limit"); return MCU_EINVAL; }
+        MCU_TRY(s.ascii[g].reserve(n[g] + 16));
+        if (n[g]) MCU_CUDA(cudaMemcpyAsync(s.ascii[g].p, seq[g], n[g], cudaMemcpyHostToDevice, s.stream));
+        s.n[g] = n[g];
+    }
+    MCU_CUDA(cudaStreamSynchronize(s.stream));
+    return MCU_OK;
+}
+
+static int run_pack(Session& s, int g, u32* err_flag)
+{
+    u64 words = div_up(s.n[g], 16) + 2;
+    MCU_TRY(s.packed[g].reserve(words * sizeof(u32)));
+    pack_kernel<<<grid_for(words, 256, 8), 256, 0, s.stream>>>(s.ascii[g].as<u8>(), s.n[g], s.packed[g].as<u32>(), words, err_flag);
+    s.launches++;
+    return MCU_OK;
+}
+
+template <typename K>
+static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int shard_count, float* stage_ms, u64* stats)
+{
+    const u64 npos0 = s.n[0] >= (u64)sp.L ? s.n[0] - sp.L + 1 : 0;
+    const u64 npos1 = s.n[1] >= (u64)sp.L ? s.n[1] - sp.L + 1 : 0;
+    const u64 ntot = npos0 + npos1;
+    const int key_bits = 2 * sp.w + 2;
+    const int passes = (key_bits + 7) / 8;
+    const bool sharded = shard_count > 1;
+    unsigned long long* ctr = s.counters.as<unsigned long long>();
+    // counters: [0] pairs [1] repeat flag [2] candidates [3] matches [4] gap error (u32) [5] shard element count
+    MCU_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), s.stream));
+    MCU_CUDA(cudaEventRecord(s.ev[0], s.stream));
+
+    // ---- pack ----
+    for (int g = 0; g < 2; ++g) MCU_TRY(run_pack(s, g, (u32*)(ctr + 4)));
+    MCU_CUDA(cudaEventRecord(s.ev[1], s.stream));
+
+    // ---- seedgen ----
+    MCU_TRY(s.keys_a.reserve((ntot + 1) * sizeof(K)));
+    MCU_TRY(s.keys_b.reserve((ntot + 1) * sizeof(K)));
+    MCU_TRY(s.vals_a.reserve((ntot + 1) * sizeof(u32)));
+    MCU_TRY(s.vals_b.reserve((ntot + 1) * sizeof(u32)));
+    MCU_TRY(radix_clear_hist(s.radix, s.stream));
+    u64 canon_lo = 0, canon_hi = ~0ull;
+    if (sharded) {
+        // equal slices of the canonical key space [0, 4^w)
+        const int kb = 2 * sp.w;
+        auto edge = [&](int i) -> u64 {
+            if (i >= shard_count) return kb >= 64 ? ~0ull : (1ull << kb);
+            unsigned __int128 span = kb >= 64 ? ((unsigned __int128)1 << 64) : ((unsigned __int128)1 << kb);
+            return (u64)(span * (unsigned)i / (unsigned)shard_count);
+        };
+        canon_lo = edge(shard_index);
+        canon_hi = edge(shard_index + 1);
+    }
+    const u64 npos[2] = {npos0, npos1};
+    u64 base = 0;
+    for (int g = 0; g < 2; ++g) {
+        if (npos[g]) {
+            seedgen_kernel<K><<<grid_for(npos[g], 256, 8), 256, passes * 256 * sizeof(u32), s.stream>>>(
+                s.packed[g].as<u32>(), npos[g], sp, (u32)g, s.keys_a.as<K>(), s.vals_a.as<u32>(), sharded ? 0 : base,
+                s.radix.hist.as<u64>(), passes, sharded ? 1 : 0, canon_lo, canon_hi, ctr + 5);
+            s.launches++;
+        }
+        base += npos[g];
+    }
+    u64 nsort = ntot;
+    if (sharded) {
+        MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        MCU_CUDA(cudaStreamSynchronize(s.stream));
+        nsort = s.h_counters[5];
+    }
+    MCU_CUDA(cudaEventRecord(s.ev[2], s.stream));
+
+    // ---- sort ----
+    bool in_a = true;
+    int passes_run = 0;
+    u64 before = s.radix.launches;
+    MCU_TRY(radix_sort_pairs<K>(s.radix, s.keys_a.as<K>(), s.vals_a.as<u32>(), s.keys_b.as<K>(), s.vals_b.as<u32>(), nsort, key_bits, true,
+                                s.stream, &in_a, &passes_run));
+    s.launches += s.radix.launches - before;
+    const K* skeys = in_a ? s.keys_a.as<K>() : s.keys_b.as<K>();
+    const u32* svals = in_a ? s.vals_a.as<u32>() : s.vals_b.as<u32>();
+    MCU_CUDA(cudaEventRecord(s.ev[3], s.stream));
+
+    // ---- join ----
+    MCU_TRY(s.partner.reserve((npos0 + 1) * sizeof(u32)));
+    MCU_TRY(s.flags.reserve(npos0 + 16));
+    MCU_CUDA(cudaMemsetAsync(s.flags.p, 0, npos0 + 16, s.stream));
+    if (nsort) {
+        join_kernel<K><<<grid_for(nsort, 256, 8), 256, 0, s.stream>>>(skeys, svals, nsort, s.partner.as<u32>(), s.flags.as<u8>(), ctr);
+        s.launches++;
+    }
+    MCU_CUDA(cudaEventRecord(s.ev[4], s.stream));
+
+    // ---- candidates + extend ----
+    MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+    MCU_CUDA(cudaStreamSynchronize(s.stream));
+    if (((u32*)(s.h_counters + 4))[0]) { set_error("gap character '-' in a genome sequence (input must be unaligned)"); return MCU_EGAP; }
+    const u64 npairs = s.h_counters[0];
+    const u64 repeat_flag = s.h_counters[1];
+    u64 ncand = 0, nmatch = 0;
+    if (npairs) {
+        MCU_TRY(s.cand.reserve(npairs * sizeof(u32)));
+        candidate_kernel<<<grid_for(npos0, 256, 8), 256, 0, s.stream>>>(s.partner.as<u32>(), s.flags.as<u8>(), npos0, s.cand.as<u32>(), ctr);
+        s.launches++;
+        MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        MCU_CUDA(cudaStreamSynchronize(s.stream));
+        ncand = s.h_counters[2];
+        MCU_TRY(s.raw_matches.reserve(ncand * sizeof(mcu_match)));
+        ExtendArgs ea;
+        ea.g0 = s.packed[0].as<u32>(); ea.g1 = s.packed[1].as<u32>();
+        ea.npos0 = npos0; ea.npos1 = npos1;
+        ea.partner = s.partner.as<u32>(); ea.flags = s.flags.as<u8>();
+        ea.cand = s.cand.as<u32>(); ea.ncand = ncand;
+        ea.out = s.raw_matches.as<mcu_match>(); ea.counters = ctr;
+        extend_kernel<<<grid_for(ncand * 32, 256, 8), 256, 0, s.stream>>>(ea, sp);
+        s.launches++;
+        MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        MCU_CUDA(cudaStreamSynchronize(s.stream));
+        nmatch = s.h_counters[3];
+    }
+    MCU_CUDA(cudaEventRecord(s.ev[5], s.stream));
+
+    // ---- order ----
+    MCU_TRY(order_matches(s, s.raw_matches.as<mcu_match>(), nmatch));
+    MCU_CUDA(cudaEventRecord(s.ev[6], s.stream));
+    MCU_CUDA(cudaStreamSynchronize(s.stream));
+    MCU_CUDA(cudaGetLastError());
+
+    if (stage_ms) {
+        for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&stage_ms[i], s.ev[i], s.ev[i + 1]);
+        cudaEventElapsedTime(&stage_ms[6], s.ev[0], s.ev[6]);
+        stage_ms[7] = (float)passes_run;
+    }
+    if (stats) {
+        stats[0] = npairs; stats[1] = nmatch; stats[2] = npairs - nmatch; stats[3] = repeat_flag;
+        stats[4] = ncand; stats[5] = nsort; stats[6] = 0; stats[7] = 0;
+    }
+    return MCU_OK;
+}
+
+int order_matches(Session& s, const mcu_match* rows_dev, u64 n)
+{
+    s.match_count = n;
+    MCU_TRY(s.matches.reserve((n + 1) * sizeof(mcu_match)));
+    if (n == 0) return MCU_OK;
+    if (n >= 0xFFFFFFFFull) { set_error("too many matches"); return MCU_EINVAL; }
+    MCU_TRY(s.ord_keys_a.reserve(n * sizeof(u64)));
+    MCU_TRY(s.ord_keys_b.reserve(n * sizeof(u64)));
+    MCU_TRY(s.ord_vals_a.reserve(n * sizeof(u32)));
+    MCU_TRY(s.ord_vals_b.reserve(n * sizeof(u32)));
+    MCU_TRY(s.cand.reserve(n * sizeof(u64)));  // reuse as the primary-key stash
+    u64* primary = s.cand.as<u64>();
+    u64* sec = s.ord_keys_a.as<u64>();
+    const int s0_bits = 33, s1_bits = 36;  // starts < 2^32 (+ length), sign bit
+    const int g = grid_for(n, 256, 8);
+    order_keys_kernel<<<g, 256, 0, s.stream>>>(rows_dev, n, s0_bits, primary, sec, s.ord_vals_a.as<u32>());
+    s.launches++;
+    bool in_a = true;
+    u64 before = s.radix.launches;
+    MCU_TRY(radix_sort_pairs<u64>(s.radix, s.ord_keys_a.as<u64>(), s.ord_vals_a.as<u32>(), s.ord_keys_b.as<u64>(), s.ord_vals_b.as<u32>(), n,
+                                  s1_bits, false, s.stream, &in_a, nullptr));
+    u32* idx1 = in_a ? s.ord_vals_a.as<u32>() : s.ord_vals_b.as<u32>();
+    u32* idx_other = in_a ? s.ord_vals_b.as<u32>() : s.ord_vals_a.as<u32>();
+    // gather primary keys in secondary order, then sort on them (stable)
+    u64* pk = s.ord_keys_a.as<u64>();
+    u64* pk_other = s.ord_keys_b.as<u64>();
+    gather_u64_kernel<<<g, 256, 0, s.stream>>>(primary, idx1, n, pk);
+    s.launches++;
+    MCU_TRY(radix_sort_pairs<u64>(s.radix, pk, idx1, pk_other, idx_other, n, s0_bits + 16, false, s.stream, &in_a, nullptr));
+    s.launches += s.radix.launches - before;
+    const u32* idx_final = in_a ? idx1 : idx_other;
+    gather_rows_kernel<<<g, 256, 0, s.stream>>>(rows_dev, idx_final, n, s.matches.as<mcu_match>());
+    s.launches++;
+    MCU_CUDA(cudaGetLastError());
+    return MCU_OK;
+}
+
+int session_run(Session& s, u64 seed, int shard_index, int shard_count, float* stage_ms, u64* stats)
+{
+    SeedParams sp;
+    MCU_TRY(make_seed_params(seed, &sp));
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) { set_error("bad shard spec"); return MCU_EINVAL; }
+    if (2 * sp.w + 2 <= 32) return run_pipeline<u32>(s, sp, shard_index, shard_count, stage_ms, stats);
+    return run_pipeline<u64>(s, sp, shard_index, shard_count, stage_ms, stats);
+}
+
+// ---- single-genome SML --------------------------------------------------------------------
+template <typename K>
+static int sml_build_t(Session& s, const SeedParams& sp, u32* pos_out, u64* mer_out, u32* packed_out, u64* len_out)
+{
+    const u64 n = s.n[0];
+    const u64 npos = n >= (u64)sp.L ? n - sp.L + 1 : 0;
+    const int key_bits = 2 * sp.w + 2;
+    const int passes = (key_bits + 7) / 8;
+    unsigned long long* ctr = s.counters.as<unsigned long long>();
+    MCU_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), s.stream));
+    MCU_TRY(run_pack(s, 0, (u32*)(ctr + 4)));
+    MCU_TRY(s.keys_a.reserve((npos + 1) * sizeof(u64)));  // u64-sized: the mer conversion reuses keys_b
+    MCU_TRY(s.keys_b.reserve((npos + 1) * sizeof(u64)));
+    MCU_TRY(s.vals_a.reserve((npos + 1) * sizeof(u32)));
+    MCU_TRY(s.vals_b.reserve((npos + 1) * sizeof(u32)));
+    MCU_TRY(radix_clear_hist(s.radix, s.stream));
+    bool in_a = true;
+    if (npos) {
+        seedgen_kernel<K><<<grid_for(npos, 256, 8), 256, passes * 256 * sizeof(u32), s.stream>>>(
+            s.packed[0].as<u32>(), npos, sp, 0u, s.keys_a.as<K>(), s.vals_a.as<u32>(), 0, s.radix.hist.as<u64>(), passes, 0, 0, ~0ull, ctr + 5);
+        s.launches++;
+        u64 before = s.radix.launches;
+        MCU_TRY(radix_sort_pairs<K>(s.radix, s.keys_a.as<K>(), s.vals_a.as<u32>(), s.keys_b.as<K>(), s.vals_b.as<u32>(), npos, key_bits, true,
+                                    s.stream, &in_a, nullptr));
+        s.launches += s.radix.launches - before;
+    }
+    MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+    MCU_CUDA(cudaStreamSynchronize(s.stream));
+    if (((u32*)(s.h_counters + 4))[0]) { set_error("gap character '-' in a genome sequence (input must be unaligned)"); return MCU_EGAP; }
+    const K* skeys = in_a ? s.keys_a.as<K>() : s.keys_b.as<K>();
+    const u32* svals = in_a ? s.vals_a.as<u32>() : s.vals_b.as<u32>();
+    if (pos_out && npos) MCU_CUDA(cudaMemcpyAsync(pos_out, svals, npos * sizeof(u32), cudaMemcpyDeviceToHost, s.stream));
+    if (mer_out && npos) {
+        u64* mers = in_a ? s.keys_b.as<u64>() : s.keys_a.as<u64>();  // the buffer not holding the result
+        keys_to_mers_kernel<K><<<grid_for(npos, 256, 8), 256, 0, s.stream>>>(skeys, npos, sp.w, mers);
+        s.launches++;
+        MCU_CUDA(cudaMemcpyAsync(mer_out, mers, npos * sizeof(u64), cudaMemcpyDeviceToHost, s.stream));
+    }
+    if (packed_out) MCU_CUDA(cudaMemcpyAsync(packed_out, s.packed[0].p, (div_up(n, 16) + 2) * sizeof(u32), cudaMemcpyDeviceToHost, s.stream));
+    MCU_CUDA(cudaStreamSynchronize(s.stream));
+    MCU_CUDA(cudaGetLastError());
+    if (len_out) *len_out = npos;
+    return MCU_OK;
+}
+
+int sml_build_device(Session& s, const char* seq, u64 n, u64 seed, u32* pos_out, u64* mer_out, u32* packed_out, u64* len_out)
+{
+    SeedParams sp;
+    MCU_TRY(make_seed_params(seed, &sp));
+    MCU_TRY(session_upload(s, seq, n, nullptr, 0));
+    if (2 * sp.w + 2 <= 32) return sml_build_t<u32>(s, sp, pos_out, mer_out, packed_out, len_out);
+    return sml_build_t<u64>(s, sp, pos_out, mer_out, packed_out, len_out);
+}
+
+}  // namespace mcu

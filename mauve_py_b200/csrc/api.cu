@@ -1,0 +1,371 @@
+// C ABI of libmauve_cuda.so (include/mauve_cuda.h): argument checking, device selection,
+// the process-wide default session, seed-pattern tables.  No compute happens on the host.
+#include <stdarg.h>
+#include <math.h>
+#include <mutex>
+#include <new>
+
+#include "anchor.cuh"
+#include "dp.cuh"
+#include "hmm.cuh"
+
+namespace mcu {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+static int g_device = -1;
+static int g_sms = 0;
+static std::mutex g_mu;
+
+int ensure_device()
+{
+    if (g_device >= 0) {
+        cudaError_t e = cudaSetDevice(g_device);
+        if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", g_device, cudaGetErrorString(e)); return MCU_ENODEV; }
+        return MCU_OK;
+    }
+    return mcu_init(0);
+}
+int sm_count() { return g_sms > 0 ? g_sms : 148; }
+
+// ---- seed patterns (LM/SeedMasks.h:44-260; low 32 bits, the high words are all zero) ----------
+// Quirks kept: weight-11 rank-0 entry equals the weight-12 one; weight-21 rank-1 is 0xaeb3f.
+static const u32 SEED_TABLE[32][6] = {
+    {0}, {0}, {0},
+    {0xb}, {0x3b},
+    {0x6b, 0x139, 0x193, 0x6b},
+    {0x58D, 0x653, 0x1AB, 0xdb},
+    {0x1953, 0x588d, 0x688b, 0x17d, 0x164d},
+    {0x3927, 0x1CA7, 0x6553, 0xb6d},
+    {0x7497, 0x1c927, 0x72a7, 0x6fb, 0x16ed},
+    {0x1d297, 0x3A497, 0xE997, 0x6D5B},
+    {0x7954f, 0x75257, 0x1c9527, 0x5bed, 0x5b26d},
+    {0x7954f, 0x3D32F, 0x768B7, 0x5B56D},
+    {0x792a4f, 0x1d64d7, 0x1d3597, 0x1b7db, 0x75ad7},
+    {0x1e6acf, 0xF59AF, 0x3D4CAF, 0x35AD6B},
+    {0x7ac9af, 0x7b2a6f, 0x79aacf, 0x16df6d, 0x6b5d6b},
+    {0xf599af, 0xEE5A77, 0x7CD59F, 0xEB5AD7},
+    {0x6dbedb},
+    {0x3E6B59F, 0x3EB335F, 0x7B3566F},
+    {0x7b974ef, 0x7d6735f, 0x1edd74f},
+    {0x1F59B35F, 0x3EDCEDF, 0xFAE675F},
+    {0x7ddaddf, 0xaeb3f, 0x7eb76bf},
+    {0x003fffff}, {0x007fffff}, {0x00ffffff}, {0x01ffffff}, {0x03ffffff},
+    {0x07ffffff}, {0x0fffffff}, {0x1fffffff}, {0x3fffffff}, {0x7fffffff}};
+
+int make_seed_params(u64 seed, SeedParams* out)
+{
+    SeedParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.seed = seed;
+    sp.L = mcu_seed_length(seed);
+    sp.w = mcu_seed_weight(seed);
+    // GetSeedMer scans the pattern from bit L-1 down to bit 0 (LM/SortedMerList.cpp:737-757) and
+    // GetMer holds at most 32 bases; a pattern with trailing zeros or L > 31 is not a valid DNA seed.
+    if (seed == 0 || !(seed & 1) || sp.L > 31 || sp.w < 1) {
+        set_error("unusable seed pattern 0x%llx (length %d, weight %d)", (unsigned long long)seed, sp.L, sp.w);
+        return MCU_EINVAL;
+    }
+    int j = 0, cum = 0;
+    while (j < sp.L) {
+        if (!((seed >> (sp.L - 1 - j)) & 1)) { ++j; continue; }
+        int len = 0;
+        while (j + len < sp.L && ((seed >> (sp.L - 1 - (j + len))) & 1)) ++len;
+        if (sp.nruns >= MCU_MAX_RUNS) { set_error("seed pattern has too many runs"); return MCU_EINVAL; }
+        sp.shift_in[sp.nruns] = (u8)(2 * (sp.L - j - len));
+        sp.shift_out[sp.nruns] = (u8)(2 * (sp.w - cum - len));
+        sp.mask[sp.nruns] = len >= 32 ? ~0ull : ((1ull << (2 * len)) - 1);
+        ++sp.nruns;
+        cum += len;
+        j += len;
+    }
+    u64 rev = 0;
+    for (int b = 0; b < sp.L; ++b) rev |= ((seed >> b) & 1) << (sp.L - 1 - b);
+    sp.palindromic = rev == seed;
+    *out = sp;
+    return MCU_OK;
+}
+
+static Session* g_default_session = nullptr;
+
+static int default_session(Session** out)
+{
+    if (!g_default_session) {
+        Session* s = new (std::nothrow) Session();
+        if (!s) return MCU_ENOMEM;
+        int r = session_init(*s);
+        if (r != MCU_OK) { delete s; return r; }
+        g_default_session = s;
+    }
+    *out = g_default_session;
+    return MCU_OK;
+}
+
+}  // namespace mcu
+
+using namespace mcu;
+
+extern "C" {
+
+int mcu_init(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no usable CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return MCU_ENODEV;
+    }
+    if (device < 0 || device >= count) { set_error("device %d out of range (0..%d)", device, count - 1); return MCU_EINVAL; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e)); return MCU_ENODEV; }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return MCU_ENODEV; }
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+        return MCU_ENODEV;
+    }
+    g_device = device;
+    g_sms = prop.multiProcessorCount;
+    return MCU_OK;
+}
+
+void mcu_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_default_session) {
+        session_destroy(*g_default_session);
+        delete g_default_session;
+        g_default_session = nullptr;
+    }
+}
+
+const char* mcu_last_error(void) { return get_error(); }
+void mcu_free(void* p) { free(p); }
+
+int mcu_host_alloc(void** out, uint64_t bytes)
+{
+    MCU_TRY(ensure_device());
+    MCU_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return MCU_OK;
+}
+void mcu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- seeds ------------------------------------------------------------------------------
+uint64_t mcu_get_seed(int weight, int rank)
+{
+    auto solid = [](int w) -> u64 { return w >= 64 ? ~0ull : ((1ull << w) - 1); };
+    if (rank == MCU_SOLID_SEED) return solid(weight);
+    if (weight > 31) return solid(32);
+    if (rank > 5) return solid(weight);
+    if (weight < 0 || rank < 0) return 0;
+    if (SEED_TABLE[weight][rank] == 0) return solid(weight);
+    return SEED_TABLE[weight][rank];
+}
+
+unsigned mcu_default_seed_weight(uint64_t avg_len)
+{
+    unsigned w = (unsigned)ceil((log((double)avg_len) / log(2.0)) / 1.5);
+    if (!(w & 1)) ++w;
+    if (w < 5) w = 0;
+    if (avg_len == 0) w = 0;
+    if (w > 31) w = 31;
+    return w;
+}
+
+int mcu_seed_length(uint64_t seed)
+{
+    if (!seed) return 0;
+    int hi = 63 - __builtin_clzll(seed), lo = __builtin_ctzll(seed);
+    return hi - lo + 1;
+}
+
+int mcu_seed_weight(uint64_t seed) { return __builtin_popcountll(seed); }
+
+// ---- SML --------------------------------------------------------------------------------
+int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out, uint64_t* mer_out, uint32_t* packed_out,
+                  uint64_t* sml_len_out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    if (n && !seq) { set_error("mcu_sml_build: NULL sequence"); return MCU_EINVAL; }
+    Session* s;
+    MCU_TRY(default_session(&s));
+    return sml_build_device(*s, seq, n, seed, pos_out, mer_out, packed_out, sml_len_out);
+}
+
+// ---- MUMs -------------------------------------------------------------------------------
+int mcu_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule, mcu_match** out,
+                  uint64_t* n_out, uint64_t* stats)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    if (!out || !n_out) { set_error("mcu_find_mums: NULL output pointer"); return MCU_EINVAL; }
+    if (rule != MCU_RULE_PAIRWISE && rule != MCU_RULE_MEMHASH) { set_error("mcu_find_mums: unknown rule %d", rule); return MCU_EINVAL; }
+    Session* s;
+    MCU_TRY(default_session(&s));
+    MCU_TRY(session_upload(*s, seq0, n0, seq1, n1));
+    MCU_TRY(session_run(*s, seed, 0, 1, nullptr, stats));
+    u64 m = s->match_count;
+    mcu_match* r = (mcu_match*)malloc((m ? m : 1) * sizeof(mcu_match));
+    if (!r) { set_error("out of host memory"); return MCU_ENOMEM; }
+    if (m) {
+        MCU_CUDA(cudaMemcpyAsync(r, s->matches.p, m * sizeof(mcu_match), cudaMemcpyDeviceToHost, s->stream));
+        MCU_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    *out = r;
+    *n_out = m;
+    return MCU_OK;
+}
+
+// ---- sessions ---------------------------------------------------------------------------
+struct mcu_session { Session s; };
+
+int mcu_session_create(mcu_session** out)
+{
+    MCU_TRY(ensure_device());
+    if (!out) return MCU_EINVAL;
+    mcu_session* h = new (std::nothrow) mcu_session();
+    if (!h) return MCU_ENOMEM;
+    int r = session_init(h->s);
+    if (r != MCU_OK) { delete h; return r; }
+    *out = h;
+    return MCU_OK;
+}
+
+void mcu_session_destroy(mcu_session* h)
+{
+    if (!h) return;
+    session_destroy(h->s);
+    delete h;
+}
+
+int mcu_session_upload(mcu_session* h, const char* seq0, uint64_t n0, const char* seq1, uint64_t n1)
+{
+    if (!h) return MCU_EINVAL;
+    MCU_TRY(ensure_device());
+    return session_upload(h->s, seq0, n0, seq1, n1);
+}
+
+int mcu_session_run(mcu_session* h, uint64_t seed, int shard_index, int shard_count, float* stage_ms, uint64_t* stats)
+{
+    if (!h) return MCU_EINVAL;
+    MCU_TRY(ensure_device());
+    return session_run(h->s, seed, shard_index, shard_count, stage_ms, stats);
+}
+
+uint64_t mcu_session_match_count(const mcu_session* h) { return h ? h->s.match_count : 0; }
+
+int mcu_session_download(mcu_session* h, mcu_match* out)
+{
+    if (!h) return MCU_EINVAL;
+    if (h->s.match_count == 0) return MCU_OK;
+    if (!out) return MCU_EINVAL;
+    MCU_CUDA(cudaMemcpyAsync(out, h->s.matches.p, h->s.match_count * sizeof(mcu_match), cudaMemcpyDeviceToHost, h->s.stream));
+    MCU_CUDA(cudaStreamSynchronize(h->s.stream));
+    return MCU_OK;
+}
+
+const void* mcu_session_matches_device(const mcu_session* h) { return h ? h->s.matches.p : nullptr; }
+uint64_t mcu_session_launch_count(const mcu_session* h) { return h ? h->s.launches : 0; }
+
+int mcu_merge_matches(const mcu_match* rows, uint64_t n, int in_device, mcu_match** out, uint64_t* n_out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    if (!out || !n_out || (n && !rows)) { set_error("mcu_merge_matches: NULL pointer"); return MCU_EINVAL; }
+    Session* s;
+    MCU_TRY(default_session(&s));
+    const mcu_match* dev_rows = rows;
+    if (!in_device && n) {
+        MCU_TRY(s->raw_matches.reserve(n * sizeof(mcu_match)));
+        MCU_CUDA(cudaMemcpyAsync(s->raw_matches.p, rows, n * sizeof(mcu_match), cudaMemcpyHostToDevice, s->stream));
+        dev_rows = s->raw_matches.as<mcu_match>();
+    }
+    MCU_TRY(order_matches(*s, dev_rows, n));
+    mcu_match* r = (mcu_match*)malloc((n ? n : 1) * sizeof(mcu_match));
+    if (!r) { set_error("out of host memory"); return MCU_ENOMEM; }
+    if (n) {
+        MCU_CUDA(cudaMemcpyAsync(r, s->matches.p, n * sizeof(mcu_match), cudaMemcpyDeviceToHost, s->stream));
+        MCU_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    // shards rediscover the same maximal match from their own seeds: equal rows are adjacent now
+    u64 k = 0;
+    for (u64 i = 0; i < n; ++i)
+        if (k == 0 || r[i].len != r[k - 1].len || r[i].start0 != r[k - 1].start0 || r[i].start1 != r[k - 1].start1) r[k++] = r[i];
+    *out = r;
+    *n_out = k;
+    return MCU_OK;
+}
+
+// ---- DP / HMM ---------------------------------------------------------------------------
+int mcu_nw_batch(uint64_t n, const char* a, const uint64_t* a_off, const char* b, const uint64_t* b_off, const uint64_t* path_off,
+                 char* path_out, uint32_t* path_len, int64_t* score, float* device_ms)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    return nw_batch(n, a, a_off, b, b_off, path_off, path_out, path_len, score, device_ms);
+}
+
+void mcu_nw_last_stats(uint64_t* out5)
+{
+    if (out5) nw_last_stats(out5);
+}
+
+int mcu_hmm_params(double gc, double go_homologous, double go_unrelated, double pct_identity, double* out)
+{
+    if (!out) return MCU_EINVAL;
+    return hmm_params(gc, go_homologous, go_unrelated, pct_identity, out);
+}
+
+int mcu_hmm_batch(uint64_t n, const char* sym, const uint64_t* off, const double* params, char* pred_out, double* post_out,
+                  float* device_ms)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    return hmm_batch(n, sym, off, params, pred_out, post_out, device_ms);
+}
+
+// ---- test hooks -------------------------------------------------------------------------
+int mcu_test_sort_pairs(void* keys, uint32_t* vals, uint64_t n, int key_bytes, int bits)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    if (key_bytes != 4 && key_bytes != 8) return MCU_EINVAL;
+    Session* s;
+    MCU_TRY(default_session(&s));
+    size_t kb = (size_t)key_bytes;
+    MCU_TRY(s->keys_a.reserve((n + 1) * kb));
+    MCU_TRY(s->keys_b.reserve((n + 1) * kb));
+    MCU_TRY(s->vals_a.reserve((n + 1) * 4));
+    MCU_TRY(s->vals_b.reserve((n + 1) * 4));
+    if (n) {
+        MCU_CUDA(cudaMemcpyAsync(s->keys_a.p, keys, n * kb, cudaMemcpyHostToDevice, s->stream));
+        MCU_CUDA(cudaMemcpyAsync(s->vals_a.p, vals, n * 4, cudaMemcpyHostToDevice, s->stream));
+    }
+    bool in_a = true;
+    if (key_bytes == 4)
+        MCU_TRY(radix_sort_pairs<u32>(s->radix, s->keys_a.as<u32>(), s->vals_a.as<u32>(), s->keys_b.as<u32>(), s->vals_b.as<u32>(), n, bits,
+                                      false, s->stream, &in_a, nullptr));
+    else
+        MCU_TRY(radix_sort_pairs<u64>(s->radix, s->keys_a.as<u64>(), s->vals_a.as<u32>(), s->keys_b.as<u64>(), s->vals_b.as<u32>(), n, bits,
+                                      false, s->stream, &in_a, nullptr));
+    if (n) {
+        MCU_CUDA(cudaMemcpyAsync(keys, in_a ? s->keys_a.p : s->keys_b.p, n * kb, cudaMemcpyDeviceToHost, s->stream));
+        MCU_CUDA(cudaMemcpyAsync(vals, in_a ? s->vals_a.p : s->vals_b.p, n * 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    MCU_CUDA(cudaStreamSynchronize(s->stream));
+    MCU_CUDA(cudaGetLastError());
+    return MCU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,463 @@
+"""Host-side mirror of the libMems / libMUSCLE / HomologyHMM interfaces of the anchoring path.
+
+Same names, argument meaning and error behaviour as the reference classes the path's callers use
+(SURVEY.md 8b), so that parity tests read like the reference's own call sites:
+
+    sml = DNAMemorySML(); sml.Create(seq, getSeed(15, CODING_SEED))          LM/MemorySML.cpp:45
+    ml = MatchList(); ml.seq_table = [a, b]; ml.CreateMemorySMLs(0, CODING_SEED)   LM/MatchList.h:431
+    PairwiseMatchFinder().FindMatches(ml)                                     LM/MemHash.cpp:109
+    paths = GlobalAlignBatch(pairs)                                           MU/glbalign.cpp:69
+    pred = run(symbols, params)                                               LM/HomologyHMM/homologymain.cc:24
+
+Every method that computes goes through the C ABI of libmauve_cuda.so (include/mauve_cuda.h);
+this module holds containers and argument marshalling only.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List
+
+import numpy as np
+
+from . import _capi
+from ._capi import CODING_SEED, SOLID_SEED, McuError, check, lib
+
+__all__ = [
+    "CODING_SEED", "SOLID_SEED", "McuError", "getSeed", "getSolidSeed", "getDefaultSeedWeight", "getSeedLength", "getSeedWeight",
+    "bmer", "DNAMemorySML", "Match", "MatchList", "MemHash", "PairwiseMatchFinder", "AnchorSession", "merge_matches",
+    "PWPath", "GlobalAlign", "GlobalAlignBatch", "Params", "getAdaptedHoxdMatrixParameters", "adaptToPercentIdentity",
+    "run", "run_batch", "sort_pairs",
+]
+
+
+def _buf(x):
+    """bytes / bytearray / numpy uint8 -> (address, length, keepalive)"""
+    if isinstance(x, (bytes, bytearray)):
+        arr = np.frombuffer(x, dtype=np.uint8)
+    else:
+        arr = np.ascontiguousarray(x, dtype=np.uint8)
+    return arr.ctypes.data, arr.size, arr
+
+
+# ---- LM/SeedMasks.h ---------------------------------------------------------------------------
+def getSeed(weight: int, seed_rank: int = 0) -> int:
+    return int(lib().mcu_get_seed(weight, seed_rank))
+
+
+def getSolidSeed(weight: int) -> int:
+    return int(lib().mcu_get_seed(weight, SOLID_SEED))
+
+
+def getDefaultSeedWeight(avg_sequence_length: int) -> int:
+    return int(lib().mcu_default_seed_weight(int(avg_sequence_length)))
+
+
+def getSeedLength(seed: int) -> int:
+    return int(lib().mcu_seed_length(seed))
+
+
+def getSeedWeight(seed: int) -> int:
+    return int(lib().mcu_seed_weight(seed))
+
+
+# ---- LM/SortedMerList.h, LM/MemorySML.h, LM/DNAMemorySML.h ---------------------------------------
+@dataclass
+class bmer:
+    position: int
+    mer: int
+
+
+class DNAMemorySML:
+    """mems::DNAMemorySML: the sorted mer list of one genome, built on the GPU."""
+
+    def __init__(self):
+        self.Clear()
+
+    def Clear(self):
+        self._pos = np.zeros(0, dtype=np.uint32)
+        self._mer = np.zeros(0, dtype=np.uint64)
+        self._packed = np.zeros(0, dtype=np.uint32)
+        self._seed = 0
+        self._length = 0
+
+    def Create(self, seq, seed: int):
+        """SortedMerList::Create + FillDnaSeedSML + sort (LM/MemorySML.cpp:45-60)."""
+        addr, n, keep = _buf(seq)
+        L = getSeedLength(seed)
+        m = max(n - L + 1, 0) if L else 0
+        pos = np.empty(max(m, 1), dtype=np.uint32)
+        mer = np.empty(max(m, 1), dtype=np.uint64)
+        packed = np.empty((2 * n) // 32 + (1 if (2 * n) % 32 else 0) + 2, dtype=np.uint32)
+        out_len = C.c_uint64(0)
+        check(lib().mcu_sml_build(addr, n, seed, pos.ctypes.data, mer.ctypes.data, packed.ctypes.data, C.byref(out_len)))
+        k = out_len.value
+        self._pos, self._mer, self._packed = pos[:k], mer[:k], packed
+        self._seed, self._length = seed, n
+
+    def Length(self):
+        return self._length
+
+    def SMLLength(self):
+        return int(self._pos.size)
+
+    def Seed(self):
+        return self._seed
+
+    def SeedLength(self):
+        return getSeedLength(self._seed)
+
+    def SeedWeight(self):
+        return getSeedWeight(self._seed)
+
+    def GetSeedMask(self):
+        w = self.SeedWeight()
+        return ((1 << 64) - 1) ^ ((1 << (64 - 2 * w)) - 1) if w else 0
+
+    def Read(self, size: int, offset: int):
+        """MemorySML::Read (LM/MemorySML.cpp:62-82): (positions, mers) of ranks [offset, offset+size)."""
+        end = min(offset + size, self.SMLLength())
+        return self._pos[offset:end], self._mer[offset:end]
+
+    def __getitem__(self, index: int) -> bmer:
+        return bmer(int(self._pos[index]), int(self._mer[index]))
+
+    def positions(self):
+        return self._pos
+
+    def mers(self):
+        return self._mer
+
+    def packed_sequence(self):
+        """SortedMerList::sequence: 2-bit packed, MSB first, two zero pad words."""
+        return self._packed
+
+    def FindMer(self, query_mer: int):
+        """SortedMerList::FindMer (LM/SortedMerList.cpp:170-179): binary search on mer & seed mask."""
+        mask = np.uint64(self.GetSeedMask())
+        keys = self._mer & mask
+        q = np.uint64(query_mer) & mask
+        i = int(np.searchsorted(keys, q, side="left"))
+        return (i < keys.size and keys[i] == q), i
+
+
+# ---- LM/Match.h, LM/MatchList.h -----------------------------------------------------------------
+@dataclass
+class Match:
+    """Ungapped match of two genomes: 1-based starts, negative start = reverse strand."""
+    length: int
+    starts: List[int]
+
+    def Length(self):
+        return self.length
+
+    def Start(self, seq: int):
+        return self.starts[seq]
+
+    def Orientation(self, seq: int):
+        return 0 if self.starts[seq] == 0 else (1 if self.starts[seq] > 0 else -1)
+
+
+@dataclass
+class MatchList:
+    seq_table: list = field(default_factory=list)
+    sml_table: list = field(default_factory=list)
+    matches: List[Match] = field(default_factory=list)
+
+    def CreateMemorySMLs(self, mer_size: int = 0, seed_rank: int = 0):
+        """LM/MatchList.h:431-461: default weight from the average length, one DNAMemorySML per genome."""
+        if mer_size == 0:
+            avg = sum(len(s) for s in self.seq_table) // max(len(self.seq_table), 1)
+            mer_size = getDefaultSeedWeight(avg)
+        seed = getSeed(mer_size, seed_rank)
+        self.sml_table = []
+        for s in self.seq_table:
+            sml = DNAMemorySML()
+            sml.Create(s, seed)
+            self.sml_table.append(sml)
+
+    def __len__(self):
+        return len(self.matches)
+
+    def __getitem__(self, i):
+        return self.matches[i]
+
+    def as_array(self):
+        """rows (length, start0, start1) in list order -- the three leading columns of WriteList (LM/MatchList.h:617-662)"""
+        return np.array([[m.length, m.starts[0], m.starts[1]] for m in self.matches], dtype=np.int64).reshape(-1, 3)
+
+
+def _find_mums(seq0, seq1, seed, rule):
+    a0, n0, k0 = _buf(seq0)
+    a1, n1, k1 = _buf(seq1)
+    out = C.POINTER(_capi.Match)()
+    n_out = C.c_uint64(0)
+    stats = np.zeros(8, dtype=np.uint64)
+    check(lib().mcu_find_mums(a0, n0, a1, n1, seed, rule, C.byref(out), C.byref(n_out), stats.ctypes.data))
+    n = n_out.value
+    if n:
+        rows = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_int64)), shape=(n, 3)).copy()
+    else:
+        rows = np.zeros((0, 3), dtype=np.int64)
+    lib().mcu_free(out)
+    return rows, stats
+
+
+class MemHash:
+    """mems::MemHash for two genomes (repeat_tolerance 0, enumeration_tolerance 1: LM/MemHash.cpp:139-162)."""
+    _rule = _capi.RULE_MEMHASH
+
+    def __init__(self):
+        self.Clear()
+
+    def Clear(self):
+        self.m_mem_count = 0
+        self.m_collision_count = 0
+        self.last_stats = np.zeros(8, dtype=np.uint64)
+        self._rows = np.zeros((0, 3), dtype=np.int64)
+
+    def MemCount(self):
+        return self.m_mem_count
+
+    def MemCollisionCount(self):
+        return self.m_collision_count
+
+    def FindMatches(self, ml: MatchList):
+        """MemHash::FindMatches(MatchList&) (LM/MemHash.cpp:109-127): reads ml.seq_table / ml.sml_table, appends into ml."""
+        if len(ml.seq_table) != 2:
+            raise McuError(_capi.MCU_EINVAL, "the CUDA match finder handles exactly two genomes (PairwiseMatchFinder / gap_mh case)")
+        if len(ml.sml_table) != 2:
+            raise McuError(_capi.MCU_EINVAL, "MatchList has no sorted mer lists (call CreateMemorySMLs first)")
+        seed = ml.sml_table[0].Seed()
+        if ml.sml_table[1].Seed() != seed:
+            raise McuError(_capi.MCU_EINVAL, "sorted mer lists were built with different seed patterns")
+        rows, stats = _find_mums(ml.seq_table[0], ml.seq_table[1], seed, self._rule)
+        self._rows, self.last_stats = rows, stats
+        self.m_mem_count = int(stats[1])
+        self.m_collision_count = int(stats[2])
+        ml.matches.extend(Match(int(r[0]), [int(r[1]), int(r[2])]) for r in rows)
+        return True
+
+    def GetMatchList(self):
+        return [Match(int(r[0]), [int(r[1]), int(r[2])]) for r in self._rows]
+
+    def rows(self):
+        return self._rows
+
+
+class PairwiseMatchFinder(MemHash):
+    """mems::PairwiseMatchFinder (LM/PairwiseMatchFinder.cpp:37-71), the finder progressiveMauve uses for <= 4 genomes."""
+    _rule = _capi.RULE_PAIRWISE
+
+
+def find_mums(seq0, seq1, seed, rule=_capi.RULE_PAIRWISE):
+    """(rows[n,3] int64 in reference list order, stats[8]) straight from mcu_find_mums."""
+    return _find_mums(seq0, seq1, seed, rule)
+
+
+class AnchorSession:
+    """Device-resident form of the same path (include/mauve_cuda.h: mcu_session_*): used by bench.py and multi-GPU runs."""
+
+    def __init__(self):
+        h = C.c_void_p()
+        check(lib().mcu_session_create(C.byref(h)))
+        self._h = h
+        self.stage_ms = np.zeros(8, dtype=np.float32)
+        self.stats = np.zeros(8, dtype=np.uint64)
+
+    def close(self):
+        if self._h:
+            lib().mcu_session_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, seq0, seq1):
+        a0, n0, k0 = _buf(seq0)
+        a1, n1, k1 = _buf(seq1)
+        check(lib().mcu_session_upload(self._h, a0, n0, a1, n1))
+
+    def upload_ptr(self, addr0, n0, addr1, n1):
+        check(lib().mcu_session_upload(self._h, addr0, n0, addr1, n1))
+
+    def run(self, seed, shard_index=0, shard_count=1):
+        check(lib().mcu_session_run(self._h, seed, shard_index, shard_count, self.stage_ms.ctypes.data, self.stats.ctypes.data))
+        return int(lib().mcu_session_match_count(self._h))
+
+    def match_count(self):
+        return int(lib().mcu_session_match_count(self._h))
+
+    def download(self, out=None):
+        n = self.match_count()
+        if out is None:
+            out = np.empty((n, 3), dtype=np.int64)
+        check(lib().mcu_session_download(self._h, out.ctypes.data))
+        return out[:n]
+
+    def download_ptr(self, addr):
+        check(lib().mcu_session_download(self._h, addr))
+
+    def matches_device(self):
+        return lib().mcu_session_matches_device(self._h)
+
+    def launch_count(self):
+        return int(lib().mcu_session_launch_count(self._h))
+
+
+def merge_matches(rows, in_device=False, n=None):
+    """Rank-0 merge of per-shard match lists (reference list order, duplicates dropped)."""
+    if in_device:
+        addr, cnt = rows, n
+    else:
+        rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3)
+        addr, cnt = rows.ctypes.data, rows.shape[0]
+    out = C.POINTER(_capi.Match)()
+    n_out = C.c_uint64(0)
+    check(lib().mcu_merge_matches(addr, cnt, 1 if in_device else 0, C.byref(out), C.byref(n_out)))
+    k = n_out.value
+    res = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_int64)), shape=(k, 3)).copy() if k else np.zeros((0, 3), dtype=np.int64)
+    lib().mcu_free(out)
+    return res
+
+
+# ---- MU/pwpath.h, MU/glbalign.cpp ------------------------------------------------------------------
+@dataclass
+class PWPath:
+    """Edge types of a pairwise path, first edge first: 'M' both advance, 'D' only A, 'I' only B (MU/pwpath.h:46-51)."""
+    edges: bytes
+    score: int
+
+    def GetEdgeCount(self):
+        return len(self.edges)
+
+
+def GlobalAlignBatch(pairs, return_ms=False):
+    """muscle::GlobalAlign for many (a, b) ACGT string pairs at once; returns one PWPath per pair."""
+    n = len(pairs)
+    if n == 0:
+        return ([], 0.0) if return_ms else []
+    a_off = np.zeros(n + 1, dtype=np.uint64)
+    b_off = np.zeros(n + 1, dtype=np.uint64)
+    la = np.fromiter((len(p[0]) for p in pairs), dtype=np.uint64, count=n)
+    lb = np.fromiter((len(p[1]) for p in pairs), dtype=np.uint64, count=n)
+    np.cumsum(la, out=a_off[1:])
+    np.cumsum(lb, out=b_off[1:])
+    a = np.frombuffer(b"".join(bytes(p[0]) for p in pairs), dtype=np.uint8)
+    b = np.frombuffer(b"".join(bytes(p[1]) for p in pairs), dtype=np.uint8)
+    res = nw_batch_arrays(a, a_off, b, b_off)
+    paths = [PWPath(res["path"][int(res["path_off"][i]):int(res["path_off"][i]) + int(res["path_len"][i])].tobytes(), int(res["score"][i]))
+             for i in range(n)]
+    return (paths, res["device_ms"]) if return_ms else paths
+
+
+def nw_batch_arrays(a, a_off, b, b_off):
+    """Array form of mcu_nw_batch: concatenated sequences + offsets in, path buffer + lengths + scores out."""
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    a_off = np.ascontiguousarray(a_off, dtype=np.uint64)
+    b_off = np.ascontiguousarray(b_off, dtype=np.uint64)
+    n = a_off.size - 1
+    path_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum((a_off[1:] - a_off[:-1]) + (b_off[1:] - b_off[:-1]), out=path_off[1:])
+    path = np.empty(max(int(path_off[-1]), 1), dtype=np.uint8)
+    path_len = np.zeros(max(n, 1), dtype=np.uint32)
+    score = np.zeros(max(n, 1), dtype=np.int64)
+    ms = C.c_float(0)
+    check(lib().mcu_nw_batch(n, a.ctypes.data, a_off.ctypes.data, b.ctypes.data, b_off.ctypes.data, path_off.ctypes.data,
+                             path.ctypes.data, path_len.ctypes.data, score.ctypes.data, C.byref(ms)))
+    stats = np.zeros(5, dtype=np.uint64)
+    lib().mcu_nw_last_stats(stats.ctypes.data)
+    return {"path": path, "path_off": path_off, "path_len": path_len[:n], "score": score[:n], "device_ms": float(ms.value), "stats": stats}
+
+
+def GlobalAlign(a, b) -> PWPath:
+    return GlobalAlignBatch([(a, b)])[0]
+
+
+# ---- LM/HomologyHMM -----------------------------------------------------------------------------------
+@dataclass
+class Params:
+    """struct Params (LM/HomologyHMM/homology.h:169-177)"""
+    iStartHomologous: float = 0.5
+    iGoHomologous: float = 0.00001
+    iGoUnrelated: float = 0.0000001
+    iGoStopFromUnrelated: float = 0.0000001
+    iGoStopFromHomologous: float = 0.0000001
+    aEmitHomologous: List[float] = field(default_factory=lambda: [0.0] * 8)
+    aEmitUnrelated: List[float] = field(default_factory=lambda: [0.0] * 8)
+
+    def as_array(self):
+        return np.array([self.iStartHomologous, self.iGoHomologous, self.iGoUnrelated, self.iGoStopFromUnrelated,
+                         self.iGoStopFromHomologous] + list(self.aEmitHomologous) + list(self.aEmitUnrelated), dtype=np.float64)
+
+    @staticmethod
+    def from_array(v):
+        v = [float(x) for x in v]
+        return Params(v[0], v[1], v[2], v[3], v[4], v[5:13], v[13:21])
+
+
+def getAdaptedHoxdMatrixParameters(gc_content: float) -> Params:
+    out = np.zeros(21, dtype=np.float64)
+    check(lib().mcu_hmm_params(gc_content, 0.0, 0.0, 0.0, out.ctypes.data))
+    return Params.from_array(out)
+
+
+def hmm_params(gc_content=0.5, go_homologous=0.0, go_unrelated=0.0, pct_identity=0.0):
+    out = np.zeros(21, dtype=np.float64)
+    check(lib().mcu_hmm_params(gc_content, go_homologous, go_unrelated, pct_identity, out.ctypes.data))
+    return out
+
+
+def adaptToPercentIdentity(params: Params, pct_identity: float) -> Params:
+    """LM/HomologyHMM/parameters.h:140-159 (host arithmetic on 8 numbers; mutates and returns params)."""
+    if pct_identity <= 0 or pct_identity > 1:
+        raise ValueError("Bad pct identity")
+    e = params.aEmitHomologous
+    gapnorm = pct_identity * (1.0 - e[6] - e[7])
+    prev = e[0] + e[1]
+    diff = prev - gapnorm
+    rest = e[2] + e[3] + e[4] + e[5]
+    for i in (2, 3, 4, 5):
+        e[i] += diff * e[i] / rest
+    for i in (0, 1):
+        e[i] -= diff * e[i] / prev
+    return params
+
+
+def run_batch(sequences, params, want_posterior=False):
+    """run() for many symbol strings ('1'..'8') at once -> list of 'H'/'N' predictions (+ posteriors)."""
+    p = params.as_array() if isinstance(params, Params) else np.ascontiguousarray(params, dtype=np.float64)
+    n = len(sequences)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(np.fromiter((len(s) for s in sequences), dtype=np.uint64, count=n), out=off[1:])
+    sym = np.frombuffer(b"".join(bytes(s) for s in sequences), dtype=np.uint8)
+    total = int(off[-1])
+    pred = np.empty(max(total, 1), dtype=np.uint8)
+    post = np.empty(max(total, 1), dtype=np.float64) if want_posterior else None
+    ms = C.c_float(0)
+    symaddr = sym.ctypes.data if total else np.zeros(1, dtype=np.uint8).ctypes.data
+    check(lib().mcu_hmm_batch(n, symaddr, off.ctypes.data, p.ctypes.data, pred.ctypes.data,
+                              post.ctypes.data if want_posterior else None, C.byref(ms)))
+    preds = [pred[int(off[i]):int(off[i + 1])].tobytes() for i in range(n)]
+    if want_posterior:
+        return preds, [post[int(off[i]):int(off[i + 1])] for i in range(n)], float(ms.value)
+    return preds
+
+
+def run(sequence, params, want_posterior=False):
+    """void run(std::string& sequence, std::string& prediction, const Params&) (LM/HomologyHMM/homology.h:47)"""
+    if want_posterior:
+        preds, posts, _ = run_batch([sequence], params, True)
+        return preds[0], posts[0]
+    return run_batch([sequence], params)[0]
+
+
+# ---- test hook --------------------------------------------------------------------------------------
+def sort_pairs(keys, vals, bits):
+    keys = np.ascontiguousarray(keys).copy()
+    vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+    assert keys.dtype in (np.uint32, np.uint64)
+    check(lib().mcu_test_sort_pairs(keys.ctypes.data, vals.ctypes.data, keys.size, keys.dtype.itemsize, bits))
+    return keys, vals

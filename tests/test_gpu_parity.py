@@ -1,0 +1,260 @@
+"""GPU (-m gpu): the CUDA path through the C ABI against the oracle on the same inputs and against the golden vectors."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import _golden
+from mauve_py_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- radix sort (test hook) ---------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,bits", [(np.uint32, 32), (np.uint32, 13), (np.uint64, 64), (np.uint64, 40), (np.uint64, 8)])
+@pytest.mark.parametrize("n", [0, 1, 31, 8191, 8192, 8193, 100003, 1 << 20])
+def test_radix_sort_pairs(mp, dtype, bits, n):
+    rng = np.random.default_rng(n + bits)
+    hi = (1 << bits) - 1
+    keys = rng.integers(0, hi, n, dtype=np.uint64, endpoint=True).astype(dtype)
+    if n > 100:
+        keys[: n // 3] = keys[0]  # heavy duplicates: stability matters
+    vals = np.arange(n, dtype=np.uint32)
+    k2, v2 = mp.sort_pairs(keys, vals, bits)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k2, keys[order])
+    assert np.array_equal(v2, vals[order])
+
+
+# ---- sorted mer list ----------------------------------------------------------------------------
+def test_sml_golden(mp):
+    z = _golden.npz("sml_small.npz")
+    for name, w, r, seed in _golden.cases(z):
+        sml = mp.DNAMemorySML()
+        sml.Create(z["seq_" + name].tobytes(), seed)
+        key = "%s_w%d_r%d" % (name, w, r)
+        assert np.array_equal(sml.mers(), z["mer_" + key]), key
+        assert np.array_equal(sml.positions(), z["pos_" + key]), key
+        assert sml.SMLLength() == z["mer_" + key].size and sml.Seed() == seed
+
+
+@pytest.mark.parametrize("n,w,r", [(20, 5, 0), (21, 15, 3), (1000, 7, 1), (65537, 11, 0), (300000, 15, 3), (300000, 16, 2), (200001, 19, 0),
+                                   (150000, 21, 0), (100000, 24, 0), (100000, 31, 0), (50000, 3, 0)])
+def test_sml_vs_oracle(mp, orc, n, w, r):
+    seq = synth.random_genome(n, 0.45, synth.rng_for(n + w)).tobytes()
+    seed = mp.getSeed(w, r)
+    sml = mp.DNAMemorySML()
+    sml.Create(seq, seed)
+    opos, omer = orc.sml_build(seq, seed)
+    assert np.array_equal(sml.mers(), omer)
+    assert np.array_equal(sml.positions(), opos)
+    # packed sequence = SortedMerList::sequence
+    import _oracle
+    words = int(_oracle.oracle().orc_packed_words(n))
+    ref_packed = np.zeros(words, dtype=np.uint32)
+    _oracle.oracle().orc_pack(seq, n, ref_packed.ctypes.data)
+    assert np.array_equal(sml.packed_sequence(), ref_packed)
+
+
+def test_sml_edge_cases(mp, orc):
+    seed = mp.getSeed(5, 0)
+    L = mp.getSeedLength(seed)
+    for seq in [b"", b"A", b"ACGT"[: L - 1], b"ACGTACGTAC"[:L], b"acgtnnRYKMSWBDHVxyz!" * 3]:
+        sml = mp.DNAMemorySML()
+        sml.Create(seq, seed)
+        opos, omer = orc.sml_build(seq, seed)
+        assert sml.SMLLength() == opos.size
+        assert np.array_equal(sml.mers(), omer) and np.array_equal(sml.positions(), opos)
+    with pytest.raises(mp.McuError) as e:  # '-' throws in the reference (LM/SortedMerList.cpp:433-437)
+        mp.DNAMemorySML().Create(b"ACGTACGT-ACGTACGTACGTACGT", seed)
+    from mauve_py_b200 import _capi
+    assert e.value.code == _capi.MCU_EGAP
+    with pytest.raises(mp.McuError):  # pattern with a trailing zero is not a DNA seed
+        mp.DNAMemorySML().Create(b"ACGTACGTACGTACGTACGT", 0b10110)
+
+
+def test_sml_mds42_digest(mp):
+    m = _golden.meta(_golden.npz("mums_mds42.npz"))["sml_full_w15_r3"]
+    _, g1 = _golden.mds42()
+    sml = mp.DNAMemorySML()
+    sml.Create(g1, 0x16df6d)
+    assert sml.SMLLength() == m["n"]
+    assert hashlib.sha1(sml.mers().tobytes()).hexdigest() == m["sha1_mer"]
+    assert hashlib.sha1(sml.positions().tobytes()).hexdigest() == m["sha1_pos_canon"]
+    found, idx = sml.FindMer(int(sml.mers()[12345]))
+    assert found and (sml.mers()[idx] >> np.uint64(34)) == (sml.mers()[12345] >> np.uint64(34))
+
+
+# ---- seed + match + extend ---------------------------------------------------------------------
+def test_mums_golden_small(mp):
+    z = _golden.npz("mums_small.npz")
+    for i, w, r, rule, seed, coll, cnt in _golden.cases(z):
+        a, b = z["a%d" % i].tobytes(), z["b%d" % i].tobytes()
+        ml = mp.MatchList(seq_table=[a, b])
+        ml.CreateMemorySMLs(w, r)
+        mh = mp.PairwiseMatchFinder() if rule == 0 else mp.MemHash()
+        mh.FindMatches(ml)
+        assert np.array_equal(ml.as_array(), z["rows%d" % i]), i
+        assert mh.MemCount() == cnt and mh.MemCollisionCount() == coll, i
+
+
+def test_mums_mds42(mp):
+    z = _golden.npz("mums_mds42.npz")
+    m = _golden.meta(z)
+    g0, g1 = _golden.mds42()
+    rows, stats = mp.libmems.find_mums(g0, g1, m["w15_r3"]["seed"])
+    assert rows.shape[0] == 29403 and int(rows[:, 0].sum()) == 3792460 and int((rows[:, 2] < 0).sum()) == 1515
+    assert np.array_equal(rows, z["rows_w15_r3"])
+    assert int(stats[0]) == 2744091 and int(stats[2]) == m["w15_r3"]["collisions"]
+    for key in ("w15_r0", "w11_r0", "w21_r0"):
+        rows, _ = mp.libmems.find_mums(g0, g1, m[key]["seed"])
+        assert rows.shape[0] == m[key]["n"] and int(rows[:, 0].sum()) == m[key]["sum_len"]
+        assert hashlib.sha1(rows.tobytes()).hexdigest() == m[key]["sha1_rows"], key
+
+
+@pytest.mark.parametrize("n,w,r,kw", [(200000, 11, 0, {}), (400000, 15, 3, dict(snp=0.01, n_inv=4)), (300000, 13, 1, dict(snp=0.08)),
+                                      (250000, 19, 0, dict(snp=0.003, n_inv=2)), (100000, 9, 0, dict(snp=0.02)),
+                                      (120000, 24, 0, dict(snp=0.001))])
+def test_mums_vs_oracle(mp, orc, n, w, r, kw):
+    a, b = synth.small_pair(n, seed=n + w, **kw)
+    seed = mp.getSeed(w, r)
+    rows, stats = mp.libmems.find_mums(a, b, seed)
+    orows, ostats = orc.find_mums(a, b, seed, 0)
+    assert np.array_equal(rows, orows)
+    assert int(stats[0]) == int(ostats[3]) and int(stats[1]) == int(ostats[1])
+
+
+def test_mums_config2_slice_vs_oracle(mp, orc):
+    a, b = synth.config2_pair(n=1_000_000)
+    seed = mp.getSeed(15, mp.CODING_SEED)
+    rows, stats = mp.libmems.find_mums(a, b, seed)
+    orows, _ = orc.find_mums(a.tobytes(), b.tobytes(), seed, 0)
+    assert rows.shape[0] > 100 and np.array_equal(rows, orows)
+
+
+def test_mums_self_and_revcomp(mp, orc):
+    g = synth.random_genome(150000, 0.5, synth.rng_for(9))
+    seed = mp.getSeed(13, 0)
+    for other in (g, synth.revcomp(g)):
+        rows, _ = mp.libmems.find_mums(g, other, seed)
+        orows, _ = orc.find_mums(g.tobytes(), other.tobytes(), seed, 0)
+        assert np.array_equal(rows, orows) and rows.shape[0] >= 1
+
+
+def test_mums_sharded_equals_unsharded(mp):
+    a, b = synth.small_pair(500000, seed=77, snp=0.01, n_inv=3)
+    seed = mp.getSeed(15, 3)
+    full, _ = mp.libmems.find_mums(a, b, seed)
+    for world in (2, 3, 8):
+        parts = []
+        s = mp.AnchorSession()
+        s.upload(a, b)
+        for rank in range(world):
+            s.run(seed, rank, world)
+            parts.append(s.download().copy())
+        s.close()
+        merged = mp.merge_matches(np.concatenate(parts, axis=0))
+        assert np.array_equal(merged, full), world
+
+
+def test_session_matches_one_shot(mp):
+    a, b = synth.small_pair(300000, seed=3)
+    seed = mp.getSeed(15, 3)
+    rows, stats = mp.libmems.find_mums(a, b, seed)
+    s = mp.AnchorSession()
+    s.upload(a, b)
+    for _ in range(3):  # re-running a session is idempotent
+        n = s.run(seed)
+        assert n == rows.shape[0] and np.array_equal(s.download(), rows)
+    assert s.launch_count() > 0 and s.stage_ms[6] > 0
+    s.close()
+
+
+# ---- gapped DP ------------------------------------------------------------------------------------
+def test_nw_golden(mp):
+    z = _golden.npz("nw_small.npz")
+    n = int(z["n"])
+    pairs = [(z["a%d" % i].tobytes(), z["b%d" % i].tobytes()) for i in range(n)]
+    paths = mp.GlobalAlignBatch(pairs)
+    for i, p in enumerate(paths):
+        assert p.edges == z["p%d" % i].tobytes(), i
+
+
+def test_nw_vs_oracle(mp, orc):
+    pairs = synth.dp_pairs(120, 1, 3000, seed=31)
+    rng = synth.rng_for(5)
+    for la, lb in [(255, 257), (256, 256), (257, 255), (512, 1), (1, 512), (513, 700), (2049, 2047), (5000, 4800), (300, 6000)]:
+        pairs.append((synth.random_genome(la, 0.5, rng).tobytes(), synth.random_genome(lb, 0.5, rng).tobytes()))
+    paths = mp.GlobalAlignBatch(pairs)
+    for (a, b), p in zip(pairs, paths):
+        op, osc = orc.nw_align(a, b)
+        assert p.score == osc, (len(a), len(b))
+        assert p.edges == op, (len(a), len(b))
+
+
+def test_nw_path_invariants_large(mp):
+    """size-independent properties at the window cap (20 kbp): path consumes both sequences, score recomputes from the path"""
+    rng = synth.rng_for(41)
+    a = synth.random_genome(20000, 0.5, rng)
+    b = synth.indels(synth.snps(a, 0.05, rng), 200, 0.3, 30, rng)
+    p = mp.GlobalAlign(a.tobytes(), b.tobytes())
+    e = np.frombuffer(p.edges, dtype=np.uint8)
+    assert int(((e == ord("M")) | (e == ord("D"))).sum()) == a.size
+    assert int(((e == ord("M")) | (e == ord("I"))).sum()) == b.size
+    # recompute the score of the returned path with the restated scoring (S + gaps: -400 interior, -200 terminal)
+    NUC = np.array([[151, -54, 29, -63], [-54, 160, -65, 29], [29, -65, 160, -54], [-63, 29, -54, 151]])
+    code = synth._CODE
+    ia = np.cumsum((e == ord("M")) | (e == ord("D"))) - 1
+    ib = np.cumsum((e == ord("M")) | (e == ord("I"))) - 1
+    m = e == ord("M")
+    score = int(NUC[code[a[ia[m]]], code[b[ib[m]]]].sum())
+    starts = np.flatnonzero((e != ord("M")) & (np.concatenate(([ord("M")], e[:-1])) != e))
+    for s in starts:
+        t = s
+        while t < e.size and e[t] == e[s]:
+            t += 1
+        score -= 200 if (s == 0 or t == e.size) else 400
+    assert score == p.score
+
+
+def test_nw_errors(mp):
+    from mauve_py_b200 import _capi
+    with pytest.raises(mp.McuError) as e:
+        mp.GlobalAlign(b"ACGTN", b"ACGT")
+    assert e.value.code == _capi.MCU_EALPHA
+    with pytest.raises(mp.McuError):
+        mp.GlobalAlign(b"", b"ACGT")
+    assert mp.GlobalAlignBatch([]) == []
+
+
+# ---- HMM ------------------------------------------------------------------------------------------
+def _check_hmm(pred, post, ref_pred, ref_post):
+    assert np.allclose(post, ref_post, rtol=1e-5, atol=1e-30), float(np.max(np.abs(post - ref_post) / np.maximum(ref_post, 1e-300)))
+    mism = np.flatnonzero(np.frombuffer(pred, dtype=np.uint8) != np.frombuffer(ref_pred, dtype=np.uint8))
+    assert all(abs(ref_post[j] - 0.9) <= 1e-5 for j in mism)
+
+
+def test_hmm_golden(mp):
+    z = _golden.npz("hmm_small.npz")
+    for c in _golden.cases(z):
+        i = c[0]
+        pred, post = mp.run(z["sym%d" % i].tobytes(), z["params%d" % i], want_posterior=True)
+        _check_hmm(pred, post, z["pred%d" % i].tobytes(), z["post%d" % i])
+
+
+def test_hmm_batch_vs_oracle(mp, orc):
+    params = mp.libmems.hmm_params(0.5, 1e-5, 1e-9, 0.7)
+    seqs = [synth.hmm_string(n, seed=n, block=b) for n, b in [(1, 10), (2, 10), (63, 40), (64, 40), (65, 40), (128, 50), (1000, 100), (100000, 500),
+                                                              (1_000_000, 3000)]]
+    seqs.insert(3, b"")
+    preds, posts, ms = mp.run_batch(seqs, params, want_posterior=True)
+    for s, pred, post in zip(seqs, preds, posts):
+        if len(s) == 0:
+            assert pred == b""
+            continue
+        opred, opost = orc.hmm_run(s, params)
+        _check_hmm(pred, post, opred, opost)
+    from mauve_py_b200 import _capi
+    with pytest.raises(mp.McuError) as e:
+        mp.run(b"12349", params)
+    assert e.value.code == _capi.MCU_EINVAL

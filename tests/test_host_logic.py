@@ -1,0 +1,84 @@
+"""CPU: host-side containers, synthetic generators, multi-rank gather (gloo, world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def test_synth_deterministic():
+    from mauve_py_b200 import synth
+    a1, b1 = synth.small_pair(20000, seed=5)
+    a2, b2 = synth.small_pair(20000, seed=5)
+    assert a1 == a2 and b1 == b2 and a1 != b1
+    assert set(a1) <= set(b"ACGT") and set(b1) <= set(b"ACGT")
+    x, y = synth.config2_pair(n=200000)
+    assert x.size == 200000 and abs(int(y.size) - 200000) < 2000
+    x3, y3 = synth.config3_pair(n=300000)
+    assert x3.size == 300000 and set(np.unique(y3)) <= set(b"ACGT")
+    p = synth.dp_pairs(10, 100, 1000, seed=3)
+    assert all(100 <= len(a) <= 1000 for a, _ in p)
+    s = synth.hmm_string(1000, seed=2)
+    assert len(s) == 1000 and set(s) <= set(b"12345678")
+
+
+def test_containers():
+    import mauve_py_b200 as mp
+    m = mp.Match(30, [5, -90])
+    assert m.Length() == 30 and m.Start(1) == -90 and m.Orientation(1) == -1 and m.Orientation(0) == 1
+    ml = mp.MatchList(seq_table=[b"ACGT", b"ACGT"])
+    ml.matches.append(m)
+    assert ml.as_array().tolist() == [[30, 5, -90]] and len(ml) == 1
+    p = mp.Params.from_array(np.arange(21) / 100.0)
+    assert np.array_equal(p.as_array(), np.arange(21) / 100.0)
+    with pytest.raises(mp.McuError):
+        mp.MemHash().FindMatches(mp.MatchList(seq_table=[b"A", b"C", b"G"]))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from mauve_py_b200 import dist as mdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # rank r holds r*3+1 rows (rank 1 of 3 holds none when world == 3 -> exercised by n=0 below)
+        n = 0 if (world == 3 and rank == 1) else rank * 3 + 1
+        rows = torch.arange(n * 3, dtype=torch.int64).reshape(n, 3) + 1000 * rank
+        out = mdist.gather_rows(rows, dst=0)
+        if rank == 0:
+            q.put(out.numpy().tolist())
+        else:
+            assert out is None
+        assert mdist.shard_of(rank, world) == (rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_rows_gloo(world):
+    import torch.multiprocessing as tmp
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    expect = []
+    for r in range(world):
+        n = 0 if (world == 3 and r == 1) else r * 3 + 1
+        expect += (np.arange(n * 3).reshape(n, 3) + 1000 * r).tolist()
+    assert got == expect

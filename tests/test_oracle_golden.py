@@ -1,0 +1,82 @@
+"""CPU: the C restatement (oracle/mauve_oracle.c) against the golden vectors minted from the reference's own code."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import _golden
+
+
+def test_seed_tables(orc):
+    t = _golden.seeds()
+    for k, v in t["get_seed"].items():
+        w, r = (int(x) for x in k.split(","))
+        assert orc.get_seed(w, r) == v, k
+    for k, v in t["seed_length"].items():
+        assert orc.seed_length(int(k)) == v
+    for k, v in t["seed_weight"].items():
+        assert orc.seed_weight(int(k)) == v
+    for k, v in t["default_weight"].items():
+        assert orc.default_seed_weight(int(k)) == v, k
+
+
+def test_sml_small(orc):
+    z = _golden.npz("sml_small.npz")
+    for name, w, r, seed in _golden.cases(z):
+        seq = z["seq_" + name].tobytes()
+        pos, mer = orc.sml_build(seq, seed)
+        key = "%s_w%d_r%d" % (name, w, r)
+        assert np.array_equal(mer, z["mer_" + key]), key
+        assert np.array_equal(pos, z["pos_" + key]), key  # oracle emits ties position-ascending = canonical form
+
+
+def test_mums_small(orc):
+    z = _golden.npz("mums_small.npz")
+    for i, w, r, rule, seed, coll, cnt in _golden.cases(z):
+        rows, stats = orc.find_mums(z["a%d" % i].tobytes(), z["b%d" % i].tobytes(), seed, rule)
+        assert np.array_equal(rows, z["rows%d" % i]), i
+        assert int(stats[1]) == cnt
+
+
+def test_mums_mds42(orc):
+    z = _golden.npz("mums_mds42.npz")
+    m = _golden.meta(z)
+    g0, g1 = _golden.mds42()
+    rows, stats = orc.find_mums(g0, g1, m["w15_r3"]["seed"], 0)
+    assert rows.shape[0] == 29403 and int(rows[:, 0].sum()) == 3792460 and int((rows[:, 2] < 0).sum()) == 1515
+    assert np.array_equal(rows, z["rows_w15_r3"])
+    assert int(stats[3]) == m["w15_r3"]["n"] + m["w15_r3"]["collisions"] == 2744091  # seed pairs = matches + collisions
+
+
+def test_sml_mds42_digest(orc):
+    z = _golden.npz("mums_mds42.npz")
+    m = _golden.meta(z)["sml_full_w15_r3"]
+    _, g1 = _golden.mds42()
+    pos, mer = orc.sml_build(g1, 0x16df6d)
+    assert mer.size == m["n"]
+    assert hashlib.sha1(mer.tobytes()).hexdigest() == m["sha1_mer"]
+    assert hashlib.sha1(pos.tobytes()).hexdigest() == m["sha1_pos_canon"]
+
+
+def test_nw_small(orc):
+    z = _golden.npz("nw_small.npz")
+    for i in range(int(z["n"])):
+        path, score = orc.nw_align(z["a%d" % i].tobytes(), z["b%d" % i].tobytes())
+        assert path == z["p%d" % i].tobytes(), i
+
+
+def test_hmm_small(orc):
+    z = _golden.npz("hmm_small.npz")
+    for c in _golden.cases(z):
+        i = c[0]
+        sym, params = z["sym%d" % i].tobytes(), z["params%d" % i]
+        # parameters: same doubles as getAdaptedHoxdMatrixParameters + adaptToPercentIdentity
+        assert np.array_equal(orc.hmm_params(c[1], c[2], c[3], c[4]), params)
+        pred, post = orc.hmm_run(sym, params)
+        ref_post = z["post%d" % i]
+        # north_star tolerance: 1e-5 relative on the posterior (the reference computes in float-mantissa bfloat)
+        assert np.allclose(post, ref_post, rtol=1e-5, atol=1e-30), (i, np.max(np.abs(post - ref_post) / np.maximum(ref_post, 1e-300)))
+        ref_pred = np.frombuffer(z["pred%d" % i].tobytes(), dtype=np.uint8)
+        mism = np.flatnonzero(np.frombuffer(pred, dtype=np.uint8) != ref_pred)
+        # H/N may flip only where the posterior sits within tolerance of the 0.9 threshold
+        assert all(abs(ref_post[j] - 0.9) <= 1e-5 for j in mism)
