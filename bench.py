@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the anchoring hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mbp 100]
+
+One "step" = one pass of seed + match + extend (pack -> seedgen -> radix sort -> join -> extend ->
+reference list order [-> NCCL gather + merge on rank 0 when N > 1]) over the synthetic 100 Mbp pair
+(BASELINE config 3, SURVEY.md 8d "C3"; the north_star target workload, it fits one GPU).  `value`
+is Mbp/s with both genomes already resident in HBM; `e2e` is the same metric through the public
+C-ABI call mcu_find_mums with pinned HOST buffers (H2D + D2H inside the timed region).  N > 1 shards
+the SAME pair by seed-key prefix ("strong" scaling).  The gapped DP (GCUPS) and the HMM are reported
+in the `dp` / `hmm` objects of the same line.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [l.strip().split(", ") for l in open(self.tmp.name) if l.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pinned_copy(lib, arr):
+    from mauve_py_b200._capi import check
+    p = C.c_void_p()
+    check(lib.mcu_host_alloc(C.byref(p), arr.size))
+    view = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(arr.size,))
+    view[:] = arr
+    return p, view
+
+
+def workload(mbp):
+    from mauve_py_b200 import synth
+    n = int(mbp * 1_000_000)
+    a, b = synth.config3_pair(n=n)
+    return a, b
+
+
+def cpu_checker():
+    """the CPU arm: the reference's own code compiled in place (oracle/_ref) when present, else the C restatement"""
+    import _oracle
+    if _oracle.have_ref():
+        return _oracle.ref_checker(), "reference"
+    return _oracle.oracle_checker(), "port"
+
+
+def cpu_sample(a, b, sample_bp):
+    """bounded sample of the same workload for the CPU arm: the leading `sample_bp` bases of both genomes"""
+    return a[:sample_bp].tobytes(), b[:sample_bp].tobytes()
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    import mauve_py_b200 as mp
+    a, b = workload(min(args.mbp, max(2 * args.cpu_sample_mbp, 1)))
+    sa, sb = cpu_sample(a, b, int(args.cpu_sample_mbp * 1e6))
+    chk, kind = cpu_checker()
+    weight = mp.getDefaultSeedWeight(int(args.mbp * 1e6))
+    seed = mp.getSeed(weight, mp.CODING_SEED)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        rows, _ = chk.find_mums(sa, sb, seed, 0)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = (len(sa) + len(sb)) / 1e6 / (ms / 1e3)
+    sample = "leading %.1f Mbp of both genomes of the %g Mbp pair, %d matches; single thread (the reference has no threads)" % (
+        args.cpu_sample_mbp, args.mbp, rows.shape[0])
+    line = {
+        "impl": "reference", "metric": "Mbp/s seed+match+extend", "value": value, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": config_dict(args, weight, seed),
+        "cpu_baseline": {"value": value, "unit": "Mbp/s", "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def config_dict(args, weight, seed):
+    return {"workload": "synthetic %g Mbp pair (BASELINE config 3 / SURVEY 8d C3: 0.9%% SNP, 0.1%% indel events, inversions, translocations), "
+                        "default seed weight %d rank CODING_SEED -> pattern 0x%x" % (args.mbp, weight, seed),
+            "genome_bp": int(args.mbp * 1e6), "seed_weight": weight, "seed_pattern": hex(seed),
+            "sharding": "seed-key prefix range per rank, NCCL gather of match rows to rank 0" if args.gpus > 1 else "none",
+            "l2": "inputs (2 x %g MB ASCII, %.1f GB of key/value pairs) exceed the 126 MB L2; no extra flush" % (args.mbp, 2 * args.mbp * 12e6 / 1e9)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mbp", type=float, default=100.0, help="genome size of the synthetic pair in Mbp")
+    ap.add_argument("--cpu-sample-mbp", type=float, default=2.0)
+    ap.add_argument("--dp-regions", type=int, default=1536)
+    ap.add_argument("--no-dp", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mauve_py_b200 as mp
+    from mauve_py_b200 import dist as mdist
+    from mauve_py_b200 import synth
+    from mauve_py_b200._capi import check
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    lib = mp.lib()
+    check(lib.mcu_init(local))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    a, b = workload(args.mbp)
+    nbases = int(a.size + b.size)
+    weight = mp.getDefaultSeedWeight((a.size + b.size) // 2)
+    seed = mp.getSeed(weight, mp.CODING_SEED)
+    L = mp.getSeedLength(seed)
+    pa, va = pinned_copy(lib, a)
+    pb, vb = pinned_copy(lib, b)
+
+    sess = mp.AnchorSession()
+    sess.upload_ptr(pa, a.size, pb, b.size)
+    shard, nshard = mdist.shard_of(rank, world)
+
+    def step_resident():
+        n = sess.run(seed, shard, nshard)
+        if world == 1:
+            return n, None
+        rows = torch.empty((n, 3), dtype=torch.int64, device="cuda")
+        sess_copy_device(sess, rows)
+        allrows = mdist.gather_rows(rows, 0)
+        if rank == 0:
+            merged = mp.merge_matches(allrows.data_ptr(), in_device=True, n=allrows.shape[0])
+            return merged.shape[0], merged
+        return n, None
+
+    def sess_copy_device(s, rows):
+        if rows.shape[0]:
+            s.download_ptr(rows.data_ptr())  # device-to-device (cudaMemcpyDefault)
+
+    # ---- value: device-resident inputs --------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    launches0 = sess.launch_count()
+    stage = np.zeros(8, dtype=np.float64)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    nmatch = 0
+    for _ in range(args.steps):
+        nmatch, _m = step_resident()
+        stage += sess.stage_ms
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    launches = sess.launch_count() - launches0
+    stats = sess.stats.copy()
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    ms_per_step = 1e3 * dt / args.steps
+    value = nbases / 1e6 / (dt / args.steps)
+    stage /= args.steps
+
+    # ---- e2e: host buffers through the public C-ABI call -----------------------------------------
+    def step_e2e():
+        if world == 1:
+            out = C.POINTER(mp._capi.Match)()
+            n_out = C.c_uint64(0)
+            check(lib.mcu_find_mums(pa, a.size, pb, b.size, seed, 0, C.byref(out), C.byref(n_out), None))
+            n = n_out.value
+            lib.mcu_free(out)
+            return n, n * 24
+        sess.upload_ptr(pa, a.size, pb, b.size)
+        n, merged = step_resident()
+        return n, (n * 24 if rank == 0 else 0)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        n_e2e, d2h = step_e2e()
+    barrier()
+    dte = time.perf_counter() - t0
+    t = torch.tensor([dte], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dte = float(t.item())
+    e2e_value = nbases / 1e6 / (dte / args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (rs_onesweep_kernel: one radix pass) ------------------------
+    peak, peak_src = measured_peaks()
+    kb = 4 if 2 * weight + 2 <= 32 else 8
+    passes = int(sess.stage_ms[7])
+    nsorted = int(stats[5])
+    bytes_per_launch = 2.0 * (kb + 4) * nsorted
+    sort_ms = float(stage[2])
+    per_launch_ms = sort_ms / max(passes, 1)
+    achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "onesweep_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    # whole-step algorithmic bytes: 1.25 + B_sml(w) + (Kb+4) per base, + 28 B per seed pair
+    P = (2 * weight + 1 + 7) // 8
+    b_per_base = 1.25 + 0.25 + (kb + 4) + P * 2 * (kb + 4) + (kb + 4)
+    step_bytes = b_per_base * nbases + 28.0 * float(stats[0])
+    dev_ms = float(stage[6])
+    roofline = {"bound": "hbm", "kernel": "rs_onesweep_kernel (one 8-bit LSD radix pass over %d key/value pairs)" % nsorted,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_launch, "launch_ms": per_launch_ms, "launches_per_step": passes,
+                "step": {"algorithmic_bytes": step_bytes, "bytes_per_base": b_per_base, "device_ms": dev_ms,
+                         "achieved": step_bytes / (dev_ms * 1e-3) / 1e9 if dev_ms > 0 else 0.0,
+                         "frac": (step_bytes / (dev_ms * 1e-3) / 1e9 / peak) if dev_ms > 0 else 0.0,
+                         "stage_ms": {"pack": float(stage[0]), "seedgen": float(stage[1]), "sort": float(stage[2]), "join": float(stage[3]),
+                                      "extend": float(stage[4]), "order": float(stage[5])}}}
+
+    # ---- CPU baseline on a bounded sample ---------------------------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        chk, kind = cpu_checker()
+        sa, sb = cpu_sample(a, b, int(args.cpu_sample_mbp * 1e6))
+        t0 = time.perf_counter()
+        rows, _ = chk.find_mums(sa, sb, seed, 0)
+        dtc = time.perf_counter() - t0
+        # parity spot check on the same sample, through the C ABI
+        grows, _ = mp.libmems.find_mums(sa, sb, seed)
+        if not np.array_equal(grows, rows):
+            print("PARITY FAILURE on the CPU sample", file=sys.stderr)
+            sys.exit(3)
+        cpu = {"value": (len(sa) + len(sb)) / 1e6 / dtc, "unit": "Mbp/s", "cores": 1, "kind": kind,
+               "sample": "leading %.1f Mbp of both genomes (%d matches, GPU result identical); single thread: the reference has no threads"
+                         % (args.cpu_sample_mbp, rows.shape[0])}
+
+    # ---- gapped DP + HMM (secondary metrics of BASELINE.json) ----------------------------------------
+    dp = hmm = None
+    if not args.no_dp:
+        pairs = synth.dp_pairs(args.dp_regions, 100, 10000, seed=20261020)
+        arrs = synth.dp_arrays(pairs)
+        mp.libmems.nw_batch_arrays(*arrs)
+        res = mp.libmems.nw_batch_arrays(*arrs)
+        cells = float(res["stats"][0])
+        dp = {"metric": "GCUPS gapped DP (full-matrix cells, NWSmall-exact paths)", "value": cells / (res["device_ms"] * 1e-3) / 1e9,
+              "unit": "GCUPS", "regions": len(pairs), "cells": cells, "device_ms": res["device_ms"],
+              "workload": "BASELINE config 5 sample: %d regions, lenA log-uniform 100 bp-10 kbp, 5%% SNP + 1%% indel events" % len(pairs)}
+        if not args.no_cpu:
+            chk, kind = cpu_checker()
+            small = [p for p in pairs if len(p[0]) <= 3000][:12]
+            t0 = time.perf_counter()
+            for x, y in small:
+                chk.nw_align(x, y)
+            dtc = time.perf_counter() - t0
+            dp["cpu_baseline"] = {"value": sum(len(x) * len(y) for x, y in small) / dtc / 1e9, "unit": "GCUPS", "cores": 1, "kind": kind,
+                                  "sample": "%d regions <= 3 kbp of the same batch" % len(small)}
+        sym = [synth.hmm_string(len(p[0]), seed=i, block=300) for i, p in enumerate(pairs[:512])]
+        params = mp.libmems.hmm_params(0.5, 1e-5, 1e-9, 0.7)
+        mp.run_batch(sym, params, True)
+        _, _, hms = mp.run_batch(sym, params, True)
+        hmm = {"metric": "HomologyHMM columns/s (Forward+Backward posteriors)", "value": sum(len(s) for s in sym) / (hms * 1e-3),
+               "unit": "columns/s", "strings": len(sym), "device_ms": hms}
+
+    line = {
+        "metric": "Mbp/s seed+match+extend", "value": value, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64" if kb == 8 else "u32",
+        "data": "synthetic", "config": config_dict(args, weight, seed), "matches": int(nmatch), "seed_pairs": int(stats[0]),
+        "device_ms_per_step": dev_ms,
+        "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": int(nbases), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * dte / args.steps, "api": "mcu_find_mums(host buffers)" if world == 1 else "mcu_session_upload+run, NCCL gather, mcu_merge_matches"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "dp": dp, "hmm": hmm,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

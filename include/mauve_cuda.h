@@ -104,7 +104,7 @@ int mcu_session_run(mcu_session* s, uint64_t seed, int shard_index, int shard_co
                     float* stage_ms, uint64_t* stats);
 /* number of matches produced by the last run */
 uint64_t mcu_session_match_count(const mcu_session* s);
-/* D2H copy of the match list into caller memory (n = mcu_session_match_count). */
+/* copy of the match list into caller memory, host or device (n = mcu_session_match_count rows). */
 int mcu_session_download(mcu_session* s, mcu_match* out);
 /* device pointer to the match rows (3 x int64 each) for NCCL gathers by the host language */
 const void* mcu_session_matches_device(const mcu_session* s);

@@ -4,9 +4,9 @@
 //   ascii[g]   n_g bytes                      input genome g
 //   packed[g]  ceil(n_g/16)+2 u32             2-bit, MSB-first per word, 2 zero pad words (SortedMerList::sequence)
 //   keys/vals  (n_0-L+1)+(n_1-L+1) pairs x2   key = canon(2w bits)<<2 | genome<<1 | strand ; val = position
-//   partner    u32 per genome-0 position      genome-1 position of the unique seed pair starting there
-//   flags      u8 per genome-0 position       bit0 = unique seed pair, bit1 = reverse strand
-//   cand       u32 list                       seeds that may be the leftmost unique seed of their match
+//   uniq       1 bit per genome-0 position    the seed starting here is unique in both genomes
+//   pairs      u64 list p0 | p1<<32           unique seed pairs, forward-strand from the front / reverse from the back
+//   cand       u64 list, same layout          pairs that may be the leftmost unique seed of their match
 //   matches    mcu_match rows                 raw, then ordered into the reference list order
 #include "anchor.cuh"
 
@@ -122,109 +122,21 @@ __global__ void keys_to_mers_kernel(const K* __restrict__ keys, u64 n, int w, u6
 // (LM/MemHash.cpp:139-162, tolerances 0/1) keep exactly the runs with one occurrence in each
 // genome.  In the combined sorted array such a run is "g0 entry immediately followed by a g1
 // entry with the same canon, different canon on both sides" -- a purely local test.
-// Output = HashMatch + SetDirection (LM/MemHash.cpp:167-203) in array form: partner[p0] = p1,
-// flags[p0] = 1 | rev<<1.  HBM traffic: sizeof(K) per pair (neighbours come from L1) + 4 B per
-// seed pair read + 5 B written.
-// counters: [0] seed pairs, [1] repeat-limit flag.
-// =========================================================================================
-template <typename K>
-__global__ void __launch_bounds__(256) join_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, u64 n,
-                                                  u32* __restrict__ partner, u8* __restrict__ flags,
-                                                  unsigned long long* __restrict__ counters)
-{
-    u32 found = 0, repeat = 0;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        K k = keys[i];
-        K canon = k >> 2;
-        if (i + 1000 < n && (keys[i + 1000] >> 2) == canon) repeat = 1;  // run longer than MER_REPEAT_LIMIT
-        if ((k >> 1) & 1) continue;    // a pair starts at its genome-0 entry
-        if (i + 1 >= n) continue;
-        K k1 = keys[i + 1];
-        if ((k1 >> 2) != canon || !((k1 >> 1) & 1)) continue;
-        if (i > 0 && (keys[i - 1] >> 2) == canon) continue;
-        if (i + 2 < n && (keys[i + 2] >> 2) == canon) continue;
-        u32 p0 = vals[i], p1 = vals[i + 1];
-        u32 rev = (u32)((k ^ k1) & 1);
-        partner[p0] = p1;
-        flags[p0] = (u8)(1u | (rev << 1));
-        ++found;
-    }
-    // block reduce
-    __shared__ u32 s_found, s_rep;
-    if (threadIdx.x == 0) { s_found = 0; s_rep = 0; }
-    __syncthreads();
-    for (int o = 16; o > 0; o >>= 1) found += __shfl_down_sync(0xffffffffu, found, o);
-    repeat = __any_sync(0xffffffffu, repeat);
-    if ((threadIdx.x & 31) == 0) {
-        if (found) atomicAdd(&s_found, found);
-        if (repeat) s_rep = 1;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_found) atomicAdd(&counters[0], (unsigned long long)s_found);
-        if (s_rep) atomicMax(&counters[1], 1ull);
-    }
-}
-
-// =========================================================================================
-// candidate filter: a seed whose left neighbour on the same diagonal is also a unique seed
-// pair cannot be the leftmost unique seed of its match -> drop it with two byte loads.
-// This is the bulk of AddHashEntry's "already contained" rejections (LM/MemHash.cpp:215-220):
-// 2.7 M seed pairs -> ~30 k candidates on MDS42.  counters[2] = number of candidates.
-// =========================================================================================
-__global__ void __launch_bounds__(256) candidate_kernel(const u32* __restrict__ partner, const u8* __restrict__ flags, u64 npos0,
-                                                       u32* __restrict__ cand, unsigned long long* __restrict__ counters)
-{
-    const u32 lane = threadIdx.x & 31;
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    const u64 rounds = (npos0 + stride - 1) / stride;
-    for (u64 r = 0; r < rounds; ++r) {
-        u64 p = r * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
-        bool is_cand = false;
-        if (p < npos0) {
-            u32 f = flags[p];
-            if (f & 1) {
-                is_cand = true;
-                if (p > 0) {
-                    u32 fl = flags[p - 1];
-                    if ((fl & 1) && fl == f) {
-                        u32 p1 = partner[p], q1 = partner[p - 1];
-                        // same diagonal: forward p1-1, reverse p1+1
-                        if ((f & 2) ? (q1 == p1 + 1) : (q1 + 1 == p1)) is_cand = false;
-                    }
-                }
-            }
-        }
-        u32 m = __ballot_sync(0xffffffffu, is_cand);
-        if (m) {
-            u64 base = 0;
-            if (lane == 0) base = atomicAdd(&counters[2], (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (is_cand) cand[base + __popc(m & lanemask_lt())] = (u32)p;
-        }
-    }
-}
-
-// =========================================================================================
-// extend: MatchFinder::ExtendMatch (LM/MatchFinder.h:218-374) + the containment dedupe of
-// MemHash::AddHashEntry (LM/MemHash.cpp:209-251), in closed form (SURVEY.md Appendix B.2):
-// on the seed's diagonal a "hit" at offset t is spaced-seed equality of the two genomes with
-// the strand relation of the seed (forward: f0 == f1; reverse: f0 == revcomp(f1) and f0 not
-// its own reverse complement -- the parity test of :281-303); the match is the maximal chain
-// of hits with gaps <= L containing the seed, clipped to valid seed positions (:248-257).
-// One warp per candidate: lanes probe the L offsets beyond the current end, ballot, jump to
-// the farthest hit.  While walking left, meeting another unique seed pair of the same diagonal
-// means this candidate is not the leftmost one of its match -> abandon (exactly one emitter
-// per match).  counters[3] = number of matches.
+// Output = HashMatch + SetDirection (LM/MemHash.cpp:167-203) as
+//   uniq   bitmap over genome-0 positions: the seed starting here is unique in both genomes
+//          (12.5 MB at 100 Mbp: L2 resident, set with fire-and-forget atomics)
+//   pairs  u64 list p0 | p1 << 32: forward-strand pairs are filled from the front, reverse-strand
+//          pairs from the back, so the strand needs no storage (one reservation per block and strand).
+// HBM traffic: sizeof(K) per sorted entry + 8 B per seed pair read (vals) + 8 B written.
+// counters: [0] forward pairs, [1] repeat-limit flag, [6] reverse pairs.
 // =========================================================================================
 struct ExtendArgs {
     const u32* g0;
     const u32* g1;
     u64 npos0, npos1;
-    const u32* partner;
-    const u8* flags;
-    const u32* cand;
-    u64 ncand;
+    const u32* uniq;
+    u64* cand;          // candidate list p0 | p1 << 32: forward-strand from the front, reverse-strand from the back
+    u64 nfwd, nrev, cap;
     mcu_match* out;
     unsigned long long* counters;
 };
@@ -241,16 +153,135 @@ __device__ __forceinline__ bool probe_hit(const ExtendArgs& a, const SeedParams&
     return f0 != revcomp_seed(f0, sp.w);
 }
 
+__device__ __forceinline__ bool uniq_bit(const u32* __restrict__ uniq, i64 t) { return (__ldg(uniq + (t >> 5)) >> (t & 31)) & 1u; }
+
+template <typename K>
+__global__ void __launch_bounds__(256) join_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, u64 n, u32* __restrict__ uniq,
+                                                  u64* __restrict__ pairs, u64 pair_cap, unsigned long long* __restrict__ counters)
+{
+    constexpr int IPT = 8;
+    __shared__ u32 s_warp[2][8];
+    __shared__ unsigned long long s_base[2];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 tile = (u64)blockIdx.x * (256 * IPT);
+    u32 repeat = 0, fmask = 0, rmask = 0;
+    u64 ent[IPT];
+#pragma unroll
+    for (int it = 0; it < IPT; ++it) {
+        const u64 i = tile + (u64)it * 256 + threadIdx.x;
+        ent[it] = 0;
+        if (i < n) {
+            const K k = keys[i];
+            const K canon = k >> 2;
+            const bool next2 = i + 2 < n && (keys[i + 2] >> 2) == canon;
+            // a run longer than MER_REPEAT_LIMIT contains an entry whose +2 and +1000 neighbours are both in it
+            if (next2 && i + 1000 < n && (keys[i + 1000] >> 2) == canon) repeat = 1;
+            if (!((k >> 1) & 1) && i + 1 < n && !next2) {  // a pair starts at its genome-0 entry
+                const K k1 = keys[i + 1];
+                if ((k1 >> 2) == canon && ((k1 >> 1) & 1) && !(i > 0 && (keys[i - 1] >> 2) == canon)) {
+                    const u32 p0 = vals[i], p1 = vals[i + 1];
+                    ent[it] = (u64)p0 | ((u64)p1 << 32);
+                    if ((k ^ k1) & 1) rmask |= 1u << it; else fmask |= 1u << it;
+                    atomicOr(&uniq[p0 >> 5], 1u << (p0 & 31));
+                }
+            }
+        }
+    }
+    // block-wide exclusive scan of the per-thread counts: one reservation per block and strand
+    const u32 cf = __popc(fmask), cr = __popc(rmask);
+    u32 inf = cf, inr = cr;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 tf = __shfl_up_sync(0xffffffffu, inf, o), tr = __shfl_up_sync(0xffffffffu, inr, o);
+        if (lane >= (u32)o) { inf += tf; inr += tr; }
+    }
+    if (lane == 31) { s_warp[0][warp] = inf; s_warp[1][warp] = inr; }
+    __syncthreads();
+    u32 wf = 0, wr = 0, totf = 0, totr = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        if ((u32)w < warp) { wf += s_warp[0][w]; wr += s_warp[1][w]; }
+        totf += s_warp[0][w];
+        totr += s_warp[1][w];
+    }
+    if (threadIdx.x == 0) {
+        s_base[0] = totf ? atomicAdd(&counters[0], (unsigned long long)totf) : 0ull;
+        s_base[1] = totr ? atomicAdd(&counters[6], (unsigned long long)totr) : 0ull;
+    }
+    __syncthreads();
+    u64 of = s_base[0] + wf + inf - cf, orv = s_base[1] + wr + inr - cr;
+#pragma unroll
+    for (int it = 0; it < IPT; ++it) {
+        if (fmask & (1u << it)) pairs[of++] = ent[it];
+        if (rmask & (1u << it)) pairs[pair_cap - 1 - (orv++)] = ent[it];
+    }
+    if (__any_sync(0xffffffffu, repeat) && lane == 0) atomicMax(&counters[1], 1ull);
+}
+
+// candidate filter: a seed pair whose left neighbour on the same diagonal is also a unique seed
+// pair cannot be the leftmost unique seed of its match.  This removes the bulk of AddHashEntry's
+// "already contained" rejections (LM/MemHash.cpp:215-220): 2.7 M seed pairs -> ~30 k candidates
+// on MDS42.  counters[2] / [7] = forward / reverse candidates.
+__global__ void __launch_bounds__(256) candidate_kernel(ExtendArgs a, SeedParams sp, const u64* __restrict__ pairs, u64 pfwd, u64 prev_, u64 pair_cap)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u64 total = pfwd + prev_;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 rounds = (total + stride - 1) / stride;
+    for (u64 r = 0; r < rounds; ++r) {
+        const u64 idx = r * stride + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+        bool is_cand = false, rev = false;
+        u64 e = 0;
+        if (idx < total) {
+            rev = idx >= pfwd;
+            e = rev ? pairs[pair_cap - 1 - (idx - pfwd)] : pairs[idx];
+            const i64 p0 = (i64)(e & 0xffffffffu), p1 = (i64)(e >> 32);
+            const i64 d = rev ? p0 + p1 : p1 - p0;
+            i64 other;
+            is_cand = !(p0 > 0 && uniq_bit(a.uniq, p0 - 1) && probe_hit(a, sp, rev, d, p0 - 1, other));
+        }
+        const u32 mf = __ballot_sync(0xffffffffu, is_cand && !rev), mr = __ballot_sync(0xffffffffu, is_cand && rev);
+        if (mf | mr) {
+            u64 bf = 0, br = 0;
+            if (lane == 0) {
+                if (mf) bf = atomicAdd(&a.counters[2], (unsigned long long)__popc(mf));
+                if (mr) br = atomicAdd(&a.counters[7], (unsigned long long)__popc(mr));
+            }
+            bf = __shfl_sync(0xffffffffu, bf, 0);
+            br = __shfl_sync(0xffffffffu, br, 0);
+            if (is_cand) {
+                if (!rev) a.cand[bf + __popc(mf & lanemask_lt())] = e;
+                else a.cand[a.cap - 1 - (br + __popc(mr & lanemask_lt()))] = e;
+            }
+        }
+    }
+}
+
+// =========================================================================================
+// extend: MatchFinder::ExtendMatch (LM/MatchFinder.h:218-374) + the containment dedupe of
+// MemHash::AddHashEntry (LM/MemHash.cpp:209-251), in closed form (SURVEY.md Appendix B.2):
+// on the seed's diagonal a "hit" at offset t is spaced-seed equality of the two genomes with
+// the strand relation of the seed (forward: f0 == f1; reverse: f0 == revcomp(f1) and f0 not
+// its own reverse complement -- the parity test of :281-303); the match is the maximal chain
+// of hits with gaps <= L containing the seed, clipped to valid seed positions (:248-257).
+// A hit at a genome-0 position whose uniq bit is set IS a unique seed pair of this diagonal
+// (its only genome-1 occurrence is the one the hit compares against).
+// =========================================================================================
+// One warp per candidate: lanes probe the L offsets beyond the current end, ballot, jump to
+// the farthest hit.  While walking left, meeting another unique seed pair of the same diagonal
+// means this candidate is not the leftmost one of its match -> abandon (exactly one emitter
+// per match).  counters[3] = number of matches.
 __global__ void __launch_bounds__(256) extend_kernel(ExtendArgs a, SeedParams sp)
 {
     const u32 lane = threadIdx.x & 31;
     const u64 warp_global = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
     const i64 L = sp.L;
-    for (u64 c = warp_global; c < a.ncand; c += nwarps) {
-        const i64 t0 = a.cand[c];
-        const bool rev = (a.flags[t0] >> 1) & 1;
-        const i64 p1 = a.partner[t0];
+    const u64 total = a.nfwd + a.nrev;
+    for (u64 c = warp_global; c < total; c += nwarps) {
+        const bool rev = c >= a.nfwd;
+        const u64 e = rev ? a.cand[a.cap - 1 - (c - a.nfwd)] : a.cand[c];
+        const i64 t0 = (i64)(e & 0xffffffffu), p1 = (i64)(e >> 32);
         const i64 d = rev ? t0 + p1 : p1 - t0;
         // ---- walk left ----
         i64 cur = t0;
@@ -258,8 +289,8 @@ __global__ void __launch_bounds__(256) extend_kernel(ExtendArgs a, SeedParams sp
         while (true) {
             i64 t = cur - 1 - (i64)lane, other = 0;
             bool h = (i64)lane < L && probe_hit(a, sp, rev, d, t, other);
-            bool uniq = h && (a.flags[t] & 1) && (i64)a.partner[t] == other;
-            if (__any_sync(0xffffffffu, uniq)) { abandoned = true; break; }
+            bool uq = h && uniq_bit(a.uniq, t);
+            if (__any_sync(0xffffffffu, uq)) { abandoned = true; break; }
             u32 hits = __ballot_sync(0xffffffffu, h);
             if (!hits) break;
             cur -= 32 - __clz(hits);  // farthest hit: highest lane = largest distance
@@ -354,8 +385,8 @@ void session_destroy(Session& s)
     if (!s.ok) return;
     cudaStreamSynchronize(s.stream);
     DevBuf* bufs[] = {&s.ascii[0], &s.ascii[1], &s.packed[0], &s.packed[1], &s.keys_a, &s.keys_b, &s.vals_a, &s.vals_b,
-                      &s.partner, &s.flags, &s.cand, &s.raw_matches, &s.ord_keys_a, &s.ord_keys_b, &s.ord_vals_a, &s.ord_vals_b,
-                      &s.matches, &s.counters, &s.radix.hist, &s.radix.status, &s.radix.counters};
+                      &s.uniq, &s.pairs, &s.cand, &s.raw_matches, &s.ord_keys_a, &s.ord_keys_b, &s.ord_vals_a, &s.ord_vals_b,
+                      &s.matches, &s.ord_primary, &s.counters, &s.radix.hist, &s.radix.status, &s.radix.counters};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(s.ev[i]);
     if (s.h_counters) cudaFreeHost(s.h_counters);
@@ -397,7 +428,7 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
     const int passes = (key_bits + 7) / 8;
     const bool sharded = shard_count > 1;
     unsigned long long* ctr = s.counters.as<unsigned long long>();
-    // counters: [0] pairs [1] repeat flag [2] candidates [3] matches [4] gap error (u32) [5] shard element count
+    // counters: [0] fwd pairs [1] repeat flag [2] fwd candidates [3] matches [4] gap error (u32) [5] shard element count [6] rev pairs [7] rev candidates
     MCU_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), s.stream));
     MCU_CUDA(cudaEventRecord(s.ev[0], s.stream));
 
@@ -454,11 +485,13 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
     MCU_CUDA(cudaEventRecord(s.ev[3], s.stream));
 
     // ---- join ----
-    MCU_TRY(s.partner.reserve((npos0 + 1) * sizeof(u32)));
-    MCU_TRY(s.flags.reserve(npos0 + 16));
-    MCU_CUDA(cudaMemsetAsync(s.flags.p, 0, npos0 + 16, s.stream));
+    const u64 pair_cap = (npos0 < npos1 ? npos0 : npos1) + 1;
+    const u64 uniq_words = div_up(npos0 + 1, 32) + 1;
+    MCU_TRY(s.uniq.reserve(uniq_words * sizeof(u32)));
+    MCU_TRY(s.pairs.reserve(pair_cap * sizeof(u64)));
+    MCU_CUDA(cudaMemsetAsync(s.uniq.p, 0, uniq_words * sizeof(u32), s.stream));
     if (nsort) {
-        join_kernel<K><<<grid_for(nsort, 256, 8), 256, 0, s.stream>>>(skeys, svals, nsort, s.partner.as<u32>(), s.flags.as<u8>(), ctr);
+        join_kernel<K><<<(unsigned)div_up(nsort, 256 * 8), 256, 0, s.stream>>>(skeys, svals, nsort, s.uniq.as<u32>(), s.pairs.as<u64>(), pair_cap, ctr);
         s.launches++;
     }
     MCU_CUDA(cudaEventRecord(s.ev[4], s.stream));
@@ -467,23 +500,26 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
     MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     MCU_CUDA(cudaStreamSynchronize(s.stream));
     if (((u32*)(s.h_counters + 4))[0]) { set_error("gap character '-' in a genome sequence (input must be unaligned)"); return MCU_EGAP; }
-    const u64 npairs = s.h_counters[0];
+    const u64 pfwd = s.h_counters[0], prev_ = s.h_counters[6];
+    const u64 npairs = pfwd + prev_;
     const u64 repeat_flag = s.h_counters[1];
     u64 ncand = 0, nmatch = 0;
     if (npairs) {
-        MCU_TRY(s.cand.reserve(npairs * sizeof(u32)));
-        candidate_kernel<<<grid_for(npos0, 256, 8), 256, 0, s.stream>>>(s.partner.as<u32>(), s.flags.as<u8>(), npos0, s.cand.as<u32>(), ctr);
-        s.launches++;
-        MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
-        MCU_CUDA(cudaStreamSynchronize(s.stream));
-        ncand = s.h_counters[2];
-        MCU_TRY(s.raw_matches.reserve(ncand * sizeof(mcu_match)));
+        MCU_TRY(s.cand.reserve((npairs + 1) * sizeof(u64)));
         ExtendArgs ea;
         ea.g0 = s.packed[0].as<u32>(); ea.g1 = s.packed[1].as<u32>();
         ea.npos0 = npos0; ea.npos1 = npos1;
-        ea.partner = s.partner.as<u32>(); ea.flags = s.flags.as<u8>();
-        ea.cand = s.cand.as<u32>(); ea.ncand = ncand;
-        ea.out = s.raw_matches.as<mcu_match>(); ea.counters = ctr;
+        ea.uniq = s.uniq.as<u32>();
+        ea.cand = s.cand.as<u64>(); ea.nfwd = 0; ea.nrev = 0; ea.cap = npairs;
+        ea.out = nullptr; ea.counters = ctr;
+        candidate_kernel<<<grid_for(npairs, 256, 8), 256, 0, s.stream>>>(ea, sp, s.pairs.as<u64>(), pfwd, prev_, pair_cap);
+        s.launches++;
+        MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        MCU_CUDA(cudaStreamSynchronize(s.stream));
+        ea.nfwd = s.h_counters[2]; ea.nrev = s.h_counters[7];
+        ncand = ea.nfwd + ea.nrev;
+        MCU_TRY(s.raw_matches.reserve((ncand + 1) * sizeof(mcu_match)));
+        ea.out = s.raw_matches.as<mcu_match>();
         extend_kernel<<<grid_for(ncand * 32, 256, 8), 256, 0, s.stream>>>(ea, sp);
         s.launches++;
         MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
@@ -520,8 +556,8 @@ int order_matches(Session& s, const mcu_match* rows_dev, u64 n)
     MCU_TRY(s.ord_keys_b.reserve(n * sizeof(u64)));
     MCU_TRY(s.ord_vals_a.reserve(n * sizeof(u32)));
     MCU_TRY(s.ord_vals_b.reserve(n * sizeof(u32)));
-    MCU_TRY(s.cand.reserve(n * sizeof(u64)));  // reuse as the primary-key stash
-    u64* primary = s.cand.as<u64>();
+    MCU_TRY(s.ord_primary.reserve(n * sizeof(u64)));
+    u64* primary = s.ord_primary.as<u64>();
     u64* sec = s.ord_keys_a.as<u64>();
     const int s0_bits = 33, s1_bits = 36;  // starts < 2^32 (+ length), sign bit
     const int g = grid_for(n, 256, 8);

@@ -10,7 +10,7 @@ struct Session {
     cudaEvent_t ev[8] = {};
     DevBuf ascii[2], packed[2];
     DevBuf keys_a, keys_b, vals_a, vals_b;
-    DevBuf partner, flags, cand, raw_matches, ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b, matches, counters;
+    DevBuf uniq, pairs, cand, raw_matches, ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b, ord_primary, matches, counters;
     RadixScratch radix;
     u64 n[2] = {0, 0};
     u64 match_count = 0;

@@ -270,7 +270,7 @@ int mcu_session_download(mcu_session* h, mcu_match* out)
     if (!h) return MCU_EINVAL;
     if (h->s.match_count == 0) return MCU_OK;
     if (!out) return MCU_EINVAL;
-    MCU_CUDA(cudaMemcpyAsync(out, h->s.matches.p, h->s.match_count * sizeof(mcu_match), cudaMemcpyDeviceToHost, h->s.stream));
+    MCU_CUDA(cudaMemcpyAsync(out, h->s.matches.p, h->s.match_count * sizeof(mcu_match), cudaMemcpyDefault, h->s.stream));
     MCU_CUDA(cudaStreamSynchronize(h->s.stream));
     return MCU_OK;
 }
