@@ -81,7 +81,9 @@ int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed,
  *      stats (optional, 8 x uint64): [0] seed pairs (unique in both genomes), [1] matches,
  *      [2] collisions = [0]-[1] (MemHash::MemCollisionCount), [3] 1 if some join run exceeds
  *      MER_REPEAT_LIMIT=1000 (the reference's skip-ahead branch, LM/MatchFinder.cpp:253-277,
- *      is not reproduced; such runs never produce seed pairs), [4..7] reserved.                */
+ *      is not reproduced; such runs never produce seed pairs), [4] extension candidates,
+ *      [5] sorted (key, position) entries, [6] hash buckets replayed in insertion order,
+ *      [7] duplicate rows the replay added (the reference stores some matches twice).            */
 #define MCU_RULE_PAIRWISE 0
 #define MCU_RULE_MEMHASH 1
 int mcu_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule,
@@ -113,8 +115,13 @@ uint64_t mcu_session_launch_count(const mcu_session* s);
 /* Rank-0 merge of per-shard lists gathered into one device or host array: sorts into the
  * reference list order and drops the duplicates that shards produce for one maximal match
  * (the distributed form of AddHashEntry's containment check).  in_device != 0 means `rows`
- * is a device pointer.  Result in library-owned host memory (*out, *n_out).               */
-int mcu_merge_matches(const mcu_match* rows, uint64_t n, int in_device, mcu_match** out, uint64_t* n_out);
+ * is a device pointer.  Result in library-owned host memory (*out, *n_out).
+ * *unclean_buckets_out (optional) = number of hash buckets whose content depends on the reference's
+ * insertion order (see csrc/replay.cu); when it is non-zero the merged list may differ from the
+ * reference's (duplicate rows / order inside those buckets) and the caller re-runs the pair unsharded
+ * (mcu_session_run with shard_count 1), which replays such buckets exactly.                          */
+int mcu_merge_matches(const mcu_match* rows, uint64_t n, int in_device, mcu_match** out, uint64_t* n_out,
+                      uint64_t* unclean_buckets_out);
 
 /* ---- gapped DP: replaces muscle::GlobalAlign (MU/glbalign.cpp:69-81 -> NWSmall
  *      MU/nwsmall.cpp:500-670 + BitTraceBack MU/bittraceback.cpp:138-) for batches of

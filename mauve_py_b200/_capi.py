@@ -78,7 +78,7 @@ def lib():
     L.mcu_session_matches_device.restype = vp
     L.mcu_session_launch_count.argtypes = [vp]
     L.mcu_session_launch_count.restype = u64
-    L.mcu_merge_matches.argtypes = [vp, u64, i32, C.POINTER(C.POINTER(Match)), C.POINTER(u64)]
+    L.mcu_merge_matches.argtypes = [vp, u64, i32, C.POINTER(C.POINTER(Match)), C.POINTER(u64), C.POINTER(u64)]
     L.mcu_nw_batch.argtypes = [u64, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
     L.mcu_nw_last_stats.argtypes = [vp]
     L.mcu_nw_last_stats.restype = None

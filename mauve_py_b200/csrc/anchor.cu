@@ -130,31 +130,6 @@ __global__ void keys_to_mers_kernel(const K* __restrict__ keys, u64 n, int w, u6
 // HBM traffic: sizeof(K) per sorted entry + 8 B per seed pair read (vals) + 8 B written.
 // counters: [0] forward pairs, [1] repeat-limit flag, [6] reverse pairs.
 // =========================================================================================
-struct ExtendArgs {
-    const u32* g0;
-    const u32* g1;
-    u64 npos0, npos1;
-    const u32* uniq;
-    u64* cand;          // candidate list p0 | p1 << 32: forward-strand from the front, reverse-strand from the back
-    u64 nfwd, nrev, cap;
-    mcu_match* out;
-    unsigned long long* counters;
-};
-
-__device__ __forceinline__ bool probe_hit(const ExtendArgs& a, const SeedParams& sp, bool rev, i64 d, i64 t, i64& other)
-{
-    if (t < 0 || t >= (i64)a.npos0) return false;
-    other = rev ? d - t : t + d;
-    if (other < 0 || other >= (i64)a.npos1) return false;
-    u64 f0 = extract_seed(load_mer32(a.g0, (u64)t), sp);
-    u64 x1 = extract_seed(load_mer32(a.g1, (u64)other), sp);
-    if (!rev) return f0 == x1;
-    if (f0 != revcomp_seed(x1, sp.w)) return false;
-    return f0 != revcomp_seed(f0, sp.w);
-}
-
-__device__ __forceinline__ bool uniq_bit(const u32* __restrict__ uniq, i64 t) { return (__ldg(uniq + (t >> 5)) >> (t & 31)) & 1u; }
-
 template <typename K>
 __global__ void __launch_bounds__(256) join_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, u64 n, u32* __restrict__ uniq,
                                                   u64* __restrict__ pairs, u64 pair_cap, unsigned long long* __restrict__ counters)
@@ -376,6 +351,7 @@ int session_init(Session& s)
     for (int i = 0; i < 8; ++i) MCU_CUDA(cudaEventCreate(&s.ev[i]));
     MCU_CUDA(cudaHostAlloc((void**)&s.h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     MCU_TRY(s.counters.reserve(8 * sizeof(unsigned long long)));
+    MCU_CUDA(cudaHostAlloc((void**)&s.h_replay, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     s.ok = true;
     return MCU_OK;
 }
@@ -386,10 +362,13 @@ void session_destroy(Session& s)
     cudaStreamSynchronize(s.stream);
     DevBuf* bufs[] = {&s.ascii[0], &s.ascii[1], &s.packed[0], &s.packed[1], &s.keys_a, &s.keys_b, &s.vals_a, &s.vals_b,
                       &s.uniq, &s.pairs, &s.cand, &s.raw_matches, &s.ord_keys_a, &s.ord_keys_b, &s.ord_vals_a, &s.ord_vals_b,
-                      &s.matches, &s.ord_primary, &s.counters, &s.radix.hist, &s.radix.status, &s.radix.counters};
+                      &s.matches, &s.ord_primary, &s.counters, &s.radix.hist, &s.radix.status, &s.radix.counters,
+                      &s.rp_ctr, &s.rp_bitmap, &s.rp_list, &s.rp_canon, &s.rp_keys_b, &s.rp_idx_a, &s.rp_idx_b, &s.rp_p0, &s.rp_row, &s.rp_bkeys,
+                      &s.rp_pool, &s.rp_extra, &s.rp_prefix, &s.rp_vinfo, &s.rp_out};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(s.ev[i]);
     if (s.h_counters) cudaFreeHost(s.h_counters);
+    if (s.h_replay) cudaFreeHost(s.h_replay);
     cudaStreamDestroy(s.stream);
     s.ok = false;
 }
@@ -530,6 +509,9 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
 
     // ---- order ----
     MCU_TRY(order_matches(s, s.raw_matches.as<mcu_match>(), nmatch));
+    u64 unclean = 0, dup_rows = 0;
+    MCU_TRY(replay_unclean(s, &sp, !sharded, &unclean, &dup_rows));
+    nmatch = s.match_count;
     MCU_CUDA(cudaEventRecord(s.ev[6], s.stream));
     MCU_CUDA(cudaStreamSynchronize(s.stream));
     MCU_CUDA(cudaGetLastError());
@@ -541,7 +523,7 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
     }
     if (stats) {
         stats[0] = npairs; stats[1] = nmatch; stats[2] = npairs - nmatch; stats[3] = repeat_flag;
-        stats[4] = ncand; stats[5] = nsort; stats[6] = 0; stats[7] = 0;
+        stats[4] = ncand; stats[5] = nsort; stats[6] = unclean; stats[7] = dup_rows;
     }
     return MCU_OK;
 }

@@ -11,6 +11,9 @@ struct Session {
     DevBuf ascii[2], packed[2];
     DevBuf keys_a, keys_b, vals_a, vals_b;
     DevBuf uniq, pairs, cand, raw_matches, ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b, ord_primary, matches, counters;
+    // bucket replay (replay.cu)
+    DevBuf rp_ctr, rp_bitmap, rp_list, rp_canon, rp_keys_b, rp_idx_a, rp_idx_b, rp_p0, rp_row, rp_bkeys, rp_pool, rp_extra, rp_prefix, rp_vinfo, rp_out;
+    unsigned long long* h_replay = nullptr;  // pinned, 8 entries
     RadixScratch radix;
     u64 n[2] = {0, 0};
     u64 match_count = 0;
@@ -25,8 +28,40 @@ int session_upload(Session& s, const char* seq0, u64 n0, const char* seq1, u64 n
 int session_run(Session& s, u64 seed, int shard_index, int shard_count, float* stage_ms, u64* stats);
 // sorts rows (device, n of them) into reference list order; result in s.matches (device)
 int order_matches(Session& s, const mcu_match* rows_dev, u64 n);
+// Looks for hash buckets whose content depends on the reference's insertion order (replay.cu) and, when `can_replay`
+// (genomes + unique-seed bitmap of the whole key space are in the session), replays those buckets exactly.
+// s.matches / s.match_count are updated in place.
+int replay_unclean(Session& s, const SeedParams* sp, bool can_replay, u64* unclean_buckets, u64* duplicate_rows);
 
 // single-genome SML (stable): outputs on device in s.keys_*/vals_* ; returns which buffer
 int sml_build_device(Session& s, const char* seq, u64 n, u64 seed, u32* pos_out, u64* mer_out, u32* packed_out, u64* len_out);
+
+#ifdef __CUDACC__
+// ---- probing one diagonal of the two packed genomes (shared by join/extend and the bucket replay) ----
+struct ExtendArgs {
+    const u32* g0;
+    const u32* g1;
+    u64 npos0, npos1;
+    const u32* uniq;
+    u64* cand;          // candidate list p0 | p1 << 32: forward-strand from the front, reverse-strand from the back
+    u64 nfwd, nrev, cap;
+    mcu_match* out;
+    unsigned long long* counters;
+};
+
+__device__ __forceinline__ bool probe_hit(const ExtendArgs& a, const SeedParams& sp, bool rev, i64 d, i64 t, i64& other)
+{
+    if (t < 0 || t >= (i64)a.npos0) return false;
+    other = rev ? d - t : t + d;
+    if (other < 0 || other >= (i64)a.npos1) return false;
+    u64 f0 = extract_seed(load_mer32(a.g0, (u64)t), sp);
+    u64 x1 = extract_seed(load_mer32(a.g1, (u64)other), sp);
+    if (!rev) return f0 == x1;
+    if (f0 != revcomp_seed(x1, sp.w)) return false;
+    return f0 != revcomp_seed(f0, sp.w);
+}
+
+__device__ __forceinline__ bool uniq_bit(const u32* __restrict__ uniq, i64 t) { return (__ldg(uniq + (t >> 5)) >> (t & 31)) & 1u; }
+#endif
 
 }  // namespace mcu

@@ -278,7 +278,7 @@ int mcu_session_download(mcu_session* h, mcu_match* out)
 const void* mcu_session_matches_device(const mcu_session* h) { return h ? h->s.matches.p : nullptr; }
 uint64_t mcu_session_launch_count(const mcu_session* h) { return h ? h->s.launches : 0; }
 
-int mcu_merge_matches(const mcu_match* rows, uint64_t n, int in_device, mcu_match** out, uint64_t* n_out)
+int mcu_merge_matches(const mcu_match* rows, uint64_t n, int in_device, mcu_match** out, uint64_t* n_out, uint64_t* unclean_buckets_out)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     MCU_TRY(ensure_device());
@@ -302,6 +302,14 @@ int mcu_merge_matches(const mcu_match* rows, uint64_t n, int in_device, mcu_matc
     u64 k = 0;
     for (u64 i = 0; i < n; ++i)
         if (k == 0 || r[i].len != r[k - 1].len || r[i].start0 != r[k - 1].start0 || r[i].start1 != r[k - 1].start1) r[k++] = r[i];
+    // buckets the reference would fill order-dependently cannot be replayed from rows alone: report them
+    u64 unclean = 0, dups = 0;
+    if (k) {
+        MCU_CUDA(cudaMemcpyAsync(s->matches.p, r, k * sizeof(mcu_match), cudaMemcpyHostToDevice, s->stream));
+        s->match_count = k;
+        MCU_TRY(replay_unclean(*s, nullptr, false, &unclean, &dups));
+    }
+    if (unclean_buckets_out) *unclean_buckets_out = unclean;
     *out = r;
     *n_out = k;
     return MCU_OK;

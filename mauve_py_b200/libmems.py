@@ -306,8 +306,9 @@ class AnchorSession:
         return int(lib().mcu_session_launch_count(self._h))
 
 
-def merge_matches(rows, in_device=False, n=None):
-    """Rank-0 merge of per-shard match lists (reference list order, duplicates dropped)."""
+def merge_matches(rows, in_device=False, n=None, return_unclean=False):
+    """Rank-0 merge of per-shard match lists (reference list order, duplicates dropped).  With return_unclean also
+    returns the number of order-dependent hash buckets (non-zero -> re-run unsharded for an exact list)."""
     if in_device:
         addr, cnt = rows, n
     else:
@@ -315,11 +316,12 @@ def merge_matches(rows, in_device=False, n=None):
         addr, cnt = rows.ctypes.data, rows.shape[0]
     out = C.POINTER(_capi.Match)()
     n_out = C.c_uint64(0)
-    check(lib().mcu_merge_matches(addr, cnt, 1 if in_device else 0, C.byref(out), C.byref(n_out)))
+    unclean = C.c_uint64(0)
+    check(lib().mcu_merge_matches(addr, cnt, 1 if in_device else 0, C.byref(out), C.byref(n_out), C.byref(unclean)))
     k = n_out.value
     res = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_int64)), shape=(k, 3)).copy() if k else np.zeros((0, 3), dtype=np.int64)
     lib().mcu_free(out)
-    return res
+    return (res, int(unclean.value)) if return_unclean else res
 
 
 # ---- MU/pwpath.h, MU/glbalign.cpp ------------------------------------------------------------------

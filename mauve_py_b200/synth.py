@@ -191,3 +191,24 @@ def hmm_string(n, seed=1, block=400):
         i += k
         homolog = not homolog
     return out.tobytes()
+
+
+def colliding_diagonals_pair(n=120_000, n_copies=150, seed=5, snp=0.01, table=40000):
+    """Pair built to make hash buckets order dependent (csrc/replay.cu): genome 1 = genome 0 with SNPs (main diagonal,
+    offset 0) plus, in a random tail, original 41-bp windows around SNPs placed at offsets that are multiples of the
+    reference's hash-table size, so their matches share bucket 0 with the main diagonal and start inside its spans."""
+    rng = rng_for(seed)
+    a = random_genome(n, 0.5, rng)
+    b = snps(a, snp, rng)
+    diff = np.flatnonzero(a != b)
+    diff = diff[(diff > 100) & (diff < n - 100)]
+    pick = rng.choice(diff, min(n_copies, diff.size), replace=False)
+    tail_len = table * 4
+    tail = random_genome(tail_len, 0.5, rng)
+    base = ((n + table - 1) // table) * table  # first multiple of the table size at or after the end of genome 1
+    for j, x in enumerate(np.sort(pick)):
+        k = int(rng.integers(0, 3))
+        q = (x - 20) + base + k * table - n  # index into the tail: genome-1 position = q + n, diagonal = base + k*table
+        if 0 <= q and q + 41 <= tail_len:
+            tail[q:q + 41] = a[x - 20:x + 21]
+    return a.tobytes(), np.concatenate([b, tail]).tobytes()

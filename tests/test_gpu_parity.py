@@ -258,3 +258,39 @@ def test_hmm_batch_vs_oracle(mp, orc):
     with pytest.raises(mp.McuError) as e:
         mp.run(b"12349", params)
     assert e.value.code == _capi.MCU_EINVAL
+
+
+@pytest.mark.parametrize("w,sd", [(11, 5), (15, 6), (9, 7), (13, 8)])
+def test_mums_order_dependent_buckets(mp, orc, w, sd):
+    """diagonals that collide mod 40000 with interleaved spans: the reference stores some matches twice (csrc/replay.cu)"""
+    a, b = synth.colliding_diagonals_pair(seed=sd)
+    seed = mp.getSeed(w, 0)
+    rows, stats = mp.libmems.find_mums(a, b, seed)
+    orows, ostats = orc.find_mums(a, b, seed, 0)
+    assert orows.shape[0] > np.unique(orows, axis=0).shape[0]  # the reference really duplicates rows here
+    assert int(stats[6]) > 0 and int(stats[7]) == orows.shape[0] - np.unique(orows, axis=0).shape[0]
+    assert np.array_equal(rows, orows)
+    assert int(stats[1]) == int(ostats[1]) and int(stats[2]) == int(ostats[0])
+
+
+def test_merge_reports_order_dependent_buckets(mp):
+    a, b = synth.colliding_diagonals_pair(seed=5)
+    seed = mp.getSeed(11, 0)
+    s = mp.AnchorSession()
+    s.upload(a, b)
+    parts = []
+    for rank in range(2):
+        s.run(seed, rank, 2)
+        parts.append(s.download().copy())
+    s.close()
+    merged, unclean = mp.merge_matches(np.concatenate(parts, axis=0), return_unclean=True)
+    assert unclean > 0
+    full, _ = mp.libmems.find_mums(a, b, seed)
+    assert np.array_equal(np.unique(merged, axis=0), np.unique(full, axis=0))
+    a2, b2 = synth.small_pair(200000, seed=3)
+    s = mp.AnchorSession()
+    s.upload(a2, b2)
+    s.run(seed)
+    merged, unclean = mp.merge_matches(s.download(), return_unclean=True)
+    assert unclean == 0
+    s.close()
