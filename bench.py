@@ -230,7 +230,7 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     launches0 = sess.launch_count()
-    stage = np.zeros(8, dtype=np.float64)
+    stage = np.zeros(16, dtype=np.float64)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.perf_counter()
@@ -284,35 +284,49 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (rs_onesweep_kernel: one radix pass) ------------------------
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------
     peak, peak_src = measured_peaks()
     kb = 4 if 2 * weight + 2 <= 32 else 8
-    passes = int(sess.stage_ms[7])
     nsorted = int(stats[5])
-    bytes_per_launch = 2.0 * (kb + 4) * nsorted
-    sort_ms = float(stage[2])
-    per_launch_ms = sort_ms / max(passes, 1)
-    achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+    bucketed = sess.stage_ms[7] < 0
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "onesweep_traffic.json")
+    prof = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(prof):
         try:
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    # whole-step algorithmic bytes: 1.25 + B_sml(w) + (Kb+4) per base, + 28 B per seed pair
+    if bucketed:
+        # bk_scatter2_kernel: one partition pass over 8-byte records (read 8 B + write 8 B per seed)
+        kname = "bk_scatter2_kernel (level-2 partition pass over %d 8-byte seed records)" % nsorted
+        bytes_per_launch = 16.0 * nsorted
+        per_launch_ms = float(stage[11])
+        launches_per_step = 1
+    else:
+        passes = int(sess.stage_ms[7])
+        kname = "rs_onesweep_kernel (one 8-bit LSD radix pass over %d key/value pairs)" % nsorted
+        bytes_per_launch = 2.0 * (kb + 4) * nsorted
+        per_launch_ms = float(stage[2]) / max(passes, 1)
+        launches_per_step = passes
+    achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+    # whole-step algorithmic bytes (LSD-sort formulation): 1.25 + B_sml(w) + (Kb+4) per base, + 28 B per seed pair
     P = (2 * weight + 1 + 7) // 8
     b_per_base = 1.25 + 0.25 + (kb + 4) + P * 2 * (kb + 4) + (kb + 4)
     step_bytes = b_per_base * nbases + 28.0 * float(stats[0])
+    # bytes the bucketed formulation actually has to move: pack 1.25, records 8 written + 8 + 16 + 8 read/written, 16 + 28 per seed pair
+    b_bucket = 1.25 + 0.5 + 40.0
     dev_ms = float(stage[6])
-    roofline = {"bound": "hbm", "kernel": "rs_onesweep_kernel (one 8-bit LSD radix pass over %d key/value pairs)" % nsorted,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_launch": bytes_per_launch, "launch_ms": per_launch_ms, "launches_per_step": passes,
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "launch_ms": per_launch_ms, "launches_per_step": launches_per_step,
                 "step": {"algorithmic_bytes": step_bytes, "bytes_per_base": b_per_base, "device_ms": dev_ms,
                          "achieved": step_bytes / (dev_ms * 1e-3) / 1e9 if dev_ms > 0 else 0.0,
                          "frac": (step_bytes / (dev_ms * 1e-3) / 1e9 / peak) if dev_ms > 0 else 0.0,
+                         "bucketed_bytes_per_base": b_bucket if bucketed else None,
                          "stage_ms": {"pack": float(stage[0]), "seedgen": float(stage[1]), "sort": float(stage[2]), "join": float(stage[3]),
-                                      "extend": float(stage[4]), "order": float(stage[5])}}}
+                                      "extend": float(stage[4]), "order": float(stage[5])},
+                         "kernel_ms": {"bk_hist1": float(stage[8]), "bk_scatter1": float(stage[9]), "bk_hist2": float(stage[10]),
+                                       "bk_scatter2": float(stage[11]), "bk_group": float(stage[12]), "candidate": float(stage[13]),
+                                       "extend": float(stage[14])}, "spilled_records": float(stage[15])}}
 
     # ---- CPU baseline on a bounded sample ---------------------------------------------------------
     cpu = None

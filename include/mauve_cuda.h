@@ -99,9 +99,12 @@ int mcu_session_create(mcu_session** out);
 void mcu_session_destroy(mcu_session* s);
 /* H2D of both genomes (async on the session stream, then synchronised). */
 int mcu_session_upload(mcu_session* s, const char* seq0, uint64_t n0, const char* seq1, uint64_t n1);
-/* pack + seedgen + sort + join + extend + order on the session stream.  stage_ms (optional,
- * 8 floats, CUDA-event times): [0] pack, [1] seedgen, [2] sort, [3] join, [4] extend,
- * [5] order, [6] total, [7] sort passes run.  Leaves the ordered match list on the device.  */
+/* pack + enumerate + extend + order on the session stream.  stage_ms (optional, 16 floats, CUDA-event
+ * times in ms): [0] pack, [1] seed generation (+ level-1 scatter), [2] sort (or level-2 scatter),
+ * [3] join (or in-bucket grouping), [4] candidates + extend, [5] order + replay, [6] total,
+ * [7] radix passes run (-1: bucketed enumeration, csrc/bucket.cu), per-kernel times: [8] bk_hist1,
+ * [9] bk_scatter1, [10] bk_hist2, [11] bk_scatter2, [12] bk_group, [13] candidate, [14] extend, [15] records spilled to the sort path.
+ * Leaves the ordered match list on the device.                                               */
 int mcu_session_run(mcu_session* s, uint64_t seed, int shard_index, int shard_count,
                     float* stage_ms, uint64_t* stats);
 /* number of matches produced by the last run */

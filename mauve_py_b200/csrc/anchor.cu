@@ -349,9 +349,11 @@ int session_init(Session& s)
     MCU_TRY(ensure_device());
     MCU_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) MCU_CUDA(cudaEventCreate(&s.ev[i]));
+    for (int i = 0; i < 12; ++i) MCU_CUDA(cudaEventCreate(&s.kev[i]));
     MCU_CUDA(cudaHostAlloc((void**)&s.h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     MCU_TRY(s.counters.reserve(8 * sizeof(unsigned long long)));
     MCU_CUDA(cudaHostAlloc((void**)&s.h_replay, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    s.use_buckets = getenv("MAUVE_CUDA_SORT_PATH") == nullptr;
     s.ok = true;
     return MCU_OK;
 }
@@ -364,9 +366,11 @@ void session_destroy(Session& s)
                       &s.uniq, &s.pairs, &s.cand, &s.raw_matches, &s.ord_keys_a, &s.ord_keys_b, &s.ord_vals_a, &s.ord_vals_b,
                       &s.matches, &s.ord_primary, &s.counters, &s.radix.hist, &s.radix.status, &s.radix.counters,
                       &s.rp_ctr, &s.rp_bitmap, &s.rp_list, &s.rp_canon, &s.rp_keys_b, &s.rp_idx_a, &s.rp_idx_b, &s.rp_p0, &s.rp_row, &s.rp_bkeys,
-                      &s.rp_pool, &s.rp_extra, &s.rp_prefix, &s.rp_vinfo, &s.rp_out};
+                      &s.rp_pool, &s.rp_extra, &s.rp_prefix, &s.rp_vinfo, &s.rp_out,
+                      &s.bk_a, &s.bk_b, &s.bk_tab1, &s.bk_tab2, &s.bk_spill};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(s.ev[i]);
+    for (int i = 0; i < 12; ++i) cudaEventDestroy(s.kev[i]);
     if (s.h_counters) cudaFreeHost(s.h_counters);
     if (s.h_replay) cudaFreeHost(s.h_replay);
     cudaStreamDestroy(s.stream);
@@ -415,63 +419,69 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
     for (int g = 0; g < 2; ++g) MCU_TRY(run_pack(s, g, (u32*)(ctr + 4)));
     MCU_CUDA(cudaEventRecord(s.ev[1], s.stream));
 
-    // ---- seedgen ----
-    MCU_TRY(s.keys_a.reserve((ntot + 1) * sizeof(K)));
-    MCU_TRY(s.keys_b.reserve((ntot + 1) * sizeof(K)));
-    MCU_TRY(s.vals_a.reserve((ntot + 1) * sizeof(u32)));
-    MCU_TRY(s.vals_b.reserve((ntot + 1) * sizeof(u32)));
-    MCU_TRY(radix_clear_hist(s.radix, s.stream));
-    u64 canon_lo = 0, canon_hi = ~0ull;
-    if (sharded) {
-        // equal slices of the canonical key space [0, 4^w)
-        const int kb = 2 * sp.w;
-        auto edge = [&](int i) -> u64 {
-            if (i >= shard_count) return kb >= 64 ? ~0ull : (1ull << kb);
-            unsigned __int128 span = kb >= 64 ? ((unsigned __int128)1 << 64) : ((unsigned __int128)1 << kb);
-            return (u64)(span * (unsigned)i / (unsigned)shard_count);
-        };
-        canon_lo = edge(shard_index);
-        canon_hi = edge(shard_index + 1);
-    }
-    const u64 npos[2] = {npos0, npos1};
-    u64 base = 0;
-    for (int g = 0; g < 2; ++g) {
-        if (npos[g]) {
-            seedgen_kernel<K><<<grid_for(npos[g], 256, 8), 256, passes * 256 * sizeof(u32), s.stream>>>(
-                s.packed[g].as<u32>(), npos[g], sp, (u32)g, s.keys_a.as<K>(), s.vals_a.as<u32>(), sharded ? 0 : base,
-                s.radix.hist.as<u64>(), passes, sharded ? 1 : 0, canon_lo, canon_hi, ctr + 5);
-            s.launches++;
-        }
-        base += npos[g];
-    }
-    u64 nsort = ntot;
-    if (sharded) {
-        MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
-        MCU_CUDA(cudaStreamSynchronize(s.stream));
-        nsort = s.h_counters[5];
-    }
-    MCU_CUDA(cudaEventRecord(s.ev[2], s.stream));
-
-    // ---- sort ----
-    bool in_a = true;
-    int passes_run = 0;
-    u64 before = s.radix.launches;
-    MCU_TRY(radix_sort_pairs<K>(s.radix, s.keys_a.as<K>(), s.vals_a.as<u32>(), s.keys_b.as<K>(), s.vals_b.as<u32>(), nsort, key_bits, true,
-                                s.stream, &in_a, &passes_run));
-    s.launches += s.radix.launches - before;
-    const K* skeys = in_a ? s.keys_a.as<K>() : s.keys_b.as<K>();
-    const u32* svals = in_a ? s.vals_a.as<u32>() : s.vals_b.as<u32>();
-    MCU_CUDA(cudaEventRecord(s.ev[3], s.stream));
-
-    // ---- join ----
+    // ---- enumerate unique seed pairs: uniq bitmap + pair list ----
     const u64 pair_cap = (npos0 < npos1 ? npos0 : npos1) + 1;
     const u64 uniq_words = div_up(npos0 + 1, 32) + 1;
     MCU_TRY(s.uniq.reserve(uniq_words * sizeof(u32)));
     MCU_TRY(s.pairs.reserve(pair_cap * sizeof(u64)));
     MCU_CUDA(cudaMemsetAsync(s.uniq.p, 0, uniq_words * sizeof(u32), s.stream));
-    if (nsort) {
-        join_kernel<K><<<(unsigned)div_up(nsort, 256 * 8), 256, 0, s.stream>>>(skeys, svals, nsort, s.uniq.as<u32>(), s.pairs.as<u64>(), pair_cap, ctr);
-        s.launches++;
+    bool bucketed = false;
+    u64 nsort = ntot;
+    int passes_run = 0;
+    s.bk_spilled = 0;
+    if (s.use_buckets) MCU_TRY(bucket_group(s, sp, shard_index, shard_count, pair_cap, s.ev[2], s.ev[3], &bucketed, &nsort));
+    if (!bucketed) {
+        // ---- seedgen ----
+        MCU_TRY(s.keys_a.reserve((ntot + 1) * sizeof(K)));
+        MCU_TRY(s.keys_b.reserve((ntot + 1) * sizeof(K)));
+        MCU_TRY(s.vals_a.reserve((ntot + 1) * sizeof(u32)));
+        MCU_TRY(s.vals_b.reserve((ntot + 1) * sizeof(u32)));
+        MCU_TRY(radix_clear_hist(s.radix, s.stream));
+        u64 canon_lo = 0, canon_hi = ~0ull;
+        if (sharded) {
+            // equal slices of the canonical key space [0, 4^w)
+            const int kb = 2 * sp.w;
+            auto edge = [&](int i) -> u64 {
+                if (i >= shard_count) return kb >= 64 ? ~0ull : (1ull << kb);
+                unsigned __int128 span = kb >= 64 ? ((unsigned __int128)1 << 64) : ((unsigned __int128)1 << kb);
+                return (u64)(span * (unsigned)i / (unsigned)shard_count);
+            };
+            canon_lo = edge(shard_index);
+            canon_hi = edge(shard_index + 1);
+        }
+        const u64 npos[2] = {npos0, npos1};
+        u64 base = 0;
+        for (int g = 0; g < 2; ++g) {
+            if (npos[g]) {
+                seedgen_kernel<K><<<grid_for(npos[g], 256, 8), 256, passes * 256 * sizeof(u32), s.stream>>>(
+                    s.packed[g].as<u32>(), npos[g], sp, (u32)g, s.keys_a.as<K>(), s.vals_a.as<u32>(), sharded ? 0 : base,
+                    s.radix.hist.as<u64>(), passes, sharded ? 1 : 0, canon_lo, canon_hi, ctr + 5);
+                s.launches++;
+            }
+            base += npos[g];
+        }
+        if (sharded) {
+            MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+            MCU_CUDA(cudaStreamSynchronize(s.stream));
+            nsort = s.h_counters[5];
+        }
+        MCU_CUDA(cudaEventRecord(s.ev[2], s.stream));
+
+        // ---- sort ----
+        bool in_a = true;
+        u64 before = s.radix.launches;
+        MCU_TRY(radix_sort_pairs<K>(s.radix, s.keys_a.as<K>(), s.vals_a.as<u32>(), s.keys_b.as<K>(), s.vals_b.as<u32>(), nsort, key_bits, true,
+                                    s.stream, &in_a, &passes_run));
+        s.launches += s.radix.launches - before;
+        const K* skeys = in_a ? s.keys_a.as<K>() : s.keys_b.as<K>();
+        const u32* svals = in_a ? s.vals_a.as<u32>() : s.vals_b.as<u32>();
+        MCU_CUDA(cudaEventRecord(s.ev[3], s.stream));
+
+        // ---- join ----
+        if (nsort) {
+            join_kernel<K><<<(unsigned)div_up(nsort, 256 * 8), 256, 0, s.stream>>>(skeys, svals, nsort, s.uniq.as<u32>(), s.pairs.as<u64>(), pair_cap, ctr);
+            s.launches++;
+        }
     }
     MCU_CUDA(cudaEventRecord(s.ev[4], s.stream));
 
@@ -491,8 +501,10 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
         ea.uniq = s.uniq.as<u32>();
         ea.cand = s.cand.as<u64>(); ea.nfwd = 0; ea.nrev = 0; ea.cap = npairs;
         ea.out = nullptr; ea.counters = ctr;
+        MCU_CUDA(cudaEventRecord(s.kev[6], s.stream));
         candidate_kernel<<<grid_for(npairs, 256, 8), 256, 0, s.stream>>>(ea, sp, s.pairs.as<u64>(), pfwd, prev_, pair_cap);
         s.launches++;
+        MCU_CUDA(cudaEventRecord(s.kev[7], s.stream));
         MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
         MCU_CUDA(cudaStreamSynchronize(s.stream));
         ea.nfwd = s.h_counters[2]; ea.nrev = s.h_counters[7];
@@ -501,6 +513,7 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
         ea.out = s.raw_matches.as<mcu_match>();
         extend_kernel<<<grid_for(ncand * 32, 256, 8), 256, 0, s.stream>>>(ea, sp);
         s.launches++;
+        MCU_CUDA(cudaEventRecord(s.kev[8], s.stream));
         MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
         MCU_CUDA(cudaStreamSynchronize(s.stream));
         nmatch = s.h_counters[3];
@@ -519,12 +532,30 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
     if (stage_ms) {
         for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&stage_ms[i], s.ev[i], s.ev[i + 1]);
         cudaEventElapsedTime(&stage_ms[6], s.ev[0], s.ev[6]);
-        stage_ms[7] = (float)passes_run;
+        stage_ms[7] = bucketed ? -1.0f : (float)passes_run;
+        for (int i = 8; i < 16; ++i) stage_ms[i] = 0.f;
+        stage_ms[15] = (float)s.bk_spilled;
+        if (bucketed)
+            for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&stage_ms[8 + i], s.kev[i], s.kev[i + 1]);
+        if (npairs) {
+            cudaEventElapsedTime(&stage_ms[13], s.kev[6], s.kev[7]);
+            if (ncand) cudaEventElapsedTime(&stage_ms[14], s.kev[7], s.kev[8]);
+        }
     }
     if (stats) {
         stats[0] = npairs; stats[1] = nmatch; stats[2] = npairs - nmatch; stats[3] = repeat_flag;
         stats[4] = ncand; stats[5] = nsort; stats[6] = unclean; stats[7] = dup_rows;
     }
+    return MCU_OK;
+}
+
+int join_sorted_u64(Session& s, const u64* keys, const u32* vals, u64 n, u64 pair_cap)
+{
+    if (!n) return MCU_OK;
+    join_kernel<u64><<<(unsigned)div_up(n, 256 * 8), 256, 0, s.stream>>>(keys, vals, n, s.uniq.as<u32>(), s.pairs.as<u64>(), pair_cap,
+                                                                        s.counters.as<unsigned long long>());
+    s.launches++;
+    MCU_CUDA(cudaGetLastError());
     return MCU_OK;
 }
 

@@ -8,9 +8,13 @@ namespace mcu {
 struct Session {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t kev[12] = {};  // per-kernel marks: 0 start, 1 hist1, 2 scatter1, 3 hist2, 4 scatter2, 5 group, 6/7 candidate, 8 extend
     DevBuf ascii[2], packed[2];
     DevBuf keys_a, keys_b, vals_a, vals_b;
     DevBuf uniq, pairs, cand, raw_matches, ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b, ord_primary, matches, counters;
+    // bucketed enumeration (bucket.cu)
+    DevBuf bk_a, bk_b, bk_tab1, bk_tab2, bk_spill;
+    u64 bk_spilled = 0;
     // bucket replay (replay.cu)
     DevBuf rp_ctr, rp_bitmap, rp_list, rp_canon, rp_keys_b, rp_idx_a, rp_idx_b, rp_p0, rp_row, rp_bkeys, rp_pool, rp_extra, rp_prefix, rp_vinfo, rp_out;
     unsigned long long* h_replay = nullptr;  // pinned, 8 entries
@@ -20,6 +24,7 @@ struct Session {
     u64 launches = 0;
     unsigned long long* h_counters = nullptr;  // pinned, 8 entries
     bool ok = false;
+    bool use_buckets = true;  // MAUVE_CUDA_SORT_PATH=1 forces the radix-sort + join enumeration
 };
 
 int session_init(Session& s);
@@ -28,6 +33,11 @@ int session_upload(Session& s, const char* seq0, u64 n0, const char* seq1, u64 n
 int session_run(Session& s, u64 seed, int shard_index, int shard_count, float* stage_ms, u64* stats);
 // sorts rows (device, n of them) into reference list order; result in s.matches (device)
 int order_matches(Session& s, const mcu_match* rows_dev, u64 n);
+// join of an already sorted (key, position) array of 64-bit keys: appends to s.uniq / s.pairs / counters (anchor.cu)
+int join_sorted_u64(Session& s, const u64* keys, const u32* vals, u64 n, u64 pair_cap);
+// bucketed seed-match enumeration (bucket.cu); *used == false when the plan does not apply (caller sorts instead)
+int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_count, u64 pair_cap, cudaEvent_t ev_scatter1, cudaEvent_t ev_scatter2,
+                 bool* used, u64* nrecords);
 // Looks for hash buckets whose content depends on the reference's insertion order (replay.cu) and, when `can_replay`
 // (genomes + unique-seed bitmap of the whole key space are in the session), replays those buckets exactly.
 // s.matches / s.match_count are updated in place.

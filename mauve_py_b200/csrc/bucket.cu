@@ -1,0 +1,667 @@
+// Bucketed seed-match enumeration (sm_100a): the B200-first replacement of "sort both mer lists, then merge".
+//
+// MatchFinder::SearchRange (LM/MatchFinder.cpp:172-340) only needs EQUAL mers of the two genomes to meet; the
+// total order std::sort produces (LM/MemorySML.cpp:54) is needed by MemorySML::Read, not by match finding.
+// So instead of P = ceil((2w+2)/8) full LSD passes over (key, position) pairs (2(Kb+4) bytes/pair/pass), the
+// seeds are PARTITIONED by the top T bits of the canonical mer (two scatter passes of d1 and d2 bits over
+// 8-byte records) into ~2^T buckets of ~2k records, and every bucket is finished inside one CTA in shared
+// memory (counting split on the next 8 bits, then warp-level match.any on the remaining key bits):
+//
+//   bk_hist1     count canonical mers per level-1 bucket          reads packed genomes only (25 MB @100 Mbp)
+//   bk_scan1     offsets + this rank's bucket range (sharding by exact counts, identical on every rank)
+//   bk_scatter1  recompute the mer, build the 8-byte record, scatter by level-1 digit      8 B/seed written
+//   bk_hist2     per level-1 bucket: count level-2 digits                                  8 B/seed read
+//   bk_scan2     exclusive scan of the (bucket, digit) table
+//   bk_scatter2  scatter by level-2 digit                                                  8 + 8 B/seed
+//   bk_group     one CTA per final bucket: unique-in-both keys -> uniq bitmap + pair list  8 B/seed + 8 B/pair
+//
+// 40 B/seed instead of 12 + 5*24 + 12 = 144 B/seed (w = 19): the path is HBM-bound, so this is the lever.
+// record = keyrem(2w - d1 bits) | strand | genome | position(pbits); the top d1 key bits are implied by the
+// bucket.  Scatter passes are unordered (atomic cursors, no look-back chain): grouping needs no stability.
+// Buckets that do not fit shared memory (low-complexity sequence) are spilled to the radix-sort + join path
+// (radix.cuh / join_kernel), which handles any size; plans that do not fit 64-bit records use that path too.
+// Output is identical to join_kernel's: uniq bitmap, pairs (forward from the front / reverse from the back),
+// counters[0]/[6] pair counts, counters[1] MER_REPEAT_LIMIT flag.
+#include "anchor.cuh"
+
+namespace mcu {
+
+constexpr int BK_THREADS = 256;
+constexpr int BK_IPT = 16;
+constexpr int BK_TILE = BK_THREADS * BK_IPT;   // records per scatter tile
+constexpr int BK_SUPER = 16 * BK_TILE;         // records per histogram block iteration
+constexpr int BK_CAP = 4096;                   // largest final bucket finished in shared memory
+constexpr int BK_MAXB = 2048;                  // max bins per level
+constexpr int BK_D3 = 11;
+
+struct BkPlan {
+    int kbits, d1, d2, d3, pbits, rem1;
+    u32 B1, B2;
+    u64 npos0, npos1, ntot;
+    u64 npad0, nidx;  // genome-0 positions padded to a multiple of 16 so that a thread's 16 consecutive positions share 3 packed words
+};
+
+struct BkMeta {  // written by bk_scan1_kernel
+    u32 b_lo, b_hi;
+    u64 nrec;    // records of this rank
+    u64 nfinal;  // (b_hi - b_lo) * B2
+};
+
+// Canonical mers are far from uniform (min(f, rc) piles up at small values, base composition skews the
+// leading bases), and only EQUALITY of mers matters here, so buckets are cut on a bijective mix of the
+// canonical mer (xorshift, odd multiply, xorshift on 2w bits): bucket sizes become Poisson-tight whatever the
+// genome looks like; identical mers still share a bucket.
+__device__ __forceinline__ u64 bk_mix(u64 x, int kbits)
+{
+    const u64 mask = kbits >= 64 ? ~0ull : ((1ull << kbits) - 1);
+    const int sh = kbits / 2 + 1;
+    x ^= x >> sh;
+    x = (x * 0x9E3779B97F4A7C15ull) & mask;
+    x ^= x >> sh;
+    x = (x * 0xD6E8FEB86659FD93ull) & mask;
+    x ^= x >> sh;
+    return x;
+}
+
+__device__ __forceinline__ void seed_canon32(u64 mer32, const SeedParams& sp, u64& key, u32& strand)
+{
+    const u64 f = extract_seed(mer32, sp);
+    const u64 rc = revcomp_seed(f, sp.w);
+    strand = rc < f;  // GetDnaSeedMer: forward wins ties
+    key = bk_mix(strand ? rc : f, 2 * sp.w);
+}
+
+// 16 consecutive positions starting at a multiple of 16 read the same three packed words
+struct BkWindow {
+    u64 hi;
+    u32 lo;
+    __device__ __forceinline__ void load(const u32* __restrict__ packed, u64 pos16)
+    {
+        const u64 k = pos16 >> 4;
+        hi = ((u64)__ldg(packed + k) << 32) | __ldg(packed + k + 1);
+        lo = __ldg(packed + k + 2);
+    }
+    __device__ __forceinline__ u64 mer(int j) const { return j ? ((hi << (2 * j)) | ((u64)lo >> (32 - 2 * j))) : hi; }
+};
+
+// ---- level 1 ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BK_THREADS) bk_hist1_kernel(const u32* __restrict__ g0, const u32* __restrict__ g1, BkPlan pl, SeedParams sp,
+                                                             unsigned long long* __restrict__ count1)
+{
+    extern __shared__ u32 sh[];
+    for (u32 i = threadIdx.x; i < pl.B1; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const u64 ngroups = pl.nidx >> 4;
+    for (u64 grp = (u64)blockIdx.x * blockDim.x + threadIdx.x; grp < ngroups; grp += (u64)gridDim.x * blockDim.x) {
+        const u64 idx = grp << 4;
+        const bool g = idx >= pl.npad0;
+        const u64 pos = g ? idx - pl.npad0 : idx, npos = g ? pl.npos1 : pl.npos0;
+        BkWindow w;
+        w.load(g ? g1 : g0, pos);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (pos + j < npos) {
+                u64 canon;
+                u32 strand;
+                seed_canon32(w.mer(j), sp, canon, strand);
+                atomicAdd(&sh[(u32)(canon >> pl.rem1)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < pl.B1; i += blockDim.x)
+        if (sh[i]) atomicAdd(&count1[i], (unsigned long long)sh[i]);
+}
+
+// offsets of the level-1 buckets of this rank.  Rank r owns the buckets [e_r, e_{r+1}) with e_i = first bucket
+// whose cumulative count reaches total*i/R: every rank derives the same edges from the same genomes.
+__global__ void bk_scan1_kernel(const unsigned long long* __restrict__ count1, BkPlan pl, int shard, int nshard, u64* __restrict__ off1,
+                                unsigned long long* __restrict__ cursor1, BkMeta* __restrict__ meta)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    u64 total = 0;
+    for (u32 b = 0; b < pl.B1; ++b) total += count1[b];
+    u32 edge_lo = 0, edge_hi = pl.B1;
+    if (nshard > 1) {
+        const u64 t_lo = (u64)((unsigned __int128)total * (unsigned)shard / (unsigned)nshard);
+        const u64 t_hi = (u64)((unsigned __int128)total * (unsigned)(shard + 1) / (unsigned)nshard);
+        u64 cum = 0;
+        bool have_lo = false, have_hi = false;
+        for (u32 b = 0; b < pl.B1; ++b) {
+            if (!have_lo && cum >= t_lo) { edge_lo = b; have_lo = true; }
+            if (!have_hi && cum >= t_hi) { edge_hi = b; have_hi = true; }
+            cum += count1[b];
+        }
+        if (!have_lo) edge_lo = pl.B1;
+        if (!have_hi || shard + 1 == nshard) edge_hi = pl.B1;
+        if (shard == 0) edge_lo = 0;
+    }
+    u64 run = 0;
+    for (u32 b = 0; b < pl.B1; ++b) {
+        off1[b] = run;
+        cursor1[b] = run;
+        if (b >= edge_lo && b < edge_hi) run += count1[b];
+    }
+    off1[pl.B1] = run;
+    meta->b_lo = edge_lo;
+    meta->b_hi = edge_hi;
+    meta->nrec = run;
+    meta->nfinal = (u64)(edge_hi - edge_lo) * pl.B2;
+}
+
+// Shared scatter machinery: every thread holds up to IPT (record, bin) items of a tile; ranks come from
+// shared-memory atomics, one global reservation per (tile, bin), then the tile is staged bin-major in shared
+// memory and streamed out so that consecutive threads write consecutive addresses inside a bin run.
+struct BkScatterSmem {
+    u64* stage;        // [BK_TILE]
+    unsigned short* sbin;  // [BK_TILE]
+    u32* cnt;          // [bins]
+    u32* sofs;         // [bins]
+    u64* gbase;        // [bins]
+    u32* warp_tot;     // [8]
+};
+
+__device__ __forceinline__ BkScatterSmem bk_carve(unsigned char* raw, u32 bins)
+{
+    BkScatterSmem s;
+    s.stage = (u64*)raw;
+    s.gbase = (u64*)(raw + (size_t)BK_TILE * 8);
+    s.cnt = (u32*)(raw + (size_t)BK_TILE * 8 + (size_t)bins * 8);
+    s.sofs = s.cnt + bins;
+    s.warp_tot = s.sofs + bins;
+    s.sbin = (unsigned short*)(s.warp_tot + 8);
+    return s;
+}
+
+static size_t bk_scatter_smem_bytes(u32 bins) { return (size_t)BK_TILE * 8 + (size_t)bins * 16 + 32 + (size_t)BK_TILE * 2; }
+
+// After cnt[] holds the tile's bin counts: reserve global space, compute the bin-major staging offsets.
+__device__ __forceinline__ void bk_reserve(const BkScatterSmem& s, u32 bins, unsigned long long* __restrict__ cursor)
+{
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // exclusive scan of cnt over `bins` entries (bins <= 2048 = 8 per thread)
+    const u32 per = (bins + BK_THREADS - 1) / BK_THREADS;
+    u32 local = 0;
+    for (u32 j = 0; j < per; ++j) {
+        const u32 b = tid * per + j;
+        if (b < bins) local += s.cnt[b];
+    }
+    u32 incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (u32)o) incl += t;
+    }
+    if (lane == 31) s.warp_tot[warp] = incl;
+    __syncthreads();
+    u32 add = 0;
+    for (u32 w = 0; w < warp; ++w) add += s.warp_tot[w];
+    u32 run = incl - local + add;
+    for (u32 j = 0; j < per; ++j) {
+        const u32 b = tid * per + j;
+        if (b < bins) {
+            const u32 c = s.cnt[b];
+            s.sofs[b] = run;
+            run += c;
+            if (c) s.gbase[b] = atomicAdd(&cursor[b], (unsigned long long)c);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void bk_flush(const BkScatterSmem& s, u32 ntile, u64* __restrict__ out)
+{
+    for (u32 j = threadIdx.x; j < ntile; j += BK_THREADS) {
+        const u32 b = s.sbin[j];
+        out[s.gbase[b] + (j - s.sofs[b])] = s.stage[j];
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter1_kernel(const u32* __restrict__ g0, const u32* __restrict__ g1, BkPlan pl, SeedParams sp,
+                                                                   const BkMeta* __restrict__ meta, unsigned long long* __restrict__ cursor1,
+                                                                   u64* __restrict__ recs)
+{
+    extern __shared__ __align__(16) unsigned char raw[];
+    const BkScatterSmem s = bk_carve(raw, pl.B1);
+    const u32 tid = threadIdx.x;
+    const u32 b_lo = meta->b_lo, b_hi = meta->b_hi;
+    for (u32 i = tid; i < pl.B1; i += BK_THREADS) s.cnt[i] = 0;
+    __syncthreads();
+    const u64 idx0 = (u64)blockIdx.x * BK_TILE + (u64)tid * BK_IPT;  // 16 consecutive positions per thread
+    u64 rec[BK_IPT];
+    u32 br[BK_IPT];  // bin << 16 | rank   (rank < BK_TILE = 4096)
+    {
+        const u32 g = idx0 >= pl.npad0;
+        const u64 pos = g ? idx0 - pl.npad0 : idx0, npos = g ? pl.npos1 : pl.npos0;
+        BkWindow w;
+        if (idx0 < pl.nidx) w.load(g ? g1 : g0, pos);
+#pragma unroll
+        for (int it = 0; it < BK_IPT; ++it) {
+            br[it] = 0xffffffffu;
+            if (idx0 < pl.nidx && pos + it < npos) {
+                u64 canon;
+                u32 strand;
+                seed_canon32(w.mer(it), sp, canon, strand);
+                const u32 b = (u32)(canon >> pl.rem1);
+                if (b >= b_lo && b < b_hi) {
+                    const u64 keyrem = canon & ((1ull << pl.rem1) - 1);
+                    rec[it] = (keyrem << (pl.pbits + 2)) | ((u64)strand << (pl.pbits + 1)) | ((u64)g << pl.pbits) | (pos + it);
+                    br[it] = (b << 16) | atomicAdd(&s.cnt[b], 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    bk_reserve(s, pl.B1, cursor1);
+    u32 ntile = 0;
+#pragma unroll
+    for (int it = 0; it < BK_IPT; ++it) {
+        if (br[it] != 0xffffffffu) {
+            const u32 b = br[it] >> 16, slot = s.sofs[b] + (br[it] & 0xffffu);
+            s.stage[slot] = rec[it];
+            s.sbin[slot] = (unsigned short)b;
+        }
+    }
+    // tile population = sofs of the last bin + its count
+    ntile = s.sofs[pl.B1 - 1] + s.cnt[pl.B1 - 1];
+    __syncthreads();
+    bk_flush(s, ntile, recs);
+}
+
+// ---- level 2 ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 bk_segment_of(const u64* __restrict__ off1, u32 B1, u64 i)
+{
+    u32 lo = 0, hi = B1;  // off1[lo] <= i < off1[hi]
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if (off1[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(BK_THREADS) bk_hist2_kernel(const u64* __restrict__ recs, BkPlan pl, const BkMeta* __restrict__ meta,
+                                                             const u64* __restrict__ off1, unsigned long long* __restrict__ count2)
+{
+    extern __shared__ u32 sh[];
+    const u64 nrec = meta->nrec;
+    const u32 b_lo = meta->b_lo;
+    const int shift = pl.pbits + 2 + pl.rem1 - pl.d2;
+    for (u64 base = (u64)blockIdx.x * BK_SUPER; base < nrec; base += (u64)gridDim.x * BK_SUPER) {
+        const u64 end = min(base + (u64)BK_SUPER, nrec);
+        u64 i0 = base;
+        while (i0 < end) {
+            const u32 seg = bk_segment_of(off1, pl.B1, i0);
+            const u64 i1 = min(end, off1[seg + 1]);
+            for (u32 i = threadIdx.x; i < pl.B2; i += blockDim.x) sh[i] = 0;
+            __syncthreads();
+            for (u64 i = i0 + threadIdx.x; i < i1; i += blockDim.x) atomicAdd(&sh[(u32)(recs[i] >> shift) & (pl.B2 - 1)], 1u);
+            __syncthreads();
+            unsigned long long* dst = count2 + (u64)(seg - b_lo) * pl.B2;
+            for (u32 i = threadIdx.x; i < pl.B2; i += blockDim.x)
+                if (sh[i]) atomicAdd(&dst[i], (unsigned long long)sh[i]);
+            __syncthreads();
+            i0 = i1;
+        }
+    }
+}
+
+// exclusive scan of count2[0 .. nfinal) -> off2 (nfinal + 1 entries) and the scatter cursors; one block
+__global__ void __launch_bounds__(1024) bk_scan2_kernel(const unsigned long long* __restrict__ count2, const BkMeta* __restrict__ meta,
+                                                       u64* __restrict__ off2, unsigned long long* __restrict__ cursor2)
+{
+    __shared__ u64 s_tot[1024];
+    const u64 n = meta->nfinal;
+    const u64 per = (n + 1023) / 1024;
+    const u32 t = threadIdx.x;
+    const u64 lo = min(n, (u64)t * per), hi = min(n, lo + per);
+    u64 local = 0;
+    for (u64 i = lo; i < hi; ++i) local += count2[i];
+    s_tot[t] = local;
+    __syncthreads();
+    if (t == 0) {
+        u64 run = 0;
+        for (u32 i = 0; i < 1024; ++i) { const u64 v = s_tot[i]; s_tot[i] = run; run += v; }
+        off2[n] = run;
+    }
+    __syncthreads();
+    u64 run = s_tot[t];
+    for (u64 i = lo; i < hi; ++i) {
+        off2[i] = run;
+        cursor2[i] = run;
+        run += count2[i];
+    }
+}
+
+__global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter2_kernel(const u64* __restrict__ src, BkPlan pl, const BkMeta* __restrict__ meta,
+                                                                   const u64* __restrict__ off1, unsigned long long* __restrict__ cursor2,
+                                                                   u64* __restrict__ dst)
+{
+    extern __shared__ __align__(16) unsigned char raw[];
+    const BkScatterSmem s = bk_carve(raw, pl.B2);
+    const u32 tid = threadIdx.x;
+    const u64 nrec = meta->nrec;
+    const u32 b_lo = meta->b_lo;
+    const int shift = pl.pbits + 2 + pl.rem1 - pl.d2;
+    const u64 base = (u64)blockIdx.x * BK_TILE;
+    if (base >= nrec) return;
+    const u64 end = min(base + (u64)BK_TILE, nrec);
+    u64 i0 = base;
+    while (i0 < end) {  // one iteration unless the tile straddles level-1 buckets
+        const u32 seg = bk_segment_of(off1, pl.B1, i0);
+        const u64 i1 = min(end, off1[seg + 1]);
+        for (u32 i = tid; i < pl.B2; i += BK_THREADS) s.cnt[i] = 0;
+        __syncthreads();
+        u64 rec[BK_IPT];
+        u32 br[BK_IPT];
+#pragma unroll
+        for (int it = 0; it < BK_IPT; ++it) {
+            const u64 i = i0 + (u64)it * BK_THREADS + tid;
+            br[it] = 0xffffffffu;
+            if (i < i1) {
+                rec[it] = src[i];
+                const u32 b = (u32)(rec[it] >> shift) & (pl.B2 - 1);
+                br[it] = (b << 16) | atomicAdd(&s.cnt[b], 1u);
+            }
+        }
+        __syncthreads();
+        bk_reserve(s, pl.B2, cursor2 + (u64)(seg - b_lo) * pl.B2);
+#pragma unroll
+        for (int it = 0; it < BK_IPT; ++it) {
+            if (br[it] != 0xffffffffu) {
+                const u32 b = br[it] >> 16, slot = s.sofs[b] + (br[it] & 0xffffu);
+                s.stage[slot] = rec[it];
+                s.sbin[slot] = (unsigned short)b;
+            }
+        }
+        __syncthreads();
+        bk_flush(s, (u32)(i1 - i0), dst);
+        __syncthreads();
+        i0 = i1;
+    }
+}
+
+// ---- final buckets ------------------------------------------------------------------------------------------
+struct BkGroupArgs {
+    const u64* recs;
+    const u64* off2;
+    const BkMeta* meta;
+    u32* uniq;
+    u64* pairs;
+    u64 pair_cap;
+    unsigned long long* counters;  // [0] fwd pairs, [1] repeat flag, [6] rev pairs
+    u32* spill_list;               // final buckets larger than BK_CAP
+    unsigned long long* spill;     // [0] buckets, [1] records
+};
+
+constexpr int BK_GIPT = BK_CAP / BK_THREADS;  // staged records per thread in bk_group
+
+__global__ void __launch_bounds__(BK_THREADS, 4) bk_group_kernel(BkGroupArgs a, BkPlan pl)
+{
+    __shared__ u64 stage[BK_CAP];
+    __shared__ u32 sofs[(1 << BK_D3) + 1];  // bin counts first, exclusive offsets after the scan
+    __shared__ u32 s_warp[2][8];
+    __shared__ unsigned long long s_base[2];
+    const u64 f = blockIdx.x;
+    if (f >= a.meta->nfinal) return;
+    const u64 beg = a.off2[f];
+    const u32 nb = (u32)(a.off2[f + 1] - beg);
+    if (nb == 0) return;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (nb > BK_CAP) {
+        if (tid == 0) {
+            a.spill_list[atomicAdd(&a.spill[0], 1ull)] = (u32)f;
+            atomicAdd(&a.spill[1], (unsigned long long)nb);
+        }
+        return;
+    }
+    const int kshift = pl.pbits + 2;
+    const u32 nsub = 1u << pl.d3;
+    const int dshift = kshift + pl.rem1 - pl.d2 - pl.d3;
+    const u64 posmask = (1ull << pl.pbits) - 1;
+    for (u32 i = tid; i <= nsub; i += BK_THREADS) sofs[i] = 0;
+    __syncthreads();
+    // counting split on the next d3 key bits: sub-groups of ~1 record, all records of one key in one sub-group
+    u64 rec[BK_GIPT];
+    u32 br[BK_GIPT];
+#pragma unroll
+    for (int it = 0; it < BK_GIPT; ++it) {
+        const u32 i = it * BK_THREADS + tid;
+        br[it] = 0xffffffffu;
+        if (i < nb) {
+            rec[it] = a.recs[beg + i];
+            const u32 b = (u32)(rec[it] >> dshift) & (nsub - 1);
+            br[it] = (b << 16) | atomicAdd(&sofs[b], 1u);
+        }
+    }
+    __syncthreads();
+    {   // exclusive scan of the counts in place: thread t owns bins [t*per, (t+1)*per)
+        const u32 per = (nsub + BK_THREADS - 1) / BK_THREADS;
+        u32 local = 0;
+        for (u32 j = 0; j < per; ++j) {
+            const u32 b = tid * per + j;
+            if (b < nsub) local += sofs[b];
+        }
+        u32 incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (u32)o) incl += t;
+        }
+        if (lane == 31) s_warp[0][warp] = incl;
+        __syncthreads();
+        u32 add = 0;
+        for (u32 w = 0; w < warp; ++w) add += s_warp[0][w];
+        u32 run = incl - local + add;
+        for (u32 j = 0; j < per; ++j) {
+            const u32 b = tid * per + j;
+            if (b < nsub) { const u32 c = sofs[b]; sofs[b] = run; run += c; }
+        }
+        if (tid == BK_THREADS - 1) sofs[nsub] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < BK_GIPT; ++it)
+        if (br[it] != 0xffffffffu) stage[sofs[br[it] >> 16] + (br[it] & 0xffffu)] = rec[it];
+    __syncthreads();
+    // record-centric: every genome-0 record scans its own sub-group; unique in both genomes -> pair (kept in registers)
+    u32 fmask = 0, rmask = 0, repeat = 0;
+#pragma unroll
+    for (int it = 0; it < BK_GIPT; ++it) {
+        if (br[it] == 0xffffffffu) continue;
+        const u64 r = rec[it];
+        if ((r >> pl.pbits) & 1) continue;
+        const u32 b = br[it] >> 16;
+        const u32 s0 = sofs[b], s1 = sofs[b + 1];
+        if (s1 - s0 < 2) continue;
+        const u64 key = r >> kshift;
+        u32 c0 = 0, c1 = 0;
+        u64 r1 = 0;
+        for (u32 j = s0; j < s1; ++j) {
+            const u64 q = stage[j];
+            if ((q >> kshift) == key) {
+                if ((q >> pl.pbits) & 1) { ++c1; r1 = q; } else ++c0;
+            }
+        }
+        if (c0 + c1 > 1000) repeat = 1;
+        if (c0 == 1 && c1 == 1) {
+            rec[it] = (r & posmask) | ((r1 & posmask) << 32);
+            if ((r ^ r1) >> (pl.pbits + 1) & 1) rmask |= 1u << it; else fmask |= 1u << it;
+        }
+    }
+    // block-wide reservation, one atomic per strand
+    const u32 cf = __popc(fmask), cr = __popc(rmask);
+    u32 inf = cf, inr = cr;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 tf = __shfl_up_sync(0xffffffffu, inf, o), tr = __shfl_up_sync(0xffffffffu, inr, o);
+        if (lane >= (u32)o) { inf += tf; inr += tr; }
+    }
+    if (lane == 31) { s_warp[0][warp] = inf; s_warp[1][warp] = inr; }
+    __syncthreads();
+    u32 wf = 0, wr = 0, totf = 0, totr = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        if ((u32)w < warp) { wf += s_warp[0][w]; wr += s_warp[1][w]; }
+        totf += s_warp[0][w];
+        totr += s_warp[1][w];
+    }
+    if (tid == 0) {
+        s_base[0] = totf ? atomicAdd(&a.counters[0], (unsigned long long)totf) : 0ull;
+        s_base[1] = totr ? atomicAdd(&a.counters[6], (unsigned long long)totr) : 0ull;
+    }
+    __syncthreads();
+    u64 of = s_base[0] + wf + inf - cf, orv = s_base[1] + wr + inr - cr;
+#pragma unroll
+    for (int it = 0; it < BK_GIPT; ++it) {
+        if ((fmask | rmask) & (1u << it)) {
+            const u32 p0 = (u32)(rec[it] & 0xffffffffu);
+            atomicOr(&a.uniq[p0 >> 5], 1u << (p0 & 31));
+            if (fmask & (1u << it)) a.pairs[of++] = rec[it];
+            else a.pairs[a.pair_cap - 1 - (orv++)] = rec[it];
+        }
+    }
+    if (__any_sync(0xffffffffu, repeat) && lane == 0) atomicMax(&a.counters[1], 1ull);
+}
+
+// spilled buckets -> (key, position) arrays of the radix-sort path: key = mixed mer << 2 | genome << 1 | strand
+__global__ void __launch_bounds__(BK_THREADS) bk_spill_kernel(const u64* __restrict__ recs, const u64* __restrict__ off2, const BkMeta* __restrict__ meta,
+                                                             const u32* __restrict__ spill_list, BkPlan pl, u64* __restrict__ keys,
+                                                             u32* __restrict__ vals, unsigned long long* __restrict__ cursor)
+{
+    __shared__ unsigned long long s_base;
+    const u32 f = spill_list[blockIdx.x];
+    const u64 beg = off2[f], nb = off2[f + 1] - beg;
+    if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned long long)nb);
+    __syncthreads();
+    const u64 b1 = meta->b_lo + f / pl.B2;
+    const u64 posmask = (1ull << pl.pbits) - 1;
+    for (u64 i = threadIdx.x; i < nb; i += blockDim.x) {
+        const u64 r = recs[beg + i];
+        const u64 mixed = (b1 << pl.rem1) | (r >> (pl.pbits + 2));  // the mixed mer: equal exactly when the mers are equal
+        keys[s_base + i] = (mixed << 2) | (((r >> pl.pbits) & 1) << 1) | ((r >> (pl.pbits + 1)) & 1);
+        vals[s_base + i] = (u32)(r & posmask);
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------
+static int bit_len(u64 x)
+{
+    int b = 0;
+    while (x) { ++b; x >>= 1; }
+    return b;
+}
+
+static bool make_plan(const SeedParams& sp, u64 npos0, u64 npos1, BkPlan* out)
+{
+    BkPlan p;
+    p.kbits = 2 * sp.w;
+    p.npos0 = npos0; p.npos1 = npos1; p.ntot = npos0 + npos1;
+    p.pbits = bit_len((npos0 > npos1 ? npos0 : npos1));
+    if (p.pbits < 1) p.pbits = 1;
+    if (p.ntot < 65536 || p.ntot >= (1ull << 40)) return false;
+    int T = bit_len(p.ntot / 2048);          // ~2k records per final bucket
+    if (T > p.kbits - 2) T = p.kbits - 2;    // keep key bits for the in-bucket comparison
+    if (T < 2 || T > 22) return false;
+    p.d1 = (T + 1) / 2;
+    // the record must fit 64 bits: (kbits - d1) + strand + genome + pbits
+    while (p.kbits - p.d1 + 2 + p.pbits > 64 && p.d1 < 11 && p.d1 < T) ++p.d1;
+    if (p.kbits - p.d1 + 2 + p.pbits > 64) return false;
+    p.d2 = T - p.d1;
+    if (p.d1 > 11 || p.d2 > 11 || p.d2 < 0) return false;
+    p.rem1 = p.kbits - p.d1;
+    p.d3 = p.rem1 - p.d2 < BK_D3 ? p.rem1 - p.d2 : BK_D3;
+    if (p.d3 < 0) return false;
+    p.B1 = 1u << p.d1;
+    p.B2 = 1u << p.d2;
+    p.npad0 = (npos0 + 15) & ~15ull;
+    p.nidx = p.npad0 + ((npos1 + 15) & ~15ull);
+    *out = p;
+    return true;
+}
+
+int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_count, u64 pair_cap, cudaEvent_t ev_scatter1, cudaEvent_t ev_scatter2,
+                 bool* used, u64* nrecords)
+{
+    *used = false;
+    const u64 npos0 = s.n[0] >= (u64)sp.L ? s.n[0] - sp.L + 1 : 0;
+    const u64 npos1 = s.n[1] >= (u64)sp.L ? s.n[1] - sp.L + 1 : 0;
+    BkPlan pl;
+    if (!npos0 || !npos1 || !make_plan(sp, npos0, npos1, &pl)) return MCU_OK;
+    cudaStream_t st = s.stream;
+    unsigned long long* ctr = s.counters.as<unsigned long long>();
+    const u64 nfinal_max = (u64)pl.B1 * pl.B2;
+    MCU_TRY(s.bk_a.reserve((pl.ntot + 1) * 8));
+    MCU_TRY(s.bk_b.reserve((pl.ntot + 1) * 8));
+    MCU_TRY(s.bk_tab1.reserve((size_t)(pl.B1 + 1) * 8 * 3 + 64));
+    MCU_TRY(s.bk_tab2.reserve((nfinal_max + 1) * 8 * 3 + 64));
+    MCU_TRY(s.bk_spill.reserve(nfinal_max * 4 + 64));
+    unsigned long long* count1 = s.bk_tab1.as<unsigned long long>();
+    u64* off1 = (u64*)(count1 + pl.B1 + 1);
+    unsigned long long* cursor1 = (unsigned long long*)(off1 + pl.B1 + 1);
+    BkMeta* meta = (BkMeta*)(cursor1 + pl.B1);  // inside the +64 bytes slack
+    unsigned long long* count2 = s.bk_tab2.as<unsigned long long>();
+    u64* off2 = (u64*)(count2 + nfinal_max + 1);
+    unsigned long long* cursor2 = (unsigned long long*)(off2 + nfinal_max + 1);
+    unsigned long long* spill = (unsigned long long*)(cursor2 + nfinal_max);  // [0] buckets [1] records [2] convert cursor
+    MCU_CUDA(cudaMemsetAsync(count1, 0, (size_t)(pl.B1 + 1) * 8, st));
+    MCU_CUDA(cudaMemsetAsync(count2, 0, (nfinal_max + 1) * 8, st));
+    MCU_CUDA(cudaMemsetAsync(spill, 0, 32, st));
+    const u32* g0 = s.packed[0].as<u32>();
+    const u32* g1 = s.packed[1].as<u32>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        MCU_CUDA(cudaFuncSetAttribute(bk_scatter1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
+        MCU_CUDA(cudaFuncSetAttribute(bk_scatter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
+        attr_done = true;
+    }
+    const int hgrid = sm_count() * 8;
+    MCU_CUDA(cudaEventRecord(s.kev[0], st));
+    bk_hist1_kernel<<<hgrid, BK_THREADS, pl.B1 * 4, st>>>(g0, g1, pl, sp, count1);
+    MCU_CUDA(cudaEventRecord(s.kev[1], st));
+    bk_scan1_kernel<<<1, 32, 0, st>>>(count1, pl, shard_index, shard_count, off1, cursor1, meta);
+    const unsigned tiles1 = (unsigned)div_up(pl.nidx, BK_TILE);
+    const unsigned tiles = (unsigned)div_up(pl.ntot, BK_TILE);
+    bk_scatter1_kernel<<<tiles1, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, meta, cursor1, s.bk_a.as<u64>());
+    MCU_CUDA(cudaEventRecord(ev_scatter1, st));
+    MCU_CUDA(cudaEventRecord(s.kev[2], st));
+    bk_hist2_kernel<<<hgrid, BK_THREADS, pl.B2 * 4, st>>>(s.bk_a.as<u64>(), pl, meta, off1, count2);
+    MCU_CUDA(cudaEventRecord(s.kev[3], st));
+    bk_scan2_kernel<<<1, 1024, 0, st>>>(count2, meta, off2, cursor2);
+    bk_scatter2_kernel<<<tiles, BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(s.bk_a.as<u64>(), pl, meta, off1, cursor2, s.bk_b.as<u64>());
+    MCU_CUDA(cudaEventRecord(ev_scatter2, st));
+    MCU_CUDA(cudaEventRecord(s.kev[4], st));
+    BkGroupArgs ga;
+    ga.recs = s.bk_b.as<u64>(); ga.off2 = off2; ga.meta = meta; ga.uniq = s.uniq.as<u32>(); ga.pairs = s.pairs.as<u64>(); ga.pair_cap = pair_cap;
+    ga.counters = ctr; ga.spill_list = s.bk_spill.as<u32>(); ga.spill = spill;
+    bk_group_kernel<<<(unsigned)nfinal_max, BK_THREADS, 0, st>>>(ga, pl);
+    MCU_CUDA(cudaEventRecord(s.kev[5], st));
+    s.launches += 7;
+    MCU_CUDA(cudaGetLastError());
+    // spilled buckets (if any) go through the radix-sort + join path
+    struct { unsigned long long spill[4]; BkMeta meta; } h;
+    MCU_CUDA(cudaMemcpyAsync(h.spill, spill, 32, cudaMemcpyDeviceToHost, st));
+    MCU_CUDA(cudaMemcpyAsync(&h.meta, meta, sizeof(BkMeta), cudaMemcpyDeviceToHost, st));
+    MCU_CUDA(cudaStreamSynchronize(st));
+    *nrecords = h.meta.nrec;
+    s.bk_spilled = h.spill[1];
+    if (h.spill[0]) {
+        const u64 ns = h.spill[1];
+        MCU_TRY(s.keys_a.reserve((ns + 1) * 8));
+        MCU_TRY(s.keys_b.reserve((ns + 1) * 8));
+        MCU_TRY(s.vals_a.reserve((ns + 1) * 4));
+        MCU_TRY(s.vals_b.reserve((ns + 1) * 4));
+        bk_spill_kernel<<<(unsigned)h.spill[0], BK_THREADS, 0, st>>>(s.bk_b.as<u64>(), off2, meta, s.bk_spill.as<u32>(), pl, s.keys_a.as<u64>(),
+                                                                     s.vals_a.as<u32>(), spill + 2);
+        s.launches++;
+        bool in_a = true;
+        u64 before = s.radix.launches;
+        MCU_TRY(radix_sort_pairs<u64>(s.radix, s.keys_a.as<u64>(), s.vals_a.as<u32>(), s.keys_b.as<u64>(), s.vals_b.as<u32>(), ns, pl.kbits + 2, false,
+                                      st, &in_a, nullptr));
+        s.launches += s.radix.launches - before;
+        MCU_TRY(join_sorted_u64(s, in_a ? s.keys_a.as<u64>() : s.keys_b.as<u64>(), in_a ? s.vals_a.as<u32>() : s.vals_b.as<u32>(), ns, pair_cap));
+    }
+    *used = true;
+    return MCU_OK;
+}
+
+}  // namespace mcu

@@ -260,7 +260,7 @@ class AnchorSession:
         h = C.c_void_p()
         check(lib().mcu_session_create(C.byref(h)))
         self._h = h
-        self.stage_ms = np.zeros(8, dtype=np.float32)
+        self.stage_ms = np.zeros(16, dtype=np.float32)
         self.stats = np.zeros(8, dtype=np.uint64)
 
     def close(self):
