@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) join_kernel(const K* __restrict__ keys, c
 // pair cannot be the leftmost unique seed of its match.  This removes the bulk of AddHashEntry's
 // "already contained" rejections (LM/MemHash.cpp:215-220): 2.7 M seed pairs -> ~30 k candidates
 // on MDS42.  counters[2] / [7] = forward / reverse candidates.
-__global__ void __launch_bounds__(256) candidate_kernel(ExtendArgs a, SeedParams sp, const u64* __restrict__ pairs, u64 pfwd, u64 prev_, u64 pair_cap)
+__global__ void __launch_bounds__(256) candidate_kernel(ExtendArgs a, SeedParams sp, const u64* __restrict__ pairs, u64 pfwd, u64 prev_, u64 pair_cap, bool solid)
 {
     const u32 lane = threadIdx.x & 31;
     const u64 total = pfwd + prev_;
@@ -213,7 +213,16 @@ __global__ void __launch_bounds__(256) candidate_kernel(ExtendArgs a, SeedParams
             const i64 p0 = (i64)(e & 0xffffffffu), p1 = (i64)(e >> 32);
             const i64 d = rev ? p0 + p1 : p1 - p0;
             i64 other;
-            is_cand = !(p0 > 0 && uniq_bit(a.uniq, p0 - 1) && probe_hit(a, sp, rev, d, p0 - 1, other));
+            if (solid) {
+                // hit(p0) is known: the left neighbour is a hit iff the one new base agrees
+                bool left_hit = false;
+                if (p0 > 0 && uniq_bit(a.uniq, p0 - 1)) {
+                    if (!rev) left_hit = p1 > 0 && base_at(a.g0, p0 - 1) == base_at(a.g1, p1 - 1);
+                    else left_hit = p1 + 1 < (i64)a.npos1 && base_at(a.g0, p0 - 1) == 3u - base_at(a.g1, p1 + sp.w);
+                }
+                is_cand = !left_hit;
+            } else
+                is_cand = !(p0 > 0 && uniq_bit(a.uniq, p0 - 1) && probe_hit(a, sp, rev, d, p0 - 1, other));
         }
         const u32 mf = __ballot_sync(0xffffffffu, is_cand && !rev), mr = __ballot_sync(0xffffffffu, is_cand && rev);
         if (mf | mr) {
@@ -242,6 +251,127 @@ __global__ void __launch_bounds__(256) candidate_kernel(ExtendArgs a, SeedParams
 // A hit at a genome-0 position whose uniq bit is set IS a unique seed pair of this diagonal
 // (its only genome-1 occurrence is the one the hit compares against).
 // =========================================================================================
+// ---- solid seeds of odd weight (the default for genomes > ~40 Mbp: LM/SeedMasks.h has no spaced pattern in the
+// CODING_SEED slot above weight 16) ---------------------------------------------------------------------------
+// With a solid pattern a hit at t means bases [t, t+w) agree on the diagonal, two consecutive hits are at most one
+// position apart, and a single mismatching base separates hits by w+1 > L: a match is exactly a maximal run of
+// agreeing bases.  (Odd w: a solid mer is never its own reverse complement, so the parity test of
+// MatchFinder.h:281-303 never fires.)  Runs are measured 32 bases per XOR instead of probing seed by seed.
+
+// reverse complement of 32 packed bases
+__device__ __forceinline__ u64 revcomp32(u64 v)
+{
+    u64 x = __brevll(~v);
+    return ((x & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((x & 0x5555555555555555ull) << 1);
+}
+
+struct SolidDiag {
+    const u32* g0;
+    const u32* g1;
+    i64 n0, n1;   // sequence lengths in bases
+    bool rev;
+    i64 d;        // forward: g1 index = g0 index + d ; reverse: g1 index = d - g0 index
+    // do base x of genome 0 and its partner base agree?  (both indices must be in range)
+    __device__ __forceinline__ bool agree(i64 x) const
+    {
+        const u32 a = base_at(g0, x);
+        return rev ? a == 3u - base_at(g1, d - x) : a == base_at(g1, x + d);
+    }
+    // XOR of the 32 bases [x, x+32) of genome 0 with their partners; caller guarantees both blocks are in range
+    __device__ __forceinline__ u64 diff32(i64 x) const
+    {
+        const u64 a = load_mer32(g0, (u64)x);
+        const u64 b = rev ? revcomp32(load_mer32(g1, (u64)(d - x - 31))) : load_mer32(g1, (u64)(x + d));
+        return a ^ b;
+    }
+};
+
+// number of agreeing bases going right from base x0 (inclusive), at most `maxlen`
+__device__ __forceinline__ i64 solid_run_right(const SolidDiag& D, i64 x0, i64 maxlen, u32 lane)
+{
+    i64 done = 0;
+    while (done + 32 <= maxlen) {  // whole blocks, 32 lanes x 32 bases per round
+        const i64 blk = done + 32 * (i64)lane;
+        u64 x = 0;
+        const bool in = blk + 32 <= maxlen;
+        if (in) x = D.diff32(x0 + blk);
+        const u32 bad = __ballot_sync(0xffffffffu, in && x != 0), live = __ballot_sync(0xffffffffu, in);
+        if (bad) {
+            const int l = __ffs(bad) - 1;
+            const u64 xl = __shfl_sync(0xffffffffu, x, l);
+            return done + 32 * (i64)l + (__clzll(xl) >> 1);
+        }
+        done += 32 * (i64)__popc(live);
+    }
+    while (done < maxlen && D.agree(x0 + done)) ++done;  // tail shorter than a block (uniform across the warp)
+    return done;
+}
+
+// number of agreeing bases going left from base x0 (inclusive), at most `maxlen`
+__device__ __forceinline__ i64 solid_run_left(const SolidDiag& D, i64 x0, i64 maxlen, u32 lane)
+{
+    i64 done = 0;
+    while (done + 32 <= maxlen) {
+        const i64 blk = done + 32 * (i64)lane;
+        u64 x = 0;
+        const bool in = blk + 32 <= maxlen;
+        if (in) x = D.diff32(x0 - blk - 31);
+        const u32 bad = __ballot_sync(0xffffffffu, in && x != 0), live = __ballot_sync(0xffffffffu, in);
+        if (bad) {
+            const int l = __ffs(bad) - 1;
+            const u64 xl = __shfl_sync(0xffffffffu, x, l);
+            return done + 32 * (i64)l + (__ffsll((long long)xl) - 1) / 2;
+        }
+        done += 32 * (i64)__popc(live);
+    }
+    while (done < maxlen && D.agree(x0 - done)) ++done;
+    return done;
+}
+
+__global__ void __launch_bounds__(256) extend_solid_kernel(ExtendArgs a, SeedParams sp, i64 n0, i64 n1)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u64 warp_global = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const i64 w = sp.w;
+    const u64 total = a.nfwd + a.nrev;
+    for (u64 c = warp_global; c < total; c += nwarps) {
+        SolidDiag D;
+        D.g0 = a.g0; D.g1 = a.g1; D.n0 = n0; D.n1 = n1;
+        D.rev = c >= a.nfwd;
+        const u64 e = D.rev ? a.cand[a.cap - 1 - (c - a.nfwd)] : a.cand[c];
+        const i64 t0 = (i64)(e & 0xffffffffu), p1 = (i64)(e >> 32);
+        // base x of genome 0 pairs with base x + (p1 - t0) (forward) or (t0 + p1 + w - 1) - x (reverse) of genome 1
+        D.d = D.rev ? t0 + p1 + w - 1 : p1 - t0;
+        // ---- left: bases t0-1, t0-2, ... ----
+        const i64 maxl = D.rev ? min(t0, n1 - 1 - (D.d - t0)) : min(t0, t0 + D.d);
+        const i64 left = maxl > 0 ? solid_run_left(D, t0 - 1, maxl, lane) : 0;
+        const i64 lo = t0 - left;
+        // another unique seed pair at a seed position in [lo, t0): not the leftmost seed of this match
+        bool other = false;
+        for (i64 wd = (lo >> 5) + lane; wd <= ((t0 - 1) >> 5) && left > 0; wd += 32) {
+            u32 bits = __ldg(a.uniq + wd);
+            if (wd == (lo >> 5)) bits &= 0xffffffffu << (lo & 31);
+            if (wd == ((t0 - 1) >> 5)) bits &= 0xffffffffu >> (31 - ((t0 - 1) & 31));
+            other |= bits != 0;
+        }
+        if (__any_sync(0xffffffffu, other)) continue;
+        // ---- right: bases t0+w, t0+w+1, ... ----
+        const i64 xr = t0 + w;
+        const i64 maxr = D.rev ? min(n0 - xr, D.d - xr + 1) : min(n0 - xr, n1 - (xr + D.d));
+        const i64 right = maxr > 0 ? solid_run_right(D, xr, maxr, lane) : 0;
+        if (lane == 0) {
+            const u64 slot = atomicAdd(&a.counters[3], 1ull);
+            mcu_match m;
+            m.len = left + w + right;
+            m.start0 = lo + 1;
+            // forward: partner of base lo; reverse: the match covers genome-1 bases [d - (lo+len-1), d - lo], reported negative
+            m.start1 = D.rev ? -((D.d - (lo + m.len - 1)) + 1) : lo + D.d + 1;
+            a.out[slot] = m;
+        }
+    }
+}
+
 // One warp per candidate: lanes probe the L offsets beyond the current end, ballot, jump to
 // the farthest hit.  While walking left, meeting another unique seed pair of the same diagonal
 // means this candidate is not the leftmost one of its match -> abandon (exactly one emitter
@@ -367,7 +497,7 @@ void session_destroy(Session& s)
                       &s.matches, &s.ord_primary, &s.counters, &s.radix.hist, &s.radix.status, &s.radix.counters,
                       &s.rp_ctr, &s.rp_bitmap, &s.rp_list, &s.rp_canon, &s.rp_keys_b, &s.rp_idx_a, &s.rp_idx_b, &s.rp_p0, &s.rp_row, &s.rp_bkeys,
                       &s.rp_pool, &s.rp_extra, &s.rp_prefix, &s.rp_vinfo, &s.rp_out,
-                      &s.bk_a, &s.bk_b, &s.bk_tab1, &s.bk_tab2, &s.bk_spill};
+                      &s.bk_a, &s.bk_b, &s.bk_tab1, &s.bk_tab2, &s.bk_spill, &s.bk_tileseg};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(s.ev[i]);
     for (int i = 0; i < 12; ++i) cudaEventDestroy(s.kev[i]);
@@ -502,7 +632,8 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
         ea.cand = s.cand.as<u64>(); ea.nfwd = 0; ea.nrev = 0; ea.cap = npairs;
         ea.out = nullptr; ea.counters = ctr;
         MCU_CUDA(cudaEventRecord(s.kev[6], s.stream));
-        candidate_kernel<<<grid_for(npairs, 256, 8), 256, 0, s.stream>>>(ea, sp, s.pairs.as<u64>(), pfwd, prev_, pair_cap);
+        const bool solid = sp.nruns == 1 && sp.L == sp.w && (sp.w & 1) && getenv("MAUVE_CUDA_NO_SOLID") == nullptr;
+        candidate_kernel<<<grid_for(npairs, 256, 8), 256, 0, s.stream>>>(ea, sp, s.pairs.as<u64>(), pfwd, prev_, pair_cap, solid);
         s.launches++;
         MCU_CUDA(cudaEventRecord(s.kev[7], s.stream));
         MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
@@ -511,7 +642,8 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
         ncand = ea.nfwd + ea.nrev;
         MCU_TRY(s.raw_matches.reserve((ncand + 1) * sizeof(mcu_match)));
         ea.out = s.raw_matches.as<mcu_match>();
-        extend_kernel<<<grid_for(ncand * 32, 256, 8), 256, 0, s.stream>>>(ea, sp);
+        if (solid) extend_solid_kernel<<<grid_for(ncand * 32, 256, 8), 256, 0, s.stream>>>(ea, sp, (i64)s.n[0], (i64)s.n[1]);
+        else extend_kernel<<<grid_for(ncand * 32, 256, 8), 256, 0, s.stream>>>(ea, sp);
         s.launches++;
         MCU_CUDA(cudaEventRecord(s.kev[8], s.stream));
         MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));

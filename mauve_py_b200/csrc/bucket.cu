@@ -30,9 +30,9 @@ constexpr int BK_THREADS = 256;
 constexpr int BK_IPT = 16;
 constexpr int BK_TILE = BK_THREADS * BK_IPT;   // records per scatter tile
 constexpr int BK_SUPER = 16 * BK_TILE;         // records per histogram block iteration
-constexpr int BK_CAP = 4096;                   // largest final bucket finished in shared memory
+constexpr int BK_CAP = 2048;                   // largest final bucket finished in shared memory
 constexpr int BK_MAXB = 2048;                  // max bins per level
-constexpr int BK_D3 = 11;
+constexpr int BK_D3 = 10;
 
 struct BkPlan {
     int kbits, d1, d2, d3, pbits, rem1;
@@ -279,6 +279,15 @@ __device__ __forceinline__ u32 bk_segment_of(const u64* __restrict__ off1, u32 B
     return lo;
 }
 
+// level-1 bucket that holds the first record of every scatter tile (so the scatter does not search)
+__global__ void bk_tileseg_kernel(const u64* __restrict__ off1, BkPlan pl, const BkMeta* __restrict__ meta, u32* __restrict__ tile_seg, u32 ntiles)
+{
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const u64 i = (u64)t * BK_TILE;
+    tile_seg[t] = i < meta->nrec ? bk_segment_of(off1, pl.B1, i) : 0u;
+}
+
 __global__ void __launch_bounds__(BK_THREADS) bk_hist2_kernel(const u64* __restrict__ recs, BkPlan pl, const BkMeta* __restrict__ meta,
                                                              const u64* __restrict__ off1, unsigned long long* __restrict__ count2)
 {
@@ -333,8 +342,8 @@ __global__ void __launch_bounds__(1024) bk_scan2_kernel(const unsigned long long
 }
 
 __global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter2_kernel(const u64* __restrict__ src, BkPlan pl, const BkMeta* __restrict__ meta,
-                                                                   const u64* __restrict__ off1, unsigned long long* __restrict__ cursor2,
-                                                                   u64* __restrict__ dst)
+                                                                   const u64* __restrict__ off1, const u32* __restrict__ tile_seg,
+                                                                   unsigned long long* __restrict__ cursor2, u64* __restrict__ dst)
 {
     extern __shared__ __align__(16) unsigned char raw[];
     const BkScatterSmem s = bk_carve(raw, pl.B2);
@@ -346,19 +355,24 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter2_kernel(const u64* _
     if (base >= nrec) return;
     const u64 end = min(base + (u64)BK_TILE, nrec);
     u64 i0 = base;
+    u32 seg = tile_seg[blockIdx.x];
     while (i0 < end) {  // one iteration unless the tile straddles level-1 buckets
-        const u32 seg = bk_segment_of(off1, pl.B1, i0);
+        while (off1[seg + 1] <= i0) ++seg;
         const u64 i1 = min(end, off1[seg + 1]);
         for (u32 i = tid; i < pl.B2; i += BK_THREADS) s.cnt[i] = 0;
         __syncthreads();
         u64 rec[BK_IPT];
         u32 br[BK_IPT];
 #pragma unroll
+        for (int it = 0; it < BK_IPT; ++it) {  // all loads in flight before the first shared-memory atomic
+            const u64 i = i0 + (u64)it * BK_THREADS + tid;
+            rec[it] = i < i1 ? __ldcs(src + i) : 0;
+        }
+#pragma unroll
         for (int it = 0; it < BK_IPT; ++it) {
             const u64 i = i0 + (u64)it * BK_THREADS + tid;
             br[it] = 0xffffffffu;
             if (i < i1) {
-                rec[it] = src[i];
                 const u32 b = (u32)(rec[it] >> shift) & (pl.B2 - 1);
                 br[it] = (b << 16) | atomicAdd(&s.cnt[b], 1u);
             }
@@ -395,7 +409,7 @@ struct BkGroupArgs {
 
 constexpr int BK_GIPT = BK_CAP / BK_THREADS;  // staged records per thread in bk_group
 
-__global__ void __launch_bounds__(BK_THREADS, 4) bk_group_kernel(BkGroupArgs a, BkPlan pl)
+__global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, BkPlan pl)
 {
     __shared__ u64 stage[BK_CAP];
     __shared__ u32 sofs[(1 << BK_D3) + 1];  // bin counts first, exclusive offsets after the scan
@@ -426,9 +440,13 @@ __global__ void __launch_bounds__(BK_THREADS, 4) bk_group_kernel(BkGroupArgs a, 
 #pragma unroll
     for (int it = 0; it < BK_GIPT; ++it) {
         const u32 i = it * BK_THREADS + tid;
+        rec[it] = i < nb ? __ldcs(a.recs + beg + i) : 0;
+    }
+#pragma unroll
+    for (int it = 0; it < BK_GIPT; ++it) {
+        const u32 i = it * BK_THREADS + tid;
         br[it] = 0xffffffffu;
         if (i < nb) {
-            rec[it] = a.recs[beg + i];
             const u32 b = (u32)(rec[it] >> dshift) & (nsub - 1);
             br[it] = (b << 16) | atomicAdd(&sofs[b], 1u);
         }
@@ -559,7 +577,7 @@ static bool make_plan(const SeedParams& sp, u64 npos0, u64 npos1, BkPlan* out)
     p.pbits = bit_len((npos0 > npos1 ? npos0 : npos1));
     if (p.pbits < 1) p.pbits = 1;
     if (p.ntot < 65536 || p.ntot >= (1ull << 40)) return false;
-    int T = bit_len(p.ntot / 2048);          // ~2k records per final bucket
+    int T = bit_len(p.ntot / 1536);          // 768..1536 records per final bucket: BK_CAP is > 13 sigma away
     if (T > p.kbits - 2) T = p.kbits - 2;    // keep key bits for the in-bucket comparison
     if (T < 2 || T > 22) return false;
     p.d1 = (T + 1) / 2;
@@ -595,6 +613,7 @@ int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_co
     MCU_TRY(s.bk_tab1.reserve((size_t)(pl.B1 + 1) * 8 * 3 + 64));
     MCU_TRY(s.bk_tab2.reserve((nfinal_max + 1) * 8 * 3 + 64));
     MCU_TRY(s.bk_spill.reserve(nfinal_max * 4 + 64));
+    MCU_TRY(s.bk_tileseg.reserve((div_up(pl.ntot, BK_TILE) + 1) * 4));
     unsigned long long* count1 = s.bk_tab1.as<unsigned long long>();
     u64* off1 = (u64*)(count1 + pl.B1 + 1);
     unsigned long long* cursor1 = (unsigned long long*)(off1 + pl.B1 + 1);
@@ -624,10 +643,11 @@ int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_co
     bk_scatter1_kernel<<<tiles1, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, meta, cursor1, s.bk_a.as<u64>());
     MCU_CUDA(cudaEventRecord(ev_scatter1, st));
     MCU_CUDA(cudaEventRecord(s.kev[2], st));
+    bk_tileseg_kernel<<<(tiles + 255) / 256, 256, 0, st>>>(off1, pl, meta, s.bk_tileseg.as<u32>(), tiles);
     bk_hist2_kernel<<<hgrid, BK_THREADS, pl.B2 * 4, st>>>(s.bk_a.as<u64>(), pl, meta, off1, count2);
     MCU_CUDA(cudaEventRecord(s.kev[3], st));
     bk_scan2_kernel<<<1, 1024, 0, st>>>(count2, meta, off2, cursor2);
-    bk_scatter2_kernel<<<tiles, BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(s.bk_a.as<u64>(), pl, meta, off1, cursor2, s.bk_b.as<u64>());
+    bk_scatter2_kernel<<<tiles, BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(s.bk_a.as<u64>(), pl, meta, off1, s.bk_tileseg.as<u32>(), cursor2, s.bk_b.as<u64>());
     MCU_CUDA(cudaEventRecord(ev_scatter2, st));
     MCU_CUDA(cudaEventRecord(s.kev[4], st));
     BkGroupArgs ga;
@@ -635,7 +655,7 @@ int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_co
     ga.counters = ctr; ga.spill_list = s.bk_spill.as<u32>(); ga.spill = spill;
     bk_group_kernel<<<(unsigned)nfinal_max, BK_THREADS, 0, st>>>(ga, pl);
     MCU_CUDA(cudaEventRecord(s.kev[5], st));
-    s.launches += 7;
+    s.launches += 8;
     MCU_CUDA(cudaGetLastError());
     // spilled buckets (if any) go through the radix-sort + join path
     struct { unsigned long long spill[4]; BkMeta meta; } h;

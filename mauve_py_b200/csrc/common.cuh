@@ -100,6 +100,9 @@ __device__ __forceinline__ u64 load_mer32(const u32* __restrict__ packed, u64 po
     return bit ? ((hi << bit) | ((u64)w2 >> (32 - bit))) : hi;
 }
 
+// 2-bit code of base i
+__device__ __forceinline__ u32 base_at(const u32* __restrict__ packed, i64 i) { return (__ldg(packed + (i >> 4)) >> (30 - 2 * (int)(i & 15))) & 3u; }
+
 // spaced seed (2w bits, right-aligned) of the L bases held left-aligned in mer32
 __device__ __forceinline__ u64 extract_seed(u64 mer32, const SeedParams& sp)
 {

@@ -294,3 +294,19 @@ def test_merge_reports_order_dependent_buckets(mp):
     merged, unclean = mp.merge_matches(s.download(), return_unclean=True)
     assert unclean == 0
     s.close()
+
+
+@pytest.mark.parametrize("w", [19, 17, 21, 23, 31])
+def test_mums_solid_seed_paths(mp, orc, w):
+    """solid odd-weight seeds take the run-length extension (extend_solid_kernel): same rows as the oracle, incl. sequence ends"""
+    a, b = synth.small_pair(300000, seed=w, snp=0.01, n_inv=3)
+    # matches touching both ends of both genomes, forward and reverse
+    tail = synth.random_genome(400, 0.5, synth.rng_for(w + 1)).tobytes()
+    a2 = tail + a + synth.revcomp(np.frombuffer(tail, dtype=np.uint8)).tobytes()
+    b2 = tail + b + synth.revcomp(np.frombuffer(tail, dtype=np.uint8)).tobytes()
+    seed = mp.getSeed(w, mp.SOLID_SEED)
+    assert mp.getSeedLength(seed) == w
+    for x, y in ((a, b), (a2, b2), (a2, synth.revcomp(np.frombuffer(b2, dtype=np.uint8)).tobytes())):
+        rows, stats = mp.libmems.find_mums(x, y, seed)
+        orows, _ = orc.find_mums(x, y, seed, 0)
+        assert rows.shape[0] > 10 and np.array_equal(rows, orows)
