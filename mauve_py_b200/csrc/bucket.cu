@@ -16,7 +16,7 @@
 //   bk_group     one CTA per final bucket: unique-in-both keys -> uniq bitmap + pair list  8 B/seed + 8 B/pair
 //
 // 40 B/seed instead of 12 + 5*24 + 12 = 144 B/seed (w = 19): the path is HBM-bound, so this is the lever.
-// record = keyrem(2w - d1 bits) | strand | genome | position(pbits); the top d1 key bits are implied by the
+// record = keyrem(2w - d1 bits) | position(pbits) | strand | genome; the top d1 key bits are implied by the
 // bucket.  Scatter passes are unordered (atomic cursors, no look-back chain): grouping needs no stability.
 // Buckets that do not fit shared memory (low-complexity sequence) are spilled to the radix-sort + join path
 // (radix.cuh / join_kernel), which handles any size; plans that do not fit 64-bit records use that path too.
@@ -49,18 +49,13 @@ struct BkMeta {  // written by bk_scan1_kernel
 
 // Canonical mers are far from uniform (min(f, rc) piles up at small values, base composition skews the
 // leading bases), and only EQUALITY of mers matters here, so buckets are cut on a bijective mix of the
-// canonical mer (xorshift, odd multiply, xorshift on 2w bits): bucket sizes become Poisson-tight whatever the
+// canonical mer (xorshift, odd multiply on 2w bits): bucket sizes become Poisson-tight whatever the
 // genome looks like; identical mers still share a bucket.
 __device__ __forceinline__ u64 bk_mix(u64 x, int kbits)
 {
     const u64 mask = kbits >= 64 ? ~0ull : ((1ull << kbits) - 1);
-    const int sh = kbits / 2 + 1;
-    x ^= x >> sh;
-    x = (x * 0x9E3779B97F4A7C15ull) & mask;
-    x ^= x >> sh;
-    x = (x * 0xD6E8FEB86659FD93ull) & mask;
-    x ^= x >> sh;
-    return x;
+    x ^= x >> (kbits / 2 + 1);                      // high bits reach the low half
+    return (x * 0x9E3779B97F4A7C15ull) & mask;      // every output bit depends on all lower input bits: the top (bucket) bits on all of them
 }
 
 __device__ __forceinline__ void seed_canon32(u64 mer32, const SeedParams& sp, u64& key, u32& strand)
@@ -245,7 +240,7 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter1_kernel(const u32* _
                 const u32 b = (u32)(canon >> pl.rem1);
                 if (b >= b_lo && b < b_hi) {
                     const u64 keyrem = canon & ((1ull << pl.rem1) - 1);
-                    rec[it] = (keyrem << (pl.pbits + 2)) | ((u64)strand << (pl.pbits + 1)) | ((u64)g << pl.pbits) | (pos + it);
+                    rec[it] = (keyrem << (pl.pbits + 2)) | ((pos + it) << 2) | ((u64)strand << 1) | (u64)g;
                     br[it] = (b << 16) | atomicAdd(&s.cnt[b], 1u);
                 }
             }
@@ -407,13 +402,14 @@ struct BkGroupArgs {
     unsigned long long* spill;     // [0] buckets, [1] records
 };
 
-constexpr int BK_GIPT = BK_CAP / BK_THREADS;  // staged records per thread in bk_group
+constexpr int BK_GIPT = BK_CAP / BK_THREADS;  // records per thread in bk_group
 
 __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, BkPlan pl)
 {
     __shared__ u64 stage[BK_CAP];
+    __shared__ u64 outp[BK_CAP / 2];        // pairs of this bucket: forward from the front, reverse from the back
     __shared__ u32 sofs[(1 << BK_D3) + 1];  // bin counts first, exclusive offsets after the scan
-    __shared__ u32 s_warp[2][8];
+    __shared__ u32 s_warp[8], s_np[2];
     __shared__ unsigned long long s_base[2];
     const u64 f = blockIdx.x;
     if (f >= a.meta->nfinal) return;
@@ -431,28 +427,30 @@ __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, 
     const int kshift = pl.pbits + 2;
     const u32 nsub = 1u << pl.d3;
     const int dshift = kshift + pl.rem1 - pl.d2 - pl.d3;
-    const u64 posmask = (1ull << pl.pbits) - 1;
+    const u64 samekey = 1ull << kshift;  // two records carry the same mer iff (x ^ y) < samekey
+    const u32 posmask = (u32)((1ull << pl.pbits) - 1);
     for (u32 i = tid; i <= nsub; i += BK_THREADS) sofs[i] = 0;
+    if (tid < 2) s_np[tid] = 0;
     __syncthreads();
-    // counting split on the next d3 key bits: sub-groups of ~1 record, all records of one key in one sub-group
-    u64 rec[BK_GIPT];
-    u32 br[BK_GIPT];
+    {   // counting split on the next d3 key bits: sub-groups of ~1 record, all records of one mer in one sub-group
+        u64 rec[BK_GIPT];
+        u32 br[BK_GIPT];
 #pragma unroll
-    for (int it = 0; it < BK_GIPT; ++it) {
-        const u32 i = it * BK_THREADS + tid;
-        rec[it] = i < nb ? __ldcs(a.recs + beg + i) : 0;
-    }
-#pragma unroll
-    for (int it = 0; it < BK_GIPT; ++it) {
-        const u32 i = it * BK_THREADS + tid;
-        br[it] = 0xffffffffu;
-        if (i < nb) {
-            const u32 b = (u32)(rec[it] >> dshift) & (nsub - 1);
-            br[it] = (b << 16) | atomicAdd(&sofs[b], 1u);
+        for (int it = 0; it < BK_GIPT; ++it) {
+            const u32 i = it * BK_THREADS + tid;
+            rec[it] = i < nb ? __ldcs(a.recs + beg + i) : 0;
         }
-    }
-    __syncthreads();
-    {   // exclusive scan of the counts in place: thread t owns bins [t*per, (t+1)*per)
+#pragma unroll
+        for (int it = 0; it < BK_GIPT; ++it) {
+            const u32 i = it * BK_THREADS + tid;
+            br[it] = 0xffffffffu;
+            if (i < nb) {
+                const u32 b = (u32)(rec[it] >> dshift) & (nsub - 1);
+                br[it] = (b << 16) | atomicAdd(&sofs[b], 1u);
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the counts in place: thread t owns bins [t*per, (t+1)*per)
         const u32 per = (nsub + BK_THREADS - 1) / BK_THREADS;
         u32 local = 0;
         for (u32 j = 0; j < per; ++j) {
@@ -465,80 +463,67 @@ __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, 
             const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= (u32)o) incl += t;
         }
-        if (lane == 31) s_warp[0][warp] = incl;
+        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        u32 add = 0;
-        for (u32 w = 0; w < warp; ++w) add += s_warp[0][w];
-        u32 run = incl - local + add;
+        u32 run = incl - local;
+        for (u32 w = 0; w < warp; ++w) run += s_warp[w];
         for (u32 j = 0; j < per; ++j) {
             const u32 b = tid * per + j;
             if (b < nsub) { const u32 c = sofs[b]; sofs[b] = run; run += c; }
         }
         if (tid == BK_THREADS - 1) sofs[nsub] = run;
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < BK_GIPT; ++it)
+            if (br[it] != 0xffffffffu) stage[sofs[br[it] >> 16] + (br[it] & 0xffffu)] = rec[it];
     }
     __syncthreads();
-#pragma unroll
-    for (int it = 0; it < BK_GIPT; ++it)
-        if (br[it] != 0xffffffffu) stage[sofs[br[it] >> 16] + (br[it] & 0xffffu)] = rec[it];
-    __syncthreads();
-    // record-centric: every genome-0 record scans its own sub-group; unique in both genomes -> pair (kept in registers)
-    u32 fmask = 0, rmask = 0, repeat = 0;
-#pragma unroll
-    for (int it = 0; it < BK_GIPT; ++it) {
-        if (br[it] == 0xffffffffu) continue;
-        const u64 r = rec[it];
-        if ((r >> pl.pbits) & 1) continue;
-        const u32 b = br[it] >> 16;
+    // every genome-0 record scans its own sub-group: mer unique in both genomes -> pair
+    u32 repeat = 0;
+#pragma unroll 1
+    for (u32 i = tid; i < nb; i += BK_THREADS) {
+        const u64 r = stage[i];
+        if (r & 1) continue;
+        const u32 b = (u32)(r >> dshift) & (nsub - 1);
         const u32 s0 = sofs[b], s1 = sofs[b + 1];
         if (s1 - s0 < 2) continue;
-        const u64 key = r >> kshift;
         u32 c0 = 0, c1 = 0;
         u64 r1 = 0;
+#pragma unroll 1
         for (u32 j = s0; j < s1; ++j) {
             const u64 q = stage[j];
-            if ((q >> kshift) == key) {
-                if ((q >> pl.pbits) & 1) { ++c1; r1 = q; } else ++c0;
+            if ((q ^ r) < samekey) {
+                if (q & 1) { ++c1; r1 = q; } else ++c0;
             }
         }
         if (c0 + c1 > 1000) repeat = 1;
         if (c0 == 1 && c1 == 1) {
-            rec[it] = (r & posmask) | ((r1 & posmask) << 32);
-            if ((r ^ r1) >> (pl.pbits + 1) & 1) rmask |= 1u << it; else fmask |= 1u << it;
-        }
-    }
-    // block-wide reservation, one atomic per strand
-    const u32 cf = __popc(fmask), cr = __popc(rmask);
-    u32 inf = cf, inr = cr;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u32 tf = __shfl_up_sync(0xffffffffu, inf, o), tr = __shfl_up_sync(0xffffffffu, inr, o);
-        if (lane >= (u32)o) { inf += tf; inr += tr; }
-    }
-    if (lane == 31) { s_warp[0][warp] = inf; s_warp[1][warp] = inr; }
-    __syncthreads();
-    u32 wf = 0, wr = 0, totf = 0, totr = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        if ((u32)w < warp) { wf += s_warp[0][w]; wr += s_warp[1][w]; }
-        totf += s_warp[0][w];
-        totr += s_warp[1][w];
-    }
-    if (tid == 0) {
-        s_base[0] = totf ? atomicAdd(&a.counters[0], (unsigned long long)totf) : 0ull;
-        s_base[1] = totr ? atomicAdd(&a.counters[6], (unsigned long long)totr) : 0ull;
-    }
-    __syncthreads();
-    u64 of = s_base[0] + wf + inf - cf, orv = s_base[1] + wr + inr - cr;
-#pragma unroll
-    for (int it = 0; it < BK_GIPT; ++it) {
-        if ((fmask | rmask) & (1u << it)) {
-            const u32 p0 = (u32)(rec[it] & 0xffffffffu);
-            atomicOr(&a.uniq[p0 >> 5], 1u << (p0 & 31));
-            if (fmask & (1u << it)) a.pairs[of++] = rec[it];
-            else a.pairs[a.pair_cap - 1 - (orv++)] = rec[it];
+            const u64 e = (u64)((u32)(r >> 2) & posmask) | ((u64)((u32)(r1 >> 2) & posmask) << 32);
+            if ((r ^ r1) & 2) outp[BK_CAP / 2 - 1 - atomicAdd(&s_np[1], 1u)] = e;
+            else outp[atomicAdd(&s_np[0], 1u)] = e;
         }
     }
     if (__any_sync(0xffffffffu, repeat) && lane == 0) atomicMax(&a.counters[1], 1ull);
+    __syncthreads();
+    const u32 nf = s_np[0], nr = s_np[1];
+    if (tid == 0) {
+        s_base[0] = nf ? atomicAdd(&a.counters[0], (unsigned long long)nf) : 0ull;
+        s_base[1] = nr ? atomicAdd(&a.counters[6], (unsigned long long)nr) : 0ull;
+    }
+    __syncthreads();
+    const u64 bf = s_base[0], br2 = s_base[1];
+    for (u32 j = tid; j < nf; j += BK_THREADS) {
+        const u64 e = outp[j];
+        const u32 p0 = (u32)e;
+        atomicOr(&a.uniq[p0 >> 5], 1u << (p0 & 31));
+        a.pairs[bf + j] = e;
+    }
+    for (u32 j = tid; j < nr; j += BK_THREADS) {
+        const u64 e = outp[BK_CAP / 2 - 1 - j];
+        const u32 p0 = (u32)e;
+        atomicOr(&a.uniq[p0 >> 5], 1u << (p0 & 31));
+        a.pairs[a.pair_cap - 1 - (br2 + j)] = e;
+    }
 }
 
 // spilled buckets -> (key, position) arrays of the radix-sort path: key = mixed mer << 2 | genome << 1 | strand
@@ -556,8 +541,8 @@ __global__ void __launch_bounds__(BK_THREADS) bk_spill_kernel(const u64* __restr
     for (u64 i = threadIdx.x; i < nb; i += blockDim.x) {
         const u64 r = recs[beg + i];
         const u64 mixed = (b1 << pl.rem1) | (r >> (pl.pbits + 2));  // the mixed mer: equal exactly when the mers are equal
-        keys[s_base + i] = (mixed << 2) | (((r >> pl.pbits) & 1) << 1) | ((r >> (pl.pbits + 1)) & 1);
-        vals[s_base + i] = (u32)(r & posmask);
+        keys[s_base + i] = (mixed << 2) | ((r & 1) << 1) | ((r >> 1) & 1);
+        vals[s_base + i] = (u32)((r >> 2) & posmask);
     }
 }
 
