@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(256) join_kernel(const K* __restrict__ keys, c
 // pair cannot be the leftmost unique seed of its match.  This removes the bulk of AddHashEntry's
 // "already contained" rejections (LM/MemHash.cpp:215-220): 2.7 M seed pairs -> ~30 k candidates
 // on MDS42.  counters[2] / [7] = forward / reverse candidates.
-__global__ void __launch_bounds__(256) candidate_kernel(ExtendArgs a, SeedParams sp, const u64* __restrict__ pairs, u64 pfwd, u64 prev_, u64 pair_cap, bool solid)
+__global__ void __launch_bounds__(256) candidate_kernel(ExtendArgs a, SeedParams sp, const u64* __restrict__ pairs, u64 pfwd, u64 prev_, u64 pair_cap, bool solid,
+                                                       bool bases_agree)
 {
     const u32 lane = threadIdx.x & 31;
     const u64 total = pfwd + prev_;
@@ -213,7 +214,10 @@ __global__ void __launch_bounds__(256) candidate_kernel(ExtendArgs a, SeedParams
             const i64 p0 = (i64)(e & 0xffffffffu), p1 = (i64)(e >> 32);
             const i64 d = rev ? p0 + p1 : p1 - p0;
             i64 other;
-            if (solid) {
+            if (bases_agree) {
+                // the bucket kernel already compared the neighbour bases (p0 > 0 and the partner exists): only the bitmap is left
+                is_cand = !uniq_bit(a.uniq, p0 - 1);
+            } else if (solid) {
                 // hit(p0) is known: the left neighbour is a hit iff the one new base agrees
                 bool left_hit = false;
                 if (p0 > 0 && uniq_bit(a.uniq, p0 - 1)) {
@@ -554,8 +558,11 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
     const u64 uniq_words = div_up(npos0 + 1, 32) + 1;
     MCU_TRY(s.uniq.reserve(uniq_words * sizeof(u32)));
     MCU_TRY(s.pairs.reserve(pair_cap * sizeof(u64)));
+    MCU_TRY(s.cand.reserve(pair_cap * sizeof(u64)));
     MCU_CUDA(cudaMemsetAsync(s.uniq.p, 0, uniq_words * sizeof(u32), s.stream));
     bool bucketed = false;
+    s.bk_direct = 0;
+    s.bk_aux = false;
     u64 nsort = ntot;
     int passes_run = 0;
     s.bk_spilled = 0;
@@ -620,20 +627,19 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
     MCU_CUDA(cudaStreamSynchronize(s.stream));
     if (((u32*)(s.h_counters + 4))[0]) { set_error("gap character '-' in a genome sequence (input must be unaligned)"); return MCU_EGAP; }
     const u64 pfwd = s.h_counters[0], prev_ = s.h_counters[6];
-    const u64 npairs = pfwd + prev_;
+    const u64 npairs = pfwd + prev_ + s.bk_direct;  // bk_direct: pairs the bucket kernel already classified as candidates
     const u64 repeat_flag = s.h_counters[1];
     u64 ncand = 0, nmatch = 0;
     if (npairs) {
-        MCU_TRY(s.cand.reserve((npairs + 1) * sizeof(u64)));
         ExtendArgs ea;
         ea.g0 = s.packed[0].as<u32>(); ea.g1 = s.packed[1].as<u32>();
         ea.npos0 = npos0; ea.npos1 = npos1;
         ea.uniq = s.uniq.as<u32>();
-        ea.cand = s.cand.as<u64>(); ea.nfwd = 0; ea.nrev = 0; ea.cap = npairs;
+        ea.cand = s.cand.as<u64>(); ea.nfwd = 0; ea.nrev = 0; ea.cap = pair_cap;
         ea.out = nullptr; ea.counters = ctr;
         MCU_CUDA(cudaEventRecord(s.kev[6], s.stream));
         const bool solid = sp.nruns == 1 && sp.L == sp.w && (sp.w & 1) && getenv("MAUVE_CUDA_NO_SOLID") == nullptr;
-        candidate_kernel<<<grid_for(npairs, 256, 8), 256, 0, s.stream>>>(ea, sp, s.pairs.as<u64>(), pfwd, prev_, pair_cap, solid);
+        candidate_kernel<<<grid_for(pfwd + prev_ + 1, 256, 8), 256, 0, s.stream>>>(ea, sp, s.pairs.as<u64>(), pfwd, prev_, pair_cap, solid, s.bk_aux);
         s.launches++;
         MCU_CUDA(cudaEventRecord(s.kev[7], s.stream));
         MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));

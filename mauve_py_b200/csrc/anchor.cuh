@@ -14,7 +14,8 @@ struct Session {
     DevBuf uniq, pairs, cand, raw_matches, ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b, ord_primary, matches, counters;
     // bucketed enumeration (bucket.cu)
     DevBuf bk_a, bk_b, bk_tab1, bk_tab2, bk_spill, bk_tileseg;
-    u64 bk_spilled = 0;
+    u64 bk_spilled = 0, bk_direct = 0;
+    bool bk_aux = false;  // bucket records carried neighbour bases: pending pairs only need the unique-seed bitmap test
     // bucket replay (replay.cu)
     DevBuf rp_ctr, rp_bitmap, rp_list, rp_canon, rp_keys_b, rp_idx_a, rp_idx_b, rp_p0, rp_row, rp_bkeys, rp_pool, rp_extra, rp_prefix, rp_vinfo, rp_out;
     unsigned long long* h_replay = nullptr;  // pinned, 8 entries

@@ -36,6 +36,9 @@ constexpr int BK_D3 = 10;
 
 struct BkPlan {
     int kbits, d1, d2, d3, pbits, rem1;
+    int aux;     // 4 neighbour-base bits per record (solid seeds only, when they fit), else 0
+    int kshift;  // pbits + 2 + aux: where the key remainder starts
+    int w;       // seed weight
     u32 B1, B2;
     u64 npos0, npos1, ntot;
     u64 npad0, nidx;  // genome-0 positions padded to a multiple of 16 so that a thread's 16 consecutive positions share 3 packed words
@@ -77,6 +80,7 @@ struct BkWindow {
         lo = __ldg(packed + k + 2);
     }
     __device__ __forceinline__ u64 mer(int j) const { return j ? ((hi << (2 * j)) | ((u64)lo >> (32 - 2 * j))) : hi; }
+    __device__ __forceinline__ u32 base(int j) const { return j < 32 ? (u32)(hi >> (62 - 2 * j)) & 3u : (lo >> (94 - 2 * j)) & 3u; }  // j < 48
 };
 
 // ---- level 1 ----------------------------------------------------------------------------------------------
@@ -229,7 +233,11 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter1_kernel(const u32* _
         const u32 g = idx0 >= pl.npad0;
         const u64 pos = g ? idx0 - pl.npad0 : idx0, npos = g ? pl.npos1 : pl.npos0;
         BkWindow w;
-        if (idx0 < pl.nidx) w.load(g ? g1 : g0, pos);
+        u32 prevbase = 0;
+        if (idx0 < pl.nidx) {
+            w.load(g ? g1 : g0, pos);
+            if (pl.aux && pos > 0) prevbase = base_at(g ? g1 : g0, (i64)pos - 1);
+        }
 #pragma unroll
         for (int it = 0; it < BK_IPT; ++it) {
             br[it] = 0xffffffffu;
@@ -240,7 +248,12 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter1_kernel(const u32* _
                 const u32 b = (u32)(canon >> pl.rem1);
                 if (b >= b_lo && b < b_hi) {
                     const u64 keyrem = canon & ((1ull << pl.rem1) - 1);
-                    rec[it] = (keyrem << (pl.pbits + 2)) | ((pos + it) << 2) | ((u64)strand << 1) | (u64)g;
+                    u64 aux = 0;
+                    if (pl.aux) {  // base before the seed | base after the seed << 2 (solid seeds: what a shift by one position adds)
+                        const u32 prev = it ? w.base(it - 1) : prevbase;
+                        aux = prev | (w.base(it + pl.w) << 2);
+                    }
+                    rec[it] = (keyrem << pl.kshift) | (aux << (pl.pbits + 2)) | ((pos + it) << 2) | ((u64)strand << 1) | (u64)g;
                     br[it] = (b << 16) | atomicAdd(&s.cnt[b], 1u);
                 }
             }
@@ -289,7 +302,7 @@ __global__ void __launch_bounds__(BK_THREADS) bk_hist2_kernel(const u64* __restr
     extern __shared__ u32 sh[];
     const u64 nrec = meta->nrec;
     const u32 b_lo = meta->b_lo;
-    const int shift = pl.pbits + 2 + pl.rem1 - pl.d2;
+    const int shift = pl.kshift + pl.rem1 - pl.d2;
     for (u64 base = (u64)blockIdx.x * BK_SUPER; base < nrec; base += (u64)gridDim.x * BK_SUPER) {
         const u64 end = min(base + (u64)BK_SUPER, nrec);
         u64 i0 = base;
@@ -345,7 +358,7 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter2_kernel(const u64* _
     const u32 tid = threadIdx.x;
     const u64 nrec = meta->nrec;
     const u32 b_lo = meta->b_lo;
-    const int shift = pl.pbits + 2 + pl.rem1 - pl.d2;
+    const int shift = pl.kshift + pl.rem1 - pl.d2;
     const u64 base = (u64)blockIdx.x * BK_TILE;
     if (base >= nrec) return;
     const u64 end = min(base + (u64)BK_TILE, nrec);
@@ -398,19 +411,23 @@ struct BkGroupArgs {
     u64* pairs;
     u64 pair_cap;
     unsigned long long* counters;  // [0] fwd pairs, [1] repeat flag, [6] rev pairs
+    u64* cand;                     // candidate list (aux mode fills it directly with the pairs whose left neighbour is no hit)
+    u64 cand_cap;
     u32* spill_list;               // final buckets larger than BK_CAP
-    unsigned long long* spill;     // [0] buckets, [1] records
+    unsigned long long* spill;     // [0] buckets, [1] records, [2] convert cursor, [3] direct candidates
 };
 
 constexpr int BK_GIPT = BK_CAP / BK_THREADS;  // records per thread in bk_group
+constexpr int BK_DIRECT = 64;                 // per-bucket buffer for pairs that are candidates for certain
 
 __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, BkPlan pl)
 {
     __shared__ u64 stage[BK_CAP];
     __shared__ u64 outp[BK_CAP / 2];        // pairs of this bucket: forward from the front, reverse from the back
     __shared__ u32 sofs[(1 << BK_D3) + 1];  // bin counts first, exclusive offsets after the scan
-    __shared__ u32 s_warp[8], s_np[2];
-    __shared__ unsigned long long s_base[2];
+    __shared__ u32 s_warp[8], s_np[2], s_nc[2];
+    __shared__ unsigned long long s_base[4];
+    __shared__ u64 candp[2][BK_DIRECT];     // pairs that are certainly candidates (aux mode)
     const u64 f = blockIdx.x;
     if (f >= a.meta->nfinal) return;
     const u64 beg = a.off2[f];
@@ -424,13 +441,13 @@ __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, 
         }
         return;
     }
-    const int kshift = pl.pbits + 2;
+    const int kshift = pl.kshift;
     const u32 nsub = 1u << pl.d3;
     const int dshift = kshift + pl.rem1 - pl.d2 - pl.d3;
     const u64 samekey = 1ull << kshift;  // two records carry the same mer iff (x ^ y) < samekey
     const u32 posmask = (u32)((1ull << pl.pbits) - 1);
     for (u32 i = tid; i <= nsub; i += BK_THREADS) sofs[i] = 0;
-    if (tid < 2) s_np[tid] = 0;
+    if (tid < 2) { s_np[tid] = 0; s_nc[tid] = 0; }
     __syncthreads();
     {   // counting split on the next d3 key bits: sub-groups of ~1 record, all records of one mer in one sub-group
         u64 rec[BK_GIPT];
@@ -498,19 +515,43 @@ __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, 
         }
         if (c0 + c1 > 1000) repeat = 1;
         if (c0 == 1 && c1 == 1) {
-            const u64 e = (u64)((u32)(r >> 2) & posmask) | ((u64)((u32)(r1 >> 2) & posmask) << 32);
-            if ((r ^ r1) & 2) outp[BK_CAP / 2 - 1 - atomicAdd(&s_np[1], 1u)] = e;
+            const u32 p0 = (u32)(r >> 2) & posmask, p1 = (u32)(r1 >> 2) & posmask;
+            const u64 e = (u64)p0 | ((u64)p1 << 32);
+            const u32 rev = (u32)((r ^ r1) >> 1) & 1u;
+            bool direct = false;
+            if (pl.aux) {
+                // solid seed: the left neighbour on the diagonal is a hit iff the one new base agrees; if it does not,
+                // this pair is certainly the leftmost seed of its hit run -> straight to the candidate list
+                const u32 a0 = (u32)(r >> (pl.pbits + 2)) & 15u, a1 = (u32)(r1 >> (pl.pbits + 2)) & 15u;
+                bool agree;
+                if (!rev) agree = p0 > 0 && p1 > 0 && (a0 & 3u) == (a1 & 3u);
+                else agree = p0 > 0 && (u64)p1 + 1 < pl.npos1 && (a0 & 3u) == 3u - (a1 >> 2);
+                direct = !agree;
+            }
+            if (direct) {
+                const u32 k = atomicAdd(&s_nc[rev], 1u);
+                if (k < BK_DIRECT) candp[rev][k] = e;
+                else if (!rev) a.cand[atomicAdd(&a.counters[2], 1ull)] = e;   // overflow of the small shared buffer: rare
+                else a.cand[a.cand_cap - 1 - atomicAdd(&a.counters[7], 1ull)] = e;
+                atomicOr(&a.uniq[p0 >> 5], 1u << (p0 & 31));
+            } else if (rev) outp[BK_CAP / 2 - 1 - atomicAdd(&s_np[1], 1u)] = e;
             else outp[atomicAdd(&s_np[0], 1u)] = e;
         }
     }
     if (__any_sync(0xffffffffu, repeat) && lane == 0) atomicMax(&a.counters[1], 1ull);
     __syncthreads();
     const u32 nf = s_np[0], nr = s_np[1];
+    const u32 ncf = min(s_nc[0], (u32)BK_DIRECT), ncr = min(s_nc[1], (u32)BK_DIRECT);
     if (tid == 0) {
         s_base[0] = nf ? atomicAdd(&a.counters[0], (unsigned long long)nf) : 0ull;
         s_base[1] = nr ? atomicAdd(&a.counters[6], (unsigned long long)nr) : 0ull;
+        s_base[2] = ncf ? atomicAdd(&a.counters[2], (unsigned long long)ncf) : 0ull;
+        s_base[3] = ncr ? atomicAdd(&a.counters[7], (unsigned long long)ncr) : 0ull;
+        if (s_nc[0] + s_nc[1]) atomicAdd(&a.spill[3], (unsigned long long)(s_nc[0] + s_nc[1]));
     }
     __syncthreads();
+    if (tid < ncf) a.cand[s_base[2] + tid] = candp[0][tid];
+    if (tid < ncr) a.cand[a.cand_cap - 1 - (s_base[3] + tid)] = candp[1][tid];
     const u64 bf = s_base[0], br2 = s_base[1];
     for (u32 j = tid; j < nf; j += BK_THREADS) {
         const u64 e = outp[j];
@@ -540,7 +581,7 @@ __global__ void __launch_bounds__(BK_THREADS) bk_spill_kernel(const u64* __restr
     const u64 posmask = (1ull << pl.pbits) - 1;
     for (u64 i = threadIdx.x; i < nb; i += blockDim.x) {
         const u64 r = recs[beg + i];
-        const u64 mixed = (b1 << pl.rem1) | (r >> (pl.pbits + 2));  // the mixed mer: equal exactly when the mers are equal
+        const u64 mixed = (b1 << pl.rem1) | (r >> pl.kshift);  // the mixed mer: equal exactly when the mers are equal
         keys[s_base + i] = (mixed << 2) | ((r & 1) << 1) | ((r >> 1) & 1);
         vals[s_base + i] = (u32)((r >> 2) & posmask);
     }
@@ -566,9 +607,13 @@ static bool make_plan(const SeedParams& sp, u64 npos0, u64 npos1, BkPlan* out)
     if (T > p.kbits - 2) T = p.kbits - 2;    // keep key bits for the in-bucket comparison
     if (T < 2 || T > 22) return false;
     p.d1 = (T + 1) / 2;
-    // the record must fit 64 bits: (kbits - d1) + strand + genome + pbits
-    while (p.kbits - p.d1 + 2 + p.pbits > 64 && p.d1 < 11 && p.d1 < T) ++p.d1;
-    if (p.kbits - p.d1 + 2 + p.pbits > 64) return false;
+    p.w = sp.w;
+    const bool solid = sp.nruns == 1 && sp.L == sp.w && (sp.w & 1) && getenv("MAUVE_CUDA_NO_SOLID") == nullptr;
+    p.aux = solid && p.kbits - p.d1 + 2 + 4 + p.pbits <= 64 ? 4 : 0;
+    // the record must fit 64 bits: (kbits - d1) + aux + strand + genome + pbits
+    while (p.kbits - p.d1 + 2 + p.aux + p.pbits > 64 && p.d1 < 11 && p.d1 < T) ++p.d1;
+    if (p.kbits - p.d1 + 2 + p.aux + p.pbits > 64) return false;
+    p.kshift = p.pbits + 2 + p.aux;
     p.d2 = T - p.d1;
     if (p.d1 > 11 || p.d2 > 11 || p.d2 < 0) return false;
     p.rem1 = p.kbits - p.d1;
@@ -638,6 +683,7 @@ int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_co
     BkGroupArgs ga;
     ga.recs = s.bk_b.as<u64>(); ga.off2 = off2; ga.meta = meta; ga.uniq = s.uniq.as<u32>(); ga.pairs = s.pairs.as<u64>(); ga.pair_cap = pair_cap;
     ga.counters = ctr; ga.spill_list = s.bk_spill.as<u32>(); ga.spill = spill;
+    ga.cand = s.cand.as<u64>(); ga.cand_cap = pair_cap;
     bk_group_kernel<<<(unsigned)nfinal_max, BK_THREADS, 0, st>>>(ga, pl);
     MCU_CUDA(cudaEventRecord(s.kev[5], st));
     s.launches += 8;
@@ -649,6 +695,8 @@ int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_co
     MCU_CUDA(cudaStreamSynchronize(st));
     *nrecords = h.meta.nrec;
     s.bk_spilled = h.spill[1];
+    s.bk_direct = h.spill[3];
+    s.bk_aux = pl.aux != 0;
     if (h.spill[0]) {
         const u64 ns = h.spill[1];
         MCU_TRY(s.keys_a.reserve((ns + 1) * 8));

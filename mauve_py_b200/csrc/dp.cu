@@ -38,6 +38,7 @@ constexpr int NW_R = 8;
 constexpr int NW_STRIPE = 32 * NW_R;
 constexpr int NW_NINF = -(1 << 29);  // never beats a real score (|score| < 2^23), never overflows
 constexpr int NW_WARPS = 8;
+constexpr int NW_COOP_STRIPES = 3;  // regions with at least this many stripes are pipelined across the warps of a CTA
 constexpr unsigned FULL = 0xffffffffu;
 
 struct NwArgs {
@@ -47,8 +48,10 @@ struct NwArgs {
     const u64* b_off;
     const u32* order;   // problems sorted by descending cell count
     u32 first, count;   // slice of `order` handled by this launch
+    const uint2* units; // work units of this launch: one long region for the whole CTA, or up to NW_WARPS short ones
+    u32 nunits;
     u32* tb;            // traceback words
-    const u64* tb_off;  // per slot of `order`: word offset into tb
+    const u64* tb_off;  // per slot of `order` (absolute index): word offset into tb
     int4* boundary;     // per warp 2 x bstride entries {M-400, D', best(shifted by one column), -}
     u64 bstride;
     int4* result;       // per problem {M, D, I, -} at (la, lb)
@@ -103,107 +106,164 @@ __device__ __forceinline__ u32 nw_rows(const u32 (&asel)[NW_R], int (&Ml)[NW_R],
     return tbw;
 }
 
+// One region.  `rank`/`team` = this warp's index and the number of warps sharing the region: warp k takes the stripes
+// k, k+team, ... and, when team > 1, follows the warp working on the stripe above through `progress` (columns of that
+// stripe whose bottom row is already in the boundary buffer), so a long region keeps a whole CTA busy as a pipeline
+// of stripes instead of one warp.
+struct NwProblem {
+    const u8* A;
+    const u8* B;
+    u32 la, lb;
+    u32* tb;
+    int4* bnd[2];   // boundary rows, alternating by stripe parity
+    int4* result;
+};
+
+__device__ __forceinline__ void nw_region(const NwProblem& P, u32 rank, u32 team, int4 (*ring)[32], volatile unsigned long long* progress, u32& bad)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u32 la = P.la, lb = P.lb;
+    const u32 T = lb + 31;
+    const u32 nstripes = (la + NW_STRIPE - 1) / NW_STRIPE;
+    const u32 fin_lane = ((la - 1) % NW_STRIPE) / NW_R;
+    const int fin_r = (int)((la - 1) % NW_R);
+    int capM = 0, capD = 0, capI = 0;
+    for (u32 s = rank; s < nstripes; s += team) {
+        const u32 i0 = s * NW_STRIPE + lane * NW_R;
+        u32 asel[NW_R];
+        int Ml[NW_R], Il[NW_R], Bp[NW_R];
+#pragma unroll
+        for (int r = 0; r < NW_R; ++r) {
+            u32 c = 0;
+            if (i0 + r < la) c = dna_code(P.A[i0 + r], bad);
+            asel[r] = 0x4440u | c;
+            Ml[r] = NW_NINF;   // M[i][0] - 400
+            Il[r] = NW_NINF;   // I'[i][0]
+            Bp[r] = -200;      // best[i][0]
+        }
+        int diag = -200, out_M = NW_NINF, out_D = NW_NINF, out_B = -200;
+        u32 sb_cur = 0;
+        const int4* bprev = P.bnd[(s + 1) & 1];
+        int4* bcur = P.bnd[s & 1];
+        const bool last = s + 1 == nstripes;
+        const u32 cap_t = lb - 1 + fin_lane;
+        u32* tbs = P.tb + (u64)s * T * 32 + lane;
+        for (u32 t = 0; t < T; ++t) {
+            if ((t & 31u) == 0) {
+                // stage the inputs of lane 0 for columns t+1 .. t+32: the row above this stripe
+                const u32 jk = t + 1 + lane;
+                if (team > 1 && s > 0) {  // wait until the stripe above has published these columns
+                    const u32 need = min(t + 32, lb);
+                    const unsigned long long want = ((unsigned long long)s << 32) | need;  // tag = stripe index + 1 of the producer
+                    while (true) {
+                        const unsigned long long v = progress[(s - 1) & 31];
+                        if ((v >> 32) == s && (u32)v >= need) break;
+                        (void)want;
+                    }
+                    __syncwarp();
+                }
+                int4 v = make_int4(NW_NINF, NW_NINF, -200, 0);
+                if (jk <= lb) {
+                    u32 bb = 0;
+                    v.w = (int)sub_column(dna_code(P.B[jk - 1], bb));
+                    if (s == 0) bad |= bb;
+                    if (s == 0) {
+                        if (jk == 1 && la > 1) v.z = 0;
+                    } else {
+                        const int4 q = __ldcg(bprev + jk);
+                        v.x = q.x;
+                        v.y = q.y;
+                        if (jk > 1) v.z = q.z;
+                    }
+                }
+                ring[(t >> 5) & 1][lane] = v;
+                __syncwarp();
+            }
+            int upM = __shfl_up_sync(FULL, out_M, 1);
+            int upD = __shfl_up_sync(FULL, out_D, 1);
+            const int upB = __shfl_up_sync(FULL, out_B, 1);
+            u32 sb = __shfl_up_sync(FULL, sb_cur, 1);  // the substitution column travels with the wavefront
+            int dg = diag;
+            diag = upB;  // best[i0][j] of the lane above: the diagonal input of the next column
+            if (lane == 0) {
+                const int4 v = ring[(t >> 5) & 1][t & 31u];
+                upM = v.x;
+                upD = v.y;
+                dg = v.z;
+                sb = (u32)v.w;
+            }
+            sb_cur = sb;
+            const int j = (int)t - (int)lane + 1;
+            if (j >= 1 && j <= (int)lb) {
+                u32 tbw;
+                if (last && t == cap_t)
+                    tbw = nw_rows<true>(asel, Ml, Il, Bp, sb, upM, upD, dg, out_B, fin_r, capM, capD, capI);
+                else
+                    tbw = nw_rows<false>(asel, Ml, Il, Bp, sb, upM, upD, dg, out_B, fin_r, capM, capD, capI);
+                out_M = upM;
+                out_D = upD;
+                __stcs(tbs + (u64)t * 32, tbw);
+                if (lane == 31 && !last) {
+                    *(int2*)(bcur + j) = make_int2(out_M, out_D);
+                    bcur[j + 1].z = out_B;
+                }
+            }
+            if (team > 1 && !last && ((t & 31u) == 31u || t + 1 == T)) {
+                // publish: lane 31 has finished columns 1 .. t-30
+                __syncwarp();
+                if (lane == 31 && t >= 31) {
+                    __threadfence_block();
+                    progress[s & 31] = ((unsigned long long)(s + 1) << 32) | (t - 30);
+                }
+            }
+        }
+        __threadfence_block();
+        __syncwarp();
+    }
+    if ((nstripes - 1) % team == rank && lane == fin_lane) *P.result = make_int4(capM, capD + 200, capI + 200, 0);
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(NW_WARPS * 32, 2) nw_forward_kernel(NwArgs g)
 {
     __shared__ int4 ring_s[NW_WARPS][2][32];
+    __shared__ unsigned long long progress[32];
+    __shared__ u32 s_unit;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 gwarp = (u64)blockIdx.x * NW_WARPS + warp;
-    int4* const bnd = g.boundary + gwarp * 2 * g.bstride;
-    int4(*ring)[32] = ring_s[warp];
+    const u64 cta_w0 = (u64)blockIdx.x * NW_WARPS;
     u32 bad = 0;
     for (;;) {
-        u32 k = 0;
-        if (lane == 0) k = atomicAdd(g.counter, 1u);
-        k = __shfl_sync(FULL, k, 0);
-        if (k >= g.count) break;
-        const u32 p = g.order[g.first + k];
+        __syncthreads();
+        if (threadIdx.x == 0) s_unit = atomicAdd(g.counter, 1u);
+        if (threadIdx.x < 32) progress[threadIdx.x] = 0;
+        __syncthreads();
+        const u32 u = s_unit;
+        if (u >= g.nunits) break;
+        const uint2 unit = g.units[u];  // x = first slot in `order`, y = count (bit 31: cooperative)
+        const bool coop = unit.y >> 31;
+        const u32 count = unit.y & 0x7fffffffu;
+        const u32 slot = coop ? unit.x : unit.x + warp;
+        if (!coop && warp >= count) continue;
+        const u32 p = g.order[slot];
         const u64 ao = g.a_off[p], bo = g.b_off[p];
-        const u32 la = (u32)(g.a_off[p + 1] - ao), lb = (u32)(g.b_off[p + 1] - bo);
-        const u8* __restrict__ A = g.a + ao;
-        const u8* __restrict__ B = g.b + bo;
-        u32* __restrict__ tb = g.tb + g.tb_off[k];
-        const u32 T = lb + 31;
-        const u32 nstripes = (la + NW_STRIPE - 1) / NW_STRIPE;
-        const u32 fin_lane = ((la - 1) % NW_STRIPE) / NW_R;
-        const int fin_r = (int)((la - 1) % NW_R);
-        int capM = 0, capD = 0, capI = 0;
-        for (u32 s = 0; s < nstripes; ++s) {
-            const u32 i0 = s * NW_STRIPE + lane * NW_R;
-            u32 asel[NW_R];
-            int Ml[NW_R], Il[NW_R], Bp[NW_R];
-#pragma unroll
-            for (int r = 0; r < NW_R; ++r) {
-                u32 c = 0;
-                if (i0 + r < la) c = dna_code(A[i0 + r], bad);
-                asel[r] = 0x4440u | c;
-                Ml[r] = NW_NINF;   // M[i][0] - 400
-                Il[r] = NW_NINF;   // I'[i][0]
-                Bp[r] = -200;      // best[i][0]
-            }
-            int diag = -200, out_M = NW_NINF, out_D = NW_NINF, out_B = -200;
-            u32 bc_cur = 0;
-            const int4* bprev = bnd + (u64)((s + 1) & 1) * g.bstride;
-            int4* bcur = bnd + (u64)(s & 1) * g.bstride;
-            const bool last = s + 1 == nstripes;
-            const u32 cap_t = lb - 1 + fin_lane;
-            u32* tbs = tb + (u64)s * T * 32 + lane;
-            for (u32 t = 0; t < T; ++t) {
-                if ((t & 31u) == 0) {
-                    // stage the inputs of lane 0 for columns t+1 .. t+32: the row above this stripe
-                    const u32 jk = t + 1 + lane;
-                    int4 v = make_int4(NW_NINF, NW_NINF, -200, 0);
-                    if (jk <= lb) {
-                        u32 bb = 0;
-                        v.w = (int)dna_code(B[jk - 1], bb);
-                        if (s == 0) bad |= bb;
-                        if (s == 0) {
-                            if (jk == 1 && la > 1) v.z = 0;
-                        } else {
-                            int4 q = __ldcg(bprev + jk);
-                            v.x = q.x;
-                            v.y = q.y;
-                            if (jk > 1) v.z = q.z;
-                        }
-                    }
-                    ring[(t >> 5) & 1][lane] = v;
-                    __syncwarp();
-                }
-                int upM = __shfl_up_sync(FULL, out_M, 1);
-                int upD = __shfl_up_sync(FULL, out_D, 1);
-                const int upB = __shfl_up_sync(FULL, out_B, 1);
-                u32 bc = __shfl_up_sync(FULL, bc_cur, 1);
-                int dg = diag;
-                diag = upB;  // best[i0][j] of the lane above: the diagonal input of the next column
-                if (lane == 0) {
-                    const int4 v = ring[(t >> 5) & 1][t & 31u];
-                    upM = v.x;
-                    upD = v.y;
-                    dg = v.z;
-                    bc = (u32)v.w;
-                }
-                bc_cur = bc;
-                const int j = (int)t - (int)lane + 1;
-                if (j >= 1 && j <= (int)lb) {
-                    const u32 sb = sub_column(bc);
-                    u32 tbw;
-                    if (last && t == cap_t)
-                        tbw = nw_rows<true>(asel, Ml, Il, Bp, sb, upM, upD, dg, out_B, fin_r, capM, capD, capI);
-                    else
-                        tbw = nw_rows<false>(asel, Ml, Il, Bp, sb, upM, upD, dg, out_B, fin_r, capM, capD, capI);
-                    out_M = upM;
-                    out_D = upD;
-                    tbs[(u64)t * 32] = tbw;
-                    if (lane == 31 && !last) {
-                        *(int2*)(bcur + j) = make_int2(out_M, out_D);
-                        bcur[j + 1].z = out_B;
-                    }
-                }
-            }
-            __threadfence_block();
-            __syncwarp();
+        NwProblem P;
+        P.A = g.a + ao;
+        P.B = g.b + bo;
+        P.la = (u32)(g.a_off[p + 1] - ao);
+        P.lb = (u32)(g.b_off[p + 1] - bo);
+        P.tb = g.tb + g.tb_off[slot];
+        P.result = g.result + p;
+        if (coop) {  // the CTA shares the boundary buffers of its first two warps
+            P.bnd[0] = g.boundary + (cta_w0 * 2) * g.bstride;
+            P.bnd[1] = g.boundary + (cta_w0 * 2 + 1) * g.bstride;
+            nw_region(P, warp, NW_WARPS, ring_s[warp], progress, bad);
+        } else {
+            P.bnd[0] = g.boundary + (gwarp * 2) * g.bstride;
+            P.bnd[1] = g.boundary + (gwarp * 2 + 1) * g.bstride;
+            nw_region(P, 0, 1, ring_s[warp], progress, bad);
         }
-        if (lane == fin_lane) g.result[p] = make_int4(capM, capD + 200, capI + 200, 0);
-        __syncwarp();
+        (void)lane;
     }
     if (bad) atomicOr(g.err, 1u);
 }
@@ -305,7 +365,7 @@ __global__ void __launch_bounds__(256) nw_shift_kernel(const u32* order, u32 fir
 
 // ---- host driver ---------------------------------------------------------------------------
 struct NwState {
-    DevBuf a, b, a_off, b_off, order, tb, tb_off, boundary, result, counter, path_off, path, path_len, path_start, score;
+    DevBuf a, b, a_off, b_off, order, tb, tb_off, boundary, result, counter, path_off, path, path_len, path_start, score, units;
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     u64 stats[5] = {0, 0, 0, 0, 0};
@@ -385,6 +445,27 @@ int nw_batch(u64 n, const char* a, const u64* a_off, const char* b, const u64* b
     const int ctas = sm_count() * 2;
     const u64 nwarps = (u64)ctas * NW_WARPS;
     const u64 bstride = max_lb + 4;
+    // work units per sub-batch: a region of >= NW_COOP_STRIPES stripes occupies a whole CTA (its warps pipeline the stripes),
+    // shorter regions are handed out NW_WARPS at a time (neighbours in the sorted order have similar sizes)
+    std::vector<uint2> units;
+    std::vector<std::pair<u32, u32>> unit_ranges;  // per sub-batch: (first unit, unit count)
+    for (auto& bt : batches) {
+        const u32 u0 = (u32)units.size();
+        u32 i = bt.first;
+        const u32 end = bt.first + bt.second;
+        while (i < end) {
+            const u64 la = a_off[order[i] + 1] - a_off[order[i]];
+            if (div_up(la, NW_STRIPE) >= NW_COOP_STRIPES) {
+                units.push_back(make_uint2(i, 1u | 0x80000000u));
+                ++i;
+            } else {
+                const u32 c = std::min<u32>(NW_WARPS, end - i);
+                units.push_back(make_uint2(i, c));
+                i += c;
+            }
+        }
+        unit_ranges.push_back({u0, (u32)units.size() - u0});
+    }
     MCU_TRY(st.a.reserve(abytes + 16));
     MCU_TRY(st.b.reserve(bbytes + 16));
     MCU_TRY(st.a_off.reserve((n + 1) * 8));
@@ -398,6 +479,7 @@ int nw_batch(u64 n, const char* a, const u64* a_off, const char* b, const u64* b
     MCU_TRY(st.score.reserve(n * 8));
     MCU_TRY(st.path.reserve(pbytes + 16));
     MCU_TRY(st.counter.reserve(256));
+    MCU_TRY(st.units.reserve(units.size() * sizeof(uint2) + 16));
     MCU_TRY(st.boundary.reserve(nwarps * 2 * bstride * sizeof(int4)));
     MCU_TRY(st.tb.reserve(max_batch_words * 4 + 16));
 
@@ -408,6 +490,7 @@ int nw_batch(u64 n, const char* a, const u64* a_off, const char* b, const u64* b
     MCU_CUDA(cudaMemcpyAsync(st.path_off.p, path_off, (n + 1) * 8, cudaMemcpyHostToDevice, s));
     MCU_CUDA(cudaMemcpyAsync(st.order.p, order.data(), n * 4, cudaMemcpyHostToDevice, s));
     MCU_CUDA(cudaMemcpyAsync(st.tb_off.p, tb_off.data(), n * 8, cudaMemcpyHostToDevice, s));
+    MCU_CUDA(cudaMemcpyAsync(st.units.p, units.data(), units.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
     MCU_CUDA(cudaMemsetAsync(st.counter.p, 0, 256, s));
 
     MCU_CUDA(cudaEventRecord(st.e0, s));
@@ -420,15 +503,15 @@ int nw_batch(u64 n, const char* a, const u64* a_off, const char* b, const u64* b
         fa.a = st.a.as<u8>(); fa.b = st.b.as<u8>();
         fa.a_off = st.a_off.as<u64>(); fa.b_off = st.b_off.as<u64>();
         fa.order = st.order.as<u32>(); fa.first = bt.first; fa.count = bt.second;
-        fa.tb = st.tb.as<u32>(); fa.tb_off = st.tb_off.as<u64>() + bt.first;
+        fa.tb = st.tb.as<u32>(); fa.tb_off = st.tb_off.as<u64>();
+        fa.units = st.units.as<uint2>() + unit_ranges[bi].first; fa.nunits = unit_ranges[bi].second;
         fa.boundary = st.boundary.as<int4>(); fa.bstride = bstride;
         fa.result = st.result.as<int4>(); fa.counter = counter; fa.err = ctr + 32;
-        u64 want = div_up(bt.second, NW_WARPS);
-        int grid = (int)std::min<u64>(want, (u64)ctas);
+        int grid = (int)std::min<u64>(fa.nunits, (u64)ctas);
         nw_forward_kernel<<<grid, NW_WARPS * 32, 0, s>>>(fa);
         TbArgs ta;
         ta.a_off = fa.a_off; ta.b_off = fa.b_off; ta.order = fa.order; ta.first = bt.first; ta.count = bt.second;
-        ta.tb = fa.tb; ta.tb_off = fa.tb_off; ta.result = fa.result; ta.path_off = st.path_off.as<u64>();
+        ta.tb = fa.tb; ta.tb_off = fa.tb_off + bt.first; ta.result = fa.result; ta.path_off = st.path_off.as<u64>();
         ta.path = st.path.as<char>(); ta.path_len = st.path_len.as<u32>(); ta.path_start = st.path_start.as<u64>();
         ta.score = st.score.as<i64>();
         nw_traceback_kernel<<<(unsigned)div_up(bt.second, 128), 128, 0, s>>>(ta);
