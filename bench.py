@@ -151,7 +151,7 @@ def config_dict(args, weight, seed):
     return {"workload": "synthetic %g Mbp pair (BASELINE config 3 / SURVEY 8d C3: 0.9%% SNP, 0.1%% indel events, inversions, translocations), "
                         "default seed weight %d rank CODING_SEED -> pattern 0x%x" % (args.mbp, weight, seed),
             "genome_bp": int(args.mbp * 1e6), "seed_weight": weight, "seed_pattern": hex(seed),
-            "sharding": "seed-key prefix range per rank, NCCL gather of match rows to rank 0" if args.gpus > 1 else "none",
+            "sharding": "seed-key slice per rank; NCCL all-reduce of the 1-bit/base unique-seed bitmap, NCCL gather of match rows to rank 0" if args.gpus > 1 else "none",
             "l2": "inputs (2 x %g MB ASCII, %.1f GB of key/value pairs) exceed the 126 MB L2; no extra flush" % (args.mbp, 2 * args.mbp * 12e6 / 1e9)}
 
 
@@ -211,20 +211,9 @@ def main():
     shard, nshard = mdist.shard_of(rank, world)
 
     def step_resident():
-        n = sess.run(seed, shard, nshard)
         if world == 1:
-            return n, None
-        rows = torch.empty((n, 3), dtype=torch.int64, device="cuda")
-        sess_copy_device(sess, rows)
-        allrows = mdist.gather_rows(rows, 0)
-        if rank == 0:
-            merged = mp.merge_matches(allrows.data_ptr(), in_device=True, n=allrows.shape[0])
-            return merged.shape[0], merged
-        return n, None
-
-    def sess_copy_device(s, rows):
-        if rows.shape[0]:
-            s.download_ptr(rows.data_ptr())  # device-to-device (cudaMemcpyDefault)
+            return sess.run(seed, shard, nshard), None
+        return mdist.run_sharded(sess, seed, rank, world), None
 
     # ---- value: device-resident inputs --------------------------------------------------------
     for _ in range(args.warmup):
@@ -378,7 +367,7 @@ def main():
         "data": "synthetic", "config": config_dict(args, weight, seed), "matches": int(nmatch), "seed_pairs": int(stats[0]),
         "device_ms_per_step": dev_ms,
         "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": int(nbases), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * dte / args.steps, "api": "mcu_find_mums(host buffers)" if world == 1 else "mcu_session_upload+run, NCCL gather, mcu_merge_matches"},
+                "ms_per_step": 1e3 * dte / args.steps, "api": "mcu_find_mums(host buffers)" if world == 1 else "mcu_session_upload + enumerate, NCCL all-reduce of the seed bitmap, finish, NCCL gather, mcu_session_merge"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "dp": dp, "hmm": hmm,
     }
     print(json.dumps(line))

@@ -107,6 +107,20 @@ int mcu_session_upload(mcu_session* s, const char* seq0, uint64_t n0, const char
  * Leaves the ordered match list on the device.                                               */
 int mcu_session_run(mcu_session* s, uint64_t seed, int shard_index, int shard_count,
                     float* stage_ms, uint64_t* stats);
+/* The same run in two phases, for multi-GPU use.  mcu_session_enumerate: pack + enumeration of the unique seed pairs
+ * whose (mixed) mer falls in this rank's slice.  Extension needs to know about unique seeds of ALL slices (a match is
+ * emitted by its leftmost unique seed, wherever that seed's mer hashes), so between the phases the ranks combine their
+ * unique-seed bitmaps: mcu_session_uniq_bitmap exposes the device buffer (n_words x uint32); the slices' bits are
+ * disjoint, so a SUM all-reduce of the words is their OR.  mcu_session_finish(uniq_is_global != 0) then runs candidates +
+ * extension + ordering; every match is found by exactly one rank.  mcu_session_run == enumerate + finish(0).            */
+int mcu_session_enumerate(mcu_session* s, uint64_t seed, int shard_index, int shard_count);
+int mcu_session_uniq_bitmap(mcu_session* s, void** device_words_out, uint64_t* n_words_out);
+int mcu_session_finish(mcu_session* s, int uniq_is_global, float* stage_ms, uint64_t* stats);
+/* Rank-0 merge for runs finished with a global bitmap: `rows` = concatenation of the ranks' lists (device or host
+ * pointer).  Orders them into the reference list order and replays order-dependent hash buckets exactly (csrc/replay.cu),
+ * using this session's genomes and bitmap.  The result replaces the session's match list (mcu_session_match_count /
+ * mcu_session_download).  stats2 (optional, 2 x uint64): [0] buckets replayed, [1] duplicate rows added.          */
+int mcu_session_merge(mcu_session* s, const mcu_match* rows, uint64_t n, int in_device, uint64_t* stats2);
 /* number of matches produced by the last run */
 uint64_t mcu_session_match_count(const mcu_session* s);
 /* copy of the match list into caller memory, host or device (n = mcu_session_match_count rows). */

@@ -21,6 +21,7 @@ SYMBOLS = [
     "mcu_get_seed", "mcu_default_seed_weight", "mcu_seed_length", "mcu_seed_weight",
     "mcu_sml_build", "mcu_find_mums",
     "mcu_session_create", "mcu_session_destroy", "mcu_session_upload", "mcu_session_run",
+    "mcu_session_enumerate", "mcu_session_uniq_bitmap", "mcu_session_finish", "mcu_session_merge",
     "mcu_session_match_count", "mcu_session_download", "mcu_session_matches_device",
     "mcu_session_launch_count", "mcu_merge_matches",
     "mcu_nw_batch", "mcu_nw_last_stats", "mcu_hmm_params", "mcu_hmm_batch", "mcu_test_sort_pairs",
@@ -71,6 +72,10 @@ def lib():
     L.mcu_session_destroy.restype = None
     L.mcu_session_upload.argtypes = [vp, vp, u64, vp, u64]
     L.mcu_session_run.argtypes = [vp, u64, i32, i32, vp, vp]
+    L.mcu_session_enumerate.argtypes = [vp, u64, i32, i32]
+    L.mcu_session_uniq_bitmap.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.mcu_session_finish.argtypes = [vp, i32, vp, vp]
+    L.mcu_session_merge.argtypes = [vp, vp, u64, i32, vp]
     L.mcu_session_match_count.argtypes = [vp]
     L.mcu_session_match_count.restype = u64
     L.mcu_session_download.argtypes = [vp, vp]

@@ -535,8 +535,9 @@ static int run_pack(Session& s, int g, u32* err_flag)
     return MCU_OK;
 }
 
+// Phase 1 of a run: pack + enumeration of the unique seed pairs of this rank's key range (uniq bitmap, pair list).
 template <typename K>
-static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int shard_count, float* stage_ms, u64* stats)
+static int run_enumerate(Session& s, const SeedParams& sp, int shard_index, int shard_count)
 {
     const u64 npos0 = s.n[0] >= (u64)sp.L ? s.n[0] - sp.L + 1 : 0;
     const u64 npos1 = s.n[1] >= (u64)sp.L ? s.n[1] - sp.L + 1 : 0;
@@ -621,11 +622,36 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
         }
     }
     MCU_CUDA(cudaEventRecord(s.ev[4], s.stream));
-
-    // ---- candidates + extend ----
     MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     MCU_CUDA(cudaStreamSynchronize(s.stream));
+    MCU_CUDA(cudaGetLastError());
     if (((u32*)(s.h_counters + 4))[0]) { set_error("gap character '-' in a genome sequence (input must be unaligned)"); return MCU_EGAP; }
+    s.run.sp = sp;
+    s.run.sharded = sharded;
+    s.run.bucketed = bucketed;
+    s.run.passes = passes_run;
+    s.run.nsort = nsort;
+    s.run.pair_cap = pair_cap;
+    s.run.uniq_words = uniq_words;
+    s.run.enumerated = true;
+    return MCU_OK;
+}
+
+// Phase 2: candidates -> extension -> reference list order (+ bucket replay when the bitmap covers the whole key space).
+static int run_finish(Session& s, bool uniq_is_global, float* stage_ms, u64* stats)
+{
+    if (!s.run.enumerated) { set_error("mcu_session_finish without mcu_session_enumerate"); return MCU_EINVAL; }
+    s.run.enumerated = false;
+    const SeedParams& sp = s.run.sp;
+    const u64 npos0 = s.n[0] >= (u64)sp.L ? s.n[0] - sp.L + 1 : 0;
+    const u64 npos1 = s.n[1] >= (u64)sp.L ? s.n[1] - sp.L + 1 : 0;
+    const bool sharded = s.run.sharded, bucketed = s.run.bucketed;
+    const int passes_run = s.run.passes;
+    const u64 nsort = s.run.nsort, pair_cap = s.run.pair_cap;
+    unsigned long long* ctr = s.counters.as<unsigned long long>();
+    s.run.uniq_global = uniq_is_global || !sharded;
+
+    // ---- candidates + extend ----
     const u64 pfwd = s.h_counters[0], prev_ = s.h_counters[6];
     const u64 npairs = pfwd + prev_ + s.bk_direct;  // bk_direct: pairs the bucket kernel already classified as candidates
     const u64 repeat_flag = s.h_counters[1];
@@ -661,7 +687,7 @@ static int run_pipeline(Session& s, const SeedParams& sp, int shard_index, int s
     // ---- order ----
     MCU_TRY(order_matches(s, s.raw_matches.as<mcu_match>(), nmatch));
     u64 unclean = 0, dup_rows = 0;
-    MCU_TRY(replay_unclean(s, &sp, !sharded, &unclean, &dup_rows));
+    MCU_TRY(replay_unclean(s, &sp, !sharded, &unclean, &dup_rows));  // sharded runs replay after the merge (session_merge)
     nmatch = s.match_count;
     MCU_CUDA(cudaEventRecord(s.ev[6], s.stream));
     MCU_CUDA(cudaStreamSynchronize(s.stream));
@@ -736,11 +762,31 @@ int order_matches(Session& s, const mcu_match* rows_dev, u64 n)
 
 int session_run(Session& s, u64 seed, int shard_index, int shard_count, float* stage_ms, u64* stats)
 {
+    MCU_TRY(session_enumerate(s, seed, shard_index, shard_count));
+    return run_finish(s, false, stage_ms, stats);
+}
+
+int session_enumerate(Session& s, u64 seed, int shard_index, int shard_count)
+{
     SeedParams sp;
     MCU_TRY(make_seed_params(seed, &sp));
     if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) { set_error("bad shard spec"); return MCU_EINVAL; }
-    if (2 * sp.w + 2 <= 32) return run_pipeline<u32>(s, sp, shard_index, shard_count, stage_ms, stats);
-    return run_pipeline<u64>(s, sp, shard_index, shard_count, stage_ms, stats);
+    if (2 * sp.w + 2 <= 32) return run_enumerate<u32>(s, sp, shard_index, shard_count);
+    return run_enumerate<u64>(s, sp, shard_index, shard_count);
+}
+
+int session_finish(Session& s, bool uniq_is_global, float* stage_ms, u64* stats) { return run_finish(s, uniq_is_global, stage_ms, stats); }
+
+// Rank-0 merge of the per-rank lists of one sharded run whose unique-seed bitmap was combined across ranks: every match
+// has exactly one emitter, so there is nothing to dedupe; order the rows and replay order-dependent buckets exactly.
+int session_merge(Session& s, const mcu_match* rows_dev, u64 n, u64* unclean, u64* dup_rows)
+{
+    *unclean = 0;
+    *dup_rows = 0;
+    MCU_TRY(order_matches(s, rows_dev, n));
+    MCU_TRY(replay_unclean(s, &s.run.sp, s.run.uniq_global, unclean, dup_rows));
+    MCU_CUDA(cudaStreamSynchronize(s.stream));
+    return MCU_OK;
 }
 
 // ---- single-genome SML --------------------------------------------------------------------

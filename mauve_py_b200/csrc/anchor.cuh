@@ -24,6 +24,12 @@ struct Session {
     u64 match_count = 0;
     u64 launches = 0;
     unsigned long long* h_counters = nullptr;  // pinned, 8 entries
+    struct RunState {  // carried from mcu_session_enumerate to mcu_session_finish / mcu_session_merge
+        SeedParams sp;
+        bool enumerated = false, sharded = false, bucketed = false, uniq_global = false;
+        int passes = 0;
+        u64 nsort = 0, pair_cap = 0, uniq_words = 0;
+    } run;
     bool ok = false;
     bool use_buckets = true;  // MAUVE_CUDA_SORT_PATH=1 forces the radix-sort + join enumeration
 };
@@ -32,6 +38,9 @@ int session_init(Session& s);
 void session_destroy(Session& s);
 int session_upload(Session& s, const char* seq0, u64 n0, const char* seq1, u64 n1);
 int session_run(Session& s, u64 seed, int shard_index, int shard_count, float* stage_ms, u64* stats);
+int session_enumerate(Session& s, u64 seed, int shard_index, int shard_count);
+int session_finish(Session& s, bool uniq_is_global, float* stage_ms, u64* stats);
+int session_merge(Session& s, const mcu_match* rows_dev, u64 n, u64* unclean, u64* dup_rows);
 // sorts rows (device, n of them) into reference list order; result in s.matches (device)
 int order_matches(Session& s, const mcu_match* rows_dev, u64 n);
 // join of an already sorted (key, position) array of 64-bit keys: appends to s.uniq / s.pairs / counters (anchor.cu)

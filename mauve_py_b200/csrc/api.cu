@@ -263,6 +263,45 @@ int mcu_session_run(mcu_session* h, uint64_t seed, int shard_index, int shard_co
     return session_run(h->s, seed, shard_index, shard_count, stage_ms, stats);
 }
 
+int mcu_session_enumerate(mcu_session* h, uint64_t seed, int shard_index, int shard_count)
+{
+    if (!h) return MCU_EINVAL;
+    MCU_TRY(ensure_device());
+    return session_enumerate(h->s, seed, shard_index, shard_count);
+}
+
+int mcu_session_uniq_bitmap(mcu_session* h, void** device_words_out, uint64_t* n_words_out)
+{
+    if (!h || !device_words_out || !n_words_out) return MCU_EINVAL;
+    *device_words_out = h->s.uniq.p;
+    *n_words_out = h->s.run.uniq_words;
+    return MCU_OK;
+}
+
+int mcu_session_finish(mcu_session* h, int uniq_is_global, float* stage_ms, uint64_t* stats)
+{
+    if (!h) return MCU_EINVAL;
+    MCU_TRY(ensure_device());
+    return session_finish(h->s, uniq_is_global != 0, stage_ms, stats);
+}
+
+int mcu_session_merge(mcu_session* h, const mcu_match* rows, uint64_t n, int in_device, uint64_t* stats2)
+{
+    if (!h || (n && !rows)) return MCU_EINVAL;
+    MCU_TRY(ensure_device());
+    Session& s = h->s;
+    const mcu_match* dev_rows = rows;
+    if (!in_device && n) {
+        MCU_TRY(s.raw_matches.reserve(n * sizeof(mcu_match)));
+        MCU_CUDA(cudaMemcpyAsync(s.raw_matches.p, rows, n * sizeof(mcu_match), cudaMemcpyHostToDevice, s.stream));
+        dev_rows = s.raw_matches.as<mcu_match>();
+    }
+    u64 unclean = 0, dups = 0;
+    MCU_TRY(session_merge(s, dev_rows, n, &unclean, &dups));
+    if (stats2) { stats2[0] = unclean; stats2[1] = dups; }
+    return MCU_OK;
+}
+
 uint64_t mcu_session_match_count(const mcu_session* h) { return h ? h->s.match_count : 0; }
 
 int mcu_session_download(mcu_session* h, mcu_match* out)

@@ -286,6 +286,30 @@ class AnchorSession:
         check(lib().mcu_session_run(self._h, seed, shard_index, shard_count, self.stage_ms.ctypes.data, self.stats.ctypes.data))
         return int(lib().mcu_session_match_count(self._h))
 
+    def enumerate(self, seed, shard_index=0, shard_count=1):
+        check(lib().mcu_session_enumerate(self._h, seed, shard_index, shard_count))
+
+    def uniq_bitmap(self):
+        """(device pointer, n_words) of the unique-seed bitmap: ranks SUM-all-reduce it between enumerate() and finish()"""
+        p, n = C.c_void_p(), C.c_uint64(0)
+        check(lib().mcu_session_uniq_bitmap(self._h, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def finish(self, uniq_is_global=False):
+        check(lib().mcu_session_finish(self._h, 1 if uniq_is_global else 0, self.stage_ms.ctypes.data, self.stats.ctypes.data))
+        return int(lib().mcu_session_match_count(self._h))
+
+    def merge(self, rows, in_device=False, n=None):
+        """rank-0 merge of the gathered per-rank rows of a run finished with a global bitmap -> (match count, [replayed buckets, duplicate rows])"""
+        if in_device:
+            addr, cnt = rows, n
+        else:
+            rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3)
+            addr, cnt = rows.ctypes.data, rows.shape[0]
+        st = np.zeros(2, dtype=np.uint64)
+        check(lib().mcu_session_merge(self._h, addr, cnt, 1 if in_device else 0, st.ctypes.data))
+        return int(lib().mcu_session_match_count(self._h)), st
+
     def match_count(self):
         return int(lib().mcu_session_match_count(self._h))
 

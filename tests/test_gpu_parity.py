@@ -310,3 +310,56 @@ def test_mums_solid_seed_paths(mp, orc, w):
         rows, stats = mp.libmems.find_mums(x, y, seed)
         orows, _ = orc.find_mums(x, y, seed, 0)
         assert rows.shape[0] > 10 and np.array_equal(rows, orows)
+
+
+# ---- two-phase sharded run (enumerate | all-reduce of the unique-seed bitmap | finish | merge) ---------------
+def _two_phase(mp, a, b, seed, world):
+    """world sessions on one GPU stand in for world ranks; the bitmap SUM is what dist.allreduce_uniq_bitmap does over NCCL"""
+    import torch
+    from mauve_py_b200.dist import _DeviceWords
+    sess = []
+    for rank in range(world):
+        s = mp.AnchorSession()
+        s.upload(a, b)
+        s.enumerate(seed, rank, world)
+        sess.append(s)
+    views = [torch.as_tensor(_DeviceWords(*s.uniq_bitmap()), device="cuda") for s in sess]
+    total = torch.stack(views).sum(dim=0, dtype=torch.int32)
+    ored = views[0].clone()
+    for v in views[1:]:
+        ored |= v
+    assert torch.equal(total, ored)  # the slices' bits are disjoint: SUM == OR
+    for v in views:
+        v.copy_(total)
+    torch.cuda.synchronize()
+    parts, emitted = [], 0
+    for s in sess:
+        n = s.finish(uniq_is_global=True)
+        emitted += n
+        parts.append(s.download().copy())
+    rows = np.concatenate(parts, axis=0)
+    n, st = sess[0].merge(rows)
+    out = sess[0].download().copy()
+    for s in sess:
+        s.close()
+    return out, emitted, st
+
+
+@pytest.mark.parametrize("w,r,n", [(15, 3, 500000), (19, 3, 400000), (11, 0, 200000), (21, 0, 300000)])
+def test_two_phase_sharded_exact(mp, w, r, n):
+    a, b = synth.small_pair(n, seed=100 + w, snp=0.01, n_inv=3)
+    seed = mp.getSeed(w, r)
+    full, _ = mp.libmems.find_mums(a, b, seed)
+    for world in (2, 3, 8):
+        out, emitted, st = _two_phase(mp, a, b, seed, world)
+        assert emitted == full.shape[0], (world, emitted, full.shape[0])  # exactly one emitter per match across ranks
+        assert np.array_equal(out, full), world
+
+
+def test_two_phase_sharded_order_dependent_buckets(mp, orc):
+    """the rank-0 merge replays the reference's order-dependent hash buckets with the global bitmap: duplicate rows included"""
+    a, b = synth.colliding_diagonals_pair(seed=5)
+    seed = mp.getSeed(11, 0)
+    orows, _ = orc.find_mums(a, b, seed, 0)
+    out, emitted, st = _two_phase(mp, a, b, seed, 2)
+    assert int(st[0]) > 0 and np.array_equal(out, orows)

@@ -60,6 +60,16 @@ def _gather_worker(rank, world, port, q):
         else:
             assert out is None
         assert mdist.shard_of(rank, world) == (rank, world)
+        # unique-seed bitmaps of the ranks' key slices are disjoint: the SUM all-reduce is their OR (sign bit included)
+        rng = np.random.default_rng(7)
+        owner = rng.integers(0, world, size=64 * 32)
+        bits = rng.integers(0, 2, size=64 * 32).astype(bool)
+        bits[31] = True
+        full = np.packbits(bits.reshape(-1, 32)[:, ::-1], axis=1, bitorder="big").view(">u4").astype(np.uint32).reshape(-1)
+        mine = np.packbits((bits & (owner == rank)).reshape(-1, 32)[:, ::-1], axis=1, bitorder="big").view(">u4").astype(np.uint32).reshape(-1)
+        words = torch.from_numpy(mine.view(np.int32).copy())
+        mdist.or_disjoint_words(words)
+        assert np.array_equal(words.numpy().view(np.uint32), full)
     finally:
         dist.destroy_process_group()
 
