@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) join_kernel(const K* __restrict__ keys, c
 // "already contained" rejections (LM/MemHash.cpp:215-220): 2.7 M seed pairs -> ~30 k candidates
 // on MDS42.  counters[2] / [7] = forward / reverse candidates.
 __global__ void __launch_bounds__(256) candidate_kernel(ExtendArgs a, SeedParams sp, const u64* __restrict__ pairs, u64 pfwd, u64 prev_, u64 pair_cap, bool solid,
-                                                       bool bases_agree)
+                                                       u64 agree_fwd, u64 agree_rev)
 {
     const u32 lane = threadIdx.x & 31;
     const u64 total = pfwd + prev_;
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) candidate_kernel(ExtendArgs a, SeedParams
             const i64 p0 = (i64)(e & 0xffffffffu), p1 = (i64)(e >> 32);
             const i64 d = rev ? p0 + p1 : p1 - p0;
             i64 other;
-            if (bases_agree) {
+            if (rev ? idx - pfwd < agree_rev : idx < agree_fwd) {
                 // the bucket kernel already compared the neighbour bases (p0 > 0 and the partner exists): only the bitmap is left
                 is_cand = !uniq_bit(a.uniq, p0 - 1);
             } else if (solid) {
@@ -665,7 +665,8 @@ static int run_finish(Session& s, bool uniq_is_global, float* stage_ms, u64* sta
         ea.out = nullptr; ea.counters = ctr;
         MCU_CUDA(cudaEventRecord(s.kev[6], s.stream));
         const bool solid = sp.nruns == 1 && sp.L == sp.w && (sp.w & 1) && getenv("MAUVE_CUDA_NO_SOLID") == nullptr;
-        candidate_kernel<<<grid_for(pfwd + prev_ + 1, 256, 8), 256, 0, s.stream>>>(ea, sp, s.pairs.as<u64>(), pfwd, prev_, pair_cap, solid, s.bk_aux);
+        candidate_kernel<<<grid_for(pfwd + prev_ + 1, 256, 8), 256, 0, s.stream>>>(ea, sp, s.pairs.as<u64>(), pfwd, prev_, pair_cap, solid,
+                                                                                     s.bk_aux ? s.bk_group_fwd : 0, s.bk_aux ? s.bk_group_rev : 0);
         s.launches++;
         MCU_CUDA(cudaEventRecord(s.kev[7], s.stream));
         MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
@@ -696,7 +697,7 @@ static int run_finish(Session& s, bool uniq_is_global, float* stage_ms, u64* sta
     if (stage_ms) {
         for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&stage_ms[i], s.ev[i], s.ev[i + 1]);
         cudaEventElapsedTime(&stage_ms[6], s.ev[0], s.ev[6]);
-        stage_ms[7] = bucketed ? -1.0f : (float)passes_run;
+        stage_ms[7] = bucketed ? (s.bk_exact ? -2.0f : -1.0f) : (float)passes_run;  // < 0: bucketed enumeration (-2: exact bucket sizes)
         for (int i = 8; i < 16; ++i) stage_ms[i] = 0.f;
         stage_ms[15] = (float)s.bk_spilled;
         if (bucketed)

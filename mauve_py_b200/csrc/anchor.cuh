@@ -14,7 +14,9 @@ struct Session {
     DevBuf uniq, pairs, cand, raw_matches, ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b, ord_primary, matches, counters;
     // bucketed enumeration (bucket.cu)
     DevBuf bk_a, bk_b, bk_tab1, bk_tab2, bk_spill, bk_tileseg;
-    u64 bk_spilled = 0, bk_direct = 0;
+    u64 bk_spilled = 0, bk_direct = 0, bk_fallbacks = 0;  // fallbacks: runs that overflowed the fixed-capacity layout and were redone exactly
+    u64 bk_group_fwd = 0, bk_group_rev = 0;  // leading forward / reverse pairs of the pair list that bk_group emitted
+    bool bk_exact = false;  // the last bucketed run used exact (counted) bucket sizes: forced, or after an overflow of the fixed layout
     bool bk_aux = false;  // bucket records carried neighbour bases: pending pairs only need the unique-seed bitmap test
     // bucket replay (replay.cu)
     DevBuf rp_ctr, rp_bitmap, rp_list, rp_canon, rp_keys_b, rp_idx_a, rp_idx_b, rp_p0, rp_row, rp_bkeys, rp_pool, rp_extra, rp_prefix, rp_vinfo, rp_out;

@@ -24,6 +24,8 @@
 // counters[0]/[6] pair counts, counters[1] MER_REPEAT_LIMIT flag.
 #include "anchor.cuh"
 
+#include <math.h>
+
 namespace mcu {
 
 constexpr int BK_THREADS = 256;
@@ -42,6 +44,9 @@ struct BkPlan {
     u32 B1, B2;
     u64 npos0, npos1, ntot;
     u64 npad0, nidx;  // genome-0 positions padded to a multiple of 16 so that a thread's 16 consecutive positions share 3 packed words
+    // fixed-capacity layout (histogram-free path): this rank owns the level-1 bins [b_lo, b_hi); every level-1 bucket has room
+    // for cap1 records, every final bucket for BK_CAP
+    u32 b_lo, b_hi, cap1;
 };
 
 struct BkMeta {  // written by bk_scan1_kernel
@@ -402,6 +407,242 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter2_kernel(const u64* _
     }
 }
 
+
+// ---- histogram-free variant: fixed-capacity buckets --------------------------------------------------------------
+// The mixed mers spread the seeds uniformly, so bucket sizes are known in advance up to Poisson noise: level-1 bucket b of
+// this rank owns recs1[(b - b_lo) * cap1 ..) with cap1 = mean + 8 sigma, final bucket f owns recs2[f * BK_CAP ..).  That
+// removes both counting passes (bk_hist1: a second evaluation of every seed; bk_hist2: a second read of every record) and
+// both scans, and the rank's share is a fixed range of level-1 bins.  Records that find their bucket full (repeats: many
+// copies of one mer) are written to the overflow arrays in the radix-sort path's (key, position) format, their final
+// bucket is marked dirty, and bk_group sends dirty / overfull buckets to that path entirely, so all copies of a mer are
+// always examined together.  If the overflow arrays themselves fill up, the caller reruns the exact (counting) path.
+struct BkOvf {
+    u64* keys;                  // mixed mer << 2 | genome << 1 | strand
+    u32* vals;                  // position
+    u64 cap;
+    unsigned long long* cursor; // records appended (may run past cap: detected by the host)
+    u32* dirty;                 // 1 bit per final bucket of this rank
+};
+
+__device__ __noinline__ void bk_overflow(u64* keys, u32* vals, u64 cap, unsigned long long* cursor, u32* dirty, u64 rec, u32 b1, u32 b1_rel, int rem1,
+                                         int kshift, int pbits, int d2)
+{
+    const u64 mixed = ((u64)b1 << rem1) | (rec >> kshift);
+    const u64 slot = atomicAdd(cursor, 1ull);
+    if (slot < cap) {
+        keys[slot] = (mixed << 2) | ((rec & 1) << 1) | ((rec >> 1) & 1);
+        vals[slot] = (u32)((rec >> 2) & ((1ull << pbits) - 1));
+    }
+    const u64 f = ((u64)b1_rel << d2) + ((rec >> (kshift + rem1 - d2)) & ((1u << d2) - 1));
+    atomicOr(&dirty[f >> 5], 1u << (f & 31));
+}
+
+// like bk_reserve, for buckets of fixed capacity: gbase[b] = absolute index of the tile's first record of bin b,
+// cnt[b] becomes the number of the tile's records of bin b that still fit.  Returns the tile population.
+template <typename BaseFn>
+__device__ __forceinline__ u32 bkf_reserve(const BkScatterSmem& s, u32 bins, unsigned long long* __restrict__ cursor, u64 cap, BaseFn bucket_base)
+{
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 per = (bins + BK_THREADS - 1) / BK_THREADS;
+    u32 local = 0;
+    for (u32 j = 0; j < per; ++j) {
+        const u32 b = tid * per + j;
+        if (b < bins) local += s.cnt[b];
+    }
+    u32 incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (u32)o) incl += t;
+    }
+    if (lane == 31) s.warp_tot[warp] = incl;
+    __syncthreads();
+    u32 add = 0, total = 0;
+#pragma unroll
+    for (u32 w = 0; w < BK_THREADS / 32; ++w) {
+        const u32 t = s.warp_tot[w];
+        if (w < warp) add += t;
+        total += t;
+    }
+    u32 run = incl - local + add;
+    for (u32 j = 0; j < per; ++j) {
+        const u32 b = tid * per + j;
+        if (b < bins) {
+            const u32 c = s.cnt[b];
+            s.sofs[b] = run;
+            run += c;
+            if (c) {
+                const u64 rel = atomicAdd(&cursor[b], (unsigned long long)c);
+                s.gbase[b] = bucket_base(b) + rel;
+                s.cnt[b] = rel >= cap ? 0u : (u32)min((u64)c, cap - rel);
+            }
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
+template <bool SOLID>
+__global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* __restrict__ g0, const u32* __restrict__ g1, BkPlan pl, SeedParams sp,
+                                                                    unsigned long long* __restrict__ cursor1, u64* __restrict__ recs, BkOvf ovf)
+{
+    extern __shared__ __align__(16) unsigned char raw[];
+    const BkScatterSmem s = bk_carve(raw, pl.B1);
+    const u32 tid = threadIdx.x;
+    const u32 b_lo = pl.b_lo, b_hi = pl.b_hi;
+    for (u32 i = tid; i < pl.B1; i += BK_THREADS) s.cnt[i] = 0;
+    __syncthreads();
+    const u64 idx0 = (u64)blockIdx.x * BK_TILE + (u64)tid * BK_IPT;  // 16 consecutive positions per thread
+    u64 rec[BK_IPT];
+    u32 br[BK_IPT];  // bin << 16 | rank   (rank < BK_TILE = 4096)
+#pragma unroll
+    for (int it = 0; it < BK_IPT; ++it) br[it] = 0xffffffffu;
+    if (idx0 < pl.nidx) {
+        const u32 g = idx0 >= pl.npad0;
+        const u64 pos = g ? idx0 - pl.npad0 : idx0, npos = g ? pl.npos1 : pl.npos0;
+        const u32* __restrict__ gp = g ? g1 : g0;
+        BkWindow w;
+        w.load(gp, pos);
+        const int kbits = 2 * sp.w;
+        const u64 kmask = (1ull << kbits) - 1;   // kbits <= 62
+        const int mshift = kbits / 2 + 1;
+        if (SOLID) {
+            // rolling evaluation: a shift by one position drops one base and adds one (forward: at the low end; reverse
+            // complement: the complement at the high end).  nx = the 16 bases [w, w+16) of the window.
+            const u32 hi_h = (u32)(w.hi >> 32), hi_l = (u32)w.hi;
+            const u32 nx = kbits < 32 ? __funnelshift_l(hi_l, hi_h, kbits) : __funnelshift_l(w.lo, hi_l, kbits - 32);
+            u32 prevbase = 0;
+            if (pl.aux && pos > 0) prevbase = base_at(gp, (i64)pos - 1);
+            u64 f = w.hi >> (64 - kbits);
+            u64 rc = revcomp_seed(f, sp.w);
+#pragma unroll
+            for (int it = 0; it < BK_IPT; ++it) {
+                const u32 nb = (nx >> (30 - 2 * it)) & 3u;  // base w + it: enters the mer at the next position, follows it at this one
+                if (pos + it < npos) {
+                    const u32 strand = rc < f;  // GetDnaSeedMer: forward wins ties
+                    u64 x = strand ? rc : f;
+                    x ^= x >> mshift;
+                    const u64 canon = (x * 0x9E3779B97F4A7C15ull) & kmask;  // == bk_mix
+                    const u32 b = (u32)(canon >> pl.rem1);
+                    if (b >= b_lo && b < b_hi) {
+                        const u64 keyrem = canon & ((1ull << pl.rem1) - 1);
+                        u64 aux = 0;
+                        if (pl.aux) {
+                            const u32 prev = it ? (u32)(w.hi >> (64 - 2 * it)) & 3u : prevbase;
+                            aux = prev | (nb << 2);
+                        }
+                        rec[it] = (keyrem << pl.kshift) | (aux << (pl.pbits + 2)) | ((pos + it) << 2) | ((u64)strand << 1) | (u64)g;
+                        br[it] = (b << 16) | atomicAdd(&s.cnt[b], 1u);
+                    }
+                }
+                f = ((f << 2) | nb) & kmask;
+                rc = (rc >> 2) | ((u64)(3u - nb) << (kbits - 2));
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < BK_IPT; ++it) {
+                if (pos + it < npos) {
+                    u64 canon;
+                    u32 strand;
+                    seed_canon32(w.mer(it), sp, canon, strand);
+                    const u32 b = (u32)(canon >> pl.rem1);
+                    if (b >= b_lo && b < b_hi) {
+                        const u64 keyrem = canon & ((1ull << pl.rem1) - 1);
+                        rec[it] = (keyrem << pl.kshift) | ((pos + it) << 2) | ((u64)strand << 1) | (u64)g;
+                        br[it] = (b << 16) | atomicAdd(&s.cnt[b], 1u);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const u64 cap1 = pl.cap1;
+    const u32 ntile = bkf_reserve(s, pl.B1, cursor1, cap1, [=](u32 b) { return (u64)(b - b_lo) * cap1; });
+#pragma unroll
+    for (int it = 0; it < BK_IPT; ++it) {
+        if (br[it] != 0xffffffffu) {
+            const u32 b = br[it] >> 16, slot = s.sofs[b] + (br[it] & 0xffffu);
+            s.stage[slot] = rec[it];
+            s.sbin[slot] = (unsigned short)b;
+        }
+    }
+    __syncthreads();
+    for (u32 j = tid; j < ntile; j += BK_THREADS) {
+        const u32 b = s.sbin[j], k = j - s.sofs[b];
+        if (k < s.cnt[b]) recs[s.gbase[b] + k] = s.stage[j];
+        else bk_overflow(ovf.keys, ovf.vals, ovf.cap, ovf.cursor, ovf.dirty, s.stage[j], b, b - b_lo, pl.rem1, pl.kshift, pl.pbits, pl.d2);
+    }
+}
+
+// level-2 partition of one tile of level-1 bucket b_lo + blockIdx.y into its B2 final buckets
+__global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter2_kernel(const u64* __restrict__ src, BkPlan pl, const unsigned long long* __restrict__ cursor1,
+                                                                    unsigned long long* __restrict__ cursor2, u64* __restrict__ dst, BkOvf ovf)
+{
+    extern __shared__ __align__(16) unsigned char raw[];
+    const u32 seg = blockIdx.y;  // relative to b_lo
+    const u64 cnt1 = min((u64)cursor1[pl.b_lo + seg], (u64)pl.cap1);
+    const u64 base = (u64)blockIdx.x * BK_TILE;
+    if (base >= cnt1) return;
+    const BkScatterSmem s = bk_carve(raw, pl.B2);
+    const u32 tid = threadIdx.x;
+    const int shift = pl.kshift + pl.rem1 - pl.d2;
+    const u32 n = (u32)min((u64)BK_TILE, cnt1 - base);
+    const u64* __restrict__ in = src + (u64)seg * pl.cap1 + base;
+    for (u32 i = tid; i < pl.B2; i += BK_THREADS) s.cnt[i] = 0;
+    __syncthreads();
+    u64 rec[BK_IPT];
+    u32 br[BK_IPT];
+#pragma unroll
+    for (int it = 0; it < BK_IPT; ++it) {  // all loads in flight before the first shared-memory atomic
+        const u32 i = it * BK_THREADS + tid;
+        rec[it] = i < n ? __ldcs(in + i) : 0;
+    }
+#pragma unroll
+    for (int it = 0; it < BK_IPT; ++it) {
+        const u32 i = it * BK_THREADS + tid;
+        br[it] = 0xffffffffu;
+        if (i < n) {
+            const u32 b = (u32)(rec[it] >> shift) & (pl.B2 - 1);
+            br[it] = (b << 16) | atomicAdd(&s.cnt[b], 1u);
+        }
+    }
+    __syncthreads();
+    const u64 fbase = (u64)seg * pl.B2;
+    bkf_reserve(s, pl.B2, cursor2 + fbase, (u64)BK_CAP, [=](u32 b) { return (fbase + b) * (u64)BK_CAP; });
+#pragma unroll
+    for (int it = 0; it < BK_IPT; ++it) {
+        if (br[it] != 0xffffffffu) {
+            const u32 b = br[it] >> 16, slot = s.sofs[b] + (br[it] & 0xffffu);
+            s.stage[slot] = rec[it];
+            s.sbin[slot] = (unsigned short)b;
+        }
+    }
+    __syncthreads();
+    for (u32 j = tid; j < n; j += BK_THREADS) {
+        const u32 b = s.sbin[j], k = j - s.sofs[b];
+        if (k < s.cnt[b]) dst[s.gbase[b] + k] = s.stage[j];
+        else bk_overflow(ovf.keys, ovf.vals, ovf.cap, ovf.cursor, ovf.dirty, s.stage[j], pl.b_lo + seg, seg, pl.rem1, pl.kshift, pl.pbits, pl.d2);
+    }
+}
+
+// records this rank holds = sum of its level-1 cursors (statistics only)
+__global__ void bkf_total_kernel(const unsigned long long* __restrict__ cursor1, BkPlan pl, BkMeta* __restrict__ meta)
+{
+    __shared__ unsigned long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    unsigned long long t = 0;
+    for (u32 b = pl.b_lo + threadIdx.x; b < pl.b_hi; b += blockDim.x) t += cursor1[b];
+    atomicAdd(&s_sum, t);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        meta->b_lo = pl.b_lo;
+        meta->b_hi = pl.b_hi;
+        meta->nrec = s_sum;
+        meta->nfinal = (u64)(pl.b_hi - pl.b_lo) * pl.B2;
+    }
+}
+
 // ---- final buckets ------------------------------------------------------------------------------------------
 struct BkGroupArgs {
     const u64* recs;
@@ -415,6 +656,11 @@ struct BkGroupArgs {
     u64 cand_cap;
     u32* spill_list;               // final buckets larger than BK_CAP
     unsigned long long* spill;     // [0] buckets, [1] records, [2] convert cursor, [3] direct candidates
+    // fixed-capacity layout (cnt2 != nullptr): bucket f = recs[f * BK_CAP ...], cnt2[f] records arrived (those beyond BK_CAP
+    // went to the overflow arrays), dirty bit f = some of its records overflowed at level 1
+    const unsigned long long* cnt2;
+    const u32* dirty;
+    u64 nfinal;
 };
 
 constexpr int BK_GIPT = BK_CAP / BK_THREADS;  // records per thread in bk_group
@@ -429,15 +675,27 @@ __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, 
     __shared__ unsigned long long s_base[4];
     __shared__ u64 candp[2][BK_DIRECT];     // pairs that are certainly candidates (aux mode)
     const u64 f = blockIdx.x;
-    if (f >= a.meta->nfinal) return;
-    const u64 beg = a.off2[f];
-    const u32 nb = (u32)(a.off2[f + 1] - beg);
+    u64 beg;
+    u32 nb;
+    bool spill_it;
+    if (a.cnt2) {
+        const unsigned long long tot = a.cnt2[f];
+        beg = f * BK_CAP;
+        nb = (u32)min(tot, (unsigned long long)BK_CAP);
+        spill_it = tot > BK_CAP || ((a.dirty[f >> 5] >> (f & 31)) & 1u);
+    } else {
+        if (f >= a.meta->nfinal) return;
+        beg = a.off2[f];
+        const u64 cnt = a.off2[f + 1] - beg;
+        nb = (u32)min(cnt, (u64)BK_CAP + 1);
+        spill_it = cnt > BK_CAP;
+    }
     if (nb == 0) return;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (nb > BK_CAP) {
+    if (spill_it) {
         if (tid == 0) {
             a.spill_list[atomicAdd(&a.spill[0], 1ull)] = (u32)f;
-            atomicAdd(&a.spill[1], (unsigned long long)nb);
+            atomicAdd(&a.spill[1], a.cnt2 ? (unsigned long long)nb : (unsigned long long)(a.off2[f + 1] - beg));
         }
         return;
     }
@@ -570,11 +828,13 @@ __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, 
 // spilled buckets -> (key, position) arrays of the radix-sort path: key = mixed mer << 2 | genome << 1 | strand
 __global__ void __launch_bounds__(BK_THREADS) bk_spill_kernel(const u64* __restrict__ recs, const u64* __restrict__ off2, const BkMeta* __restrict__ meta,
                                                              const u32* __restrict__ spill_list, BkPlan pl, u64* __restrict__ keys,
-                                                             u32* __restrict__ vals, unsigned long long* __restrict__ cursor)
+                                                             u32* __restrict__ vals, unsigned long long* __restrict__ cursor,
+                                                             const unsigned long long* __restrict__ cnt2)
 {
     __shared__ unsigned long long s_base;
     const u32 f = spill_list[blockIdx.x];
-    const u64 beg = off2[f], nb = off2[f + 1] - beg;
+    const u64 beg = cnt2 ? (u64)f * BK_CAP : off2[f];
+    const u64 nb = cnt2 ? min((u64)cnt2[f], (u64)BK_CAP) : off2[f + 1] - beg;
     if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned long long)nb);
     __syncthreads();
     const u64 b1 = meta->b_lo + f / pl.B2;
@@ -627,6 +887,107 @@ static bool make_plan(const SeedParams& sp, u64 npos0, u64 npos1, BkPlan* out)
     return true;
 }
 
+// Histogram-free run (see "fixed-capacity buckets" above).  *fell_back is set when the overflow arrays filled up: nothing
+// usable was produced and the caller must reset uniq / counters and take the exact path.
+static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int shard_index, int shard_count, u64 pair_cap, cudaEvent_t ev_scatter1,
+                              cudaEvent_t ev_scatter2, bool* fell_back, u64* nrecords)
+{
+    *fell_back = false;
+    cudaStream_t st = s.stream;
+    unsigned long long* ctr = s.counters.as<unsigned long long>();
+    pl.b_lo = (u32)((u64)pl.B1 * (u64)shard_index / (u64)shard_count);
+    pl.b_hi = (u32)((u64)pl.B1 * (u64)(shard_index + 1) / (u64)shard_count);
+    const u32 nb1 = pl.b_hi - pl.b_lo;
+    const double mean1 = (double)pl.ntot / pl.B1;
+    pl.cap1 = (u32)(((u64)(mean1 + 8.0 * sqrt(mean1) + 64.0) + 31) & ~31ull);
+    const u64 nfinal = (u64)nb1 * pl.B2;
+    u64 ovf_cap = pl.ntot / 8 / (u64)shard_count + (1ull << 20);
+    if (const char* e = getenv("MAUVE_CUDA_OVF_CAP")) ovf_cap = strtoull(e, nullptr, 10);  // tests: force the fallback
+    const u64 dirty_words = nfinal / 32 + 1;
+    MCU_TRY(s.bk_a.reserve(((u64)nb1 * pl.cap1 + 1) * 8));
+    MCU_TRY(s.bk_b.reserve((nfinal * BK_CAP + 1) * 8));
+    MCU_TRY(s.bk_tab1.reserve((size_t)(pl.B1 + 1) * 8 * 3 + 64));
+    MCU_TRY(s.bk_tab2.reserve((nfinal + 1) * 8 * 3 + 64 + dirty_words * 4));
+    MCU_TRY(s.bk_spill.reserve(nfinal * 4 + 64));
+    MCU_TRY(s.keys_a.reserve((ovf_cap + 1) * 8));
+    MCU_TRY(s.vals_a.reserve((ovf_cap + 1) * 4));
+    unsigned long long* cursor1 = s.bk_tab1.as<unsigned long long>();
+    BkMeta* meta = (BkMeta*)(cursor1 + (size_t)(pl.B1 + 1) * 3);  // inside the +64 bytes slack, as in the exact path
+    unsigned long long* cursor2 = s.bk_tab2.as<unsigned long long>();
+    unsigned long long* spill = cursor2 + nfinal + 1;  // [0] buckets [1] records [2] overflow / convert cursor [3] direct candidates
+    u32* dirty = (u32*)(spill + 4);
+    MCU_CUDA(cudaMemsetAsync(cursor1, 0, (size_t)(pl.B1 + 1) * 8, st));
+    MCU_CUDA(cudaMemsetAsync(cursor2, 0, (nfinal + 1) * 8 + 32 + dirty_words * 4, st));
+    const u32* g0 = s.packed[0].as<u32>();
+    const u32* g1 = s.packed[1].as<u32>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        MCU_CUDA(cudaFuncSetAttribute(bkf_scatter1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
+        MCU_CUDA(cudaFuncSetAttribute(bkf_scatter1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
+        MCU_CUDA(cudaFuncSetAttribute(bkf_scatter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
+        attr_done = true;
+    }
+    BkOvf ovf;
+    ovf.keys = s.keys_a.as<u64>(); ovf.vals = s.vals_a.as<u32>(); ovf.cap = ovf_cap; ovf.cursor = spill + 2; ovf.dirty = dirty;
+    const bool solid_pattern = sp.nruns == 1 && sp.L == sp.w && getenv("MAUVE_CUDA_NO_SOLID") == nullptr;
+    const unsigned tiles1 = (unsigned)div_up(pl.nidx, BK_TILE);
+    MCU_CUDA(cudaEventRecord(s.kev[0], st));
+    MCU_CUDA(cudaEventRecord(s.kev[1], st));
+    if (nb1) {
+        if (solid_pattern) bkf_scatter1_kernel<true><<<tiles1, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf);
+        else bkf_scatter1_kernel<false><<<tiles1, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf);
+    }
+    MCU_CUDA(cudaEventRecord(ev_scatter1, st));
+    MCU_CUDA(cudaEventRecord(s.kev[2], st));
+    bkf_total_kernel<<<1, 256, 0, st>>>(cursor1, pl, meta);
+    MCU_CUDA(cudaEventRecord(s.kev[3], st));
+    if (nb1) {
+        const dim3 grid2((unsigned)div_up(pl.cap1, BK_TILE), nb1);
+        bkf_scatter2_kernel<<<grid2, BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(s.bk_a.as<u64>(), pl, cursor1, cursor2, s.bk_b.as<u64>(), ovf);
+    }
+    MCU_CUDA(cudaEventRecord(ev_scatter2, st));
+    MCU_CUDA(cudaEventRecord(s.kev[4], st));
+    BkGroupArgs ga;
+    ga.recs = s.bk_b.as<u64>(); ga.off2 = nullptr; ga.meta = meta; ga.uniq = s.uniq.as<u32>(); ga.pairs = s.pairs.as<u64>(); ga.pair_cap = pair_cap;
+    ga.counters = ctr; ga.spill_list = s.bk_spill.as<u32>(); ga.spill = spill;
+    ga.cand = s.cand.as<u64>(); ga.cand_cap = pair_cap;
+    ga.cnt2 = cursor2; ga.dirty = dirty; ga.nfinal = nfinal;
+    if (nfinal) bk_group_kernel<<<(unsigned)nfinal, BK_THREADS, 0, st>>>(ga, pl);
+    MCU_CUDA(cudaEventRecord(s.kev[5], st));
+    s.launches += 4;
+    MCU_CUDA(cudaGetLastError());
+    struct { unsigned long long spill[4]; BkMeta meta; unsigned long long ctr[8]; } h;
+    MCU_CUDA(cudaMemcpyAsync(h.spill, spill, 32, cudaMemcpyDeviceToHost, st));
+    MCU_CUDA(cudaMemcpyAsync(&h.meta, meta, sizeof(BkMeta), cudaMemcpyDeviceToHost, st));
+    MCU_CUDA(cudaMemcpyAsync(h.ctr, ctr, 64, cudaMemcpyDeviceToHost, st));
+    MCU_CUDA(cudaStreamSynchronize(st));
+    // pairs listed so far came from bk_group (neighbour bases already compared in aux mode); the sort path may append more
+    s.bk_group_fwd = h.ctr[0];
+    s.bk_group_rev = h.ctr[6];
+    *nrecords = h.meta.nrec;
+    const u64 novf = h.spill[2], ns = novf + h.spill[1];
+    if (novf > ovf_cap || ns > ovf_cap) { *fell_back = true; return MCU_OK; }
+    s.bk_spilled = ns;
+    s.bk_direct = h.spill[3];
+    s.bk_aux = pl.aux != 0;
+    if (ns) {
+        MCU_TRY(s.keys_b.reserve((ns + 1) * 8));
+        MCU_TRY(s.vals_b.reserve((ns + 1) * 4));
+        if (h.spill[0]) {
+            bk_spill_kernel<<<(unsigned)h.spill[0], BK_THREADS, 0, st>>>(s.bk_b.as<u64>(), nullptr, meta, s.bk_spill.as<u32>(), pl, s.keys_a.as<u64>(),
+                                                                         s.vals_a.as<u32>(), spill + 2, cursor2);
+            s.launches++;
+        }
+        bool in_a = true;
+        u64 before = s.radix.launches;
+        MCU_TRY(radix_sort_pairs<u64>(s.radix, s.keys_a.as<u64>(), s.vals_a.as<u32>(), s.keys_b.as<u64>(), s.vals_b.as<u32>(), ns, pl.kbits + 2, false,
+                                      st, &in_a, nullptr));
+        s.launches += s.radix.launches - before;
+        MCU_TRY(join_sorted_u64(s, in_a ? s.keys_a.as<u64>() : s.keys_b.as<u64>(), in_a ? s.vals_a.as<u32>() : s.vals_b.as<u32>(), ns, pair_cap));
+    }
+    return MCU_OK;
+}
+
 int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_count, u64 pair_cap, cudaEvent_t ev_scatter1, cudaEvent_t ev_scatter2,
                  bool* used, u64* nrecords)
 {
@@ -637,6 +998,22 @@ int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_co
     if (!npos0 || !npos1 || !make_plan(sp, npos0, npos1, &pl)) return MCU_OK;
     cudaStream_t st = s.stream;
     unsigned long long* ctr = s.counters.as<unsigned long long>();
+    if (getenv("MAUVE_CUDA_EXACT_BUCKETS") == nullptr) {
+        bool fell_back = false;
+        MCU_TRY(bucket_group_fixed(s, sp, pl, shard_index, shard_count, pair_cap, ev_scatter1, ev_scatter2, &fell_back, nrecords));
+        if (!fell_back) { *used = true; s.bk_exact = false; return MCU_OK; }
+        // too many copies of too many mers for the overflow arrays: start over with exact bucket sizes
+        const u64 uniq_words = div_up(npos0 + 1, 32) + 1;
+        u32 gap_flag = 0;
+        MCU_CUDA(cudaMemcpyAsync(&gap_flag, ctr + 4, 4, cudaMemcpyDeviceToHost, st));
+        MCU_CUDA(cudaStreamSynchronize(st));
+        MCU_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), st));
+        MCU_CUDA(cudaMemcpyAsync(ctr + 4, &gap_flag, 4, cudaMemcpyHostToDevice, st));
+        MCU_CUDA(cudaMemsetAsync(s.uniq.p, 0, uniq_words * sizeof(u32), st));
+        s.bk_fallbacks++;
+    }
+    pl.b_lo = pl.b_hi = pl.cap1 = 0;
+    s.bk_exact = true;
     const u64 nfinal_max = (u64)pl.B1 * pl.B2;
     MCU_TRY(s.bk_a.reserve((pl.ntot + 1) * 8));
     MCU_TRY(s.bk_b.reserve((pl.ntot + 1) * 8));
@@ -684,15 +1061,20 @@ int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_co
     ga.recs = s.bk_b.as<u64>(); ga.off2 = off2; ga.meta = meta; ga.uniq = s.uniq.as<u32>(); ga.pairs = s.pairs.as<u64>(); ga.pair_cap = pair_cap;
     ga.counters = ctr; ga.spill_list = s.bk_spill.as<u32>(); ga.spill = spill;
     ga.cand = s.cand.as<u64>(); ga.cand_cap = pair_cap;
+    ga.cnt2 = nullptr; ga.dirty = nullptr; ga.nfinal = nfinal_max;
     bk_group_kernel<<<(unsigned)nfinal_max, BK_THREADS, 0, st>>>(ga, pl);
     MCU_CUDA(cudaEventRecord(s.kev[5], st));
     s.launches += 8;
     MCU_CUDA(cudaGetLastError());
     // spilled buckets (if any) go through the radix-sort + join path
-    struct { unsigned long long spill[4]; BkMeta meta; } h;
+    struct { unsigned long long spill[4]; BkMeta meta; unsigned long long ctr[8]; } h;
     MCU_CUDA(cudaMemcpyAsync(h.spill, spill, 32, cudaMemcpyDeviceToHost, st));
     MCU_CUDA(cudaMemcpyAsync(&h.meta, meta, sizeof(BkMeta), cudaMemcpyDeviceToHost, st));
+    MCU_CUDA(cudaMemcpyAsync(h.ctr, ctr, 64, cudaMemcpyDeviceToHost, st));
     MCU_CUDA(cudaStreamSynchronize(st));
+    // pairs listed so far came from bk_group (neighbour bases already compared in aux mode); the sort path may append more
+    s.bk_group_fwd = h.ctr[0];
+    s.bk_group_rev = h.ctr[6];
     *nrecords = h.meta.nrec;
     s.bk_spilled = h.spill[1];
     s.bk_direct = h.spill[3];
@@ -704,7 +1086,7 @@ int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_co
         MCU_TRY(s.vals_a.reserve((ns + 1) * 4));
         MCU_TRY(s.vals_b.reserve((ns + 1) * 4));
         bk_spill_kernel<<<(unsigned)h.spill[0], BK_THREADS, 0, st>>>(s.bk_b.as<u64>(), off2, meta, s.bk_spill.as<u32>(), pl, s.keys_a.as<u64>(),
-                                                                     s.vals_a.as<u32>(), spill + 2);
+                                                                     s.vals_a.as<u32>(), spill + 2, nullptr);
         s.launches++;
         bool in_a = true;
         u64 before = s.radix.launches;

@@ -212,3 +212,20 @@ def colliding_diagonals_pair(n=120_000, n_copies=150, seed=5, snp=0.01, table=40
         if 0 <= q and q + 41 <= tail_len:
             tail[q:q + 41] = a[x - 20:x + 21]
     return a.tobytes(), np.concatenate([b, tail]).tobytes()
+
+
+def repeat_rich_pair(n=300_000, unit=61, copies=3000, seed=11, snp=0.01):
+    """Pair with a long tandem repeat (every mer inside the unit occurs `copies` times) and dispersed copies of a
+    second element: exercises the overflow / spill paths of the bucketed enumeration (csrc/bucket.cu) and
+    MER_REPEAT_LIMIT-sized runs (LM/MatchFinder.cpp:166)."""
+    rng = rng_for(seed)
+    a = random_genome(n, 0.5, rng)
+    u = random_genome(unit, 0.5, rng)
+    tandem = np.tile(u, copies)
+    k = n // 3
+    a = np.concatenate([a[:k], tandem, a[k:]])
+    elem = random_genome(400, 0.5, rng)
+    for p in rng.integers(0, a.size - 400, 700):
+        a[p:p + 400] = elem
+    b = snps(a, snp, rng)
+    return a.tobytes(), b.tobytes()

@@ -363,3 +363,35 @@ def test_two_phase_sharded_order_dependent_buckets(mp, orc):
     orows, _ = orc.find_mums(a, b, seed, 0)
     out, emitted, st = _two_phase(mp, a, b, seed, 2)
     assert int(st[0]) > 0 and np.array_equal(out, orows)
+
+
+# ---- bucketed enumeration: repeats overflow the fixed-capacity buckets ------------------------------------------
+@pytest.mark.parametrize("w,r", [(15, 3), (19, 3), (11, 0)])
+def test_mums_repeat_rich_overflow_paths(mp, orc, monkeypatch, w, r):
+    """many copies of one mer: overflow records + dirty buckets take the radix-sort path; a full overflow array makes the
+    run start over with exact bucket sizes; all three give the oracle's rows"""
+    a, b = synth.repeat_rich_pair(seed=w)
+    seed = mp.getSeed(w, r)
+    orows, ostats = orc.find_mums(a, b, seed, 0)
+    s = mp.AnchorSession()
+    s.upload(a, b)
+    s.run(seed)
+    assert s.stage_ms[7] == -1 and s.stage_ms[15] > 0       # fixed-capacity layout, some buckets spilled to the sort path
+    assert int(s.stats[3]) == 1                              # a run longer than MER_REPEAT_LIMIT was seen
+    assert np.array_equal(s.download(), orows)
+    monkeypatch.setenv("MAUVE_CUDA_OVF_CAP", "100")
+    s.run(seed)
+    assert s.stage_ms[7] == -2                               # fell back to exact bucket sizes
+    assert np.array_equal(s.download(), orows)
+    monkeypatch.delenv("MAUVE_CUDA_OVF_CAP")
+    monkeypatch.setenv("MAUVE_CUDA_EXACT_BUCKETS", "1")
+    s.run(seed)
+    assert s.stage_ms[7] == -2 and np.array_equal(s.download(), orows)
+    monkeypatch.delenv("MAUVE_CUDA_EXACT_BUCKETS")
+    for world in (2, 5):                                     # sharded: fixed level-1 bin ranges per rank
+        parts = []
+        for rank in range(world):
+            s.run(seed, rank, world)
+            parts.append(s.download().copy())
+        assert np.array_equal(np.unique(mp.merge_matches(np.concatenate(parts, axis=0)), axis=0), np.unique(orows, axis=0))
+    s.close()
