@@ -74,9 +74,6 @@ def test_hmm_small(orc):
         assert np.array_equal(orc.hmm_params(c[1], c[2], c[3], c[4]), params)
         pred, post = orc.hmm_run(sym, params)
         ref_post = z["post%d" % i]
-        # north_star tolerance: 1e-5 relative on the posterior (the reference computes in float-mantissa bfloat)
-        assert np.allclose(post, ref_post, rtol=1e-5, atol=1e-30), (i, np.max(np.abs(post - ref_post) / np.maximum(ref_post, 1e-300)))
-        ref_pred = np.frombuffer(z["pred%d" % i].tobytes(), dtype=np.uint8)
-        mism = np.flatnonzero(np.frombuffer(pred, dtype=np.uint8) != ref_pred)
-        # H/N may flip only where the posterior sits within tolerance of the 0.9 threshold
-        assert all(abs(ref_post[j] - 0.9) <= 1e-5 for j in mism)
+        # the restatement performs the reference's bfloat operations (float32 mantissa) in the same order: bit-identical
+        assert np.array_equal(post, ref_post), (i, np.max(np.abs(post - ref_post) / np.maximum(ref_post, 1e-300)))
+        assert pred == z["pred%d" % i].tobytes()
