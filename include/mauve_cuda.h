@@ -89,6 +89,20 @@ int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed,
 int mcu_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule,
                   mcu_match** out, uint64_t* n_out, uint64_t* stats);
 
+/* ---- batched gap search: replaces the per-gap calls of recursive anchoring, pairwiseAnchorSearch
+ *      (LM/ProgressiveAligner.cpp:590-679, called for every gap by recurseOnPairs :681-924) and the pairwise part of
+ *      SearchLCBGaps (LM/Aligner.cpp:784-930): per gap two DNAMemorySML::Create + MemHash::FindMatches with the MUM
+ *      settings.  Pair i = seq0[off0[i], off0[i+1]) vs seq1[off1[i], off1[i+1]) searched with pattern seeds[i]
+ *      (the caller picks it as the reference does: getSeed(getDefaultSeedWeight(average gap length), 0), :617-626;
+ *      seeds[i] == 0 skips the pair, as the reference does for weights < 5, :627).  Pairs sharing a pattern are
+ *      processed in one launch sequence (segment-tagged keys, one radix sort).  Output: *out = all rows, pair by
+ *      pair, each pair's rows in the reference's list order with coordinates local to the pair's sequences;
+ *      out_off (n_pairs + 1, caller-allocated): rows of pair i are [out_off[i], out_off[i+1]).  stats (optional,
+ *      4 x uint64): [0] unique seed pairs, [1] matches, [2] pairs redone one by one because a hash bucket was
+ *      order dependent (csrc/replay.cu), [3] distinct patterns (= launch sequences).                              */
+int mcu_find_mums_batch(uint64_t n_pairs, const char* seq0, const uint64_t* off0, const char* seq1, const uint64_t* off1,
+                        const uint64_t* seeds, int rule, mcu_match** out, uint64_t* out_off, uint64_t* stats);
+
 /* ---- device-resident session (measurement + multi-GPU sharding) -------------------------
  * Same computation as mcu_find_mums, split so the timed region can start with both genomes
  * already in HBM.  shard_index/shard_count partition the seed-key space by canonical-key

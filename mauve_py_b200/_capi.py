@@ -19,7 +19,7 @@ RULE_PAIRWISE, RULE_MEMHASH = 0, 1
 SYMBOLS = [
     "mcu_init", "mcu_shutdown", "mcu_last_error", "mcu_free", "mcu_host_alloc", "mcu_host_free",
     "mcu_get_seed", "mcu_default_seed_weight", "mcu_seed_length", "mcu_seed_weight",
-    "mcu_sml_build", "mcu_find_mums",
+    "mcu_sml_build", "mcu_find_mums", "mcu_find_mums_batch",
     "mcu_session_create", "mcu_session_destroy", "mcu_session_upload", "mcu_session_run",
     "mcu_session_enumerate", "mcu_session_uniq_bitmap", "mcu_session_finish", "mcu_session_merge",
     "mcu_session_match_count", "mcu_session_download", "mcu_session_matches_device",
@@ -67,6 +67,7 @@ def lib():
     L.mcu_seed_weight.argtypes = [u64]
     L.mcu_sml_build.argtypes = [vp, u64, u64, vp, vp, vp, C.POINTER(u64)]
     L.mcu_find_mums.argtypes = [vp, u64, vp, u64, u64, i32, C.POINTER(C.POINTER(Match)), C.POINTER(u64), vp]
+    L.mcu_find_mums_batch.argtypes = [u64, vp, vp, vp, vp, vp, i32, C.POINTER(C.POINTER(Match)), vp, vp]
     L.mcu_session_create.argtypes = [C.POINTER(vp)]
     L.mcu_session_destroy.argtypes = [vp]
     L.mcu_session_destroy.restype = None

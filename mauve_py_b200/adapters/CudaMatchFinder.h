@@ -15,10 +15,13 @@
 
 #include <iostream>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "libMems/MemHash.h"
 #include "libMems/PairwiseMatchFinder.h"
 #include "libMems/MatchList.h"
+#include "libMems/SeedMasks.h"
 #include "mauve_cuda.h"
 
 namespace mems {
@@ -77,6 +80,45 @@ public:
 		cuda_detail::FindMatchesTwoGenomes(ml, MCU_RULE_MEMHASH, m_mem_count, m_collision_count);
 	}
 };
+
+// One round of recursive anchoring in one device call: the matches MemHash (MUM settings) finds in every gap pair, i.e.
+// what pairwiseAnchorSearch (LM/ProgressiveAligner.cpp:590-679) has in gap_list after gap_mh.FindMatches (:651) and before
+// EliminateOverlaps_v2 / LengthFilter (:656-660), which stay with the caller together with the coordinate shift (:662-671).
+// The seed of a gap is the reference's: getSeed(getDefaultSeedWeight((len0 + len1) / 2), 0), no search below
+// MIN_DNA_SEED_WEIGHT (:617-634).  (--seed-family, three seeds per gap, is not batched: use CudaMemHash per gap.)
+// out[i]: slot-allocated Match copies for gap i, in GetMatchList order, coordinates local to the gap sequences.
+inline void CudaGapSearchBatch(const std::vector<std::pair<std::string, std::string> >& gaps, std::vector<std::vector<Match*> >& out)
+{
+	const size_t n = gaps.size();
+	out.assign(n, std::vector<Match*>());
+	std::string c0, c1;
+	std::vector<uint64_t> o0(1, 0), o1(1, 0), seeds(n, 0), out_off(n + 1, 0);
+	for (size_t i = 0; i < n; ++i) {
+		c0 += gaps[i].first;
+		c1 += gaps[i].second;
+		o0.push_back(c0.size());
+		o1.push_back(c1.size());
+		const uint w = getDefaultSeedWeight((gaps[i].first.size() + gaps[i].second.size()) / 2);
+		seeds[i] = w < MIN_DNA_SEED_WEIGHT ? 0 : (uint64_t)getSeed(w, 0);
+	}
+	mcu_match* rows = NULL;
+	const int rc = mcu_find_mums_batch(n, c0.data(), &o0[0], c1.data(), &o1[0], n ? &seeds[0] : NULL, MCU_RULE_MEMHASH, &rows, &out_off[0], NULL);
+	if (rc == MCU_EGAP) throw "ERROR: gap character encountered in input sequence";
+	if (rc != MCU_OK) {
+		std::cerr << "CudaGapSearchBatch: " << mcu_last_error() << std::endl;
+		Throw_gnEx(InvalidData());
+	}
+	Match mm(2);
+	for (size_t i = 0; i < n; ++i)
+		for (uint64_t r = out_off[i]; r < out_off[i + 1]; ++r) {
+			Match* m = mm.Copy();
+			m->SetStart(0, rows[r].start0);
+			m->SetStart(1, rows[r].start1);
+			m->SetLength(rows[r].len);
+			out[i].push_back(m);
+		}
+	mcu_free(rows);
+}
 
 }  // namespace mems
 

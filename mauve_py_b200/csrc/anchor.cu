@@ -501,7 +501,7 @@ void session_destroy(Session& s)
                       &s.matches, &s.ord_primary, &s.counters, &s.radix.hist, &s.radix.status, &s.radix.counters,
                       &s.rp_ctr, &s.rp_bitmap, &s.rp_list, &s.rp_canon, &s.rp_keys_b, &s.rp_idx_a, &s.rp_idx_b, &s.rp_p0, &s.rp_row, &s.rp_bkeys,
                       &s.rp_pool, &s.rp_extra, &s.rp_prefix, &s.rp_vinfo, &s.rp_out,
-                      &s.bk_a, &s.bk_b, &s.bk_tab1, &s.bk_tab2, &s.bk_spill, &s.bk_tileseg};
+                      &s.bk_a, &s.bk_b, &s.bk_tab1, &s.bk_tab2, &s.bk_spill, &s.bk_tileseg, &s.bt_tab, &s.bt_seg_a, &s.bt_seg_b};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(s.ev[i]);
     for (int i = 0; i < 12; ++i) cudaEventDestroy(s.kev[i]);
@@ -534,6 +534,8 @@ static int run_pack(Session& s, int g, u32* err_flag)
     s.launches++;
     return MCU_OK;
 }
+
+int run_pack_genome(Session& s, int g, u32* err_flag) { return run_pack(s, g, err_flag); }
 
 // Phase 1 of a run: pack + enumeration of the unique seed pairs of this rank's key range (uniq bitmap, pair list).
 template <typename K>

@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "radix.cuh"
 
+#include <vector>
+
 namespace mcu {
 
 struct Session {
@@ -14,6 +16,7 @@ struct Session {
     DevBuf uniq, pairs, cand, raw_matches, ord_keys_a, ord_keys_b, ord_vals_a, ord_vals_b, ord_primary, matches, counters;
     // bucketed enumeration (bucket.cu)
     DevBuf bk_a, bk_b, bk_tab1, bk_tab2, bk_spill, bk_tileseg;
+    DevBuf bt_tab, bt_seg_a, bt_seg_b;  // batched gap search (batch.cu)
     u64 bk_spilled = 0, bk_direct = 0, bk_fallbacks = 0;  // fallbacks: runs that overflowed the fixed-capacity layout and were redone exactly
     u64 bk_group_fwd = 0, bk_group_rev = 0;  // leading forward / reverse pairs of the pair list that bk_group emitted
     bool bk_exact = false;  // the last bucketed run used exact (counted) bucket sizes: forced, or after an overflow of the fixed layout
@@ -55,6 +58,13 @@ int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_co
 // s.matches / s.match_count are updated in place.
 int replay_unclean(Session& s, const SeedParams* sp, bool can_replay, u64* unclean_buckets, u64* duplicate_rows);
 
+// batched gap search (batch.cu): n_seg sequence pairs given as two concatenations + offsets, one seed for all of them.
+// Host outputs: rows (segment-local coordinates, reference list order inside every segment, segments ascending), the
+// segment of every row, and the segments whose hash buckets are order dependent (to be redone one by one).
+int batch_find_mums(Session& s, const char* cat0, const u64* off0, const char* cat1, const u64* off1, u32 n_seg, u64 seed,
+                    std::vector<mcu_match>* rows, std::vector<u32>* row_seg, std::vector<u32>* unclean_segs, u64* seed_pairs);
+int run_pack_genome(Session& s, int g, u32* err_flag);
+
 // single-genome SML (stable): outputs on device in s.keys_*/vals_* ; returns which buffer
 int sml_build_device(Session& s, const char* seq, u64 n, u64 seed, u32* pos_out, u64* mer_out, u32* packed_out, u64* len_out);
 
@@ -70,6 +80,24 @@ struct ExtendArgs {
     mcu_match* out;
     unsigned long long* counters;
 };
+
+// valid seed start positions of the two sequences being compared: [lo0, hi0) in genome 0, [lo1, hi1) in genome 1
+// (the whole genomes, or one segment pair of a batched gap search)
+struct DiagBounds {
+    i64 lo0, hi0, lo1, hi1;
+};
+
+__device__ __forceinline__ bool probe_hit_in(const ExtendArgs& a, const SeedParams& sp, bool rev, i64 d, i64 t, i64& other, const DiagBounds& b)
+{
+    if (t < b.lo0 || t >= b.hi0) return false;
+    other = rev ? d - t : t + d;
+    if (other < b.lo1 || other >= b.hi1) return false;
+    u64 f0 = extract_seed(load_mer32(a.g0, (u64)t), sp);
+    u64 x1 = extract_seed(load_mer32(a.g1, (u64)other), sp);
+    if (!rev) return f0 == x1;
+    if (f0 != revcomp_seed(x1, sp.w)) return false;
+    return f0 != revcomp_seed(f0, sp.w);
+}
 
 __device__ __forceinline__ bool probe_hit(const ExtendArgs& a, const SeedParams& sp, bool rev, i64 d, i64 t, i64& other)
 {

@@ -2,7 +2,10 @@
 // the process-wide default session, seed-pattern tables.  No compute happens on the host.
 #include <stdarg.h>
 #include <math.h>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 #include <new>
 
 #include "anchor.cuh"
@@ -224,6 +227,88 @@ int mcu_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, 
     }
     *out = r;
     *n_out = m;
+    return MCU_OK;
+}
+
+// ---- batched gap search -------------------------------------------------------------------
+int mcu_find_mums_batch(uint64_t n_pairs, const char* seq0, const uint64_t* off0, const char* seq1, const uint64_t* off1, const uint64_t* seeds,
+                        int rule, mcu_match** out, uint64_t* out_off, uint64_t* stats)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    if (!out || !out_off) { set_error("mcu_find_mums_batch: NULL output pointer"); return MCU_EINVAL; }
+    if (n_pairs && (!seq0 || !seq1 || !off0 || !off1 || !seeds)) { set_error("mcu_find_mums_batch: NULL input pointer"); return MCU_EINVAL; }
+    if (rule != MCU_RULE_PAIRWISE && rule != MCU_RULE_MEMHASH) { set_error("mcu_find_mums_batch: unknown rule %d", rule); return MCU_EINVAL; }
+    if (n_pairs >= 0xFFFFFFFFull) { set_error("mcu_find_mums_batch: too many pairs"); return MCU_EINVAL; }
+    for (uint64_t i = 0; i < n_pairs; ++i)
+        if (off0[i + 1] < off0[i] || off1[i + 1] < off1[i]) { set_error("mcu_find_mums_batch: offsets not monotone at pair %llu", (unsigned long long)i); return MCU_EINVAL; }
+    Session* s;
+    MCU_TRY(default_session(&s));
+    // pairs that share a seed pattern go through the device together (LM/ProgressiveAligner.cpp:617-626: the weight depends on
+    // the gap length only, so a round of recursive anchoring uses a handful of patterns); seed 0 = "no search" (:627)
+    std::map<uint64_t, std::vector<uint32_t> > groups;
+    for (uint64_t i = 0; i < n_pairs; ++i)
+        if (seeds[i]) groups[seeds[i]].push_back((uint32_t)i);
+    std::vector<mcu_match> all_rows;
+    std::vector<uint32_t> all_pair;
+    std::vector<uint32_t> redo;
+    uint64_t seed_pairs_total = 0;
+    for (auto& g : groups) {
+        const std::vector<uint32_t>& idx = g.second;
+        // chunks keep the concatenations below the 32-bit position limit of the reference's match coordinates
+        size_t first = 0;
+        while (first < idx.size()) {
+            std::string c0, c1;
+            std::vector<u64> o0(1, 0), o1(1, 0);
+            size_t last = first;
+            while (last < idx.size()) {
+                const uint64_t i = idx[last];
+                const u64 l0 = off0[i + 1] - off0[i], l1 = off1[i + 1] - off1[i];
+                if (last > first && (c0.size() + l0 >= 0xF0000000ull || c1.size() + l1 >= 0xF0000000ull)) break;
+                c0.append(seq0 + off0[i], l0);
+                c1.append(seq1 + off1[i], l1);
+                o0.push_back(c0.size());
+                o1.push_back(c1.size());
+                ++last;
+            }
+            std::vector<mcu_match> rows;
+            std::vector<u32> seg, unclean;
+            u64 sp = 0;
+            MCU_TRY(batch_find_mums(*s, c0.data(), o0.data(), c1.data(), o1.data(), (u32)(last - first), g.first, &rows, &seg, &unclean, &sp));
+            seed_pairs_total += sp;
+            std::vector<char> is_unclean(last - first, 0);
+            for (u32 u : unclean) { is_unclean[u] = 1; redo.push_back(idx[first + u]); }
+            for (size_t r = 0; r < rows.size(); ++r) {
+                if (is_unclean[seg[r]]) continue;
+                all_rows.push_back(rows[r]);
+                all_pair.push_back(idx[first + seg[r]]);
+            }
+            first = last;
+        }
+    }
+    // order-dependent hash buckets (csrc/replay.cu): those pairs take the single-pair path, which replays them exactly
+    for (uint32_t i : redo) {
+        MCU_TRY(session_upload(*s, seq0 + off0[i], off0[i + 1] - off0[i], seq1 + off1[i], off1[i + 1] - off1[i]));
+        MCU_TRY(session_run(*s, seeds[i], 0, 1, nullptr, nullptr));
+        const u64 m = s->match_count;
+        std::vector<mcu_match> rows(m);
+        if (m) {
+            MCU_CUDA(cudaMemcpyAsync(rows.data(), s->matches.p, m * sizeof(mcu_match), cudaMemcpyDeviceToHost, s->stream));
+            MCU_CUDA(cudaStreamSynchronize(s->stream));
+        }
+        for (u64 r = 0; r < m; ++r) { all_rows.push_back(rows[r]); all_pair.push_back(i); }
+    }
+    // rows of one pair stay in the order they were produced; pairs ascending
+    for (uint64_t i = 0; i <= n_pairs; ++i) out_off[i] = 0;
+    for (uint32_t p : all_pair) out_off[p + 1]++;
+    for (uint64_t i = 0; i < n_pairs; ++i) out_off[i + 1] += out_off[i];
+    const u64 total = all_rows.size();
+    mcu_match* r = (mcu_match*)malloc((total ? total : 1) * sizeof(mcu_match));
+    if (!r) { set_error("out of host memory"); return MCU_ENOMEM; }
+    std::vector<u64> cursor(out_off, out_off + n_pairs);
+    for (u64 k = 0; k < total; ++k) r[cursor[all_pair[k]]++] = all_rows[k];
+    *out = r;
+    if (stats) { stats[0] = seed_pairs_total; stats[1] = total; stats[2] = redo.size(); stats[3] = groups.size(); }
     return MCU_OK;
 }
 

@@ -253,6 +253,35 @@ def find_mums(seq0, seq1, seed, rule=_capi.RULE_PAIRWISE):
     return _find_mums(seq0, seq1, seed, rule)
 
 
+def find_mums_batch(pairs, seeds=None, rule=_capi.RULE_MEMHASH, seed_rank=0):
+    """Gap search over many sequence pairs at once (mcu_find_mums_batch): the device form of one round of
+    pairwiseAnchorSearch calls (LM/ProgressiveAligner.cpp:590-679).  pairs: [(bytes, bytes), ...]; seeds: one pattern per
+    pair, default = the reference's choice getSeed(getDefaultSeedWeight((len0 + len1) / 2), rank 0) with 0 (no search) when
+    the weight is below 5 (:617-627).  Returns ([rows[n_i,3] per pair, coordinates local to the pair], stats[4])."""
+    n = len(pairs)
+    if seeds is None:
+        seeds = []
+        for a, b in pairs:
+            w = getDefaultSeedWeight((len(a) + len(b)) // 2)
+            seeds.append(getSeed(w, seed_rank) if w >= 5 else 0)
+    seeds = np.asarray(seeds, dtype=np.uint64)
+    cat0 = b"".join(bytes(a) for a, _ in pairs)
+    cat1 = b"".join(bytes(b) for _, b in pairs)
+    off0 = np.zeros(n + 1, dtype=np.uint64)
+    off1 = np.zeros(n + 1, dtype=np.uint64)
+    off0[1:] = np.cumsum([len(a) for a, _ in pairs], dtype=np.uint64)
+    off1[1:] = np.cumsum([len(b) for _, b in pairs], dtype=np.uint64)
+    out = C.POINTER(_capi.Match)()
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    stats = np.zeros(4, dtype=np.uint64)
+    check(lib().mcu_find_mums_batch(n, cat0, off0.ctypes.data, cat1, off1.ctypes.data, seeds.ctypes.data, rule, C.byref(out),
+                                    out_off.ctypes.data, stats.ctypes.data))
+    total = int(out_off[n])
+    rows = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_int64)), shape=(max(total, 1), 3))[:total].copy() if total else np.zeros((0, 3), dtype=np.int64)
+    lib().mcu_free(out)
+    return [rows[int(out_off[i]):int(out_off[i + 1])] for i in range(n)], stats
+
+
 class AnchorSession:
     """Device-resident form of the same path (include/mauve_cuda.h: mcu_session_*): used by bench.py and multi-GPU runs."""
 

@@ -6,6 +6,7 @@
 //
 //   sml  <fasta> <weight> <rank>            DNAMemorySML vs CudaDNAMemorySML: Read() over the whole list
 //   mums <a.fa> <b.fa> <weight> <rank> [memhash]   PairwiseMatchFinder / MemHash vs the Cuda* finders: MatchList rows, in order
+//   gaps <pairs> <seed>                     the per-gap loop of pairwiseAnchorSearch (DNAMemorySML x2 + MemHash) vs one CudaGapSearchBatch call
 //   dp   <regions> <seed>                   muscle::GlobalAlign on ProfileFromMSA profiles vs CudaGlobalAlignBatch: PWPath edges
 //   hmm  <columns> <seed>                   run() vs run_cuda(): prediction strings
 //
@@ -174,6 +175,67 @@ static int cmd_mums(int argc, char** argv)
 	return ok ? 0 : 1;
 }
 
+// ---- gap search: per-gap MemHash (the reference's loop) vs one CudaGapSearchBatch call ----
+static int cmd_gaps(int argc, char** argv)
+{
+	if (argc < 4) return 2;
+	const int n = atoi(argv[2]);
+	Lcg rng(atoi(argv[3]));
+	vector<pair<string, string> > gaps(n);
+	for (int k = 0; k < n; ++k) {
+		const unsigned la = 20 + (unsigned)(exp(rng.unit() * log(400.0)) * 20.0);   // 40 bp .. 8 kbp
+		string a, b;
+		for (unsigned i = 0; i < la; ++i) a += "ACGT"[rng.next() & 3];
+		for (unsigned i = 0; i < la; ++i) {
+			const double u = rng.unit();
+			if (u < 0.005) continue;
+			if (u < 0.01) b += "ACGT"[rng.next() & 3];
+			b += u < 0.04 ? "ACGT"[rng.next() & 3] : a[i];
+		}
+		if (k % 4 == 0) {   // reverse complement
+			string r(b.rbegin(), b.rend());
+			for (size_t i = 0; i < r.size(); ++i) r[i] = r[i] == 'A' ? 'T' : r[i] == 'C' ? 'G' : r[i] == 'G' ? 'C' : 'A';
+			b = r;
+		}
+		gaps[k] = make_pair(a, b);
+	}
+	double t0 = now_s();
+	vector<vector<Match*> > cu;
+	CudaGapSearchBatch(gaps, cu);
+	double t1 = now_s();
+	bool ok = true;
+	size_t total = 0;
+	MemHash gap_mh;
+	gap_mh.SetRepeatTolerance(0);
+	gap_mh.SetEnumerationTolerance(1);
+	for (int k = 0; k < n; ++k) {   // LM/ProgressiveAligner.cpp:609-651
+		MatchList gap_list;
+		gap_list.seq_table.push_back(new gnSequence(gaps[k].first));
+		gap_list.seq_table.push_back(new gnSequence(gaps[k].second));
+		gap_list.sml_table.push_back(new DNAMemorySML());
+		gap_list.sml_table.push_back(new DNAMemorySML());
+		const gnSeqI avg_len = (gap_list.seq_table[0]->length() + gap_list.seq_table[1]->length()) / 2;
+		const uint w = getDefaultSeedWeight(avg_len);
+		gap_mh.Clear();
+		if (w >= MIN_DNA_SEED_WEIGHT) {
+			const uint64 seed = getSeed(w, 0);
+			for (uint s = 0; s < 2; ++s) gap_list.sml_table[s]->Create(*gap_list.seq_table[s], seed);
+			gap_mh.ClearSequences();
+			gap_mh.FindMatches(gap_list);
+		}
+		if (gap_list.size() != cu[k].size()) ok = false;
+		for (size_t i = 0; ok && i < gap_list.size(); ++i)
+			ok = gap_list[i]->Length() == cu[k][i]->Length() && gap_list[i]->Start(0) == cu[k][i]->Start(0) && gap_list[i]->Start(1) == cu[k][i]->Start(1);
+		total += gap_list.size();
+		for (size_t i = 0; i < gap_list.size(); ++i) gap_list[i]->Free();
+		for (size_t i = 0; i < cu[k].size(); ++i) cu[k][i]->Free();
+		for (uint s = 0; s < 2; ++s) { delete gap_list.seq_table[s]; delete gap_list.sml_table[s]; }
+	}
+	double t2 = now_s();
+	cout << "gaps " << n << "\nmatches " << total << "\ncuda_s " << (t1 - t0) << "\nreference_s " << (t2 - t1) << "\nRESULT " << (ok ? "identical" : "DIFFERENT") << endl;
+	return ok ? 0 : 1;
+}
+
 // ---- DP: globals exactly as MuscleInterface::ProfileAlignFast (LM/MuscleInterface.cpp:1086-1106) ----
 static void dp_globals()
 {
@@ -326,6 +388,7 @@ int main(int argc, char** argv)
 		const string c = argv[1];
 		if (c == "sml") return cmd_sml(argc, argv);
 		if (c == "mums") return cmd_mums(argc, argv);
+		if (c == "gaps") return cmd_gaps(argc, argv);
 		if (c == "dp") return cmd_dp(argc, argv);
 		if (c == "hmm") return cmd_hmm(argc, argv);
 	} catch (const char* msg) {

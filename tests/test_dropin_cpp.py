@@ -79,6 +79,14 @@ def test_dropin_sml(tmp_path, w, r):
 
 @needs_bin
 @pytest.mark.gpu
+def test_dropin_gap_search_batch():
+    """one round of recursive anchoring: 2000 gap pairs through the reference's per-gap loop and through one batched call"""
+    rc, kv, out = _run("gaps", 2000, 11)
+    assert rc == 0 and kv["RESULT"] == "identical" and int(kv["matches"]) > 2000, out
+
+
+@needs_bin
+@pytest.mark.gpu
 def test_dropin_dp_and_hmm():
     rc, kv, out = _run("dp", 120, 7)
     assert rc == 0 and kv["RESULT"] == "identical", out

@@ -413,3 +413,47 @@ def test_mums_repeat_rich_overflow_paths(mp, orc, monkeypatch, w, r):
             parts.append(s.download().copy())
         assert np.array_equal(np.unique(mp.merge_matches(np.concatenate(parts, axis=0)), axis=0), np.unique(orows, axis=0))
     s.close()
+
+
+# ---- batched gap search (recursive anchoring: many small pairs per call) ------------------------------------------
+def _gap_pairs(n, lo, hi, seed):
+    rng = np.random.default_rng(seed)
+    pairs = []
+    for i in range(n):
+        la = int(np.exp(rng.uniform(np.log(lo), np.log(hi))))
+        a, b = synth.small_pair(la, seed=seed * 1000 + i, snp=0.03, n_inv=1 if i % 3 == 0 else 0)
+        if i % 5 == 0:
+            b = synth.revcomp(np.frombuffer(b, dtype=np.uint8)).tobytes()
+        if i % 7 == 0:
+            b = b[: len(b) // 2]
+        pairs.append((a, b))
+    return pairs
+
+
+def test_gap_batch_vs_oracle(mp, orc):
+    """every pair of the batch gets the rows the oracle (= MemHash on that pair alone) gives, in the same order"""
+    pairs = _gap_pairs(300, 30, 6000, 5) + [(b"", b"ACGT"), (b"ACGTACGTAC", b"ACGTACGTAC"), (b"A" * 500, b"A" * 400)]
+    res, stats = mp.libmems.find_mums_batch(pairs)
+    assert len(res) == len(pairs) and int(stats[3]) >= 3          # several seed weights in one call
+    nonempty = 0
+    for (a, b), rows in zip(pairs, res):
+        w = mp.getDefaultSeedWeight((len(a) + len(b)) // 2)
+        if w < 5:
+            assert rows.shape[0] == 0
+            continue
+        orows, _ = orc.find_mums(a, b, mp.getSeed(w, 0), 1)
+        assert np.array_equal(rows, orows), (len(a), len(b), w)
+        nonempty += rows.shape[0] > 0
+    assert nonempty > 200
+
+
+def test_gap_batch_equals_single_pair_calls(mp):
+    """same rows as mcu_find_mums pair by pair, including a pair with order-dependent hash buckets (redone one by one)"""
+    pairs = _gap_pairs(40, 200, 20000, 9)
+    pairs.insert(7, synth.colliding_diagonals_pair(seed=5))
+    seeds = [mp.getSeed(11, 0)] * len(pairs)
+    res, stats = mp.libmems.find_mums_batch(pairs, seeds=seeds)
+    assert int(stats[2]) >= 1 and int(stats[3]) == 1
+    for (a, b), rows in zip(pairs, res):
+        single, _ = mp.libmems.find_mums(a, b, seeds[0], 1)
+        assert np.array_equal(rows, single)
