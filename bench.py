@@ -144,7 +144,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "Mbp/s", "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def config_dict(args, weight, seed):
@@ -155,7 +155,29 @@ def config_dict(args, weight, seed):
             "l2": "inputs (2 x %g MB ASCII, %.1f GB of key/value pairs) exceed the 126 MB L2; no extra flush" % (args.mbp, 2 * args.mbp * 12e6 / 1e9)}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Native libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout.  Everything
+    else goes to stderr: fd 1 is pointed at fd 2 for the run and the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -371,7 +393,7 @@ def main():
                 "ms_per_step": 1e3 * dte / args.steps, "api": "mcu_find_mums(host buffers)" if world == 1 else "mcu_session_upload + enumerate, NCCL all-reduce of the seed bitmap, finish, NCCL gather, mcu_session_merge"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "dp": dp, "hmm": hmm,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

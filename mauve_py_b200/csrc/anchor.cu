@@ -65,13 +65,14 @@ __global__ void __launch_bounds__(256) pack_kernel(const u8* __restrict__ seq, u
 template <typename K>
 __global__ void __launch_bounds__(256) seedgen_kernel(const u32* __restrict__ packed, u64 npos, SeedParams sp, u32 genome,
                                                      K* __restrict__ keys, u32* __restrict__ vals, u64 out_base,
-                                                     u64* __restrict__ hist, int passes, int sharded, u64 canon_lo, u64 canon_hi,
+                                                     u64* __restrict__ hist, int passes, u32 shard, u32 nshard,
                                                      unsigned long long* __restrict__ out_counter)
 {
     extern __shared__ u32 sh_hist[];  // passes*256
     for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) sh_hist[i] = 0;
     __syncthreads();
     const u32 lane = threadIdx.x & 31;
+    const bool sharded = nshard > 1;
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const u64 rounds = (npos + stride - 1) / stride;
     for (u64 r = 0; r < rounds; ++r) {
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) seedgen_kernel(const u32* __restrict__ pa
             u32 strand = rc < f;  // GetDnaSeedMer: forward wins ties (f < rc|1)
             u64 canon = strand ? rc : f;
             key = (canon << 2) | (genome << 1) | strand;
-            if (sharded) live = canon >= canon_lo && canon < canon_hi;
+            live = seed_owned(f, rc, shard, nshard);
         }
         u64 slot = out_base + p;
         if (sharded) {  // unordered compaction (tie order is irrelevant for match finding)
@@ -577,25 +578,13 @@ static int run_enumerate(Session& s, const SeedParams& sp, int shard_index, int 
         MCU_TRY(s.vals_a.reserve((ntot + 1) * sizeof(u32)));
         MCU_TRY(s.vals_b.reserve((ntot + 1) * sizeof(u32)));
         MCU_TRY(radix_clear_hist(s.radix, s.stream));
-        u64 canon_lo = 0, canon_hi = ~0ull;
-        if (sharded) {
-            // equal slices of the canonical key space [0, 4^w)
-            const int kb = 2 * sp.w;
-            auto edge = [&](int i) -> u64 {
-                if (i >= shard_count) return kb >= 64 ? ~0ull : (1ull << kb);
-                unsigned __int128 span = kb >= 64 ? ((unsigned __int128)1 << 64) : ((unsigned __int128)1 << kb);
-                return (u64)(span * (unsigned)i / (unsigned)shard_count);
-            };
-            canon_lo = edge(shard_index);
-            canon_hi = edge(shard_index + 1);
-        }
         const u64 npos[2] = {npos0, npos1};
         u64 base = 0;
         for (int g = 0; g < 2; ++g) {
             if (npos[g]) {
                 seedgen_kernel<K><<<grid_for(npos[g], 256, 8), 256, passes * 256 * sizeof(u32), s.stream>>>(
                     s.packed[g].as<u32>(), npos[g], sp, (u32)g, s.keys_a.as<K>(), s.vals_a.as<u32>(), sharded ? 0 : base,
-                    s.radix.hist.as<u64>(), passes, sharded ? 1 : 0, canon_lo, canon_hi, ctr + 5);
+                    s.radix.hist.as<u64>(), passes, (u32)shard_index, (u32)shard_count, ctr + 5);
                 s.launches++;
             }
             base += npos[g];
@@ -811,7 +800,7 @@ static int sml_build_t(Session& s, const SeedParams& sp, u32* pos_out, u64* mer_
     bool in_a = true;
     if (npos) {
         seedgen_kernel<K><<<grid_for(npos, 256, 8), 256, passes * 256 * sizeof(u32), s.stream>>>(
-            s.packed[0].as<u32>(), npos, sp, 0u, s.keys_a.as<K>(), s.vals_a.as<u32>(), 0, s.radix.hist.as<u64>(), passes, 0, 0, ~0ull, ctr + 5);
+            s.packed[0].as<u32>(), npos, sp, 0u, s.keys_a.as<K>(), s.vals_a.as<u32>(), 0, s.radix.hist.as<u64>(), passes, 0u, 1u, ctr + 5);
         s.launches++;
         u64 before = s.radix.launches;
         MCU_TRY(radix_sort_pairs<K>(s.radix, s.keys_a.as<K>(), s.vals_a.as<u32>(), s.keys_b.as<K>(), s.vals_b.as<u32>(), npos, key_bits, true,

@@ -47,6 +47,7 @@ struct BkPlan {
     // fixed-capacity layout (histogram-free path): this rank owns the level-1 bins [b_lo, b_hi); every level-1 bucket has room
     // for cap1 records, every final bucket for BK_CAP
     u32 b_lo, b_hi, cap1;
+    u32 shard, nshard;  // seed ownership in a sharded run (seed_owned, common.cuh)
 };
 
 struct BkMeta {  // written by bk_scan1_kernel
@@ -66,12 +67,15 @@ __device__ __forceinline__ u64 bk_mix(u64 x, int kbits)
     return (x * 0x9E3779B97F4A7C15ull) & mask;      // every output bit depends on all lower input bits: the top (bucket) bits on all of them
 }
 
-__device__ __forceinline__ void seed_canon32(u64 mer32, const SeedParams& sp, u64& key, u32& strand)
+// false when another rank owns the seed
+__device__ __forceinline__ bool seed_canon32(u64 mer32, const SeedParams& sp, u32 shard, u32 nshard, u64& key, u32& strand)
 {
     const u64 f = extract_seed(mer32, sp);
     const u64 rc = revcomp_seed(f, sp.w);
+    if (!seed_owned(f, rc, shard, nshard)) return false;
     strand = rc < f;  // GetDnaSeedMer: forward wins ties
     key = bk_mix(strand ? rc : f, 2 * sp.w);
+    return true;
 }
 
 // 16 consecutive positions starting at a multiple of 16 read the same three packed words
@@ -107,8 +111,7 @@ __global__ void __launch_bounds__(BK_THREADS) bk_hist1_kernel(const u32* __restr
             if (pos + j < npos) {
                 u64 canon;
                 u32 strand;
-                seed_canon32(w.mer(j), sp, canon, strand);
-                atomicAdd(&sh[(u32)(canon >> pl.rem1)], 1u);
+                if (seed_canon32(w.mer(j), sp, pl.shard, pl.nshard, canon, strand)) atomicAdd(&sh[(u32)(canon >> pl.rem1)], 1u);
             }
         }
     }
@@ -117,29 +120,14 @@ __global__ void __launch_bounds__(BK_THREADS) bk_hist1_kernel(const u32* __restr
         if (sh[i]) atomicAdd(&count1[i], (unsigned long long)sh[i]);
 }
 
-// offsets of the level-1 buckets of this rank.  Rank r owns the buckets [e_r, e_{r+1}) with e_i = first bucket
-// whose cumulative count reaches total*i/R: every rank derives the same edges from the same genomes.
+// offsets of the level-1 buckets (counts of this rank's seeds)
 __global__ void bk_scan1_kernel(const unsigned long long* __restrict__ count1, BkPlan pl, int shard, int nshard, u64* __restrict__ off1,
                                 unsigned long long* __restrict__ cursor1, BkMeta* __restrict__ meta)
 {
     if (threadIdx.x || blockIdx.x) return;
     u64 total = 0;
     for (u32 b = 0; b < pl.B1; ++b) total += count1[b];
-    u32 edge_lo = 0, edge_hi = pl.B1;
-    if (nshard > 1) {
-        const u64 t_lo = (u64)((unsigned __int128)total * (unsigned)shard / (unsigned)nshard);
-        const u64 t_hi = (u64)((unsigned __int128)total * (unsigned)(shard + 1) / (unsigned)nshard);
-        u64 cum = 0;
-        bool have_lo = false, have_hi = false;
-        for (u32 b = 0; b < pl.B1; ++b) {
-            if (!have_lo && cum >= t_lo) { edge_lo = b; have_lo = true; }
-            if (!have_hi && cum >= t_hi) { edge_hi = b; have_hi = true; }
-            cum += count1[b];
-        }
-        if (!have_lo) edge_lo = pl.B1;
-        if (!have_hi || shard + 1 == nshard) edge_hi = pl.B1;
-        if (shard == 0) edge_lo = 0;
-    }
+    const u32 edge_lo = 0, edge_hi = pl.B1;  // ownership is decided per seed (seed_owned): every bucket holds this rank's share
     u64 run = 0;
     for (u32 b = 0; b < pl.B1; ++b) {
         off1[b] = run;
@@ -228,7 +216,6 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter1_kernel(const u32* _
     extern __shared__ __align__(16) unsigned char raw[];
     const BkScatterSmem s = bk_carve(raw, pl.B1);
     const u32 tid = threadIdx.x;
-    const u32 b_lo = meta->b_lo, b_hi = meta->b_hi;
     for (u32 i = tid; i < pl.B1; i += BK_THREADS) s.cnt[i] = 0;
     __syncthreads();
     const u64 idx0 = (u64)blockIdx.x * BK_TILE + (u64)tid * BK_IPT;  // 16 consecutive positions per thread
@@ -249,9 +236,8 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter1_kernel(const u32* _
             if (idx0 < pl.nidx && pos + it < npos) {
                 u64 canon;
                 u32 strand;
-                seed_canon32(w.mer(it), sp, canon, strand);
-                const u32 b = (u32)(canon >> pl.rem1);
-                if (b >= b_lo && b < b_hi) {
+                if (seed_canon32(w.mer(it), sp, pl.shard, pl.nshard, canon, strand)) {
+                    const u32 b = (u32)(canon >> pl.rem1);
                     const u64 keyrem = canon & ((1ull << pl.rem1) - 1);
                     u64 aux = 0;
                     if (pl.aux) {  // base before the seed | base after the seed << 2 (solid seeds: what a shift by one position adds)
@@ -489,7 +475,7 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* 
     extern __shared__ __align__(16) unsigned char raw[];
     const BkScatterSmem s = bk_carve(raw, pl.B1);
     const u32 tid = threadIdx.x;
-    const u32 b_lo = pl.b_lo, b_hi = pl.b_hi;
+    const u32 b_lo = pl.b_lo;
     for (u32 i = tid; i < pl.B1; i += BK_THREADS) s.cnt[i] = 0;
     __syncthreads();
     const u64 idx0 = (u64)blockIdx.x * BK_TILE + (u64)tid * BK_IPT;  // 16 consecutive positions per thread
@@ -518,13 +504,13 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* 
 #pragma unroll
             for (int it = 0; it < BK_IPT; ++it) {
                 const u32 nb = (nx >> (30 - 2 * it)) & 3u;  // base w + it: enters the mer at the next position, follows it at this one
-                if (pos + it < npos) {
+                if (pos + it < npos && seed_owned(f, rc, pl.shard, pl.nshard)) {
                     const u32 strand = rc < f;  // GetDnaSeedMer: forward wins ties
                     u64 x = strand ? rc : f;
                     x ^= x >> mshift;
                     const u64 canon = (x * 0x9E3779B97F4A7C15ull) & kmask;  // == bk_mix
                     const u32 b = (u32)(canon >> pl.rem1);
-                    if (b >= b_lo && b < b_hi) {
+                    {
                         const u64 keyrem = canon & ((1ull << pl.rem1) - 1);
                         u64 aux = 0;
                         if (pl.aux) {
@@ -541,12 +527,11 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* 
         } else {
 #pragma unroll
             for (int it = 0; it < BK_IPT; ++it) {
-                if (pos + it < npos) {
-                    u64 canon;
-                    u32 strand;
-                    seed_canon32(w.mer(it), sp, canon, strand);
+                u64 canon;
+                u32 strand;
+                if (pos + it < npos && seed_canon32(w.mer(it), sp, pl.shard, pl.nshard, canon, strand)) {
                     const u32 b = (u32)(canon >> pl.rem1);
-                    if (b >= b_lo && b < b_hi) {
+                    {
                         const u64 keyrem = canon & ((1ull << pl.rem1) - 1);
                         rec[it] = (keyrem << pl.kshift) | ((pos + it) << 2) | ((u64)strand << 1) | (u64)g;
                         br[it] = (b << 16) | atomicAdd(&s.cnt[b], 1u);
@@ -855,15 +840,17 @@ static int bit_len(u64 x)
     return b;
 }
 
-static bool make_plan(const SeedParams& sp, u64 npos0, u64 npos1, BkPlan* out)
+// `share`: 1 / fraction of the seeds this rank owns (shard count)
+static bool make_plan(const SeedParams& sp, u64 npos0, u64 npos1, u64 share, BkPlan* out)
 {
     BkPlan p;
     p.kbits = 2 * sp.w;
     p.npos0 = npos0; p.npos1 = npos1; p.ntot = npos0 + npos1;
     p.pbits = bit_len((npos0 > npos1 ? npos0 : npos1));
     if (p.pbits < 1) p.pbits = 1;
-    if (p.ntot < 65536 || p.ntot >= (1ull << 40)) return false;
-    int T = bit_len(p.ntot / 1536);          // 768..1536 records per final bucket: BK_CAP is > 13 sigma away
+    const u64 expect = p.ntot / share;  // records this rank will hold
+    if (expect < 65536 || p.ntot >= (1ull << 40)) return false;
+    int T = bit_len(expect / 1536);          // 768..1536 records per final bucket: BK_CAP is > 13 sigma away
     if (T > p.kbits - 2) T = p.kbits - 2;    // keep key bits for the in-bucket comparison
     if (T < 2 || T > 22) return false;
     p.d1 = (T + 1) / 2;
@@ -895,10 +882,10 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     *fell_back = false;
     cudaStream_t st = s.stream;
     unsigned long long* ctr = s.counters.as<unsigned long long>();
-    pl.b_lo = (u32)((u64)pl.B1 * (u64)shard_index / (u64)shard_count);
-    pl.b_hi = (u32)((u64)pl.B1 * (u64)(shard_index + 1) / (u64)shard_count);
+    pl.b_lo = 0;   // seeds are owned by hash (seed_owned), so every bucket holds this rank's 1/shard_count share
+    pl.b_hi = pl.B1;
     const u32 nb1 = pl.b_hi - pl.b_lo;
-    const double mean1 = (double)pl.ntot / pl.B1;
+    const double mean1 = (double)pl.ntot / (double)shard_count / pl.B1;
     pl.cap1 = (u32)(((u64)(mean1 + 8.0 * sqrt(mean1) + 64.0) + 31) & ~31ull);
     const u64 nfinal = (u64)nb1 * pl.B2;
     u64 ovf_cap = pl.ntot / 8 / (u64)shard_count + (1ull << 20);
@@ -995,7 +982,9 @@ int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_co
     const u64 npos0 = s.n[0] >= (u64)sp.L ? s.n[0] - sp.L + 1 : 0;
     const u64 npos1 = s.n[1] >= (u64)sp.L ? s.n[1] - sp.L + 1 : 0;
     BkPlan pl;
-    if (!npos0 || !npos1 || !make_plan(sp, npos0, npos1, &pl)) return MCU_OK;
+    if (!npos0 || !npos1 || !make_plan(sp, npos0, npos1, (u64)shard_count, &pl)) return MCU_OK;
+    pl.shard = (u32)shard_index;
+    pl.nshard = (u32)shard_count;
     cudaStream_t st = s.stream;
     unsigned long long* ctr = s.counters.as<unsigned long long>();
     if (getenv("MAUVE_CUDA_EXACT_BUCKETS") == nullptr) {

@@ -121,6 +121,17 @@ __device__ __forceinline__ u64 revcomp_seed(u64 f, int w)
     return x >> (64 - 2 * w);
 }
 
+// Which rank of a sharded run owns a seed: a hash of forward ^ reverse-complement, which is the same for a mer and its
+// reverse complement, so the decision needs neither the canonical form nor the bucket of the mer -- the non-owners'
+// whole cost per position is the rolling update of the two words and this test.  Every enumeration path uses it, so
+// ranks that end up on different paths (bucket overflow fallback) still agree on the partition.
+__device__ __forceinline__ bool seed_owned(u64 f, u64 rc, u32 shard, u32 nshard)
+{
+    if (nshard <= 1) return true;
+    const u32 h = (u32)(((f ^ rc) * 0xD6E8FEB86659FD93ull) >> 32);
+    return (u32)(((u64)h * nshard) >> 32) == shard;
+}
+
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ u32 lanemask_lt()
 {
