@@ -155,6 +155,40 @@ def config_dict(args, weight, seed):
             "l2": "inputs (2 x %g MB ASCII, %.1f GB of key/value pairs) exceed the 126 MB L2; no extra flush" % (args.mbp, 2 * args.mbp * 12e6 / 1e9)}
 
 
+def measure_dp(mp, synth, args):
+    """GCUPS of the gapped DP on a sample of BASELINE config 5 (+ the reference's NWSmall on a few regions of the same batch)"""
+    pairs = synth.dp_pairs(args.dp_regions, 100, 10000, seed=20261020)
+    arrs = synth.dp_arrays(pairs)
+    mp.libmems.nw_batch_arrays(*arrs)
+    res = mp.libmems.nw_batch_arrays(*arrs)
+    cells = float(res["stats"][0])
+    dp = {"metric": "GCUPS gapped DP (full-matrix cells, NWSmall-exact paths)", "value": cells / (res["device_ms"] * 1e-3) / 1e9,
+          "unit": "GCUPS", "regions": len(pairs), "cells": cells, "device_ms": res["device_ms"],
+          "workload": "BASELINE config 5 sample: %d regions, lenA log-uniform 100 bp-10 kbp, 5%% SNP + 1%% indel events" % len(pairs)}
+    if not args.no_cpu:
+        chk, kind = cpu_checker()
+        small = [p for p in pairs if len(p[0]) <= 3000][:12]
+        t0 = time.perf_counter()
+        for x, y in small:
+            chk.nw_align(x, y)
+        dtc = time.perf_counter() - t0
+        dp["cpu_baseline"] = {"value": sum(len(x) * len(y) for x, y in small) / dtc / 1e9, "unit": "GCUPS", "cores": 1, "kind": kind,
+                              "sample": "%d regions <= 3 kbp of the same batch" % len(small)}
+    return dp
+
+
+def measure_hmm(mp, synth, args):
+    """columns/s of the homology HMM: one column string per region (BASELINE config 5 scores every region), 512 distinct strings
+    tiled to 32768"""
+    pairs = synth.dp_pairs(512, 100, 10000, seed=20261020)
+    sym = [synth.hmm_string(len(p[0]), seed=i, block=300) for i, p in enumerate(pairs)] * 64
+    params = mp.libmems.hmm_params(0.5, 1e-5, 1e-9, 0.7)
+    mp.run_batch(sym, params, True)
+    _, _, hms = mp.run_batch(sym, params, True)
+    return {"metric": "HomologyHMM columns/s (Forward+Backward posteriors, bfloat-faithful: bit-identical to the reference)",
+            "value": sum(len(s) for s in sym) / (hms * 1e-3), "unit": "columns/s", "strings": len(sym), "device_ms": hms}
+
+
 _REAL_STDOUT = None
 
 
@@ -359,30 +393,15 @@ def main():
     # ---- gapped DP + HMM (secondary metrics of BASELINE.json) ----------------------------------------
     dp = hmm = None
     if not args.no_dp:
-        pairs = synth.dp_pairs(args.dp_regions, 100, 10000, seed=20261020)
-        arrs = synth.dp_arrays(pairs)
-        mp.libmems.nw_batch_arrays(*arrs)
-        res = mp.libmems.nw_batch_arrays(*arrs)
-        cells = float(res["stats"][0])
-        dp = {"metric": "GCUPS gapped DP (full-matrix cells, NWSmall-exact paths)", "value": cells / (res["device_ms"] * 1e-3) / 1e9,
-              "unit": "GCUPS", "regions": len(pairs), "cells": cells, "device_ms": res["device_ms"],
-              "workload": "BASELINE config 5 sample: %d regions, lenA log-uniform 100 bp-10 kbp, 5%% SNP + 1%% indel events" % len(pairs)}
-        if not args.no_cpu:
-            chk, kind = cpu_checker()
-            small = [p for p in pairs if len(p[0]) <= 3000][:12]
-            t0 = time.perf_counter()
-            for x, y in small:
-                chk.nw_align(x, y)
-            dtc = time.perf_counter() - t0
-            dp["cpu_baseline"] = {"value": sum(len(x) * len(y) for x, y in small) / dtc / 1e9, "unit": "GCUPS", "cores": 1, "kind": kind,
-                                  "sample": "%d regions <= 3 kbp of the same batch" % len(small)}
-        # one column string per region (BASELINE config 5 scores every region): 512 distinct strings tiled to 32768
-        sym = [synth.hmm_string(len(p[0]), seed=i, block=300) for i, p in enumerate(pairs[:512])] * 64
-        params = mp.libmems.hmm_params(0.5, 1e-5, 1e-9, 0.7)
-        mp.run_batch(sym, params, False)
-        _, _, hms = mp.run_batch(sym, params, False)
-        hmm = {"metric": "HomologyHMM columns/s (Forward+Backward posteriors, bfloat-faithful: bit-identical to the reference)",
-               "value": sum(len(s) for s in sym) / (hms * 1e-3), "unit": "columns/s", "strings": len(sym), "device_ms": hms}
+        # secondary metrics must never cost the headline line: a failure is reported inside the object
+        try:
+            dp = measure_dp(mp, synth, args)
+        except Exception as e:  # noqa: BLE001
+            dp = {"error": "%s: %s" % (type(e).__name__, e)}
+        try:
+            hmm = measure_hmm(mp, synth, args)
+        except Exception as e:  # noqa: BLE001
+            hmm = {"error": "%s: %s" % (type(e).__name__, e)}
 
     line = {
         "metric": "Mbp/s seed+match+extend", "value": value, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
