@@ -121,7 +121,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     import mauve_py_b200 as mp
-    a, b = workload(min(args.mbp, max(2 * args.cpu_sample_mbp, 1)))
+    a, b = workload(args.mbp)  # the same pair the GPU arm runs; the CPU gets its leading part
     sa, sb = cpu_sample(a, b, int(args.cpu_sample_mbp * 1e6))
     chk, kind = cpu_checker()
     weight = mp.getDefaultSeedWeight(int(args.mbp * 1e6))
@@ -218,7 +218,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mbp", type=float, default=100.0, help="genome size of the synthetic pair in Mbp")
-    ap.add_argument("--cpu-sample-mbp", type=float, default=2.0)
+    ap.add_argument("--cpu-sample-mbp", type=float, default=10.0, help="leading Mbp of both genomes timed on the CPU (10-30 s of reference work)")
     ap.add_argument("--dp-regions", type=int, default=1536)
     ap.add_argument("--no-dp", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -341,12 +341,22 @@ def main():
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    other = None
     if bucketed:
-        # bk_scatter2_kernel: one partition pass over 8-byte records (read 8 B + write 8 B per seed)
-        kname = "bk_scatter2_kernel (level-2 partition pass over %d 8-byte seed records)" % nsorted
-        bytes_per_launch = 16.0 * nsorted
-        per_launch_ms = float(stage[11])
+        # dominant kernel of the step by time: bk_group_kernel reads every 8-byte seed record once and writes 8 bytes per unique seed pair
+        npairs = float(stats[0])
+        kname = "bk_group_kernel (in-bucket grouping of %d 8-byte seed records into %d unique seed pairs)" % (nsorted, int(npairs))
+        bytes_per_launch = 8.0 * nsorted + 8.0 * npairs
+        per_launch_ms = float(stage[12])
         launches_per_step = 1
+        if world > 1 or abs(args.mbp - 100.0) > 1e-9:
+            traffic = None  # the ncu capture under profiles/ is of the unsharded 100 Mbp launch
+        # the two partition passes, same formula (algorithmic bytes / CUDA-event time)
+        other = {}
+        for name, nbytes, ms in (("bkf_scatter1_kernel", 8.0 * nsorted + 0.25 * nbases, float(stage[9])),
+                                 ("bkf_scatter2_kernel", 16.0 * nsorted, float(stage[11]))):
+            if ms > 0:
+                other[name] = {"bytes_per_launch": nbytes, "launch_ms": ms, "achieved": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
     else:
         passes = int(sess.stage_ms[7])
         kname = "rs_onesweep_kernel (one 8-bit LSD radix pass over %d key/value pairs)" % nsorted
@@ -363,6 +373,9 @@ def main():
     dev_ms = float(stage[6])
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "launch_ms": per_launch_ms, "launches_per_step": launches_per_step,
+                "note": "bk_group is issue-bound (ncu: 81 % of issue slots busy, profiles/r01_ncu_bucket_enumeration_summary.txt), so its HBM fraction is low by construction; "
+                        "`step` gives the whole pass against SURVEY.md 8d's algorithmic bytes" if bucketed else None,
+                "other_kernels": other,
                 "step": {"algorithmic_bytes": step_bytes, "bytes_per_base": b_per_base, "device_ms": dev_ms,
                          "achieved": step_bytes / (dev_ms * 1e-3) / 1e9 if dev_ms > 0 else 0.0,
                          "frac": (step_bytes / (dev_ms * 1e-3) / 1e9 / peak) if dev_ms > 0 else 0.0,
@@ -376,19 +389,22 @@ def main():
     # ---- CPU baseline on a bounded sample ---------------------------------------------------------
     cpu = None
     if not args.no_cpu:
-        chk, kind = cpu_checker()
-        sa, sb = cpu_sample(a, b, int(args.cpu_sample_mbp * 1e6))
-        t0 = time.perf_counter()
-        rows, _ = chk.find_mums(sa, sb, seed, 0)
-        dtc = time.perf_counter() - t0
-        # parity spot check on the same sample, through the C ABI
-        grows, _ = mp.libmems.find_mums(sa, sb, seed)
-        if not np.array_equal(grows, rows):
-            print("PARITY FAILURE on the CPU sample", file=sys.stderr)
-            sys.exit(3)
-        cpu = {"value": (len(sa) + len(sb)) / 1e6 / dtc, "unit": "Mbp/s", "cores": 1, "kind": kind,
-               "sample": "leading %.1f Mbp of both genomes (%d matches, GPU result identical); single thread: the reference has no threads"
-                         % (args.cpu_sample_mbp, rows.shape[0])}
+        try:
+            chk, kind = cpu_checker()
+            sa, sb = cpu_sample(a, b, int(args.cpu_sample_mbp * 1e6))
+            t0 = time.perf_counter()
+            rows, _ = chk.find_mums(sa, sb, seed, 0)
+            dtc = time.perf_counter() - t0
+            # parity spot check on the same sample, through the C ABI
+            grows, _ = mp.libmems.find_mums(sa, sb, seed)
+            same = bool(np.array_equal(grows, rows))
+            if not same:
+                print("PARITY FAILURE on the CPU sample", file=sys.stderr)
+            cpu = {"value": (len(sa) + len(sb)) / 1e6 / dtc, "unit": "Mbp/s", "cores": 1, "kind": kind, "parity": "identical" if same else "FAILED",
+                   "sample": "leading %.1f Mbp of both genomes (%d matches, GPU result %s); single thread: the reference has no threads"
+                             % (args.cpu_sample_mbp, rows.shape[0], "identical" if same else "DIFFERENT")}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # ---- gapped DP + HMM (secondary metrics of BASELINE.json) ----------------------------------------
     dp = hmm = None
