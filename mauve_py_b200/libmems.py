@@ -185,6 +185,57 @@ class MatchList:
         return np.array([[m.length, m.starts[0], m.starts[1]] for m in self.matches], dtype=np.int64).reshape(-1, 3)
 
 
+def WriteList(rows, stream, seq_filenames=("null", "null"), seq_lengths=(0, 0)):
+    """The match-list text format `progressiveMauve --mums` writes and `--match-input` reads back
+    (WriteList, LM/MatchList.h:617-662; consumed by ReadList :526-614 at MA/progressiveMauve.cpp:472-491): a device-built
+    list written here can be fed to the UNMODIFIED binary.  rows: [n, 3] (length, start0, start1) in list order, or a
+    MatchList.  The reference prints each Match's address as its id (any distinct integer does: ReadList only keys a map with
+    it); like the reference, nothing at all is written for an empty list."""
+    if isinstance(rows, MatchList):
+        rows = rows.as_array()
+    rows = np.asarray(rows, dtype=np.int64).reshape(-1, 3)
+    if rows.shape[0] == 0:
+        return
+    w = stream.write
+    w("FormatVersion\t3\n")
+    w("SequenceCount\t2\n")
+    for i in range(2):
+        w("Sequence%dFile\t%s\n" % (i, seq_filenames[i] if i < len(seq_filenames) else "null"))
+        w("Sequence%dLength\t%d\n" % (i, seq_lengths[i] if i < len(seq_lengths) else 0))
+    w("MatchCount\t%d\n" % rows.shape[0])
+    for k, (ln, s0, s1) in enumerate(rows.tolist()):
+        w("%d\t%d\t%d\t%d\t0\t0\n" % (ln, s0, s1, k + 1))
+
+
+def ReadList(stream):
+    """ReadList (LM/MatchList.h:526-614) for two sequences -> (rows[n,3], seq_filenames, seq_lengths); the same format errors raise ValueError"""
+    tok = stream.read().split("\n")
+    head = [l for l in tok[:7]]
+    def field(line, tag):
+        parts = line.split("\t", 1)
+        if parts[0] != tag:
+            raise ValueError("InvalidFileFormat: expected %s, found %r" % (tag, parts[0]))
+        return parts[1] if len(parts) > 1 else ""
+    if len(head) < 7 or field(head[0], "FormatVersion").strip() != "3":
+        raise ValueError("InvalidFileFormat: FormatVersion 3 expected")
+    if int(field(head[1], "SequenceCount")) != 2:
+        raise ValueError("only two-sequence lists are handled here")
+    names = [field(head[2], "Sequence0File"), field(head[4], "Sequence1File")]
+    lens = [int(field(head[3], "Sequence0Length")), int(field(head[5], "Sequence1Length"))]
+    count = int(field(head[6], "MatchCount"))
+    rows = []
+    for line in tok[7:]:
+        if not line.strip():
+            continue
+        f = line.split()
+        if int(f[4]) > 0:
+            raise ValueError("Unable to read file, invalid format, cannot read subset data")
+        rows.append((int(f[0]), int(f[1]), int(f[2])))
+    if len(rows) != count:
+        raise ValueError("InvalidFileFormat: MatchCount %d but %d rows" % (count, len(rows)))
+    return np.array(rows, dtype=np.int64).reshape(-1, 3), names, lens
+
+
 def _find_mums(seq0, seq1, seed, rule):
     a0, n0, k0 = _buf(seq0)
     a1, n1, k1 = _buf(seq1)

@@ -137,6 +137,56 @@ long long ref_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_
 
 void ref_free(void* p) { free(p); }
 
+// ---- match list file format (LM/MatchList.h:526-662), as --mums writes and --match-input reads ----
+// WriteList of n rows -> malloc'd NUL-terminated text (free with ref_free); the match-id column is the pointer value.
+char* ref_write_list(const ref_match* rows, uint64_t n, const char* name0, const char* name1, uint64_t len0, uint64_t len1)
+{
+	try {
+		MatchList ml;
+		ml.seq_filename.push_back(name0);
+		ml.seq_filename.push_back(name1);
+		ml.seq_table.push_back(new gnSequence(string((size_t)len0, 'A')));
+		ml.seq_table.push_back(new gnSequence(string((size_t)len1, 'A')));
+		Match mm(2);
+		for (uint64_t i = 0; i < n; ++i) {
+			Match* m = mm.Copy();
+			m->SetStart(0, rows[i].start0);
+			m->SetStart(1, rows[i].start1);
+			m->SetLength(rows[i].len);
+			ml.push_back(m);
+		}
+		stringstream ss;
+		WriteList(ml, ss);
+		for (size_t i = 0; i < ml.size(); ++i) ml[i]->Free();
+		delete ml.seq_table[0]; delete ml.seq_table[1];
+		ml.seq_table.clear();
+		string t = ss.str();
+		char* out = (char*)malloc(t.size() + 1);
+		memcpy(out, t.c_str(), t.size() + 1);
+		return out;
+	} catch (...) { return NULL; }
+}
+
+// ReadList of a text -> rows (malloc'd, free with ref_free); returns the row count or -1 when the reference rejects the text
+long long ref_read_list(const char* text, ref_match** out)
+{
+	try {
+		MatchList ml;
+		stringstream ss(text);
+		ReadList(ml, ss);
+		size_t m = ml.size();
+		ref_match* r = (ref_match*)malloc(sizeof(ref_match) * (m ? m : 1));
+		for (size_t i = 0; i < m; ++i) {
+			r[i].len = (int64_t)ml[i]->Length();
+			r[i].start0 = ml[i]->Start(0);
+			r[i].start1 = ml[i]->Start(1);
+			ml[i]->Free();
+		}
+		*out = r;
+		return (long long)m;
+	} catch (...) { return -1; }
+}
+
 // ---- DP ------------------------------------------------------------------
 // Global settings exactly as MuscleInterface::ProfileAlignFast (LM/MuscleInterface.cpp:1086-1106).
 static void ref_dp_globals(unsigned nseq)

@@ -92,3 +92,44 @@ def test_gather_rows_gloo(world):
         n = 0 if (world == 3 and r == 1) else r * 3 + 1
         expect += (np.arange(n * 3).reshape(n, 3) + 1000 * r).tolist()
     assert got == expect
+
+
+def test_match_list_file_format_round_trips_through_the_reference(refc):
+    """--mums / --match-input text format (LM/MatchList.h:526-662): what we write, the reference's ReadList accepts with the
+    same rows; what the reference's WriteList prints, we read; both writers agree byte for byte except the match-id column."""
+    import ctypes as C
+    import io
+    import _oracle
+    import mauve_py_b200 as mp
+    lib = _oracle.ref()
+    lib.ref_write_list.restype = C.c_void_p
+    lib.ref_write_list.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint64]
+    lib.ref_read_list.restype = C.c_longlong
+    lib.ref_read_list.argtypes = [C.c_char_p, C.POINTER(C.POINTER(_oracle.Match3))]
+    rng = np.random.default_rng(3)
+    rows = np.stack([rng.integers(21, 5000, 500), rng.integers(1, 4_000_000, 500), rng.integers(1, 4_000_000, 500)], axis=1).astype(np.int64)
+    rows[::7, 2] *= -1  # reverse-strand matches carry a negative start
+    # ours -> reference
+    buf = io.StringIO()
+    mp.libmems.WriteList(rows, buf, ("a.fa", "dir with space/b.fa"), (4000000, 4100000))
+    out = C.POINTER(_oracle.Match3)()
+    n = lib.ref_read_list(buf.getvalue().encode(), C.byref(out))
+    assert n == rows.shape[0]
+    got = np.array([[out[i].len, out[i].s0, out[i].s1] for i in range(n)], dtype=np.int64)
+    lib.ref_free(out)
+    assert np.array_equal(got, rows)
+    # reference -> ours
+    arr = np.ascontiguousarray(rows)
+    txt_p = lib.ref_write_list(arr.ctypes.data, rows.shape[0], b"a.fa", b"dir with space/b.fa", 4000000, 4100000)
+    txt = C.string_at(txt_p).decode()
+    lib.ref_free(txt_p)
+    back, names, lens = mp.libmems.ReadList(io.StringIO(txt))
+    assert np.array_equal(back, rows) and names == ["a.fa", "dir with space/b.fa"] and lens == [4000000, 4100000]
+    strip = lambda t: ["\t".join(l.split("\t")[:3] + l.split("\t")[4:]) if l[:1].isdigit() or l[:1] == "-" else l for l in t.strip().split("\n")]
+    assert strip(txt) == strip(buf.getvalue())
+    # empty list: the reference writes nothing at all, and rejects an empty file
+    e = io.StringIO()
+    mp.libmems.WriteList(np.zeros((0, 3), dtype=np.int64), e)
+    assert e.getvalue() == "" and lib.ref_read_list(b"", C.byref(out)) == -1
+    with pytest.raises(ValueError):
+        mp.libmems.ReadList(io.StringIO("FormatVersion\t2\n"))
