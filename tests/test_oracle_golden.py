@@ -77,3 +77,43 @@ def test_hmm_small(orc):
         # the restatement performs the reference's bfloat operations (float32 mantissa) in the same order: bit-identical
         assert np.array_equal(post, ref_post), (i, np.max(np.abs(post - ref_post) / np.maximum(ref_post, 1e-300)))
         assert pred == z["pred%d" % i].tobytes()
+
+
+# ---- the full-size property checkers (tests/_properties.py) are validated here against oracle output ----
+@pytest.mark.parametrize("w,r,n", [(19, 3, 250000), (15, 3, 200000), (11, 0, 120000)])
+def test_property_checkers_accept_oracle_mums_and_reject_damage(orc, w, r, n):
+    import _properties as P
+    import mauve_py_b200 as mp
+    from mauve_py_b200 import synth
+    a, b = synth.small_pair(n, seed=70 + w, snp=0.02, n_inv=3)
+    seed = mp.getSeed(w, r)
+    L = mp.getSeedLength(seed)
+    rows, _ = orc.find_mums(a, b, seed, 0)
+    assert rows.shape[0] > 50 and (rows[:, 2] < 0).any()
+    assert P.check_mum_rows(a, b, rows, seed, L) == rows.shape[0]
+    for damage in ("shorten", "shift", "swap"):
+        bad = rows.copy()
+        k = rows.shape[0] // 2
+        if damage == "shorten":
+            bad[k, 0] -= 1       # no longer maximal
+        elif damage == "shift":
+            bad[k, 1] += 1       # end seeds are no hits (or order breaks)
+        else:
+            bad[[0, -1]] = bad[[-1, 0]]
+        with pytest.raises(AssertionError):
+            P.check_mum_rows(a, b, bad, seed, L)
+
+
+def test_property_checkers_nw_and_mers(orc):
+    import _properties as P
+    import mauve_py_b200 as mp
+    from mauve_py_b200 import synth
+    for x, y in synth.dp_pairs(25, 5, 600, seed=9) + [(b"A", b"ACGT"), (b"ACGTT", b"C"), (b"A", b"A"), (b"AC", b"A"), (b"AAAA", b"TTTTGGGG")]:
+        path, score = orc.nw_align(x, y)
+        assert P.nw_path_score(x, y, path) == score
+    a, _ = synth.small_pair(60000, seed=4)
+    for w, r in ((15, 3), (21, 0), (7, 0)):
+        seed = mp.getSeed(w, r)
+        L, wt = mp.getSeedLength(seed), mp.getSeedWeight(seed)
+        pos, mer = orc.sml_build(a, seed)
+        assert np.array_equal(P.canonical_mers(a, seed, L, wt, pos), mer)
