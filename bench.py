@@ -87,6 +87,81 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class NvmlSampler:
+    """SM clock + throttle reasons through NVML from a background thread (every ~2 ms): the timed region of this bench is tens of
+    milliseconds, far shorter than nvidia-smi's sampling period.  start() returns False when NVML is unusable (the caller then
+    falls back to the nvidia-smi sampler)."""
+
+    def __init__(self, torch_device_index):
+        self.idx = torch_device_index
+        self.samples = []
+        self._stop = False
+        self._thread = None
+        self._h = None
+        self._nv = None
+
+    def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:  # noqa: BLE001
+                h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                phys = self.idx
+                if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                    phys = int(vis.split(",")[self.idx])
+                h = nv.nvmlDeviceGetHandleByIndex(phys)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)  # probe
+            self._h, self._nv = h, nv
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+            return True
+        except Exception:  # noqa: BLE001
+            return False
+
+    def _run(self):
+        nv, h = self._nv, self._h
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(reasons(h))))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop = True
+        if self._thread is not None:
+            self._thread.join(1.0)
+        nv, h = self._nv, self._h
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            mx = None
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": ["no samples"], "source": "nvml"}
+        bits = 0
+        for _, r in self.samples:
+            bits |= r
+        names = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        return {"sm_mhz": float(np.median([c for c, _ in self.samples])), "sm_max_mhz": mx, "reasons": [n for n, b in names if bits & b],
+                "samples": len(self.samples), "source": "nvml"}
+
+
+def start_clock_sampler(gpu_index):
+    s = NvmlSampler(gpu_index)
+    if s.start():
+        return s
+    return ClockSampler(gpu_index)
+
+
 def pinned_copy(lib, arr):
     from mauve_py_b200._capi import check
     p = C.c_void_p()
@@ -277,7 +352,7 @@ def main():
     launches0 = sess.launch_count()
     stage = np.zeros(16, dtype=np.float64)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = start_clock_sampler(local) if rank == 0 else None
     t0 = time.perf_counter()
     nmatch = 0
     for _ in range(args.steps):
