@@ -80,8 +80,11 @@ int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed,
  *      -> GetMatchList (LM/MemHash.h:183-203).  Rows come back in the reference's list order.
  *      stats (optional, 8 x uint64): [0] seed pairs (unique in both genomes), [1] matches,
  *      [2] collisions = [0]-[1] (MemHash::MemCollisionCount), [3] 1 if some join run exceeds
- *      MER_REPEAT_LIMIT=1000 (the reference's skip-ahead branch, LM/MatchFinder.cpp:253-277,
- *      is not reproduced; such runs never produce seed pairs), [4] extension candidates,
+ *      MER_REPEAT_LIMIT=1000: the reference's skip-ahead branch (LM/MatchFinder.cpp:253-277) is not
+ *      reproduced.  The dropped run itself never produces seed pairs, but the reference resumes the other
+ *      genome's list mid-run (the `&&` at :117) and can then report a few spurious matches between repeat
+ *      copies whose identity depends on std::sort's tie order; they are left out,
+ *      [4] extension candidates,
  *      [5] sorted (key, position) entries, [6] hash buckets replayed in insertion order,
  *      [7] duplicate rows the replay added (the reference stores some matches twice).            */
 #define MCU_RULE_PAIRWISE 0
