@@ -3,12 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mbp 100]
 
-One "step" = one pass of seed + match + extend (pack -> seedgen -> radix sort -> join -> extend ->
-reference list order [-> NCCL gather + merge on rank 0 when N > 1]) over the synthetic 100 Mbp pair
+One "step" = one pass of seed + match + extend (pack -> two partition passes over 8-byte seed records -> in-bucket
+grouping -> candidates -> extension -> reference list order; at N > 1: NCCL all-reduce of the unique-seed bitmap before
+extension and NCCL gather + merge of the match rows on rank 0) over the synthetic 100 Mbp pair
 (BASELINE config 3, SURVEY.md 8d "C3"; the north_star target workload, it fits one GPU).  `value`
 is Mbp/s with both genomes already resident in HBM; `e2e` is the same metric through the public
 C-ABI call mcu_find_mums with pinned HOST buffers (H2D + D2H inside the timed region).  N > 1 shards
-the SAME pair by seed-key prefix ("strong" scaling).  The gapped DP (GCUPS) and the HMM are reported
+the SAME pair by a seed-ownership hash ("strong" scaling).  The gapped DP (GCUPS) and the HMM are reported
 in the `dp` / `hmm` objects of the same line.  Prints ONE JSON line on rank 0.
 """
 import argparse

@@ -108,9 +108,10 @@ int mcu_find_mums_batch(uint64_t n_pairs, const char* seq0, const uint64_t* off0
 
 /* ---- device-resident session (measurement + multi-GPU sharding) -------------------------
  * Same computation as mcu_find_mums, split so the timed region can start with both genomes
- * already in HBM.  shard_index/shard_count partition the seed-key space by canonical-key
- * prefix: each rank keeps only keys in its range; the per-rank match lists are
- * merged by mcu_merge_matches on rank 0.                                                    */
+ * already in HBM.  shard_index/shard_count partition the seeds among ranks by a
+ * hash of forward ^ reverse-complement mer, identical for a mer and its reverse complement: every
+ * rank keeps the seeds it owns; the per-rank match lists are merged on rank 0 (mcu_session_merge
+ * after the two-phase run below, or mcu_merge_matches for independently finished shards).   */
 typedef struct mcu_session mcu_session;
 int mcu_session_create(mcu_session** out);
 void mcu_session_destroy(mcu_session* s);
