@@ -227,7 +227,7 @@ def config_dict(args, weight, seed):
     return {"workload": "synthetic %g Mbp pair (BASELINE config 3 / SURVEY 8d C3: 0.9%% SNP, 0.1%% indel events, inversions, translocations), "
                         "default seed weight %d rank CODING_SEED -> pattern 0x%x" % (args.mbp, weight, seed),
             "genome_bp": int(args.mbp * 1e6), "seed_weight": weight, "seed_pattern": hex(seed),
-            "sharding": "seed-key slice per rank; NCCL all-reduce of the 1-bit/base unique-seed bitmap, NCCL gather of match rows to rank 0" if args.gpus > 1 else "none",
+            "sharding": "seed-ownership hash per rank; NCCL all-reduce of the 1-bit/base unique-seed bitmap, NCCL gather of match rows to rank 0" if args.gpus > 1 else "none",
             "l2": "inputs (2 x %g MB ASCII, %.1f GB of key/value pairs) exceed the 126 MB L2; no extra flush" % (args.mbp, 2 * args.mbp * 12e6 / 1e9)}
 
 

@@ -1,9 +1,10 @@
 """Multi-GPU plumbing of the anchoring path: one process per GPU, torch.distributed.
 
-Shards are slices of the (mixed) seed-key space.  Two exchanges exist on the data path, both tiny:
-(1) a SUM all-reduce of the unique-seed bitmaps (1 bit per genome-0 position; the slices' bits are
+Every seed belongs to one rank (a hash of forward ^ reverse-complement mer, csrc/common.cuh seed_owned).  Two exchanges exist
+on the data path, both tiny:
+(1) a SUM all-reduce of the unique-seed bitmaps (1 bit per genome-0 position; the ranks' bits are
 disjoint) between enumeration and extension, because a match is emitted by its leftmost unique
-seed wherever that seed's key hashes; (2) the gather of match rows to rank 0: an all_gather of the
+seed whichever rank owns that seed; (2) the gather of match rows to rank 0: an all_gather of the
 per-rank row counts followed by a variable-length gather of 24-byte rows.  NCCL over NVLink on the
 GPU box; gloo on CPU in the unit tests.
 """
