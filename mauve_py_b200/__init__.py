@@ -9,5 +9,6 @@ entry fails, without an sm_100 GPU every compute call raises McuError.
 from . import libmems  # noqa: F401
 from .libmems import *  # noqa: F401,F403
 from ._capi import LIB_PATH, SYMBOLS, McuError, lib  # noqa: F401
+from .buildindex import buildIndex  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,16 +1,12 @@
-// Minimal stand-in for boost/algorithm/string.hpp (replace_all, erase_all, to_lower/upper) (oracle build only).
+// TEST INFRASTRUCTURE ONLY: stand-in for boost/algorithm/string.hpp (replace_all + the erase / case headers).
 #pragma once
 #include <string>
-#include <cctype>
+#include "boost/algorithm/string/erase.hpp"
+#include "boost/algorithm/string/case_conv.hpp"
 namespace boost { namespace algorithm {
 inline void replace_all(std::string& s, const std::string& from, const std::string& to) {
   if (from.empty()) return;
   std::string::size_type p = 0;
   while ((p = s.find(from, p)) != std::string::npos) { s.replace(p, from.size(), to); p += to.size(); }
 }
-inline void erase_all(std::string& s, const std::string& what) { replace_all(s, what, ""); }
-inline void to_lower(std::string& s) { for (std::string::size_type i = 0; i < s.size(); ++i) s[i] = (char)std::tolower((unsigned char)s[i]); }
-inline void to_upper(std::string& s) { for (std::string::size_type i = 0; i < s.size(); ++i) s[i] = (char)std::toupper((unsigned char)s[i]); }
-}
-using algorithm::replace_all; using algorithm::erase_all; using algorithm::to_lower; using algorithm::to_upper;
-}
+} using algorithm::replace_all; }

@@ -1,0 +1,161 @@
+"""The outermost parity check: the int32 LUT of `mauve.buildIndex(mds42_recoded.fa, mds42_full.fa)`.
+
+tests/golden/mds42_lut.npz was minted by the reference's OWN buildIndex (its Python, its Cython helpers, its binary compiled in
+place: tests/golden/make_golden_lut.py).  CPU: the host-side mirror of the Python layer (mauve_py_b200/buildindex.py: XMFA parser,
+column walk, fixZeroIdx / fillGaps / smoothEdges) reproduces that LUT from the reference binary's XMFA.  GPU: the drop-in
+`mauve_py_b200.buildIndex`, whose initial anchors come from the device and enter the UNMODIFIED binary through --match-input,
+returns the same LUT."""
+import ast
+import gzip
+import hashlib
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+BINARY = os.path.join(REF_DIR, "progressiveMauve")
+
+needs_bin = pytest.mark.skipif(not os.path.exists(BINARY), reason="oracle/_ref/progressiveMauve not built (needs /root/reference at build time)")
+
+
+def _golden():
+    z = np.load(os.path.join(GOLDEN, "mds42_lut.npz"))
+    lut = np.cumsum(z["lut_diff"].astype(np.int64)).astype(np.int32)
+    return lut, ast.literal_eval(str(z["meta"]))
+
+
+def _fastas(tmp_path):
+    out = []
+    for name in ("mds42_recoded", "mds42_full"):
+        p = os.path.join(str(tmp_path), name + ".fa")
+        with gzip.open(os.path.join(GOLDEN, name + ".fa.gz"), "rb") as f, open(p, "wb") as g:
+            shutil.copyfileobj(f, g)
+        out.append(p)
+    return out
+
+
+def test_golden_lut_is_self_consistent():
+    lut, meta = _golden()
+    assert lut.size == meta["length"] == 3981477 and int((lut >= 0).sum()) == meta["mapped"]
+    assert hashlib.sha1(lut.tobytes()).hexdigest() == meta["lut_sha1"]
+
+
+def test_cli_match_list_equals_the_golden_list():
+    """the list `progressiveMauve --mums` wrote during the LUT run (sha1 in the LUT fixture) is the 29,403-row golden list the oracle
+    and the CUDA path are held to (tests/golden/mums_mds42.npz, minted through the library-level driver)"""
+    import _golden as G
+    _, meta = _golden()
+    rows = G.npz("mums_mds42.npz")["rows_w15_r3"]
+    text = b"\n".join(b"\t".join(str(int(v)).encode() for v in r) for r in rows)
+    assert rows.shape[0] == meta["mums_rows"] == 29403 and hashlib.sha1(text).hexdigest() == meta["mums_sha1"]
+
+
+def test_lut_healing_on_crafted_tables():
+    """fillGaps / smoothEdges against a literal transcription of the reference loops (mauve/indexutils.pyx:46-108)"""
+    from mauve_py_b200 import buildindex as B
+
+    def ref_fill(v, width):
+        v = v.copy()
+        for idx in range(1, len(v)):
+            if v[idx] == -1 and v[idx - 1] != -1:
+                for up in range(idx + 1, len(v)):
+                    if up - idx > width:
+                        break
+                    if v[up] - v[idx - 1] == up - (idx - 1):
+                        v[idx - 1:up + 1] = np.arange(v[idx - 1], v[up] + 1)
+                        break
+        return v
+
+    def ref_smooth(v, radius):
+        v = v.copy()
+        for idx in range(1, len(v)):
+            if v[idx] != v[idx - 1] + 1 and v[idx - 1] != -1:
+                for up in range(idx + 1, len(v)):
+                    if up - idx > radius:
+                        break
+                    if v[up] - v[idx - 1] == up - (idx - 1):
+                        v[idx - 1:up + 1] = np.arange(v[idx - 1], v[up] + 1)
+                        break
+        return v
+
+    rng = np.random.default_rng(11)
+    for trial in range(200):
+        n = int(rng.integers(5, 400))
+        v = np.arange(n, dtype=np.int32) + int(rng.integers(0, 50))
+        for _ in range(int(rng.integers(0, 12))):      # holes, jumps and noise
+            i = int(rng.integers(0, n))
+            j = min(n, i + int(rng.integers(1, 30)))
+            kind = rng.integers(0, 3)
+            if kind == 0:
+                v[i:j] = -1
+            elif kind == 1:
+                v[i:] += int(rng.integers(1, 40))
+            else:
+                v[i:j] = rng.integers(0, 500, j - i)
+        for width in (3, 20, 300):
+            a = v.copy()
+            B.fillGaps(a, width)
+            assert np.array_equal(a, ref_fill(v, width)), (trial, width)
+            b = v.copy()
+            B.smoothEdges(b, width)
+            assert np.array_equal(b, ref_smooth(v, width)), (trial, width)
+
+
+@needs_bin
+def test_python_layer_reproduces_the_reference_lut(tmp_path):
+    """reference binary -> XMFA -> our parser + walk + healing == the LUT the reference's own Python produced"""
+    from mauve_py_b200 import buildindex as B
+    lut, meta = _golden()
+    fas = _fastas(tmp_path)
+    subprocess.check_call([BINARY, "--output=mds42.xmfa", os.path.basename(fas[0]), os.path.basename(fas[1])], cwd=str(tmp_path),
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    xmfa = os.path.join(str(tmp_path), "mds42.xmfa")
+    body = b"".join(b" ".join(l.split()[:3]) + b"\n" if l.startswith(b">") else l for l in open(xmfa, "rb") if not l.startswith(b"#"))
+    assert hashlib.sha1(body).hexdigest() == meta["xmfa_body_sha1"]
+    got = B.lut_from_xmfa(xmfa, B.getSeqFromFile(fas[0]), B.getSeqFromFile(fas[1]))
+    assert got.dtype == np.int32 and np.array_equal(got, lut)
+
+
+@needs_bin
+def test_buildindex_flow_with_the_oracle_list(tmp_path, monkeypatch, orc):
+    """everything of buildIndex() except the device call, on the CPU: with the match list the oracle computes (= the list the GPU
+    returns, tests/test_gpu_parity.py::test_mums_mds42) handed to the unmodified binary through --match-input, the LUT is the
+    reference's.  The product itself never falls back like this: the substitution is made here, by the test."""
+    from mauve_py_b200 import buildindex as B
+    lut, meta = _golden()
+    fas = _fastas(tmp_path)
+    bindir = os.path.join(str(tmp_path), "bin")
+    os.makedirs(bindir)
+    os.symlink(BINARY, os.path.join(bindir, "progressiveMauveStatic"))
+    monkeypatch.setenv("MAUVE_DIR", bindir)
+    monkeypatch.setattr(B.libmems, "find_mums", lambda a, b, seed, rule=0: orc.find_mums(a, b, seed, rule))
+    got = B.buildIndex(fas[0], fas[1])
+    assert np.array_equal(got, lut)
+    assert not os.path.exists(fas[0] + ".sslist") and not os.path.exists(fas[1] + ".sslist")
+    monkeypatch.delenv("MAUVE_DIR")
+    with pytest.raises(IOError):
+        B.buildIndex(fas[0], fas[1])
+
+
+@needs_bin
+@pytest.mark.gpu
+def test_buildindex_dropin_mds42(tmp_path, monkeypatch):
+    """BASELINE config 1 / north_star target: bit-exact MDS42 buildIndex LUT with the anchoring stage on the GPU"""
+    import mauve_py_b200 as mp
+    from mauve_py_b200._capi import check
+    check(mp.lib().mcu_init(0))
+    lut, meta = _golden()
+    fas = _fastas(tmp_path)
+    bindir = os.path.join(str(tmp_path), "bin")
+    os.makedirs(bindir)
+    os.symlink(BINARY, os.path.join(bindir, "progressiveMauveStatic"))
+    monkeypatch.setenv("MAUVE_DIR", bindir)
+    got = mp.buildIndex(fas[0], fas[1])
+    assert got.dtype == np.int32 and got.shape == lut.shape
+    assert np.array_equal(got, lut)
+    assert not os.path.exists(fas[0] + ".sslist")   # cleaned up like the reference does
