@@ -6,8 +6,9 @@ The reference runs `progressiveMauveStatic a.fa b.fa --output x.xmfa`, parses th
 the 0-based index of the identical aligned base of genome B (or -1), then heals the table (fixZeroIdx, fillGaps, smoothEdges of
 mauve/indexutils.pyx:27-108).  Here the initial seed + match + extend pass -- `PairwiseMatchFinder::FindMatches` on two
 `DNAFileSML`s, MA/progressiveMauve.cpp:446-503 -- runs on the device (mcu_find_mums) and the UNMODIFIED binary is started with
-`--match-input` (MA/progressiveMauve.cpp:472-491 -> ReadList, LM/MatchList.h:526-614), so it skips its own match finding and
-continues with the list it is given; everything after that (LCBs, recursive anchoring, gapped alignment, backbone, XMFA writer)
+`--match-input` (MA/progressiveMauve.cpp:472-491 -> ReadList, LM/MatchList.h:526-614) and finds the two `<fasta>.sslist` sorted mer
+lists already written from the device's lists, so it skips its own SML construction and match finding and continues with what
+it is given; everything after that (LCBs, recursive anchoring, gapped alignment, backbone, XMFA writer)
 is the reference's code.  The LUT is bit-identical to `mauve.buildIndex` (tests/golden/mds42_lut.npz was minted by the reference's
 own buildIndex, tests/golden/make_golden_lut.py).
 
@@ -186,7 +187,15 @@ def buildIndex(genome_fp, ref_genome_fp, genome_seq=None, ref_genome_seq=None, f
     ref_genome_seq = ref_genome_seq or getSeqFromFile(ref_genome_fp)
     # initial anchors on the device: default seed weight from the average length, coding pattern (LM/MatchList.h:265-280)
     weight = libmems.getDefaultSeedWeight((len(genome_seq) + len(ref_genome_seq)) // 2)
-    rows, _ = libmems.find_mums(genome_seq.encode("ascii"), ref_genome_seq.encode("ascii"), libmems.getSeed(weight, libmems.CODING_SEED))
+    seed = libmems.getSeed(weight, libmems.CODING_SEED)
+    seqs = (genome_seq.encode("ascii"), ref_genome_seq.encode("ascii"))
+    rows, _ = libmems.find_mums(seqs[0], seqs[1], seed)
+    # the sorted mer lists the binary would build next to the FASTA files (DNAFileSML::Create, LM/FileSML.cpp:401-459): written from
+    # the device's lists, MatchList::LoadSMLs loads them instead (LM/MatchList.h:296-330); runMauve removes them afterwards
+    for fp, seq in zip((genome_fp, ref_genome_fp), seqs):
+        sml = libmems.DNAMemorySML()
+        sml.Create(seq, seed)
+        sml.WriteFile(fp + ".sslist")
     work = tempfile.mkdtemp()
     try:
         flags = {"--output": os.path.join(work, "mauveout.xmfa")}

@@ -123,6 +123,10 @@ class DNAMemorySML:
     def positions(self):
         return self._pos
 
+    def WriteFile(self, path):
+        """leave this list on disk as `path` (normally <fasta>.sslist) in DNAFileSML's format"""
+        write_sslist(path, self._length, self._seed, self._packed, self._pos)
+
     def mers(self):
         return self._mer
 
@@ -183,6 +187,37 @@ class MatchList:
     def as_array(self):
         """rows (length, start0, start1) in list order -- the three leading columns of WriteList (LM/MatchList.h:617-662)"""
         return np.array([[m.length, m.starts[0], m.starts[1]] for m in self.matches], dtype=np.int64).reshape(-1, 3)
+
+
+SML_FORMAT_VERSION = 5            # DNAFileSML::FormatVersion, LM/DNAFileSML.h:59-62
+SML_HEADER_BYTES = 2352           # sizeof(struct SMLHeader), LM/SortedMerList.h:48-63, with the C alignment rules of x86-64
+
+
+def write_sslist(path, seq_length, seed, packed, positions):
+    """The on-disk sorted mer list `<fasta>.sslist` that DNAFileSML::Create leaves (LM/FileSML.cpp:401-459) and FileSML::LoadFile2
+    reads back (:120-195): SMLHeader, the 2-bit sequence (ceil(2n/32) + 2 words), the uint32 positions in sorted order.  A list
+    written here is picked up by the unmodified binary instead of being rebuilt (MatchList::LoadSMLs, LM/MatchList.h:296-330:
+    format version and seed pattern must match).  Header fields the reference leaves uninitialised (word size, byte-order flag,
+    description: they hold stray heap bytes in its files and are never read) are written as defined values."""
+    packed = np.ascontiguousarray(packed, dtype=np.uint32)
+    positions = np.ascontiguousarray(positions, dtype=np.uint32)
+    L = getSeedLength(seed)
+    words = (2 * seq_length) // 32 + (1 if (2 * seq_length) % 32 else 0) + 2
+    if packed.size != words or positions.size != max(seq_length - L + 1, 0):
+        raise ValueError("write_sslist: array sizes do not match a sequence of %d bases" % seq_length)
+    h = np.zeros(SML_HEADER_BYTES, dtype=np.uint8)
+    import struct
+    struct.pack_into("<IIQIIQII", h, 0, SML_FORMAT_VERSION, 2, seed, L, getSeedWeight(seed), seq_length, 0xFFFFFFFF, 32)
+    h[40] = 1  # little_endian; id (int16 at 42) and circular (44) stay 0
+    table = np.zeros(255, dtype=np.uint8)  # SortedMerList::BasicDNATable, LM/SortedMerList.cpp:29-47
+    for letters, code in (("cCbByY", 1), ("gGsSkK", 2), ("tT", 3)):
+        for ch in letters:
+            table[ord(ch)] = code
+    h[45:300] = table
+    with open(path, "wb") as f:
+        f.write(h.tobytes())
+        f.write(packed.tobytes())
+        f.write(positions.tobytes())
 
 
 def WriteList(rows, stream, seq_filenames=("null", "null"), seq_lengths=(0, 0)):

@@ -134,6 +134,20 @@ def test_buildindex_flow_with_the_oracle_list(tmp_path, monkeypatch, orc):
     os.symlink(BINARY, os.path.join(bindir, "progressiveMauveStatic"))
     monkeypatch.setenv("MAUVE_DIR", bindir)
     monkeypatch.setattr(B.libmems, "find_mums", lambda a, b, seed, rule=0: orc.find_mums(a, b, seed, rule))
+    import _oracle
+    olib = _oracle.oracle()
+
+    class OracleSML:   # stands in for the device-built DNAMemorySML: same positions (ties position-ascending), same packed sequence
+        def Create(self, seq, seed):
+            self.n, self.seed = len(seq), seed
+            self.pos, _ = orc.sml_build(seq, seed)
+            self.packed = np.zeros(int(olib.orc_packed_words(len(seq))), dtype=np.uint32)
+            olib.orc_pack(seq, len(seq), self.packed.ctypes.data)
+
+        def WriteFile(self, path):
+            B.libmems.write_sslist(path, self.n, self.seed, self.packed, self.pos)
+
+    monkeypatch.setattr(B.libmems, "DNAMemorySML", OracleSML)
     got = B.buildIndex(fas[0], fas[1])
     assert np.array_equal(got, lut)
     assert not os.path.exists(fas[0] + ".sslist") and not os.path.exists(fas[1] + ".sslist")
@@ -159,3 +173,51 @@ def test_buildindex_dropin_mds42(tmp_path, monkeypatch):
     assert got.dtype == np.int32 and got.shape == lut.shape
     assert np.array_equal(got, lut)
     assert not os.path.exists(fas[0] + ".sslist")   # cleaned up like the reference does
+
+
+@needs_bin
+def test_sslist_files_are_loaded_by_the_unmodified_binary(tmp_path, orc):
+    """a `<fasta>.sslist` written by mauve_py_b200.libmems.write_sslist (here from the oracle's sorted mer list,
+    whose tie order -- position-ascending, like the device's -- differs from the reference's std::sort) is accepted by
+    MatchList::LoadSMLs instead of being rebuilt, and the alignment that follows is byte-identical: no consumer depends on the
+    order inside equal-mer runs."""
+    import ctypes as C
+    import _oracle
+    import mauve_py_b200 as mp
+    from mauve_py_b200 import synth
+    a, b = synth.small_pair(150000, seed=21, snp=0.02, n_inv=2)
+    d = str(tmp_path)
+    for name, s in (("a", a), ("b", b)):
+        with open(os.path.join(d, name + ".fa"), "wb") as f:
+            f.write(b">" + name.encode() + b"\n" + b"\n".join(s[i:i + 80] for i in range(0, len(s), 80)) + b"\n")
+
+    def run(tag):
+        r = subprocess.run([BINARY, "--output=%s.xmfa" % tag, "a.fa", "b.fa"], cwd=d, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-300:]
+        body = b"".join(l for l in open(os.path.join(d, tag + ".xmfa"), "rb") if not l.startswith(b"#"))
+        return r.stdout, body
+
+    log0, plain = run("plain")
+    assert "Creating sorted mer list" in log0
+    ref_files = {n: open(os.path.join(d, n + ".fa.sslist"), "rb").read() for n in ("a", "b")}
+    seed = mp.getSeed(mp.getDefaultSeedWeight((len(a) + len(b)) // 2), mp.CODING_SEED)
+    lib = _oracle.oracle()
+    for name, s in (("a", a), ("b", b)):
+        os.remove(os.path.join(d, name + ".fa.sslist"))
+        pos, mer = orc.sml_build(s, seed)
+        packed = np.zeros(int(lib.orc_packed_words(len(s))), dtype=np.uint32)
+        lib.orc_pack(s, len(s), packed.ctypes.data)
+        mp.libmems.write_sslist(os.path.join(d, name + ".fa.sslist"), len(s), seed, packed, pos)
+        ours = open(os.path.join(d, name + ".fa.sslist"), "rb").read()
+        theirs = ref_files[name]
+        H = mp.libmems.SML_HEADER_BYTES
+        assert len(ours) == len(theirs) and ours[:36] == theirs[:36]            # version .. unique_mers
+        assert ours[44:300] == theirs[44:300]                                   # circular flag + translation table
+        nseq = packed.size * 4
+        core = ((2 * len(s) + 31) // 32) * 4                                    # the reference leaves its two pad words uninitialised
+        assert ours[H:H + core] == theirs[H:H + core]                           # the 2-bit sequence
+        mine, ref_pos = np.frombuffer(ours[H + nseq:], dtype=np.uint32), np.frombuffer(theirs[H + nseq:], dtype=np.uint32)
+        assert np.array_equal(np.sort(mine), np.sort(ref_pos)) and not np.array_equal(mine, ref_pos)   # same list up to tie order
+    log1, loaded = run("loaded")
+    assert "Sorted mer list loaded successfully" in log1 and "Creating sorted mer list" not in log1
+    assert loaded == plain
