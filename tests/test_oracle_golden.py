@@ -117,3 +117,20 @@ def test_property_checkers_nw_and_mers(orc):
         L, wt = mp.getSeedLength(seed), mp.getSeedWeight(seed)
         pos, mer = orc.sml_build(a, seed)
         assert np.array_equal(P.canonical_mers(a, seed, L, wt, pos), mer)
+
+
+def _real_dp_calls():
+    import ast
+    z = _golden.npz("dp_mds42_calls.npz")
+    split = lambda k: z[k].tobytes().split(b"\n")
+    return list(zip(split("a"), split("b"), split("path"))), ast.literal_eval(str(z["meta"]))
+
+
+def test_nw_real_pipeline_calls(orc):
+    """gapped-DP calls recorded from the reference binary aligning the MDS42 pair (tests/golden/make_golden_dp.py): all 61,773
+    GlobalAlign calls of that run are of the single-sequence ACGT form; on the committed sample the restatement returns the
+    reference's path"""
+    calls, meta = _real_dp_calls()
+    assert meta["calls"] == meta["single_sequence_acgt_calls"] == 61773 and len(calls) >= 1300
+    for a, b, p in calls:
+        assert orc.nw_align(a, b)[0] == p

@@ -8,6 +8,7 @@ size-independent properties of tests/_properties.py, whose checkers are validate
 import numpy as np
 import pytest
 
+import _golden
 import _properties as P
 from mauve_py_b200 import synth
 
@@ -96,3 +97,16 @@ def test_config5_dp_batch_properties(mp):
     for k, (x, y) in enumerate(pairs):
         edges = path[int(off[k]):int(off[k]) + int(plen[k])].tobytes()
         assert P.nw_path_score(x, y, edges) == int(score[k]), k
+
+
+def test_nw_real_pipeline_calls(mp):
+    """the gapped-DP calls the reference binary really makes while aligning the MDS42 pair (recorded with a link-time tap on
+    muscle::GlobalAlign, tests/golden/make_golden_dp.py): one batch, every path equal to the one NWSmall + BitTraceBack returned"""
+    import ast
+    z = _golden.npz("dp_mds42_calls.npz")
+    a, b, want = (z[k].tobytes().split(b"\n") for k in ("a", "b", "path"))
+    meta = ast.literal_eval(str(z["meta"]))
+    assert meta["calls"] == meta["single_sequence_acgt_calls"] and len(a) >= 1300
+    got = mp.GlobalAlignBatch(list(zip(a, b)))
+    for g, w in zip(got, want):
+        assert g.edges == w
