@@ -1,7 +1,7 @@
 """Mints tests/golden/dp_mds42_calls.npz: gapped-DP inputs and paths from the REAL pipeline.
 
-oracle/_ref/progressiveMauve_dptrace is the unmodified reference binary with a link-time tap on muscle::GlobalAlign
-(oracle/trace_globalalign.cpp).  Aligning the MDS42 pair with it records every GlobalAlign call: the two profiles (as letter
+oracle/_ref/progressiveMauve_trace is the unmodified reference binary with a link-time tap on muscle::GlobalAlign
+(oracle/trace_taps.cpp).  Aligning the MDS42 pair with it records every GlobalAlign call: the two profiles (as letter
 strings when every column is one ungapped ACGT letter) and the path NWSmall + BitTraceBack returned.  The fixture keeps the 200
 largest calls and 1,300 random ones, plus the statistics of the whole run (they describe the DP workload buildIndex really
 generates: DESIGN.md section 5).
@@ -18,7 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-BINARY = os.path.join(ROOT, "oracle", "_ref", "progressiveMauve_dptrace")
+BINARY = os.path.join(ROOT, "oracle", "_ref", "progressiveMauve_trace")
 
 
 def main():

@@ -134,3 +134,33 @@ def test_nw_real_pipeline_calls(orc):
     assert meta["calls"] == meta["single_sequence_acgt_calls"] == 61773 and len(calls) >= 1300
     for a, b, p in calls:
         assert orc.nw_align(a, b)[0] == p
+
+
+def _real_gap_calls():
+    import ast
+    z = _golden.npz("gaps_mds42_calls.npz")
+    s0, s1 = z["seq0"].tobytes().split(b"\n"), z["seq1"].tobytes().split(b"\n")
+    bounds = np.concatenate(([0], np.cumsum(z["counts"])))
+    rows = [z["rows"][bounds[i]:bounds[i + 1]] for i in range(len(s0))]
+    return s0, s1, z["seeds"], rows, ast.literal_eval(str(z["meta"]))
+
+
+def test_gap_searches_of_the_real_pipeline(orc):
+    """the 371 MemHash::FindMatches calls recursive anchoring makes while the reference aligns the MDS42 pair (recorded with a
+    link-time tap, tests/golden/make_golden_taps.py): same rows, same order"""
+    s0, s1, seeds, rows, meta = _real_gap_calls()
+    assert len(s0) == meta["gap_searches"] == 371 and sum(r.shape[0] for r in rows) == meta["matches"]
+    for a, b, seed, want in zip(s0, s1, seeds, rows):
+        got, _ = orc.find_mums(a, b, int(seed), 1)
+        assert np.array_equal(got, want.reshape(-1, 3))
+
+
+def test_hmm_call_of_the_real_pipeline(orc):
+    """the backbone stage makes ONE run() call for the MDS42 pair, on a 3,983,034-column string; its first million columns with
+    the prediction of the reference's run(): the restatement's calls are identical"""
+    import ast
+    z = _golden.npz("hmm_mds42_call.npz")
+    meta = ast.literal_eval(str(z["meta"]))
+    assert meta["run_calls"] == 1 and meta["columns_per_call"] == [3983034]
+    pred, post = orc.hmm_run(z["sym"].tobytes(), z["params"])
+    assert pred == z["pred"].tobytes() and pred.count(b"H") == meta["prefix_homologous"]

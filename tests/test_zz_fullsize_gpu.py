@@ -110,3 +110,26 @@ def test_nw_real_pipeline_calls(mp):
     got = mp.GlobalAlignBatch(list(zip(a, b)))
     for g, w in zip(got, want):
         assert g.edges == w
+
+
+def test_gap_searches_of_the_real_pipeline(mp):
+    """the 371 gap searches of the reference's MDS42 run in ONE mcu_find_mums_batch call, with the seeds the reference chose: every
+    gap gets the rows MemHash returned (fixture: tests/golden/make_golden_taps.py)"""
+    z = _golden.npz("gaps_mds42_calls.npz")
+    s0, s1 = z["seq0"].tobytes().split(b"\n"), z["seq1"].tobytes().split(b"\n")
+    bounds = np.concatenate(([0], np.cumsum(z["counts"])))
+    res, stats = mp.libmems.find_mums_batch(list(zip(s0, s1)), seeds=[int(x) for x in z["seeds"]])
+    assert len(res) == 371 and int(stats[1]) == int(z["counts"].sum())
+    for i, rows in enumerate(res):
+        assert np.array_equal(rows, z["rows"][bounds[i]:bounds[i + 1]].reshape(-1, 3)), i
+    # and the seeds are the ones the adapter derives: getSeed(getDefaultSeedWeight((len0 + len1) / 2), 0)
+    for a, b, seed in zip(s0, s1, z["seeds"]):
+        assert mp.getSeed(mp.getDefaultSeedWeight((len(a) + len(b)) // 2), 0) == int(seed)
+
+
+def test_hmm_call_of_the_real_pipeline(mp):
+    """first million columns of the one genome-sized column string the reference's backbone stage scores for the MDS42 pair:
+    H/N calls identical to run()'s"""
+    z = _golden.npz("hmm_mds42_call.npz")
+    pred = mp.run(z["sym"].tobytes(), z["params"])
+    assert pred == z["pred"].tobytes()
