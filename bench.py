@@ -435,6 +435,7 @@ def main():
                 other[name] = {"bytes_per_launch": nbytes, "launch_ms": ms, "achieved": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
     else:
         passes = int(sess.stage_ms[7])
+        traffic = None  # the capture under profiles/ describes bk_group
         kname = "rs_onesweep_kernel (one 8-bit LSD radix pass over %d key/value pairs)" % nsorted
         bytes_per_launch = 2.0 * (kb + 4) * nsorted
         per_launch_ms = float(stage[2]) / max(passes, 1)
