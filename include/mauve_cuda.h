@@ -182,6 +182,27 @@ int mcu_hmm_params(double gc_content, double go_homologous, double go_unrelated,
 int mcu_hmm_batch(uint64_t n, const char* sym, const uint64_t* off, const double* params,
                   char* pred_out, double* post_out, float* device_ms);
 
+/* ---- seed occurrence list: replaces mems::SeedOccurrenceList::construct
+ *      (LM/SeedOccurrenceList.h:22-78, smoothFrequencies :103-119), called once per genome on the match finder's sorted mer
+ *      list (LM/ProgressiveAligner.cpp:3908-3912).  freq_out[n]: what getFrequency(position) returns (:81-84): the
+ *      multiplicity of the seed starting at each position (1 for the last L-1 positions), averaged over the L seeds that
+ *      start at position-L+1 .. position; the last position keeps its raw count.  Bit-identical floats.
+ *      n < L (no seed at all): the reference reads an uninitialised count; all ones here.                          */
+int mcu_sol_build(const char* seq, uint64_t n, uint64_t seed, float* freq_out);
+
+/* ---- anchor scores: replaces mems::GetPairwiseAnchorScore (LM/GreedyBreakpointElimination.h:403-476, penalize_gaps = false:
+ *      the form LM/ProgressiveAligner.cpp:1825 and :3422 call) for the LCBs of one genome pair made of ungapped matches.
+ *      rows[n_rows]: matches (1-based starts, negative = reverse strand); LCB l owns rows [lcb_off[l], lcb_off[l+1]).
+ *      freq0/freq1: the genomes' seed occurrence lists from mcu_sol_build (n0 / n1 floats); NULL = built here from `seed`.
+ *      matrix: 16 x int32 substitution scores [A,C,G,T][A,C,G,T] (NULL = hoxd_matrix, LM/SubstitutionMatrix.h:23-33).
+ *      penalize_repeats: the reference's global of that name (LM/GreedyBreakpointElimination.cpp:37, default false).
+ *      Outputs: lcb_score_out[n_lcb] (the function's return value per LCB), match_score_out[n_rows] (optional: m_score of
+ *      every match, an integer).  Sequence bytes outside the IUPAC DNA alphabet in reverse-strand rows are not supported
+ *      (gnFilter::ReverseFilter deletes them, which shifts the reference's columns).                                  */
+int mcu_anchor_scores(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, const float* freq0, const float* freq1,
+                      const mcu_match* rows, uint64_t n_rows, const uint64_t* lcb_off, uint64_t n_lcb, const int32_t* matrix,
+                      int penalize_repeats, double* lcb_score_out, int64_t* match_score_out);
+
 /* ---- test hooks (exercise single kernels through the ABI) -------------------------------- */
 /* stable LSD radix sort of (key,val) pairs on the low `bits` bits; key_bytes is 4 or 8 */
 int mcu_test_sort_pairs(void* keys, uint32_t* vals, uint64_t n, int key_bytes, int bits);

@@ -24,7 +24,8 @@ SYMBOLS = [
     "mcu_session_enumerate", "mcu_session_uniq_bitmap", "mcu_session_finish", "mcu_session_merge",
     "mcu_session_match_count", "mcu_session_download", "mcu_session_matches_device",
     "mcu_session_launch_count", "mcu_merge_matches",
-    "mcu_nw_batch", "mcu_nw_last_stats", "mcu_hmm_params", "mcu_hmm_batch", "mcu_test_sort_pairs",
+    "mcu_nw_batch", "mcu_nw_last_stats", "mcu_hmm_params", "mcu_hmm_batch", "mcu_sol_build", "mcu_anchor_scores",
+    "mcu_test_sort_pairs",
 ]
 
 
@@ -90,6 +91,8 @@ def lib():
     L.mcu_nw_last_stats.restype = None
     L.mcu_hmm_params.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, vp]
     L.mcu_hmm_batch.argtypes = [u64, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
+    L.mcu_sol_build.argtypes = [vp, u64, u64, vp]
+    L.mcu_anchor_scores.argtypes = [vp, u64, vp, u64, u64, vp, vp, vp, u64, vp, u64, vp, i32, vp, vp]
     L.mcu_test_sort_pairs.argtypes = [vp, vp, u64, i32, i32]
     _lib = L
     return L

@@ -502,7 +502,8 @@ void session_destroy(Session& s)
                       &s.matches, &s.ord_primary, &s.counters, &s.radix.hist, &s.radix.status, &s.radix.counters,
                       &s.rp_ctr, &s.rp_bitmap, &s.rp_list, &s.rp_canon, &s.rp_keys_b, &s.rp_idx_a, &s.rp_idx_b, &s.rp_p0, &s.rp_row, &s.rp_bkeys,
                       &s.rp_pool, &s.rp_extra, &s.rp_prefix, &s.rp_vinfo, &s.rp_out,
-                      &s.bk_a, &s.bk_b, &s.bk_tab1, &s.bk_tab2, &s.bk_spill, &s.bk_tileseg, &s.bt_tab, &s.bt_seg_a, &s.bt_seg_b};
+                      &s.bk_a, &s.bk_b, &s.bk_tab1, &s.bk_tab2, &s.bk_spill, &s.bk_tileseg, &s.bt_tab, &s.bt_seg_a, &s.bt_seg_b,
+                      &s.sol_raw, &s.sol_freq[0], &s.sol_freq[1], &s.as_rows, &s.as_match, &s.as_off, &s.as_lcb};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(s.ev[i]);
     for (int i = 0; i < 12; ++i) cudaEventDestroy(s.kev[i]);
@@ -812,6 +813,10 @@ static int sml_build_t(Session& s, const SeedParams& sp, u32* pos_out, u64* mer_
     if (((u32*)(s.h_counters + 4))[0]) { set_error("gap character '-' in a genome sequence (input must be unaligned)"); return MCU_EGAP; }
     const K* skeys = in_a ? s.keys_a.as<K>() : s.keys_b.as<K>();
     const u32* svals = in_a ? s.vals_a.as<u32>() : s.vals_b.as<u32>();
+    s.sml_keys = skeys;  // consumers of the sorted list on the device (sol.cu)
+    s.sml_vals = svals;
+    s.sml_npos = npos;
+    s.sml_key_bytes = (int)sizeof(K);
     if (pos_out && npos) MCU_CUDA(cudaMemcpyAsync(pos_out, svals, npos * sizeof(u32), cudaMemcpyDeviceToHost, s.stream));
     if (mer_out && npos) {
         u64* mers = in_a ? s.keys_b.as<u64>() : s.keys_a.as<u64>();  // the buffer not holding the result

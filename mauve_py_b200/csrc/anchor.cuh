@@ -25,6 +25,12 @@ struct Session {
     DevBuf rp_ctr, rp_bitmap, rp_list, rp_canon, rp_keys_b, rp_idx_a, rp_idx_b, rp_p0, rp_row, rp_bkeys, rp_pool, rp_extra, rp_prefix, rp_vinfo, rp_out;
     unsigned long long* h_replay = nullptr;  // pinned, 8 entries
     RadixScratch radix;
+    // where the last single-genome sorted list lies (set by sml_build_device) + seed occurrence list / anchor scores (sol.cu)
+    const void* sml_keys = nullptr;
+    const u32* sml_vals = nullptr;
+    u64 sml_npos = 0;
+    int sml_key_bytes = 0;
+    DevBuf sol_raw, sol_freq[2], as_rows, as_match, as_off, as_lcb;
     u64 n[2] = {0, 0};
     u64 match_count = 0;
     u64 launches = 0;

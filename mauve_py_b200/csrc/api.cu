@@ -11,6 +11,7 @@
 #include "anchor.cuh"
 #include "dp.cuh"
 #include "hmm.cuh"
+#include "sol.cuh"
 
 namespace mcu {
 
@@ -465,6 +466,33 @@ int mcu_hmm_batch(uint64_t n, const char* sym, const uint64_t* off, const double
     std::lock_guard<std::mutex> lk(g_mu);
     MCU_TRY(ensure_device());
     return hmm_batch(n, sym, off, params, pred_out, post_out, device_ms);
+}
+
+// ---- seed occurrence list + anchor scores (sol.cu) ------------------------------------------------
+int mcu_sol_build(const char* seq, uint64_t n, uint64_t seed, float* freq_out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    if (n && (!seq || !freq_out)) { set_error("mcu_sol_build: NULL pointer"); return MCU_EINVAL; }
+    Session* s;
+    MCU_TRY(default_session(&s));
+    return sol_build(*s, seq, n, seed, freq_out);
+}
+
+int mcu_anchor_scores(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, const float* freq0, const float* freq1,
+                      const mcu_match* rows, uint64_t n_rows, const uint64_t* lcb_off, uint64_t n_lcb, const int32_t* matrix,
+                      int penalize_repeats, double* lcb_score_out, int64_t* match_score_out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    if ((n0 && !seq0) || (n1 && !seq1) || (n_rows && !rows) || (n_lcb && (!lcb_off || !lcb_score_out))) {
+        set_error("mcu_anchor_scores: NULL pointer");
+        return MCU_EINVAL;
+    }
+    Session* s;
+    MCU_TRY(default_session(&s));
+    return anchor_scores(*s, seq0, n0, seq1, n1, seed, freq0, freq1, rows, n_rows, lcb_off, n_lcb, matrix, penalize_repeats, lcb_score_out,
+                         (i64*)match_score_out);
 }
 
 // ---- test hooks -------------------------------------------------------------------------

@@ -25,7 +25,7 @@ __all__ = [
     "CODING_SEED", "SOLID_SEED", "McuError", "getSeed", "getSolidSeed", "getDefaultSeedWeight", "getSeedLength", "getSeedWeight",
     "bmer", "DNAMemorySML", "Match", "MatchList", "MemHash", "PairwiseMatchFinder", "AnchorSession", "merge_matches",
     "PWPath", "GlobalAlign", "GlobalAlignBatch", "Params", "getAdaptedHoxdMatrixParameters", "adaptToPercentIdentity",
-    "run", "run_batch", "sort_pairs",
+    "run", "run_batch", "sort_pairs", "SeedOccurrenceList", "GetPairwiseAnchorScore", "anchor_scores", "hoxd_matrix",
 ]
 
 
@@ -78,6 +78,7 @@ class DNAMemorySML:
         self._packed = np.zeros(0, dtype=np.uint32)
         self._seed = 0
         self._length = 0
+        self._seq = np.zeros(0, dtype=np.uint8)  # the sequence the list was built from (SortedMerList keeps it 2-bit packed)
 
     def Create(self, seq, seed: int):
         """SortedMerList::Create + FillDnaSeedSML + sort (LM/MemorySML.cpp:45-60)."""
@@ -91,7 +92,7 @@ class DNAMemorySML:
         check(lib().mcu_sml_build(addr, n, seed, pos.ctypes.data, mer.ctypes.data, packed.ctypes.data, C.byref(out_len)))
         k = out_len.value
         self._pos, self._mer, self._packed = pos[:k], mer[:k], packed
-        self._seed, self._length = seed, n
+        self._seed, self._length, self._seq = seed, n, keep
 
     def Length(self):
         return self._length
@@ -596,6 +597,64 @@ def run(sequence, params, want_posterior=False):
 
 
 # ---- test hook --------------------------------------------------------------------------------------
+# ---- LM/SeedOccurrenceList.h, LM/GreedyBreakpointElimination.h:403-476 -----------------------------------
+hoxd_matrix = np.array([[91, -114, -31, -123], [-114, 100, -125, -31], [-31, -125, 100, -114], [-123, -31, -114, 91]],
+                       dtype=np.int32)  # LM/SubstitutionMatrix.h:23-33
+
+
+class SeedOccurrenceList:
+    """mems::SeedOccurrenceList (LM/SeedOccurrenceList.h): construct(sml) computes the smoothed seed multiplicity of every
+    position of the sml's sequence on the device; getFrequency(position) reads it."""
+
+    def __init__(self):
+        self._freq = np.zeros(0, dtype=np.float32)
+
+    def construct(self, sml: DNAMemorySML):
+        seq = sml._seq
+        a, n, keep = _buf(seq)
+        out = np.zeros(max(n, 1), dtype=np.float32)
+        check(lib().mcu_sol_build(a, n, sml.Seed(), out.ctypes.data))
+        self._freq = out[:n]
+
+    def getFrequency(self, position: int) -> float:
+        return float(self._freq[position])
+
+    def frequencies(self):
+        return self._freq
+
+
+def anchor_scores(seq0, seq1, rows, lcb_off, seed=0, sol_1=None, sol_2=None, matrix=None, penalize_repeats=False):
+    """mcu_anchor_scores: (lcb_scores float64[n_lcb], match_scores int64[n_rows]).  rows: int64 [n,3] (len, start0, start1);
+    lcb_off: n_lcb+1 row offsets; sol_1/sol_2: SeedOccurrenceList (None = built on the device from `seed`)."""
+    a0, n0, k0 = _buf(seq0)
+    a1, n1, k1 = _buf(seq1)
+    rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3)
+    off = np.ascontiguousarray(lcb_off, dtype=np.uint64)
+    n_lcb = max(off.size - 1, 0)
+    f0 = None if sol_1 is None else np.ascontiguousarray(sol_1.frequencies(), dtype=np.float32)
+    f1 = None if sol_2 is None else np.ascontiguousarray(sol_2.frequencies(), dtype=np.float32)
+    for f, n in ((f0, n0), (f1, n1)):
+        if f is not None and f.size != n:
+            raise McuError(_capi.MCU_EINVAL, "seed occurrence list length differs from the sequence length")
+    mat = None if matrix is None else np.ascontiguousarray(matrix, dtype=np.int32).reshape(16)
+    lcb = np.zeros(max(n_lcb, 1), dtype=np.float64)
+    ms = np.zeros(max(rows.shape[0], 1), dtype=np.int64)
+    check(lib().mcu_anchor_scores(a0, n0, a1, n1, seed, None if f0 is None else f0.ctypes.data, None if f1 is None else f1.ctypes.data,
+                                  rows.ctypes.data, rows.shape[0], off.ctypes.data, n_lcb, None if mat is None else mat.ctypes.data,
+                                  1 if penalize_repeats else 0, lcb.ctypes.data, ms.ctypes.data))
+    return lcb[:n_lcb], ms[:rows.shape[0]]
+
+
+def GetPairwiseAnchorScore(lcb, seq_table, subst_scoring, sol_1, sol_2, penalize_gaps=False, penalize_repeats=False):
+    """mems::GetPairwiseAnchorScore (LM/GreedyBreakpointElimination.h:403-476) for one LCB: a list of Match (ungapped, two
+    genomes).  subst_scoring: 4x4 matrix or None for the default scheme."""
+    if penalize_gaps:
+        raise McuError(_capi.MCU_EINVAL, "penalize_gaps: ungapped matches have no gaps to penalize; the aligner never sets it")
+    rows = np.array([[m.Length(), m.Start(0), m.Start(1)] for m in lcb], dtype=np.int64).reshape(-1, 3)
+    scores, _ = anchor_scores(seq_table[0], seq_table[1], rows, [0, rows.shape[0]], 0, sol_1, sol_2, subst_scoring, penalize_repeats)
+    return float(scores[0])
+
+
 def sort_pairs(keys, vals, bits):
     keys = np.ascontiguousarray(keys).copy()
     vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()

@@ -14,6 +14,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "libmauve_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libmauve_ref.so")
+REF_FULL_SO = os.path.join(ROOT, "oracle", "_ref", "libmauve_ref_full.so")  # all of libMems: the rows next to the hot path
 
 
 class Match3(C.Structure):
@@ -55,6 +56,10 @@ def oracle(build=True):
         lib.orc_pack.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p]
         lib.orc_packed_words.restype = C.c_uint64
         lib.orc_packed_words.argtypes = [C.c_uint64]
+        lib.orc_sol_build.restype = C.c_longlong
+        lib.orc_sol_build.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        lib.orc_anchor_scores.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                          C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _cache["o"] = lib
     return _cache["o"]
 
@@ -70,6 +75,51 @@ def ref():
         lib.ref_nw_align.argtypes = [C.c_char_p, C.c_uint, C.c_char_p, C.c_uint, C.c_void_p]
         _cache["r"] = lib
     return _cache["r"]
+
+
+def have_ref_full():
+    return os.path.exists(REF_FULL_SO)
+
+
+def ref_full():
+    if "rf" not in _cache:
+        lib = C.CDLL(REF_FULL_SO)
+        u64, p = C.c_uint64, C.c_void_p
+        lib.ref_sol_build.restype = C.c_longlong
+        lib.ref_sol_build.argtypes = [C.c_char_p, u64, u64, p]
+        lib.ref_anchor_scores.argtypes = [C.c_char_p, u64, C.c_char_p, u64, u64, p, u64, p, u64, C.c_int, p]
+        _cache["rf"] = lib
+    return _cache["rf"]
+
+
+def sol_build(seq: bytes, seed: int, use_ref=False):
+    """SeedOccurrenceList::construct: float32[n].  use_ref: the reference's own class (oracle/_ref), else the C restatement"""
+    out = np.zeros(max(len(seq), 1), dtype=np.float32)
+    f = ref_full().ref_sol_build if use_ref else oracle().orc_sol_build
+    if f(seq, len(seq), seed, out.ctypes.data) != len(seq):
+        raise RuntimeError("sol_build failed")
+    return out[:len(seq)]
+
+
+def anchor_scores(s0: bytes, s1: bytes, seed: int, rows, lcb_off, penalize_repeats=False, use_ref=False, freq=None, matrix=None):
+    """GetPairwiseAnchorScore per LCB: (lcb_scores float64, match_scores int64 or None for the reference)"""
+    rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3)
+    off = np.ascontiguousarray(lcb_off, dtype=np.uint64)
+    n_lcb = off.size - 1
+    lcb = np.zeros(max(n_lcb, 1), dtype=np.float64)
+    if use_ref:
+        assert matrix is None
+        if ref_full().ref_anchor_scores(s0, len(s0), s1, len(s1), seed, rows.ctypes.data, rows.shape[0], off.ctypes.data, n_lcb,
+                                        int(penalize_repeats), lcb.ctypes.data) != 0:
+            raise RuntimeError("ref_anchor_scores failed")
+        return lcb[:n_lcb], None
+    f0, f1 = freq if freq is not None else (sol_build(s0, seed), sol_build(s1, seed))
+    ms = np.zeros(max(rows.shape[0], 1), dtype=np.int64)
+    mat = None if matrix is None else np.ascontiguousarray(matrix, dtype=np.int32)
+    if oracle().orc_anchor_scores(s0, len(s0), s1, len(s1), f0.ctypes.data, f1.ctypes.data, rows.ctypes.data, rows.shape[0], off.ctypes.data,
+                                  n_lcb, None if mat is None else mat.ctypes.data, int(penalize_repeats), lcb.ctypes.data, ms.ctypes.data) != 0:
+        raise RuntimeError("orc_anchor_scores failed")
+    return lcb[:n_lcb], ms[:rows.shape[0]]
 
 
 class Checker:

@@ -114,3 +114,18 @@ def canonical_mers(seq, seed, L, w, positions):
     strand = r < f
     canon = np.where(strand, r, f)
     return (canon << np.uint64(64 - 2 * w)) | strand.astype(np.uint64)
+
+
+def sol_expected(positions, mers, seed_mask, n, L):
+    """SeedOccurrenceList frequencies from a sorted mer list, evaluated independently of the device code and of the restatement:
+    multiplicities from run lengths, exact integer window sums through a cumulative sum, one double division, one rounding."""
+    masked = np.asarray(mers, dtype=np.uint64) & np.uint64(seed_mask)
+    raw = np.ones(n, dtype=np.int64)
+    if masked.size:
+        starts = np.flatnonzero(np.concatenate([[True], masked[1:] != masked[:-1]]))
+        lens = np.diff(np.concatenate([starts, [masked.size]]))
+        raw[np.asarray(positions)] = np.repeat(lens, lens)
+    c = np.concatenate([[0], np.cumsum(np.concatenate([np.ones(L - 1, dtype=np.int64), raw]))])
+    want = ((c[L:] - c[:-L]).astype(np.float64) / float(L)).astype(np.float32)
+    want[n - 1] = np.float32(raw[n - 1])
+    return want

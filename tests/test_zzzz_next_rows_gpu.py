@@ -1,0 +1,136 @@
+"""GPU (-m gpu): the rows next to the hot path: seed occurrence list + anchor scores, through the C ABI
+(mcu_sol_build, mcu_anchor_scores), against the golden vectors minted from the reference's own SeedOccurrenceList /
+GetPairwiseAnchorScore, against the oracle on further inputs, through a full-size property check, and through the C++ adapters
+next to the reference classes (oracle/_ref/dropin_check_next).  Written after the round's GPU budget was spent: the file sorts
+last so that nothing verified earlier depends on it."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import _golden
+import _oracle
+import _properties as P
+from mauve_py_b200 import synth
+from test_sol_cpu import NEXT_BIN, run_next, write_fasta
+
+pytestmark = pytest.mark.gpu
+
+
+def _sol(mp, seq, seed):
+    sml = mp.DNAMemorySML()
+    sml.Create(seq, seed)
+    sol = mp.SeedOccurrenceList()
+    sol.construct(sml)
+    return sol
+
+
+def test_sol_and_anchor_scores_golden(mp):
+    z = _golden.npz("sol_small.npz")
+    for c in _golden.cases(z):
+        k = c["key"]
+        s0, s1 = z["seq_%s_0" % c["name"]].tobytes(), z["seq_%s_1" % c["name"]].tobytes()
+        sol0, sol1 = _sol(mp, s0, c["seed"]), _sol(mp, s1, c["seed"])
+        assert np.array_equal(sol0.frequencies().view(np.uint32), z[k + "_f0"].view(np.uint32)), k
+        assert np.array_equal(sol1.frequencies().view(np.uint32), z[k + "_f1"].view(np.uint32)), k
+        assert sol0.getFrequency(0) == float(z[k + "_f0"][0])
+        rows, cuts = z[k + "_rows"], z[k + "_cuts"]
+        for pen, name in ((False, "_lcb"), (True, "_lcb_pen")):
+            lcb, ms = mp.libmems.anchor_scores(s0, s1, rows, cuts, sol_1=sol0, sol_2=sol1, penalize_repeats=pen)
+            assert np.array_equal(lcb, z[k + name]), (k, pen)
+            # frequencies built inside the call from the seed
+            lcb2, ms2 = mp.libmems.anchor_scores(s0, s1, rows, cuts, seed=c["seed"], penalize_repeats=pen)
+            assert np.array_equal(lcb2, z[k + name]) and np.array_equal(ms, ms2), (k, pen)
+            _, oms = _oracle.anchor_scores(s0, s1, c["seed"], rows, cuts, pen, freq=(z[k + "_f0"], z[k + "_f1"]))
+            assert np.array_equal(ms, oms), (k, pen)
+
+
+def test_sol_mds42_golden(mp):
+    """BASELINE config 1: both MDS42 genomes (coding seed w15) and the anchor scores of the 29,403-row golden match list"""
+    z = _golden.npz("sol_mds42.npz")
+    md = _golden.meta(z)
+    g0, g1 = _golden.mds42()
+    sol0, sol1 = _sol(mp, g0, md["seed"]), _sol(mp, g1, md["seed"])
+    assert hashlib.sha1(sol0.frequencies().tobytes()).hexdigest() == md["sha1_f0"]
+    assert hashlib.sha1(sol1.frequencies().tobytes()).hexdigest() == md["sha1_f1"]
+    rows = _golden.npz("mums_mds42.npz")["rows_w15_r3"]
+    lcb, ms = mp.libmems.anchor_scores(g0, g1, rows, z["cuts"], sol_1=sol0, sol_2=sol1)
+    assert np.array_equal(lcb, z["lcb"])
+    # the reference's interface, one LCB
+    first = [mp.Match(int(r[0]), [int(r[1]), int(r[2])]) for r in rows[:64]]
+    assert mp.GetPairwiseAnchorScore(first, [g0, g1], None, sol0, sol1) == float(z["lcb"][0])
+
+
+@pytest.mark.parametrize("w,rank", [(7, 0), (11, 0), (15, 3), (19, 3), (21, 0), (31, 0)])
+def test_sol_edges_vs_oracle(mp, orc, w, rank):
+    """no seed at all, exactly one seed, long runs (the bisection branch of sol_run_length), IUPAC and lower-case letters"""
+    rng = np.random.default_rng(300 + w)
+    seed = orc.get_seed(w, rank)
+    L = orc.seed_length(seed)
+    a, _b = synth.repeat_rich_pair(n=80_000, unit=61, copies=500, seed=w)
+    seqs = [a, b"A" * 200_000, b"AC" * 40_000 + a[:3000], bytes(rng.choice(list(b"ACGT"), L).astype(np.uint8)),
+            bytes(rng.choice(list(b"ACGT"), L + 1).astype(np.uint8)), bytes(rng.choice(list(b"ACGT"), max(L - 1, 1)).astype(np.uint8)), b"G",
+            bytes(rng.choice(list(b"ACGTNRYKMSWnacgt"), 5000).astype(np.uint8))]
+    for s in seqs:
+        got = _sol(mp, s, seed).frequencies()
+        want = _oracle.sol_build(s, seed)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (len(s), w, np.flatnonzero(got != want)[:5])
+
+
+def test_anchor_scores_argument_errors(mp):
+    a, b = synth.small_pair(5000, seed=3)
+    seed = mp.getSeed(11, 0)
+    ok = np.array([[50, 1, 1], [50, 100, -200]], dtype=np.int64)
+    lcb, ms = mp.libmems.anchor_scores(a, b, ok, [0, 1, 2], seed=seed)
+    assert lcb.shape == (2,) and ms[0] == lcb[0]
+    for bad in ([[50, 0, 1]], [[50, 1, len(b)]], [[-1, 1, 1]], [[len(a) + 1, 1, 1]]):
+        with pytest.raises(mp.McuError):
+            mp.libmems.anchor_scores(a, b, np.array(bad, dtype=np.int64), [0, 1], seed=seed)
+    with pytest.raises(mp.McuError):
+        mp.libmems.anchor_scores(a, b, ok, [0, 3], seed=seed)
+    lcb, ms = mp.libmems.anchor_scores(a, b, np.zeros((0, 3), dtype=np.int64), [0, 0], seed=seed)   # an empty LCB scores 0
+    assert lcb.tolist() == [0.0] and ms.size == 0
+
+
+def test_sol_full_size_property(mp):
+    """20 Mbp of the config-3 genome at its default weight: the frequencies equal an independent numpy evaluation (multiplicities
+    from the device's own sorted list, exact integer window sums, one double division, one rounding to float)"""
+    a, _b = synth.config3_pair(n=20_000_000)
+    seq = a.tobytes()
+    seed = mp.getSeed(mp.getDefaultSeedWeight(len(seq)), mp.CODING_SEED)
+    L = mp.getSeedLength(seed)
+    sml = mp.DNAMemorySML()
+    sml.Create(seq, seed)
+    sol = mp.SeedOccurrenceList()
+    sol.construct(sml)
+    f = sol.frequencies()
+    want = P.sol_expected(sml.positions(), sml.mers(), sml.GetSeedMask(), len(seq), L)
+    assert f.shape == want.shape and np.array_equal(f.view(np.uint32), want.view(np.uint32))
+    assert f.min() >= 1.0 and (f != 1.0).sum() > 0
+
+
+needs_next = pytest.mark.skipif(not os.path.exists(NEXT_BIN), reason="oracle/_ref/dropin_check_next not built (needs /root/reference at build time)")
+
+
+@needs_next
+def test_dropin_sol_and_scores_next_to_the_reference_classes(tmp_path):
+    """the reference's SeedOccurrenceList / GetPairwiseAnchorScore and the C++ adapters in one process, on the LCBs the reference's
+    own EliminateOverlaps_v2 / IdentifyBreakpoints / ComputeLCBs_v2 produce"""
+    a, b = synth.small_pair(400000, seed=71, snp=0.02, n_inv=4)
+    write_fasta(tmp_path / "a.fa", "a", a)
+    write_fasta(tmp_path / "b.fa", "b", b)
+    rc, kv, out = run_next(["sol", tmp_path / "a.fa", 15, 3])
+    assert rc == 0 and kv["RESULT"] == "identical" and int(kv["not_one"]) > 0, out
+    for w, r in ((15, 3), (11, 0), (0, 3)):
+        rc, kv, out = run_next(["scores", tmp_path / "a.fa", tmp_path / "b.fa", w, r])
+        assert rc == 0 and kv["RESULT"] == "identical" and int(kv["lcbs"]) >= 1, out
+
+
+@needs_next
+def test_dropin_scores_mds42(tmp_path):
+    g0, g1 = _golden.mds42()
+    write_fasta(tmp_path / "recoded.fa", "recoded", g0)
+    write_fasta(tmp_path / "full.fa", "full", g1)
+    rc, kv, out = run_next(["scores", tmp_path / "recoded.fa", tmp_path / "full.fa", 0, 3])
+    assert rc == 0 and kv["RESULT"] == "identical" and kv["matches"] == "29403", out
