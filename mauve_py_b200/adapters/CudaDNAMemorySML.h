@@ -38,7 +38,8 @@ public:
 	virtual void Create(const genome::gnSequence& seq, const uint64 seed)
 	{
 		SortedMerList::Create(seq, seed);  // header, masks and the 2-bit `sequence`: unchanged host code (LM/SortedMerList.cpp:786-824)
-		const std::string bases = seq.ToString();
+		// explicit length: gnRAWSequence::ToString() with default arguments drops the last two bases (LM/gnRAWSequence.h:157-161)
+		const std::string bases = seq.ToString(seq.length(), 1);
 		positions.assign(SMLLength(), 0);
 		uint64_t n = 0;
 		const int rc = mcu_sml_build(bases.data(), bases.size(), seed, positions.empty() ? NULL : &positions[0], NULL, NULL, &n);

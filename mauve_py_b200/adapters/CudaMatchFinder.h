@@ -31,7 +31,9 @@ namespace cuda_detail {
 // true when the list was produced on the device
 inline bool FindMatchesTwoGenomes(MatchList& ml, int rule, uint64& mem_count, uint64& collision_count)
 {
-	const std::string s0 = ml.seq_table[0]->ToString(), s1 = ml.seq_table[1]->ToString();
+	// explicit lengths: progressiveMauve holds gnRAWSequence objects, whose ToString() with default arguments drops the last two
+	// bases (LM/gnRAWSequence.h:157-161)
+	const std::string s0 = ml.seq_table[0]->ToString(ml.seq_table[0]->length(), 1), s1 = ml.seq_table[1]->ToString(ml.seq_table[1]->length(), 1);
 	mcu_match* rows = NULL;
 	uint64_t n = 0, stats[8];
 	const int rc = mcu_find_mums(s0.data(), s0.size(), s1.data(), s1.size(), ml.sml_table[0]->Seed(), rule, &rows, &n, stats);

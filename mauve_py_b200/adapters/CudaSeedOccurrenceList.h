@@ -91,7 +91,8 @@ void CudaPairwiseAnchorScores(std::vector<MatchVector>& LCB_list, std::vector<ge
 		}
 		off.push_back(rows.size());
 	}
-	const std::string s0 = seq_table[0]->ToString(), s1 = seq_table[1]->ToString();
+	// explicit lengths: gnRAWSequence::ToString() with default arguments drops the last two bases (LM/gnRAWSequence.h:157-161)
+	const std::string s0 = seq_table[0]->ToString(seq_table[0]->length(), 1), s1 = seq_table[1]->ToString(seq_table[1]->length(), 1);
 	int32_t matrix[16];
 	for (int i = 0; i < 4; ++i)
 		for (int j = 0; j < 4; ++j) matrix[4 * i + j] = subst_scoring.matrix[i][j];

@@ -1,9 +1,10 @@
 /* TEST INFRASTRUCTURE ONLY -- never shipped, never loaded by the product.
  *
- * LD_PRELOAD stand-in for the few libmauve_cuda.so entry points the C++ adapters of SURVEY.md 8f-2 call, answering from the
- * CPU restatement (oracle/libmauve_oracle.so).  It lets the CPU suite run oracle/_ref/dropin_check_next -- i.e. the adapters'
- * own host code (2-bit unpacking, temp-file mapping, LCB marshalling) next to the reference classes -- in a container
- * without a GPU.  The GPU tests run the same binary against the real library.
+ * LD_PRELOAD stand-in for the few libmauve_cuda.so entry points the C++ adapters of SURVEY.md 8f-2 and the DP seam
+ * (adapters/seams/anchoredpp_batch.cpp) call, answering from the CPU restatement (oracle/libmauve_oracle.so).  It lets the CPU
+ * suite run oracle/_ref/dropin_check_next and oracle/_ref/progressiveMauve_cuda -- i.e. the adapters' own host code (2-bit
+ * unpacking, temp-file mapping, LCB marshalling, range batching) next to / inside the reference -- in a container without a
+ * GPU.  The GPU tests run the same binaries against the real library.
  */
 #include <stdint.h>
 #include <stddef.h>
@@ -25,3 +26,40 @@ int mcu_anchor_scores(const char* seq0, uint64_t n0, const char* seq1, uint64_t 
     if (!freq0 || !freq1) return -3;
     return orc_anchor_scores(seq0, n0, seq1, n1, freq0, freq1, rows, n_rows, lcb_off, n_lcb, matrix, penalize_repeats, lcb_score_out, match_score_out) == 0 ? 0 : -3;
 }
+
+long long orc_nw_align(const char* a, unsigned la, const char* b, unsigned lb, char* path_out, int64_t* score_out);
+static unsigned long long g_nw_calls = 0, g_nw_problems = 0;
+int mcu_nw_batch(uint64_t n, const char* a, const uint64_t* a_off, const char* b, const uint64_t* b_off, const uint64_t* path_off, char* path_out,
+                 uint32_t* path_len, int64_t* score, float* device_ms)
+{
+    uint64_t i;
+    ++g_nw_calls;
+    g_nw_problems += n;
+    for (i = 0; i < n; ++i) {
+        long long r = orc_nw_align(a + a_off[i], (unsigned)(a_off[i + 1] - a_off[i]), b + b_off[i], (unsigned)(b_off[i + 1] - b_off[i]),
+                                   path_out + path_off[i], &score[i]);
+        if (r < 0) return -6;
+        path_len[i] = (uint32_t)r;
+    }
+    if (device_ms) *device_ms = 0;
+    return 0;
+}
+#include <stdio.h>
+#include <stdlib.h>
+__attribute__((destructor)) static void stub_report(void)
+{
+    if (getenv("MAUVE_CUDA_SEAM_REPORT")) fprintf(stderr, "stub: %llu mcu_nw_batch calls, %llu problems\n", g_nw_calls, g_nw_problems);
+}
+
+/* match finder (adapters/seams/memhash_seam.cpp, CudaMatchFinder.h) */
+long long orc_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule, mcu_match** out, uint64_t* stats);
+int mcu_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule, mcu_match** out, uint64_t* n_out, uint64_t* stats)
+{
+    uint64_t st[4] = {0, 0, 0, 0};
+    long long n = orc_find_mums(seq0, n0, seq1, n1, seed, rule, out, st);
+    if (n < 0) return -3;
+    *n_out = (uint64_t)n;
+    if (stats) { int i; for (i = 0; i < 8; ++i) stats[i] = 0; stats[0] = st[3]; stats[1] = st[1]; stats[2] = st[0]; }
+    return 0;
+}
+void mcu_free(void* p) { free(p); }

@@ -221,3 +221,104 @@ def test_sslist_files_are_loaded_by_the_unmodified_binary(tmp_path, orc):
     log1, loaded = run("loaded")
     assert "Sorted mer list loaded successfully" in log1 and "Creating sorted mer list" not in log1
     assert loaded == plain
+
+
+# ---- progressiveMauve_cuda / progressiveMauve_cuda_mh: the reference binary with link-time seams (adapters/seams) ---------------
+CUDA_BINARY = os.path.join(REF_DIR, "progressiveMauve_cuda")         # gapped DP of every window on the device
+CUDA_MH_BINARY = os.path.join(REF_DIR, "progressiveMauve_cuda_mh")   # + MemHash::FindMatches of two genomes on the device
+needs_cuda_bin = pytest.mark.skipif(not (os.path.exists(CUDA_BINARY) and os.path.exists(CUDA_MH_BINARY)),
+                                    reason="oracle/_ref/progressiveMauve_cuda[_mh] not built (needs /root/reference at build time)")
+
+
+def _xmfa_body_sha1(xmfa):
+    body = b"".join(b" ".join(l.split()[:3]) + b"\n" if l.startswith(b">") else l for l in open(xmfa, "rb") if not l.startswith(b"#"))
+    return hashlib.sha1(body).hexdigest()
+
+
+def _align(binary, d, a, b, out, env=None):
+    for f in os.listdir(d):
+        if f.endswith(".sslist"):
+            os.remove(os.path.join(d, f))
+    return subprocess.run([binary, "--output=" + out, a, b], cwd=d, capture_output=True, text=True, env=env)
+
+
+def _seam_counts(stderr):
+    out = {}
+    for l in stderr.splitlines():
+        if l.startswith("AnchoredProfileProfile seam:") or l.startswith("MemHash::FindMatches seam:"):
+            out[l.split(" seam:")[0]] = [int(x) for x in l.replace(",", "").split() if x.isdigit()]
+    return out
+
+
+@needs_cuda_bin
+def test_seams_host_code_inside_the_reference_binary(tmp_path):
+    """The link-time seams (mauve_py_b200/adapters/seams: all DP ranges of a window -> one CudaGlobalAlignBatch call;
+    MemHash::FindMatches of two genomes -> mcu_find_mums) inside the unmodified reference objects align the MDS42 pair to the
+    byte-identical XMFA.  Here, without a GPU, the device entry points are answered by the CPU restatement through an LD_PRELOAD
+    stub (tests/_stub): this checks the seams' own host code -- range collection, profile order, path -> PWPath, output assembly,
+    sequence extraction from progressiveMauve's gnRAWSequence objects, Match construction; the GPU suite runs the same binaries
+    against the real library.  Without the stub the binaries stop with the library's error: no CPU fallback behind the seams."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: the GPU suite runs these binaries against the real library")
+    import _emu
+    from mauve_py_b200 import synth
+    d = str(tmp_path)
+    a, b = synth.small_pair(60000, seed=33, snp=0.03, n_inv=1)
+    for name, s_ in (("a", a), ("b", b)):
+        with open(os.path.join(d, name + ".fa"), "wb") as f:
+            f.write(b">" + name.encode() + b"\n" + b"\n".join(s_[i:i + 70] for i in range(0, len(s_), 70)) + b"\n")
+    r = _align(CUDA_BINARY, d, "a.fa", "b.fa", "x.xmfa")
+    assert r.returncode == 3 and "no usable CUDA device" in (r.stdout + r.stderr)
+    r = _align(CUDA_MH_BINARY, d, "a.fa", "b.fa", "x.xmfa")
+    assert r.returncode != 0 and "no usable CUDA device" in (r.stdout + r.stderr)
+    env = dict(os.environ, LD_PRELOAD=_emu.stub_library(), MAUVE_CUDA_SEAM_REPORT="1")
+    assert _align(BINARY, d, "a.fa", "b.fa", "ref.xmfa").returncode == 0
+    r = _align(CUDA_BINARY, d, "a.fa", "b.fa", "dp.xmfa", env)
+    assert r.returncode == 0 and _xmfa_body_sha1(os.path.join(d, "dp.xmfa")) == _xmfa_body_sha1(os.path.join(d, "ref.xmfa")), r.stderr[-500:]
+    c = _seam_counts(r.stderr)["AnchoredProfileProfile"]
+    assert c[0] >= 1 and c[1] == c[2] > 10
+    # BASELINE config 1 with every seam on: initial anchors, the gap searches of recursive anchoring, the DP of every window
+    _lut, meta = _golden()
+    fas = _fastas(tmp_path)
+    env["MAUVE_CUDA_GAP_SEAM"] = "1"
+    r = _align(CUDA_MH_BINARY, d, os.path.basename(fas[0]), os.path.basename(fas[1]), "cuda.xmfa", env)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert _xmfa_body_sha1(os.path.join(d, "cuda.xmfa")) == meta["xmfa_body_sha1"]
+    c = _seam_counts(r.stderr)
+    assert c["MemHash::FindMatches"][0] > 300                 # 1 initial search + the 371 gap searches
+    assert c["AnchoredProfileProfile"][0] > 100 and c["AnchoredProfileProfile"][1] == c["AnchoredProfileProfile"][2] > 40000   # 165 windows, 41,806 ranges
+
+
+@needs_cuda_bin
+@pytest.mark.gpu
+@pytest.mark.parametrize("binary,gap_seam", [(CUDA_BINARY, "0"), (CUDA_MH_BINARY, "0"), (CUDA_MH_BINARY, "1")])
+def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, gap_seam):
+    """mauve_py_b200.buildIndex with a seam binary as $MAUVE_DIR/progressiveMauveStatic: sorted mer lists, anchors AND the gapped DP
+    of every window (and, last case, the gap searches of recursive anchoring) on the device; the LUT is the reference's.  Then the
+    binary on its own, from the FASTA files: byte-identical XMFA."""
+    import time
+    import mauve_py_b200 as mp
+    from mauve_py_b200._capi import check
+    check(mp.lib().mcu_init(0))
+    lut, meta = _golden()
+    fas = _fastas(tmp_path)
+    bindir = os.path.join(str(tmp_path), "bin")
+    os.makedirs(bindir)
+    os.symlink(binary, os.path.join(bindir, "progressiveMauveStatic"))
+    monkeypatch.setenv("MAUVE_DIR", bindir)
+    monkeypatch.setenv("MAUVE_CUDA_GAP_SEAM", gap_seam)
+    t0 = time.time()
+    got = mp.buildIndex(fas[0], fas[1])
+    t1 = time.time()
+    assert np.array_equal(got, lut)
+    env = dict(os.environ, MAUVE_CUDA_SEAM_REPORT="1")
+    r = _align(binary, str(tmp_path), os.path.basename(fas[0]), os.path.basename(fas[1]), "cuda.xmfa", env)
+    t2 = time.time()
+    assert r.returncode == 0, r.stderr[-500:]
+    assert _xmfa_body_sha1(os.path.join(str(tmp_path), "cuda.xmfa")) == meta["xmfa_body_sha1"]
+    c = _seam_counts(r.stderr)
+    assert c["AnchoredProfileProfile"][1] == c["AnchoredProfileProfile"][2] > 40000
+    if binary == CUDA_MH_BINARY:
+        assert c["MemHash::FindMatches"][0] >= (300 if gap_seam == "1" else 1)
+    print("buildIndex %.1f s, standalone binary %.1f s (%s, gap seam %s)" % (t1 - t0, t2 - t1, os.path.basename(binary), gap_seam))
