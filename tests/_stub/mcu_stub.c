@@ -8,6 +8,9 @@
  */
 #include <stdint.h>
 #include <stddef.h>
+#include <time.h>
+static double g_stub_seconds = 0;
+static double stub_now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 typedef struct { int64_t len, start0, start1; } mcu_match;
 long long orc_sol_build(const char* seq, uint64_t n, uint64_t seed, float* freq_out);
@@ -33,6 +36,7 @@ int mcu_nw_batch(uint64_t n, const char* a, const uint64_t* a_off, const char* b
                  uint32_t* path_len, int64_t* score, float* device_ms)
 {
     uint64_t i;
+    const double t0 = stub_now();
     ++g_nw_calls;
     g_nw_problems += n;
     for (i = 0; i < n; ++i) {
@@ -42,13 +46,14 @@ int mcu_nw_batch(uint64_t n, const char* a, const uint64_t* a_off, const char* b
         path_len[i] = (uint32_t)r;
     }
     if (device_ms) *device_ms = 0;
+    g_stub_seconds += stub_now() - t0;
     return 0;
 }
 #include <stdio.h>
 #include <stdlib.h>
 __attribute__((destructor)) static void stub_report(void)
 {
-    if (getenv("MAUVE_CUDA_SEAM_REPORT")) fprintf(stderr, "stub: %llu mcu_nw_batch calls, %llu problems\n", g_nw_calls, g_nw_problems);
+    if (getenv("MAUVE_CUDA_SEAM_REPORT")) fprintf(stderr, "stub: %llu mcu_nw_batch calls, %llu problems; %.2f s inside the stand-in entry points\n", g_nw_calls, g_nw_problems, g_stub_seconds);
 }
 
 /* match finder (adapters/seams/memhash_seam.cpp, CudaMatchFinder.h) */
@@ -56,7 +61,9 @@ long long orc_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_
 int mcu_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule, mcu_match** out, uint64_t* n_out, uint64_t* stats)
 {
     uint64_t st[4] = {0, 0, 0, 0};
+    const double t0 = stub_now();
     long long n = orc_find_mums(seq0, n0, seq1, n1, seed, rule, out, st);
+    g_stub_seconds += stub_now() - t0;
     if (n < 0) return -3;
     *n_out = (uint64_t)n;
     if (stats) { int i; for (i = 0; i < 8; ++i) stats[i] = 0; stats[0] = st[3]; stats[1] = st[1]; stats[2] = st[0]; }
