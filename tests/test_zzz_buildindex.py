@@ -226,8 +226,9 @@ def test_sslist_files_are_loaded_by_the_unmodified_binary(tmp_path, orc):
 # ---- progressiveMauve_cuda / progressiveMauve_cuda_mh: the reference binary with link-time seams (adapters/seams) ---------------
 CUDA_BINARY = os.path.join(REF_DIR, "progressiveMauve_cuda")         # gapped DP of every window on the device
 CUDA_MH_BINARY = os.path.join(REF_DIR, "progressiveMauve_cuda_mh")   # + MemHash::FindMatches of two genomes on the device
-needs_cuda_bin = pytest.mark.skipif(not (os.path.exists(CUDA_BINARY) and os.path.exists(CUDA_MH_BINARY)),
-                                    reason="oracle/_ref/progressiveMauve_cuda[_mh] not built (needs /root/reference at build time)")
+CUDA_ALL_BINARY = os.path.join(REF_DIR, "progressiveMauve_cuda_all")  # + the DP of RefineW's windows prefetched on the device
+needs_cuda_bin = pytest.mark.skipif(not all(os.path.exists(b) for b in (CUDA_BINARY, CUDA_MH_BINARY, CUDA_ALL_BINARY)),
+                                    reason="oracle/_ref/progressiveMauve_cuda[_mh|_all] not built (needs /root/reference at build time)")
 
 
 def _xmfa_body_sha1(xmfa):
@@ -245,7 +246,7 @@ def _align(binary, d, a, b, out, env=None):
 def _seam_counts(stderr):
     out = {}
     for l in stderr.splitlines():
-        if l.startswith("AnchoredProfileProfile seam:") or l.startswith("MemHash::FindMatches seam:"):
+        if l.startswith("AnchoredProfileProfile seam:") or l.startswith("MemHash::FindMatches seam:") or l.startswith("RefineW seam:"):
             out[l.split(" seam:")[0]] = [int(x) for x in l.replace(",", "").split() if x.isdigit()]
     return out
 
@@ -253,8 +254,9 @@ def _seam_counts(stderr):
 @needs_cuda_bin
 def test_seams_host_code_inside_the_reference_binary(tmp_path):
     """The link-time seams (mauve_py_b200/adapters/seams: all DP ranges of a window -> one CudaGlobalAlignBatch call;
-    MemHash::FindMatches of two genomes -> mcu_find_mums) inside the unmodified reference objects align the MDS42 pair to the
-    byte-identical XMFA.  Here, without a GPU, the device entry points are answered by the CPU restatement through an LD_PRELOAD
+    MemHash::FindMatches of two genomes -> mcu_find_mums; the DP of all windows of a RefineW call prefetched in one mcu_nw_batch
+    call) inside the unmodified reference objects align the MDS42 pair to the byte-identical XMFA, with EVERY ONE of the run's
+    61,773 gapped-DP calls answered by the device entry point.  Here, without a GPU, the device entry points are answered by the CPU restatement through an LD_PRELOAD
     stub (tests/_stub): this checks the seams' own host code -- range collection, profile order, path -> PWPath, output assembly,
     sequence extraction from progressiveMauve's gnRAWSequence objects, Match construction; the GPU suite runs the same binaries
     against the real library.  Without the stub the binaries stop with the library's error: no CPU fallback behind the seams."""
@@ -282,17 +284,20 @@ def test_seams_host_code_inside_the_reference_binary(tmp_path):
     _lut, meta = _golden()
     fas = _fastas(tmp_path)
     env["MAUVE_CUDA_GAP_SEAM"] = "1"
-    r = _align(CUDA_MH_BINARY, d, os.path.basename(fas[0]), os.path.basename(fas[1]), "cuda.xmfa", env)
+    r = _align(CUDA_ALL_BINARY, d, os.path.basename(fas[0]), os.path.basename(fas[1]), "cuda.xmfa", env)
     assert r.returncode == 0, r.stderr[-500:]
     assert _xmfa_body_sha1(os.path.join(d, "cuda.xmfa")) == meta["xmfa_body_sha1"]
     c = _seam_counts(r.stderr)
     assert c["MemHash::FindMatches"][0] > 300                 # 1 initial search + the 371 gap searches
     assert c["AnchoredProfileProfile"][0] > 100 and c["AnchoredProfileProfile"][1] == c["AnchoredProfileProfile"][2] > 40000   # 165 windows, 41,806 ranges
+    calls, prefetched, hits, misses = c["RefineW"]
+    assert calls > 100 and hits > 19000 and misses == 0       # 19,967 windows of RefineFast: every GlobalAlign answered from the prefetch
+    assert c["AnchoredProfileProfile"][2] + hits == 61773     # = all gapped-DP calls of the run (tests/golden/dp_mds42_calls.npz meta)
 
 
 @needs_cuda_bin
 @pytest.mark.gpu
-@pytest.mark.parametrize("binary,gap_seam", [(CUDA_BINARY, "0"), (CUDA_MH_BINARY, "0"), (CUDA_MH_BINARY, "1")])
+@pytest.mark.parametrize("binary,gap_seam", [(CUDA_BINARY, "0"), (CUDA_MH_BINARY, "0"), (CUDA_MH_BINARY, "1"), (CUDA_ALL_BINARY, "1")])
 def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, gap_seam):
     """mauve_py_b200.buildIndex with a seam binary as $MAUVE_DIR/progressiveMauveStatic: sorted mer lists, anchors AND the gapped DP
     of every window (and, last case, the gap searches of recursive anchoring) on the device; the LUT is the reference's.  Then the
@@ -319,6 +324,8 @@ def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, 
     assert _xmfa_body_sha1(os.path.join(str(tmp_path), "cuda.xmfa")) == meta["xmfa_body_sha1"]
     c = _seam_counts(r.stderr)
     assert c["AnchoredProfileProfile"][1] == c["AnchoredProfileProfile"][2] > 40000
-    if binary == CUDA_MH_BINARY:
+    if binary != CUDA_BINARY:
         assert c["MemHash::FindMatches"][0] >= (300 if gap_seam == "1" else 1)
+    if binary == CUDA_ALL_BINARY:
+        assert c["RefineW"][3] == 0 and c["AnchoredProfileProfile"][2] + c["RefineW"][2] == 61773
     print("buildIndex %.1f s, standalone binary %.1f s (%s, gap seam %s)" % (t1 - t0, t2 - t1, os.path.basename(binary), gap_seam))
