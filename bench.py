@@ -241,6 +241,18 @@ def measure_dp(mp, synth, args):
     dp = {"metric": "GCUPS gapped DP (full-matrix cells, NWSmall-exact paths)", "value": cells / (res["device_ms"] * 1e-3) / 1e9,
           "unit": "GCUPS", "regions": len(pairs), "cells": cells, "device_ms": res["device_ms"],
           "workload": "BASELINE config 5 sample: %d regions, lenA log-uniform 100 bp-10 kbp, 5%% SNP + 1%% indel events" % len(pairs)}
+    # DP roofline: ~12 int32 operations per cell against the INT32 issue rate MEASURED on this device by a register-resident
+    # add/max microbenchmark (mcu_test_int32_peak); the kernel's own count is ~22 instructions per cell
+    try:
+        gops, pms = C.c_double(0.0), C.c_float(0.0)
+        mp._capi.check(mp.lib().mcu_test_int32_peak(C.byref(gops), C.byref(pms)))
+        if gops.value > 0:
+            achieved = 12.0 * dp["value"]
+            dp["roofline"] = {"bound": "int32 issue", "achieved": achieved, "peak": gops.value, "unit": "G thread-instructions/s", "frac": achieved / gops.value,
+                              "ops_per_cell": 12, "peak_source": "measured: mcu_test_int32_peak (8 independent VIADDMNMX chains per thread, register "
+                                                                 "resident, %.2f ms); achieved = 12 algorithmic int32 operations per cell (SURVEY.md 8d)" % pms.value}
+    except Exception as e:  # noqa: BLE001
+        dp["roofline"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if not args.no_cpu:
         chk, kind = cpu_checker()
         small = [p for p in pairs if len(p[0]) <= 3000][:12]

@@ -206,6 +206,10 @@ int mcu_anchor_scores(const char* seq0, uint64_t n0, const char* seq1, uint64_t 
 /* ---- test hooks (exercise single kernels through the ABI) -------------------------------- */
 /* stable LSD radix sort of (key,val) pairs on the low `bits` bits; key_bytes is 4 or 8 */
 int mcu_test_sort_pairs(void* keys, uint32_t* vals, uint64_t n, int key_bytes, int bits);
+/* INT32 issue-rate microbenchmark (the measured denominator of the gapped-DP roofline): 8 independent add/max chains
+ * per thread, register resident, one full-device launch timed with CUDA events.  *gops_out = thread-level integer instructions / s / 1e9
+ * (ptxas fuses every add+max pair of the loop into one VIADDMNMX: one instruction, two operations). */
+int mcu_test_int32_peak(double* gops_out, float* ms_out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mcu_session_match_count", "mcu_session_download", "mcu_session_matches_device",
     "mcu_session_launch_count", "mcu_merge_matches",
     "mcu_nw_batch", "mcu_nw_last_stats", "mcu_hmm_params", "mcu_hmm_batch", "mcu_sol_build", "mcu_anchor_scores",
-    "mcu_test_sort_pairs",
+    "mcu_test_sort_pairs", "mcu_test_int32_peak",
 ]
 
 
@@ -94,6 +94,7 @@ def lib():
     L.mcu_sol_build.argtypes = [vp, u64, u64, vp]
     L.mcu_anchor_scores.argtypes = [vp, u64, vp, u64, u64, vp, vp, vp, u64, vp, u64, vp, i32, vp, vp]
     L.mcu_test_sort_pairs.argtypes = [vp, vp, u64, i32, i32]
+    L.mcu_test_int32_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_float)]
     _lib = L
     return L
 

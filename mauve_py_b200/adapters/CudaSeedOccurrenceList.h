@@ -29,6 +29,31 @@
 
 namespace mems {
 
+namespace cuda_detail {
+
+// getFrequency() values of every position of the list's sequence, computed on the device
+template <typename SMLType>
+inline void SolFrequencies(SMLType& sml, std::vector<SeedOccurrenceList::frequency_type>& count)
+{
+	const size_t total_len = sml.Length();
+	std::string bases(total_len, 'A');
+	if (total_len) {   // 2-bit codes -> letters (the SML build on the device packs them back to the same codes)
+		const gnSeqI words = (total_len * 2) / 32 + (((total_len * 2) % 32) ? 1 : 0);
+		std::vector<uint32> buf(words + 4, 0);
+		uint32* packed = &buf[1];   // GetBSequence masks dest[-1] when the sequence is shorter than one word (LM/SortedMerList.cpp:369-372)
+		sml.GetBSequence(packed, total_len, 0);
+		static const char letters[4] = {'A', 'C', 'G', 'T'};
+		for (gnSeqI i = 0; i < total_len; ++i) bases[i] = letters[(packed[i >> 4] >> (30 - 2 * (i & 15))) & 3];
+	}
+	count.assign(total_len ? total_len : 1, 1.0f);
+	if (mcu_sol_build(bases.data(), total_len, sml.Seed(), &count[0]) != MCU_OK) {
+		std::cerr << "CudaSeedOccurrenceList::construct: " << mcu_last_error() << std::endl;
+		throw "CudaSeedOccurrenceList::construct failed";
+	}
+}
+
+}  // namespace cuda_detail
+
 class CudaSeedOccurrenceList : public SeedOccurrenceList
 {
 public:
@@ -38,20 +63,8 @@ public:
 	void construct(SMLType& sml)
 	{
 		total_len = sml.Length();
-		std::string bases(total_len, 'A');
-		if (total_len) {   // 2-bit codes -> letters (the SML build on the device packs them back to the same codes)
-			const gnSeqI words = (total_len * 2) / 32 + (((total_len * 2) % 32) ? 1 : 0);
-			std::vector<uint32> buf(words + 4, 0);
-			uint32* packed = &buf[1];   // GetBSequence masks dest[-1] when the sequence is shorter than one word (LM/SortedMerList.cpp:369-372)
-			sml.GetBSequence(packed, total_len, 0);
-			static const char letters[4] = {'A', 'C', 'G', 'T'};
-			for (gnSeqI i = 0; i < total_len; ++i) bases[i] = letters[(packed[i >> 4] >> (30 - 2 * (i & 15))) & 3];
-		}
-		std::vector<frequency_type> count(total_len ? total_len : 1);
-		if (mcu_sol_build(bases.data(), total_len, sml.Seed(), &count[0]) != MCU_OK) {
-			std::cerr << "CudaSeedOccurrenceList::construct: " << mcu_last_error() << std::endl;
-			throw "CudaSeedOccurrenceList::construct failed";
-		}
+		std::vector<frequency_type> count;
+		cuda_detail::SolFrequencies(sml, count);
 		// as the reference from here on (:67-77): temporary file, memory mapped
 		tmpfile = CreateTempFileName("sol");
 		{

@@ -496,6 +496,13 @@ int mcu_anchor_scores(const char* seq0, uint64_t n0, const char* seq1, uint64_t 
 }
 
 // ---- test hooks -------------------------------------------------------------------------
+int mcu_test_int32_peak(double* gops_out, float* ms_out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    return int32_peak(gops_out, ms_out);
+}
+
 int mcu_test_sort_pairs(void* keys, uint32_t* vals, uint64_t n, int key_bytes, int bits)
 {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -377,6 +377,48 @@ void nw_last_stats(u64* out5)
     for (int i = 0; i < 5; ++i) out5[i] = g_nw.stats[i];
 }
 
+// ---- INT32 issue-rate microbenchmark: the denominator of the DP roofline --------------------------------------------
+// Register-resident: 8 independent add/max chains per thread, no memory traffic; the DP inner loop is made of exactly these
+// instruction classes (VIADD / VIMNMX; ptxas fuses each add+max pair here into one VIADDMNMX).  Counted: 8 * iters INSTRUCTIONS per thread.
+__global__ void __launch_bounds__(256) int32_peak_kernel(int* __restrict__ sink, int iters, int b, int c)
+{
+    int a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#define MCU_STEP(x) asm volatile("add.s32 %0, %0, %1;\n\tmax.s32 %0, %0, %2;" : "+r"(x) : "r"(b), "r"(c))
+        MCU_STEP(a0); MCU_STEP(a1); MCU_STEP(a2); MCU_STEP(a3); MCU_STEP(a4); MCU_STEP(a5); MCU_STEP(a6); MCU_STEP(a7);
+#undef MCU_STEP
+    }
+    const int r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (r == 0x7fffffff) sink[0] = r;   // never true for the arguments used; keeps the chains alive
+}
+
+// G thread-level integer instructions per second sustained by the whole device (each one a fused add+max)
+int int32_peak(double* gops_out, float* ms_out)
+{
+    NwState& st = g_nw;
+    if (!st.stream) MCU_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    MCU_CUDA(cudaEventCreate(&e0));
+    MCU_CUDA(cudaEventCreate(&e1));
+    int* sink = nullptr;
+    MCU_CUDA(cudaMalloc(&sink, 256));
+    const int iters = 1 << 16, blocks = sm_count() * 8, threads = 256;
+    int32_peak_kernel<<<blocks, threads, 0, st.stream>>>(sink, 64, 1, -5);   // warm-up
+    MCU_CUDA(cudaEventRecord(e0, st.stream));
+    int32_peak_kernel<<<blocks, threads, 0, st.stream>>>(sink, iters, 1, -5);
+    MCU_CUDA(cudaEventRecord(e1, st.stream));
+    MCU_CUDA(cudaStreamSynchronize(st.stream));
+    MCU_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (ms_out) *ms_out = ms;
+    if (gops_out) *gops_out = ms > 0.f ? 8.0 * (double)iters * (double)blocks * (double)threads / ((double)ms * 1e-3) / 1e9 : 0.0;
+    return MCU_OK;
+}
+
 int nw_batch(u64 n, const char* a, const u64* a_off, const char* b, const u64* b_off, const u64* path_off, char* path_out, u32* path_len,
              i64* score, float* device_ms)
 {

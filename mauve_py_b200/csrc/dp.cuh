@@ -11,4 +11,7 @@ int nw_batch(u64 n, const char* a, const u64* a_off, const char* b, const u64* b
 // [3] sub-batches, [4] traceback bytes
 void nw_last_stats(u64* out5);
 
+// register-resident add/max microbenchmark: Gops/s of thread-level INT32 instructions the device sustains (DP roofline denominator)
+int int32_peak(double* gops_out, float* ms_out);
+
 }  // namespace mcu

@@ -246,7 +246,7 @@ def _align(binary, d, a, b, out, env=None):
 def _seam_counts(stderr):
     out = {}
     for l in stderr.splitlines():
-        if l.startswith("AnchoredProfileProfile seam:") or l.startswith("MemHash::FindMatches seam:") or l.startswith("RefineW seam:"):
+        if l.split(" seam:")[0] in ("AnchoredProfileProfile", "MemHash::FindMatches", "RefineW", "SeedOccurrenceList::construct"):
             out[l.split(" seam:")[0]] = [int(x) for x in l.replace(",", "").split() if x.isdigit()]
     return out
 
@@ -284,6 +284,7 @@ def test_seams_host_code_inside_the_reference_binary(tmp_path):
     _lut, meta = _golden()
     fas = _fastas(tmp_path)
     env["MAUVE_CUDA_GAP_SEAM"] = "1"
+    env["MAUVE_CUDA_SOL_SEAM"] = "1"
     r = _align(CUDA_ALL_BINARY, d, os.path.basename(fas[0]), os.path.basename(fas[1]), "cuda.xmfa", env)
     assert r.returncode == 0, r.stderr[-500:]
     assert _xmfa_body_sha1(os.path.join(d, "cuda.xmfa")) == meta["xmfa_body_sha1"]
@@ -293,12 +294,15 @@ def test_seams_host_code_inside_the_reference_binary(tmp_path):
     calls, prefetched, hits, misses = c["RefineW"]
     assert calls > 100 and hits > 19000 and misses == 0       # 19,967 windows of RefineFast: every GlobalAlign answered from the prefetch
     assert c["AnchoredProfileProfile"][2] + hits == 61773     # = all gapped-DP calls of the run (tests/golden/dp_mds42_calls.npz meta)
+    assert c["SeedOccurrenceList::construct"] == [2, 0]       # both genomes' seed occurrence lists (adapters/seams/sol_seam.cpp)
 
 
 @needs_cuda_bin
 @pytest.mark.gpu
-@pytest.mark.parametrize("binary,gap_seam", [(CUDA_BINARY, "0"), (CUDA_MH_BINARY, "0"), (CUDA_MH_BINARY, "1"), (CUDA_ALL_BINARY, "1")])
-def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, gap_seam):
+@pytest.mark.parametrize("binary,gap_seam,sol_seam", [(CUDA_BINARY, "0", "0"), (CUDA_MH_BINARY, "0", "0"), (CUDA_MH_BINARY, "1", "0"),
+                                                      (CUDA_ALL_BINARY, "1", "0"), (CUDA_ALL_BINARY, "1", "1")],
+                         ids=["dp", "dp+pmf", "dp+pmf+gaps", "dp+pmf+gaps+refine", "dp+pmf+gaps+refine+sol"])
+def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, gap_seam, sol_seam):
     """mauve_py_b200.buildIndex with a seam binary as $MAUVE_DIR/progressiveMauveStatic: sorted mer lists, anchors AND the gapped DP
     of every window (and, last case, the gap searches of recursive anchoring) on the device; the LUT is the reference's.  Then the
     binary on its own, from the FASTA files: byte-identical XMFA."""
@@ -313,6 +317,7 @@ def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, 
     os.symlink(binary, os.path.join(bindir, "progressiveMauveStatic"))
     monkeypatch.setenv("MAUVE_DIR", bindir)
     monkeypatch.setenv("MAUVE_CUDA_GAP_SEAM", gap_seam)
+    monkeypatch.setenv("MAUVE_CUDA_SOL_SEAM", sol_seam)
     t0 = time.time()
     got = mp.buildIndex(fas[0], fas[1])
     t1 = time.time()
@@ -328,4 +333,5 @@ def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, 
         assert c["MemHash::FindMatches"][0] >= (300 if gap_seam == "1" else 1)
     if binary == CUDA_ALL_BINARY:
         assert c["RefineW"][3] == 0 and c["AnchoredProfileProfile"][2] + c["RefineW"][2] == 61773
-    print("buildIndex %.1f s, standalone binary %.1f s (%s, gap seam %s)" % (t1 - t0, t2 - t1, os.path.basename(binary), gap_seam))
+        assert c["SeedOccurrenceList::construct"] == ([2, 0] if sol_seam == "1" else [0, 2])
+    print("buildIndex %.1f s, standalone binary %.1f s (%s, gap seam %s, sol seam %s)" % (t1 - t0, t2 - t1, os.path.basename(binary), gap_seam, sol_seam))
