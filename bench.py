@@ -10,7 +10,8 @@ extension and NCCL gather + merge of the match rows on rank 0) over the syntheti
 is Mbp/s with both genomes already resident in HBM; `e2e` is the same metric through the public
 C-ABI call mcu_find_mums with pinned HOST buffers (H2D + D2H inside the timed region).  N > 1 shards
 the SAME pair by a seed-ownership hash ("strong" scaling).  The gapped DP (GCUPS) and the HMM are reported
-in the `dp` / `hmm` objects of the same line.  Prints ONE JSON line on rank 0.
+in the `dp` / `hmm` objects of the same line; `buildindex` (N = 1) is BASELINE config 0 end to end: mauve.buildIndex on the MDS42
+pair, the reference's own binary timed beside ours, LUT checked against the golden one.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes as C
@@ -277,6 +278,68 @@ def measure_hmm(mp, synth, args):
             "value": sum(len(s) for s in sym) / (hms * 1e-3), "unit": "columns/s", "strings": len(sym), "device_ms": hms}
 
 
+def measure_buildindex(mp, args):
+    """BASELINE config 0 end to end: mauve.buildIndex on the MDS42 pair.  Reference arm = the reference's own progressiveMauve binary
+    (oracle/_ref, unmodified sources) + the LUT construction, on the box's host cores; ours = mauve_py_b200.buildIndex (sorted mer
+    lists + initial anchors on the device) driving the reference binary with the link-time seams (every gapped DP of the run, the gap
+    searches of recursive anchoring on the device).  The LUT is checked against the golden one minted by the
+    reference's own Python (tests/golden/mds42_lut.npz).  Wall-clock seconds; lower is better."""
+    import ast
+    import gzip
+    import hashlib
+    import shutil
+    from mauve_py_b200 import buildindex as B
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    ref_bin = os.path.join(ref_dir, "progressiveMauve")
+    ours_bin = next((os.path.join(ref_dir, n) for n in ("progressiveMauve_cuda_all", "progressiveMauve_cuda") if os.path.exists(os.path.join(ref_dir, n))), None)
+    if not os.path.exists(ref_bin) or ours_bin is None:
+        return {"unavailable": "oracle/_ref binaries not built (they need /root/reference at build time)"}
+    golden = os.path.join(ROOT, "tests", "golden")
+    z = np.load(os.path.join(golden, "mds42_lut.npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    work = tempfile.mkdtemp()
+    saved = {k: os.environ.get(k) for k in ("MAUVE_DIR", "MAUVE_CUDA_GAP_SEAM")}
+    try:
+        fas = []
+        for name in ("mds42_recoded", "mds42_full"):
+            fp = os.path.join(work, name + ".fa")
+            with gzip.open(os.path.join(golden, name + ".fa.gz"), "rb") as f, open(fp, "wb") as g:
+                shutil.copyfileobj(f, g)
+            fas.append(fp)
+        seqs = [B.getSeqFromFile(fp) for fp in fas]
+        # reference arm
+        t0 = time.perf_counter()
+        subprocess.run([ref_bin, "--output=" + os.path.join(work, "ref.xmfa"), fas[0], fas[1]], cwd=work, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, timeout=600, check=True)
+        ref_lut = B.lut_from_xmfa(os.path.join(work, "ref.xmfa"), seqs[0], seqs[1])
+        t_ref = time.perf_counter() - t0
+        for fp in fas:
+            if os.path.exists(fp + ".sslist"):
+                os.remove(fp + ".sslist")
+        # ours
+        bindir = os.path.join(work, "bin")
+        os.makedirs(bindir)
+        os.symlink(ours_bin, os.path.join(bindir, "progressiveMauveStatic"))
+        os.environ["MAUVE_DIR"] = bindir
+        os.environ["MAUVE_CUDA_GAP_SEAM"] = "1"
+        t0 = time.perf_counter()
+        lut = mp.buildIndex(fas[0], fas[1])
+        t_ours = time.perf_counter() - t0
+        ok = hashlib.sha1(lut.tobytes()).hexdigest() == meta["lut_sha1"] and hashlib.sha1(ref_lut.tobytes()).hexdigest() == meta["lut_sha1"]
+        return {"metric": "buildIndex wall seconds, MDS42 pair (BASELINE config 0)", "unit": "s", "higher_is_better": False,
+                "reference_s": t_ref, "ours_s": t_ours, "speedup": t_ref / t_ours if t_ours > 0 else None,
+                "lut": "identical to the golden LUT (3,981,477 entries)" if ok else "DIFFERENT",
+                "ours": "sorted mer lists + anchors on the device, %s (gapped DP, gap searches on the device)" % os.path.basename(ours_bin),
+                "reference": "oracle/_ref/progressiveMauve (unmodified sources) + LUT construction, 1 thread"}
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        shutil.rmtree(work, ignore_errors=True)
+
+
 _REAL_STDOUT = None
 
 
@@ -310,6 +373,7 @@ def main():
     ap.add_argument("--dp-regions", type=int, default=1536)
     ap.add_argument("--no-dp", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-buildindex", action="store_true", help="skip the MDS42 buildIndex end-to-end measurement (~1 minute of host time)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -507,6 +571,12 @@ def main():
             hmm = measure_hmm(mp, synth, args)
         except Exception as e:  # noqa: BLE001
             hmm = {"error": "%s: %s" % (type(e).__name__, e)}
+    bidx = None
+    if world == 1 and not args.no_cpu and not args.no_buildindex:
+        try:
+            bidx = measure_buildindex(mp, args)
+        except Exception as e:  # noqa: BLE001
+            bidx = {"error": "%s: %s" % (type(e).__name__, e)}
 
     line = {
         "metric": "Mbp/s seed+match+extend", "value": value, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -515,7 +585,7 @@ def main():
         "device_ms_per_step": dev_ms,
         "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": int(nbases), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * dte / args.steps, "api": "mcu_find_mums(host buffers)" if world == 1 else "mcu_session_upload + enumerate, NCCL all-reduce of the seed bitmap, finish, NCCL gather, mcu_session_merge"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "dp": dp, "hmm": hmm,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "dp": dp, "hmm": hmm, "buildindex": bidx,
     }
     emit(line)
     if world > 1:
