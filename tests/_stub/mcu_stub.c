@@ -70,3 +70,16 @@ int mcu_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, 
     return 0;
 }
 void mcu_free(void* p) { free(p); }
+
+/* sorted mer list (adapters/seams/filesml_seam.cpp, CudaDNAMemorySML.h) */
+long long orc_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out, uint64_t* mer_out);
+int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out, uint64_t* mer_out, uint32_t* packed_out, uint64_t* sml_len_out)
+{
+    const double t0 = stub_now();
+    long long r = orc_sml_build(seq, n, seed, pos_out, mer_out);
+    g_stub_seconds += stub_now() - t0;
+    (void)packed_out;
+    if (r < 0) return -3;
+    if (sml_len_out) *sml_len_out = (uint64_t)r;
+    return 0;
+}

@@ -246,7 +246,7 @@ def _align(binary, d, a, b, out, env=None):
 def _seam_counts(stderr):
     out = {}
     for l in stderr.splitlines():
-        if l.split(" seam:")[0] in ("AnchoredProfileProfile", "MemHash::FindMatches", "RefineW", "SeedOccurrenceList::construct"):
+        if l.split(" seam:")[0] in ("AnchoredProfileProfile", "MemHash::FindMatches", "RefineW", "SeedOccurrenceList::construct", "FileSML::Create"):
             out[l.split(" seam:")[0]] = [int(x) for x in l.replace(",", "").split() if x.isdigit()]
     return out
 
@@ -255,7 +255,7 @@ def _seam_counts(stderr):
 def test_seams_host_code_inside_the_reference_binary(tmp_path):
     """The link-time seams (mauve_py_b200/adapters/seams: all DP ranges of a window -> one CudaGlobalAlignBatch call;
     MemHash::FindMatches of two genomes -> mcu_find_mums; the DP of all windows of a RefineW call prefetched in one mcu_nw_batch
-    call) inside the unmodified reference objects align the MDS42 pair to the byte-identical XMFA, with EVERY ONE of the run's
+    call; FileSML::Create -> mcu_sml_build; SeedOccurrenceList::construct -> mcu_sol_build) inside the unmodified reference objects align the MDS42 pair to the byte-identical XMFA, with EVERY ONE of the run's
     61,773 gapped-DP calls answered by the device entry point.  Here, without a GPU, the device entry points are answered by the CPU restatement through an LD_PRELOAD
     stub (tests/_stub): this checks the seams' own host code -- range collection, profile order, path -> PWPath, output assembly,
     sequence extraction from progressiveMauve's gnRAWSequence objects, Match construction; the GPU suite runs the same binaries
@@ -295,6 +295,7 @@ def test_seams_host_code_inside_the_reference_binary(tmp_path):
     assert calls > 100 and hits > 19000 and misses == 0       # 19,967 windows of RefineFast: every GlobalAlign answered from the prefetch
     assert c["AnchoredProfileProfile"][2] + hits == 61773     # = all gapped-DP calls of the run (tests/golden/dp_mds42_calls.npz meta)
     assert c["SeedOccurrenceList::construct"] == [2, 0]       # both genomes' seed occurrence lists (adapters/seams/sol_seam.cpp)
+    assert c["FileSML::Create"] == [2, 0]                     # both `.sslist` files (adapters/seams/filesml_seam.cpp)
 
 
 @needs_cuda_bin
@@ -334,4 +335,5 @@ def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, 
     if binary == CUDA_ALL_BINARY:
         assert c["RefineW"][3] == 0 and c["AnchoredProfileProfile"][2] + c["RefineW"][2] == 61773
         assert c["SeedOccurrenceList::construct"] == ([2, 0] if sol_seam == "1" else [0, 2])
+        assert c["FileSML::Create"] == [2, 0]
     print("buildIndex %.1f s, standalone binary %.1f s (%s, gap seam %s, sol seam %s)" % (t1 - t0, t2 - t1, os.path.basename(binary), gap_seam, sol_seam))
