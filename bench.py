@@ -476,6 +476,42 @@ def main():
     dte = float(t.item())
     e2e_value = nbases / 1e6 / (dte / args.steps)
 
+    # ---- N > 1: gapped DP and HMM divided among the ranks (independent regions / strings, LPT; no collective on the data path) ----
+    # every rank reaches the two all-reduces below whatever happened in its own share, so a failure cannot leave the others waiting
+    dp_sharded = hmm_sharded = None
+    if world > 1 and not args.no_dp:
+        vals = [0.0, 0.0, 0.0, 0.0, 1.0]   # dp cells, hmm columns | dp ms, hmm ms | ok
+        try:
+            pairs = synth.dp_pairs(args.dp_regions, 100, 10000, seed=20261020)
+            mine = [pairs[i] for i in mdist.lpt_partition([len(x) * len(y) for x, y in pairs], world)[rank]]
+            if mine:
+                arrs = synth.dp_arrays(mine)
+                mp.libmems.nw_batch_arrays(*arrs)
+                res = mp.libmems.nw_batch_arrays(*arrs)
+                vals[0], vals[2] = float(res["stats"][0]), float(res["device_ms"])
+            sym = [synth.hmm_string(len(p_[0]), seed=i, block=300) for i, p_ in enumerate(synth.dp_pairs(512, 100, 10000, seed=20261020))] * 64
+            smine = [sym[i] for i in mdist.lpt_partition([len(x) for x in sym], world)[rank]]
+            if smine:
+                params = mp.libmems.hmm_params(0.5, 1e-5, 1e-9, 0.7)
+                mp.run_batch(smine, params, True)
+                _p, _q, hms = mp.run_batch(smine, params, True)
+                vals[1], vals[3] = float(sum(len(x) for x in smine)), float(hms)
+        except Exception as e:  # noqa: BLE001
+            print("rank %d: sharded DP/HMM measurement failed: %s: %s" % (rank, type(e).__name__, e), file=sys.stderr)
+            vals = [0.0, 0.0, 0.0, 0.0, 0.0]
+        tsum = torch.tensor(vals[:2], dtype=torch.float64, device="cuda")
+        tmax = torch.tensor([vals[2], vals[3], -vals[4]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum, tmax = tsum.tolist(), tmax.tolist()
+        if tmax[2] == -1.0 and tmax[0] > 0 and tmax[1] > 0:   # every rank succeeded
+            dp_sharded = {"metric": "GCUPS gapped DP (full-matrix cells, NWSmall-exact paths)", "value": tsum[0] / (tmax[0] * 1e-3) / 1e9, "unit": "GCUPS",
+                          "cells": tsum[0], "device_ms": tmax[0], "sharding": "regions divided among %d ranks by LPT on lenA*lenB; device ms = max over ranks" % world}
+            hmm_sharded = {"metric": "HomologyHMM columns/s (bfloat-faithful)", "value": tsum[1] / (tmax[1] * 1e-3), "unit": "columns/s",
+                           "device_ms": tmax[1], "sharding": "strings divided among %d ranks by LPT on length; device ms = max over ranks" % world}
+        else:
+            dp_sharded = hmm_sharded = {"error": "a rank failed (see stderr)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -541,7 +577,7 @@ def main():
 
     # ---- CPU baseline on a bounded sample ---------------------------------------------------------
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # rank 0 at N = 1 only (the reference arm, --impl reference, covers every N)
         try:
             chk, kind = cpu_checker()
             sa, sb = cpu_sample(a, b, int(args.cpu_sample_mbp * 1e6))
@@ -561,7 +597,9 @@ def main():
 
     # ---- gapped DP + HMM (secondary metrics of BASELINE.json) ----------------------------------------
     dp = hmm = None
-    if not args.no_dp:
+    if world > 1:
+        dp, hmm = dp_sharded, hmm_sharded
+    elif not args.no_dp:
         # secondary metrics must never cost the headline line: a failure is reported inside the object
         try:
             dp = measure_dp(mp, synth, args)

@@ -75,3 +75,96 @@ def gather_rows(rows: torch.Tensor, dst: int = 0, group=None):
     if rows.shape[0] > 0:
         dist.send(rows, dst=dst, group=group)
     return None
+
+
+# ---- gapped DP and HMM: independent regions / strings, no collective on the data path --------------------------------
+def lpt_partition(costs, world):
+    """Longest-processing-time-first assignment of independent work items to `world` ranks: items in descending cost order, each to
+    the least loaded rank (ties: lowest rank).  Deterministic, so every rank derives the same plan from the same costs.
+    Returns `world` ascending index lists."""
+    import heapq
+    order = sorted(range(len(costs)), key=lambda i: (-int(costs[i]), i))
+    heap = [(0, r) for r in range(world)]
+    parts = [[] for _ in range(world)]
+    for i in order:
+        load, r = heapq.heappop(heap)
+        parts[r].append(i)
+        heapq.heappush(heap, (load + int(costs[i]), r))
+    return [sorted(p) for p in parts]
+
+
+def gather_bytes(payload: bytes, dst: int = 0, group=None, device=None):
+    """variable-length gather of one byte string per rank to `dst` (list in rank order there, None elsewhere); the same counts +
+    point-to-point pattern as gather_rows, on `device` (cuda for nccl, cpu for gloo)"""
+    import numpy as np
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if device is None:
+        device = torch.device("cuda") if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    buf = torch.from_numpy(np.frombuffer(payload, dtype=np.uint8).copy()).to(device)
+    n = torch.tensor([buf.numel()], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    if rank == dst:
+        parts = [torch.empty(c, dtype=torch.uint8, device=device) for c in counts]
+        parts[dst] = buf
+        reqs = [dist.irecv(parts[r], src=r, group=group) for r in range(world) if r != dst and counts[r] > 0]
+        for q in reqs:
+            q.wait()
+        return [p.cpu().numpy().tobytes() for p in parts]
+    if buf.numel() > 0:
+        dist.send(buf, dst=dst, group=group)
+    return None
+
+
+def align_sharded(pairs, rank, world, group=None, align=None):
+    """muscle::GlobalAlign for a batch of region pairs divided among the ranks by LPT on lenA * lenB.  Every rank holds the
+    whole `pairs` list (like the genomes), aligns its share on its GPU and ships (lengths, scores, edges) to rank 0, which returns
+    the PWPaths in input order; other ranks return None.  `align` defaults to libmems.GlobalAlignBatch."""
+    import numpy as np
+    from . import libmems
+    align = align or libmems.GlobalAlignBatch
+    plan = lpt_partition([len(a) * len(b) for a, b in pairs], world)
+    mine = plan[rank]
+    paths = align([pairs[i] for i in mine]) if mine else []
+    lens = np.array([len(p.edges) for p in paths], dtype=np.int64)
+    scores = np.array([p.score for p in paths], dtype=np.int64)
+    payload = lens.tobytes() + scores.tobytes() + b"".join(p.edges for p in paths)
+    if world == 1:
+        return paths
+    got = gather_bytes(payload, 0, group)
+    if rank != 0:
+        return None
+    out = [None] * len(pairs)
+    for r, blob in enumerate(got):
+        k = len(plan[r])
+        ln = np.frombuffer(blob[:8 * k], dtype=np.int64)
+        sc = np.frombuffer(blob[8 * k:16 * k], dtype=np.int64)
+        pos = 16 * k
+        for j, i in enumerate(plan[r]):
+            out[i] = libmems.PWPath(blob[pos:pos + int(ln[j])], int(sc[j]))
+            pos += int(ln[j])
+    return out
+
+
+def hmm_sharded(sequences, params, rank, world, group=None, run_batch=None):
+    """run() of the HomologyHMM for a batch of column strings divided among the ranks by LPT on their lengths; rank 0 returns the
+    H/N predictions in input order, other ranks None.  `run_batch` defaults to libmems.run_batch."""
+    from . import libmems
+    run_batch = run_batch or libmems.run_batch
+    plan = lpt_partition([len(s) for s in sequences], world)
+    mine = plan[rank]
+    preds = run_batch([sequences[i] for i in mine], params) if mine else []
+    if world == 1:
+        return preds
+    got = gather_bytes(b"".join(preds), 0, group)
+    if rank != 0:
+        return None
+    out = [None] * len(sequences)
+    for r, blob in enumerate(got):
+        pos = 0
+        for i in plan[r]:
+            out[i] = blob[pos:pos + len(sequences[i])]
+            pos += len(sequences[i])
+    return out

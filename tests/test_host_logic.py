@@ -94,6 +94,68 @@ def test_gather_rows_gloo(world):
     assert got == expect
 
 
+def _shard_worker(rank, world, port, q):
+    """DP regions and HMM strings divided among ranks (LPT), results gathered on rank 0: the plumbing of dist.align_sharded /
+    dist.hmm_sharded with the CPU restatement standing in for the device calls (tests only)"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import torch.distributed as dist
+    import _oracle
+    from mauve_py_b200 import dist as mdist, libmems, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        orc = _oracle.oracle_checker()
+        pairs = synth.dp_pairs(23, 30, 400, seed=4)
+
+        def align(ps):
+            return [libmems.PWPath(*orc.nw_align(a, b)) for a, b in ps]
+
+        params = orc.hmm_params(0.5, 1e-5, 1e-9, 0.7)
+        strings = [synth.hmm_string(50 + 37 * i, seed=i) for i in range(11)] + [b""]
+
+        def run_batch(ss, p):
+            return [orc.hmm_run(s, p)[0] if len(s) else b"" for s in ss]
+
+        paths = mdist.align_sharded(pairs, rank, world, align=align)
+        preds = mdist.hmm_sharded(strings, params, rank, world, run_batch=run_batch)
+        if rank == 0:
+            q.put(([(p.edges, p.score) for p in paths], preds))
+        else:
+            assert paths is None and preds is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_dp_and_hmm_sharding_gloo(world, orc):
+    import torch.multiprocessing as tmp
+    from mauve_py_b200 import dist as mdist, synth
+    # the plan: every item exactly once, heaviest items spread first, identical on every rank
+    costs = [5, 100, 7, 100, 3, 50, 1]
+    plan = mdist.lpt_partition(costs, world)
+    assert sorted(i for p in plan for i in p) == list(range(len(costs))) and plan == mdist.lpt_partition(costs, world)
+    loads = [sum(costs[i] for i in p) for p in plan]
+    assert max(loads) - min(loads) <= max(costs)
+    assert mdist.lpt_partition([], world) == [[] for _ in range(world)]
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    paths, preds = q.get(timeout=180)
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    pairs = synth.dp_pairs(23, 30, 400, seed=4)
+    assert paths == [orc.nw_align(a, b) for a, b in pairs]
+    params = orc.hmm_params(0.5, 1e-5, 1e-9, 0.7)
+    strings = [synth.hmm_string(50 + 37 * i, seed=i) for i in range(11)] + [b""]
+    assert preds == [orc.hmm_run(s, params)[0] if len(s) else b"" for s in strings]
+
+
 def test_match_list_file_format_round_trips_through_the_reference(refc):
     """--mums / --match-input text format (LM/MatchList.h:526-662): what we write, the reference's ReadList accepts with the
     same rows; what the reference's WriteList prints, we read; both writers agree byte for byte except the match-id column."""
