@@ -102,3 +102,31 @@ def test_dropin_hmm_lcb_sized_string_is_bit_faithful():
     rc, kv, out = _run("hmm", 3000000, 5)
     assert rc == 0 and kv["RESULT"] == "identical" and kv["differing_columns"] == "0" and kv["threshold_columns"] == "0", out
     assert float(kv["max_rel_err"]) < 1e-12, out
+
+
+@needs_bin
+def test_dropin_adapters_host_code_through_the_stub(tmp_path):
+    """the adapters' own host code (sequence extraction, Match construction, PWPath conversion) next to the reference classes on a
+    machine without a GPU: the device entry points are answered by the CPU restatement through an LD_PRELOAD stub (tests/_stub).
+    The GPU suite runs the same binary against the real library."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: the GPU tests above run this binary against the real library")
+    import _emu
+    env = dict(os.environ, LD_PRELOAD=_emu.stub_library())
+
+    def run(*args):
+        r = subprocess.run([BIN] + [str(a) for a in args], capture_output=True, text=True, timeout=600, env=env)
+        return r.returncode, dict(l.split(" ", 1) for l in r.stdout.splitlines() if " " in l), r.stdout + r.stderr
+
+    a, b = synth.small_pair(200000, seed=52, snp=0.02, n_inv=3)
+    _fasta(tmp_path / "a.fa", "a", a)
+    _fasta(tmp_path / "b.fa", "b", b)
+    for w, r in ((15, 3), (21, 0)):
+        rc, kv, out = run("sml", tmp_path / "a.fa", w, r)
+        assert rc == 0 and kv["RESULT"] == "identical", out
+    for args in ((15, 3), (9, 0, "memhash")):
+        rc, kv, out = run("mums", tmp_path / "a.fa", tmp_path / "b.fa", *args)
+        assert rc == 0 and kv["RESULT"] == "identical" and int(kv["matches_cuda"]) > 100, out
+    rc, kv, out = run("dp", 40, 7)
+    assert rc == 0 and kv["RESULT"] == "identical", out
