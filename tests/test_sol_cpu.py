@@ -111,6 +111,30 @@ def test_device_value_functions_sol(orc, w, rank):
         assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), (len(s), w, np.flatnonzero(x != y)[:5])
 
 
+@pytest.mark.parametrize("key_bytes", [4, 8])
+def test_device_value_functions_run_lengths_random_sorted_lists(key_bytes):
+    """sol_run_length on arbitrary sorted key arrays: runs of every length around the walk limit (8), runs touching both ends of the
+    list, one run spanning the whole list; strand bits vary inside a run as they do in a real list"""
+    import _properties as P
+    rng = np.random.default_rng(17 + key_bytes)
+    L = 13
+    for trial in range(40):
+        npos = int(rng.integers(1, 3000))
+        nkeys = int(rng.integers(1, max(2, npos // int(rng.integers(1, 40)))))
+        top = (1 << 30) if key_bytes == 4 else (1 << 50)
+        canon = np.sort(rng.choice(rng.integers(0, top, size=nkeys), size=npos))
+        if trial == 0:
+            canon[:] = canon[0]
+        keys = (canon.astype(np.uint64) << np.uint64(2)) | rng.integers(0, 2, size=npos).astype(np.uint64)
+        keys = np.sort(keys)
+        vals = rng.permutation(npos).astype(np.uint32)
+        n = npos + L - 1
+        out = np.zeros(n, dtype=np.float32)
+        _emu.emu().emu_sol(keys.ctypes.data, vals.ctypes.data, npos, n, L, key_bytes, out.ctypes.data)
+        want = P.sol_expected(vals, keys, (1 << 64) - 4, n, L)
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), (trial, npos, nkeys)
+
+
 def test_device_value_functions_sol_golden(orc):
     z, cases = _small()
     for c in cases:
