@@ -581,6 +581,9 @@ def main():
                          "achieved": step_bytes / (dev_ms * 1e-3) / 1e9 if dev_ms > 0 else 0.0,
                          "frac": (step_bytes / (dev_ms * 1e-3) / 1e9 / peak) if dev_ms > 0 else 0.0,
                          "bucketed_bytes_per_base": b_bucket if bucketed else None,
+                         # the compulsory lower bound the reference itself quotes (LM/DNAMemorySML.h:23-24): not to be conflated
+                         "compulsory_bytes_per_base": 4.25,
+                         "compulsory_frac": (4.25 * nbases / (dev_ms * 1e-3) / 1e9 / peak) if dev_ms > 0 else 0.0,
                          "stage_ms": {"pack": float(stage[0]), "seedgen": float(stage[1]), "sort": float(stage[2]), "join": float(stage[3]),
                                       "extend": float(stage[4]), "order": float(stage[5])},
                          "kernel_ms": {"bk_hist1": float(stage[8]), "bk_scatter1": float(stage[9]), "bk_hist2": float(stage[10]),
