@@ -58,7 +58,7 @@ for n in mds42_recoded mds42_full; do zcat tests/golden/$n.fa.gz > $W/$n.fa; don
       ( cd $W && MAUVE_CUDA_GAP_SEAM=1 MAUVE_CUDA_SOL_SEAM=$sol MAUVE_CUDA_SEAM_REPORT=1 timeout 600 "$OLDPWD/oracle/_ref/$bin" --output=$bin.$sol.xmfa mds42_recoded.fa mds42_full.fa > $bin.$sol.log 2> $bin.$sol.err )
       rc=$?
       e=$(date +%s.%N)
-      echo "== $bin sol_seam=$sol rc=$rc wall_s=$(echo "$e - $s" | bc) xmfa_sha1=$(grep -v '^#' $W/$bin.$sol.xmfa | sed -E 's/^(> *[^ ]+ [^ ]+) .*/\1/' | sha1sum | cut -c1-40)"
+      echo "== $bin sol_seam=$sol rc=$rc wall_s=$(awk -v a="$s" -v b="$e" 'BEGIN{printf "%.2f", b - a}') xmfa_sha1=$(grep -v '^#' $W/$bin.$sol.xmfa | sed -E 's/^(> *[^ ]+ [^ ]+) .*/\1/' | sha1sum | cut -c1-40)"
       grep -a "seam:" $W/$bin.$sol.err
     done
   done
