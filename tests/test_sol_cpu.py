@@ -6,6 +6,7 @@
     the arithmetic the kernels execute is checked here, the kernels' indexing on the GPU (tests/test_zzzz_next_rows_gpu.py).
 """
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -13,6 +14,7 @@ import pytest
 import _emu
 import _golden
 import _oracle
+from _bins import NEXT_BIN, run_next, write_fasta
 from mauve_py_b200 import synth
 
 
@@ -166,25 +168,6 @@ def test_device_value_functions_anchor_scores(orc):
 
 
 # ---- the C++ adapters' host code next to the reference classes (device calls answered by the restatement) --------------------
-import os  # noqa: E402
-import subprocess  # noqa: E402
-
-NEXT_BIN = os.path.join(_oracle.ROOT, "oracle", "_ref", "dropin_check_next")
-
-
-def run_next(args, env=None, timeout=900):
-    r = subprocess.run([NEXT_BIN] + [str(a) for a in args], capture_output=True, text=True, timeout=timeout, env=env)
-    kv = dict(l.split(" ", 1) for l in r.stdout.splitlines() if " " in l)
-    return r.returncode, kv, r.stdout + r.stderr
-
-
-def write_fasta(path, name, seq):
-    with open(path, "wb") as f:
-        f.write(b">" + name.encode() + b"\n")
-        for i in range(0, len(seq), 80):
-            f.write(seq[i:i + 80] + b"\n")
-
-
 @pytest.mark.skipif(not os.path.exists(NEXT_BIN), reason="oracle/_ref/dropin_check_next not built (needs /root/reference at build time)")
 def test_adapters_host_code_next_to_the_reference_classes(tmp_path):
     """CudaSeedOccurrenceList / CudaPairwiseAnchorScores (mauve_py_b200/adapters) inside the reference's own flow

@@ -13,7 +13,7 @@ import _golden
 import _oracle
 import _properties as P
 from mauve_py_b200 import synth
-from test_sol_cpu import NEXT_BIN, run_next, write_fasta
+from _bins import NEXT_BIN, run_next, write_fasta
 
 pytestmark = pytest.mark.gpu
 
