@@ -1,7 +1,7 @@
 #!/bin/bash
-# One gpurun call that collects everything a round needs from the GPU box (about 12-15 minutes on one B200):
+# One gpurun call that collects everything a round needs from the GPU box (about 20-25 minutes on one B200):
 #
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_session.sh'
 #
 # Everything lands under gpurun_out/ (merged back by gpurun); summarise what is to be judged into profiles/.
 #   pytest_gpu.log        python -m pytest tests -m gpu (no -x: one failure must not hide the rest), with durations
@@ -11,6 +11,7 @@
 #   sol.ncu-rep           ncu --set full of the seed occurrence list / anchor score kernels (8f-2)
 #   seams.log             reference binary vs the seam binaries on the MDS42 pair (wall seconds, XMFA sha1, seam reports)
 #   dropin*.log           the C++ drop-in checks with their own timings
+#   config5.json, config4.jsonl   BASELINE configs 5 (50,000 regions) and 4 (1 Gbp weight sweep)
 set -u
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 mkdir -p gpurun_out
@@ -68,5 +69,8 @@ rm -rf $W
 timeout 300 oracle/_ref/dropin_check gaps 5000 3 > gpurun_out/dropin_gaps.log 2>&1
 timeout 300 oracle/_ref/dropin_check dp 400 3 > gpurun_out/dropin_dp.log 2>&1
 timeout 300 oracle/_ref/dropin_check hmm 5000000 9 > gpurun_out/dropin_hmm.log 2>&1
+# BASELINE configs 4 and 5 at (or near) full size
+timeout 500 python tools/config5_dp.py --regions 50000 > gpurun_out/config5.json 2> gpurun_out/config5.err
+timeout 900 python tools/config4_sweep.py --gbp 1.0 --reps 1 > gpurun_out/config4.jsonl 2> gpurun_out/config4.err
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/nvidia_smi.csv 2>&1
 echo done
