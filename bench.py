@@ -218,7 +218,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "Mbp/s seed+match+extend", "value": value, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "config": config_dict(args, weight, seed),
-        "cpu_baseline": {"value": value, "unit": "Mbp/s", "cores": 1, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mbp/s", "cores": 1, "kind": kind, "sample": sample, "cores_on_box": os.cpu_count(),
+                         "projection_if_embarrassingly_parallel": value * (os.cpu_count() or 1),
+                         "projection_note": "PROJECTION, not a measurement: the reference has no threads; value x cores_on_box"},
         "e2e": {"value": value, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -605,6 +607,8 @@ def main():
             if not same:
                 print("PARITY FAILURE on the CPU sample", file=sys.stderr)
             cpu = {"value": (len(sa) + len(sb)) / 1e6 / dtc, "unit": "Mbp/s", "cores": 1, "kind": kind, "parity": "identical" if same else "FAILED",
+                   "cores_on_box": os.cpu_count(), "projection_if_embarrassingly_parallel": (len(sa) + len(sb)) / 1e6 / dtc * (os.cpu_count() or 1),
+                   "projection_note": "PROJECTION, not a measurement: the reference has no threads; value x cores_on_box",
                    "sample": "leading %.1f Mbp of both genomes (%d matches, GPU result %s); single thread: the reference has no threads"
                              % (args.cpu_sample_mbp, rows.shape[0], "identical" if same else "DIFFERENT")}
         except Exception as e:  # noqa: BLE001
