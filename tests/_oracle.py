@@ -3,7 +3,7 @@
 `oracle()`  -> oracle/libmauve_oracle.so : our C restatement (oracle/mauve_oracle.c)
 `ref()`     -> oracle/_ref/libmauve_ref.so : the reference's own sources compiled in place
                (only present where oracle/Makefile.ref was run; tests skip when absent).
-Nothing under mauve_b200/ imports this module.
+Nothing under mauve_py_b200/ imports this module.
 """
 import ctypes as C
 import os
