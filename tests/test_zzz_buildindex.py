@@ -243,6 +243,22 @@ def _align(binary, d, a, b, out, env=None):
     return subprocess.run([binary, "--output=" + out, a, b], cwd=d, capture_output=True, text=True, env=env)
 
 
+def _spiked_pair(d):
+    """a 80 kbp pair with an inversion, single N and runs of N in both genomes: a.fa, b.fa in directory d.  The N columns make some DP
+    ranges / refine windows fall outside the integer kernel's form, so the seams' fall-back to the reference's own code is exercised"""
+    from mauve_py_b200 import synth
+    a, b = synth.small_pair(80000, seed=77, snp=0.03, n_inv=1)
+    rng = np.random.default_rng(5)
+    for name, s_ in (("a", a), ("b", b)):
+        s_ = bytearray(s_)
+        for i in rng.integers(0, len(s_), 60):
+            s_[i] = ord("N")
+        for i in rng.integers(0, len(s_) - 30, 5):
+            s_[i:i + 30] = b"N" * 30
+        with open(os.path.join(d, name + ".fa"), "wb") as f:
+            f.write(b">" + name.encode() + b"\n" + b"\n".join(bytes(s_[i:i + 70]) for i in range(0, len(s_), 70)) + b"\n")
+
+
 def _seam_counts(stderr):
     out = {}
     for l in stderr.splitlines():
@@ -266,25 +282,25 @@ def test_seams_host_code_inside_the_reference_binary(tmp_path):
     import _emu
     from mauve_py_b200 import synth
     d = str(tmp_path)
-    a, b = synth.small_pair(60000, seed=33, snp=0.03, n_inv=1)
-    for name, s_ in (("a", a), ("b", b)):
-        with open(os.path.join(d, name + ".fa"), "wb") as f:
-            f.write(b">" + name.encode() + b"\n" + b"\n".join(s_[i:i + 70] for i in range(0, len(s_), 70)) + b"\n")
+    _spiked_pair(d)
     r = _align(CUDA_BINARY, d, "a.fa", "b.fa", "x.xmfa")
     assert r.returncode == 3 and "no usable CUDA device" in (r.stdout + r.stderr)
     r = _align(CUDA_MH_BINARY, d, "a.fa", "b.fa", "x.xmfa")
     assert r.returncode != 0 and "no usable CUDA device" in (r.stdout + r.stderr)
-    env = dict(os.environ, LD_PRELOAD=_emu.stub_library(), MAUVE_CUDA_SEAM_REPORT="1")
+    env = dict(os.environ, LD_PRELOAD=_emu.stub_library(), MAUVE_CUDA_SEAM_REPORT="1", MAUVE_CUDA_GAP_SEAM="1", MAUVE_CUDA_SOL_SEAM="1")
     assert _align(BINARY, d, "a.fa", "b.fa", "ref.xmfa").returncode == 0
-    r = _align(CUDA_BINARY, d, "a.fa", "b.fa", "dp.xmfa", env)
-    assert r.returncode == 0 and _xmfa_body_sha1(os.path.join(d, "dp.xmfa")) == _xmfa_body_sha1(os.path.join(d, "ref.xmfa")), r.stderr[-500:]
-    c = _seam_counts(r.stderr)["AnchoredProfileProfile"]
-    assert c[0] >= 1 and c[1] == c[2] > 10
+    for binary in (CUDA_BINARY, CUDA_ALL_BINARY):
+        r = _align(binary, d, "a.fa", "b.fa", "seam.xmfa", env)
+        assert r.returncode == 0 and _xmfa_body_sha1(os.path.join(d, "seam.xmfa")) == _xmfa_body_sha1(os.path.join(d, "ref.xmfa")), r.stderr[-500:]
+        c = _seam_counts(r.stderr)
+        calls, ranges, device = c["AnchoredProfileProfile"]
+        assert calls >= 1 and 10 < device < ranges           # ranges with an N column take the reference's ProfileProfile
+        if binary == CUDA_ALL_BINARY:
+            assert c["RefineW"][2] > 10 and c["RefineW"][3] > 0   # windows with an N are not prefetched: the reference's NWSmall aligns them
+            assert c["MemHash::FindMatches"][0] > 10 and c["FileSML::Create"] == [2, 0] and c["SeedOccurrenceList::construct"] == [2, 0]
     # BASELINE config 1 with every seam on: initial anchors, the gap searches of recursive anchoring, the DP of every window
     _lut, meta = _golden()
     fas = _fastas(tmp_path)
-    env["MAUVE_CUDA_GAP_SEAM"] = "1"
-    env["MAUVE_CUDA_SOL_SEAM"] = "1"
     r = _align(CUDA_ALL_BINARY, d, os.path.basename(fas[0]), os.path.basename(fas[1]), "cuda.xmfa", env)
     assert r.returncode == 0, r.stderr[-500:]
     assert _xmfa_body_sha1(os.path.join(d, "cuda.xmfa")) == meta["xmfa_body_sha1"]
@@ -336,4 +352,11 @@ def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, 
         assert c["RefineW"][3] == 0 and c["AnchoredProfileProfile"][2] + c["RefineW"][2] == 61773
         assert c["SeedOccurrenceList::construct"] == ([2, 0] if sol_seam == "1" else [0, 2])
         assert c["FileSML::Create"] == [2, 0]
+    # a pair with N columns: part of the DP falls back to the reference's code, the alignment stays the reference's
+    d2 = os.path.join(str(tmp_path), "spiked")
+    os.makedirs(d2)
+    _spiked_pair(d2)
+    assert _align(BINARY, d2, "a.fa", "b.fa", "ref.xmfa").returncode == 0
+    r = _align(binary, d2, "a.fa", "b.fa", "seam.xmfa", env)
+    assert r.returncode == 0 and _xmfa_body_sha1(os.path.join(d2, "seam.xmfa")) == _xmfa_body_sha1(os.path.join(d2, "ref.xmfa")), r.stderr[-500:]
     print("buildIndex %.1f s, standalone binary %.1f s (%s, gap seam %s, sol seam %s)" % (t1 - t0, t2 - t1, os.path.basename(binary), gap_seam, sol_seam))
