@@ -316,9 +316,9 @@ def test_seams_host_code_inside_the_reference_binary(tmp_path):
 
 @needs_cuda_bin
 @pytest.mark.gpu
-@pytest.mark.parametrize("binary,gap_seam,sol_seam", [(CUDA_BINARY, "0", "0"), (CUDA_MH_BINARY, "0", "0"), (CUDA_MH_BINARY, "1", "0"),
+@pytest.mark.parametrize("binary,gap_seam,sol_seam", [(CUDA_BINARY, "0", "0"), (CUDA_MH_BINARY, "1", "0"),
                                                       (CUDA_ALL_BINARY, "1", "0"), (CUDA_ALL_BINARY, "1", "1")],
-                         ids=["dp", "dp+pmf", "dp+pmf+gaps", "dp+pmf+gaps+refine", "dp+pmf+gaps+refine+sol"])
+                         ids=["dp", "dp+pmf+gaps", "dp+pmf+gaps+refine+sml", "dp+pmf+gaps+refine+sml+sol"])
 def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, gap_seam, sol_seam):
     """mauve_py_b200.buildIndex with a seam binary as $MAUVE_DIR/progressiveMauveStatic: sorted mer lists, anchors AND the gapped DP
     of every window (and, last case, the gap searches of recursive anchoring) on the device; the LUT is the reference's.  Then the
