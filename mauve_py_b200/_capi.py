@@ -24,7 +24,7 @@ SYMBOLS = [
     "mcu_session_enumerate", "mcu_session_uniq_bitmap", "mcu_session_finish", "mcu_session_merge",
     "mcu_session_match_count", "mcu_session_download", "mcu_session_matches_device",
     "mcu_session_launch_count", "mcu_merge_matches",
-    "mcu_nw_batch", "mcu_nw_last_stats", "mcu_hmm_params", "mcu_hmm_batch", "mcu_sol_build", "mcu_anchor_scores",
+    "mcu_nw_batch", "mcu_nw_batch_wild", "mcu_nw_last_stats", "mcu_hmm_params", "mcu_hmm_batch", "mcu_sol_build", "mcu_anchor_scores",
     "mcu_test_sort_pairs", "mcu_test_int32_peak",
 ]
 
@@ -87,6 +87,7 @@ def lib():
     L.mcu_session_launch_count.restype = u64
     L.mcu_merge_matches.argtypes = [vp, u64, i32, C.POINTER(C.POINTER(Match)), C.POINTER(u64), C.POINTER(u64)]
     L.mcu_nw_batch.argtypes = [u64, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
+    L.mcu_nw_batch_wild.argtypes = [u64, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_float)]
     L.mcu_nw_last_stats.argtypes = [vp]
     L.mcu_nw_last_stats.restype = None
     L.mcu_hmm_params.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, vp]

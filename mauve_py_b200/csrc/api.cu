@@ -468,6 +468,14 @@ int mcu_hmm_batch(uint64_t n, const char* sym, const uint64_t* off, const double
     return hmm_batch(n, sym, off, params, pred_out, post_out, device_ms);
 }
 
+int mcu_nw_batch_wild(uint64_t n, const char* a, const uint64_t* a_off, const char* b, const uint64_t* b_off, const uint64_t* path_off,
+                      char* path_out, uint32_t* path_len, float* score, float* device_ms)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    return nw_batch_wild(n, a, a_off, b, b_off, path_off, path_out, path_len, score, device_ms);
+}
+
 // ---- seed occurrence list + anchor scores (sol.cu) ------------------------------------------------
 int mcu_sol_build(const char* seq, uint64_t n, uint64_t seed, float* freq_out)
 {

@@ -11,6 +11,10 @@ int nw_batch(u64 n, const char* a, const u64* a_off, const char* b, const u64* b
 // [3] sub-batches, [4] traceback bytes
 void nw_last_stats(u64* out5);
 
+// NWSmall in the reference's float arithmetic for regions with DNA wildcard columns (dpwild.cu): one thread per region
+int nw_batch_wild(u64 n, const char* a, const u64* a_off, const char* b, const u64* b_off, const u64* path_off, char* path_out, u32* path_len,
+                  float* score, float* device_ms);
+
 // register-resident add/max microbenchmark: Gops/s of thread-level INT32 instructions the device sustains (DP roofline denominator)
 int int32_peak(double* gops_out, float* ms_out);
 

@@ -24,7 +24,7 @@ from ._capi import CODING_SEED, SOLID_SEED, McuError, check, lib
 __all__ = [
     "CODING_SEED", "SOLID_SEED", "McuError", "getSeed", "getSolidSeed", "getDefaultSeedWeight", "getSeedLength", "getSeedWeight",
     "bmer", "DNAMemorySML", "Match", "MatchList", "MemHash", "PairwiseMatchFinder", "AnchorSession", "merge_matches",
-    "PWPath", "GlobalAlign", "GlobalAlignBatch", "Params", "getAdaptedHoxdMatrixParameters", "adaptToPercentIdentity",
+    "PWPath", "GlobalAlign", "GlobalAlignBatch", "GlobalAlignBatchWild", "Params", "getAdaptedHoxdMatrixParameters", "adaptToPercentIdentity",
     "run", "run_batch", "sort_pairs", "SeedOccurrenceList", "GetPairwiseAnchorScore", "anchor_scores", "hoxd_matrix",
 ]
 
@@ -512,6 +512,29 @@ def nw_batch_arrays(a, a_off, b, b_off):
     stats = np.zeros(5, dtype=np.uint64)
     lib().mcu_nw_last_stats(stats.ctypes.data)
     return {"path": path, "path_off": path_off, "path_len": path_len[:n], "score": score[:n], "device_ms": float(ms.value), "stats": stats}
+
+
+def GlobalAlignBatchWild(pairs):
+    """muscle::GlobalAlign for (a, b) pairs whose sequences may contain DNA wildcards (mcu_nw_batch_wild: the reference's float
+    arithmetic, one thread per region); PWPath.score is the reference's float score."""
+    n = len(pairs)
+    if n == 0:
+        return []
+    a_off = np.zeros(n + 1, dtype=np.uint64)
+    b_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(np.fromiter((len(p[0]) for p in pairs), dtype=np.uint64, count=n), out=a_off[1:])
+    np.cumsum(np.fromiter((len(p[1]) for p in pairs), dtype=np.uint64, count=n), out=b_off[1:])
+    a = np.frombuffer(b"".join(bytes(p[0]) for p in pairs) or b"\0", dtype=np.uint8)
+    b = np.frombuffer(b"".join(bytes(p[1]) for p in pairs) or b"\0", dtype=np.uint8)
+    path_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum((a_off[1:] - a_off[:-1]) + (b_off[1:] - b_off[:-1]), out=path_off[1:])
+    path = np.zeros(max(int(path_off[-1]), 1), dtype=np.uint8)
+    path_len = np.zeros(n, dtype=np.uint32)
+    score = np.zeros(n, dtype=np.float32)
+    ms = C.c_float(0)
+    check(lib().mcu_nw_batch_wild(n, a.ctypes.data, a_off.ctypes.data, b.ctypes.data, b_off.ctypes.data, path_off.ctypes.data,
+                                  path.ctypes.data, path_len.ctypes.data, score.ctypes.data, C.byref(ms)))
+    return [PWPath(path[int(path_off[i]):int(path_off[i]) + int(path_len[i])].tobytes(), float(score[i])) for i in range(n)]
 
 
 def GlobalAlign(a, b) -> PWPath:

@@ -12,7 +12,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "mauve_py_b200", "csrc")
 OUT = os.path.join(ROOT, "tests", "_emu", "libmcu_emu.so")
-SOURCES = ["sol.cu", "anchorcols.cu"]
+SOURCES = ["sol.cu", "dpwild.cu"]
 
 _lib = None
 
@@ -35,6 +35,8 @@ def emu():
     L.emu_sol.restype = None
     L.emu_anchor_scores.argtypes = [vp, vp, vp, vp, vp, u64, vp, C.c_int, vp]
     L.emu_anchor_scores.restype = None
+    L.emu_nw_wild.argtypes = [C.c_char_p, C.c_uint, C.c_char_p, C.c_uint, vp, vp]
+    L.emu_nw_wild.restype = C.c_longlong
     _lib = L
     return L
 

@@ -56,6 +56,8 @@ def oracle(build=True):
         lib.orc_pack.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p]
         lib.orc_packed_words.restype = C.c_uint64
         lib.orc_packed_words.argtypes = [C.c_uint64]
+        lib.orc_nw_align_f.restype = C.c_longlong
+        lib.orc_nw_align_f.argtypes = [C.c_char_p, C.c_uint, C.c_char_p, C.c_uint, C.c_void_p, C.c_void_p]
         lib.orc_sol_build.restype = C.c_longlong
         lib.orc_sol_build.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p]
         lib.orc_anchor_scores.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -75,6 +77,16 @@ def ref():
         lib.ref_nw_align.argtypes = [C.c_char_p, C.c_uint, C.c_char_p, C.c_uint, C.c_void_p]
         _cache["r"] = lib
     return _cache["r"]
+
+
+def nw_align_f(a: bytes, b: bytes):
+    """NWSmall for sequences with DNA wildcards, in the reference's float arithmetic (orc_nw_align_f): (path bytes, float score)"""
+    buf = np.zeros(len(a) + len(b) + 1, dtype=np.uint8)
+    score = C.c_float(0)
+    n = oracle().orc_nw_align_f(a, len(a), b, len(b), buf.ctypes.data, C.byref(score))
+    if n < 0:
+        raise RuntimeError("nw_align_f failed")
+    return buf[:n].tobytes(), float(score.value)
 
 
 def have_ref_full():

@@ -134,3 +134,45 @@ def test_dropin_scores_mds42(tmp_path):
     write_fasta(tmp_path / "full.fa", "full", g1)
     rc, kv, out = run_next(["scores", tmp_path / "recoded.fa", tmp_path / "full.fa", 0, 3])
     assert rc == 0 and kv["RESULT"] == "identical" and kv["matches"] == "29403", out
+
+
+# ---- gapped DP for regions with DNA wildcard columns (mcu_nw_batch_wild, csrc/dpwild.cu) -------------------------------------------
+def test_nw_wild_golden_and_oracle(mp, orc):
+    """paths of the reference's own NWSmall for inputs with N, X, R, Y, ... (golden), the float restatement on further inputs,
+    and the integer kernel's paths on pure ACGT input"""
+    z = _golden.npz("nw_wild.npz")
+    n = int(z["n"])
+    pairs = [(z["a%d" % i].tobytes(), z["b%d" % i].tobytes()) for i in range(n)]
+    got = mp.GlobalAlignBatchWild(pairs)
+    for i, p in enumerate(got):
+        assert p.edges == z["p%d" % i].tobytes(), i
+        assert p.score == _oracle.nw_align_f(*pairs[i])[1], i
+    rng = np.random.default_rng(8)
+    more = []
+    for _ in range(300):
+        wild = [b"N", b"NX", b"MRWSYKVHDBXNacgtn"][int(rng.integers(0, 3))]
+        more.append((bytes(rng.choice(list(b"ACGT") * 5 + list(wild), int(rng.integers(1, 600))).astype(np.uint8)),
+                     bytes(rng.choice(list(b"ACGT") * 5 + list(wild), int(rng.integers(1, 600))).astype(np.uint8))))
+    more += [(b"N" * 3000, b"ACGT" * 700), (b"A", b"N"), (b"ACGTN" * 400, b"ACGTN" * 400)]
+    for (a, b), p in zip(more, mp.GlobalAlignBatchWild(more)):
+        want, score = _oracle.nw_align_f(a, b)
+        assert p.edges == want and p.score == score, (len(a), len(b))
+    acgt = synth.dp_pairs(60, 1, 800, seed=77)
+    for p, q in zip(mp.GlobalAlignBatchWild(acgt), mp.GlobalAlignBatch(acgt)):
+        assert p.edges == q.edges and p.score == float(q.score)
+
+
+def test_nw_wild_errors(mp):
+    from mauve_py_b200 import _capi
+    with pytest.raises(mp.McuError) as e:
+        mp.GlobalAlignBatchWild([(b"ACG1", b"ACGT")])
+    assert e.value.code == _capi.MCU_EALPHA
+    with pytest.raises(mp.McuError) as e:
+        mp.GlobalAlignBatchWild([(b"ACG-", b"ACGT")])
+    assert e.value.code == _capi.MCU_EALPHA
+    with pytest.raises(mp.McuError) as e:
+        mp.GlobalAlignBatchWild([(b"N" * 5000, b"A" * 5000)])   # 2.5e7 cells: the caller keeps such a region on the host
+    assert e.value.code == _capi.MCU_EINVAL
+    with pytest.raises(mp.McuError):
+        mp.GlobalAlignBatchWild([(b"", b"ACGT")])
+    assert mp.GlobalAlignBatchWild([]) == []
