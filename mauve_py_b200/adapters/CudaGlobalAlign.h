@@ -4,8 +4,8 @@
 // AnchoredProfileProfile (MU/anchoredpp.cpp:501-549) calls ProfileProfile -> AlignTwoProfs -> GlobalAlign once per
 // range; the batch seam collects the (ProfPos*, length) pairs of all ranges and submits them in one call.  For the
 // two-genome path both profiles hold one ungapped ACGT sequence, the case the integer-exact device kernel covers
-// (SURVEY.md 8a-13); a range that is not of that form is reported through `handled[i] == false` and the caller runs
-// the reference GlobalAlign for it.  Paths are the reference's PWPath edge lists (MU/pwpath.h:46-51).
+// (SURVEY.md 8a-13); with `wildcards` set, ranges with N / X columns go to the float kernel (mcu_nw_batch_wild); a range that is of
+// neither form is reported through `handled[i] == false` and the caller runs the reference GlobalAlign for it.  Paths are the reference's PWPath edge lists (MU/pwpath.h:46-51).
 #ifndef CUDA_GLOBAL_ALIGN_H_
 #define CUDA_GLOBAL_ALIGN_H_
 
@@ -50,45 +50,92 @@ inline bool ProfileToString(const ProfPos* P, unsigned n, std::string& out)
 	return n > 0;
 }
 
+// the letter of a one-sequence profile column that may be a DNA wildcard: A C G T, 'X' (MSA::GetFractionalWeightedCounts gives it G and A
+// halves, MU/msa2.cpp:71-79 with NX_X == AX_R) or 'N' for every other wildcard (1/20 for each letter); 0 for any other column
+inline char SingleLetterOrWildcard(const ProfPos& pp)
+{
+	const char c = SingleLetter(pp);
+	if (c || pp.m_bAllGaps) return c;
+	const FCOUNT* f = pp.m_fcCounts;
+	const FCOUNT n = (FCOUNT)1.0 / 20;
+	if (f[0] == n && f[1] == n && f[2] == n && f[3] == n) return 'N';
+	if (f[0] == (FCOUNT)0.5 && f[2] == (FCOUNT)0.5 && f[1] == 0 && f[3] == 0) return 'X';
+	return 0;
+}
+
+// false when a column is neither; *has_wildcard tells which device entry takes the string
+inline bool ProfileToStringWild(const ProfPos* P, unsigned n, std::string& out, bool* has_wildcard)
+{
+	out.resize(n);
+	*has_wildcard = false;
+	for (unsigned i = 0; i < n; ++i) {
+		const char c = SingleLetterOrWildcard(P[i]);
+		if (!c) return false;
+		if (c == 'N' || c == 'X') *has_wildcard = true;
+		out[i] = c;
+	}
+	return n > 0;
+}
+
+const unsigned long long kWildMaxCells = 1ull << 24;   // mcu_nw_batch_wild walks a region with one thread
+
+// edge string -> PWPath (PWEdge prefix lengths count the letters consumed including this edge)
+inline void EdgesToPath(const char* e, uint32_t len, PWPath& P)
+{
+	unsigned ua = 0, ub = 0;
+	for (uint32_t j = 0; j < len; ++j) {
+		if (e[j] != 'I') ++ua;
+		if (e[j] != 'D') ++ub;
+		P.AppendEdge(e[j], ua, ub);
+	}
+}
+
 }  // namespace cuda_detail
 
 // Aligns every range on the device; paths (ranges.size() caller-owned objects: PWPath is not copyable) is filled for
 // handled[i] == true.
 inline void CudaGlobalAlignBatch(const std::vector<CudaDPRange>& ranges, PWPath* paths, std::vector<bool>& handled,
-                                 std::vector<long long>* scores = NULL)
+                                 std::vector<long long>* scores = NULL, bool wildcards = false)
 {
 	const size_t n = ranges.size();
 	for (size_t i = 0; i < n; ++i) paths[i].Clear();
 	handled.assign(n, false);
 	if (scores) scores->assign(n, 0);
-	std::string a, b, sa, sb;
-	std::vector<uint64_t> a_off(1, 0), b_off(1, 0), p_off(1, 0);
-	std::vector<size_t> index;
+	// two groups: columns that are all A/C/G/T (integer kernels, mcu_nw_batch) and, when `wildcards` is set, ranges with N / X columns
+	// small enough for mcu_nw_batch_wild (the reference's float arithmetic, one thread per range)
+	struct Group {
+		std::string a, b;
+		std::vector<uint64_t> a_off, b_off, p_off;
+		std::vector<size_t> index;
+		Group() : a_off(1, 0), b_off(1, 0), p_off(1, 0) {}
+	} g[2];
+	std::string sa, sb;
 	for (size_t i = 0; i < n; ++i) {
-		if (!cuda_detail::ProfileToString(ranges[i].PA, ranges[i].uLengthA, sa) || !cuda_detail::ProfileToString(ranges[i].PB, ranges[i].uLengthB, sb))
+		bool wa = false, wb = false;
+		if (!cuda_detail::ProfileToStringWild(ranges[i].PA, ranges[i].uLengthA, sa, &wa) || !cuda_detail::ProfileToStringWild(ranges[i].PB, ranges[i].uLengthB, sb, &wb))
 			continue;
-		a += sa; b += sb;
-		a_off.push_back(a.size()); b_off.push_back(b.size()); p_off.push_back(p_off.back() + sa.size() + sb.size());
-		index.push_back(i);
+		const int k = (wa || wb) ? 1 : 0;
+		if (k == 1 && (!wildcards || (unsigned long long)sa.size() * sb.size() > cuda_detail::kWildMaxCells)) continue;
+		g[k].a += sa; g[k].b += sb;
+		g[k].a_off.push_back(g[k].a.size()); g[k].b_off.push_back(g[k].b.size()); g[k].p_off.push_back(g[k].p_off.back() + sa.size() + sb.size());
+		g[k].index.push_back(i);
 	}
-	const size_t m = index.size();
-	if (!m) return;
-	std::vector<char> path(p_off.back());
-	std::vector<uint32_t> plen(m);
-	std::vector<int64_t> score(m);
-	const int rc = mcu_nw_batch(m, a.data(), &a_off[0], b.data(), &b_off[0], &p_off[0], &path[0], &plen[0], &score[0], NULL);
-	if (rc != MCU_OK) throw std::runtime_error(std::string("CudaGlobalAlignBatch: ") + mcu_last_error());
-	for (size_t k = 0; k < m; ++k) {
-		PWPath& P = paths[index[k]];
-		unsigned ua = 0, ub = 0;
-		const char* e = &path[p_off[k]];
-		for (uint32_t j = 0; j < plen[k]; ++j) {   // PWEdge prefix lengths count the letters consumed including this edge
-			if (e[j] != 'I') ++ua;
-			if (e[j] != 'D') ++ub;
-			P.AppendEdge(e[j], ua, ub);
+	for (int k = 0; k < 2; ++k) {
+		const size_t m = g[k].index.size();
+		if (!m) continue;
+		std::vector<char> path(g[k].p_off.back());
+		std::vector<uint32_t> plen(m);
+		std::vector<int64_t> score(m);
+		std::vector<float> fscore(m);
+		const int rc = k == 0
+			? mcu_nw_batch(m, g[k].a.data(), &g[k].a_off[0], g[k].b.data(), &g[k].b_off[0], &g[k].p_off[0], &path[0], &plen[0], &score[0], NULL)
+			: mcu_nw_batch_wild(m, g[k].a.data(), &g[k].a_off[0], g[k].b.data(), &g[k].b_off[0], &g[k].p_off[0], &path[0], &plen[0], &fscore[0], NULL);
+		if (rc != MCU_OK) throw std::runtime_error(std::string("CudaGlobalAlignBatch: ") + mcu_last_error());
+		for (size_t j = 0; j < m; ++j) {
+			cuda_detail::EdgesToPath(&path[g[k].p_off[j]], plen[j], paths[g[k].index[j]]);
+			handled[g[k].index[j]] = true;
+			if (scores) (*scores)[g[k].index[j]] = k == 0 ? score[j] : (long long)fscore[j];
 		}
-		handled[index[k]] = true;
-		if (scores) (*scores)[index[k]] = score[k];
 	}
 }
 

@@ -9,7 +9,8 @@
 // first, one CudaGlobalAlignBatch call (mcu_nw_batch), then AlignTwoMSAsGivenPath per range.  The profile AlignTwoProfsGivenPath
 // builds after every DP (`ProfOut`, MU/profile.cpp:86,92) is deleted unused by the reference and is not built here.
 // A range the integer kernel does not cover (a profile column that is not one ungapped ACGT letter, an empty side) takes the
-// reference's ProfileProfile unchanged.  MAUVE_CUDA_DP_SEAM=0 sends every call to the reference's function.
+// reference's ProfileProfile unchanged (with MAUVE_CUDA_WILD=1 ranges with wildcard columns go to the float kernel,
+// mcu_nw_batch_wild, first).  MAUVE_CUDA_DP_SEAM=0 sends every call to the reference's function.
 #include <cstdio>
 #include <cstdlib>
 #include <exception>
@@ -131,7 +132,9 @@ void AnchoredProfileProfile(MSA& msa1, MSA& msa2, MSA& msaOut)
 	std::vector<bool> handled;
 	if (!dp.empty()) {
 		try {
-			CudaGlobalAlignBatch(dp, paths, handled);
+			// MAUVE_CUDA_WILD=1: ranges with N / X columns go to mcu_nw_batch_wild instead of the reference's NWSmall
+			static const bool wild = getenv("MAUVE_CUDA_WILD") && getenv("MAUVE_CUDA_WILD")[0] == '1';
+			CudaGlobalAlignBatch(dp, paths, handled, NULL, wild);
 		} catch (std::exception& e) {
 			// MuscleInterface::ProfileAlignFast swallows every exception (LM/MuscleInterface.cpp:1155-1159) and the aligner would go on
 			// without this window: a device failure must stop the run, the way MUSCLE's own Quit() does

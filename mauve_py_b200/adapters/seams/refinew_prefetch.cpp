@@ -13,7 +13,8 @@
 //     profiles are single ungapped ACGT sequences whose strings are in it (after the SetTermGaps calls NWSmall would have made,
 //     MU/nwsmall.cpp:506-507), and otherwise runs the reference's NWSmall.
 // So the reference's control flow is executed as it is and only the origin of the path changes; a cache miss costs nothing but
-// the CPU time it always cost.  MAUVE_CUDA_REFINE_SEAM=0 switches the prefetch off.
+// the CPU time it always cost.  MAUVE_CUDA_REFINE_SEAM=0 switches the prefetch off; MAUVE_CUDA_WILD=1 also prefetches windows with
+// DNA wildcard letters (N, X, ...) through mcu_nw_batch_wild, the reference's float arithmetic on the device.
 #include <cstdio>
 #include <cstdlib>
 #include <exception>
@@ -50,19 +51,14 @@ SCORE GlobalAlign(const ProfPos* PA, unsigned uLengthA, const ProfPos* PB, unsig
 {
 	if (!g_paths.empty()) {
 		std::string a, b;
-		if (cuda_detail::ProfileToString(PA, uLengthA, a) && cuda_detail::ProfileToString(PB, uLengthB, b)) {
+		bool wa = false, wb = false;
+		if (cuda_detail::ProfileToStringWild(PA, uLengthA, a, &wa) && cuda_detail::ProfileToStringWild(PB, uLengthB, b, &wb)) {
 			std::unordered_map<std::string, std::string>::const_iterator it = g_paths.find(a + '|' + b);
 			if (it != g_paths.end()) {
 				SetTermGaps(PA, uLengthA);   // the side effect NWSmall has on the caller's profiles (MU/nwsmall.cpp:506-507)
 				SetTermGaps(PB, uLengthB);
 				Path.Clear();
-				unsigned ua = 0, ub = 0;
-				const std::string& e = it->second;
-				for (size_t j = 0; j < e.size(); ++j) {
-					if (e[j] != 'I') ++ua;
-					if (e[j] != 'D') ++ub;
-					Path.AppendEdge(e[j], ua, ub);
-				}
+				cuda_detail::EdgesToPath(it->second.data(), (uint32_t)it->second.size(), Path);
 				++g_ga_hits;
 				return 0;   // NWSmall's own return value is literally 0 (MU/nwsmall.cpp:669)
 			}
@@ -72,15 +68,25 @@ SCORE GlobalAlign(const ProfPos* PA, unsigned uLengthA, const ProfPos* PB, unsig
 	return GlobalAlign_reference(PA, uLengthA, PB, uLengthB, Path);
 }
 
-// ungapped upper-case letters of row `uSeqIndex` in columns [uColFrom, uColTo]; false when a letter is not A, C, G or T
-static bool WindowLetters(const MSA& msa, unsigned uSeqIndex, unsigned uColFrom, unsigned uColTo, std::string& s)
+// ungapped upper-case letters of row `uSeqIndex` in columns [uColFrom, uColTo].  Wildcards are written as the two profile classes
+// they fall into ('X' -> 'X', every other DNA wildcard -> 'N': what cuda_detail::ProfileToStringWild reads back from a profile);
+// false when a byte is neither a letter nor a wildcard, or when a wildcard is met and `wild` is off.
+static bool WindowLetters(const MSA& msa, unsigned uSeqIndex, unsigned uColFrom, unsigned uColTo, std::string& s, bool wild, bool* has_wildcard)
 {
 	s.clear();
 	for (unsigned uColIndex = uColFrom; uColIndex <= uColTo; ++uColIndex) {
 		char c = msa.GetChar(uSeqIndex, uColIndex);
 		if (IsGapChar(c)) continue;
 		if (c >= 'a' && c <= 'z') c = (char)(c - 'a' + 'A');
-		if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return false;
+		if (c != 'A' && c != 'C' && c != 'G' && c != 'T') {
+			if (!wild) return false;
+			switch (c) {
+			case 'X': break;
+			case 'M': case 'R': case 'W': case 'S': case 'Y': case 'K': case 'V': case 'H': case 'D': case 'B': case 'N': c = 'N'; break;
+			default: return false;
+			}
+			*has_wildcard = true;
+		}
 		s += c;
 	}
 	return true;
@@ -96,41 +102,54 @@ void RefineW(const MSA& msaIn, MSA& msaOut)
 		// the window bounds of MU/refinew.cpp:91-113 (g_uWindowTo == 0 means "to the last window")
 		const unsigned uWindowCount = (uColCount + g_uRefineWindow.get() - 1) / g_uRefineWindow.get();
 		const unsigned uWindowTo = 0 == g_uWindowTo.get() ? uWindowCount - 1 : g_uWindowTo.get();
-		std::vector<std::string> keys;
-		std::string a, b, s0, s1;
-		std::vector<uint64_t> a_off(1, 0), b_off(1, 0), p_off(1, 0);
+		// group 0: all letters A/C/G/T (mcu_nw_batch); group 1 (MAUVE_CUDA_WILD=1): windows with wildcard letters (mcu_nw_batch_wild)
+		static const bool wild = getenv("MAUVE_CUDA_WILD") && getenv("MAUVE_CUDA_WILD")[0] == '1';
+		struct Group {
+			std::vector<std::string> keys;
+			std::string a, b;
+			std::vector<uint64_t> a_off, b_off, p_off;
+			Group() : a_off(1, 0), b_off(1, 0), p_off(1, 0) {}
+		} grp[2];
+		std::string s0, s1;
 		for (unsigned uWindowIndex = g_uWindowFrom.get(); uWindowIndex <= uWindowTo; ++uWindowIndex) {
 			const unsigned uColFrom = g_uWindowOffset.get() + uWindowIndex * g_uRefineWindow.get();
 			if (uColFrom >= uColCount) break;
 			unsigned uColTo = uColFrom + g_uRefineWindow.get() - 1;
 			if (uColTo >= uColCount) uColTo = uColCount - 1;
-			if (!WindowLetters(msaIn, 0, uColFrom, uColTo, s0) || !WindowLetters(msaIn, 1, uColFrom, uColTo, s1)) continue;
+			bool has_wildcard = false;
+			if (!WindowLetters(msaIn, 0, uColFrom, uColTo, s0, wild, &has_wildcard) || !WindowLetters(msaIn, 1, uColFrom, uColTo, s1, wild, &has_wildcard)) continue;
 			if (s0.empty() || s1.empty()) continue;   // MUSCLE() is not called for a window with one empty row (MU/refinew.cpp:141-142)
+			if (has_wildcard && (unsigned long long)s0.size() * s1.size() > cuda_detail::kWildMaxCells) continue;
+			Group& g = grp[has_wildcard ? 1 : 0];
 			for (int order = 0; order < 2; ++order) {   // the guide tree decides which sequence is operand A: both orders are prepared
 				const std::string& x = order ? s1 : s0;
 				const std::string& y = order ? s0 : s1;
 				const std::string key = x + '|' + y;
 				if (g_paths.find(key) != g_paths.end()) continue;
 				g_paths[key] = std::string();
-				keys.push_back(key);
-				a += x;
-				b += y;
-				a_off.push_back(a.size());
-				b_off.push_back(b.size());
-				p_off.push_back(p_off.back() + x.size() + y.size());
+				g.keys.push_back(key);
+				g.a += x;
+				g.b += y;
+				g.a_off.push_back(g.a.size());
+				g.b_off.push_back(g.b.size());
+				g.p_off.push_back(g.p_off.back() + x.size() + y.size());
 			}
 		}
-		const size_t m = keys.size();
-		if (m) {
-			std::vector<char> path(p_off.back());
+		for (int k = 0; k < 2; ++k) {
+			Group& g = grp[k];
+			const size_t m = g.keys.size();
+			if (!m) continue;
+			std::vector<char> path(g.p_off.back());
 			std::vector<uint32_t> plen(m);
 			std::vector<int64_t> score(m);
-			const int rc = mcu_nw_batch(m, a.data(), &a_off[0], b.data(), &b_off[0], &p_off[0], &path[0], &plen[0], &score[0], NULL);
+			std::vector<float> fscore(m);
+			const int rc = k == 0 ? mcu_nw_batch(m, g.a.data(), &g.a_off[0], g.b.data(), &g.b_off[0], &g.p_off[0], &path[0], &plen[0], &score[0], NULL)
+			                      : mcu_nw_batch_wild(m, g.a.data(), &g.a_off[0], g.b.data(), &g.b_off[0], &g.p_off[0], &path[0], &plen[0], &fscore[0], NULL);
 			if (rc != MCU_OK) {   // RefineFast's callers would carry on with a half-refined alignment: stop, like MUSCLE's Quit()
 				fprintf(stderr, "\n*** FATAL: RefineW prefetch: %s\n", mcu_last_error());
 				exit(3);
 			}
-			for (size_t k = 0; k < m; ++k) g_paths[keys[k]].assign(&path[p_off[k]], plen[k]);
+			for (size_t j = 0; j < m; ++j) g_paths[g.keys[j]].assign(&path[g.p_off[j]], plen[j]);
 			g_rw_prefetched += m;
 		}
 	}

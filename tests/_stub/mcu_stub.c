@@ -83,3 +83,27 @@ int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out,
     if (sml_len_out) *sml_len_out = (uint64_t)r;
     return 0;
 }
+
+/* regions with DNA wildcard columns (CudaGlobalAlign.h, seams with MAUVE_CUDA_WILD=1) */
+long long orc_nw_align_f(const char* a, unsigned la, const char* b, unsigned lb, char* path_out, float* score_out);
+static unsigned long long g_nwf_problems = 0;
+int mcu_nw_batch_wild(uint64_t n, const char* a, const uint64_t* a_off, const char* b, const uint64_t* b_off, const uint64_t* path_off, char* path_out,
+                      uint32_t* path_len, float* score, float* device_ms)
+{
+    uint64_t i;
+    const double t0 = stub_now();
+    g_nwf_problems += n;
+    for (i = 0; i < n; ++i) {
+        long long r = orc_nw_align_f(a + a_off[i], (unsigned)(a_off[i + 1] - a_off[i]), b + b_off[i], (unsigned)(b_off[i + 1] - b_off[i]),
+                                     path_out + path_off[i], &score[i]);
+        if (r < 0) return -6;
+        path_len[i] = (uint32_t)r;
+    }
+    if (device_ms) *device_ms = 0;
+    g_stub_seconds += stub_now() - t0;
+    return 0;
+}
+__attribute__((destructor)) static void stub_report_wild(void)
+{
+    if (getenv("MAUVE_CUDA_SEAM_REPORT") && g_nwf_problems) fprintf(stderr, "stub: %llu mcu_nw_batch_wild problems\n", g_nwf_problems);
+}

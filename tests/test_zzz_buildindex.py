@@ -298,6 +298,14 @@ def test_seams_host_code_inside_the_reference_binary(tmp_path):
         if binary == CUDA_ALL_BINARY:
             assert c["RefineW"][2] > 10 and c["RefineW"][3] > 0   # windows with an N are not prefetched: the reference's NWSmall aligns them
             assert c["MemHash::FindMatches"][0] > 10 and c["FileSML::Create"] == [2, 0] and c["SeedOccurrenceList::construct"] == [2, 0]
+    # MAUVE_CUDA_WILD=1: the ranges and windows with N columns go to the float kernel's entry point instead: nothing is left to the
+    # reference's NWSmall, and the alignment is still the reference's
+    env_w = dict(env, MAUVE_CUDA_WILD="1")
+    r = _align(CUDA_ALL_BINARY, d, "a.fa", "b.fa", "wild.xmfa", env_w)
+    assert r.returncode == 0 and _xmfa_body_sha1(os.path.join(d, "wild.xmfa")) == _xmfa_body_sha1(os.path.join(d, "ref.xmfa")), r.stderr[-500:]
+    c = _seam_counts(r.stderr)
+    assert c["AnchoredProfileProfile"][1] == c["AnchoredProfileProfile"][2] and c["RefineW"][3] == 0
+    assert "mcu_nw_batch_wild problems" in r.stderr
     # BASELINE config 1 with every seam on: initial anchors, the gap searches of recursive anchoring, the DP of every window
     _lut, meta = _golden()
     fas = _fastas(tmp_path)
@@ -382,3 +390,20 @@ def test_seam_binary_config2_pair(tmp_path):
     assert want.startswith("3fd365f4") and _xmfa_body_sha1(os.path.join(d, "seam.xmfa")) == want
     c = _seam_counts(r.stderr)
     assert c["AnchoredProfileProfile"][1] == c["AnchoredProfileProfile"][2] > 40000 and c["RefineW"][3] == 0 and c["MemHash::FindMatches"][0] > 2000
+
+
+@needs_cuda_bin
+@pytest.mark.gpu
+def test_seam_binary_wildcards_on_device(tmp_path):
+    """MAUVE_CUDA_WILD=1: the DP ranges and refine windows that contain N columns go to mcu_nw_batch_wild (the reference's float
+    arithmetic on the device) instead of the reference's NWSmall; every DP of the run is then on the device and the XMFA is the
+    reference binary's"""
+    d = str(tmp_path)
+    _spiked_pair(d)
+    assert _align(BINARY, d, "a.fa", "b.fa", "ref.xmfa").returncode == 0
+    env = dict(os.environ, MAUVE_CUDA_SEAM_REPORT="1", MAUVE_CUDA_GAP_SEAM="1", MAUVE_CUDA_SOL_SEAM="0", MAUVE_CUDA_WILD="1")
+    r = _align(CUDA_ALL_BINARY, d, "a.fa", "b.fa", "wild.xmfa", env)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert _xmfa_body_sha1(os.path.join(d, "wild.xmfa")) == _xmfa_body_sha1(os.path.join(d, "ref.xmfa"))
+    c = _seam_counts(r.stderr)
+    assert c["AnchoredProfileProfile"][1] == c["AnchoredProfileProfile"][2] > 100 and c["RefineW"][2] > 100 and c["RefineW"][3] == 0
