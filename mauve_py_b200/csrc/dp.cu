@@ -395,19 +395,19 @@ __global__ void __launch_bounds__(256) int32_peak_kernel(int* __restrict__ sink,
 // G thread-level integer instructions per second sustained by the whole device (each one a fused add+max)
 int int32_peak(double* gops_out, float* ms_out)
 {
-    NwState& st = g_nw;
-    if (!st.stream) MCU_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+    static cudaStream_t stream = nullptr;   // its own stream: nw_batch creates g_nw's stream together with its events
+    if (!stream) MCU_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     cudaEvent_t e0, e1;
     MCU_CUDA(cudaEventCreate(&e0));
     MCU_CUDA(cudaEventCreate(&e1));
     int* sink = nullptr;
     MCU_CUDA(cudaMalloc(&sink, 256));
     const int iters = 1 << 16, blocks = sm_count() * 8, threads = 256;
-    int32_peak_kernel<<<blocks, threads, 0, st.stream>>>(sink, 64, 1, -5);   // warm-up
-    MCU_CUDA(cudaEventRecord(e0, st.stream));
-    int32_peak_kernel<<<blocks, threads, 0, st.stream>>>(sink, iters, 1, -5);
-    MCU_CUDA(cudaEventRecord(e1, st.stream));
-    MCU_CUDA(cudaStreamSynchronize(st.stream));
+    int32_peak_kernel<<<blocks, threads, 0, stream>>>(sink, 64, 1, -5);   // warm-up
+    MCU_CUDA(cudaEventRecord(e0, stream));
+    int32_peak_kernel<<<blocks, threads, 0, stream>>>(sink, iters, 1, -5);
+    MCU_CUDA(cudaEventRecord(e1, stream));
+    MCU_CUDA(cudaStreamSynchronize(stream));
     MCU_CUDA(cudaGetLastError());
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
