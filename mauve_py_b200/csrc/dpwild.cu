@@ -317,7 +317,8 @@ __attribute__((visibility("default"))) long long emu_nw_wild(const char* a, unsi
     if (la == 0 || lb == 0) return -1;
     float sub[36];
     for (int k = 0; k < 36; ++k) sub[k] = mcu::nwf_pair_score(k / 6, k % 6);
-    float* rows = (float*)calloc(4 * ((size_t)lb + 1), sizeof(float));
+    float* rows = (float*)malloc(4 * ((size_t)lb + 1) * sizeof(float));
+    memset(rows, 0xFF, 4 * ((size_t)lb + 1) * sizeof(float));   // NaN: the device scratch is not initialised either, nothing may depend on it
     u8* tb = (u8*)calloc(((size_t)la + 1) * ((size_t)lb + 1), 1);
     const unsigned n = mcu::nwf_align_one((const u8*)a, la, (const u8*)b, lb, sub, rows, tb, path_out, score_out);
     free(rows);
