@@ -64,6 +64,18 @@ def test_compute_calls_fail_loudly_without_gpu():
         mp.run(b"1234", mp.libmems.hmm_params())
     with pytest.raises(mp.McuError):
         mp.libmems.find_mums(b"ACGT" * 10, b"ACGT" * 10, mp.getSeed(5, 0))
+    # the entry points added for the rows next to the path and for wildcard regions: no host path behind them either
+    sml = mp.DNAMemorySML()
+    sml._seq, sml._seed, sml._length = np.frombuffer(b"ACGT" * 10, dtype=np.uint8), mp.getSeed(5, 0), 40
+    with pytest.raises(mp.McuError) as e:
+        mp.SeedOccurrenceList().construct(sml)
+    assert e.value.code == _capi.MCU_ENODEV
+    with pytest.raises(mp.McuError) as e:
+        mp.libmems.anchor_scores(b"ACGT" * 10, b"ACGT" * 10, np.array([[8, 1, 1]], dtype=np.int64), [0, 1], seed=mp.getSeed(5, 0))
+    assert e.value.code == _capi.MCU_ENODEV
+    with pytest.raises(mp.McuError) as e:
+        mp.GlobalAlignBatchWild([(b"ACGN", b"ACGT")])
+    assert e.value.code == _capi.MCU_ENODEV
 
 
 def test_product_does_not_touch_oracle():
