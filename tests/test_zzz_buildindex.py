@@ -323,6 +323,36 @@ def test_seams_host_code_inside_the_reference_binary(tmp_path):
 
 
 @needs_cuda_bin
+@pytest.mark.parametrize("option", ["--seed-family", "--collinear", "--skip-refinement", "--solid-seeds"])
+def test_seam_binary_under_other_command_lines(tmp_path, option):
+    """other paths through the aligner (a family of three seeds through UniqueMatchFinder, collinear genomes, no refinement, solid
+    seeds): the seam binary's alignment equals the reference binary's.  CPU: device calls answered through the stub; with a GPU:
+    the real library."""
+    import torch
+    d = str(tmp_path)
+    _spiked_pair(d)
+    env = dict(os.environ, MAUVE_CUDA_SEAM_REPORT="1", MAUVE_CUDA_SOL_SEAM="1", MAUVE_CUDA_WILD="1")
+    if not torch.cuda.is_available():
+        import _emu
+        env["LD_PRELOAD"] = _emu.stub_library()
+
+    def run(binary, out, e=None):
+        for f in os.listdir(d):
+            if f.endswith(".sslist"):
+                os.remove(os.path.join(d, f))
+        return subprocess.run([binary, option, "--output=" + out, "a.fa", "b.fa"], cwd=d, capture_output=True, text=True, env=e)
+
+    assert run(BINARY, "ref.xmfa").returncode == 0
+    r = run(CUDA_ALL_BINARY, "seam.xmfa", env)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert _xmfa_body_sha1(os.path.join(d, "seam.xmfa")) == _xmfa_body_sha1(os.path.join(d, "ref.xmfa"))
+    c = _seam_counts(r.stderr)
+    assert c["AnchoredProfileProfile"][1] == c["AnchoredProfileProfile"][2] > 100
+    if option == "--seed-family":
+        assert c["MemHash::FindMatches"][0] == 0          # UniqueMatchFinder and the hash-table readers stay with the reference's code
+
+
+@needs_cuda_bin
 @pytest.mark.gpu
 @pytest.mark.parametrize("binary,gap_seam,sol_seam", [(CUDA_BINARY, "0", "0"), (CUDA_MH_BINARY, "1", "0"),
                                                       (CUDA_ALL_BINARY, "1", "0"), (CUDA_ALL_BINARY, "1", "1")],
