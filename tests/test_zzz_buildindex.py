@@ -353,6 +353,40 @@ def test_seam_binary_under_other_command_lines(tmp_path, option):
 
 
 @needs_cuda_bin
+def test_seam_binary_three_genomes(tmp_path):
+    """three genomes: the pairwise parts (gap searches of the pairwise recursion, DP ranges between two single sequences, one seed
+    occurrence list and one `.sslist` per genome) go through the C ABI, everything that involves profiles of several sequences or
+    three-way match finding stays with the reference's code; the alignment equals the reference binary's"""
+    import torch
+    from mauve_py_b200 import synth
+    d = str(tmp_path)
+    a, b = synth.small_pair(50000, seed=91, snp=0.03, n_inv=1)
+    c = synth.snps(np.frombuffer(a, dtype=np.uint8), 0.04, synth.rng_for(92)).tobytes()
+    for name, s_ in (("g1", a), ("g2", b), ("g3", c)):
+        with open(os.path.join(d, name + ".fa"), "wb") as f:
+            f.write(b">" + name.encode() + b"\n" + b"\n".join(s_[i:i + 70] for i in range(0, len(s_), 70)) + b"\n")
+    env = dict(os.environ, MAUVE_CUDA_SEAM_REPORT="1", MAUVE_CUDA_GAP_SEAM="1", MAUVE_CUDA_SOL_SEAM="1")
+    if not torch.cuda.is_available():
+        import _emu
+        env["LD_PRELOAD"] = _emu.stub_library()
+
+    def run(binary, out, e=None):
+        for f in os.listdir(d):
+            if f.endswith(".sslist"):
+                os.remove(os.path.join(d, f))
+        return subprocess.run([binary, "--output=" + out, "g1.fa", "g2.fa", "g3.fa"], cwd=d, capture_output=True, text=True, env=e)
+
+    assert run(BINARY, "ref.xmfa").returncode == 0
+    r = run(CUDA_ALL_BINARY, "seam.xmfa", env)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert _xmfa_body_sha1(os.path.join(d, "seam.xmfa")) == _xmfa_body_sha1(os.path.join(d, "ref.xmfa"))
+    cnt = _seam_counts(r.stderr)
+    assert cnt["FileSML::Create"] == [3, 0] and cnt["SeedOccurrenceList::construct"] == [3, 0]
+    assert 0 < cnt["AnchoredProfileProfile"][2] < cnt["AnchoredProfileProfile"][1]     # ranges between multi-sequence profiles: reference
+    assert cnt["MemHash::FindMatches"][0] > 10 and cnt["MemHash::FindMatches"][1] > 0  # the three-way searches: reference
+
+
+@needs_cuda_bin
 @pytest.mark.gpu
 @pytest.mark.parametrize("binary,gap_seam,sol_seam", [(CUDA_BINARY, "0", "0"), (CUDA_MH_BINARY, "1", "0"),
                                                       (CUDA_ALL_BINARY, "1", "0"), (CUDA_ALL_BINARY, "1", "1")],
