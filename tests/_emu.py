@@ -54,3 +54,19 @@ def stub_library():
         subprocess.check_call(["/usr/bin/gcc", "-O2", "-fPIC", "-shared", "-o", STUB, src, "-L" + os.path.dirname(_oracle.ORACLE_SO), "-lmauve_oracle",
                                "-Wl,-rpath," + os.path.dirname(_oracle.ORACLE_SO)])
     return STUB
+
+
+BENCH_STUB = os.path.join(ROOT, "tests", "_stub", "libmcu_bench_stub.so")
+
+
+def bench_stub_library():
+    """Stand-in for EVERY symbol of libmauve_cuda.so answered from the CPU restatement (tests/_stub/mcu_bench_stub.c): lets the CPU
+    suite execute bench.py's and libmems.py's host code end to end (tests/test_bench_dryrun.py).  Returns the path."""
+    here = os.path.join(ROOT, "tests", "_stub")
+    srcs = [os.path.join(here, "mcu_bench_stub.c"), os.path.join(here, "mcu_stub.c")]
+    import _oracle
+    _oracle.oracle()
+    if not os.path.exists(BENCH_STUB) or os.path.getmtime(BENCH_STUB) < max([os.path.getmtime(s) for s in srcs] + [os.path.getmtime(_oracle.ORACLE_SO)]):
+        subprocess.check_call(["/usr/bin/gcc", "-O2", "-fPIC", "-shared", "-o", BENCH_STUB, srcs[0], "-L" + os.path.dirname(_oracle.ORACLE_SO),
+                               "-lmauve_oracle", "-Wl,-rpath," + os.path.dirname(_oracle.ORACLE_SO)])
+    return BENCH_STUB

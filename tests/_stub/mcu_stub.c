@@ -73,13 +73,14 @@ void mcu_free(void* p) { free(p); }
 
 /* sorted mer list (adapters/seams/filesml_seam.cpp, CudaDNAMemorySML.h) */
 long long orc_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out, uint64_t* mer_out);
+int orc_pack(const char* seq, uint64_t n, uint32_t* out);
 int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out, uint64_t* mer_out, uint32_t* packed_out, uint64_t* sml_len_out)
 {
     const double t0 = stub_now();
     long long r = orc_sml_build(seq, n, seed, pos_out, mer_out);
     g_stub_seconds += stub_now() - t0;
-    (void)packed_out;
     if (r < 0) return -3;
+    if (packed_out && orc_pack(seq, n, packed_out) != 0) return -4;
     if (sml_len_out) *sml_len_out = (uint64_t)r;
     return 0;
 }

@@ -1,0 +1,105 @@
+"""bench.py executed end to end on the CPU: its own host code (argument handling, timed loops, roofline arithmetic, secondary objects,
+the ONE JSON line on the real stdout) with libmauve_cuda.so replaced by a stand-in that answers from the oracle
+(tests/_stub/mcu_bench_stub.c) and the three torch.cuda calls it makes turned into no-ops.  Nothing here is a measurement: the test
+exists because a Python error in bench.py would cost the round's benchmark line, and the box with the GPU is not available while
+developing.  The reference arm (--impl reference) needs no stand-in and is run as it is."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+DRIVER = r"""
+import sys, os
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import torch
+import mauve_py_b200._capi as capi
+capi.LIB_PATH = {stub!r}
+torch.cuda.set_device = lambda *a, **k: None
+torch.cuda.synchronize = lambda *a, **k: None
+_tensor = torch.tensor
+torch.tensor = lambda *a, **k: _tensor(*a, **{{x: y for x, y in k.items() if x != "device"}})
+sys.argv = ["bench.py"] + {argv!r}
+import bench
+bench.main()
+"""
+
+REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+            "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"]
+
+
+def run_bench(argv, stub=True, timeout=600):
+    import _emu
+    code = DRIVER.format(root=ROOT, stub=_emu.bench_stub_library(), argv=argv) if stub else None
+    cmd = [sys.executable, "-c", code] if stub else [sys.executable, os.path.join(ROOT, "bench.py")] + argv
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, "stdout must hold exactly ONE line: %r" % r.stdout[-2000:]
+    return json.loads(lines[0]), r.stderr
+
+
+def test_bench_main_line_dry_run():
+    line, err = run_bench(["--mbp", "0.3", "--cpu-sample-mbp", "0.1", "--dp-regions", "6", "--steps", "2", "--warmup", "1", "--no-buildindex"])
+    for k in REQUIRED:
+        assert k in line, k
+    assert line["metric"] == "Mbp/s seed+match+extend" and line["unit"] == "Mbp/s" and line["n_gpus"] == 1
+    assert line["steps"] == 2 and line["warmup"] == 3   # W >= 3 is enforced
+    assert line["value"] > 0 and line["matches"] > 0 and line["gpu_launches"] > 0
+    assert line["config"]["workload"].startswith("synthetic 0.3 Mbp pair") and "model" not in line["config"]
+    e2e = line["e2e"]
+    assert e2e["value"] > 0 and abs(e2e["h2d_bytes_per_step"] - 600000) < 6000 and e2e["d2h_bytes_per_step"] == 24 * line["matches"]
+    rf = line["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in rf, k
+    assert rf["bound"] == "hbm" and rf["achieved"] > 0 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert rf["traffic"] is None   # the ncu capture describes the 100 Mbp launch only
+    assert set(rf["other_kernels"]) == {"bkf_scatter1_kernel", "bkf_scatter2_kernel"} and rf["step"]["frac"] > 0
+    cpu = line["cpu_baseline"]
+    assert "error" not in cpu, cpu
+    assert cpu["kind"] in ("reference", "port") and cpu["cores"] == 1 and cpu["value"] > 0 and cpu["parity"] == "identical"
+    assert "error" not in line["dp"], line["dp"]
+    assert line["dp"]["value"] > 0 and line["dp"]["roofline"]["frac"] > 0 and line["dp"]["cpu_baseline"]["value"] > 0
+    assert "error" not in line["hmm"], line["hmm"]
+    assert line["hmm"]["value"] > 0 and line["hmm"]["strings"] == 32768
+    assert line["clocks"] is not None and "reasons" in line["clocks"]
+    assert line["buildindex"] is None
+
+
+def test_bench_reference_arm():
+    line, _ = run_bench(["--impl", "reference", "--mbp", "0.3", "--cpu-sample-mbp", "0.1", "--steps", "2", "--warmup", "1"], stub=False)
+    assert line["impl"] == "reference" and line["metric"] == "Mbp/s seed+match+extend" and line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["value"] == line["value"]
+    assert line["config"]["workload"].startswith("synthetic 0.3 Mbp pair")
+
+
+def test_bench_reference_arm_other_ranks_do_nothing():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True,
+                       timeout=120, env=env, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "progressiveMauve_cuda_all")),
+                    reason="oracle/_ref binaries not built (they need /root/reference at build time)")
+def test_bench_buildindex_child_dry_run():
+    """the `buildindex` object of the bench line (child process `bench.py --buildindex-only`): BASELINE config 0 end to end, the
+    reference binary beside mauve_py_b200.buildIndex driving the binary with every seam; the stand-in is preloaded into the binaries"""
+    import _emu
+    stub = _emu.bench_stub_library()
+    code = DRIVER.format(root=ROOT, stub=stub, argv=["--buildindex-only"])
+    env = dict(os.environ, LD_PRELOAD=stub)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    out = json.loads(lines[0])
+    assert "error" not in out and "unavailable" not in out, out
+    assert out["lut"].startswith("identical to the golden LUT") and out["reference_s"] > 0 and out["ours_s"] > 0
