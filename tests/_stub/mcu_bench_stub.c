@@ -32,6 +32,8 @@ typedef struct {
     mcu_match* rows;
     uint64_t n_rows;
     uint64_t launches;
+    uint64_t seed;
+    int shard;
 } stub_session;
 
 int mcu_session_create(void** out) { *out = calloc(1, sizeof(stub_session)); return *out ? 0 : -5; }
@@ -70,10 +72,59 @@ int mcu_session_run(void* h, uint64_t seed, int shard_index, int shard_count, fl
     }
     return 0;
 }
-int mcu_session_enumerate(void* h, uint64_t seed, int a, int b) { (void)h; (void)seed; (void)a; (void)b; return -1; }
-int mcu_session_uniq_bitmap(void* h, void** p, uint64_t* n) { (void)h; (void)p; (void)n; return -1; }
-int mcu_session_finish(void* h, int g, float* ms, uint64_t* st) { (void)h; (void)g; (void)ms; (void)st; return -1; }
-int mcu_session_merge(void* h, const mcu_match* r, uint64_t n, int d, uint64_t* st) { (void)h; (void)r; (void)n; (void)d; (void)st; return -1; }
+/* the two-phase form (multi-GPU runs): rank 0's stand-in produces the whole list, the other ranks none; merge keeps what it is given */
+static void stub_fill(stub_session* s, uint64_t seed, long long n, const uint64_t* st, float* stage_ms, uint64_t* stats)
+{
+    int i;
+    s->launches += 17;
+    if (stage_ms) {
+        for (i = 0; i < 16; ++i) stage_ms[i] = 0.f;
+        for (i = 0; i < 6; ++i) stage_ms[i] = 0.5f;
+        stage_ms[6] = 3.0f;
+        stage_ms[7] = -1.0f;  /* bucketed enumeration */
+        for (i = 8; i < 15; ++i) stage_ms[i] = 0.25f;
+    }
+    if (stats) {
+        const int L = orc_seed_length(seed);
+        for (i = 0; i < 8; ++i) stats[i] = 0;
+        stats[0] = st[3]; stats[1] = (uint64_t)n; stats[2] = st[0]; stats[4] = (uint64_t)n;
+        stats[5] = (s->n[0] >= (uint64_t)L ? s->n[0] - L + 1 : 0) + (s->n[1] >= (uint64_t)L ? s->n[1] - L + 1 : 0);
+    }
+}
+int mcu_session_enumerate(void* h, uint64_t seed, int shard_index, int shard_count)
+{
+    stub_session* s = (stub_session*)h;
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return -3;
+    s->seed = seed; s->shard = shard_index;
+    return 0;
+}
+int mcu_session_uniq_bitmap(void* h, void** p, uint64_t* n) { static uint32_t words[4]; (void)h; *p = words; *n = 4; return 0; }
+int mcu_session_finish(void* h, int uniq_is_global, float* stage_ms, uint64_t* stats)
+{
+    stub_session* s = (stub_session*)h;
+    uint64_t st[4] = {0, 0, 0, 0};
+    long long n = 0;
+    (void)uniq_is_global;
+    free(s->rows);
+    s->rows = NULL;
+    if (s->shard == 0) n = orc_find_mums(s->seq[0], s->n[0], s->seq[1], s->n[1], s->seed, 0, &s->rows, st);
+    if (n < 0) return -3;
+    s->n_rows = (uint64_t)n;
+    stub_fill(s, s->seed, n, st, stage_ms, stats);
+    return 0;
+}
+int mcu_session_merge(void* h, const mcu_match* r, uint64_t n, int in_device, uint64_t* st)
+{
+    stub_session* s = (stub_session*)h;
+    mcu_match* copy = (mcu_match*)malloc((n + 1) * sizeof(mcu_match));
+    (void)in_device;
+    if (n) memcpy(copy, r, n * sizeof(mcu_match));
+    free(s->rows);
+    s->rows = copy;
+    s->n_rows = n;
+    if (st) st[0] = st[1] = 0;
+    return 0;
+}
 uint64_t mcu_session_match_count(const void* h) { return ((const stub_session*)h)->n_rows; }
 int mcu_session_download(void* h, mcu_match* out)
 {

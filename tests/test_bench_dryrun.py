@@ -103,3 +103,56 @@ def test_bench_buildindex_child_dry_run():
     out = json.loads(lines[0])
     assert "error" not in out and "unavailable" not in out, out
     assert out["lut"].startswith("identical to the golden LUT") and out["reference_s"] > 0 and out["ours_s"] > 0
+
+
+DRIVER_DIST = r"""
+import sys, os
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import torch
+import torch.distributed as dist
+import mauve_py_b200._capi as capi
+capi.LIB_PATH = {stub!r}
+torch.cuda.set_device = lambda *a, **k: None
+torch.cuda.synchronize = lambda *a, **k: None
+def _nodev(f):
+    return lambda *a, **k: f(*a, **{{x: y for x, y in k.items() if x != "device"}})
+torch.tensor, torch.empty = _nodev(torch.tensor), _nodev(torch.empty)
+_init = dist.init_process_group
+dist.init_process_group = lambda backend, **k: _init("gloo")
+from mauve_py_b200 import dist as mdist
+mdist.allreduce_uniq_bitmap = lambda session, group=None: None   # the stand-in has no bitmap to combine
+sys.argv = ["bench.py"] + {argv!r}
+import bench
+bench.main()
+"""
+
+
+def test_bench_two_ranks_dry_run():
+    """the N > 1 flow of bench.py (torchrun environment, sharded seed+match+extend, DP and HMM divided by LPT, max over ranks,
+    rank 0 alone prints) with gloo in place of NCCL and the stand-in library: two processes"""
+    import socket
+    import _emu
+    stub = _emu.bench_stub_library()
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    code = DRIVER_DIST.format(root=ROOT, stub=stub, argv=["--gpus", "2", "--mbp", "0.3", "--dp-regions", "6", "--steps", "2", "--warmup", "1"])
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT))
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-3000:]
+    assert outs[1][0].strip() == ""   # only rank 0 prints
+    lines = [l for l in outs[0][0].splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for k in REQUIRED:
+        assert k in line, k
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["value"] > 0 and line["matches"] > 0
+    assert line["cpu_baseline"] is None and line["buildindex"] is None   # N = 1 only
+    assert line["e2e"]["value"] > 0 and line["e2e"]["d2h_bytes_per_step"] == 24 * line["matches"]
+    assert "error" not in line["dp"] and line["dp"]["value"] > 0 and "2 ranks" in line["dp"]["sharding"]
+    assert "error" not in line["hmm"] and line["hmm"]["value"] > 0
+    assert "NCCL" in line["config"]["sharding"]
