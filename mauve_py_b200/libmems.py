@@ -24,7 +24,7 @@ from ._capi import CODING_SEED, SOLID_SEED, McuError, check, lib
 __all__ = [
     "CODING_SEED", "SOLID_SEED", "McuError", "getSeed", "getSolidSeed", "getDefaultSeedWeight", "getSeedLength", "getSeedWeight",
     "bmer", "DNAMemorySML", "Match", "MatchList", "MemHash", "PairwiseMatchFinder", "AnchorSession", "merge_matches",
-    "PWPath", "GlobalAlign", "GlobalAlignBatch", "GlobalAlignBatchWild", "Params", "getAdaptedHoxdMatrixParameters", "adaptToPercentIdentity",
+    "PWPath", "GlobalAlign", "GlobalAlignBatch", "GlobalAlignBatchWild", "Params", "hmm_params", "getAdaptedHoxdMatrixParameters", "adaptToPercentIdentity",
     "run", "run_batch", "sort_pairs", "SeedOccurrenceList", "GetPairwiseAnchorScore", "anchor_scores", "hoxd_matrix",
 ]
 

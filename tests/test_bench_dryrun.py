@@ -156,3 +156,33 @@ def test_bench_two_ranks_dry_run():
     assert "error" not in line["dp"] and line["dp"]["value"] > 0 and "2 ranks" in line["dp"]["sharding"]
     assert "error" not in line["hmm"] and line["hmm"]["value"] > 0
     assert "NCCL" in line["config"]["sharding"]
+
+
+def test_smoke_host_code_dry_run():
+    """__graft_entry__.smoke()'s own Python (names it uses from the package, argument forms, comparisons with the oracle) against the
+    stand-in: the driver runs smoke() on the GPU box before the bench, and an AttributeError there would be found only then"""
+    import _emu
+    code = ("import sys, os; sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tests'))\n"
+            "import mauve_py_b200._capi as capi; capi.LIB_PATH = %r\n"
+            "import __graft_entry__ as g; g.smoke()\n") % (ROOT, ROOT, _emu.bench_stub_library())
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_every_package_name_used_by_tests_bench_and_tools_exists():
+    """`mp.<name>` in tests/, tools/, bench.py and __graft_entry__.py must resolve in the package namespace (libmems.__all__)"""
+    import glob
+    import re
+    import types
+    import mauve_py_b200 as mp
+    files = glob.glob(os.path.join(ROOT, "tests", "*.py")) + glob.glob(os.path.join(ROOT, "tools", "*.py")) + \
+        [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    missing = []
+    for f in files:
+        for m in re.finditer(r"\bmp\.([A-Za-z_]\w*)(?:\.([A-Za-z_]\w*))?", open(f).read()):
+            a, b = m.group(1), m.group(2)
+            if not hasattr(mp, a):
+                missing.append((os.path.basename(f), a))
+            elif b and isinstance(getattr(mp, a), types.ModuleType) and not hasattr(getattr(mp, a), b):
+                missing.append((os.path.basename(f), a + "." + b))
+    assert not missing, missing
