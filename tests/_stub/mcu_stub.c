@@ -8,6 +8,7 @@
  */
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include <time.h>
 static double g_stub_seconds = 0;
 static double stub_now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
@@ -25,9 +26,16 @@ int mcu_anchor_scores(const char* seq0, uint64_t n0, const char* seq1, uint64_t 
                       const mcu_match* rows, uint64_t n_rows, const uint64_t* lcb_off, uint64_t n_lcb, const int32_t* matrix, int penalize_repeats,
                       double* lcb_score_out, int64_t* match_score_out)
 {
-    (void)seed;
-    if (!freq0 || !freq1) return -3;
-    return orc_anchor_scores(seq0, n0, seq1, n1, freq0, freq1, rows, n_rows, lcb_off, n_lcb, matrix, penalize_repeats, lcb_score_out, match_score_out) == 0 ? 0 : -3;
+    static const int32_t hoxd[16] = {91, -114, -31, -123, -114, 100, -125, -31, -31, -125, 100, -114, -123, -31, -114, 91};  /* LM/SubstitutionMatrix.h:23-33 */
+    float *f0 = NULL, *f1 = NULL;
+    int rc;
+    /* frequencies not given: built from the seed, as the library does (csrc/sol.cu anchor_scores) */
+    if (!freq0) { f0 = (float*)malloc((n0 + 1) * sizeof(float)); if (orc_sol_build(seq0, n0, seed, f0) != (long long)n0) { free(f0); return -3; } freq0 = f0; }
+    if (!freq1) { f1 = (float*)malloc((n1 + 1) * sizeof(float)); if (orc_sol_build(seq1, n1, seed, f1) != (long long)n1) { free(f0); free(f1); return -3; } freq1 = f1; }
+    rc = orc_anchor_scores(seq0, n0, seq1, n1, freq0, freq1, rows, n_rows, lcb_off, n_lcb, matrix ? matrix : hoxd, penalize_repeats, lcb_score_out, match_score_out) == 0 ? 0 : -3;
+    free(f0);
+    free(f1);
+    return rc;
 }
 
 long long orc_nw_align(const char* a, unsigned la, const char* b, unsigned lb, char* path_out, int64_t* score_out);
