@@ -473,7 +473,16 @@ def main():
             return n, n * 24
         sess.upload_ptr(pa, a.size, pb, b.size)
         n, merged = step_resident()
+        if rank == 0 and n:   # the merged list is the step's result: read it back into pinned host memory
+            assert n <= e2e_rows_cap, "match count changed between steps"
+            sess.download_ptr(e2e_rows)
         return n, (n * 24 if rank == 0 else 0)
+
+    e2e_rows, e2e_rows_cap = None, 0
+    if world > 1 and rank == 0:
+        e2e_rows_cap = max(int(nmatch), 1)
+        e2e_rows = C.c_void_p()
+        check(lib.mcu_host_alloc(C.byref(e2e_rows), e2e_rows_cap * 24))
 
     for _ in range(2):
         step_e2e()
@@ -644,7 +653,7 @@ def main():
         "data": "synthetic", "config": config_dict(args, weight, seed), "matches": int(nmatch), "seed_pairs": int(stats[0]),
         "device_ms_per_step": dev_ms,
         "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": int(nbases), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * dte / args.steps, "api": "mcu_find_mums(host buffers)" if world == 1 else "mcu_session_upload + enumerate, NCCL all-reduce of the seed bitmap, finish, NCCL gather, mcu_session_merge"},
+                "ms_per_step": 1e3 * dte / args.steps, "api": "mcu_find_mums(host buffers)" if world == 1 else "mcu_session_upload + enumerate, NCCL all-reduce of the seed bitmap, finish, NCCL gather, mcu_session_merge, mcu_session_download (rank 0)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "dp": dp, "hmm": hmm, "buildindex": bidx,
     }
     emit(line)
