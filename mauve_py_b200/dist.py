@@ -63,7 +63,7 @@ def gather_rows(rows: torch.Tensor, dst: int = 0, group=None):
     n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
     counts = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
+    counts = torch.cat(counts).tolist()   # one device->host read for all ranks' counts
     rows = rows.contiguous()
     if rank == dst:
         parts = [torch.empty((c, 3), dtype=torch.int64, device=rows.device) for c in counts]
@@ -105,7 +105,7 @@ def gather_bytes(payload: bytes, dst: int = 0, group=None, device=None):
     n = torch.tensor([buf.numel()], dtype=torch.int64, device=device)
     counts = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
+    counts = torch.cat(counts).tolist()
     if rank == dst:
         parts = [torch.empty(c, dtype=torch.uint8, device=device) for c in counts]
         parts[dst] = buf
