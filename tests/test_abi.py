@@ -87,3 +87,18 @@ def test_product_does_not_touch_oracle():
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "libmauve_oracle" not in txt and "libmauve_ref" not in txt and "mauve_oracle.c" not in txt, f
                 assert not re.search(r"^\s*(from|import)\s+_oracle", txt, flags=re.M), f
+
+
+def test_ctypes_prototypes_match_the_header_arity():
+    """every prototype of include/mauve_cuda.h has as many parameters as the ctypes binding declares (no compute call)"""
+    import re
+    import mauve_py_b200 as mp
+    lib = mp.lib()
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "mauve_cuda.h")).read(), flags=re.S)
+    protos = re.findall(r"\b(mcu_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text)
+    assert len(protos) == len(mp.SYMBOLS) and {n for n, _ in protos} == set(mp.SYMBOLS)
+    for name, args in protos:
+        args = args.strip()
+        n = 0 if args in ("", "void") else len(args.split(","))
+        declared = getattr(lib, name).argtypes
+        assert (declared is None and n == 0) or (declared is not None and len(declared) == n), (name, n, declared)
