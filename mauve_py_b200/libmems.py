@@ -23,7 +23,7 @@ from ._capi import CODING_SEED, SOLID_SEED, McuError, check, lib
 
 __all__ = [
     "CODING_SEED", "SOLID_SEED", "McuError", "getSeed", "getSolidSeed", "getDefaultSeedWeight", "getSeedLength", "getSeedWeight",
-    "bmer", "DNAMemorySML", "Match", "MatchList", "MemHash", "PairwiseMatchFinder", "AnchorSession", "merge_matches",
+    "bmer", "DNAMemorySML", "read_sslist", "write_sslist", "Match", "MatchList", "MemHash", "PairwiseMatchFinder", "AnchorSession", "merge_matches",
     "PWPath", "GlobalAlign", "GlobalAlignBatch", "GlobalAlignBatchWild", "Params", "hmm_params", "getAdaptedHoxdMatrixParameters", "adaptToPercentIdentity",
     "run", "run_batch", "sort_pairs", "SeedOccurrenceList", "GetPairwiseAnchorScore", "anchor_scores", "hoxd_matrix",
 ]
@@ -128,6 +128,17 @@ class DNAMemorySML:
         """leave this list on disk as `path` (normally <fasta>.sslist) in DNAFileSML's format"""
         write_sslist(path, self._length, self._seed, self._packed, self._pos)
 
+    def LoadFile(self, path, seq=None):
+        """take the list from a `.sslist` file (FileSML::LoadFile2's return code; 0 = loaded).  The file holds no mers (the reference
+        recomputes them with GetSeedMer on every Read): mers() stays empty unless the list is rebuilt with Create."""
+        code, header, packed, positions = read_sslist(path)
+        if code != 0:
+            return code
+        self._pos, self._packed, self._mer = positions, packed, np.zeros(0, dtype=np.uint64)
+        self._seed, self._length = int(header["seed"]), int(header["length"])
+        self._seq = np.zeros(0, dtype=np.uint8) if seq is None else seq
+        return 0
+
     def mers(self):
         return self._mer
 
@@ -219,6 +230,41 @@ def write_sslist(path, seq_length, seed, packed, positions):
         f.write(h.tobytes())
         f.write(packed.tobytes())
         f.write(positions.tobytes())
+
+
+def read_sslist(path):
+    """FileSML::LoadFile2 (LM/FileSML.cpp:120-195) for a `<fasta>.sslist` file: returns (code, header, packed, positions) with the
+    reference's return codes -- 0 ok, 1 file cannot be opened, 2 short header, 3 format version other than DNAFileSML's, 4 short
+    sequence data, 5 position array shorter than header.length entries -- and None for what could not be read.  header: dict of the
+    SMLHeader fields the reference reads (LM/SortedMerList.h:48-63).  packed: ceil(2n/32) + 2 words; positions: the uint32 array of
+    n - seed_length + 1 sorted ranks (the file reserves `length` entries after the sequence, :175-176; DNAFileSML::Create writes
+    SMLLength() of them, LM/FileSML.cpp:432-445)."""
+    import struct
+    try:
+        f = open(path, "rb")
+    except OSError:
+        return 1, None, None, None
+    with f:
+        raw = f.read(SML_HEADER_BYTES)
+        if len(raw) < SML_HEADER_BYTES:
+            return 2, None, None, None
+        version, abits, seed, slen, sweight, length, unique_mers, word_size = struct.unpack_from("<IIQIIQII", raw, 0)
+        if version != SML_FORMAT_VERSION:
+            return 3, None, None, None
+        header = {"version": version, "alphabet_bits": abits, "seed": seed, "seed_length": slen, "seed_weight": sweight, "length": length,
+                  "unique_mers": unique_mers, "word_size": word_size, "little_endian": raw[40], "circular": raw[44],
+                  "translation_table": np.frombuffer(raw, dtype=np.uint8, count=255, offset=45).copy()}
+        seq_len = length + (slen - 1 if header["circular"] else 0)
+        words = (seq_len * abits) // 32 + (1 if (seq_len * abits) % 32 else 0) + 2
+        buf = f.read(4 * words)
+        if len(buf) < 4 * words:
+            return 4, header, None, None
+        packed = np.frombuffer(buf, dtype="<u4").copy()
+        npos = max(length - slen + 1, 0) if slen else 0
+        buf = f.read(4 * npos)
+        if len(buf) < 4 * npos:
+            return 5, header, packed, None
+        return 0, header, packed, np.frombuffer(buf, dtype="<u4").copy()
 
 
 def WriteList(rows, stream, seq_filenames=("null", "null"), seq_lengths=(0, 0)):

@@ -223,6 +223,62 @@ def test_sslist_files_are_loaded_by_the_unmodified_binary(tmp_path, orc):
     assert loaded == plain
 
 
+@needs_bin
+def test_sslist_reader_on_the_reference_binarys_own_files(tmp_path, orc):
+    """SURVEY.md 8f-3, the reading side: mauve_py_b200.libmems.read_sslist (= FileSML::LoadFile2, LM/FileSML.cpp:120-195) on the
+    `.sslist` the UNMODIFIED binary leaves next to its FASTA input: header fields, the 2-bit sequence and the sorted positions are
+    the oracle's sorted mer list (same mer at every rank, same position multiset inside every equal-mer run: SURVEY.md 8a-4);
+    LoadFile2's return codes for files cut short; write_sslist -> read_sslist round trip."""
+    import _oracle
+    import mauve_py_b200 as mp
+    from mauve_py_b200 import synth
+    L_ = mp.libmems
+    a, b = synth.small_pair(60000, seed=33, snp=0.03, n_inv=1)
+    d = str(tmp_path)
+    for name, s in (("a", a), ("b", b)):
+        with open(os.path.join(d, name + ".fa"), "wb") as f:
+            f.write(b">" + name.encode() + b"\n" + b"\n".join(s[i:i + 80] for i in range(0, len(s), 80)) + b"\n")
+    r = subprocess.run([BINARY, "--output=x.xmfa", "a.fa", "b.fa"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-300:]
+    seed = mp.getSeed(mp.getDefaultSeedWeight((len(a) + len(b)) // 2), mp.CODING_SEED)
+    lib = _oracle.oracle()
+    for name, s in (("a", a), ("b", b)):
+        path = os.path.join(d, name + ".fa.sslist")
+        code, h, packed, pos = L_.read_sslist(path)
+        assert code == 0
+        assert (h["version"], h["alphabet_bits"], h["seed"], h["length"], h["circular"]) == (L_.SML_FORMAT_VERSION, 2, seed, len(s), 0)
+        assert h["seed_length"] == mp.getSeedLength(seed) and h["seed_weight"] == mp.getSeedWeight(seed)
+        want = np.zeros(int(lib.orc_packed_words(len(s))), dtype=np.uint32)
+        lib.orc_pack(s, len(s), want.ctypes.data)
+        core = (2 * len(s) + 31) // 32   # the reference leaves its two pad words uninitialised
+        assert packed.size == want.size and np.array_equal(packed[:core], want[:core])
+        opos, omer = orc.sml_build(s, seed)
+        assert pos.size == opos.size == len(s) - h["seed_length"] + 1
+        mer_at = np.empty(len(s), dtype=np.uint64)
+        mer_at[opos] = omer                                  # canonical seed mer of every position, from the oracle
+        assert np.array_equal(mer_at[pos], omer)             # the reference's file: same mer at every rank
+        key = np.lexsort((pos, mer_at[pos]))                 # ties position-ascending == the oracle's (and the device's) order
+        assert np.array_equal(pos[key], opos)
+        sml = mp.DNAMemorySML()
+        assert sml.LoadFile(path) == 0 and sml.SMLLength() == pos.size and sml.Seed() == seed and sml.Length() == len(s)
+        # files cut short: LoadFile2's codes
+        raw = open(path, "rb").read()
+        H = L_.SML_HEADER_BYTES
+        cases = {2: raw[:H - 1], 4: raw[:H + 4 * packed.size - 1], 5: raw[:-1], 3: b"\x04" + raw[1:]}
+        for want_code, data in cases.items():
+            q = os.path.join(d, "cut%d.sslist" % want_code)
+            open(q, "wb").write(data)
+            assert L_.read_sslist(q)[0] == want_code
+            assert mp.DNAMemorySML().LoadFile(q) == want_code
+        assert L_.read_sslist(os.path.join(d, "absent.sslist"))[0] == 1
+        # round trip of our writer
+        q = os.path.join(d, "rt.sslist")
+        L_.write_sslist(q, len(s), seed, want, opos)
+        code, h2, packed2, pos2 = L_.read_sslist(q)
+        assert code == 0 and np.array_equal(packed2, want) and np.array_equal(pos2, opos) and h2["seed"] == seed and h2["little_endian"] == 1
+        assert np.array_equal(h2["translation_table"], h["translation_table"])
+
+
 # ---- progressiveMauve_cuda / progressiveMauve_cuda_mh: the reference binary with link-time seams (adapters/seams) ---------------
 CUDA_BINARY = os.path.join(REF_DIR, "progressiveMauve_cuda")         # gapped DP of every window on the device
 CUDA_MH_BINARY = os.path.join(REF_DIR, "progressiveMauve_cuda_mh")   # + MemHash::FindMatches of two genomes on the device
