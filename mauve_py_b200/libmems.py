@@ -121,6 +121,87 @@ class DNAMemorySML:
     def __getitem__(self, index: int) -> bmer:
         return bmer(int(self._pos[index]), int(self._mer[index]))
 
+    # ---- host-side accessors the reference's callers use besides Read; plain integer code on the packed sequence ----
+    def _forward_mer(self, position: int) -> int:
+        """SortedMerList::GetMer (LM/SortedMerList.cpp:321-342): the SeedLength() bases at `position`, left-aligned in 64 bits"""
+        w, bit = (2 * position) // 32, (2 * position) % 32
+        seq = self._packed
+        x = (int(seq[w]) << 32) | int(seq[w + 1])
+        if bit:
+            x = ((x << bit) | (int(seq[w + 2]) >> (32 - bit))) & 0xFFFFFFFFFFFFFFFF
+        L = self.SeedLength()
+        return x & (((1 << 64) - 1) ^ ((1 << (64 - 2 * L)) - 1))
+
+    @staticmethod
+    def _revcomp_mer(mer: int, length: int) -> int:
+        """SortedMerList::RevCompMer (:597-614): complement, reverse the 2-bit groups, left-align, strand flag in bit 0"""
+        x = (~mer & 0xFFFFFFFFFFFFFFFF) >> (64 - 2 * length)
+        rc = 0
+        for _ in range(length):
+            rc = (rc << 2) | (x & 3)
+            x >>= 2
+        return ((rc << (64 - 2 * length)) & 0xFFFFFFFFFFFFFFFF) | 1
+
+    def GetMer(self, position: int) -> int:
+        """DNAMemorySML::GetMer = SortedMerList::GetDnaMer (LM/DNAMemorySML.cpp:35-37, LM/SortedMerList.cpp:581-593): the smaller of the
+        contiguous SeedLength()-mer at `position` and its reverse complement"""
+        fwd = self._forward_mer(position)
+        rc = self._revcomp_mer(fwd, self.SeedLength())
+        return fwd if fwd < rc else rc
+
+    def _forward_seed_mer(self, position: int) -> int:
+        """SortedMerList::GetSeedMer (:726-762): the bases under the 1s of the seed pattern (pattern MSB = first base), left-aligned"""
+        mer, L, w = self._forward_mer(position), self.SeedLength(), self.SeedWeight()
+        out = 0
+        for i in range(L):
+            if (self._seed >> (L - 1 - i)) & 1:
+                out = (out << 2) | ((mer >> (62 - 2 * i)) & 3)
+        return (out << (64 - 2 * w)) & 0xFFFFFFFFFFFFFFFF
+
+    def GetDnaSeedMer(self, position: int) -> int:
+        """SortedMerList::GetDnaSeedMer (:764-769): the smaller of the forward seed mer and its reverse complement (strand flag in
+        bit 0); a tie keeps the forward one"""
+        fwd = self._forward_seed_mer(position)
+        rc = self._revcomp_mer(fwd, self.SeedWeight())
+        return fwd if fwd < rc else rc
+
+    def GetSeedMer(self, position: int) -> int:
+        """DNAMemorySML::GetSeedMer = GetDnaSeedMer (LM/DNAMemorySML.cpp:39-41): what ExtendMatch and operator[] compare"""
+        return self.GetDnaSeedMer(position)
+
+    def FindMer(self, query_mer: int):
+        """SortedMerList::FindMer (:170-179) over bsearch (:380-394) -> (found, rank): the rank the recursion stops at (where the mer
+        would be when it is absent), found = the mer AT that rank equals the query (strand flag included, as operator[] returns it)"""
+        last = self._length
+        L = self.SeedLength()
+        if last == 0 or last < L:
+            return False, 0
+        start, end = 0, last - L
+        while True:
+            middle = (start + end) // 2
+            m = int(self._mer[middle])
+            if m == query_mer:
+                break
+            if m < query_mer and middle < end:
+                start = middle + 1
+            elif m > query_mer and start < middle:
+                end = middle - 1
+            else:
+                break
+        return int(self._mer[middle]) == query_mer, middle
+
+    def Clone(self):
+        """gnClone::Clone: an independent copy"""
+        c = DNAMemorySML()
+        c._pos, c._mer, c._packed = self._pos.copy(), self._mer.copy(), self._packed.copy()
+        c._seed, c._length, c._seq = self._seed, self._length, self._seq
+        return c
+
+    def GetHeader(self):
+        """the SMLHeader fields Create sets (LM/SortedMerList.cpp:786-824)"""
+        return {"version": SML_FORMAT_VERSION, "alphabet_bits": 2, "seed": self._seed, "seed_length": self.SeedLength(),
+                "seed_weight": self.SeedWeight(), "length": self._length, "unique_mers": 0xFFFFFFFF, "circular": 0}
+
     def positions(self):
         return self._pos
 
@@ -146,13 +227,6 @@ class DNAMemorySML:
         """SortedMerList::sequence: 2-bit packed, MSB first, two zero pad words."""
         return self._packed
 
-    def FindMer(self, query_mer: int):
-        """SortedMerList::FindMer (LM/SortedMerList.cpp:170-179): binary search on mer & seed mask."""
-        mask = np.uint64(self.GetSeedMask())
-        keys = self._mer & mask
-        q = np.uint64(query_mer) & mask
-        i = int(np.searchsorted(keys, q, side="left"))
-        return (i < keys.size and keys[i] == q), i
 
 
 # ---- LM/Match.h, LM/MatchList.h -----------------------------------------------------------------

@@ -85,6 +85,29 @@ long long ref_pack(const char* seq, uint64_t n, uint32_t* out, uint64_t out_word
 	} catch (...) { return -1; }
 }
 
+// FindMer for every query (LM/SortedMerList.cpp:170-179, bsearch :380-394) and GetMer / GetSeedMer / GetDnaSeedMer at every probe
+// position (:321-342, :726-769) on the list the reference builds for `seq`.  found_out / rank_out: nq entries; the three mer arrays: np.
+long long ref_sml_probe(const char* seq, uint64_t n, uint64_t seed, const uint64_t* queries, uint64_t nq, uint8_t* found_out, uint64_t* rank_out,
+                        const uint64_t* positions, uint64_t np, uint64_t* getmer_out, uint64_t* seedmer_out, uint64_t* dnaseedmer_out)
+{
+	try {
+		gnSequence s(string(seq, n));
+		DNAMemorySML sml;
+		sml.Create(s, seed);
+		for (uint64_t i = 0; i < nq; ++i) {
+			gnSeqI r = 0;
+			found_out[i] = sml.FindMer(queries[i], r) ? 1 : 0;
+			rank_out[i] = (uint64_t)r;
+		}
+		for (uint64_t i = 0; i < np; ++i) {
+			getmer_out[i] = sml.GetMer((gnSeqI)positions[i]);
+			seedmer_out[i] = sml.GetSeedMer((gnSeqI)positions[i]);
+			dnaseedmer_out[i] = sml.GetDnaSeedMer((gnSeqI)positions[i]);
+		}
+		return (long long)sml.SMLLength();
+	} catch (...) { return -1; }
+}
+
 // ---- MUMs ----------------------------------------------------------------
 struct ref_match { int64_t len; int64_t start0; int64_t start1; };
 

@@ -195,3 +195,50 @@ def test_match_list_file_format_round_trips_through_the_reference(refc):
     assert e.getvalue() == "" and lib.ref_read_list(b"", C.byref(out)) == -1
     with pytest.raises(ValueError):
         mp.libmems.ReadList(io.StringIO("FormatVersion\t2\n"))
+
+
+def test_sml_accessors_against_the_reference_classes(orc):
+    """The host-side accessors of the sorted mer list that the reference's callers use besides Read: GetMer, GetSeedMer,
+    GetDnaSeedMer (LM/SortedMerList.cpp:321-342, :726-769, RevCompMer :597-614) and FindMer / bsearch (:170-179, :380-394) of the Python
+    mirror equal the reference's DNAMemorySML on the same list (oracle/_ref, ref_sml_probe): every probe position, present and absent
+    query mers, the rank bsearch stops at included.  The mirror is filled from the oracle's list here (no device on this machine)."""
+    import ctypes as C
+    import _oracle
+    import mauve_py_b200 as mp
+    from mauve_py_b200 import synth
+    if not _oracle.have_ref():
+        pytest.skip("oracle/_ref/libmauve_ref.so not built (needs /root/reference)")
+    ref, lib = _oracle.ref(), _oracle.oracle()
+    ref.ref_sml_probe.restype = C.c_longlong
+    ref.ref_sml_probe.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64] + [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p] + \
+        [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    a, _ = synth.small_pair(30000, seed=12)
+    rep = (b"ACGTTGCA" * 400) + a[:3000] + (b"A" * 500) + a[:3000]   # repeats: long equal-mer runs for bsearch to land in
+    for seq, (w, r) in ((a, (15, 3)), (a, (11, 0)), (rep, (9, 0)), (a[:40], (5, 0)), (a, (21, 0)), (a, (19, 3))):
+        seed = mp.getSeed(w, r)
+        pos, mer = orc.sml_build(seq, seed)
+        sml = mp.DNAMemorySML()
+        sml._pos, sml._mer, sml._seed, sml._length = pos, mer, seed, len(seq)
+        sml._packed = np.zeros(int(lib.orc_packed_words(len(seq))), dtype=np.uint32)
+        lib.orc_pack(seq, len(seq), sml._packed.ctypes.data)
+        probes = np.unique(np.concatenate([rng.integers(0, pos.size, 300), [0, pos.size - 1]])).astype(np.uint64)
+        present = mer[rng.integers(0, mer.size, 200)]
+        queries = np.concatenate([present, present ^ np.uint64(1), present + np.uint64(1 << 20), rng.integers(0, 2**63, 100).astype(np.uint64) * np.uint64(2),
+                                  np.array([0, 2**64 - 1, int(mer[0]), int(mer[-1])], dtype=np.uint64)]).astype(np.uint64)
+        found, rank = np.zeros(queries.size, dtype=np.uint8), np.zeros(queries.size, dtype=np.uint64)
+        gm, sm, dm = (np.zeros(probes.size, dtype=np.uint64) for _ in range(3))
+        n = ref.ref_sml_probe(seq, len(seq), seed, queries.ctypes.data, queries.size, found.ctypes.data, rank.ctypes.data,
+                              probes.ctypes.data, probes.size, gm.ctypes.data, sm.ctypes.data, dm.ctypes.data)
+        assert n == pos.size
+        for k, p in enumerate(probes):
+            assert (sml.GetMer(int(p)), sml.GetSeedMer(int(p)), sml.GetDnaSeedMer(int(p))) == (int(gm[k]), int(sm[k]), int(dm[k])), (w, r, int(p))
+        # the mer the list holds at a rank is GetDnaSeedMer of its position (MemorySML::operator[], LM/MemorySML.cpp:88-94)
+        for i in rng.integers(0, pos.size, 100):
+            assert sml.GetDnaSeedMer(int(pos[i])) == int(mer[i])
+        for k, q in enumerate(queries):
+            ok, at = sml.FindMer(int(q))
+            assert (ok, at) == (bool(found[k]), int(rank[k])), (w, r, hex(int(q)))
+        c = sml.Clone()
+        c._pos[0] ^= 1
+        assert sml._pos[0] != c._pos[0] and sml.GetHeader()["seed"] == seed and c.GetHeader()["length"] == len(seq)

@@ -176,3 +176,21 @@ def test_nw_wild_errors(mp):
     with pytest.raises(mp.McuError):
         mp.GlobalAlignBatchWild([(b"", b"ACGT")])
     assert mp.GlobalAlignBatchWild([]) == []
+
+
+def test_sml_accessors_on_a_device_built_list(mp, orc):
+    """GetMer / GetSeedMer / FindMer of the mirror on a list built by mcu_sml_build: the mer at every sampled rank is
+    GetSeedMer(position) (MemorySML::operator[], LM/MemorySML.cpp:88-94) and FindMer stops on a rank holding the query"""
+    a, _ = synth.small_pair(40000, seed=8)
+    for w, r in ((15, 3), (11, 0), (21, 0)):
+        seed = mp.getSeed(w, r)
+        sml = mp.DNAMemorySML()
+        sml.Create(a, seed)
+        rng = np.random.default_rng(w)
+        for i in rng.integers(0, sml.SMLLength(), 200):
+            b = sml[int(i)]
+            assert sml.GetSeedMer(b.position) == b.mer
+            found, at = sml.FindMer(b.mer)
+            assert found and int(sml.mers()[at]) == b.mer
+        assert sml.FindMer(int(sml.mers()[-1]) + 2)[0] is False or int(sml.mers()[-1]) + 2 in sml.mers()
+        assert sml.Clone().SMLLength() == sml.SMLLength() and sml.GetHeader()["seed"] == seed
