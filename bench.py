@@ -652,6 +652,9 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64" if kb == 8 else "u32",
         "data": "synthetic", "config": config_dict(args, weight, seed), "matches": int(nmatch), "seed_pairs": int(stats[0]),
         "device_ms_per_step": dev_ms,
+        "timing": "value/ms_per_step: K steps between barrier + device synchronisation on both sides, max over ranks (a step has host-visible "
+                  "synchronisation points of its own, so this is the whole step); device_ms_per_step, roofline launch_ms and kernel_ms: CUDA "
+                  "events recorded by the library on the stream it launches on (rank 0)",
         "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": int(nbases), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * dte / args.steps, "api": "mcu_find_mums(host buffers)" if world == 1 else "mcu_session_upload + enumerate, NCCL all-reduce of the seed bitmap, finish, NCCL gather, mcu_session_merge, mcu_session_download (rank 0)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "dp": dp, "hmm": hmm, "buildindex": bidx,
