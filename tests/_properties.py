@@ -129,3 +129,46 @@ def sol_expected(positions, mers, seed_mask, n, L):
     want = ((c[L:] - c[:-L]).astype(np.float64) / float(L)).astype(np.float32)
     want[n - 1] = np.float32(raw[n - 1])
     return want
+
+
+# ---- the integer recurrence csrc/dp.cu is built on (header comment there), cell by cell in plain Python -----------------------------
+# biased=False: as the kernel evaluates it today (D' = D - 200, I' = I - 200, M - 400 carried); biased=True: the form of
+# experiments/README.md (gap states + 400, M carried).  Returns the four traceback predicates per cell and the final (M, D, I).
+NW_NINF = -(1 << 29)
+NW_SUB = np.array([[151, -54, 29, -63], [-54, 160, -65, 29], [29, -65, 160, -54], [-63, 29, -54, 151]])  # NUC_SP + 60 (MU/nucmx.cpp:8-25), A C G T
+
+
+def nw_integer_recurrence(a, b, biased=False):
+    la, lb = len(a), len(b)
+    bias = 400 if biased else 0
+    # row 0 / column 0 as in dp.cu: best[0][0] = 0 (-200 if la == 1), best[i][0] = best[0][j] = -200; no M, D', I' outside the matrix
+    best_prev = [(-200 if la == 1 else 0)] + [-200] * lb
+    Mrow_prev = [NW_NINF] * (lb + 1)      # the CARRIED M of row i-1: M - 400 today, M in the biased form; NW_NW_NINF outside the matrix in both
+    Drow_prev = [NW_NINF] * (lb + 1)      # D state of row i-1 (biased or not)
+    bits = np.zeros((la, lb), dtype=np.uint8)
+    last = None
+    for i in range(la):
+        best_row = [-200] + [0] * lb
+        Mrow = [NW_NINF] * (lb + 1)
+        Drow = [NW_NINF] * (lb + 1)
+        I_left, M_left = NW_NINF, NW_NINF
+        for j in range(1, lb + 1):
+            M = NW_SUB[a[i], b[j - 1]] + best_prev[j - 1]
+            upM, upD = Mrow_prev[j], Drow_prev[j]
+            D = max(upD, upM)
+            I = max(I_left, M_left)
+            if biased:
+                best = max(max(D, I) - 400, M)
+                b0 = best > M
+                carried = M
+            else:
+                best = max(M, max(D, I))
+                b0 = max(D, I) > M
+                carried = M - 400
+            b1, b2, b3 = I > D, upM >= upD, M_left >= I_left
+            bits[i, j - 1] = b0 | (b1 << 1) | (b2 << 2) | (b3 << 3)
+            Mrow[j], Drow[j], best_row[j] = carried, D, best
+            I_left, M_left = I, carried
+            last = (M, D + 200 - bias, I + 200 - bias)   # what nw_region stores as the result: (M, D, I) = (M, D' + 200, I' + 200)
+        best_prev, Mrow_prev, Drow_prev = best_row, Mrow, Drow
+    return bits, last

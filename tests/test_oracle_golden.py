@@ -119,6 +119,62 @@ def test_property_checkers_nw_and_mers(orc):
         assert np.array_equal(P.canonical_mers(a, seed, L, wt, pos), mer)
 
 
+def _path_from_predicates(bits, last, la, lb):
+    """nw_traceback_kernel's walk (csrc/dp.cu) over the four predicates per cell: bit0 = best is not M, bit1 = I beats D,
+    bit2 = D came from M, bit3 = I came from M; cells of row / column 1 take the kernel's first-row / first-column rule"""
+    M, D, I = last
+    edge, sc = "M", M
+    if D > sc:
+        edge, sc = "D", D
+    if I > sc:
+        edge, sc = "I", I
+    pa, pb, out = la, lb, []
+    nib = lambda i, j: int(bits[i - 1, j - 1])
+    while True:
+        out.append(edge)
+        if edge == "M":
+            if pa >= 2 and pb >= 2:
+                nb = nib(pa - 1, pb - 1)
+                x = (nb & 1) + (nb & (nb >> 1) & 1)
+                nxt = "MDI"[x]
+            else:
+                nxt = "D" if pa >= 2 else "I"
+            pa, pb = pa - 1, pb - 1
+        elif edge == "D":
+            nxt = "M" if (pb >= 1 and nib(pa, pb) & 4) else "D"
+            pa -= 1
+        else:
+            nxt = "M" if (pa >= 1 and nib(pa, pb) & 8) else "I"
+            pb -= 1
+        if pa == 0 and pb == 0:
+            break
+        edge = nxt
+        assert not ((edge == "M" and (pa == 0 or pb == 0)) or (edge == "D" and pa == 0) or (edge == "I" and pb == 0))
+    return "".join(reversed(out)), sc
+
+
+def test_integer_recurrence_of_the_dp_kernel_equals_nwsmall_on_every_tiny_region(orc):
+    """the integer recurrence csrc/dp.cu is built on (its header: D' = D - 200, I' = I - 200, terminal gaps folded into the first row
+    and column, la == 1 special case) and the kernel's traceback walk, restated in plain Python (tests/_properties.py), give the
+    oracle's NWSmall path and score for EVERY pair of sequences up to 3 x 3 (7,056 pairs: all first-row / first-column / la == 1 /
+    lb == 1 cases) and for random longer ones; the biased form proposed in experiments/README.md gives the same predicates"""
+    import itertools
+    import _properties as P
+    L = b"ACGT"
+    todo = [(a, b) for la in (1, 2, 3) for lb in (1, 2, 3) for a in itertools.product(range(4), repeat=la) for b in itertools.product(range(4), repeat=lb)]
+    rng = np.random.default_rng(12)
+    todo += [(tuple(rng.integers(0, 4, int(rng.integers(1, 40)))), tuple(rng.integers(0, 4, int(rng.integers(1, 40))))) for _ in range(60)]
+    for a, b in todo:
+        bits, last = P.nw_integer_recurrence(np.array(a), np.array(b), biased=False)
+        path, sc = _path_from_predicates(bits, last, len(a), len(b))
+        opath, osc = orc.nw_align(bytes(L[i] for i in a), bytes(L[i] for i in b))
+        opath = opath.decode() if isinstance(opath, bytes) else "".join(opath)
+        assert sc == osc and path == opath, (a, b, path, opath, sc, osc)
+        if len(a) * len(b) > 4:
+            bits2, last2 = P.nw_integer_recurrence(np.array(a), np.array(b), biased=True)
+            assert np.array_equal(bits, bits2) and (last == last2 or min(last) < P.NW_NINF // 2)
+
+
 def _real_dp_calls():
     import ast
     z = _golden.npz("dp_mds42_calls.npz")
