@@ -12,6 +12,7 @@
 #   seams.log             reference binary vs the seam binaries on the MDS42 pair (wall seconds, XMFA sha1, seam reports)
 #   dropin*.log           the C++ drop-in checks with their own timings
 #   config5.json, config4.jsonl   BASELINE configs 5 (50,000 regions) and 4 (1 Gbp weight sweep)
+#   ab/, ab.log           (AB=1) tools/gpu_ab_patch.sh: every experiments/*.patch against this tree
 set -u
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 mkdir -p gpurun_out
@@ -72,5 +73,7 @@ timeout 300 oracle/_ref/dropin_check hmm 5000000 9 > gpurun_out/dropin_hmm.log 2
 # BASELINE configs 4 and 5 at (or near) full size
 timeout 500 python tools/config5_dp.py --regions 50000 > gpurun_out/config5.json 2> gpurun_out/config5.err
 timeout 900 python tools/config4_sweep.py --gbp 1.0 --reps 1 > gpurun_out/config4.jsonl 2> gpurun_out/config4.err
+# A/B of the unverified patches under experiments/ against this tree (adds ~8 minutes): AB=1 bash tools/gpu_session.sh
+[ "${AB:-0}" = 1 ] && timeout 1500 bash tools/gpu_ab_patch.sh > gpurun_out/ab.log 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/nvidia_smi.csv 2>&1
 echo done
