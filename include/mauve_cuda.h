@@ -33,6 +33,7 @@ extern "C" {
 #define MCU_EGAP (-4)     /* '-' in a genome sequence: the reference throws (LM/SortedMerList.cpp:433-437) */
 #define MCU_ENOMEM (-5)
 #define MCU_EALPHA (-6)   /* DP input outside ACGT (integer-exact kernel only) */
+#define MCU_ESMALL (-7)   /* caller-provided output buffer too small; the required size is reported */
 
 /* One ungapped match, exactly the fields of a reference match-list row
  * (LM/MatchList.h:617-662 WriteList: length, start0, start1; 1-based, start1 < 0 = reverse strand). */
@@ -92,6 +93,13 @@ int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed,
 int mcu_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule,
                   mcu_match** out, uint64_t* n_out, uint64_t* stats);
 
+/* The same call with the rows written into CALLER memory (pinned memory from mcu_host_alloc makes the device-to-host copy a
+ * plain DMA): rows_out has room for cap rows; *n_out = rows found; MCU_ESMALL (nothing copied) when they do not fit.
+ * Inputs of 8 MB and more are uploaded in pieces on a copy stream and the 2-bit pack + first partition pass of a piece run
+ * under the copies of the next ones (mcu_find_mums does the same).                                                        */
+int mcu_find_mums_into(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule,
+                       mcu_match* rows_out, uint64_t cap, uint64_t* n_out, uint64_t* stats);
+
 /* ---- batched gap search: replaces the per-gap calls of recursive anchoring, pairwiseAnchorSearch
  *      (LM/ProgressiveAligner.cpp:590-679, called for every gap by recurseOnPairs :681-924) and the pairwise part of
  *      SearchLCBGaps (LM/Aligner.cpp:784-930): per gap two DNAMemorySML::Create + MemHash::FindMatches with the MUM
@@ -117,6 +125,9 @@ int mcu_session_create(mcu_session** out);
 void mcu_session_destroy(mcu_session* s);
 /* H2D of both genomes (async on the session stream, then synchronised). */
 int mcu_session_upload(mcu_session* s, const char* seq0, uint64_t n0, const char* seq1, uint64_t n1);
+/* The same copy in `chunks` pieces per genome on a copy stream, returning at once: the next mcu_session_run packs and
+ * partitions every piece as it lands.  The host buffers must stay valid until that run has returned.                 */
+int mcu_session_upload_begin(mcu_session* s, const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, int chunks);
 /* pack + enumerate + extend + order on the session stream.  stage_ms (optional, 16 floats, CUDA-event
  * times in ms): [0] pack, [1] seed generation (+ level-1 scatter), [2] sort (or level-2 scatter),
  * [3] join (or in-bucket grouping), [4] candidates + extend, [5] order + replay, [6] total,
@@ -157,6 +168,39 @@ uint64_t mcu_session_launch_count(const mcu_session* s);
  * (mcu_session_run with shard_count 1), which replays such buckets exactly.                          */
 int mcu_merge_matches(const mcu_match* rows, uint64_t n, int in_device, mcu_match** out, uint64_t* n_out,
                       uint64_t* unclean_buckets_out);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink inside this library.  The reference has no distributed
+ *      match finder; its closest relative is ParallelMemHash (LM/ParallelMemHash.cpp:63-101: OpenMP threads over mer ranges of
+ *      the sorted lists, one MemHash per thread, merged afterwards).  Here every seed is owned by the rank its mer hashes to.
+ *      Start-up: rank 0 calls mcu_comm_unique_id and hands the 128 bytes to the other ranks by any means (file, socket, MPI,
+ *      torch.distributed store); every rank then calls mcu_init(local device) and mcu_comm_init(rank, world, id).
+ *      All entry points below are COLLECTIVE: every rank calls them with the same arguments, in the same order.            */
+#define MCU_COMM_ID_BYTES 128
+int mcu_comm_unique_id(void* id_out);
+int mcu_comm_init(int rank, int world, const void* id);
+void mcu_comm_destroy(void);
+int mcu_comm_rank(void);
+int mcu_comm_world(void);
+/* device synchronise + a one-word all-reduce: every rank has finished what it enqueued before any rank returns */
+int mcu_comm_barrier(void);
+/* in-place all-reduce of n host doubles; op: 0 sum, 1 max, 2 min (timing: max over ranks) */
+int mcu_comm_allreduce_f64(double* v, int n, int op);
+/* variable-length gather of host bytes to rank 0 over NCCL send/recv (DP paths, HMM predictions of a sharded batch).
+ * Rank 0: *out = concatenation in rank order (library-owned, mcu_free), counts_out[world] = bytes per rank; others: *out = NULL */
+int mcu_comm_gather_bytes(const void* send, uint64_t n, void** out, uint64_t* counts_out);
+int mcu_device_synchronize(void);
+/* H2D of the slice of both genomes this rank packs (1 / world of each, asynchronous on the session stream); with world == 1
+ * the same as mcu_session_upload.  A session filled by mcu_session_upload (whole genomes on every rank) works as well.    */
+int mcu_session_upload_sharded(mcu_session* s, const char* seq0, uint64_t n0, const char* seq1, uint64_t n1);
+/* One seed + match + extend pass sharded over the ranks, all on the session's stream: pack 1 / world + ncclAllGather of the
+ * packed genomes, enumeration of this rank's seeds, ncclAllReduce(SUM == OR) of the unique-seed bitmaps, extension,
+ * ncclAllGather of the row counts, ncclSend / ncclRecv of the rows to rank 0, merge there (reference list order + exact
+ * bucket replay).  Afterwards rank 0's session holds the complete list (mcu_session_match_count / mcu_session_download);
+ * stats as in mcu_find_mums, summed over the ranks; stage_ms[6] = the whole step on this rank.                             */
+int mcu_session_run_sharded(mcu_session* s, uint64_t seed, float* stage_ms, uint64_t* stats);
+/* mcu_find_mums_into as a collective: host buffers in, rows in rank 0's rows_out (other ranks: *n_out only). */
+int mcu_find_mums_sharded(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule,
+                          mcu_match* rows_out, uint64_t cap, uint64_t* n_out, uint64_t* stats);
 
 /* ---- gapped DP: replaces muscle::GlobalAlign (MU/glbalign.cpp:69-81 -> NWSmall
  *      MU/nwsmall.cpp:500-670 + BitTraceBack MU/bittraceback.cpp:138-) for batches of

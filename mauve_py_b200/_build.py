@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmauve_cuda.so")
-SOURCES = ["api.cu", "radix.cu", "anchor.cu", "bucket.cu", "replay.cu", "batch.cu", "dp.cu", "hmm.cu", "sol.cu", "dpwild.cu"]
+SOURCES = ["api.cu", "radix.cu", "anchor.cu", "bucket.cu", "replay.cu", "batch.cu", "dp.cu", "hmm.cu", "sol.cu", "dpwild.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "-diag-suppress", "177"]
 
@@ -56,7 +56,7 @@ def build_library(force=False, verbose=False):
         list(ex.map(compile_one, jobs))
     objs = [os.path.join(objdir, src.replace(".cu", ".o")) for src in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        cmd = [cc, "-shared", "-cudart", "static", "-o", LIB] + objs
+        cmd = [cc, "-shared", "-cudart", "static", "-o", LIB] + objs + ["-lnccl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s" % r.stderr)

@@ -27,10 +27,10 @@ __device__ __forceinline__ u32 base_code(u32 c, u32& gap)
     return (u - 65u) < 26u ? (u32)((TABLE >> (2 * (c & 31u))) & 3ull) : 0u;
 }
 
-__global__ void __launch_bounds__(256) pack_kernel(const u8* __restrict__ seq, u64 n, u32* __restrict__ packed, u64 words_total, u32* __restrict__ err)
+__global__ void __launch_bounds__(256) pack_kernel(const u8* __restrict__ seq, u64 n, u32* __restrict__ packed, u64 word_lo, u64 word_hi, u32* __restrict__ err)
 {
     u32 gap = 0;
-    for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < words_total; w += (u64)gridDim.x * blockDim.x) {
+    for (u64 w = word_lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; w < word_hi; w += (u64)gridDim.x * blockDim.x) {
         u64 base = w * 16;
         u32 v = 0;
         if (base + 16 <= n) {
@@ -485,6 +485,7 @@ int session_init(Session& s)
     MCU_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) MCU_CUDA(cudaEventCreate(&s.ev[i]));
     for (int i = 0; i < 12; ++i) MCU_CUDA(cudaEventCreate(&s.kev[i]));
+    MCU_CUDA(cudaEventCreateWithFlags(&s.ev_aux, cudaEventDisableTiming));
     MCU_CUDA(cudaHostAlloc((void**)&s.h_counters, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     MCU_TRY(s.counters.reserve(8 * sizeof(unsigned long long)));
     MCU_CUDA(cudaHostAlloc((void**)&s.h_replay, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -503,7 +504,13 @@ void session_destroy(Session& s)
                       &s.rp_ctr, &s.rp_bitmap, &s.rp_list, &s.rp_canon, &s.rp_keys_b, &s.rp_idx_a, &s.rp_idx_b, &s.rp_p0, &s.rp_row, &s.rp_bkeys,
                       &s.rp_pool, &s.rp_extra, &s.rp_prefix, &s.rp_vinfo, &s.rp_out,
                       &s.bk_a, &s.bk_b, &s.bk_tab1, &s.bk_tab2, &s.bk_spill, &s.bk_tileseg, &s.bt_tab, &s.bt_seg_a, &s.bt_seg_b,
-                      &s.sol_raw, &s.sol_freq[0], &s.sol_freq[1], &s.as_rows, &s.as_match, &s.as_off, &s.as_lcb};
+                      &s.sol_raw, &s.sol_freq[0], &s.sol_freq[1], &s.as_rows, &s.as_match, &s.as_off, &s.as_lcb, &s.gathered, &s.comm_small};
+    if (s.copy_stream) { cudaStreamSynchronize(s.copy_stream); cudaStreamDestroy(s.copy_stream); s.copy_stream = nullptr; }
+    for (cudaEvent_t e : s.up_events) cudaEventDestroy(e);
+    s.up_events.clear();
+    if (s.ev_aux) cudaEventDestroy(s.ev_aux);
+    if (s.h_comm) cudaFreeHost(s.h_comm);
+    s.h_comm = nullptr;
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(s.ev[i]);
     for (int i = 0; i < 12; ++i) cudaEventDestroy(s.kev[i]);
@@ -517,6 +524,7 @@ int session_upload(Session& s, const char* seq0, u64 n0, const char* seq1, u64 n
 {
     const char* seq[2] = {seq0, seq1};
     u64 n[2] = {n0, n1};
+    s.up_chunks = 0;
     for (int g = 0; g < 2; ++g) {
         if (n[g] && !seq[g]) { set_error("session_upload: NULL sequence"); return MCU_EINVAL; }
         if (n[g] >= 0xFFFFFFFFull) { set_error("sequence longer than the reference's 32-bit position limit"); return MCU_EINVAL; }
@@ -528,16 +536,108 @@ int session_upload(Session& s, const char* seq0, u64 n0, const char* seq1, u64 n
     return MCU_OK;
 }
 
-static int run_pack(Session& s, int g, u32* err_flag)
+// packs words [w0, w1) of genome g (words past the end of the sequence become the zero padding)
+int session_upload_slice(Session& s, const char* seq0, u64 n0, const char* seq1, u64 n1, int rank, int world)
 {
-    u64 words = div_up(s.n[g], 16) + 2;
-    MCU_TRY(s.packed[g].reserve(words * sizeof(u32)));
-    pack_kernel<<<grid_for(words, 256, 8), 256, 0, s.stream>>>(s.ascii[g].as<u8>(), s.n[g], s.packed[g].as<u32>(), words, err_flag);
+    const char* seq[2] = {seq0, seq1};
+    u64 n[2] = {n0, n1};
+    s.up_chunks = 0;
+    for (int g = 0; g < 2; ++g) {
+        if (n[g] && !seq[g]) { set_error("session_upload_slice: NULL sequence"); return MCU_EINVAL; }
+        if (n[g] >= 0xFFFFFFFFull) { set_error("sequence longer than the reference's 32-bit position limit"); return MCU_EINVAL; }
+        MCU_TRY(s.ascii[g].reserve(n[g] + 16));
+        const u64 chunk = pack_chunk_words(n[g], world);
+        const u64 b0 = chunk * 16 * (u64)rank, b1 = chunk * 16 * (u64)(rank + 1);
+        const u64 lo = b0 < n[g] ? b0 : n[g], hi = b1 < n[g] ? b1 : n[g];
+        if (hi > lo) MCU_CUDA(cudaMemcpyAsync(s.ascii[g].as<char>() + lo, seq[g] + lo, hi - lo, cudaMemcpyHostToDevice, s.stream));
+        s.n[g] = n[g];
+    }
+    return MCU_OK;
+}
+
+int session_upload_begin(Session& s, const char* seq0, u64 n0, const char* seq1, u64 n1, int chunks)
+{
+    const char* seq[2] = {seq0, seq1};
+    u64 n[2] = {n0, n1};
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    if (!s.copy_stream) MCU_CUDA(cudaStreamCreateWithFlags(&s.copy_stream, cudaStreamNonBlocking));
+    while (s.up_events.size() < (size_t)2 * chunks) {
+        cudaEvent_t e;
+        MCU_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s.up_events.push_back(e);
+    }
+    // the copies must not overtake work of an earlier run that still reads the buffers
+    MCU_CUDA(cudaEventRecord(s.ev_aux, s.stream));
+    MCU_CUDA(cudaStreamWaitEvent(s.copy_stream, s.ev_aux, 0));
+    for (int g = 0; g < 2; ++g) {
+        if (n[g] && !seq[g]) { set_error("session_upload_begin: NULL sequence"); return MCU_EINVAL; }
+        if (n[g] >= 0xFFFFFFFFull) { set_error("sequence longer than the reference's 32-bit position limit"); return MCU_EINVAL; }
+        MCU_TRY(s.ascii[g].reserve(n[g] + 16));
+        s.n[g] = n[g];
+        const u64 cb = (div_up(div_up(n[g], (u64)chunks), 4096) * 4096);  // whole scatter tiles per piece
+        s.up_chunk_bases[g] = cb ? cb : 4096;
+    }
+    s.up_chunks = chunks;
+    for (int g = 0; g < 2; ++g)
+        for (int c = 0; c < chunks; ++c) {
+            const u64 cb = s.up_chunk_bases[g];
+            const u64 b0 = (u64)c * cb < n[g] ? (u64)c * cb : n[g];
+            const u64 b1 = c == chunks - 1 ? n[g] : ((u64)(c + 1) * cb < n[g] ? (u64)(c + 1) * cb : n[g]);
+            if (b1 > b0) MCU_CUDA(cudaMemcpyAsync(s.ascii[g].as<char>() + b0, seq[g] + b0, b1 - b0, cudaMemcpyHostToDevice, s.copy_stream));
+            MCU_CUDA(cudaEventRecord(s.up_events[(size_t)g * chunks + c], s.copy_stream));
+        }
+    return MCU_OK;
+}
+
+static int run_pack_words(Session& s, int g, u64 w0, u64 w1, u32* err_flag)
+{
+    if (w1 <= w0) return MCU_OK;
+    pack_kernel<<<grid_for(w1 - w0, 256, 8), 256, 0, s.stream>>>(s.ascii[g].as<u8>(), s.n[g], s.packed[g].as<u32>(), w0, w1, err_flag);
     s.launches++;
     return MCU_OK;
 }
 
+static int run_pack(Session& s, int g, u32* err_flag)
+{
+    const u64 words = div_up(s.n[g], 16) + 2;
+    if (s.pack_world > 1) {  // this rank's chunk; the other chunks arrive through after_pack (NCCL all-gather, comm.cu)
+        const u64 chunk = pack_chunk_words(s.n[g], s.pack_world);
+        MCU_TRY(s.packed[g].reserve(chunk * (u64)s.pack_world * sizeof(u32)));
+        return run_pack_words(s, g, chunk * (u64)s.pack_rank, chunk * (u64)(s.pack_rank + 1), err_flag);
+    }
+    MCU_TRY(s.packed[g].reserve(words * sizeof(u32)));
+    return run_pack_words(s, g, 0, words, err_flag);
+}
+
 int run_pack_genome(Session& s, int g, u32* err_flag) { return run_pack(s, g, err_flag); }
+
+// chunked upload: makes the session stream wait for piece c of genome g and packs the words that piece completes.
+// Returns through *bases_ready how many leading bases of the genome are packed afterwards.
+int run_pack_piece(Session& s, int g, int c, u32* err_flag, u64* bases_ready)
+{
+    const u64 cb = s.up_chunk_bases[g], n = s.n[g];
+    const u64 words = div_up(n, 16) + 2;
+    MCU_CUDA(cudaStreamWaitEvent(s.stream, s.up_events[(size_t)g * s.up_chunks + c], 0));
+    const bool last = c == s.up_chunks - 1;
+    const u64 b0 = (u64)c * cb, b1 = last ? n : (u64)(c + 1) * cb;
+    const u64 w0 = b0 / 16 < words ? b0 / 16 : words, w1 = last ? words : (b1 / 16 < words ? b1 / 16 : words);
+    if (c == 0) MCU_TRY(s.packed[g].reserve(words * sizeof(u32)));
+    MCU_TRY(run_pack_words(s, g, w0, w1, err_flag));
+    *bases_ready = last ? n : (b1 < n ? b1 : n);
+    return MCU_OK;
+}
+
+// whatever is still in flight of a chunked upload: wait for it and pack everything (paths that do not overlap)
+static int finish_chunked_upload(Session& s, u32* err_flag)
+{
+    for (int g = 0; g < 2; ++g) {
+        u64 ready = 0;
+        for (int c = 0; c < s.up_chunks; ++c) MCU_TRY(run_pack_piece(s, g, c, err_flag, &ready));
+    }
+    s.up_chunks = 0;
+    return MCU_OK;
+}
 
 // Phase 1 of a run: pack + enumeration of the unique seed pairs of this rank's key range (uniq bitmap, pair list).
 template <typename K>
@@ -554,8 +654,14 @@ static int run_enumerate(Session& s, const SeedParams& sp, int shard_index, int 
     MCU_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), s.stream));
     MCU_CUDA(cudaEventRecord(s.ev[0], s.stream));
 
-    // ---- pack ----
-    for (int g = 0; g < 2; ++g) MCU_TRY(run_pack(s, g, (u32*)(ctr + 4)));
+    // ---- pack ----  (a chunked upload in flight: the bucketed path packs piece by piece under the copies, bucket.cu)
+    const bool chunked = s.up_chunks > 0 && s.pack_world == 1;
+    const bool overlap = chunked && s.use_buckets && bucket_plan_applies(sp, npos0, npos1, shard_count);
+    if (chunked && !overlap) MCU_TRY(finish_chunked_upload(s, (u32*)(ctr + 4)));
+    else if (!chunked) {
+        for (int g = 0; g < 2; ++g) MCU_TRY(run_pack(s, g, (u32*)(ctr + 4)));
+        if (s.after_pack) MCU_TRY(s.after_pack(s));
+    }
     MCU_CUDA(cudaEventRecord(s.ev[1], s.stream));
 
     // ---- enumerate unique seed pairs: uniq bitmap + pair list ----
@@ -572,6 +678,7 @@ static int run_enumerate(Session& s, const SeedParams& sp, int shard_index, int 
     int passes_run = 0;
     s.bk_spilled = 0;
     if (s.use_buckets) MCU_TRY(bucket_group(s, sp, shard_index, shard_count, pair_cap, s.ev[2], s.ev[3], &bucketed, &nsort));
+    if (s.up_chunks > 0 && s.pack_world == 1) MCU_TRY(finish_chunked_upload(s, (u32*)(ctr + 4)));  // no-op when the bucketed path consumed the pieces
     if (!bucketed) {
         // ---- seedgen ----
         MCU_TRY(s.keys_a.reserve((ntot + 1) * sizeof(K)));
@@ -617,7 +724,8 @@ static int run_enumerate(Session& s, const SeedParams& sp, int shard_index, int 
     MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     MCU_CUDA(cudaStreamSynchronize(s.stream));
     MCU_CUDA(cudaGetLastError());
-    if (((u32*)(s.h_counters + 4))[0]) { set_error("gap character '-' in a genome sequence (input must be unaligned)"); return MCU_EGAP; }
+    s.gap_seen = ((u32*)(s.h_counters + 4))[0] != 0;
+    if (s.gap_seen && !s.defer_gap_error) { set_error("gap character '-' in a genome sequence (input must be unaligned)"); return MCU_EGAP; }
     s.run.sp = sp;
     s.run.sharded = sharded;
     s.run.bucketed = bucketed;

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "radix.cuh"
 
+#include <mutex>
 #include <vector>
 
 namespace mcu {
@@ -10,6 +11,7 @@ namespace mcu {
 struct Session {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_aux = nullptr;  // cross-stream ordering (chunked upload)
     cudaEvent_t kev[12] = {};  // per-kernel marks: 0 start, 1 hist1, 2 scatter1, 3 hist2, 4 scatter2, 5 group, 6/7 candidate, 8 extend
     DevBuf ascii[2], packed[2];
     DevBuf keys_a, keys_b, vals_a, vals_b;
@@ -43,11 +45,37 @@ struct Session {
     } run;
     bool ok = false;
     bool use_buckets = true;  // MAUVE_CUDA_SORT_PATH=1 forces the radix-sort + join enumeration
+    // multi-GPU runs (comm.cu): this rank packs words [pack_rank * chunk, (pack_rank + 1) * chunk) of every genome and
+    // `after_pack` all-gathers the chunks; a '-' in a rank's slice is reported after the ranks exchanged their flags
+    int pack_rank = 0, pack_world = 1;
+    int (*after_pack)(Session&) = nullptr;
+    bool defer_gap_error = false, gap_seen = false;
+    DevBuf gathered, comm_small;            // rank 0: rows of all ranks; per-rank stat vectors
+    unsigned long long* h_comm = nullptr;   // pinned, (world + 1) * 8 entries
+    // chunked upload (session_upload_begin): the genomes arrive on `copy_stream` in `up_chunks` pieces per genome, one event each;
+    // pack and the level-1 scatter of a piece start as soon as it (and the piece after it) is on the device
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> up_events;
+    int up_chunks = 0;                      // 0: the whole genomes are resident (session_upload)
+    u64 up_chunk_bases[2] = {0, 0};         // bases per piece (a multiple of 4096)
 };
 
+// packed words rank r of `world` produces for a genome of n bases: [r * chunk, (r + 1) * chunk), chunk a multiple of 4 words
+static inline u64 pack_chunk_words(u64 n, int world)
+{
+    const u64 words = div_up(n, 16) + 2;
+    return (div_up(words, (u64)world) + 3) & ~3ull;
+}
+
 int session_init(Session& s);
+int default_session(Session** out);  // the process-wide session behind the one-call entry points (api.cu); hold api_mutex()
+std::mutex& api_mutex();
 void session_destroy(Session& s);
 int session_upload(Session& s, const char* seq0, u64 n0, const char* seq1, u64 n1);
+// H2D of the bases this rank packs in a run sharded over `world` ranks (asynchronous on the session stream)
+int session_upload_slice(Session& s, const char* seq0, u64 n0, const char* seq1, u64 n1, int rank, int world);
+// asynchronous H2D in pieces on the copy stream; the next session_run overlaps pack + level-1 scatter with the copies
+int session_upload_begin(Session& s, const char* seq0, u64 n0, const char* seq1, u64 n1, int chunks);
 int session_run(Session& s, u64 seed, int shard_index, int shard_count, float* stage_ms, u64* stats);
 int session_enumerate(Session& s, u64 seed, int shard_index, int shard_count);
 int session_finish(Session& s, bool uniq_is_global, float* stage_ms, u64* stats);
@@ -70,6 +98,9 @@ int replay_unclean(Session& s, const SeedParams* sp, bool can_replay, u64* uncle
 int batch_find_mums(Session& s, const char* cat0, const u64* off0, const char* cat1, const u64* off1, u32 n_seg, u64 seed,
                     std::vector<mcu_match>* rows, std::vector<u32>* row_seg, std::vector<u32>* unclean_segs, u64* seed_pairs);
 int run_pack_genome(Session& s, int g, u32* err_flag);
+int run_pack_piece(Session& s, int g, int c, u32* err_flag, u64* bases_ready);
+// true when bucket_group will take the fixed-capacity bucketed path for these sizes (decided from sizes alone)
+bool bucket_plan_applies(const SeedParams& sp, u64 npos0, u64 npos1, int shard_count);
 
 // single-genome SML (stable): outputs on device in s.keys_*/vals_* ; returns which buffer
 int sml_build_device(Session& s, const char* seq, u64 n, u64 seed, u32* pos_out, u64* mer_out, u32* packed_out, u64* len_out);
@@ -121,3 +152,5 @@ __device__ __forceinline__ bool uniq_bit(const u32* __restrict__ uniq, i64 t) { 
 #endif
 
 }  // namespace mcu
+
+struct mcu_session { mcu::Session s; };

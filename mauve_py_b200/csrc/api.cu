@@ -29,9 +29,11 @@ const char* get_error() { return g_err; }
 static int g_device = -1;
 static int g_sms = 0;
 static std::mutex g_mu;
+static std::recursive_mutex g_dev_mu;  // device selection (mcu_init / ensure_device); g_mu serialises the default session
 
 int ensure_device()
 {
+    std::lock_guard<std::recursive_mutex> lk(g_dev_mu);
     if (g_device >= 0) {
         cudaError_t e = cudaSetDevice(g_device);
         if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", g_device, cudaGetErrorString(e)); return MCU_ENODEV; }
@@ -101,7 +103,9 @@ int make_seed_params(u64 seed, SeedParams* out)
 
 static Session* g_default_session = nullptr;
 
-static int default_session(Session** out)
+std::mutex& api_mutex() { return g_mu; }
+
+int default_session(Session** out)
 {
     if (!g_default_session) {
         Session* s = new (std::nothrow) Session();
@@ -122,6 +126,7 @@ extern "C" {
 
 int mcu_init(int device)
 {
+    std::lock_guard<std::recursive_mutex> lk(g_dev_mu);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -168,10 +173,10 @@ void mcu_host_free(void* p) { if (p) cudaFreeHost(p); }
 uint64_t mcu_get_seed(int weight, int rank)
 {
     auto solid = [](int w) -> u64 { return w >= 64 ? ~0ull : ((1ull << w) - 1); };
+    if (weight < 0 || rank < 0) return 0;
     if (rank == MCU_SOLID_SEED) return solid(weight);
     if (weight > 31) return solid(32);
     if (rank > 5) return solid(weight);
-    if (weight < 0 || rank < 0) return 0;
     if (SEED_TABLE[weight][rank] == 0) return solid(weight);
     return SEED_TABLE[weight][rank];
 }
@@ -217,17 +222,42 @@ int mcu_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, 
     if (rule != MCU_RULE_PAIRWISE && rule != MCU_RULE_MEMHASH) { set_error("mcu_find_mums: unknown rule %d", rule); return MCU_EINVAL; }
     Session* s;
     MCU_TRY(default_session(&s));
-    MCU_TRY(session_upload(*s, seq0, n0, seq1, n1));
+    if (n0 + n1 >= (8ull << 20) && getenv("MAUVE_CUDA_NO_OVERLAP") == nullptr) MCU_TRY(session_upload_begin(*s, seq0, n0, seq1, n1, 8));
+    else MCU_TRY(session_upload(*s, seq0, n0, seq1, n1));
     MCU_TRY(session_run(*s, seed, 0, 1, nullptr, stats));
     u64 m = s->match_count;
     mcu_match* r = (mcu_match*)malloc((m ? m : 1) * sizeof(mcu_match));
     if (!r) { set_error("out of host memory"); return MCU_ENOMEM; }
     if (m) {
-        MCU_CUDA(cudaMemcpyAsync(r, s->matches.p, m * sizeof(mcu_match), cudaMemcpyDeviceToHost, s->stream));
-        MCU_CUDA(cudaStreamSynchronize(s->stream));
+        cudaError_t e = cudaMemcpyAsync(r, s->matches.p, m * sizeof(mcu_match), cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) { free(r); set_error("mcu_find_mums: copy of the rows failed: %s", cudaGetErrorString(e)); return MCU_ECUDA; }
     }
     *out = r;
     *n_out = m;
+    return MCU_OK;
+}
+
+int mcu_find_mums_into(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule, mcu_match* rows_out,
+                       uint64_t cap, uint64_t* n_out, uint64_t* stats)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    if (!n_out || (cap && !rows_out)) { set_error("mcu_find_mums_into: NULL output pointer"); return MCU_EINVAL; }
+    if (rule != MCU_RULE_PAIRWISE && rule != MCU_RULE_MEMHASH) { set_error("mcu_find_mums_into: unknown rule %d", rule); return MCU_EINVAL; }
+    Session* s;
+    MCU_TRY(default_session(&s));
+    // large inputs arrive in pieces on a copy stream; pack and the level-1 partition of a piece run under the next copies
+    if (n0 + n1 >= (8ull << 20) && getenv("MAUVE_CUDA_NO_OVERLAP") == nullptr) MCU_TRY(session_upload_begin(*s, seq0, n0, seq1, n1, 8));
+    else MCU_TRY(session_upload(*s, seq0, n0, seq1, n1));
+    MCU_TRY(session_run(*s, seed, 0, 1, nullptr, stats));
+    const u64 m = s->match_count;
+    *n_out = m;
+    if (m > cap) { set_error("mcu_find_mums_into: %llu rows do not fit the caller's %llu", (unsigned long long)m, (unsigned long long)cap); return MCU_ESMALL; }
+    if (m) {
+        MCU_CUDA(cudaMemcpyAsync(rows_out, s->matches.p, m * sizeof(mcu_match), cudaMemcpyDeviceToHost, s->stream));
+        MCU_CUDA(cudaStreamSynchronize(s->stream));
+    }
     return MCU_OK;
 }
 
@@ -314,7 +344,6 @@ int mcu_find_mums_batch(uint64_t n_pairs, const char* seq0, const uint64_t* off0
 }
 
 // ---- sessions ---------------------------------------------------------------------------
-struct mcu_session { Session s; };
 
 int mcu_session_create(mcu_session** out)
 {
@@ -340,6 +369,13 @@ int mcu_session_upload(mcu_session* h, const char* seq0, uint64_t n0, const char
     if (!h) return MCU_EINVAL;
     MCU_TRY(ensure_device());
     return session_upload(h->s, seq0, n0, seq1, n1);
+}
+
+int mcu_session_upload_begin(mcu_session* h, const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, int chunks)
+{
+    if (!h) return MCU_EINVAL;
+    MCU_TRY(ensure_device());
+    return session_upload_begin(h->s, seq0, n0, seq1, n1, chunks);
 }
 
 int mcu_session_run(mcu_session* h, uint64_t seed, int shard_index, int shard_count, float* stage_ms, uint64_t* stats)
@@ -420,8 +456,9 @@ int mcu_merge_matches(const mcu_match* rows, uint64_t n, int in_device, mcu_matc
     mcu_match* r = (mcu_match*)malloc((n ? n : 1) * sizeof(mcu_match));
     if (!r) { set_error("out of host memory"); return MCU_ENOMEM; }
     if (n) {
-        MCU_CUDA(cudaMemcpyAsync(r, s->matches.p, n * sizeof(mcu_match), cudaMemcpyDeviceToHost, s->stream));
-        MCU_CUDA(cudaStreamSynchronize(s->stream));
+        cudaError_t e = cudaMemcpyAsync(r, s->matches.p, n * sizeof(mcu_match), cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) { free(r); set_error("mcu_merge_matches: copy of the rows failed: %s", cudaGetErrorString(e)); return MCU_ECUDA; }
     }
     // shards rediscover the same maximal match from their own seeds: equal rows are adjacent now
     u64 k = 0;
@@ -430,9 +467,11 @@ int mcu_merge_matches(const mcu_match* rows, uint64_t n, int in_device, mcu_matc
     // buckets the reference would fill order-dependently cannot be replayed from rows alone: report them
     u64 unclean = 0, dups = 0;
     if (k) {
-        MCU_CUDA(cudaMemcpyAsync(s->matches.p, r, k * sizeof(mcu_match), cudaMemcpyHostToDevice, s->stream));
+        cudaError_t e = cudaMemcpyAsync(s->matches.p, r, k * sizeof(mcu_match), cudaMemcpyHostToDevice, s->stream);
+        if (e != cudaSuccess) { free(r); set_error("mcu_merge_matches: %s", cudaGetErrorString(e)); return MCU_ECUDA; }
         s->match_count = k;
-        MCU_TRY(replay_unclean(*s, nullptr, false, &unclean, &dups));
+        const int rc = replay_unclean(*s, nullptr, false, &unclean, &dups);
+        if (rc != MCU_OK) { free(r); return rc; }
     }
     if (unclean_buckets_out) *unclean_buckets_out = unclean;
     *out = r;

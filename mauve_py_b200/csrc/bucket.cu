@@ -470,7 +470,7 @@ __device__ __forceinline__ u32 bkf_reserve(const BkScatterSmem& s, u32 bins, uns
 
 template <bool SOLID>
 __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* __restrict__ g0, const u32* __restrict__ g1, BkPlan pl, SeedParams sp,
-                                                                    unsigned long long* __restrict__ cursor1, u64* __restrict__ recs, BkOvf ovf)
+                                                                    unsigned long long* __restrict__ cursor1, u64* __restrict__ recs, BkOvf ovf, u32 tile_base)
 {
     extern __shared__ __align__(16) unsigned char raw[];
     const BkScatterSmem s = bk_carve(raw, pl.B1);
@@ -478,11 +478,18 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* 
     const u32 b_lo = pl.b_lo;
     for (u32 i = tid; i < pl.B1; i += BK_THREADS) s.cnt[i] = 0;
     __syncthreads();
-    const u64 idx0 = (u64)blockIdx.x * BK_TILE + (u64)tid * BK_IPT;  // 16 consecutive positions per thread
+    const u64 idx0 = ((u64)tile_base + blockIdx.x) * BK_TILE + (u64)tid * BK_IPT;  // 16 consecutive positions per thread
     u64 rec[BK_IPT];
     u32 br[BK_IPT];  // bin << 16 | rank   (rank < BK_TILE = 4096)
 #pragma unroll
     for (int it = 0; it < BK_IPT; ++it) br[it] = 0xffffffffu;
+    // sharded solid-seed runs: ownership mask of this thread's 16 positions, consumed after the range test below so that
+    // EVERY lane of the warp (also those beyond nidx, whose mask stays 0) takes part in the warp votes
+    u32 own_mask = 0, own_nx = 0, own_prev = 0, own_g = 0;
+    u64 own_pos = 0;
+    BkWindow own_w;
+    own_w.hi = 0; own_w.lo = 0;
+    const bool compact = SOLID && pl.nshard > 1;
     if (idx0 < pl.nidx) {
         const u32 g = idx0 >= pl.npad0;
         const u64 pos = g ? idx0 - pl.npad0 : idx0, npos = g ? pl.npos1 : pl.npos0;
@@ -492,7 +499,21 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* 
         const int kbits = 2 * sp.w;
         const u64 kmask = (1ull << kbits) - 1;   // kbits <= 62
         const int mshift = kbits / 2 + 1;
-        if (SOLID) {
+        if (compact) {
+            const u32 hi_h = (u32)(w.hi >> 32), hi_l = (u32)w.hi;
+            const u32 nx = kbits < 32 ? __funnelshift_l(hi_l, hi_h, kbits) : __funnelshift_l(w.lo, hi_l, kbits - 32);
+            u64 f = w.hi >> (64 - kbits);
+            u64 rc = revcomp_seed(f, sp.w);
+#pragma unroll
+            for (int it = 0; it < BK_IPT; ++it) {
+                const u32 nb = (nx >> (30 - 2 * it)) & 3u;
+                if (pos + it < npos && seed_owned(f, rc, pl.shard, pl.nshard)) own_mask |= 1u << it;
+                f = ((f << 2) | nb) & kmask;
+                rc = (rc >> 2) | ((u64)(3u - nb) << (kbits - 2));
+            }
+            own_nx = nx; own_g = g; own_pos = pos; own_w = w;
+            if (pl.aux && pos > 0) own_prev = base_at(gp, (i64)pos - 1);
+        } else if (SOLID) {
             // rolling evaluation: a shift by one position drops one base and adds one (forward: at the low end; reverse
             // complement: the complement at the high end).  nx = the 16 bases [w, w+16) of the window.
             const u32 hi_h = (u32)(w.hi >> 32), hi_l = (u32)w.hi;
@@ -537,6 +558,35 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* 
                         br[it] = (b << 16) | atomicAdd(&s.cnt[b], 1u);
                     }
                 }
+            }
+        }
+    }
+    if (compact) {
+        // as many rounds of record building as the busiest lane of the warp owns seeds (mean 16 / nshard)
+        const int kbits = 2 * sp.w;
+        const u64 kmask = (1ull << kbits) - 1;
+        const int mshift = kbits / 2 + 1;
+#pragma unroll
+        for (int k = 0; k < BK_IPT; ++k) {
+            if (!__any_sync(0xffffffffu, own_mask != 0)) break;   // uniform: all 32 lanes are here
+            if (own_mask) {
+                const int it = __ffs(own_mask) - 1;
+                own_mask &= own_mask - 1;
+                const u64 mer = (own_w.hi << (2 * it)) | ((u64)own_w.lo >> (32 - 2 * it));
+                const u64 ff = mer >> (64 - kbits), rr = revcomp_seed(ff, sp.w);
+                const u32 strand = rr < ff;
+                u64 x = strand ? rr : ff;
+                x ^= x >> mshift;
+                const u64 canon = (x * 0x9E3779B97F4A7C15ull) & kmask;  // == bk_mix
+                const u32 b = (u32)(canon >> pl.rem1);
+                const u64 keyrem = canon & ((1ull << pl.rem1) - 1);
+                u64 aux = 0;
+                if (pl.aux) {
+                    const u32 prev = it ? (u32)(own_w.hi >> (64 - 2 * it)) & 3u : own_prev;
+                    aux = prev | (((own_nx >> (30 - 2 * it)) & 3u) << 2);
+                }
+                rec[k] = (keyrem << pl.kshift) | (aux << (pl.pbits + 2)) | ((own_pos + it) << 2) | ((u64)strand << 1) | (u64)own_g;
+                br[k] = (b << 16) | atomicAdd(&s.cnt[b], 1u);
             }
         }
     }
@@ -920,10 +970,37 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     const unsigned tiles1 = (unsigned)div_up(pl.nidx, BK_TILE);
     MCU_CUDA(cudaEventRecord(s.kev[0], st));
     MCU_CUDA(cudaEventRecord(s.kev[1], st));
-    if (nb1) {
-        if (solid_pattern) bkf_scatter1_kernel<true><<<tiles1, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf);
-        else bkf_scatter1_kernel<false><<<tiles1, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf);
-    }
+    auto scatter1 = [&](unsigned t0, unsigned t1) {
+        if (t1 <= t0) return;
+        if (solid_pattern) bkf_scatter1_kernel<true><<<t1 - t0, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf, t0);
+        else bkf_scatter1_kernel<false><<<t1 - t0, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf, t0);
+        s.launches++;
+    };
+    if (s.up_chunks > 0 && s.pack_world == 1) {
+        // chunked upload in flight (session_upload_begin): pack every piece as it lands and scatter the tiles whose seeds it
+        // completes.  A seed window (and the neighbour bases of aux records) reads at most 64 bases past its position.
+        unsigned done = 0;
+        for (int g = 0; g < 2; ++g) MCU_TRY(s.packed[g].reserve((div_up(s.n[g], 16) + 2) * sizeof(u32)));
+        g0 = s.packed[0].as<u32>();
+        g1 = s.packed[1].as<u32>();
+        for (int g = 0; g < 2; ++g)
+            for (int c = 0; c < s.up_chunks; ++c) {
+                u64 ready = 0;
+                MCU_TRY(run_pack_piece(s, g, c, (u32*)(ctr + 4), &ready));
+                const bool last = c == s.up_chunks - 1;
+                const u64 npos_g = g ? pl.npos1 : pl.npos0;
+                u64 pos_ok = last ? npos_g : (ready > 64 ? ready - 64 : 0);  // positions of genome g whose windows are packed
+                if (pos_ok > npos_g) pos_ok = npos_g;
+                u64 idx_ok = g ? pl.npad0 + pos_ok : pos_ok;
+                if (last) idx_ok = g ? pl.nidx : pl.npad0;  // padding positions produce no record: the tile may run
+                // tiles wholly below idx_ok (genome 0's last tile usually straddles into genome 1: it waits for genome 1's first piece)
+                unsigned upto = (g == 1 && last) ? tiles1 : (unsigned)(idx_ok / BK_TILE);
+                if (upto > tiles1) upto = tiles1;
+                if (nb1) scatter1(done, upto);
+                if (upto > done) done = upto;
+            }
+        s.up_chunks = 0;
+    } else if (nb1) scatter1(0, tiles1);
     MCU_CUDA(cudaEventRecord(ev_scatter1, st));
     MCU_CUDA(cudaEventRecord(s.kev[2], st));
     bkf_total_kernel<<<1, 256, 0, st>>>(cursor1, pl, meta);
@@ -941,7 +1018,7 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     ga.cnt2 = cursor2; ga.dirty = dirty; ga.nfinal = nfinal;
     if (nfinal) bk_group_kernel<<<(unsigned)nfinal, BK_THREADS, 0, st>>>(ga, pl);
     MCU_CUDA(cudaEventRecord(s.kev[5], st));
-    s.launches += 4;
+    s.launches += 3;
     MCU_CUDA(cudaGetLastError());
     struct { unsigned long long spill[4]; BkMeta meta; unsigned long long ctr[8]; } h;
     MCU_CUDA(cudaMemcpyAsync(h.spill, spill, 32, cudaMemcpyDeviceToHost, st));
@@ -973,6 +1050,12 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
         MCU_TRY(join_sorted_u64(s, in_a ? s.keys_a.as<u64>() : s.keys_b.as<u64>(), in_a ? s.vals_a.as<u32>() : s.vals_b.as<u32>(), ns, pair_cap));
     }
     return MCU_OK;
+}
+
+bool bucket_plan_applies(const SeedParams& sp, u64 npos0, u64 npos1, int shard_count)
+{
+    BkPlan pl;
+    return npos0 && npos1 && getenv("MAUVE_CUDA_EXACT_BUCKETS") == nullptr && make_plan(sp, npos0, npos1, (u64)shard_count, &pl);
 }
 
 int bucket_group(Session& s, const SeedParams& sp, int shard_index, int shard_count, u64 pair_cap, cudaEvent_t ev_scatter1, cudaEvent_t ev_scatter2,
