@@ -4,17 +4,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mbp 100]
 
 One "step" = one pass of seed + match + extend (pack -> two partition passes over 8-byte seed records -> in-bucket
-grouping -> candidates -> extension -> reference list order; at N > 1: NCCL all-reduce of the unique-seed bitmap before
-extension and NCCL gather + merge of the match rows on rank 0) over the synthetic 100 Mbp pair
-(BASELINE config 3, SURVEY.md 8d "C3"; the north_star target workload, it fits one GPU).  `value`
-is Mbp/s with both genomes already resident in HBM; `e2e` is the same metric through the public
-C-ABI call mcu_find_mums with pinned HOST buffers (H2D + D2H inside the timed region).  N > 1 shards
-the SAME pair by a seed-ownership hash ("strong" scaling).  The gapped DP (GCUPS) and the HMM are reported
-in the `dp` / `hmm` objects of the same line; `buildindex` (N = 1) is BASELINE config 0 end to end: mauve.buildIndex on the MDS42
-pair, the reference's own binary timed beside ours, LUT checked against the golden one.  Prints ONE JSON line on rank 0.
+grouping -> candidates -> extension -> reference list order) over the synthetic 100 Mbp pair (BASELINE config 3, SURVEY.md 8d
+"C3"; the north_star target workload, it fits one GPU).  `value` is Mbp/s with both genomes already resident in HBM; `e2e` is
+the same metric through the public C-ABI call (mcu_find_mums_into / mcu_find_mums_sharded) with pinned HOST buffers, H2D + D2H
+inside the timed region.  N > 1 shards the SAME pair ("strong" scaling): the whole sharded step is ONE library call
+(mcu_session_run_sharded, csrc/comm.cu) that calls NCCL itself on the session's stream; there is no torch in this file.
+The match list of every run is compared with the reference's own list for the pair (tests/golden/config3_rows.json: sha1 of
+the rows oracle/_ref produced on the full 100 Mbp pair) at every N.  The sorted-mer-list build (config 4), the gapped DP
+(GCUPS, config 5) and the HMM are reported in the `sml` / `dp` / `hmm` objects of the same line; `buildindex` (N = 1) is BASELINE
+config 0 end to end.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -107,19 +109,11 @@ class NvmlSampler:
             import threading
             import pynvml as nv
             nv.nvmlInit()
-            h = None
-            try:
-                import torch
-                uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
-                h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
-            except Exception:  # noqa: BLE001
-                h = None
-            if h is None:
-                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-                phys = self.idx
-                if vis and all(t.strip().isdigit() for t in vis.split(",")):
-                    phys = int(vis.split(",")[self.idx])
-                h = nv.nvmlDeviceGetHandleByIndex(phys)
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.idx
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                phys = int(vis.split(",")[self.idx])
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
             nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)  # probe
             self._h, self._nv = h, nv
             self._thread = threading.Thread(target=self._run, daemon=True)
@@ -193,16 +187,26 @@ def cpu_sample(a, b, sample_bp):
     return a[:sample_bp].tobytes(), b[:sample_bp].tobytes()
 
 
+def golden_config3():
+    """what the reference itself returns for the full 100 Mbp pair (tests/golden/make_golden_config3.py ran oracle/_ref on it)"""
+    p = os.path.join(ROOT, "tests", "golden", "config3_rows.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f)
+
+
 def run_reference_arm(args):
+    """--impl reference: the reference's own match finder (oracle/_ref: unmodified sources compiled in place; else the C restatement)
+    on the host cores.  Nothing of the product is imported here."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    import mauve_py_b200 as mp
     a, b = workload(args.mbp)  # the same pair the GPU arm runs; the CPU gets its leading part
     sa, sb = cpu_sample(a, b, int(args.cpu_sample_mbp * 1e6))
     chk, kind = cpu_checker()
-    weight = mp.getDefaultSeedWeight(int(args.mbp * 1e6))
-    seed = mp.getSeed(weight, mp.CODING_SEED)
+    weight = chk.default_seed_weight(int(args.mbp * 1e6))
+    seed = chk.get_seed(weight, 3)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -214,10 +218,16 @@ def run_reference_arm(args):
     value = (len(sa) + len(sb)) / 1e6 / (ms / 1e3)
     sample = "leading %.1f Mbp of both genomes of the %g Mbp pair, %d matches; single thread (the reference has no threads)" % (
         args.cpu_sample_mbp, args.mbp, rows.shape[0])
+    cfg = config_dict(args, weight, seed)
+    g = golden_config3()
+    cfg["reference_arm_sample"] = sample
+    if g and abs(args.mbp - 100.0) < 1e-9:
+        cfg["reference_arm_full_size"] = "the same code on the FULL pair: %.0f s = %.3f Mbp/s, %d rows (tests/golden/config3_rows.json)" % (
+            g["reference_seconds"], (g["n0"] + g["n1"]) / 1e6 / g["reference_seconds"], g["reference"]["rows"])
     line = {
         "impl": "reference", "metric": "Mbp/s seed+match+extend", "value": value, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic", "config": config_dict(args, weight, seed),
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": "Mbp/s", "cores": 1, "kind": kind, "sample": sample, "cores_on_box": os.cpu_count(),
                          "projection_if_embarrassingly_parallel": value * (os.cpu_count() or 1),
                          "projection_note": "PROJECTION, not a measurement: the reference has no threads; value x cores_on_box"},
@@ -230,54 +240,154 @@ def config_dict(args, weight, seed):
     return {"workload": "synthetic %g Mbp pair (BASELINE config 3 / SURVEY 8d C3: 0.9%% SNP, 0.1%% indel events, inversions, translocations), "
                         "default seed weight %d rank CODING_SEED -> pattern 0x%x" % (args.mbp, weight, seed),
             "genome_bp": int(args.mbp * 1e6), "seed_weight": weight, "seed_pattern": hex(seed),
-            "sharding": "seed-ownership hash per rank; NCCL all-reduce of the 1-bit/base unique-seed bitmap, NCCL gather of match rows to rank 0" if args.gpus > 1 else "none",
-            "l2": "inputs (2 x %g MB ASCII, %.1f GB of key/value pairs) exceed the 126 MB L2; no extra flush" % (args.mbp, 2 * args.mbp * 12e6 / 1e9)}
+            "sharding": ("one library call per step (mcu_session_run_sharded): each rank packs 1/N of the genomes + ncclAllGather, seeds owned per rank by a "
+                         "mer hash, ncclAllReduce of the 1-bit/base unique-seed bitmap, ncclSend/ncclRecv gather of match rows to rank 0, merge there")
+            if args.gpus > 1 else "none",
+            "l2": "inputs (2 x %g MB ASCII, %.1f GB of 8-byte seed records) exceed the 126 MB L2; no extra flush" % (args.mbp, 2 * args.mbp * 8e6 / 1e9)}
 
 
-def measure_dp(mp, synth, args):
-    """GCUPS of the gapped DP on a sample of BASELINE config 5 (+ the reference's NWSmall on a few regions of the same batch)"""
-    pairs = synth.dp_pairs(args.dp_regions, 100, 10000, seed=20261020)
+def _nw_one(p):
+    import _oracle
+    chk = _oracle.ref_checker() if _oracle.have_ref() else _oracle.oracle_checker()
+    chk.nw_align(p[0], p[1])
+    return len(p[0]) * len(p[1])
+
+
+def measure_dp(mp, synth, args, rank=0, comm=None):
+    """GCUPS of the gapped DP on BASELINE config 5's regions (lenA log-uniform 100 bp - 10 kbp, 5 % SNP + 1 % indel events):
+    --dp-regions regions PER GPU (every rank draws its own), wall clock around mcu_nw_batch with host buffers (H2D of the sequences,
+    kernels, D2H of the paths); kernel-only GCUPS beside it; the reference's NWSmall on a stratified sample of the same regions."""
+    from mauve_py_b200 import dist as mdist
+    world = comm.world if comm is not None else 1
+    pairs = synth.dp_pairs(args.dp_regions, 100, 10000, seed=20261020 + 7919 * rank)
     arrs = synth.dp_arrays(pairs)
-    mp.libmems.nw_batch_arrays(*arrs)
+    mp.libmems.nw_batch_arrays(*arrs)          # warm-up: allocations
+    if comm is not None:
+        comm.barrier()
+    t0 = time.perf_counter()
     res = mp.libmems.nw_batch_arrays(*arrs)
+    wall = time.perf_counter() - t0
     cells = float(res["stats"][0])
-    dp = {"metric": "GCUPS gapped DP (full-matrix cells, NWSmall-exact paths)", "value": cells / (res["device_ms"] * 1e-3) / 1e9,
-          "unit": "GCUPS", "regions": len(pairs), "cells": cells, "device_ms": res["device_ms"],
-          "workload": "BASELINE config 5 sample: %d regions, lenA log-uniform 100 bp-10 kbp, 5%% SNP + 1%% indel events" % len(pairs)}
+    dev_ms = float(res["device_ms"])
+    if comm is not None and world > 1:
+        cells = comm.allreduce([cells], mdist.SUM)[0]
+        wall, dev_ms = comm.allreduce([wall, dev_ms], mdist.MAX)
+    dp = {"metric": "GCUPS gapped DP (full-matrix cells, NWSmall-exact paths)", "value": cells / wall / 1e9, "unit": "GCUPS",
+          "timing": "wall clock around mcu_nw_batch with HOST buffers (H2D of the sequences, kernels, D2H of the paths), max over ranks",
+          "kernel_only_gcups": cells / (dev_ms * 1e-3) / 1e9, "regions": len(pairs) * world, "regions_per_gpu": len(pairs), "cells": cells,
+          "wall_ms": 1e3 * wall, "device_ms": dev_ms, "scaling": "weak" if world > 1 else None,
+          "workload": "BASELINE config 5: %d regions per GPU, lenA log-uniform 100 bp-10 kbp, 5%% SNP + 1%% indel events" % len(pairs)}
+    if rank != 0:
+        return dp
     # DP roofline (SURVEY.md 8d): ~12 int32 operations per cell against the INT32 issue rate MEASURED on this device by a register-resident
-    # add/max microbenchmark (mcu_test_int32_peak); the kernel's own count is ~22 instructions per cell (DESIGN.md section 5)
+    # add/max microbenchmark (mcu_test_int32_peak)
     try:
         gops, pms = C.c_double(0.0), C.c_float(0.0)
         mp._capi.check(mp.lib().mcu_test_int32_peak(C.byref(gops), C.byref(pms)))
         if gops.value > 0:
-            achieved = 12.0 * dp["value"]
+            achieved = 12.0 * dp["kernel_only_gcups"] / world
             dp["roofline"] = {"bound": "int32 issue", "achieved": achieved, "peak": gops.value, "unit": "G thread-instructions/s", "frac": achieved / gops.value,
                               "ops_per_cell": 12, "peak_source": "measured: mcu_test_int32_peak (8 independent VIADDMNMX chains per thread, register "
-                                                                 "resident, %.2f ms); achieved = 12 algorithmic int32 operations per cell (SURVEY.md 8d)" % pms.value}
+                                                                 "resident, %.2f ms); achieved = 12 algorithmic int32 operations per cell (SURVEY.md 8d), kernel time, per GPU" % pms.value}
     except Exception as e:  # noqa: BLE001
         dp["roofline"] = {"error": "%s: %s" % (type(e).__name__, e)}
-    if not args.no_cpu:
-        chk, kind = cpu_checker()
-        small = [p for p in pairs if len(p[0]) <= 3000][:12]
+    if not args.no_cpu and world == 1:
+        # stratified: the regions in length order, every k-th one
+        order = sorted(range(len(pairs)), key=lambda i: len(pairs[i][0]))
+        k = max(1, len(order) // max(args.dp_cpu_regions, 1))
+        sample = [pairs[i] for i in order[k // 2::k]][:args.dp_cpu_regions]
+        import multiprocessing as mproc
+        procs = max(1, min(os.cpu_count() or 1, 16))
         t0 = time.perf_counter()
-        for x, y in small:
-            chk.nw_align(x, y)
+        with mproc.get_context("fork").Pool(procs) as pool:
+            done = sum(pool.map(_nw_one, sample, chunksize=max(1, len(sample) // (procs * 8))))
         dtc = time.perf_counter() - t0
-        dp["cpu_baseline"] = {"value": sum(len(x) * len(y) for x, y in small) / dtc / 1e9, "unit": "GCUPS", "cores": 1, "kind": kind,
-                              "sample": "%d regions <= 3 kbp of the same batch" % len(small)}
+        _, kind = cpu_checker()
+        dp["cpu_baseline"] = {"value": done / dtc / 1e9, "unit": "GCUPS", "cores": procs, "kind": kind, "per_core": done / dtc / 1e9 / procs,
+                              "sample": "%d regions of the same batch, stratified by length (every %d-th in length order), one region per task over %d "
+                                        "processes (the reference has no threads; regions are independent)" % (len(sample), k, procs)}
     return dp
 
 
-def measure_hmm(mp, synth, args):
-    """columns/s of the homology HMM: one column string per region (BASELINE config 5 scores every region), 512 distinct strings
-    tiled to 32768"""
-    pairs = synth.dp_pairs(512, 100, 10000, seed=20261020)
-    sym = [synth.hmm_string(len(p[0]), seed=i, block=300) for i, p in enumerate(pairs)] * 64
+def measure_hmm(mp, synth, args, rank=0, comm=None):
+    """columns/s of the homology HMM: one column string per DP region (BASELINE config 5 scores every region); 2048 distinct strings
+    tiled to --dp-regions per GPU.  Wall clock around mcu_hmm_batch with host buffers; kernel time beside it."""
+    from mauve_py_b200 import dist as mdist
+    world = comm.world if comm is not None else 1
+    nreg = args.dp_regions
+    base = min(nreg, 2048)
+    rng = np.random.default_rng(20261020 + rank)
+    lens = np.clip(np.exp(rng.uniform(np.log(100), np.log(10000), base)).astype(np.int64), 100, 10000)
+    sym = [synth.hmm_string(int(l), seed=i + 4096 * rank, block=300) for i, l in enumerate(lens)]
+    sym = (sym * ((nreg + base - 1) // base))[:nreg]
     params = mp.libmems.hmm_params(0.5, 1e-5, 1e-9, 0.7)
     mp.run_batch(sym, params, True)
+    if comm is not None:
+        comm.barrier()
+    t0 = time.perf_counter()
     _, _, hms = mp.run_batch(sym, params, True)
-    return {"metric": "HomologyHMM columns/s (Forward+Backward posteriors, bfloat-faithful: bit-identical to the reference)",
-            "value": sum(len(s) for s in sym) / (hms * 1e-3), "unit": "columns/s", "strings": len(sym), "device_ms": hms}
+    wall = time.perf_counter() - t0
+    cols = float(sum(len(s) for s in sym))
+    if comm is not None and world > 1:
+        cols = comm.allreduce([cols], mdist.SUM)[0]
+        wall, hms = comm.allreduce([wall, float(hms)], mdist.MAX)
+    out = {"metric": "HomologyHMM columns/s (Forward+Backward posteriors, bfloat-faithful: bit-identical to the reference)",
+           "value": cols / wall, "unit": "columns/s", "kernel_only_columns_s": cols / (hms * 1e-3), "strings": len(sym) * world, "columns": cols,
+           "wall_ms": 1e3 * wall, "device_ms": float(hms),
+           "timing": "wall clock around mcu_hmm_batch with HOST buffers incl. the posterior array back (8 B/column), max over ranks"}
+    if rank == 0:
+        try:   # the case the aligner really has: ONE genome-sized string (LM/Islands.h:161)
+            one = synth.hmm_string(args.hmm_single_columns, seed=99, block=400)
+            mp.run_batch([one], params, True)
+            t0 = time.perf_counter()
+            _, _, ms1 = mp.run_batch([one], params, True)
+            w1 = time.perf_counter() - t0
+            out["single_string"] = {"columns": len(one), "wall_ms": 1e3 * w1, "device_ms": float(ms1), "columns_s": len(one) / w1}
+            if not args.no_cpu and world == 1:
+                chk, kind = cpu_checker()
+                t0 = time.perf_counter()
+                chk.hmm_run(one, params)
+                out["single_string"]["cpu_columns_s"] = len(one) / (time.perf_counter() - t0)
+                out["single_string"]["cpu_kind"] = kind
+        except Exception as e:  # noqa: BLE001
+            out["single_string"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    return out
+
+
+def measure_sml(mp, synth, args, a, pa, peak):
+    """BASELINE config 4's stage at the size of this run: DNAMemorySML::Create = mcu_sml_build of genome 0 of the pair (pinned host
+    sequence in, sorted list left on the device), for seed weights 11..21 at rank 0 and rank 3 (CODING_SEED).  Wall clock per call;
+    pack / seed generation / radix sort from the library's CUDA events; the onesweep pass against the HBM roofline with SURVEY 8d's
+    2 x (Kb + 4) bytes per pair and pass."""
+    lib = mp.lib()
+    out = {"metric": "Mbp/s sorted-mer-list build (DNAMemorySML::Create, one genome)", "unit": "Mbp/s", "genome_bp": int(a.size), "rows": []}
+    best = None
+    for w in range(11, 22, 2):
+        for r in (0, 3):
+            seed = mp.getSeed(w, r)
+            L, wt = mp.getSeedLength(seed), mp.getSeedWeight(seed)
+            n_out = C.c_uint64(0)
+            mp._capi.check(lib.mcu_sml_build(pa, a.size, seed, None, None, None, C.byref(n_out)))
+            t0 = time.perf_counter()
+            mp._capi.check(lib.mcu_sml_build(pa, a.size, seed, None, None, None, C.byref(n_out)))
+            wall = time.perf_counter() - t0
+            st = np.zeros(6, dtype=np.float32)
+            lib.mcu_sml_last_stats(st.ctypes.data)
+            passes, kb, npos = int(st[3]), int(st[4]), float(n_out.value)
+            sort_bytes = passes * 2.0 * (kb + 4) * npos
+            row = {"weight_requested": w, "rank": r, "seed": hex(seed), "seed_length": L, "seed_weight": wt, "wall_ms": 1e3 * wall,
+                   "mbp_s": a.size / 1e6 / wall, "device_mbp_s": a.size / 1e6 / (float(st[0] + st[1] + st[2]) * 1e-3),
+                   "pack_ms": float(st[0]), "seedgen_ms": float(st[1]), "sort_ms": float(st[2]), "radix_passes": passes, "key_bytes": kb,
+                   "onesweep_gbs": sort_bytes / (float(st[2]) * 1e-3) / 1e9 if st[2] > 0 else None,
+                   "onesweep_frac": sort_bytes / (float(st[2]) * 1e-3) / 1e9 / peak if st[2] > 0 else None}
+            out["rows"].append(row)
+            if w == args.sml_headline_weight and r == 3:
+                best = row
+    best = best or out["rows"][-1]
+    out["value"] = best["mbp_s"]
+    out["headline"] = "weight %d rank 3: %.0f Mbp/s wall (H2D of the ASCII genome inside), %.0f Mbp/s device; onesweep %.0f GB/s = %.2f of measured HBM" % (
+        best["weight_requested"], best["mbp_s"], best["device_mbp_s"], best["onesweep_gbs"] or 0.0, best["onesweep_frac"] or 0.0)
+    return out
 
 
 def measure_buildindex(mp, args):
@@ -363,6 +473,11 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def spread(xs):
+    xs = sorted(xs)
+    return {"min": xs[0], "median": xs[len(xs) // 2], "max": xs[-1]} if xs else None
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -372,8 +487,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mbp", type=float, default=100.0, help="genome size of the synthetic pair in Mbp")
     ap.add_argument("--cpu-sample-mbp", type=float, default=10.0, help="leading Mbp of both genomes timed on the CPU (10-30 s of reference work)")
-    ap.add_argument("--dp-regions", type=int, default=1536)
+    ap.add_argument("--dp-regions", type=int, default=100000, help="BASELINE config 5 regions per GPU")
+    ap.add_argument("--dp-cpu-regions", type=int, default=1000, help="stratified sample of the regions aligned by the reference's NWSmall")
+    ap.add_argument("--hmm-single-columns", type=int, default=4000000)
+    ap.add_argument("--sml-headline-weight", type=int, default=19)
     ap.add_argument("--no-dp", action="store_true")
+    ap.add_argument("--no-sml", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-buildindex", action="store_true", help="skip the MDS42 buildIndex end-to-end measurement (~1 minute of host time)")
     ap.add_argument("--buildindex-only", action="store_true", help=argparse.SUPPRESS)
@@ -395,183 +514,165 @@ def main():
         run_reference_arm(args)
         return
 
-    import torch
-    import torch.distributed as dist
     import mauve_py_b200 as mp
     from mauve_py_b200 import dist as mdist
     from mauve_py_b200 import synth
     from mauve_py_b200._capi import check
 
-    world = env_int("WORLD_SIZE", 1)
-    rank = env_int("RANK", 0)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    comm = mdist.init_from_env()   # mcu_init(LOCAL_RANK) + the library's own NCCL communicator
+    world, rank = comm.world, comm.rank
     local = env_int("LOCAL_RANK", 0)
-    if world != args.gpus and world > 1:
-        args.gpus = world
-    torch.cuda.set_device(local)
-    lib = mp.lib()
-    check(lib.mcu_init(local))
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        args.gpus = world
+    lib = mp.lib()
 
     a, b = workload(args.mbp)
     nbases = int(a.size + b.size)
     weight = mp.getDefaultSeedWeight((a.size + b.size) // 2)
     seed = mp.getSeed(weight, mp.CODING_SEED)
-    L = mp.getSeedLength(seed)
     pa, va = pinned_copy(lib, a)
     pb, vb = pinned_copy(lib, b)
 
     sess = mp.AnchorSession()
-    sess.upload_ptr(pa, a.size, pb, b.size)
-    shard, nshard = mdist.shard_of(rank, world)
+    sess.upload_ptr(pa, a.size, pb, b.size)   # `value`: both genomes resident in HBM (on every rank) before the timed region
 
     def step_resident():
-        if world == 1:
-            return sess.run(seed, shard, nshard), None
-        return mdist.run_sharded(sess, seed, rank, world), None
+        return sess.run(seed) if world == 1 else sess.run_sharded(seed)
 
     # ---- value: device-resident inputs --------------------------------------------------------
     for _ in range(args.warmup):
         step_resident()
     launches0 = sess.launch_count()
     stage = np.zeros(16, dtype=np.float64)
-    barrier()
+    step_ms, dev_ms_steps = [], []
+    comm.barrier()
     sampler = start_clock_sampler(local) if rank == 0 else None
     t0 = time.perf_counter()
     nmatch = 0
     for _ in range(args.steps):
-        nmatch, _m = step_resident()
+        ts = time.perf_counter()
+        nmatch = step_resident()
+        step_ms.append(1e3 * (time.perf_counter() - ts))
         stage += sess.stage_ms
-    barrier()
+        dev_ms_steps.append(float(sess.stage_ms[6]))
+    comm.barrier()
     dt = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
     launches = sess.launch_count() - launches0
     stats = sess.stats.copy()
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+    dt = comm.allreduce([dt], mdist.MAX)[0]
     ms_per_step = 1e3 * dt / args.steps
     value = nbases / 1e6 / (dt / args.steps)
     stage /= args.steps
 
+    # ---- parity of what was just timed: the merged list against the reference's own list for this pair -------------
+    parity = None
+    if rank == 0:
+        rows = sess.download().copy()
+        sha = hashlib.sha1(np.ascontiguousarray(rows, dtype=np.int64).tobytes()).hexdigest()
+        g = golden_config3()
+        parity = {"rows": int(rows.shape[0]), "rows_sha1": sha, "repeat_limit_flag": int(stats[3]),
+                  "rows_left_out_by_the_repeat_limit_divergence": 0 if int(stats[3]) == 0 else None}
+        if g and abs(args.mbp - 100.0) < 1e-9:
+            parity["golden_sha1"] = g["reference"]["sha1"]
+            parity["golden"] = "oracle/_ref (the reference's own MatchFinder / MemHash, unmodified sources) on the full pair: %d rows, %.0f s" % (
+                g["reference"]["rows"], g["reference_seconds"])
+            parity["identical"] = bool(sha == g["reference"]["sha1"])
+            if not parity["identical"]:
+                print("PARITY FAILURE: rows differ from the reference's list for this pair", file=sys.stderr)
+
     # ---- e2e: host buffers through the public C-ABI call -----------------------------------------
+    cap = max(int(nmatch) + 1024, 1)
+    e2e_rows = C.c_void_p()
+    check(lib.mcu_host_alloc(C.byref(e2e_rows), cap * 24))
+    n_out = C.c_uint64(0)
+
     def step_e2e():
         if world == 1:
-            out = C.POINTER(mp._capi.Match)()
-            n_out = C.c_uint64(0)
-            check(lib.mcu_find_mums(pa, a.size, pb, b.size, seed, 0, C.byref(out), C.byref(n_out), None))
-            n = n_out.value
-            lib.mcu_free(out)
-            return n, n * 24
-        sess.upload_ptr(pa, a.size, pb, b.size)
-        n, merged = step_resident()
-        if rank == 0 and n:   # the merged list is the step's result: read it back into pinned host memory
-            assert n <= e2e_rows_cap, "match count changed between steps"
-            sess.download_ptr(e2e_rows)
-        return n, (n * 24 if rank == 0 else 0)
-
-    e2e_rows, e2e_rows_cap = None, 0
-    if world > 1 and rank == 0:
-        e2e_rows_cap = max(int(nmatch), 1)
-        e2e_rows = C.c_void_p()
-        check(lib.mcu_host_alloc(C.byref(e2e_rows), e2e_rows_cap * 24))
+            check(lib.mcu_find_mums_into(pa, a.size, pb, b.size, seed, 0, e2e_rows, cap, C.byref(n_out), None))
+        else:
+            check(lib.mcu_find_mums_sharded(pa, a.size, pb, b.size, seed, 0, e2e_rows, cap, C.byref(n_out), None))
+        return int(n_out.value)
 
     for _ in range(2):
         step_e2e()
-    barrier()
+    e2e_ms = []
+    comm.barrier()
     t0 = time.perf_counter()
-    d2h = 0
     for _ in range(args.steps):
-        n_e2e, d2h = step_e2e()
-    barrier()
-    dte = time.perf_counter() - t0
-    t = torch.tensor([dte], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dte = float(t.item())
+        ts = time.perf_counter()
+        n_e2e = step_e2e()
+        e2e_ms.append(1e3 * (time.perf_counter() - ts))
+    comm.barrier()
+    dte = comm.allreduce([time.perf_counter() - t0], mdist.MAX)[0]
     e2e_value = nbases / 1e6 / (dte / args.steps)
+    e2e_same = None
+    if rank == 0 and parity is not None:
+        got = np.ctypeslib.as_array(C.cast(e2e_rows, C.POINTER(C.c_int64)), shape=(max(n_e2e, 1), 3))[:n_e2e]
+        e2e_same = bool(hashlib.sha1(np.ascontiguousarray(got).tobytes()).hexdigest() == parity["rows_sha1"])
+        parity["e2e_rows_identical_to_resident_rows"] = e2e_same
+    def slice_bases(n):   # what one rank uploads of a genome of n bases (csrc/anchor.cuh pack_chunk_words)
+        words = (n + 15) // 16 + 2
+        chunk = (((words + world - 1) // world) + 3) & ~3
+        return min(n, 16 * chunk)
+    h2d = nbases if world == 1 else slice_bases(int(a.size)) + slice_bases(int(b.size))
 
-    # ---- N > 1: gapped DP and HMM divided among the ranks (independent regions / strings, LPT; no collective on the data path) ----
-    # every rank reaches the two all-reduces below whatever happened in its own share, so a failure cannot leave the others waiting
-    dp_sharded = hmm_sharded = None
-    if world > 1 and not args.no_dp:
-        vals = [0.0, 0.0, 0.0, 0.0, 1.0]   # dp cells, hmm columns | dp ms, hmm ms | ok
+    # ---- secondary metrics: every rank takes part at N > 1 (weak scaling: --dp-regions per GPU) ----
+    dp = hmm = sml = None
+    if not args.no_dp:
         try:
-            pairs = synth.dp_pairs(args.dp_regions, 100, 10000, seed=20261020)
-            mine = [pairs[i] for i in mdist.lpt_partition([len(x) * len(y) for x, y in pairs], world)[rank]]
-            if mine:
-                arrs = synth.dp_arrays(mine)
-                mp.libmems.nw_batch_arrays(*arrs)
-                res = mp.libmems.nw_batch_arrays(*arrs)
-                vals[0], vals[2] = float(res["stats"][0]), float(res["device_ms"])
-            sym = [synth.hmm_string(len(p_[0]), seed=i, block=300) for i, p_ in enumerate(synth.dp_pairs(512, 100, 10000, seed=20261020))] * 64
-            smine = [sym[i] for i in mdist.lpt_partition([len(x) for x in sym], world)[rank]]
-            if smine:
-                params = mp.libmems.hmm_params(0.5, 1e-5, 1e-9, 0.7)
-                mp.run_batch(smine, params, True)
-                _p, _q, hms = mp.run_batch(smine, params, True)
-                vals[1], vals[3] = float(sum(len(x) for x in smine)), float(hms)
+            dp = measure_dp(mp, synth, args, rank, comm)
         except Exception as e:  # noqa: BLE001
-            print("rank %d: sharded DP/HMM measurement failed: %s: %s" % (rank, type(e).__name__, e), file=sys.stderr)
-            vals = [0.0, 0.0, 0.0, 0.0, 0.0]
-        tsum = torch.tensor(vals[:2], dtype=torch.float64, device="cuda")
-        tmax = torch.tensor([vals[2], vals[3], -vals[4]], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum, tmax = tsum.tolist(), tmax.tolist()
-        if tmax[2] == -1.0 and tmax[0] > 0 and tmax[1] > 0:   # every rank succeeded
-            dp_sharded = {"metric": "GCUPS gapped DP (full-matrix cells, NWSmall-exact paths)", "value": tsum[0] / (tmax[0] * 1e-3) / 1e9, "unit": "GCUPS",
-                          "cells": tsum[0], "device_ms": tmax[0], "sharding": "regions divided among %d ranks by LPT on lenA*lenB; device ms = max over ranks" % world}
-            hmm_sharded = {"metric": "HomologyHMM columns/s (bfloat-faithful)", "value": tsum[1] / (tmax[1] * 1e-3), "unit": "columns/s",
-                           "device_ms": tmax[1], "sharding": "strings divided among %d ranks by LPT on length; device ms = max over ranks" % world}
-        else:
-            dp_sharded = hmm_sharded = {"error": "a rank failed (see stderr)"}
+            print("rank %d: DP measurement failed: %s: %s" % (rank, type(e).__name__, e), file=sys.stderr)
+            dp = {"error": "%s: %s" % (type(e).__name__, e)}
+        try:
+            hmm = measure_hmm(mp, synth, args, rank, comm)
+        except Exception as e:  # noqa: BLE001
+            print("rank %d: HMM measurement failed: %s: %s" % (rank, type(e).__name__, e), file=sys.stderr)
+            hmm = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        comm.barrier()
+        comm.close()
         return
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------
     peak, peak_src = measured_peaks()
     kb = 4 if 2 * weight + 2 <= 32 else 8
-    nsorted = int(stats[5])
+    nsorted = float(stats[5])          # seed records (all ranks)
+    npairs = float(stats[0])
     bucketed = sess.stage_ms[7] < 0
-    traffic = None
+    traffic_tab = {}
     prof = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            traffic_tab = json.load(open(prof))
         except Exception:
-            traffic = None
+            traffic_tab = {}
     other = None
     if bucketed:
-        # dominant kernel of the step by time: bk_group_kernel reads every 8-byte seed record once and writes 8 bytes per unique seed pair
-        npairs = float(stats[0])
-        kname = "bk_group_kernel (in-bucket grouping of %d 8-byte seed records into %d unique seed pairs)" % (nsorted, int(npairs))
-        bytes_per_launch = 8.0 * nsorted + 8.0 * npairs
-        per_launch_ms = float(stage[12])
+        per_rank = 1.0 / world
+        kern = {"bkf_scatter1_kernel": (8.0 * nsorted * per_rank + 0.25 * nbases, float(stage[9]),
+                                        "level-1 partition: 2-bit genomes in, one 8-byte seed record per owned position out"),
+                "bkf_scatter2_kernel": (16.0 * nsorted * per_rank, float(stage[11]), "level-2 partition of the 8-byte seed records"),
+                "bk_group2_kernel": ((8.0 * nsorted + 8.0 * npairs) * per_rank, float(stage[12]),
+                                     "in-bucket grouping (TMA-fed): every 8-byte seed record read once, 8 bytes per unique seed pair written")}
+        dom = max(kern, key=lambda k: kern[k][1])
+        bytes_per_launch, per_launch_ms, what = kern[dom]
+        kname = "%s (%s)" % (dom, what)
         launches_per_step = 1
-        if world > 1 or abs(args.mbp - 100.0) > 1e-9:
-            traffic = None  # the ncu capture under profiles/ is of the unsharded 100 Mbp launch
-        # the two partition passes, same formula (algorithmic bytes / CUDA-event time)
+        traffic = None
+        if world == 1 and abs(args.mbp - 100.0) < 1e-9:
+            traffic = (traffic_tab.get("kernels", {}).get(dom) or {}).get("dram_bytes_per_launch")
         other = {}
-        for name, nbytes, ms in (("bkf_scatter1_kernel", 8.0 * nsorted + 0.25 * nbases, float(stage[9])),
-                                 ("bkf_scatter2_kernel", 16.0 * nsorted, float(stage[11]))):
+        for name, (nbytes, ms, _w) in kern.items():
             if ms > 0:
                 other[name] = {"bytes_per_launch": nbytes, "launch_ms": ms, "achieved": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
     else:
         passes = int(sess.stage_ms[7])
-        traffic = None  # the capture under profiles/ describes bk_group
-        kname = "rs_onesweep_kernel (one 8-bit LSD radix pass over %d key/value pairs)" % nsorted
+        traffic = None
+        kname = "rs_onesweep_kernel (one 8-bit LSD radix pass over %d key/value pairs)" % int(nsorted)
         bytes_per_launch = 2.0 * (kb + 4) * nsorted
         per_launch_ms = float(stage[2]) / max(passes, 1)
         launches_per_step = passes
@@ -579,19 +680,22 @@ def main():
     # whole-step algorithmic bytes (LSD-sort formulation): 1.25 + B_sml(w) + (Kb+4) per base, + 28 B per seed pair
     P = (2 * weight + 1 + 7) // 8
     b_per_base = 1.25 + 0.25 + (kb + 4) + P * 2 * (kb + 4) + (kb + 4)
-    step_bytes = b_per_base * nbases + 28.0 * float(stats[0])
-    # bytes the bucketed formulation actually has to move: pack 1.25, records 8 written + 8 + 16 + 8 read/written, 16 + 28 per seed pair
+    step_bytes = b_per_base * nbases + 28.0 * npairs
+    # bytes the bucketed formulation itself has to move: pack 1.25, records 8 written + 8 + 16 + 8 read/written, 16 + 28 per seed pair
     b_bucket = 1.25 + 0.5 + 40.0
+    bucket_bytes = b_bucket * nbases + 44.0 * npairs
     dev_ms = float(stage[6])
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "launch_ms": per_launch_ms, "launches_per_step": launches_per_step,
-                "note": "bk_group is issue-bound (ncu: 81 % of issue slots busy, profiles/r01_ncu_bucket_enumeration_summary.txt), so its HBM fraction is low by construction; "
-                        "`step` gives the whole pass against SURVEY.md 8d's algorithmic bytes" if bucketed else None,
+                "note": "dominant kernel = the longest of the three partition / grouping kernels of this run (CUDA events on the launching stream); "
+                        "`step` gives the whole pass against SURVEY.md 8d's algorithmic bytes AND against the bytes the bucketed pipeline itself moves" if bucketed else None,
                 "other_kernels": other,
                 "step": {"algorithmic_bytes": step_bytes, "bytes_per_base": b_per_base, "device_ms": dev_ms,
                          "achieved": step_bytes / (dev_ms * 1e-3) / 1e9 if dev_ms > 0 else 0.0,
                          "frac": (step_bytes / (dev_ms * 1e-3) / 1e9 / peak) if dev_ms > 0 else 0.0,
+                         "frac_e2e": step_bytes / (dte / args.steps) / 1e9 / peak,
                          "bucketed_bytes_per_base": b_bucket if bucketed else None,
+                         "bucketed_frac": (bucket_bytes / (dev_ms * 1e-3) / 1e9 / peak) if (bucketed and dev_ms > 0) else None,
                          # the compulsory lower bound the reference itself quotes (LM/DNAMemorySML.h:23-24): not to be conflated
                          "compulsory_bytes_per_base": 4.25,
                          "compulsory_frac": (4.25 * nbases / (dev_ms * 1e-3) / 1e9 / peak) if dev_ms > 0 else 0.0,
@@ -608,35 +712,26 @@ def main():
             chk, kind = cpu_checker()
             sa, sb = cpu_sample(a, b, int(args.cpu_sample_mbp * 1e6))
             t0 = time.perf_counter()
-            rows, _ = chk.find_mums(sa, sb, seed, 0)
+            rows_c, _ = chk.find_mums(sa, sb, seed, 0)
             dtc = time.perf_counter() - t0
             # parity spot check on the same sample, through the C ABI
             grows, _ = mp.libmems.find_mums(sa, sb, seed)
-            same = bool(np.array_equal(grows, rows))
+            same = bool(np.array_equal(grows, rows_c))
             if not same:
                 print("PARITY FAILURE on the CPU sample", file=sys.stderr)
             cpu = {"value": (len(sa) + len(sb)) / 1e6 / dtc, "unit": "Mbp/s", "cores": 1, "kind": kind, "parity": "identical" if same else "FAILED",
                    "cores_on_box": os.cpu_count(), "projection_if_embarrassingly_parallel": (len(sa) + len(sb)) / 1e6 / dtc * (os.cpu_count() or 1),
                    "projection_note": "PROJECTION, not a measurement: the reference has no threads; value x cores_on_box",
                    "sample": "leading %.1f Mbp of both genomes (%d matches, GPU result %s); single thread: the reference has no threads"
-                             % (args.cpu_sample_mbp, rows.shape[0], "identical" if same else "DIFFERENT")}
+                             % (args.cpu_sample_mbp, rows_c.shape[0], "identical" if same else "DIFFERENT")}
         except Exception as e:  # noqa: BLE001
             cpu = {"error": "%s: %s" % (type(e).__name__, e)}
 
-    # ---- gapped DP + HMM (secondary metrics of BASELINE.json) ----------------------------------------
-    dp = hmm = None
-    if world > 1:
-        dp, hmm = dp_sharded, hmm_sharded
-    elif not args.no_dp:
-        # secondary metrics must never cost the headline line: a failure is reported inside the object
+    if world == 1 and not args.no_sml:
         try:
-            dp = measure_dp(mp, synth, args)
+            sml = measure_sml(mp, synth, args, a, pa, peak)
         except Exception as e:  # noqa: BLE001
-            dp = {"error": "%s: %s" % (type(e).__name__, e)}
-        try:
-            hmm = measure_hmm(mp, synth, args)
-        except Exception as e:  # noqa: BLE001
-            hmm = {"error": "%s: %s" % (type(e).__name__, e)}
+            sml = {"error": "%s: %s" % (type(e).__name__, e)}
     bidx = None
     if world == 1 and not args.no_cpu and not args.no_buildindex:
         # in a child process with a time limit: it drives external binaries, and nothing there may cost the headline line
@@ -651,17 +746,23 @@ def main():
         "metric": "Mbp/s seed+match+extend", "value": value, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64" if kb == 8 else "u32",
         "data": "synthetic", "config": config_dict(args, weight, seed), "matches": int(nmatch), "seed_pairs": int(stats[0]),
-        "device_ms_per_step": dev_ms,
+        "device_ms_per_step": dev_ms, "step_ms": spread(step_ms), "device_step_ms": spread(dev_ms_steps), "parity": parity,
         "timing": "value/ms_per_step: K steps between barrier + device synchronisation on both sides, max over ranks (a step has host-visible "
-                  "synchronisation points of its own, so this is the whole step); device_ms_per_step, roofline launch_ms and kernel_ms: CUDA "
-                  "events recorded by the library on the stream it launches on (rank 0)",
-        "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": int(nbases), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * dte / args.steps, "api": "mcu_find_mums(host buffers)" if world == 1 else "mcu_session_upload + enumerate, NCCL all-reduce of the seed bitmap, finish, NCCL gather, mcu_session_merge, mcu_session_download (rank 0)"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "dp": dp, "hmm": hmm, "buildindex": bidx,
+                  "synchronisation points of its own, so this is the whole step); step_ms: host clock per step on rank 0; device_ms_per_step, roofline "
+                  "launch_ms and kernel_ms: CUDA events recorded by the library on the stream it launches on (rank 0; at N > 1 the whole step incl. "
+                  "collectives and the merge)",
+        "e2e": {"value": e2e_value, "unit": "Mbp/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n_e2e) * 24,
+                "ms_per_step": 1e3 * dte / args.steps, "step_ms": spread(e2e_ms),
+                "api": "mcu_find_mums_into(pinned host sequences -> pinned host rows): chunked H2D on a copy stream overlapped with pack + the level-1 "
+                       "partition" if world == 1 else "mcu_find_mums_sharded (collective): every rank uploads 1/N of both genomes, packs it, ncclAllGather of "
+                       "the packed words; rows to rank 0's pinned buffer (h2d_bytes_per_step is per rank)"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "sml": sml, "dp": dp, "hmm": hmm, "buildindex": bidx,
     }
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    comm.barrier()
+    comm.close()
+    if parity is not None and parity.get("identical") is False:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

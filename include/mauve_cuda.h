@@ -73,6 +73,10 @@ int mcu_seed_weight(uint64_t seed);
 int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed,
                   uint32_t* pos_out, uint64_t* mer_out, uint32_t* packed_out, uint64_t* sml_len_out);
 
+/* device times of the last mcu_sml_build call (6 floats): [0] pack ms, [1] seed generation ms, [2] radix sort ms (CUDA events
+ * on the launching stream), [3] radix passes, [4] key bytes (4 or 8), [5] list length */
+void mcu_sml_last_stats(float* out6);
+
 /* ---- seed-match enumeration + extension: replaces MemHash::FindMatches(MatchList&)
  *      (LM/MemHash.cpp:109-127) for two genomes, i.e. MatchFinder::SearchRange
  *      (LM/MatchFinder.cpp:172-340) -> EnumerateMatches (LM/PairwiseMatchFinder.cpp:37-71 for

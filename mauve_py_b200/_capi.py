@@ -8,9 +8,10 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmauve_cuda.so")
+LIB_PATH = os.environ.get("MAUVE_CUDA_LIB") or os.path.join(HERE, "libmauve_cuda.so")   # the override selects an A/B build of the SAME library
 
-MCU_OK, MCU_ENODEV, MCU_ECUDA, MCU_EINVAL, MCU_EGAP, MCU_ENOMEM, MCU_EALPHA = 0, -1, -2, -3, -4, -5, -6
+MCU_OK, MCU_ENODEV, MCU_ECUDA, MCU_EINVAL, MCU_EGAP, MCU_ENOMEM, MCU_EALPHA, MCU_ESMALL = 0, -1, -2, -3, -4, -5, -6, -7
+COMM_ID_BYTES = 128
 SOLID_SEED = 0x7FFFFFFF
 CODING_SEED = 3
 RULE_PAIRWISE, RULE_MEMHASH = 0, 1
@@ -19,12 +20,15 @@ RULE_PAIRWISE, RULE_MEMHASH = 0, 1
 SYMBOLS = [
     "mcu_init", "mcu_shutdown", "mcu_last_error", "mcu_free", "mcu_host_alloc", "mcu_host_free",
     "mcu_get_seed", "mcu_default_seed_weight", "mcu_seed_length", "mcu_seed_weight",
-    "mcu_sml_build", "mcu_find_mums", "mcu_find_mums_batch",
-    "mcu_session_create", "mcu_session_destroy", "mcu_session_upload", "mcu_session_run",
+    "mcu_sml_build", "mcu_sml_last_stats", "mcu_find_mums", "mcu_find_mums_into", "mcu_find_mums_batch",
+    "mcu_session_create", "mcu_session_destroy", "mcu_session_upload", "mcu_session_upload_begin", "mcu_session_run",
     "mcu_session_enumerate", "mcu_session_uniq_bitmap", "mcu_session_finish", "mcu_session_merge",
     "mcu_session_match_count", "mcu_session_download", "mcu_session_matches_device",
     "mcu_session_launch_count", "mcu_merge_matches",
     "mcu_nw_batch", "mcu_nw_batch_wild", "mcu_nw_last_stats", "mcu_hmm_params", "mcu_hmm_batch", "mcu_sol_build", "mcu_anchor_scores",
+    "mcu_comm_unique_id", "mcu_comm_init", "mcu_comm_destroy", "mcu_comm_rank", "mcu_comm_world", "mcu_comm_barrier",
+    "mcu_comm_allreduce_f64", "mcu_comm_gather_bytes", "mcu_device_synchronize",
+    "mcu_session_upload_sharded", "mcu_session_run_sharded", "mcu_find_mums_sharded",
     "mcu_test_sort_pairs", "mcu_test_int32_peak",
 ]
 
@@ -67,7 +71,19 @@ def lib():
     L.mcu_seed_length.argtypes = [u64]
     L.mcu_seed_weight.argtypes = [u64]
     L.mcu_sml_build.argtypes = [vp, u64, u64, vp, vp, vp, C.POINTER(u64)]
+    L.mcu_sml_last_stats.argtypes = [vp]
+    L.mcu_sml_last_stats.restype = None
     L.mcu_find_mums.argtypes = [vp, u64, vp, u64, u64, i32, C.POINTER(C.POINTER(Match)), C.POINTER(u64), vp]
+    L.mcu_find_mums_into.argtypes = [vp, u64, vp, u64, u64, i32, vp, u64, C.POINTER(u64), vp]
+    L.mcu_find_mums_sharded.argtypes = [vp, u64, vp, u64, u64, i32, vp, u64, C.POINTER(u64), vp]
+    L.mcu_session_upload_begin.argtypes = [vp, vp, u64, vp, u64, i32]
+    L.mcu_session_upload_sharded.argtypes = [vp, vp, u64, vp, u64]
+    L.mcu_session_run_sharded.argtypes = [vp, u64, vp, vp]
+    L.mcu_comm_unique_id.argtypes = [vp]
+    L.mcu_comm_init.argtypes = [i32, i32, vp]
+    L.mcu_comm_destroy.restype = None
+    L.mcu_comm_allreduce_f64.argtypes = [vp, i32, i32]
+    L.mcu_comm_gather_bytes.argtypes = [vp, u64, C.POINTER(vp), vp]
     L.mcu_find_mums_batch.argtypes = [u64, vp, vp, vp, vp, vp, i32, C.POINTER(C.POINTER(Match)), vp, vp]
     L.mcu_session_create.argtypes = [C.POINTER(vp)]
     L.mcu_session_destroy.argtypes = [vp]

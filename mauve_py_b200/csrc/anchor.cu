@@ -907,7 +907,9 @@ static int sml_build_t(Session& s, const SeedParams& sp, u32* pos_out, u64* mer_
     const int passes = (key_bits + 7) / 8;
     unsigned long long* ctr = s.counters.as<unsigned long long>();
     MCU_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), s.stream));
+    MCU_CUDA(cudaEventRecord(s.ev[0], s.stream));
     MCU_TRY(run_pack(s, 0, (u32*)(ctr + 4)));
+    MCU_CUDA(cudaEventRecord(s.ev[1], s.stream));
     MCU_TRY(s.keys_a.reserve((npos + 1) * sizeof(u64)));  // u64-sized: the mer conversion reuses keys_b
     MCU_TRY(s.keys_b.reserve((npos + 1) * sizeof(u64)));
     MCU_TRY(s.vals_a.reserve((npos + 1) * sizeof(u32)));
@@ -918,13 +920,18 @@ static int sml_build_t(Session& s, const SeedParams& sp, u32* pos_out, u64* mer_
         seedgen_kernel<K><<<grid_for(npos, 256, 8), 256, passes * 256 * sizeof(u32), s.stream>>>(
             s.packed[0].as<u32>(), npos, sp, 0u, s.keys_a.as<K>(), s.vals_a.as<u32>(), 0, s.radix.hist.as<u64>(), passes, 0u, 1u, ctr + 5);
         s.launches++;
+        MCU_CUDA(cudaEventRecord(s.ev[2], s.stream));
         u64 before = s.radix.launches;
         MCU_TRY(radix_sort_pairs<K>(s.radix, s.keys_a.as<K>(), s.vals_a.as<u32>(), s.keys_b.as<K>(), s.vals_b.as<u32>(), npos, key_bits, true,
-                                    s.stream, &in_a, nullptr));
+                                    s.stream, &in_a, &s.sml_passes));
         s.launches += s.radix.launches - before;
-    }
+    } else
+        MCU_CUDA(cudaEventRecord(s.ev[2], s.stream));
+    MCU_CUDA(cudaEventRecord(s.ev[3], s.stream));
     MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     MCU_CUDA(cudaStreamSynchronize(s.stream));
+    for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&s.sml_ms[i], s.ev[i], s.ev[i + 1]);
+    s.sml_key_bytes_last = (int)sizeof(K);
     if (((u32*)(s.h_counters + 4))[0]) { set_error("gap character '-' in a genome sequence (input must be unaligned)"); return MCU_EGAP; }
     const K* skeys = in_a ? s.keys_a.as<K>() : s.keys_b.as<K>();
     const u32* svals = in_a ? s.vals_a.as<u32>() : s.vals_b.as<u32>();

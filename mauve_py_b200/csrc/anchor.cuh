@@ -32,6 +32,8 @@ struct Session {
     const u32* sml_vals = nullptr;
     u64 sml_npos = 0;
     int sml_key_bytes = 0;
+    float sml_ms[3] = {0, 0, 0};  // last sml_build_device: pack, seed generation, radix sort (CUDA events)
+    int sml_passes = 0, sml_key_bytes_last = 0;
     DevBuf sol_raw, sol_freq[2], as_rows, as_match, as_off, as_lcb;
     u64 n[2] = {0, 0};
     u64 match_count = 0;

@@ -212,6 +212,15 @@ int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out,
     return sml_build_device(*s, seq, n, seed, pos_out, mer_out, packed_out, sml_len_out);
 }
 
+void mcu_sml_last_stats(float* out6)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!out6 || !g_default_session) return;
+    const Session& s = *g_default_session;
+    out6[0] = s.sml_ms[0]; out6[1] = s.sml_ms[1]; out6[2] = s.sml_ms[2];
+    out6[3] = (float)s.sml_passes; out6[4] = (float)s.sml_key_bytes_last; out6[5] = (float)s.sml_npos;
+}
+
 // ---- MUMs -------------------------------------------------------------------------------
 int mcu_find_mums(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule, mcu_match** out,
                   uint64_t* n_out, uint64_t* stats)

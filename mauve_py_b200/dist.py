@@ -1,80 +1,174 @@
-"""Multi-GPU plumbing of the anchoring path: one process per GPU, torch.distributed.
+"""Multi-GPU plumbing of the anchoring path: one process per GPU.
 
-Every seed belongs to one rank (a hash of forward ^ reverse-complement mer, csrc/common.cuh seed_owned).  Two exchanges exist
-on the data path, both tiny:
-(1) a SUM all-reduce of the unique-seed bitmaps (1 bit per genome-0 position; the ranks' bits are
-disjoint) between enumeration and extension, because a match is emitted by its leftmost unique
-seed whichever rank owns that seed; (2) the gather of match rows to rank 0: an all_gather of the
-per-rank row counts followed by a variable-length gather of 24-byte rows.  NCCL over NVLink on the
-GPU box; gloo on CPU in the unit tests.
+The data path lives in the library (csrc/comm.cu): NCCL is called from C++ on the session's stream -- the sharded
+seed + match + extend step is ONE call (`AnchorSession.run_sharded` -> mcu_session_run_sharded) with no Python between its
+phases.  What is left here is start-up and the division of independent work:
+
+* `init_from_env()`     rank / world / device from the torchrun environment (RANK, WORLD_SIZE, LOCAL_RANK, MASTER_PORT), the
+                        128-byte NCCL id travels from rank 0 to the others through a file (one node), then mcu_comm_init.
+                        No torch anywhere on this path.
+* `NcclComm`            thin face of mcu_comm_* (barrier, all-reduce of host doubles, gather of host bytes to rank 0)
+* `TorchComm`           the same three operations over torch.distributed (gloo): lets the CPU test-suite run the host logic below
+                        with two and three processes; torch is imported only there
+* `lpt_partition`, `align_sharded`, `hmm_sharded`   gapped DP regions and HMM strings are independent: longest-processing-time-first
+                        division among the ranks, no collective on the data path, results gathered on rank 0
 """
-import torch
-import torch.distributed as dist
+import os
+import time
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, lib
+
+SUM, MAX, MIN = 0, 1, 2
 
 
-def shard_of(rank, world):
-    """(shard_index, shard_count) handed to mcu_session_run: rank r owns canonical-key slice r of `world` equal slices"""
-    return rank, world
+# ---- start-up ---------------------------------------------------------------------------------------------------------------------
+def _id_path(port):
+    # every rank of one launch is a child of the same launcher process (torchrun's agent), so its pid names the launch
+    tag = os.environ.get("MCU_RENDEZVOUS_TAG") or "%d" % os.getppid()
+    return os.path.join(os.environ.get("MCU_RENDEZVOUS_DIR", "/tmp"), "mcu_nccl_id_%s_%s" % (port, tag))
 
 
-class _DeviceWords:
-    """zero-copy view of a device buffer of int32 words for torch (CUDA array interface)"""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
-
-
-def allreduce_uniq_bitmap(session, group=None):
-    """Combine the ranks' unique-seed bitmaps in place.  Every genome-0 position belongs to exactly one rank's key slice,
-    so the bit sets are disjoint and an integer SUM of the words is their OR (NCCL has no bitwise reduction)."""
-    ptr, n = session.uniq_bitmap()
-    words = torch.as_tensor(_DeviceWords(ptr, n), device="cuda")
-    or_disjoint_words(words, group)
-    torch.cuda.current_stream().synchronize()
-
-
-def or_disjoint_words(words: torch.Tensor, group=None):
-    """in-place bitwise OR across ranks of int32 words whose set bits are disjoint between ranks (SUM == OR, carry-free)"""
-    dist.all_reduce(words, op=dist.ReduceOp.SUM, group=group)
-    return words
-
-
-def run_sharded(session, seed, rank, world, group=None):
-    """One sharded pass: enumerate this rank's slice, combine bitmaps, extend, gather rows to rank 0 and merge there.
-    Returns the number of matches on rank 0 (the session then holds the merged list), else this rank's own count."""
-    session.enumerate(seed, rank, world)
-    allreduce_uniq_bitmap(session, group)
-    n = session.finish(uniq_is_global=True)
-    rows = torch.empty((n, 3), dtype=torch.int64, device="cuda")
-    if n:
-        session.download_ptr(rows.data_ptr())
-    allrows = gather_rows(rows, 0, group)
+def exchange_id(rank, world, make_id, timeout=300.0):
+    """rank 0 makes the id and publishes it (write + atomic rename); the others poll for the file"""
+    path = _id_path(os.environ.get("MASTER_PORT", "0"))
     if rank == 0:
-        total, _ = session.merge(allrows.data_ptr(), in_device=True, n=allrows.shape[0])
-        return total
-    return n
+        blob = make_id()
+        tmp = path + ".tmp%d" % os.getpid()
+        with open(tmp, "wb") as f:
+            f.write(blob)
+        os.replace(tmp, path)
+        return blob, path
+    t0 = time.time()
+    while True:
+        try:
+            with open(path, "rb") as f:
+                blob = f.read()
+            if len(blob) == _capi.COMM_ID_BYTES:
+                return blob, path
+        except OSError:
+            pass
+        if time.time() - t0 > timeout:
+            raise TimeoutError("rank %d: no NCCL id at %s after %.0f s" % (rank, path, timeout))
+        time.sleep(0.01)
 
 
-def gather_rows(rows: torch.Tensor, dst: int = 0, group=None):
-    """rows: [n, 3] int64 tensor (cuda for nccl, cpu for gloo).  Returns the concatenation of all ranks' rows
-    (in rank order) on `dst`, None elsewhere."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = torch.cat(counts).tolist()   # one device->host read for all ranks' counts
-    rows = rows.contiguous()
-    if rank == dst:
-        parts = [torch.empty((c, 3), dtype=torch.int64, device=rows.device) for c in counts]
-        parts[dst] = rows
-        reqs = [dist.irecv(parts[r], src=r, group=group) for r in range(world) if r != dst and counts[r] > 0]
-        for q in reqs:
-            q.wait()
-        return torch.cat(parts, dim=0) if parts else rows
-    if rows.shape[0] > 0:
-        dist.send(rows, dst=dst, group=group)
-    return None
+class NcclComm:
+    """the library's own NCCL communicator (csrc/comm.cu); one per process"""
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def barrier(self):
+        check(lib().mcu_comm_barrier())
+
+    def allreduce(self, values, op=SUM):
+        """element-wise reduction of a list of floats over the ranks -> list of floats"""
+        v = np.ascontiguousarray(values, dtype=np.float64).copy()
+        check(lib().mcu_comm_allreduce_f64(v.ctypes.data, int(v.size), int(op)))
+        return v.tolist()
+
+    def gather_bytes(self, payload: bytes):
+        """one byte string per rank -> list in rank order on rank 0, None elsewhere"""
+        import ctypes as C
+        out = C.c_void_p()
+        counts = np.zeros(self.world, dtype=np.uint64)
+        buf = np.frombuffer(payload, dtype=np.uint8)
+        check(lib().mcu_comm_gather_bytes(buf.ctypes.data if buf.size else None, int(buf.size), C.byref(out), counts.ctypes.data))
+        if self.rank != 0:
+            return None
+        total = int(counts.sum())
+        blob = C.string_at(out, total) if total else b""
+        lib().mcu_free(out)
+        parts, pos = [], 0
+        for c in counts.tolist():
+            parts.append(blob[pos:pos + int(c)])
+            pos += int(c)
+        return parts
+
+    def close(self):
+        lib().mcu_comm_destroy()
+
+
+def init_from_env():
+    """mcu_init(LOCAL_RANK) + mcu_comm_init for the process layout torchrun (or any launcher setting the same variables) gives.
+    Returns an NcclComm; with WORLD_SIZE absent or 1 it is a one-rank communicator and no NCCL call is made."""
+    import ctypes as C
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    L = lib()
+    check(L.mcu_init(local))
+    if world == 1:
+        check(L.mcu_comm_init(0, 1, None))
+        return NcclComm(0, 1)
+
+    def make_id():
+        buf = C.create_string_buffer(_capi.COMM_ID_BYTES)
+        check(L.mcu_comm_unique_id(buf))
+        return buf.raw
+
+    blob, path = exchange_id(rank, world, make_id)
+    check(L.mcu_comm_init(rank, world, blob))
+    comm = NcclComm(rank, world)
+    comm.barrier()
+    if rank == 0:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+    return comm
+
+
+class TorchComm:
+    """barrier / allreduce / gather_bytes over an initialised torch.distributed group (gloo on CPU): test plumbing for the host
+    logic of this module; the product path uses NcclComm"""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist, self._group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def barrier(self):
+        self._dist.barrier(group=self._group)
+
+    def allreduce(self, values, op=SUM):
+        import torch
+        t = torch.tensor(list(values), dtype=torch.float64)
+        ops = {SUM: self._dist.ReduceOp.SUM, MAX: self._dist.ReduceOp.MAX, MIN: self._dist.ReduceOp.MIN}
+        self._dist.all_reduce(t, op=ops[op], group=self._group)
+        return t.tolist()
+
+    def gather_bytes(self, payload: bytes):
+        import torch
+        dist = self._dist
+        buf = torch.from_numpy(np.frombuffer(payload, dtype=np.uint8).copy())
+        n = torch.tensor([buf.numel()], dtype=torch.int64)
+        counts = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(counts, n, group=self._group)
+        counts = torch.cat(counts).tolist()
+        if self.rank == 0:
+            parts = [torch.empty(c, dtype=torch.uint8) for c in counts]
+            parts[0] = buf
+            reqs = [dist.irecv(parts[r], src=r, group=self._group) for r in range(self.world) if r != 0 and counts[r] > 0]
+            for q in reqs:
+                q.wait()
+            return [p.numpy().tobytes() for p in parts]
+        if buf.numel() > 0:
+            dist.send(buf, dst=0, group=self._group)
+        return None
+
+
+def gather_rows(rows, comm):
+    """rows: int64 [n, 3] array per rank -> concatenation in rank order on rank 0 (None elsewhere).  Host-side helper for callers
+    that finished shards independently (mcu_merge_matches); the sharded step itself gathers on the device (comm.cu)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3)
+    parts = comm.gather_bytes(rows.tobytes())
+    if parts is None:
+        return None
+    return np.frombuffer(b"".join(parts), dtype=np.int64).reshape(-1, 3).copy()
 
 
 # ---- gapped DP and HMM: independent regions / strings, no collective on the data path --------------------------------
@@ -93,47 +187,21 @@ def lpt_partition(costs, world):
     return [sorted(p) for p in parts]
 
 
-def gather_bytes(payload: bytes, dst: int = 0, group=None, device=None):
-    """variable-length gather of one byte string per rank to `dst` (list in rank order there, None elsewhere); the same counts +
-    point-to-point pattern as gather_rows, on `device` (cuda for nccl, cpu for gloo)"""
-    import numpy as np
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    if device is None:
-        device = torch.device("cuda") if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    buf = torch.from_numpy(np.frombuffer(payload, dtype=np.uint8).copy()).to(device)
-    n = torch.tensor([buf.numel()], dtype=torch.int64, device=device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = torch.cat(counts).tolist()
-    if rank == dst:
-        parts = [torch.empty(c, dtype=torch.uint8, device=device) for c in counts]
-        parts[dst] = buf
-        reqs = [dist.irecv(parts[r], src=r, group=group) for r in range(world) if r != dst and counts[r] > 0]
-        for q in reqs:
-            q.wait()
-        return [p.cpu().numpy().tobytes() for p in parts]
-    if buf.numel() > 0:
-        dist.send(buf, dst=dst, group=group)
-    return None
-
-
-def align_sharded(pairs, rank, world, group=None, align=None):
+def align_sharded(pairs, comm, align=None):
     """muscle::GlobalAlign for a batch of region pairs divided among the ranks by LPT on lenA * lenB.  Every rank holds the
     whole `pairs` list (like the genomes), aligns its share on its GPU and ships (lengths, scores, edges) to rank 0, which returns
     the PWPaths in input order; other ranks return None.  `align` defaults to libmems.GlobalAlignBatch."""
-    import numpy as np
     from . import libmems
     align = align or libmems.GlobalAlignBatch
+    rank, world = comm.rank, comm.world
     plan = lpt_partition([len(a) * len(b) for a, b in pairs], world)
     mine = plan[rank]
     paths = align([pairs[i] for i in mine]) if mine else []
-    lens = np.array([len(p.edges) for p in paths], dtype=np.int64)
-    scores = np.array([p.score for p in paths], dtype=np.int64)
-    payload = lens.tobytes() + scores.tobytes() + b"".join(p.edges for p in paths)
     if world == 1:
         return paths
-    got = gather_bytes(payload, 0, group)
+    lens = np.array([len(p.edges) for p in paths], dtype=np.int64)
+    scores = np.array([p.score for p in paths], dtype=np.int64)
+    got = comm.gather_bytes(lens.tobytes() + scores.tobytes() + b"".join(p.edges for p in paths))
     if rank != 0:
         return None
     out = [None] * len(pairs)
@@ -148,17 +216,18 @@ def align_sharded(pairs, rank, world, group=None, align=None):
     return out
 
 
-def hmm_sharded(sequences, params, rank, world, group=None, run_batch=None):
+def hmm_sharded(sequences, params, comm, run_batch=None):
     """run() of the HomologyHMM for a batch of column strings divided among the ranks by LPT on their lengths; rank 0 returns the
     H/N predictions in input order, other ranks None.  `run_batch` defaults to libmems.run_batch."""
     from . import libmems
     run_batch = run_batch or libmems.run_batch
+    rank, world = comm.rank, comm.world
     plan = lpt_partition([len(s) for s in sequences], world)
     mine = plan[rank]
     preds = run_batch([sequences[i] for i in mine], params) if mine else []
     if world == 1:
         return preds
-    got = gather_bytes(b"".join(preds), 0, group)
+    got = comm.gather_bytes(b"".join(preds))
     if rank != 0:
         return None
     out = [None] * len(sequences)

@@ -518,9 +518,23 @@ class AnchorSession:
     def upload_ptr(self, addr0, n0, addr1, n1):
         check(lib().mcu_session_upload(self._h, addr0, n0, addr1, n1))
 
+    def upload_begin_ptr(self, addr0, n0, addr1, n1, chunks=8):
+        """asynchronous chunked H2D (copy stream); the next run() overlaps pack + the first partition pass with the copies"""
+        check(lib().mcu_session_upload_begin(self._h, addr0, n0, addr1, n1, chunks))
+
+    def upload_sharded_ptr(self, addr0, n0, addr1, n1):
+        """collective: this rank's 1 / world slice of both genomes (mcu_comm_init first)"""
+        check(lib().mcu_session_upload_sharded(self._h, addr0, n0, addr1, n1))
+
     def run(self, seed, shard_index=0, shard_count=1):
         check(lib().mcu_session_run(self._h, seed, shard_index, shard_count, self.stage_ms.ctypes.data, self.stats.ctypes.data))
         return int(lib().mcu_session_match_count(self._h))
+
+    def run_sharded(self, seed):
+        """collective (every rank): one pass sharded over the ranks of mcu_comm_init; rank 0's session ends up with the whole list.
+        Returns the total number of matches (on every rank)."""
+        check(lib().mcu_session_run_sharded(self._h, seed, self.stage_ms.ctypes.data, self.stats.ctypes.data))
+        return int(self.stats[1])
 
     def enumerate(self, seed, shard_index=0, shard_count=1):
         check(lib().mcu_session_enumerate(self._h, seed, shard_index, shard_count))

@@ -173,3 +173,144 @@ int mcu_hmm_batch(uint64_t n, const char* sym, const uint64_t* off, const double
 }
 int mcu_test_sort_pairs(void* k, void* v, uint64_t n, int bits, int kb) { (void)k; (void)v; (void)n; (void)bits; (void)kb; return -1; }
 int mcu_test_int32_peak(double* gops, float* ms) { if (gops) *gops = 1000.0; if (ms) *ms = 1.0f; return 0; }
+
+/* ---- round 2 entry points: caller-buffer form, chunked upload, the library's own communicator ------------------------------------ */
+#include <stdio.h>
+#include <unistd.h>
+#include <sys/stat.h>
+
+int mcu_find_mums_into(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule, mcu_match* rows_out, uint64_t cap,
+                       uint64_t* n_out, uint64_t* stats)
+{
+    mcu_match* r = NULL;
+    uint64_t n = 0;
+    const int rc = mcu_find_mums(seq0, n0, seq1, n1, seed, rule, &r, &n, stats);
+    if (rc) return rc;
+    *n_out = n;
+    if (n > cap) { free(r); return -7; }
+    if (n) memcpy(rows_out, r, n * sizeof(mcu_match));
+    free(r);
+    return 0;
+}
+void mcu_sml_last_stats(float* out6) { out6[0] = 0.1f; out6[1] = 1.0f; out6[2] = 2.0f; out6[3] = 5.0f; out6[4] = 8.0f; out6[5] = 0.0f; }
+int mcu_session_upload_begin(void* h, const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, int chunks)
+{
+    (void)chunks;
+    return mcu_session_upload(h, seq0, n0, seq1, n1);
+}
+int mcu_device_synchronize(void) { return 0; }
+
+/* communicator over files: every collective writes one file per rank and reads the others' (same directory, same sequence number) */
+static struct { int rank, world, ok; unsigned long long seq; char tag[80]; } g_sc;
+int mcu_comm_unique_id(void* id_out)
+{
+    memset(id_out, 0, 128);
+    snprintf((char*)id_out, 64, "%ld_%ld", (long)getpid(), (long)time(NULL));
+    return 0;
+}
+int mcu_comm_init(int rank, int world, const void* id)
+{
+    g_sc.rank = rank; g_sc.world = world; g_sc.ok = 1; g_sc.seq = 0;
+    snprintf(g_sc.tag, sizeof g_sc.tag, "/tmp/mcu_stub_comm_%s", world > 1 ? (const char*)id : "solo");
+    return 0;
+}
+void mcu_comm_destroy(void) { g_sc.ok = 0; }
+int mcu_comm_rank(void) { return g_sc.ok ? g_sc.rank : 0; }
+int mcu_comm_world(void) { return g_sc.ok ? g_sc.world : 1; }
+static void sc_path(char* out, size_t cap, unsigned long long seq, int rank) { snprintf(out, cap, "%s_%llu_%d", g_sc.tag, seq, rank); }
+/* all-gather of one blob per rank: out[r] = malloc'ed copy, len[r] */
+static int sc_exchange(const void* mine, uint64_t n, void** out, uint64_t* len)
+{
+    char path[200], tmp[220];
+    int r;
+    const unsigned long long seq = g_sc.seq++;
+    sc_path(path, sizeof path, seq, g_sc.rank);
+    snprintf(tmp, sizeof tmp, "%s.tmp", path);
+    FILE* f = fopen(tmp, "wb");
+    if (!f) return -2;
+    if (n) fwrite(mine, 1, n, f);
+    fclose(f);
+    rename(tmp, path);
+    for (r = 0; r < g_sc.world; ++r) {
+        struct stat st;
+        int tries = 0;
+        sc_path(path, sizeof path, seq, r);
+        while (stat(path, &st) != 0) { usleep(2000); if (++tries > 150000) return -2; }
+        len[r] = (uint64_t)st.st_size;
+        out[r] = malloc(len[r] ? len[r] : 1);
+        f = fopen(path, "rb");
+        if (len[r] && fread(out[r], 1, len[r], f) != len[r]) { fclose(f); return -2; }
+        fclose(f);
+    }
+    /* second phase: nobody removes a file before every rank has read all of them */
+    {
+        const unsigned long long seq2 = g_sc.seq++;
+        sc_path(path, sizeof path, seq2, g_sc.rank);
+        f = fopen(path, "wb"); fclose(f);
+        for (r = 0; r < g_sc.world; ++r) {
+            struct stat st;
+            int tries = 0;
+            sc_path(path, sizeof path, seq2, r);
+            while (stat(path, &st) != 0) { usleep(2000); if (++tries > 150000) return -2; }
+        }
+        sc_path(path, sizeof path, seq, g_sc.rank);
+        remove(path);
+    }
+    return 0;
+}
+int mcu_comm_allreduce_f64(double* v, int n, int op)
+{
+    void* out[64];
+    uint64_t len[64];
+    int r, i;
+    if (!g_sc.ok) return -3;
+    if (g_sc.world == 1 || n == 0) return 0;
+    if (sc_exchange(v, (uint64_t)n * sizeof(double), out, len)) return -2;
+    for (i = 0; i < n; ++i) {
+        double acc = ((double*)out[0])[i];
+        for (r = 1; r < g_sc.world; ++r) {
+            const double x = ((double*)out[r])[i];
+            acc = op == 0 ? acc + x : op == 1 ? (x > acc ? x : acc) : (x < acc ? x : acc);
+        }
+        v[i] = acc;
+    }
+    for (r = 0; r < g_sc.world; ++r) free(out[r]);
+    return 0;
+}
+int mcu_comm_barrier(void) { double one = 1.0; return g_sc.ok ? mcu_comm_allreduce_f64(&one, 1, 0) : -3; }
+int mcu_comm_gather_bytes(const void* send, uint64_t n, void** out, uint64_t* counts_out)
+{
+    void* parts[64];
+    uint64_t len[64], total = 0, pos = 0;
+    int r;
+    if (!g_sc.ok) return -3;
+    *out = NULL;
+    if (g_sc.world == 1) { parts[0] = malloc(n ? n : 1); if (n) memcpy(parts[0], send, n); len[0] = n; }
+    else if (sc_exchange(send, n, parts, len)) return -2;
+    for (r = 0; r < g_sc.world; ++r) { total += len[r]; if (counts_out) counts_out[r] = len[r]; }
+    if (g_sc.rank == 0) {
+        char* cat = (char*)malloc(total ? total : 1);
+        for (r = 0; r < g_sc.world; ++r) { if (len[r]) memcpy(cat + pos, parts[r], len[r]); pos += len[r]; }
+        *out = cat;
+    }
+    for (r = 0; r < g_sc.world; ++r) free(parts[r]);
+    return 0;
+}
+int mcu_session_upload_sharded(void* h, const char* seq0, uint64_t n0, const char* seq1, uint64_t n1) { return mcu_session_upload(h, seq0, n0, seq1, n1); }
+/* every rank's stand-in computes the whole list (they hold the whole genomes); rank 0's is "the merged one" */
+int mcu_session_run_sharded(void* h, uint64_t seed, float* stage_ms, uint64_t* stats) { return mcu_session_run(h, seed, 0, 1, stage_ms, stats); }
+int mcu_find_mums_sharded(const char* seq0, uint64_t n0, const char* seq1, uint64_t n1, uint64_t seed, int rule, mcu_match* rows_out, uint64_t cap,
+                          uint64_t* n_out, uint64_t* stats)
+{
+    mcu_match* r = NULL;
+    uint64_t n = 0;
+    const int rc = mcu_find_mums(seq0, n0, seq1, n1, seed, rule, &r, &n, stats);
+    if (rc) return rc;
+    *n_out = n;
+    if (g_sc.rank == 0) {
+        if (n > cap) { free(r); return -7; }
+        if (n) memcpy(rows_out, r, n * sizeof(mcu_match));
+    }
+    free(r);
+    return 0;
+}

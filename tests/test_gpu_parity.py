@@ -332,9 +332,9 @@ def test_mums_solid_seed_paths(mp, orc, w):
 
 # ---- two-phase sharded run (enumerate | all-reduce of the unique-seed bitmap | finish | merge) ---------------
 def _two_phase(mp, a, b, seed, world):
-    """world sessions on one GPU stand in for world ranks; the bitmap SUM is what dist.allreduce_uniq_bitmap does over NCCL"""
+    """world sessions on one GPU stand in for world ranks; the bitmap SUM is what comm.cu's ncclAllReduce does between real ranks"""
     import torch
-    from mauve_py_b200.dist import _DeviceWords
+    from _devwords import DeviceWords as _DeviceWords
     sess = []
     for rank in range(world):
         s = mp.AnchorSession()
@@ -457,3 +457,64 @@ def test_gap_batch_equals_single_pair_calls(mp):
     for (a, b), rows in zip(pairs, res):
         single, _ = mp.libmems.find_mums(a, b, seeds[0], 1)
         assert np.array_equal(rows, single)
+
+
+# ---- chunked upload: pack + level-1 partition of a piece run under the copies of the next pieces (mcu_session_upload_begin) ----
+@pytest.mark.parametrize("w,r,n,chunks", [(15, 3, 400000, 1), (15, 3, 400000, 3), (19, 3, 350000, 8), (13, 0, 277777, 5), (19, 3, 70000, 64),
+                                          (9, 0, 20000, 4)])
+def test_chunked_upload_overlap_exact(mp, orc, w, r, n, chunks):
+    """whatever the piece boundaries (a piece is a whole number of 4096-position scatter tiles; seeds reach into the next piece;
+    genome 0's last tile straddles into genome 1), the rows equal the oracle's; sizes below the bucketed plan take the unoverlapped path"""
+    a, b = synth.small_pair(n, seed=7 * n + w, snp=0.01, n_inv=2)
+    seed = mp.getSeed(w, r)
+    ha, hb = np.frombuffer(a, dtype=np.uint8).copy(), np.frombuffer(b, dtype=np.uint8).copy()
+    s = mp.AnchorSession()
+    for _ in range(2):   # twice: the second upload starts while the first run's buffers are the live ones
+        s.upload_begin_ptr(ha.ctypes.data, ha.size, hb.ctypes.data, hb.size, chunks)
+        cnt = s.run(seed)
+        rows = s.download().copy()
+        orows, _ = orc.find_mums(a, b, seed, 0)
+        assert cnt == orows.shape[0] and np.array_equal(rows, orows)
+    # a plain upload after a chunked one leaves no stale piece state behind
+    s.upload(a, b)
+    assert s.run(seed) == orows.shape[0] and np.array_equal(s.download(), orows)
+    s.close()
+
+
+def test_find_mums_into_caller_buffer(mp, orc):
+    """mcu_find_mums_into: rows land in caller memory; a buffer that is too small is refused with the required size"""
+    import ctypes as C
+    a, b = synth.small_pair(300000, seed=5, snp=0.01)
+    seed = mp.getSeed(15, 3)
+    orows, _ = orc.find_mums(a, b, seed, 0)
+    buf = np.zeros((orows.shape[0] + 5, 3), dtype=np.int64)
+    n_out = C.c_uint64(0)
+    stats = np.zeros(8, dtype=np.uint64)
+    rc = mp.lib().mcu_find_mums_into(a, len(a), b, len(b), seed, 0, buf.ctypes.data, buf.shape[0], C.byref(n_out), stats.ctypes.data)
+    assert rc == 0 and n_out.value == orows.shape[0] and np.array_equal(buf[:n_out.value], orows)
+    rc = mp.lib().mcu_find_mums_into(a, len(a), b, len(b), seed, 0, buf.ctypes.data, 3, C.byref(n_out), None)
+    assert rc == -7 and n_out.value == orows.shape[0]
+
+
+def test_sharded_entry_points_with_one_rank(mp, orc):
+    """a one-rank communicator makes the collective entry points plain calls (no NCCL): same rows"""
+    import ctypes as C
+    lib = mp.lib()
+    if lib.mcu_comm_world() == 1 and lib.mcu_comm_rank() == 0:
+        lib.mcu_comm_init(0, 1, None)    # idempotence is not promised: a second call answers MCU_EINVAL and changes nothing
+    a, b = synth.small_pair(200000, seed=9, snp=0.01)
+    seed = mp.getSeed(13, 0)
+    orows, _ = orc.find_mums(a, b, seed, 0)
+    s = mp.AnchorSession()
+    s.upload(a, b)
+    assert s.run_sharded(seed) == orows.shape[0] and np.array_equal(s.download(), orows)
+    buf = np.zeros((orows.shape[0] + 1, 3), dtype=np.int64)
+    n_out = C.c_uint64(0)
+    assert lib.mcu_find_mums_sharded(a, len(a), b, len(b), seed, 0, buf.ctypes.data, buf.shape[0], C.byref(n_out), None) == 0
+    assert np.array_equal(buf[:n_out.value], orows)
+    st = np.zeros(6, dtype=np.float32)
+    sml = mp.DNAMemorySML()
+    sml.Create(a, seed)
+    lib.mcu_sml_last_stats(st.ctypes.data)
+    assert st[2] > 0 and int(st[3]) >= 1 and int(st[5]) == len(a) - mp.getSeedLength(seed) + 1
+    s.close()

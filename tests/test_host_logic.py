@@ -44,32 +44,26 @@ def _free_port():
 
 
 def _gather_worker(rank, world, port, q):
-    import torch
     import torch.distributed as dist
     from mauve_py_b200 import dist as mdist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        comm = mdist.TorchComm()
+        assert (comm.rank, comm.world) == (rank, world)
         # rank r holds r*3+1 rows (rank 1 of 3 holds none when world == 3 -> exercised by n=0 below)
         n = 0 if (world == 3 and rank == 1) else rank * 3 + 1
-        rows = torch.arange(n * 3, dtype=torch.int64).reshape(n, 3) + 1000 * rank
-        out = mdist.gather_rows(rows, dst=0)
+        rows = np.arange(n * 3, dtype=np.int64).reshape(n, 3) + 1000 * rank
+        out = mdist.gather_rows(rows, comm)
         if rank == 0:
-            q.put(out.numpy().tolist())
+            q.put(out.tolist())
         else:
             assert out is None
-        assert mdist.shard_of(rank, world) == (rank, world)
-        # unique-seed bitmaps of the ranks' key slices are disjoint: the SUM all-reduce is their OR (sign bit included)
-        rng = np.random.default_rng(7)
-        owner = rng.integers(0, world, size=64 * 32)
-        bits = rng.integers(0, 2, size=64 * 32).astype(bool)
-        bits[31] = True
-        full = np.packbits(bits.reshape(-1, 32)[:, ::-1], axis=1, bitorder="big").view(">u4").astype(np.uint32).reshape(-1)
-        mine = np.packbits((bits & (owner == rank)).reshape(-1, 32)[:, ::-1], axis=1, bitorder="big").view(">u4").astype(np.uint32).reshape(-1)
-        words = torch.from_numpy(mine.view(np.int32).copy())
-        mdist.or_disjoint_words(words)
-        assert np.array_equal(words.numpy().view(np.uint32), full)
+        # the three reductions bench.py uses (sum of cells, max of times over ranks)
+        assert comm.allreduce([1.0, float(rank)], mdist.SUM) == [float(world), float(sum(range(world)))]
+        assert comm.allreduce([float(rank)], mdist.MAX) == [float(world - 1)] and comm.allreduce([float(rank) + 5], mdist.MIN) == [5.0]
+        comm.barrier()
     finally:
         dist.destroy_process_group()
 
@@ -118,8 +112,9 @@ def _shard_worker(rank, world, port, q):
         def run_batch(ss, p):
             return [orc.hmm_run(s, p)[0] if len(s) else b"" for s in ss]
 
-        paths = mdist.align_sharded(pairs, rank, world, align=align)
-        preds = mdist.hmm_sharded(strings, params, rank, world, run_batch=run_batch)
+        comm = mdist.TorchComm()
+        paths = mdist.align_sharded(pairs, comm, align=align)
+        preds = mdist.hmm_sharded(strings, params, comm, run_batch=run_batch)
         if rank == 0:
             q.put(([(p.edges, p.score) for p in paths], preds))
         else:
@@ -242,3 +237,45 @@ def test_sml_accessors_against_the_reference_classes(orc):
         c = sml.Clone()
         c._pos[0] ^= 1
         assert sml._pos[0] != c._pos[0] and sml.GetHeader()["seed"] == seed and c.GetHeader()["length"] == len(seq)
+
+
+def _rendezvous_worker(rank, world, port, tag, stub, q):
+    """init_from_env of the product's dist module in a launcher-like environment, with the stand-in library (its communicator exchanges
+    files): the NCCL id reaches every rank through the rendezvous file, collectives of the C ABI line up, rank 0 removes the file"""
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_PORT=str(port), MCU_RENDEZVOUS_TAG=tag)
+    import mauve_py_b200._capi as capi
+    capi.LIB_PATH = stub
+    from mauve_py_b200 import dist as mdist
+    comm = mdist.init_from_env()
+    assert (comm.rank, comm.world) == (rank, world)
+    assert comm.allreduce([float(rank + 1)], mdist.SUM) == [float(world * (world + 1) // 2)]
+    parts = comm.gather_bytes(bytes([65 + rank]) * (rank * 2))   # rank 0 contributes nothing
+    if rank == 0:
+        q.put([p.decode() for p in parts])
+    else:
+        assert parts is None
+    comm.barrier()
+    comm.close()
+
+
+def test_rendezvous_file_and_library_communicator_two_ranks():
+    import multiprocessing as mproc
+    import _emu
+    from mauve_py_b200 import dist as mdist
+    stub = _emu.bench_stub_library()
+    ctx = mproc.get_context("spawn")
+    q = ctx.Queue()
+    port, tag = _free_port(), "pytest%d" % os.getpid()
+    procs = [ctx.Process(target=_rendezvous_worker, args=(r, 3, port, tag, stub, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert got == ["", "BB", "CCCC"]
+    os.environ["MCU_RENDEZVOUS_TAG"] = tag
+    try:
+        assert not os.path.exists(mdist._id_path(port))     # removed by rank 0 after the first barrier
+    finally:
+        del os.environ["MCU_RENDEZVOUS_TAG"]

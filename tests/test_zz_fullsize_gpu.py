@@ -38,6 +38,15 @@ def test_config3_100mbp_pair_properties(mp):
     n = s.run(seed)
     rows = s.download().copy()
     assert n == rows.shape[0] > 500000
+    # the WHOLE list equals the list the reference's own code returns for this pair (tests/golden/make_golden_config3.py ran
+    # oracle/_ref = unmodified MatchFinder / MemHash sources on the full 100 Mbp pair: 414 s on one core)
+    import hashlib
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config3_rows.json")))
+    assert n == g["reference"]["rows"] == 827941
+    assert hashlib.sha1(np.ascontiguousarray(rows, dtype=np.int64).tobytes()).hexdigest() == g["reference"]["sha1"]
+    assert int(s.stats[3]) == 0 and g["oracle_equals_reference"]       # no mer beyond MER_REPEAT_LIMIT: the documented divergence cannot occur here
     assert int(s.stats[0]) - int(s.stats[1]) == int(s.stats[2])          # seed pairs = matches + collisions
     # every sampled row is a maximal run of seed hits inside both genomes; the whole list is in GetMatchList order
     assert P.check_mum_rows(ab, bb, rows, seed, L, sample=4000, rng=np.random.default_rng(1)) == 4000
@@ -49,7 +58,7 @@ def test_config3_100mbp_pair_properties(mp):
     assert s.run(seed) == n and np.array_equal(s.download(), rows)
     # a sharded run (each "rank" owning half of the seeds, bitmaps combined) emits every match exactly once
     import torch
-    from mauve_py_b200.dist import _DeviceWords
+    from _devwords import DeviceWords as _DeviceWords
     t = mp.AnchorSession()
     t.upload(ab, bb)
     s.enumerate(seed, 0, 2)
