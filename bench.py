@@ -546,8 +546,8 @@ def main():
     launches0 = sess.launch_count()
     stage = np.zeros(16, dtype=np.float64)
     step_ms, dev_ms_steps = [], []
+    sampler = start_clock_sampler(local) if rank == 0 else None   # before the barrier: its start-up (NVML init) is not part of any rank's steps
     comm.barrier()
-    sampler = start_clock_sampler(local) if rank == 0 else None
     t0 = time.perf_counter()
     nmatch = 0
     for _ in range(args.steps):
@@ -656,7 +656,7 @@ def main():
         kern = {"bkf_scatter1_kernel": (8.0 * nsorted * per_rank + 0.25 * nbases, float(stage[9]),
                                         "level-1 partition: 2-bit genomes in, one 8-byte seed record per owned position out"),
                 "bkf_scatter2_kernel": (16.0 * nsorted * per_rank, float(stage[11]), "level-2 partition of the 8-byte seed records"),
-                "bk_group2_kernel": ((8.0 * nsorted + 8.0 * npairs) * per_rank, float(stage[12]),
+                "bk_group3_kernel": ((8.0 * nsorted + 8.0 * npairs) * per_rank, float(stage[12]),
                                      "in-bucket grouping (TMA-fed): every 8-byte seed record read once, 8 bytes per unique seed pair written")}
         dom = max(kern, key=lambda k: kern[k][1])
         bytes_per_launch, per_launch_ms, what = kern[dom]

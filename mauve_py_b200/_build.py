@@ -56,7 +56,7 @@ def build_library(force=False, verbose=False):
         list(ex.map(compile_one, jobs))
     objs = [os.path.join(objdir, src.replace(".cu", ".o")) for src in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        cmd = [cc, "-shared", "-cudart", "static", "-o", LIB] + objs + ["-lnccl"]
+        cmd = [cc, "-shared", "-cudart", "static", "-o", LIB] + objs + ["-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s" % r.stderr)

@@ -19,6 +19,7 @@
 #include "libMUSCLE/profile.h"
 #include "libMUSCLE/pwpath.h"
 #include "libMUSCLE/alpha.h"
+#include "libMUSCLE/params.h"
 #include "mauve_cuda.h"
 
 namespace muscle {
@@ -77,7 +78,25 @@ inline bool ProfileToStringWild(const ProfPos* P, unsigned n, std::string& out, 
 	return n > 0;
 }
 
-const unsigned long long kWildMaxCells = 1ull << 24;   // mcu_nw_batch_wild walks a region with one thread
+// The device kernels have the reference's DEFAULT DNA scoring built in: substitution NUC_SP (MU/nucmx.cpp:8-25 with the +60 centre),
+// gap open = close = -400 / 2 per column, terminal gaps free, gap extend 0 (MU/params.cpp:296-313; libMems calls MUSCLE with these:
+// LM/MuscleInterface.cpp:1086-1106).  --muscle-args or a caller of CallMuscleFast can change them; a range whose profiles were built
+// with anything else must stay with the reference's ProfileProfile.  Checked on what the profile columns themselves carry.
+inline bool DefaultScoring(const ProfPos* P, unsigned n)
+{
+	static const SCORE nuc[4][4] = {{151, -54, 29, -63}, {-54, 160, -65, 29}, {29, -65, 160, -54}, {-63, 29, -54, 151}};
+	if (g_scoreGapExtend.get() != 0 || g_PPScore.get() != PPSCORE_SPN) return false;
+	for (unsigned i = 0; i < n; ++i) {
+		const ProfPos& pp = P[i];
+		if (pp.m_scoreGapOpen != (SCORE)-200 && !(i == 0 && pp.m_scoreGapOpen == 0)) return false;
+		if (pp.m_scoreGapClose != (SCORE)-200 && !(i + 1 == n && pp.m_scoreGapClose == 0)) return false;
+		const unsigned u = pp.m_uSortOrder[0];
+		if (u < 4 && pp.m_fcCounts[u] == 1.0f)   // a plain letter: its AAScores row is the substitution matrix row
+			for (unsigned j = 0; j < 4; ++j)
+				if (pp.m_AAScores[j] != nuc[u][j]) return false;
+	}
+	return true;
+}
 
 // edge string -> PWPath (PWEdge prefix lengths count the letters consumed including this edge)
 inline void EdgesToPath(const char* e, uint32_t len, PWPath& P)
@@ -95,14 +114,14 @@ inline void EdgesToPath(const char* e, uint32_t len, PWPath& P)
 // Aligns every range on the device; paths (ranges.size() caller-owned objects: PWPath is not copyable) is filled for
 // handled[i] == true.
 inline void CudaGlobalAlignBatch(const std::vector<CudaDPRange>& ranges, PWPath* paths, std::vector<bool>& handled,
-                                 std::vector<long long>* scores = NULL, bool wildcards = false)
+                                 std::vector<long long>* scores = NULL, bool wildcards = true)
 {
 	const size_t n = ranges.size();
 	for (size_t i = 0; i < n; ++i) paths[i].Clear();
 	handled.assign(n, false);
 	if (scores) scores->assign(n, 0);
-	// two groups: columns that are all A/C/G/T (integer kernels, mcu_nw_batch) and, when `wildcards` is set, ranges with N / X columns
-	// small enough for mcu_nw_batch_wild (the reference's float arithmetic, one thread per range)
+	// two groups: columns that are all A/C/G/T (integer wavefront kernels, mcu_nw_batch) and ranges with N / X columns (float wavefront
+	// kernel with the reference's arithmetic, mcu_nw_batch_wild; `wildcards` = false leaves those to the caller)
 	struct Group {
 		std::string a, b;
 		std::vector<uint64_t> a_off, b_off, p_off;
@@ -115,7 +134,8 @@ inline void CudaGlobalAlignBatch(const std::vector<CudaDPRange>& ranges, PWPath*
 		if (!cuda_detail::ProfileToStringWild(ranges[i].PA, ranges[i].uLengthA, sa, &wa) || !cuda_detail::ProfileToStringWild(ranges[i].PB, ranges[i].uLengthB, sb, &wb))
 			continue;
 		const int k = (wa || wb) ? 1 : 0;
-		if (k == 1 && (!wildcards || (unsigned long long)sa.size() * sb.size() > cuda_detail::kWildMaxCells)) continue;
+		if (k == 1 && !wildcards) continue;
+		if (!cuda_detail::DefaultScoring(ranges[i].PA, ranges[i].uLengthA) || !cuda_detail::DefaultScoring(ranges[i].PB, ranges[i].uLengthB)) continue;
 		g[k].a += sa; g[k].b += sb;
 		g[k].a_off.push_back(g[k].a.size()); g[k].b_off.push_back(g[k].b.size()); g[k].p_off.push_back(g[k].p_off.back() + sa.size() + sb.size());
 		g[k].index.push_back(i);

@@ -133,7 +133,7 @@ void AnchoredProfileProfile(MSA& msa1, MSA& msa2, MSA& msaOut)
 	if (!dp.empty()) {
 		try {
 			// MAUVE_CUDA_WILD=1: ranges with N / X columns go to mcu_nw_batch_wild instead of the reference's NWSmall
-			static const bool wild = getenv("MAUVE_CUDA_WILD") && getenv("MAUVE_CUDA_WILD")[0] == '1';
+			static const bool wild = !(getenv("MAUVE_CUDA_WILD") && getenv("MAUVE_CUDA_WILD")[0] == '0');
 			CudaGlobalAlignBatch(dp, paths, handled, NULL, wild);
 		} catch (std::exception& e) {
 			// MuscleInterface::ProfileAlignFast swallows every exception (LM/MuscleInterface.cpp:1155-1159) and the aligner would go on

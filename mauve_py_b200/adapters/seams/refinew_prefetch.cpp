@@ -103,7 +103,7 @@ void RefineW(const MSA& msaIn, MSA& msaOut)
 		const unsigned uWindowCount = (uColCount + g_uRefineWindow.get() - 1) / g_uRefineWindow.get();
 		const unsigned uWindowTo = 0 == g_uWindowTo.get() ? uWindowCount - 1 : g_uWindowTo.get();
 		// group 0: all letters A/C/G/T (mcu_nw_batch); group 1 (MAUVE_CUDA_WILD=1): windows with wildcard letters (mcu_nw_batch_wild)
-		static const bool wild = getenv("MAUVE_CUDA_WILD") && getenv("MAUVE_CUDA_WILD")[0] == '1';
+		static const bool wild = !(getenv("MAUVE_CUDA_WILD") && getenv("MAUVE_CUDA_WILD")[0] == '0');
 		struct Group {
 			std::vector<std::string> keys;
 			std::string a, b;
@@ -119,7 +119,6 @@ void RefineW(const MSA& msaIn, MSA& msaOut)
 			bool has_wildcard = false;
 			if (!WindowLetters(msaIn, 0, uColFrom, uColTo, s0, wild, &has_wildcard) || !WindowLetters(msaIn, 1, uColFrom, uColTo, s1, wild, &has_wildcard)) continue;
 			if (s0.empty() || s1.empty()) continue;   // MUSCLE() is not called for a window with one empty row (MU/refinew.cpp:141-142)
-			if (has_wildcard && (unsigned long long)s0.size() * s1.size() > cuda_detail::kWildMaxCells) continue;
 			Group& g = grp[has_wildcard ? 1 : 0];
 			for (int order = 0; order < 2; ++order) {   // the guide tree decides which sequence is operand A: both orders are prepared
 				const std::string& x = order ? s1 : s0;

@@ -860,56 +860,51 @@ __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, 
     }
 }
 
-// ---- final buckets, second version: TMA-fed, atomic-free grouping ---------------------------------------------------------
-// bk_group_kernel above ranks every record with a returning shared-memory atomic (counting split) and then lets every genome-0
-// record scan its sub-group: ncu (profiles/r01_ncu_bucket_enumeration_summary.txt) has it issue-bound at 340 thread-instructions
-// per record with 120 M shared-memory bank conflicts.  This version never ranks and never scans:
+// ---- final buckets, TMA-fed version: one open-addressing table per bucket ------------------------------------------------
+// bk_group_kernel above ranks every record with a returning shared-memory atomic (counting split), re-stages the 8-byte
+// records and then lets every genome-0 record scan its sub-group: ncu (profiles/r01_ncu_bucket_enumeration_summary.txt) has it
+// issue-bound at 340 thread-instructions per record with 120 M shared-memory bank conflicts.  This version:
 //   * persistent CTAs; every final bucket (a contiguous run of <= 2048 8-byte records, 16 KB-aligned in the fixed-capacity
 //     layout) is brought into shared memory by ONE bulk asynchronous copy (cp.async.bulk + mbarrier complete_tx), double
-//     buffered: bucket k+1 is in flight while bucket k is grouped;
-//   * grouping = "last writer wins" hash tables, one per genome, plain stores only: every record stores its index at the slot of
-//     its key bits; after a barrier the slot's owner represents the key, a record that finds another record of the SAME key there
-//     marks the owner as duplicated, a record that finds a DIFFERENT key moves on to the next (smaller) table, which is addressed
-//     by other key bits -- with <= 22 distinguishing key bits two rounds separate all keys, four rounds cover 38 bits;
-//   * a key is a seed pair iff its genome-0 representative and its genome-1 representative exist and neither is duplicated:
-//     one probe chain per genome-0 representative.
-// Buckets that cannot be finished this way (a record left over after four rounds, or >= 999 duplicate losers: a mer with more
-// than MER_REPEAT_LIMIT copies may be inside, which only the sorted path counts exactly) go to the radix-sort + join path like
-// overfull buckets do.  Output is identical to bk_group_kernel's (pair order inside the lists is unspecified in both).
-constexpr int G2_S1 = 4096, G2_S2 = 1024, G2_S3 = 256, G2_S4 = 256;   // slots per genome and round
-constexpr u32 G2_EMPTY = 0xffffu;
-
-struct G2Smem {
-    u64 raw[2][BK_CAP];                 // TMA destinations (16 KB each)
-    unsigned short t1[2][G2_S1];        // [genome][slot] -> record index; the four tables are contiguous (cleared as one block)
-    unsigned short t2[2][G2_S2];
-    unsigned short t3[2][G2_S3];
-    unsigned short t4[2][G2_S4];
-    unsigned char dup[BK_CAP];          // record i represents a key that has more copies in its genome
-    u64 outp[BK_CAP / 2];               // pairs of this bucket: forward from the front, reverse from the back
-    u64 candp[2][BK_DIRECT];
-    unsigned long long bar[2];          // mbarriers of the two buffers
-    unsigned long long s_base[4];
-    u32 s_np[2], s_nc[2], s_flags, s_losers;
+//     buffered: bucket k+1 is in flight while bucket k is grouped; records are never moved again;
+//   * one table of 32-bit words per bucket, open addressing on the low key bits: word = key bits << 4 | dup1 dup0 seen1 seen0.
+//     A record claims the slot of its key with ONE atomicCAS (all eight of a thread's records in flight together); a record that
+//     finds its key already there ORs its genome's `seen` bit in, and its `dup` bit if `seen` was set already.  Genome-1
+//     records also leave their index at the slot;
+//   * a genome-0 record whose slot reads seen0 | seen1 and nothing else is a seed pair; pairs are classified in registers and
+//     go straight to the global lists (no staging): a warp prefix over packed per-thread counts and one reservation per bucket
+//     and list give every thread its output ranges.
+// Buckets with >= 999 duplicate records (a mer with more than MER_REPEAT_LIMIT copies may be inside, which only the sorted path
+// counts exactly) go to the radix-sort + join path like dirty / overfull buckets do.  Output is identical to bk_group_kernel's
+// (pair order inside the lists is unspecified in both).
+template <int LOGS>
+struct G3Smem {
+    u64 raw[2][BK_CAP];                   // TMA destinations (16 KB each)
+    u32 tab[1 << LOGS];                   // key << 4 | flags; 0 = empty
+    unsigned short idx1[1 << LOGS];       // index of a genome-1 record of the slot's key
+    unsigned long long bar[2];            // mbarriers of the two buffers
+    unsigned long long base[4];           // global reservations: forward pairs, reverse pairs, forward / reverse direct candidates
+    u32 wtot[BK_THREADS / 32][2];         // per-warp totals: [0] forward | reverse << 16, [1] forward direct | reverse direct << 16
+    u32 losers;
 };
-constexpr int G2_TABLE_BYTES = 2 * (G2_S1 + G2_S2 + G2_S3 + G2_S4) * 2;
+constexpr int G3_MAX_KEY_BITS = 28;
 
-__device__ __forceinline__ u32 g2_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void g2_mbar_init(unsigned long long* bar, u32 count)
+__device__ __forceinline__ u32 g3_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g3_mbar_init(unsigned long long* bar, u32 count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g2_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g3_smem_addr(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void g2_mbar_expect_tx(unsigned long long* bar, u32 bytes)
+__device__ __forceinline__ void g3_mbar_expect_tx(unsigned long long* bar, u32 bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g2_smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g3_smem_addr(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void g2_bulk_load(void* dst, const void* src, u32 bytes, unsigned long long* bar)
+__device__ __forceinline__ void g3_bulk_load(void* dst, const void* src, u32 bytes, unsigned long long* bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(g2_smem_addr(dst)), "l"(src),
-                 "r"(bytes), "r"(g2_smem_addr(bar))
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(g3_smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(g3_smem_addr(bar))
                  : "memory");
 }
-__device__ __forceinline__ void g2_mbar_wait(unsigned long long* bar, u32 parity)
+__device__ __forceinline__ void g3_mbar_wait(unsigned long long* bar, u32 parity)
 {
     u32 done = 0;
     while (!done) {
@@ -920,38 +915,57 @@ __device__ __forceinline__ void g2_mbar_wait(unsigned long long* bar, u32 parity
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(g2_smem_addr(bar)), "r"(parity)
+            : "r"(g3_smem_addr(bar)), "r"(parity)
             : "memory");
     }
 }
 
-struct G2Hash {
-    int s1, kb;       // h1 = the top 12 of the kb key bits that differ inside a bucket
-    u64 kmask;
-    __device__ __forceinline__ u64 key(u64 rec, int kshift) const { return (rec >> kshift) & kmask; }
-    __device__ __forceinline__ u32 h1(u64 k) const { return (u32)(k >> s1) & (G2_S1 - 1); }
-    __device__ __forceinline__ u32 h2(u64 k) const { return (u32)k & (G2_S2 - 1); }
-    __device__ __forceinline__ u32 h3(u64 k) const { return (u32)(k >> 10) & (G2_S3 - 1); }
-    __device__ __forceinline__ u32 h4(u64 k) const { return (u32)(k >> 18) & (G2_S4 - 1); }
-};
-
-__global__ void __launch_bounds__(BK_THREADS, 3) bk_group2_kernel(BkGroupArgs a, BkPlan pl)
+// seed pair (p0 | p1 << 32) of two records with the same mer, and where it goes: 0 forward pair, 1 reverse pair,
+// 2 / 3 forward / reverse pair that is certainly a candidate (solid seeds: the base left of the seed differs on the diagonal,
+// or there is no such base).  Branch-free: every lane of a warp classifies a pair of its own.
+__device__ __forceinline__ u32 g3_classify(u64 r, u64 r1, bool aux, int auxshift, u32 posmask, u32 last1, u64& e)
 {
-    extern __shared__ __align__(128) unsigned char g2_raw[];
-    G2Smem& sm = *reinterpret_cast<G2Smem*>(g2_raw);
-    const u32 tid = threadIdx.x, lane = tid & 31;
+    const u32 p0 = (u32)(r >> 2) & posmask, p1 = (u32)(r1 >> 2) & posmask;
+    e = (u64)p0 | ((u64)p1 << 32);
+    const u32 rev = (u32)((r ^ r1) >> 1) & 1u;
+    u32 direct = 0;
+    if (aux) {   // uniform
+        const u32 a0 = (u32)(r >> auxshift), a1 = (u32)(r1 >> auxshift);      // bits 0-1: base before the seed, bits 2-3: base after it
+        const u32 want = rev ? 3u - ((a1 >> 2) & 3u) : a1 & 3u;
+        const bool inside = p0 > 0 && (rev ? p1 < last1 : p1 > 0);            // the left neighbour on the diagonal exists
+        direct = (inside && (a0 & 3u) == want) ? 0u : 2u;
+    }
+    return rev | direct;
+}
+
+template <int LOGS, int CTAS>
+__global__ void __launch_bounds__(BK_THREADS, CTAS) bk_group3_kernel(BkGroupArgs a, BkPlan pl)
+{
+    extern __shared__ __align__(128) unsigned char g3_raw[];
+    typedef G3Smem<LOGS> Smem;
+    Smem& sm = *reinterpret_cast<Smem*>(g3_raw);
+    constexpr u32 SMASK = (1u << LOGS) - 1u;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 nfinal = a.nfinal, stride = gridDim.x;
     const int kshift = pl.kshift;
     const u32 posmask = (u32)((1ull << pl.pbits) - 1);
-    G2Hash H;
-    H.kb = pl.rem1 - pl.d2;
-    H.kmask = H.kb >= 64 ? ~0ull : ((1ull << H.kb) - 1);
-    H.s1 = H.kb > 12 ? H.kb - 12 : 0;
+    const int kb = pl.rem1 - pl.d2;   // <= G3_MAX_KEY_BITS (host)
+    const u32 kmask = (1u << kb) - 1u;
+    const bool aux = pl.aux != 0;
+    const int auxshift = pl.pbits + 2;
+    const u32 last1 = (u32)(pl.npos1 - 1);   // positions fit 32 bits (pairs are p0 | p1 << 32)
 
     if (tid == 0) {
-        g2_mbar_init(&sm.bar[0], 1);
-        g2_mbar_init(&sm.bar[1], 1);
+        g3_mbar_init(&sm.bar[0], 1);
+        g3_mbar_init(&sm.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sm.losers = 0;
+    }
+    {   // the table starts empty; every bucket leaves it empty again
+        uint4* t = reinterpret_cast<uint4*>(sm.tab);
+        for (u32 i = tid; i < (4u << LOGS) / 16; i += BK_THREADS) t[i] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* x = reinterpret_cast<uint4*>(sm.idx1);   // indices are read before they are known to be meaningful: keep them in range
+        for (u32 i = tid; i < (2u << LOGS) / 16; i += BK_THREADS) x[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
 
@@ -967,8 +981,8 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bk_group2_kernel(BkGroupArgs a,
     };
     auto issue = [&](int buf, u64 f, u32 nb) {  // one thread
         const u32 bytes = (nb * 8u + 15u) & ~15u;  // an odd count reads one record of slack inside the bucket's own 16 KB
-        g2_mbar_expect_tx(&sm.bar[buf], bytes);
-        g2_bulk_load(sm.raw[buf], a.recs + f * BK_CAP, bytes, &sm.bar[buf]);
+        g3_mbar_expect_tx(&sm.bar[buf], bytes);
+        g3_bulk_load(sm.raw[buf], a.recs + f * BK_CAP, bytes, &sm.bar[buf]);
     };
 
     u64 f = blockIdx.x;
@@ -986,180 +1000,125 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bk_group2_kernel(BkGroupArgs a,
         bool spill_it = sp0;
         const u32 nb = nb0;
         if (nb && !spill_it) {
-            // ---- clear tables, duplicate flags, counters (overlaps the copy) ----
-            {
-                uint4* t = reinterpret_cast<uint4*>(&sm.t1[0][0]);
-                const uint4 ones = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-                for (u32 i = tid; i < G2_TABLE_BYTES / 16; i += BK_THREADS) t[i] = ones;
-                uint4* d = reinterpret_cast<uint4*>(&sm.dup[0]);
-                if (tid < BK_CAP / 16) d[tid] = make_uint4(0u, 0u, 0u, 0u);
-                if (tid < 2) { sm.s_np[tid] = 0; sm.s_nc[tid] = 0; }
-                if (tid == 2) { sm.s_flags = 0; sm.s_losers = 0; }
-            }
-            g2_mbar_wait(&sm.bar[buf], (parity >> buf) & 1u);
+            g3_mbar_wait(&sm.bar[buf], (parity >> buf) & 1u);
             parity ^= 1u << buf;
             const u64* __restrict__ raw = sm.raw[buf];
             u64 rec[BK_GIPT];
-#pragma unroll
-            for (int it = 0; it < BK_GIPT; ++it) {
-                const u32 i = it * BK_THREADS + tid;
-                rec[it] = i < nb ? raw[i] : 0;
-            }
-            __syncthreads();  // tables are clear
-            // ---- round 1 ----
-#pragma unroll
-            for (int it = 0; it < BK_GIPT; ++it) {
-                const u32 i = it * BK_THREADS + tid;
-                if (i < nb) sm.t1[rec[it] & 1][H.h1(H.key(rec[it], kshift))] = (unsigned short)i;
-            }
-            __syncthreads();
-            u32 pending = 0, winner = 0, losers = 0;
-#pragma unroll
-            for (int it = 0; it < BK_GIPT; ++it) {
-                const u32 i = it * BK_THREADS + tid;
-                if (i < nb) {
-                    const u64 r = rec[it];
-                    const u32 g = (u32)r & 1u;
-                    const u32 w = sm.t1[g][H.h1(H.key(r, kshift))];
-                    if (w == i) winner |= 1u << it;
-                    else if (((raw[w] ^ r) >> kshift) == 0) { sm.dup[w] = 1; ++losers; }
-                    else { pending |= 1u << it; sm.t2[g][H.h2(H.key(r, kshift))] = (unsigned short)i; }
-                }
-            }
-            __syncthreads();
-            // ---- rounds 2..4: only records that met a different key ----
-#pragma unroll
-            for (int round = 2; round <= 4; ++round) {
-                if (pending) {
-#pragma unroll
-                    for (int it = 0; it < BK_GIPT; ++it) {
-                        if (pending & (1u << it)) {
-                            const u32 i = it * BK_THREADS + tid;
-                            const u64 r = rec[it];
-                            const u32 g = (u32)r & 1u;
-                            const u64 key = H.key(r, kshift);
-                            const u32 w = round == 2 ? sm.t2[g][H.h2(key)] : round == 3 ? sm.t3[g][H.h3(key)] : sm.t4[g][H.h4(key)];
-                            if (w == i) { winner |= 1u << it; pending &= ~(1u << it); }
-                            else if (((raw[w] ^ r) >> kshift) == 0) { sm.dup[w] = 1; ++losers; pending &= ~(1u << it); }
-                            else if (round == 2) sm.t3[g][H.h3(key)] = (unsigned short)i;
-                            else if (round == 3) sm.t4[g][H.h4(key)] = (unsigned short)i;
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-            // ---- can this bucket be finished here? ----
+            u32 slot[BK_GIPT];
+            // ---- insert: one CAS per record, all of a thread's records in flight ----
             {
-                u32 l = losers;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-                if (lane == 0 && l) atomicAdd(&sm.s_losers, l);
-                if (__any_sync(0xffffffffu, pending != 0) && lane == 0) atomicOr(&sm.s_flags, 1u);
-            }
-            __syncthreads();
-            spill_it = (sm.s_flags & 1u) || sm.s_losers >= 999u;
-            if (!spill_it) {
-                // ---- pairing: every unduplicated genome-0 representative looks its key up in genome 1's tables ----
+                u32 old[BK_GIPT];
 #pragma unroll
                 for (int it = 0; it < BK_GIPT; ++it) {
-                    const u32 i0 = it * BK_THREADS + tid;
-                    const u64 r = rec[it];
-                    u32 kind = 4;  // 0 forward pair, 1 reverse pair, 2 forward candidate, 3 reverse candidate, 4 nothing
-                    u64 e = 0;
-                    if (((winner >> it) & 1u) && !(r & 1) && !sm.dup[i0]) {
-                        const u64 key = H.key(r, kshift);
-                        u32 w = sm.t1[1][H.h1(key)];
-                        bool found = false;
-                        if (w != G2_EMPTY) {
-                            found = ((raw[w] ^ r) >> kshift) == 0;
-                            if (!found) {
-                                w = sm.t2[1][H.h2(key)];
-                                if (w != G2_EMPTY) {
-                                    found = ((raw[w] ^ r) >> kshift) == 0;
-                                    if (!found) {
-                                        w = sm.t3[1][H.h3(key)];
-                                        if (w != G2_EMPTY) {
-                                            found = ((raw[w] ^ r) >> kshift) == 0;
-                                            if (!found) {
-                                                w = sm.t4[1][H.h4(key)];
-                                                found = w != G2_EMPTY && ((raw[w] ^ r) >> kshift) == 0;
-                                            }
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                        if (found && !sm.dup[w]) {
-                            const u64 r1 = raw[w];
-                            const u32 p0 = (u32)(r >> 2) & posmask, p1 = (u32)(r1 >> 2) & posmask;
-                            e = (u64)p0 | ((u64)p1 << 32);
-                            const u32 rev = (u32)((r ^ r1) >> 1) & 1u;
-                            bool direct = false;
-                            if (pl.aux) {  // solid seed: the left neighbour on the diagonal is a hit iff the one new base agrees
-                                const u32 a0 = (u32)(r >> (pl.pbits + 2)) & 15u, a1 = (u32)(r1 >> (pl.pbits + 2)) & 15u;
-                                bool agree;
-                                if (!rev) agree = p0 > 0 && p1 > 0 && (a0 & 3u) == (a1 & 3u);
-                                else agree = p0 > 0 && (u64)p1 + 1 < pl.npos1 && (a0 & 3u) == 3u - (a1 >> 2);
-                                direct = !agree;
-                            }
-                            kind = rev | (direct ? 2u : 0u);
-                        }
-                    }
-                    // one shared-memory reservation per warp and kind
+                    const u32 i = it * BK_THREADS + tid;
+                    rec[it] = i < nb ? raw[i] : 0;
+                    const u32 kk = (u32)(rec[it] >> kshift) & kmask;
+                    slot[it] = kk & SMASK;
+                    old[it] = 0;
+                    if (i < nb) old[it] = atomicCAS(&sm.tab[slot[it]], 0u, (kk << 4) | (1u << ((u32)rec[it] & 1u)));
+                }
+                u32 losers = 0;
 #pragma unroll
-                    for (u32 q = 0; q < 4; ++q) {
-                        const u32 m = __ballot_sync(0xffffffffu, kind == q);
-                        if (m) {
-                            u32 base = 0;
-                            if (lane == (u32)(__ffs(m) - 1)) base = atomicAdd(q < 2 ? &sm.s_np[q] : &sm.s_nc[q - 2], (u32)__popc(m));
-                            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-                            if (kind == q) {
-                                const u32 slot = base + __popc(m & lanemask_lt());
-                                if (q == 0) sm.outp[slot] = e;
-                                else if (q == 1) sm.outp[BK_CAP / 2 - 1 - slot] = e;
-                                else {
-                                    if (slot < BK_DIRECT) sm.candp[q - 2][slot] = e;
-                                    else if (q == 2) a.cand[atomicAdd(&a.counters[2], 1ull)] = e;   // overflow of the small buffer: rare
-                                    else a.cand[a.cand_cap - 1 - atomicAdd(&a.counters[7], 1ull)] = e;
-                                    atomicOr(&a.uniq[(u32)e >> 5], 1u << ((u32)e & 31));
-                                }
-                            }
+                for (int it = 0; it < BK_GIPT; ++it) {
+                    const u32 i = it * BK_THREADS + tid;
+                    if (i < nb) {
+                        const u32 g = (u32)rec[it] & 1u;
+                        const u32 val = (((u32)(rec[it] >> kshift) & kmask) << 4) | (1u << g);
+                        u32 o = old[it], s = slot[it];
+                        while (o != 0 && ((o ^ val) >> 4) != 0) {   // another key lives here: next slot
+                            s = (s + 1) & SMASK;
+                            o = atomicCAS(&sm.tab[s], 0u, val);
                         }
+                        if (o != 0) {   // the key was there already
+                            const u32 bit = 1u << g;
+                            if ((o & bit) || (atomicOr(&sm.tab[s], bit) & bit)) { atomicOr(&sm.tab[s], bit << 2); ++losers; }
+                        }
+                        if (g) sm.idx1[s] = (unsigned short)i;
+                        slot[it] = s;
                     }
                 }
-                __syncthreads();
-                const u32 nf = sm.s_np[0], nr = sm.s_np[1];
-                const u32 ncf = min(sm.s_nc[0], (u32)BK_DIRECT), ncr = min(sm.s_nc[1], (u32)BK_DIRECT);
+                if (losers) atomicAdd(&sm.losers, losers);
+            }
+            __syncthreads();
+            spill_it = sm.losers >= 999u;
+            // ---- pairing: a genome-0 record whose key was seen once in each genome ----
+            u64 e[BK_GIPT];
+            u32 kinds = 0;            // 4 bits per record: 0 forward, 1 reverse, 2 forward direct, 3 reverse direct, 4 nothing
+            u32 cA = 0, cB = 0;       // forward | reverse << 16, forward direct | reverse direct << 16
+#pragma unroll
+            for (int it = 0; it < BK_GIPT; ++it) {
+                const u32 i = it * BK_THREADS + tid;
+                u32 kind = 4;
+                e[it] = 0;
+                if (i < nb && !spill_it) {   // uniform except in the bucket's last round
+                    const u32 s = slot[it];
+                    const u64 r1 = raw[sm.idx1[s]];   // a stale index for a key without genome-1 record: any record of the bucket, unused
+                    const u32 k = g3_classify(rec[it], r1, aux, auxshift, posmask, last1, e[it]);
+                    if ((sm.tab[s] & 15u) == 3u && !((u32)rec[it] & 1u)) {
+                        kind = k;
+                        const u32 inc = 1u << ((k & 1u) << 4);
+                        cA += k < 2 ? inc : 0u;
+                        cB += k < 2 ? 0u : inc;
+                    }
+                }
+                kinds |= kind << (4 * it);
+            }
+            // warp prefix of the packed counts
+            u32 iA = cA, iB = cB;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 tA = __shfl_up_sync(0xffffffffu, iA, o), tB = __shfl_up_sync(0xffffffffu, iB, o);
+                if (lane >= (u32)o) { iA += tA; iB += tB; }
+            }
+            if (lane == 31) { sm.wtot[warp][0] = iA; sm.wtot[warp][1] = iB; }
+            __syncthreads();   // every read of the table is done
+            {   // ---- empty the table for the next bucket (the reservation below is in flight meanwhile) ----
+                uint4* t = reinterpret_cast<uint4*>(sm.tab);
+#pragma unroll
+                for (u32 i = tid; i < (4u << LOGS) / 16; i += BK_THREADS) t[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (tid == 0) sm.losers = 0;
+            }
+            if (!spill_it) {
+                u32 bA = 0, bB = 0, tA = 0, tB = 0;
+#pragma unroll
+                for (u32 w = 0; w < BK_THREADS / 32; ++w) {
+                    const u32 xA = sm.wtot[w][0], xB = sm.wtot[w][1];
+                    if (w < warp) { bA += xA; bB += xB; }
+                    tA += xA; tB += xB;
+                }
                 if (tid == 0) {
-                    sm.s_base[0] = nf ? atomicAdd(&a.counters[0], (unsigned long long)nf) : 0ull;
-                    sm.s_base[1] = nr ? atomicAdd(&a.counters[6], (unsigned long long)nr) : 0ull;
-                    sm.s_base[2] = ncf ? atomicAdd(&a.counters[2], (unsigned long long)ncf) : 0ull;
-                    sm.s_base[3] = ncr ? atomicAdd(&a.counters[7], (unsigned long long)ncr) : 0ull;
-                    if (sm.s_nc[0] + sm.s_nc[1]) atomicAdd(&a.spill[3], (unsigned long long)(sm.s_nc[0] + sm.s_nc[1]));
+                    const u32 nf = tA & 0xffffu, nr = tA >> 16, ncf = tB & 0xffffu, ncr = tB >> 16;
+                    sm.base[0] = nf ? atomicAdd(&a.counters[0], (unsigned long long)nf) : 0ull;
+                    sm.base[1] = nr ? atomicAdd(&a.counters[6], (unsigned long long)nr) : 0ull;
+                    sm.base[2] = ncf ? atomicAdd(&a.counters[2], (unsigned long long)ncf) : 0ull;
+                    sm.base[3] = ncr ? atomicAdd(&a.counters[7], (unsigned long long)ncr) : 0ull;
+                    if (ncf + ncr) atomicAdd(&a.spill[3], (unsigned long long)(ncf + ncr));
                 }
                 __syncthreads();
-                if (tid < ncf) a.cand[sm.s_base[2] + tid] = sm.candp[0][tid];
-                if (tid < ncr) a.cand[a.cand_cap - 1 - (sm.s_base[3] + tid)] = sm.candp[1][tid];
-                const u64 bf = sm.s_base[0], br2 = sm.s_base[1];
-                for (u32 j = tid; j < nf; j += BK_THREADS) {
-                    const u64 e = sm.outp[j];
-                    const u32 p0 = (u32)e;
-                    atomicOr(&a.uniq[p0 >> 5], 1u << (p0 & 31));
-                    a.pairs[bf + j] = e;
-                }
-                for (u32 j = tid; j < nr; j += BK_THREADS) {
-                    const u64 e = sm.outp[BK_CAP / 2 - 1 - j];
-                    const u32 p0 = (u32)e;
-                    atomicOr(&a.uniq[p0 >> 5], 1u << (p0 & 31));
-                    a.pairs[a.pair_cap - 1 - (br2 + j)] = e;
+                bA += iA - cA;
+                bB += iB - cB;
+                // running pointers of this thread's four output ranges (reverse lists grow downwards from the end of the arrays)
+                u64* q0 = a.pairs + (sm.base[0] + (bA & 0xffffu));
+                u64* q1 = a.pairs + (a.pair_cap - 1 - (sm.base[1] + (bA >> 16)));
+                u64* q2 = a.cand + (sm.base[2] + (bB & 0xffffu));
+                u64* q3 = a.cand + (a.cand_cap - 1 - (sm.base[3] + (bB >> 16)));
+#pragma unroll
+                for (int it = 0; it < BK_GIPT; ++it) {
+                    const u32 kind = (kinds >> (4 * it)) & 15u;
+                    const u64 ee = e[it];
+                    if (kind == 0) *q0++ = ee;
+                    if (kind == 1) *q1-- = ee;
+                    if (kind == 2) *q2++ = ee;
+                    if (kind == 3) *q3-- = ee;
+                    if (kind < 4) atomicOr(&a.uniq[(u32)ee >> 5], 1u << ((u32)ee & 31));
                 }
             }
         }
-        if (spill_it && nb && tid == 0) {
+        if (spill_it && tid == 0) {
             a.spill_list[atomicAdd(&a.spill[0], 1ull)] = (u32)f;
             atomicAdd(&a.spill[1], (unsigned long long)nb);
         }
-        __syncthreads();  // every read of raw[buf], the tables and the staging lists is done: the next rounds may overwrite them
+        __syncthreads();  // every read of raw[buf] and of the reservations is done, the table is empty: the next round may begin
         nb0 = nb1; sp0 = sp1;
         nb1 = nb2; sp1 = sp2;
     }
@@ -1321,16 +1280,27 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     ga.counters = ctr; ga.spill_list = s.bk_spill.as<u32>(); ga.spill = spill;
     ga.cand = s.cand.as<u64>(); ga.cand_cap = pair_cap;
     ga.cnt2 = cursor2; ga.dirty = dirty; ga.nfinal = nfinal;
-    static const bool group_v1 = getenv("MAUVE_CUDA_GROUP_V1") != nullptr;
+    // bk_group3 keeps <= 28 key bits that differ inside a final bucket next to four flag bits; wider keys (not reached by the seed
+    // tables at sizes that take this path) keep bk_group.  MAUVE_CUDA_GROUP_V1 / MAUVE_CUDA_GROUP_S11: A/B switches.
+    static const bool group_v1_env = getenv("MAUVE_CUDA_GROUP_V1") != nullptr;
+    static const bool group_s11 = getenv("MAUVE_CUDA_GROUP_S11") != nullptr;
+    const bool group_v1 = group_v1_env || pl.rem1 - pl.d2 > G3_MAX_KEY_BITS;
     if (nfinal && group_v1) bk_group_kernel<<<(unsigned)nfinal, BK_THREADS, 0, st>>>(ga, pl);
     else if (nfinal) {
-        static bool attr2_done = false;
-        if (!attr2_done) {
-            MCU_CUDA(cudaFuncSetAttribute(bk_group2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G2Smem)));
-            attr2_done = true;
+        static bool attr3_done = false;
+        if (!attr3_done) {
+            MCU_CUDA(cudaFuncSetAttribute(bk_group3_kernel<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G3Smem<12>)));
+            MCU_CUDA(cudaFuncSetAttribute(bk_group3_kernel<11, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G3Smem<11>)));
+            attr3_done = true;
         }
-        const u64 want = (u64)sm_count() * 3;  // persistent: as many CTAs as fit (3 per SM), each walks the buckets with stride gridDim.x
-        bk_group2_kernel<<<(unsigned)(nfinal < want ? nfinal : want), BK_THREADS, sizeof(G2Smem), st>>>(ga, pl);
+        // persistent: as many CTAs as fit, each walks the buckets with stride gridDim.x
+        if (group_s11) {
+            const u64 want = (u64)sm_count() * 4;
+            bk_group3_kernel<11, 4><<<(unsigned)(nfinal < want ? nfinal : want), BK_THREADS, sizeof(G3Smem<11>), st>>>(ga, pl);
+        } else {
+            const u64 want = (u64)sm_count() * 3;
+            bk_group3_kernel<12, 3><<<(unsigned)(nfinal < want ? nfinal : want), BK_THREADS, sizeof(G3Smem<12>), st>>>(ga, pl);
+        }
     }
     MCU_CUDA(cudaEventRecord(s.kev[5], st));
     s.launches += 3;

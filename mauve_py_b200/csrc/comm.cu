@@ -13,7 +13,8 @@
 //   ncclSend/Recv   one group: the rows go to rank 0 (the "NCCL gather" of the north star)
 //   merge           rank 0: reference list order + exact replay of order-dependent hash buckets (replay.cu)
 // Host synchronisations are the ones a single-GPU step has (counter read-backs that size the next launch) plus one for the counts.
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is opened at run time (see load_nccl)
 
 #include <mutex>
 #include <new>
@@ -32,11 +33,60 @@ struct Comm {
 };
 static Comm g_comm;
 
+// NCCL is bound with dlopen when the first communicator call is made, not at link time: libmauve_cuda.so must stay loadable in a
+// process that brings its own libnccl.so.2 (PyTorch bundles a newer one than the system's; two different libnccl.so.2 cannot share
+// a process, and whichever is mapped first wins the soname).  Order: $MAUVE_CUDA_NCCL_LIB, a copy that is already mapped, the
+// system's libnccl.so.2.
+struct NcclApi {
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl()
+{
+    if (g_nccl.handle) return MCU_OK;
+    void* h = nullptr;
+    if (const char* e = getenv("MAUVE_CUDA_NCCL_LIB")) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { set_error("cannot load libnccl.so.2 (%s); set MAUVE_CUDA_NCCL_LIB", dlerror()); return MCU_ENODEV; }
+    NcclApi a;
+    a.handle = h;
+#define MCU_SYM(field, name)                                                           \
+    a.field = (decltype(a.field))dlsym(h, name);                                      \
+    if (!a.field) { set_error("libnccl.so.2 has no %s", name); return MCU_ENODEV; }
+    MCU_SYM(GetUniqueId, "ncclGetUniqueId")
+    MCU_SYM(CommInitRank, "ncclCommInitRank")
+    MCU_SYM(CommDestroy, "ncclCommDestroy")
+    MCU_SYM(GetErrorString, "ncclGetErrorString")
+    MCU_SYM(AllReduce, "ncclAllReduce")
+    MCU_SYM(AllGather, "ncclAllGather")
+    MCU_SYM(Send, "ncclSend")
+    MCU_SYM(Recv, "ncclRecv")
+    MCU_SYM(GroupStart, "ncclGroupStart")
+    MCU_SYM(GroupEnd, "ncclGroupEnd")
+    MCU_SYM(GetVersion, "ncclGetVersion")
+#undef MCU_SYM
+    g_nccl = a;
+    return MCU_OK;
+}
+
 #define MCU_NCCL(call)                                                                              \
     do {                                                                                            \
         ncclResult_t r__ = (call);                                                                  \
         if (r__ != ncclSuccess) {                                                                   \
-            mcu::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__)); \
+            mcu::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__)); \
             return MCU_ECUDA;                                                                       \
         }                                                                                           \
     } while (0)
@@ -53,7 +103,7 @@ static int allgather_packed(Session& s)
     for (int g = 0; g < 2; ++g) {
         const u64 chunk = pack_chunk_words(s.n[g], s.pack_world);
         u32* base = s.packed[g].as<u32>();
-        MCU_NCCL(ncclAllGather(base + chunk * (u64)s.pack_rank, base, chunk, ncclUint32, g_comm.comm, s.stream));
+        MCU_NCCL(g_nccl.AllGather(base + chunk * (u64)s.pack_rank, base, chunk, ncclUint32, g_comm.comm, s.stream));
     }
     return MCU_OK;
 }
@@ -79,7 +129,7 @@ static int run_sharded(Session& s, u64 seed, float* stage_ms, u64* stats)
     MCU_TRY(r);
 
     // ---- unique-seed bitmaps of all ranks ----
-    MCU_NCCL(ncclAllReduce(s.uniq.p, s.uniq.p, s.run.uniq_words, ncclUint32, ncclSum, c.comm, s.stream));
+    MCU_NCCL(g_nccl.AllReduce(s.uniq.p, s.uniq.p, s.run.uniq_words, ncclUint32, ncclSum, c.comm, s.stream));
 
     // ---- candidates + extension of this rank's pairs ----
     float st[16];
@@ -95,7 +145,7 @@ static int run_sharded(Session& s, u64 seed, float* stage_ms, u64* stats)
     h_send[0] = nmine; h_send[1] = mine[0]; h_send[2] = mine[4]; h_send[3] = mine[5]; h_send[4] = mine[3];
     h_send[5] = s.gap_seen ? 1 : 0; h_send[6] = 0; h_send[7] = 0;
     MCU_CUDA(cudaMemcpyAsync(d_send, h_send, 64, cudaMemcpyHostToDevice, s.stream));
-    MCU_NCCL(ncclAllGather(d_send, d_all, 8, ncclUint64, c.comm, s.stream));
+    MCU_NCCL(g_nccl.AllGather(d_send, d_all, 8, ncclUint64, c.comm, s.stream));
     MCU_CUDA(cudaMemcpyAsync(h_all, d_all, (size_t)W * 64, cudaMemcpyDeviceToHost, s.stream));
     MCU_CUDA(cudaStreamSynchronize(s.stream));
     u64 total = 0, pairs = 0, cands = 0, recs = 0, repeat = 0, gap = 0;
@@ -107,17 +157,17 @@ static int run_sharded(Session& s, u64 seed, float* stage_ms, u64* stats)
 
     // ---- rows to rank 0 ----
     if (c.rank == 0) MCU_TRY(s.gathered.reserve((total + 1) * sizeof(mcu_match)));
-    MCU_NCCL(ncclGroupStart());
+    MCU_NCCL(g_nccl.GroupStart());
     if (c.rank == 0) {
         u64 off = h_all[0];
         for (int k = 1; k < W; ++k) {
             const u64 cnt = h_all[8 * k];
-            if (cnt) MCU_NCCL(ncclRecv(s.gathered.as<mcu_match>() + off, cnt * 3, ncclInt64, k, c.comm, s.stream));
+            if (cnt) MCU_NCCL(g_nccl.Recv(s.gathered.as<mcu_match>() + off, cnt * 3, ncclInt64, k, c.comm, s.stream));
             off += cnt;
         }
     } else if (nmine)
-        MCU_NCCL(ncclSend(s.matches.p, nmine * 3, ncclInt64, 0, c.comm, s.stream));
-    MCU_NCCL(ncclGroupEnd());
+        MCU_NCCL(g_nccl.Send(s.matches.p, nmine * 3, ncclInt64, 0, c.comm, s.stream));
+    MCU_NCCL(g_nccl.GroupEnd());
 
     // ---- merge on rank 0 ----
     u64 unclean = 0, dups = 0;
@@ -149,9 +199,10 @@ extern "C" {
 int mcu_comm_unique_id(void* id_out)
 {
     if (!id_out) return MCU_EINVAL;
+    MCU_TRY(load_nccl());
     static_assert(sizeof(ncclUniqueId) == MCU_COMM_ID_BYTES, "ncclUniqueId size");
     ncclUniqueId id;
-    MCU_NCCL(ncclGetUniqueId(&id));
+    MCU_NCCL(g_nccl.GetUniqueId(&id));
     memcpy(id_out, &id, sizeof id);
     return MCU_OK;
 }
@@ -164,9 +215,10 @@ int mcu_comm_init(int rank, int world, const void* id)
     g_comm.rank = rank;
     g_comm.world = world;
     if (world > 1) {
+        MCU_TRY(load_nccl());
         ncclUniqueId uid;
         memcpy(&uid, id, sizeof uid);
-        MCU_NCCL(ncclCommInitRank(&g_comm.comm, world, uid, rank));
+        MCU_NCCL(g_nccl.CommInitRank(&g_comm.comm, world, uid, rank));
         MCU_CUDA(cudaStreamCreateWithFlags(&g_comm.stream, cudaStreamNonBlocking));
     }
     g_comm.ok = true;
@@ -178,7 +230,7 @@ void mcu_comm_destroy(void)
     if (!g_comm.ok) return;
     if (g_comm.comm) {
         if (g_comm.stream) cudaStreamSynchronize(g_comm.stream);
-        ncclCommDestroy(g_comm.comm);
+        g_nccl.CommDestroy(g_comm.comm);
         g_comm.comm = nullptr;
     }
     if (g_comm.stream) { cudaStreamDestroy(g_comm.stream); g_comm.stream = nullptr; }
@@ -206,7 +258,7 @@ int mcu_comm_allreduce_f64(double* v, int n, int op)
     const ncclRedOp_t ops[3] = {ncclSum, ncclMax, ncclMin};
     MCU_TRY(g_comm.scratch.reserve((size_t)n * sizeof(double)));
     MCU_CUDA(cudaMemcpyAsync(g_comm.scratch.p, v, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g_comm.stream));
-    MCU_NCCL(ncclAllReduce(g_comm.scratch.p, g_comm.scratch.p, (size_t)n, ncclDouble, ops[op], g_comm.comm, g_comm.stream));
+    MCU_NCCL(g_nccl.AllReduce(g_comm.scratch.p, g_comm.scratch.p, (size_t)n, ncclDouble, ops[op], g_comm.comm, g_comm.stream));
     MCU_CUDA(cudaMemcpyAsync(v, g_comm.scratch.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, g_comm.stream));
     MCU_CUDA(cudaStreamSynchronize(g_comm.stream));
     return MCU_OK;
@@ -242,7 +294,7 @@ int mcu_comm_gather_bytes(const void* send, uint64_t n, void** out, uint64_t* co
     unsigned long long* d = g_comm.scratch.as<unsigned long long>();
     unsigned long long mine = n;
     MCU_CUDA(cudaMemcpyAsync(d, &mine, 8, cudaMemcpyHostToDevice, st));
-    MCU_NCCL(ncclAllGather(d, d + 1, 1, ncclUint64, g_comm.comm, st));
+    MCU_NCCL(g_nccl.AllGather(d, d + 1, 1, ncclUint64, g_comm.comm, st));
     MCU_CUDA(cudaMemcpyAsync(cnt.data(), d + 1, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
     MCU_CUDA(cudaStreamSynchronize(st));
     u64 total = 0;
@@ -254,16 +306,16 @@ int mcu_comm_gather_bytes(const void* send, uint64_t n, void** out, uint64_t* co
     MCU_TRY(stage.reserve((rank == 0 ? total : n) + 16));
     u64 off0 = 0;
     if (n) MCU_CUDA(cudaMemcpyAsync(stage.p, send, n, cudaMemcpyHostToDevice, st));
-    MCU_NCCL(ncclGroupStart());
+    MCU_NCCL(g_nccl.GroupStart());
     if (rank == 0) {
         u64 off = cnt[0];
         for (int k = 1; k < W; ++k) {
-            if (cnt[k]) MCU_NCCL(ncclRecv(stage.as<char>() + off, cnt[k], ncclUint8, k, g_comm.comm, st));
+            if (cnt[k]) MCU_NCCL(g_nccl.Recv(stage.as<char>() + off, cnt[k], ncclUint8, k, g_comm.comm, st));
             off += cnt[k];
         }
     } else if (n)
-        MCU_NCCL(ncclSend(stage.as<char>() + off0, n, ncclUint8, 0, g_comm.comm, st));
-    MCU_NCCL(ncclGroupEnd());
+        MCU_NCCL(g_nccl.Send(stage.as<char>() + off0, n, ncclUint8, 0, g_comm.comm, st));
+    MCU_NCCL(g_nccl.GroupEnd());
     int rc = MCU_OK;
     if (rank == 0) {
         void* r = malloc(total ? total : 1);

@@ -83,25 +83,33 @@ __device__ __forceinline__ u32 nw_rows(const u32 (&asel)[NW_R], int (&Ml)[NW_R],
 {
     u32 tbw = 0;
     int best = 0;
+    // Gap states are carried with a +400 bias (D'' = D' + 400, I'' = I' + 400) and M is carried unbiased, so neither gap recurrence
+    // needs an add and best = max(max(D'', I'') - 400, M) is one fused add+max.  Every comparison below has the same constant on both
+    // sides as the unbiased form (experiments/check_dp_biased_recurrence.py).
+    // traceback nibble of row r: bit0 = best > M (= max(D', I') > M), bit1 = I'' > D'' (state of best: x = bit0 + (bit0 & bit1)),
+    // bit2 = D'' came from M (not DD > MD), bit3 = I'' came from M (MI >= II).  One setp + one predicated or per bit.
+#define NW_TB_BIT(cmp, lhs, rhs, bit) \
+    asm("{\n\t.reg .pred p;\n\tsetp." cmp ".s32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(tbw) : "r"(lhs), "r"(rhs), "r"(bit))
 #pragma unroll
     for (int r = 0; r < NW_R; ++r) {
         const int M = (int)__byte_perm(sb, 0u, asel[r]) + dg - 65;
-        const bool keepD = upD > upM;           // DD > MD: stay in D, else (ties too) come from M
-        const int D = max(upD, upM);
-        const bool fromMI = Ml[r] >= Il[r];     // MI >= II: come from M
-        const int I = max(Ml[r], Il[r]);
-        best = max(M, max(D, I));
-        const u32 x = (M == best) ? 0u : ((D == best) ? 1u : 2u);
-        const u32 nib = x | (keepD ? 0u : 4u) | (fromMI ? 8u : 0u);
-        tbw |= nib << (4 * r);
+        const int D = max(upD, upM);            // DD > MD: stay in D, else (ties too) come from M
+        const int I = max(Ml[r], Il[r]);        // MI >= II: come from M
+        const int DI = max(D, I);
+        best = max(DI - 400, M);
+        NW_TB_BIT("gt", best, M, 1u << (4 * r));
+        NW_TB_BIT("gt", I, D, 2u << (4 * r));
+        NW_TB_BIT("ge", upM, upD, 4u << (4 * r));
+        NW_TB_BIT("ge", Ml[r], Il[r], 8u << (4 * r));
         if (CAP && r == cap_r) { capM = M; capD = D; capI = I; }
         dg = Bp[r];
         Bp[r] = best;
-        upM = M - 400;
-        Ml[r] = upM;
+        upM = M;
+        Ml[r] = M;
         Il[r] = I;
         upD = D;
     }
+#undef NW_TB_BIT
     out_best = best;
     return tbw;
 }
@@ -137,8 +145,8 @@ __device__ __forceinline__ void nw_region(const NwProblem& P, u32 rank, u32 team
             u32 c = 0;
             if (i0 + r < la) c = dna_code(P.A[i0 + r], bad);
             asel[r] = 0x4440u | c;
-            Ml[r] = NW_NINF;   // M[i][0] - 400
-            Il[r] = NW_NINF;   // I'[i][0]
+            Ml[r] = NW_NINF;   // M[i][0]
+            Il[r] = NW_NINF;   // I''[i][0]
             Bp[r] = -200;      // best[i][0]
         }
         int diag = -200, out_M = NW_NINF, out_D = NW_NINF, out_B = -200;
@@ -220,7 +228,7 @@ __device__ __forceinline__ void nw_region(const NwProblem& P, u32 rank, u32 team
         __threadfence_block();
         __syncwarp();
     }
-    if ((nstripes - 1) % team == rank && lane == fin_lane) *P.result = make_int4(capM, capD + 200, capI + 200, 0);
+    if ((nstripes - 1) % team == rank && lane == fin_lane) *P.result = make_int4(capM, capD - 200, capI - 200, 0);   // D = D'' - 200, I = I'' - 200
     __syncwarp();
 }
 
@@ -316,7 +324,8 @@ __global__ void __launch_bounds__(128) nw_traceback_kernel(TbArgs g)
         char next;
         if (edge == 'M') {
             if (pa >= 2 && pb >= 2) {
-                u32 x = nw_nibble(tb, T, pa - 1, pb - 1) & 3u;
+                const u32 nb = nw_nibble(tb, T, pa - 1, pb - 1);
+                const u32 x = (nb & 1u) + (nb & (nb >> 1) & 1u);   // bit0 = not M; bit1 = I beats D
                 next = x == 0 ? 'M' : (x == 1 ? 'D' : 'I');
             } else if (pa >= 2) next = 'D';   // first column: reached through a leading gap in B (nwsmall.cpp:586-592)
             else next = 'I';                  // first row

@@ -56,7 +56,7 @@ def test_bench_main_line_dry_run():
         assert k in rf, k
     assert rf["bound"] == "hbm" and rf["achieved"] > 0 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
     assert rf["traffic"] is None   # the ncu capture describes the 100 Mbp launch only
-    assert set(rf["other_kernels"]) == {"bkf_scatter1_kernel", "bkf_scatter2_kernel", "bk_group2_kernel"} and rf["step"]["frac"] > 0
+    assert set(rf["other_kernels"]) == {"bkf_scatter1_kernel", "bkf_scatter2_kernel", "bk_group3_kernel"} and rf["step"]["frac"] > 0
     assert "torch" not in sys.modules or True   # bench.py itself imports no torch (checked below on the source)
     assert "import torch" not in open(os.path.join(ROOT, "bench.py")).read()
     assert line["parity"]["rows"] == line["matches"] and len(line["parity"]["rows_sha1"]) == 40 and line["parity"]["e2e_rows_identical_to_resident_rows"]
