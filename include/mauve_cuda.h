@@ -222,9 +222,11 @@ void mcu_nw_last_stats(uint64_t* out5);
 /* The same call for regions whose sequences contain DNA wildcards (N X M R W S Y K V H D B, either case): there
  * NWSmall's scores are not integers, and the path is reproduced by executing the reference's float operations in the reference's
  * order (MSA::GetFractionalWeightedCounts MU/msa2.cpp:20-90 incl. its treatment of 'X', ProfileFromMSA MU/profilefrommsa.cpp:246-322,
- * ScoreProfPos2SPN MU/scorepp.cpp:80-92, NWSmall, BitTraceBack), one thread per region.  Meant for the few ranges mcu_nw_batch
- * refuses with MCU_EALPHA; pure ACGT regions give the same paths here, only slower.  score: max(MAB, DAB, IAB) as the reference's
- * float.  A region may have at most 2^24 cells (MCU_EINVAL beyond); a byte that is no DNA letter or wildcard gives MCU_EALPHA.   */
+ * ScoreProfPos2SPN MU/scorepp.cpp:80-92, NWSmall, BitTraceBack) as a float32 wavefront: a warp per region, the cell update of
+ * NWSmall in round-to-nearest operations without contraction, 4 traceback bits per cell.  Meant for the ranges mcu_nw_batch refuses
+ * with MCU_EALPHA; pure ACGT regions give the same paths here, only slower.  score: max(MAB, DAB, IAB) as the reference's float.
+ * Sequences of up to 2^26 - 1 letters each (MCU_EINVAL beyond; MCU_ENOMEM when one region's traceback does not fit the device);
+ * a byte that is no DNA letter or wildcard gives MCU_EALPHA.   */
 int mcu_nw_batch_wild(uint64_t n, const char* a, const uint64_t* a_off, const char* b, const uint64_t* b_off,
                       const uint64_t* path_off, char* path_out, uint32_t* path_len, float* score, float* device_ms);
 

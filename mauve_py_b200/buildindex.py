@@ -181,7 +181,9 @@ def runMauve(fasta_files, flags):
 
 def buildIndex(genome_fp, ref_genome_fp, genome_seq=None, ref_genome_seq=None, fill_gaps=True, max_gap_width=300, smooth_edges=True,
                smoothing_radius=20):
-    """Drop-in for mauve.buildIndex (buildindex.py:90-138): index mapping from the genome in `genome_fp` to the one in `ref_genome_fp`."""
+    """Drop-in for mauve.buildIndex (buildindex.py:90-138): index mapping from the genome in `genome_fp` to the one in `ref_genome_fp`.
+    Initial anchors and sorted mer lists come from the device; when a mer occurs more than MER_REPEAT_LIMIT times (stats[3] of
+    mcu_find_mums) only the lists do and the binary finds its anchors itself (see below)."""
     genome_fp, ref_genome_fp = os.path.abspath(genome_fp), os.path.abspath(ref_genome_fp)
     genome_seq = genome_seq or getSeqFromFile(genome_fp)
     ref_genome_seq = ref_genome_seq or getSeqFromFile(ref_genome_fp)
@@ -189,7 +191,12 @@ def buildIndex(genome_fp, ref_genome_fp, genome_seq=None, ref_genome_seq=None, f
     weight = libmems.getDefaultSeedWeight((len(genome_seq) + len(ref_genome_seq)) // 2)
     seed = libmems.getSeed(weight, libmems.CODING_SEED)
     seqs = (genome_seq.encode("ascii"), ref_genome_seq.encode("ascii"))
-    rows, _ = libmems.find_mums(seqs[0], seqs[1], seed)
+    rows, stats = libmems.find_mums(seqs[0], seqs[1], seed)
+    # stats[3] != 0: some mer has more than MER_REPEAT_LIMIT (1000) copies.  There the reference's own list carries a few rows whose
+    # existence depends on std::sort's tie order (include/mauve_cuda.h); the device list leaves them out.  To keep
+    # the LUT the reference binary's in that case too, the anchors are then NOT handed over: the unmodified binary runs its own
+    # PairwiseMatchFinder on the sorted mer lists written below (the lists themselves are identical either way).
+    repeat_limit_hit = int(stats[3]) != 0
     # the sorted mer lists the binary would build next to the FASTA files (DNAFileSML::Create, LM/FileSML.cpp:401-459): written from
     # the device's lists, MatchList::LoadSMLs loads them instead (LM/MatchList.h:296-330); runMauve removes them afterwards
     for fp, seq in zip((genome_fp, ref_genome_fp), seqs):
@@ -199,7 +206,7 @@ def buildIndex(genome_fp, ref_genome_fp, genome_seq=None, ref_genome_seq=None, f
     work = tempfile.mkdtemp()
     try:
         flags = {"--output": os.path.join(work, "mauveout.xmfa")}
-        if rows.shape[0]:  # WriteList prints nothing for an empty list (LM/MatchList.h:619-620): let the binary search itself then
+        if rows.shape[0] and not repeat_limit_hit:  # WriteList prints nothing for an empty list (LM/MatchList.h:619-620): let the binary search itself then
             mums_fp = os.path.join(work, "anchors.mums")
             with open(mums_fp, "w") as f:
                 libmems.WriteList(rows, f, (genome_fp, ref_genome_fp), (len(genome_seq), len(ref_genome_seq)))

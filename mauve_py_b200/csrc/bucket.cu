@@ -33,6 +33,7 @@ constexpr int BK_IPT = 16;
 constexpr int BK_TILE = BK_THREADS * BK_IPT;   // records per scatter tile
 constexpr int BK_SUPER = 16 * BK_TILE;         // records per histogram block iteration
 constexpr int BK_CAP = 2048;                   // largest final bucket finished in shared memory
+constexpr int BK_HALF = BK_CAP / 2;            // fixed-capacity layout: records of genome 0 in the first half of a final bucket, genome 1 in the second
 constexpr int BK_MAXB = 2048;                  // max bins per level
 constexpr int BK_D3 = 10;
 
@@ -43,10 +44,11 @@ struct BkPlan {
     int w;       // seed weight
     u32 B1, B2;
     u64 npos0, npos1, ntot;
-    u64 npad0, nidx;  // genome-0 positions padded to a multiple of 16 so that a thread's 16 consecutive positions share 3 packed words
-    // fixed-capacity layout (histogram-free path): this rank owns the level-1 bins [b_lo, b_hi); every level-1 bucket has room
-    // for cap1 records, every final bucket for BK_CAP
-    u32 b_lo, b_hi, cap1;
+    u64 npad0, nidx;  // genome-0 positions padded to a multiple of BK_TILE: a thread's 16 consecutive positions share 3 packed words and a scatter tile holds one genome
+    // fixed-capacity layout (histogram-free path): this rank owns the level-1 bins [b_lo, b_hi); level-1 bucket b keeps the records of
+    // genome g in its own segment of cap1g[g] records (segment g of bucket b starts at b * (cap1g[0] + cap1g[1]) + g * cap1g[0]);
+    // a final bucket has BK_HALF records of room per genome.  cap1 = max(cap1g)
+    u32 b_lo, b_hi, cap1, cap1g[2];
     u32 shard, nshard;  // seed ownership in a sharded run (seed_owned, common.cuh)
 };
 
@@ -426,7 +428,7 @@ __device__ __noinline__ void bk_overflow(u64* keys, u32* vals, u64 cap, unsigned
 // like bk_reserve, for buckets of fixed capacity: gbase[b] = absolute index of the tile's first record of bin b,
 // cnt[b] becomes the number of the tile's records of bin b that still fit.  Returns the tile population.
 template <typename BaseFn>
-__device__ __forceinline__ u32 bkf_reserve(const BkScatterSmem& s, u32 bins, unsigned long long* __restrict__ cursor, u64 cap, BaseFn bucket_base)
+__device__ __forceinline__ u32 bkf_reserve(const BkScatterSmem& s, u32 bins, unsigned long long* __restrict__ cursor, u32 cstride, u64 cap, BaseFn bucket_base)
 {
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 per = (bins + BK_THREADS - 1) / BK_THREADS;
@@ -458,7 +460,7 @@ __device__ __forceinline__ u32 bkf_reserve(const BkScatterSmem& s, u32 bins, uns
             s.sofs[b] = run;
             run += c;
             if (c) {
-                const u64 rel = atomicAdd(&cursor[b], (unsigned long long)c);
+                const u64 rel = atomicAdd(&cursor[(size_t)b * cstride], (unsigned long long)c);
                 s.gbase[b] = bucket_base(b) + rel;
                 s.cnt[b] = rel >= cap ? 0u : (u32)min((u64)c, cap - rel);
             }
@@ -500,17 +502,24 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* 
         const u64 kmask = (1ull << kbits) - 1;   // kbits <= 62
         const int mshift = kbits / 2 + 1;
         if (compact) {
+            // ownership of the 16 seeds from two sliding windows (seed_owned_x, common.cuh): the low word of the forward seed is its
+            // last m = min(16, w) bases, the low word of its reverse complement the complemented reversal of its first m bases.
             const u32 hi_h = (u32)(w.hi >> 32), hi_l = (u32)w.hi;
             const u32 nx = kbits < 32 ? __funnelshift_l(hi_l, hi_h, kbits) : __funnelshift_l(w.lo, hi_l, kbits - 32);
-            u64 f = w.hi >> (64 - kbits);
-            u64 rc = revcomp_seed(f, sp.w);
+            const int m = sp.w < 16 ? sp.w : 16, skip = sp.w - m;                       // skip <= 15
+            const u64 last = skip ? (w.hi << (2 * skip)) | ((u64)w.lo >> (32 - 2 * skip)) : w.hi;   // bases [skip, skip + 32) of the window
+            const u64 tail = last >> (34 - 2 * m);                                      // seed `it` ends at bit 30 - 2 it of `tail`
+            u64 head = __brevll(~w.hi);                                                 // complemented reversal of bases [0, 32)
+            head = ((head & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((head & 0x5555555555555555ull) << 1);
+            const u32 xmask = m == 16 ? 0xffffffffu : (1u << (2 * m)) - 1u;
+            const u32 nvalid = pos >= npos ? 0u : (npos - pos >= 16 ? 16u : (u32)(npos - pos));
 #pragma unroll
             for (int it = 0; it < BK_IPT; ++it) {
-                const u32 nb = (nx >> (30 - 2 * it)) & 3u;
-                if (pos + it < npos && seed_owned(f, rc, pl.shard, pl.nshard)) own_mask |= 1u << it;
-                f = ((f << 2) | nb) & kmask;
-                rc = (rc >> 2) | ((u64)(3u - nb) << (kbits - 2));
+                // first m bases of seed `it` = bases [it, it + m): `head` has the complement of base k at bits 2k+1, 2k
+                const u32 x = ((u32)(tail >> (30 - 2 * it)) ^ (u32)(head >> (2 * it))) & xmask;
+                if (seed_owned_x(x, pl.shard, pl.nshard)) own_mask |= 1u << it;
             }
+            own_mask &= (1u << nvalid) - 1u;
             own_nx = nx; own_g = g; own_pos = pos; own_w = w;
             if (pl.aux && pos > 0) own_prev = base_at(gp, (i64)pos - 1);
         } else if (SOLID) {
@@ -591,8 +600,10 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* 
         }
     }
     __syncthreads();
-    const u64 cap1 = pl.cap1;
-    const u32 ntile = bkf_reserve(s, pl.B1, cursor1, cap1, [=](u32 b) { return (u64)(b - b_lo) * cap1; });
+    // the tile's genome (npad0 is a multiple of BK_TILE): its records go to that genome's segment of every level-1 bucket
+    const u32 gt = ((u64)tile_base + blockIdx.x) * BK_TILE >= pl.npad0 ? 1u : 0u;
+    const u64 cap1 = gt ? pl.cap1g[1] : pl.cap1g[0], segw = (u64)pl.cap1g[0] + pl.cap1g[1], goff = gt ? pl.cap1g[0] : 0;
+    const u32 ntile = bkf_reserve(s, pl.B1, cursor1 + (size_t)gt * pl.B1, 1, cap1, [=](u32 b) { return (u64)(b - b_lo) * segw + goff; });
 #pragma unroll
     for (int it = 0; it < BK_IPT; ++it) {
         if (br[it] != 0xffffffffu) {
@@ -611,18 +622,20 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* 
 
 // level-2 partition of one tile of level-1 bucket b_lo + blockIdx.y into its B2 final buckets
 __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter2_kernel(const u64* __restrict__ src, BkPlan pl, const unsigned long long* __restrict__ cursor1,
-                                                                    unsigned long long* __restrict__ cursor2, u64* __restrict__ dst, BkOvf ovf)
+                                                                    unsigned long long* __restrict__ cursor2, u64* __restrict__ dst, BkOvf ovf, u32 gsel)
 {
     extern __shared__ __align__(16) unsigned char raw[];
-    const u32 seg = blockIdx.y;  // relative to b_lo
-    const u64 cnt1 = min((u64)cursor1[pl.b_lo + seg], (u64)pl.cap1);
+    // level-1 bucket relative to b_lo, genome: gsel = 2 covers both genomes' segments with one grid, gsel = 0 / 1 one genome's (the
+    // segments of genome 0 are complete while genome 1 is still being uploaded)
+    const u32 seg = gsel == 2 ? blockIdx.y >> 1 : blockIdx.y, g = gsel == 2 ? blockIdx.y & 1 : gsel;
+    const u64 cnt1 = min((u64)cursor1[(size_t)g * pl.B1 + pl.b_lo + seg], (u64)(g ? pl.cap1g[1] : pl.cap1g[0]));
     const u64 base = (u64)blockIdx.x * BK_TILE;
     if (base >= cnt1) return;
     const BkScatterSmem s = bk_carve(raw, pl.B2);
     const u32 tid = threadIdx.x;
     const int shift = pl.kshift + pl.rem1 - pl.d2;
     const u32 n = (u32)min((u64)BK_TILE, cnt1 - base);
-    const u64* __restrict__ in = src + (u64)seg * pl.cap1 + base;
+    const u64* __restrict__ in = src + (u64)seg * ((u64)pl.cap1g[0] + pl.cap1g[1]) + (g ? pl.cap1g[0] : 0) + base;
     for (u32 i = tid; i < pl.B2; i += BK_THREADS) s.cnt[i] = 0;
     __syncthreads();
     u64 rec[BK_IPT];
@@ -643,7 +656,7 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter2_kernel(const u64* 
     }
     __syncthreads();
     const u64 fbase = (u64)seg * pl.B2;
-    bkf_reserve(s, pl.B2, cursor2 + fbase, (u64)BK_CAP, [=](u32 b) { return (fbase + b) * (u64)BK_CAP; });
+    bkf_reserve(s, pl.B2, cursor2 + fbase * 2 + g, 2, (u64)BK_HALF, [=](u32 b) { return (fbase + b) * (u64)BK_CAP + (u64)g * BK_HALF; });
 #pragma unroll
     for (int it = 0; it < BK_IPT; ++it) {
         if (br[it] != 0xffffffffu) {
@@ -667,7 +680,7 @@ __global__ void bkf_total_kernel(const unsigned long long* __restrict__ cursor1,
     if (threadIdx.x == 0) s_sum = 0;
     __syncthreads();
     unsigned long long t = 0;
-    for (u32 b = pl.b_lo + threadIdx.x; b < pl.b_hi; b += blockDim.x) t += cursor1[b];
+    for (u32 b = pl.b_lo + threadIdx.x; b < pl.b_hi; b += blockDim.x) t += cursor1[b] + cursor1[(size_t)pl.B1 + b];
     atomicAdd(&s_sum, t);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -691,8 +704,8 @@ struct BkGroupArgs {
     u64 cand_cap;
     u32* spill_list;               // final buckets larger than BK_CAP
     unsigned long long* spill;     // [0] buckets, [1] records, [2] convert cursor, [3] direct candidates
-    // fixed-capacity layout (cnt2 != nullptr): bucket f = recs[f * BK_CAP ...], cnt2[f] records arrived (those beyond BK_CAP
-    // went to the overflow arrays), dirty bit f = some of its records overflowed at level 1
+    // fixed-capacity layout (cnt2 != nullptr): bucket f = recs[f * BK_CAP ...], genome g's records in [g * BK_HALF, ...): cnt2[2 f + g]
+    // arrived (those beyond BK_HALF went to the overflow arrays), dirty bit f = some of its records overflowed
     const unsigned long long* cnt2;
     const u32* dirty;
     u64 nfinal;
@@ -711,13 +724,14 @@ __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, 
     __shared__ u64 candp[2][BK_DIRECT];     // pairs that are certainly candidates (aux mode)
     const u64 f = blockIdx.x;
     u64 beg;
-    u32 nb;
+    u32 nb, n0 = 0xffffffffu;   // split layout: records [n0, nb) start at beg + BK_HALF
     bool spill_it;
     if (a.cnt2) {
-        const unsigned long long tot = a.cnt2[f];
+        const unsigned long long t0 = a.cnt2[2 * f], t1 = a.cnt2[2 * f + 1];
         beg = f * BK_CAP;
-        nb = (u32)min(tot, (unsigned long long)BK_CAP);
-        spill_it = tot > BK_CAP || ((a.dirty[f >> 5] >> (f & 31)) & 1u);
+        n0 = (u32)min(t0, (unsigned long long)BK_HALF);
+        nb = n0 + (u32)min(t1, (unsigned long long)BK_HALF);
+        spill_it = t0 > BK_HALF || t1 > BK_HALF || ((a.dirty[f >> 5] >> (f & 31)) & 1u);
     } else {
         if (f >= a.meta->nfinal) return;
         beg = a.off2[f];
@@ -748,7 +762,7 @@ __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, 
 #pragma unroll
         for (int it = 0; it < BK_GIPT; ++it) {
             const u32 i = it * BK_THREADS + tid;
-            rec[it] = i < nb ? __ldcs(a.recs + beg + i) : 0;
+            rec[it] = i < nb ? __ldcs(a.recs + beg + (i < n0 ? i : i - n0 + BK_HALF)) : 0;
         }
 #pragma unroll
         for (int it = 0; it < BK_GIPT; ++it) {
@@ -860,34 +874,38 @@ __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, 
     }
 }
 
-// ---- final buckets, TMA-fed version: one open-addressing table per bucket ------------------------------------------------
+// ---- final buckets, TMA-fed version: a hash join per bucket -----------------------------------------------------------------
 // bk_group_kernel above ranks every record with a returning shared-memory atomic (counting split), re-stages the 8-byte
 // records and then lets every genome-0 record scan its sub-group: ncu (profiles/r01_ncu_bucket_enumeration_summary.txt) has it
 // issue-bound at 340 thread-instructions per record with 120 M shared-memory bank conflicts.  This version:
-//   * persistent CTAs; every final bucket (a contiguous run of <= 2048 8-byte records, 16 KB-aligned in the fixed-capacity
-//     layout) is brought into shared memory by ONE bulk asynchronous copy (cp.async.bulk + mbarrier complete_tx), double
-//     buffered: bucket k+1 is in flight while bucket k is grouped; records are never moved again;
-//   * one table of 32-bit words per bucket, open addressing on the low key bits: word = key bits << 4 | dup1 dup0 seen1 seen0.
-//     A record claims the slot of its key with ONE atomicCAS (all eight of a thread's records in flight together); a record that
-//     finds its key already there ORs its genome's `seen` bit in, and its `dup` bit if `seen` was set already.  Genome-1
-//     records also leave their index at the slot;
+//   * persistent CTAs; the two halves of a final bucket (genome 0's and genome 1's records: contiguous runs of <= 1024 8-byte
+//     records at 8 KB-aligned addresses of the fixed-capacity layout) are brought into shared memory by bulk asynchronous copies
+//     (cp.async.bulk + mbarrier complete_tx), double buffered: bucket k+1 is in flight while bucket k is joined; records are
+//     never moved again;
+//   * build: every genome-1 record claims a slot of an open-addressing table (32-bit words: key bits << 4 | dup0 dup1 seen0 seen1,
+//     addressed by the low key bits) with ONE atomicCAS -- all of a thread's records in flight together -- and leaves its index
+//     there; a record that finds its key already present marks it dup1;
+//   * probe: every genome-0 record walks the table with plain loads; on a hit it ORs seen0 in (dup0 if it was set already);
 //   * a genome-0 record whose slot reads seen0 | seen1 and nothing else is a seed pair; pairs are classified in registers and
 //     go straight to the global lists (no staging): a warp prefix over packed per-thread counts and one reservation per bucket
 //     and list give every thread its output ranges.
 // Buckets with >= 999 duplicate records (a mer with more than MER_REPEAT_LIMIT copies may be inside, which only the sorted path
-// counts exactly) go to the radix-sort + join path like dirty / overfull buckets do.  Output is identical to bk_group_kernel's
-// (pair order inside the lists is unspecified in both).
+// counts exactly: with c1 >= 1 copies in genome 1 the duplicates number c0 + c1 - 2, and more than 1000 copies in genome 0 alone
+// overflow its half) go to the radix-sort + join path like dirty / overfull buckets do.  Output is identical to
+// bk_group_kernel's (pair order inside the lists is unspecified in both).
+constexpr int G3_IPT = BK_HALF / BK_THREADS;   // records per thread and genome
 template <int LOGS>
 struct G3Smem {
-    u64 raw[2][BK_CAP];                   // TMA destinations (16 KB each)
+    u64 raw[2][BK_CAP];                   // TMA destinations: [buffer][genome 0: 0.., genome 1: BK_HALF..]
     u32 tab[1 << LOGS];                   // key << 4 | flags; 0 = empty
-    unsigned short idx1[1 << LOGS];       // index of a genome-1 record of the slot's key
+    unsigned short idx1[1 << LOGS];       // index of the genome-1 record that claimed the slot
     unsigned long long bar[2];            // mbarriers of the two buffers
     unsigned long long base[4];           // global reservations: forward pairs, reverse pairs, forward / reverse direct candidates
     u32 wtot[BK_THREADS / 32][2];         // per-warp totals: [0] forward | reverse << 16, [1] forward direct | reverse direct << 16
     u32 losers;
 };
 constexpr int G3_MAX_KEY_BITS = 28;
+constexpr u32 G3_SEEN1 = 1u, G3_SEEN0 = 2u, G3_DUP1 = 4u, G3_DUP0 = 8u;
 
 __device__ __forceinline__ u32 g3_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void g3_mbar_init(unsigned long long* bar, u32 count)
@@ -945,12 +963,16 @@ __global__ void __launch_bounds__(BK_THREADS, CTAS) bk_group3_kernel(BkGroupArgs
     typedef G3Smem<LOGS> Smem;
     Smem& sm = *reinterpret_cast<Smem*>(g3_raw);
     constexpr u32 SMASK = (1u << LOGS) - 1u;
+    constexpr u32 NONE = 0xffffffffu;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u64 nfinal = a.nfinal, stride = gridDim.x;
     const int kshift = pl.kshift;
     const u32 posmask = (u32)((1ull << pl.pbits) - 1);
     const int kb = pl.rem1 - pl.d2;   // <= G3_MAX_KEY_BITS (host)
     const u32 kmask = (1u << kb) - 1u;
+    // slots are addressed by the TOP key bits: the keys are bits of x * odd constant, whose low bits depend on the low bits of x alone
+    // (a few bases of the mer: as skewed as the base composition), while the high bits mix all of x
+    const int hshift = kb > LOGS ? kb - LOGS : 0;
     const bool aux = pl.aux != 0;
     const int auxshift = pl.pbits + 2;
     const u32 last1 = (u32)(pl.npos1 - 1);   // positions fit 32 bits (pairs are p0 | p1 << 32)
@@ -964,104 +986,175 @@ __global__ void __launch_bounds__(BK_THREADS, CTAS) bk_group3_kernel(BkGroupArgs
     {   // the table starts empty; every bucket leaves it empty again
         uint4* t = reinterpret_cast<uint4*>(sm.tab);
         for (u32 i = tid; i < (4u << LOGS) / 16; i += BK_THREADS) t[i] = make_uint4(0u, 0u, 0u, 0u);
-        uint4* x = reinterpret_cast<uint4*>(sm.idx1);   // indices are read before they are known to be meaningful: keep them in range
-        for (u32 i = tid; i < (2u << LOGS) / 16; i += BK_THREADS) x[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
 
-    // bucket descriptor: records that arrived (capped), and whether the bucket has to take the sorted path
-    auto describe = [&](u64 f, u32& nb, bool& spill) {
-        nb = 0;
-        spill = false;
+    // bucket descriptor: what arrived of the two genomes and the word holding the bucket's dirty bit.  Loaded two rounds ahead,
+    // decoded when needed, so that nobody waits for the loads.
+    struct Desc { unsigned long long c0, c1; u32 dirty; };
+    auto fetch = [&](u64 f) {
+        Desc d;
+        d.c0 = d.c1 = 0; d.dirty = 0;
         if (f < nfinal) {
-            const unsigned long long tot = __ldg(a.cnt2 + f);
-            nb = (u32)min(tot, (unsigned long long)BK_CAP);
-            spill = tot > BK_CAP || ((__ldg(a.dirty + (f >> 5)) >> (f & 31)) & 1u);
+            const ulonglong2 c = __ldg(reinterpret_cast<const ulonglong2*>(a.cnt2) + f);
+            d.c0 = c.x; d.c1 = c.y;
+            d.dirty = __ldg(a.dirty + (f >> 5));
         }
+        return d;
     };
-    auto issue = [&](int buf, u64 f, u32 nb) {  // one thread
-        const u32 bytes = (nb * 8u + 15u) & ~15u;  // an odd count reads one record of slack inside the bucket's own 16 KB
-        g3_mbar_expect_tx(&sm.bar[buf], bytes);
-        g3_bulk_load(sm.raw[buf], a.recs + f * BK_CAP, bytes, &sm.bar[buf]);
+    auto decode = [&](const Desc& d, u64 f, u32& n0, u32& n1, bool& spill) {
+        n0 = (u32)min(d.c0, (unsigned long long)BK_HALF);
+        n1 = (u32)min(d.c1, (unsigned long long)BK_HALF);
+        spill = d.c0 > BK_HALF || d.c1 > BK_HALF || ((d.dirty >> (f & 31)) & 1u);
+    };
+    auto issue = [&](int buf, u64 f, u32 n0, u32 n1) {  // one thread; an odd count reads one record of slack inside the half's own 8 KB
+        const u32 b0 = (n0 * 8u + 15u) & ~15u, b1 = (n1 * 8u + 15u) & ~15u;
+        g3_mbar_expect_tx(&sm.bar[buf], b0 + b1);
+        g3_bulk_load(sm.raw[buf], a.recs + f * BK_CAP, b0, &sm.bar[buf]);
+        g3_bulk_load(sm.raw[buf] + BK_HALF, a.recs + f * BK_CAP + BK_HALF, b1, &sm.bar[buf]);
     };
 
     u64 f = blockIdx.x;
-    u32 nb0, nb1, nb2;
-    bool sp0, sp1, sp2;
-    describe(f, nb0, sp0);
-    if (tid == 0 && nb0 && !sp0) issue(0, f, nb0);
-    describe(f + stride, nb1, sp1);
+    u32 n0a, n1a, n0b, n1b;   // this bucket, the next
+    bool spa, spb;
+    {
+        const Desc da = fetch(f), db = fetch(f + stride);
+        decode(da, f, n0a, n1a, spa);
+        decode(db, f + stride, n0b, n1b, spb);
+    }
+    if (tid == 0 && n0a && n1a && !spa) issue(0, f, n0a, n1a);
+    Desc dc = fetch(f + 2 * stride);
     u32 parity = 0;  // bit b: phase parity buffer b completes next
+
+    // pairs of the previous bucket: written one round late, so that the global reservations (tid < 4) have a round to come back
+    u64 pe[G3_IPT];
+    u32 pkinds = 0x4444u, pA = 0, pB = 0;    // kinds, this thread's offsets inside the bucket's four lists
+    bool pany = false;                       // the previous bucket has pairs (uniform)
+    unsigned long long resv = 0;             // tid < 4: reservation of list tid
+#pragma unroll
+    for (int it = 0; it < G3_IPT; ++it) pe[it] = 0;
+
+    auto write_out = [&]() {
+        u64* q0 = a.pairs + (sm.base[0] + (pA & 0xffffu));
+        u64* q1 = a.pairs + (a.pair_cap - 1 - (sm.base[1] + (pA >> 16)));
+#pragma unroll
+        for (int it = 0; it < G3_IPT; ++it) {
+            const u32 kind = (pkinds >> (4 * it)) & 15u;
+            const u64 ee = pe[it];
+            u64* q = kind ? q1 : q0;
+            if (kind < 2) {
+                *q = ee;
+                atomicOr(&a.uniq[(u32)ee >> 5], 1u << ((u32)ee & 31));
+            }
+            q0 += kind == 0 ? 1 : 0;
+            q1 -= kind == 1 ? 1 : 0;
+        }
+        if (pkinds & 0x2222u) {   // direct candidates: about one pair in a hundred
+            u64* q2 = a.cand + (sm.base[2] + (pB & 0xffffu));
+            u64* q3 = a.cand + (a.cand_cap - 1 - (sm.base[3] + (pB >> 16)));
+#pragma unroll
+            for (int it = 0; it < G3_IPT; ++it) {
+                const u32 kind = (pkinds >> (4 * it)) & 15u;
+                const u64 ee = pe[it];
+                if (kind == 2) *q2++ = ee;
+                if (kind == 3) *q3-- = ee;
+                if ((kind & 6u) == 2u) atomicOr(&a.uniq[(u32)ee >> 5], 1u << ((u32)ee & 31));
+            }
+        }
+    };
 
     for (u32 k = 0; f < nfinal; ++k, f += stride) {
         const int buf = (int)(k & 1);
-        if (tid == 0 && nb1 && !sp1) issue(buf ^ 1, f + stride, nb1);  // the other buffer was released by the barrier ending the previous round
-        describe(f + 2 * stride, nb2, sp2);
-        bool spill_it = sp0;
-        const u32 nb = nb0;
-        if (nb && !spill_it) {
+        if (tid == 0 && n0b && n1b && !spb) issue(buf ^ 1, f + stride, n0b, n1b);  // the other buffer was released by the barrier ending the previous round
+        const Desc dn = fetch(f + 3 * stride);
+        bool spill_it = spa;
+        const u32 n0 = n0a, n1 = n1a;
+        const bool work = n0 && n1 && !spill_it;   // a bucket with records of one genome only has no pair
+        u32 losers = 0;
+        const u64* __restrict__ raw = sm.raw[buf];
+        if (work) {
             g3_mbar_wait(&sm.bar[buf], (parity >> buf) & 1u);
             parity ^= 1u << buf;
-            const u64* __restrict__ raw = sm.raw[buf];
-            u64 rec[BK_GIPT];
-            u32 slot[BK_GIPT];
-            // ---- insert: one CAS per record, all of a thread's records in flight ----
-            {
-                u32 old[BK_GIPT];
+            // ---- build: genome 1 ----
+            u32 old[G3_IPT], val[G3_IPT];
 #pragma unroll
-                for (int it = 0; it < BK_GIPT; ++it) {
-                    const u32 i = it * BK_THREADS + tid;
-                    rec[it] = i < nb ? raw[i] : 0;
-                    const u32 kk = (u32)(rec[it] >> kshift) & kmask;
-                    slot[it] = kk & SMASK;
-                    old[it] = 0;
-                    if (i < nb) old[it] = atomicCAS(&sm.tab[slot[it]], 0u, (kk << 4) | (1u << ((u32)rec[it] & 1u)));
+            for (int it = 0; it < G3_IPT; ++it) {
+                const u32 i = it * BK_THREADS + tid;
+                old[it] = 0;
+                val[it] = 0;
+                if (i < n1) {
+                    const u32 kk = (u32)(raw[BK_HALF + i] >> kshift) & kmask;
+                    val[it] = (kk << 4) | G3_SEEN1;
+                    old[it] = atomicCAS(&sm.tab[(kk >> hshift) & SMASK], 0u, val[it]);
                 }
-                u32 losers = 0;
-#pragma unroll
-                for (int it = 0; it < BK_GIPT; ++it) {
-                    const u32 i = it * BK_THREADS + tid;
-                    if (i < nb) {
-                        const u32 g = (u32)rec[it] & 1u;
-                        const u32 val = (((u32)(rec[it] >> kshift) & kmask) << 4) | (1u << g);
-                        u32 o = old[it], s = slot[it];
-                        while (o != 0 && ((o ^ val) >> 4) != 0) {   // another key lives here: next slot
-                            s = (s + 1) & SMASK;
-                            o = atomicCAS(&sm.tab[s], 0u, val);
-                        }
-                        if (o != 0) {   // the key was there already
-                            const u32 bit = 1u << g;
-                            if ((o & bit) || (atomicOr(&sm.tab[s], bit) & bit)) { atomicOr(&sm.tab[s], bit << 2); ++losers; }
-                        }
-                        if (g) sm.idx1[s] = (unsigned short)i;
-                        slot[it] = s;
-                    }
-                }
-                if (losers) atomicAdd(&sm.losers, losers);
             }
-            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < G3_IPT; ++it) {
+                const u32 i = it * BK_THREADS + tid;
+                if (i < n1) {
+                    u32 o = old[it], s = (val[it] >> (4 + hshift)) & SMASK;
+                    while (o != 0 && ((o ^ val[it]) >> 4) != 0) {   // another key lives here: next slot
+                        s = (s + 1) & SMASK;
+                        o = atomicCAS(&sm.tab[s], 0u, val[it]);
+                    }
+                    if (o == 0) sm.idx1[s] = (unsigned short)i;
+                    else { atomicOr(&sm.tab[s], G3_DUP1); ++losers; }
+                }
+            }
+        }
+        if (pany && tid < 4) sm.base[tid] = resv;   // the previous bucket's reservations have had the build phase to arrive
+        __syncthreads();
+        u64 rec[G3_IPT];
+        u32 slot[G3_IPT];
+        if (work) {
+            // ---- probe: genome 0 ----
+            u32 t[G3_IPT];
+#pragma unroll
+            for (int it = 0; it < G3_IPT; ++it) {
+                const u32 i = it * BK_THREADS + tid;
+                rec[it] = i < n0 ? raw[i] : 0;
+                slot[it] = (((u32)(rec[it] >> kshift) & kmask) >> hshift) & SMASK;   // (& kmask: the level-2 bin bits sit above the key bits)
+                t[it] = i < n0 ? sm.tab[slot[it]] : 0u;
+            }
+#pragma unroll
+            for (int it = 0; it < G3_IPT; ++it) {
+                const u32 kk = (u32)(rec[it] >> kshift) & kmask;
+                u32 v = t[it], s = slot[it];
+                while (v != 0 && (v >> 4) != kk) {
+                    s = (s + 1) & SMASK;
+                    v = sm.tab[s];
+                }
+                slot[it] = NONE;
+                if (v != 0 && !(v & G3_DUP1)) {   // (an empty slot: the mer does not occur in genome 1; also every i >= n0)
+                    const u32 o = atomicOr(&sm.tab[s], G3_SEEN0);
+                    if (o & G3_SEEN0) { atomicOr(&sm.tab[s], G3_DUP0); ++losers; }
+                    slot[it] = s;
+                } else if (v != 0) ++losers;      // one of many copies in genome 1: counted like a duplicate
+            }
+            if (losers) atomicAdd(&sm.losers, losers);
+        }
+        if (pany) write_out();   // previous bucket
+        pany = false;
+        pkinds = 0x4444u;
+        __syncthreads();
+        if (work) {
             spill_it = sm.losers >= 999u;
             // ---- pairing: a genome-0 record whose key was seen once in each genome ----
-            u64 e[BK_GIPT];
-            u32 kinds = 0;            // 4 bits per record: 0 forward, 1 reverse, 2 forward direct, 3 reverse direct, 4 nothing
             u32 cA = 0, cB = 0;       // forward | reverse << 16, forward direct | reverse direct << 16
+            if (!spill_it) {
+                pkinds = 0;           // 4 bits per record: 0 forward, 1 reverse, 2 forward direct, 3 reverse direct, 4 nothing
 #pragma unroll
-            for (int it = 0; it < BK_GIPT; ++it) {
-                const u32 i = it * BK_THREADS + tid;
-                u32 kind = 4;
-                e[it] = 0;
-                if (i < nb && !spill_it) {   // uniform except in the bucket's last round
+                for (int it = 0; it < G3_IPT; ++it) {
+                    u32 kind = 4;
                     const u32 s = slot[it];
-                    const u64 r1 = raw[sm.idx1[s]];   // a stale index for a key without genome-1 record: any record of the bucket, unused
-                    const u32 k = g3_classify(rec[it], r1, aux, auxshift, posmask, last1, e[it]);
-                    if ((sm.tab[s] & 15u) == 3u && !((u32)rec[it] & 1u)) {
-                        kind = k;
-                        const u32 inc = 1u << ((k & 1u) << 4);
-                        cA += k < 2 ? inc : 0u;
-                        cB += k < 2 ? 0u : inc;
+                    if (s != NONE && (sm.tab[s] & 15u) == (G3_SEEN0 | G3_SEEN1)) {
+                        kind = g3_classify(rec[it], raw[BK_HALF + sm.idx1[s]], aux, auxshift, posmask, last1, pe[it]);
+                        const u32 inc = 1u << ((kind & 1u) << 4);
+                        cA += kind < 2 ? inc : 0u;
+                        cB += kind < 2 ? 0u : inc;
                     }
+                    pkinds |= kind << (4 * it);
                 }
-                kinds |= kind << (4 * it);
             }
             // warp prefix of the packed counts
             u32 iA = cA, iB = cB;
@@ -1071,56 +1164,47 @@ __global__ void __launch_bounds__(BK_THREADS, CTAS) bk_group3_kernel(BkGroupArgs
                 if (lane >= (u32)o) { iA += tA; iB += tB; }
             }
             if (lane == 31) { sm.wtot[warp][0] = iA; sm.wtot[warp][1] = iB; }
-            __syncthreads();   // every read of the table is done
-            {   // ---- empty the table for the next bucket (the reservation below is in flight meanwhile) ----
+            pA = iA - cA;
+            pB = iB - cB;
+        }
+        __syncthreads();   // every read of the table and of raw[buf] is done
+        if (work) {
+            {   // ---- empty the table for the next bucket ----
                 uint4* t = reinterpret_cast<uint4*>(sm.tab);
 #pragma unroll
                 for (u32 i = tid; i < (4u << LOGS) / 16; i += BK_THREADS) t[i] = make_uint4(0u, 0u, 0u, 0u);
                 if (tid == 0) sm.losers = 0;
             }
             if (!spill_it) {
-                u32 bA = 0, bB = 0, tA = 0, tB = 0;
+                u32 tA = 0, tB = 0;
 #pragma unroll
                 for (u32 w = 0; w < BK_THREADS / 32; ++w) {
                     const u32 xA = sm.wtot[w][0], xB = sm.wtot[w][1];
-                    if (w < warp) { bA += xA; bB += xB; }
+                    if (w < warp) { pA += xA; pB += xB; }
                     tA += xA; tB += xB;
                 }
-                if (tid == 0) {
-                    const u32 nf = tA & 0xffffu, nr = tA >> 16, ncf = tB & 0xffffu, ncr = tB >> 16;
-                    sm.base[0] = nf ? atomicAdd(&a.counters[0], (unsigned long long)nf) : 0ull;
-                    sm.base[1] = nr ? atomicAdd(&a.counters[6], (unsigned long long)nr) : 0ull;
-                    sm.base[2] = ncf ? atomicAdd(&a.counters[2], (unsigned long long)ncf) : 0ull;
-                    sm.base[3] = ncr ? atomicAdd(&a.counters[7], (unsigned long long)ncr) : 0ull;
-                    if (ncf + ncr) atomicAdd(&a.spill[3], (unsigned long long)(ncf + ncr));
-                }
-                __syncthreads();
-                bA += iA - cA;
-                bB += iB - cB;
-                // running pointers of this thread's four output ranges (reverse lists grow downwards from the end of the arrays)
-                u64* q0 = a.pairs + (sm.base[0] + (bA & 0xffffu));
-                u64* q1 = a.pairs + (a.pair_cap - 1 - (sm.base[1] + (bA >> 16)));
-                u64* q2 = a.cand + (sm.base[2] + (bB & 0xffffu));
-                u64* q3 = a.cand + (a.cand_cap - 1 - (sm.base[3] + (bB >> 16)));
-#pragma unroll
-                for (int it = 0; it < BK_GIPT; ++it) {
-                    const u32 kind = (kinds >> (4 * it)) & 15u;
-                    const u64 ee = e[it];
-                    if (kind == 0) *q0++ = ee;
-                    if (kind == 1) *q1-- = ee;
-                    if (kind == 2) *q2++ = ee;
-                    if (kind == 3) *q3-- = ee;
-                    if (kind < 4) atomicOr(&a.uniq[(u32)ee >> 5], 1u << ((u32)ee & 31));
+                pany = (tA | tB) != 0;
+                if (tid < 4) {   // one reservation per list; consumed in the next round
+                    const u32 tot = tid == 0 ? tA & 0xffffu : tid == 1 ? tA >> 16 : tid == 2 ? tB & 0xffffu : tB >> 16;
+                    unsigned long long* ctr = tid == 0 ? &a.counters[0] : tid == 1 ? &a.counters[6] : tid == 2 ? &a.counters[2] : &a.counters[7];
+                    resv = tot ? atomicAdd(ctr, (unsigned long long)tot) : 0ull;
+                    if (tid >= 2 && tot) atomicAdd(&a.spill[3], (unsigned long long)tot);
                 }
             }
         }
         if (spill_it && tid == 0) {
             a.spill_list[atomicAdd(&a.spill[0], 1ull)] = (u32)f;
-            atomicAdd(&a.spill[1], (unsigned long long)nb);
+            atomicAdd(&a.spill[1], (unsigned long long)(n0 + n1));
         }
-        __syncthreads();  // every read of raw[buf] and of the reservations is done, the table is empty: the next round may begin
-        nb0 = nb1; sp0 = sp1;
-        nb1 = nb2; sp1 = sp2;
+        __syncthreads();  // the table is empty, the per-warp totals are read: the next round may begin
+        n0a = n0b; n1a = n1b; spa = spb;
+        decode(dc, f + 2 * stride, n0b, n1b, spb);
+        dc = dn;
+    }
+    if (pany) {   // the last bucket's pairs
+        if (tid < 4) sm.base[tid] = resv;
+        __syncthreads();
+        write_out();
     }
 }
 
@@ -1133,13 +1217,14 @@ __global__ void __launch_bounds__(BK_THREADS) bk_spill_kernel(const u64* __restr
     __shared__ unsigned long long s_base;
     const u32 f = spill_list[blockIdx.x];
     const u64 beg = cnt2 ? (u64)f * BK_CAP : off2[f];
-    const u64 nb = cnt2 ? min((u64)cnt2[f], (u64)BK_CAP) : off2[f + 1] - beg;
+    const u64 n0 = cnt2 ? min((u64)cnt2[2 * (u64)f], (u64)BK_HALF) : ~0ull;   // split layout: records [n0, nb) start at beg + BK_HALF
+    const u64 nb = cnt2 ? n0 + min((u64)cnt2[2 * (u64)f + 1], (u64)BK_HALF) : off2[f + 1] - beg;
     if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned long long)nb);
     __syncthreads();
     const u64 b1 = meta->b_lo + f / pl.B2;
     const u64 posmask = (1ull << pl.pbits) - 1;
     for (u64 i = threadIdx.x; i < nb; i += blockDim.x) {
-        const u64 r = recs[beg + i];
+        const u64 r = recs[beg + (i < n0 ? i : i - n0 + BK_HALF)];
         const u64 mixed = (b1 << pl.rem1) | (r >> pl.kshift);  // the mixed mer: equal exactly when the mers are equal
         keys[s_base + i] = (mixed << 2) | ((r & 1) << 1) | ((r >> 1) & 1);
         vals[s_base + i] = (u32)((r >> 2) & posmask);
@@ -1162,7 +1247,9 @@ static bool make_plan(const SeedParams& sp, u64 npos0, u64 npos1, u64 share, BkP
     p.npos0 = npos0; p.npos1 = npos1; p.ntot = npos0 + npos1;
     p.pbits = bit_len((npos0 > npos1 ? npos0 : npos1));
     if (p.pbits < 1) p.pbits = 1;
-    const u64 expect = p.ntot / share;  // records this rank will hold
+    // records this rank will hold, counting the smaller genome like the larger one: final buckets keep the two genomes' records
+    // in separate halves, so the bucket count follows the larger genome
+    const u64 expect = 2 * (npos0 > npos1 ? npos0 : npos1) / share;
     if (expect < 65536 || p.ntot >= (1ull << 40)) return false;
     int T = bit_len(expect / 1536);          // 768..1536 records per final bucket: BK_CAP is > 13 sigma away
     if (T > p.kbits - 2) T = p.kbits - 2;    // keep key bits for the in-bucket comparison
@@ -1182,7 +1269,7 @@ static bool make_plan(const SeedParams& sp, u64 npos0, u64 npos1, u64 share, BkP
     if (p.d3 < 0) return false;
     p.B1 = 1u << p.d1;
     p.B2 = 1u << p.d2;
-    p.npad0 = (npos0 + 15) & ~15ull;
+    p.npad0 = (npos0 + BK_TILE - 1) / BK_TILE * BK_TILE;
     p.nidx = p.npad0 + ((npos1 + 15) & ~15ull);
     *out = p;
     return true;
@@ -1199,13 +1286,16 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     pl.b_lo = 0;   // seeds are owned by hash (seed_owned), so every bucket holds this rank's 1/shard_count share
     pl.b_hi = pl.B1;
     const u32 nb1 = pl.b_hi - pl.b_lo;
-    const double mean1 = (double)pl.ntot / (double)shard_count / pl.B1;
-    pl.cap1 = (u32)(((u64)(mean1 + 8.0 * sqrt(mean1) + 64.0) + 31) & ~31ull);
+    for (int g = 0; g < 2; ++g) {
+        const double mean1 = (double)(g ? pl.npos1 : pl.npos0) / (double)shard_count / pl.B1;
+        pl.cap1g[g] = (u32)(((u64)(mean1 + 8.0 * sqrt(mean1) + 64.0) + 31) & ~31ull);
+    }
+    pl.cap1 = pl.cap1g[0] > pl.cap1g[1] ? pl.cap1g[0] : pl.cap1g[1];
     const u64 nfinal = (u64)nb1 * pl.B2;
     u64 ovf_cap = pl.ntot / 8 / (u64)shard_count + (1ull << 20);
     if (const char* e = getenv("MAUVE_CUDA_OVF_CAP")) ovf_cap = strtoull(e, nullptr, 10);  // tests: force the fallback
     const u64 dirty_words = nfinal / 32 + 1;
-    MCU_TRY(s.bk_a.reserve(((u64)nb1 * pl.cap1 + 1) * 8));
+    MCU_TRY(s.bk_a.reserve(((u64)nb1 * ((u64)pl.cap1g[0] + pl.cap1g[1]) + 1) * 8));
     MCU_TRY(s.bk_b.reserve((nfinal * BK_CAP + 1) * 8));
     MCU_TRY(s.bk_tab1.reserve((size_t)(pl.B1 + 1) * 8 * 3 + 64));
     MCU_TRY(s.bk_tab2.reserve((nfinal + 1) * 8 * 3 + 64 + dirty_words * 4));
@@ -1215,10 +1305,10 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     unsigned long long* cursor1 = s.bk_tab1.as<unsigned long long>();
     BkMeta* meta = (BkMeta*)(cursor1 + (size_t)(pl.B1 + 1) * 3);  // inside the +64 bytes slack, as in the exact path
     unsigned long long* cursor2 = s.bk_tab2.as<unsigned long long>();
-    unsigned long long* spill = cursor2 + nfinal + 1;  // [0] buckets [1] records [2] overflow / convert cursor [3] direct candidates
+    unsigned long long* spill = cursor2 + 2 * nfinal + 2;  // [0] buckets [1] records [2] overflow / convert cursor [3] direct candidates
     u32* dirty = (u32*)(spill + 4);
-    MCU_CUDA(cudaMemsetAsync(cursor1, 0, (size_t)(pl.B1 + 1) * 8, st));
-    MCU_CUDA(cudaMemsetAsync(cursor2, 0, (nfinal + 1) * 8 + 32 + dirty_words * 4, st));
+    MCU_CUDA(cudaMemsetAsync(cursor1, 0, (size_t)(2 * pl.B1 + 1) * 8, st));
+    MCU_CUDA(cudaMemsetAsync(cursor2, 0, (2 * nfinal + 2) * 8 + 32 + dirty_words * 4, st));
     const u32* g0 = s.packed[0].as<u32>();
     const u32* g1 = s.packed[1].as<u32>();
     static bool attr_done = false;
@@ -1240,6 +1330,7 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
         else bkf_scatter1_kernel<false><<<t1 - t0, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf, t0);
         s.launches++;
     };
+    bool scatter2_done = false;
     if (s.up_chunks > 0 && s.pack_world == 1) {
         // chunked upload in flight (session_upload_begin): pack every piece as it lands and scatter the tiles whose seeds it
         // completes.  A seed window (and the neighbour bases of aux records) reads at most 64 bases past its position.
@@ -1262,6 +1353,13 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
                 if (upto > tiles1) upto = tiles1;
                 if (nb1) scatter1(done, upto);
                 if (upto > done) done = upto;
+                if (nb1 && last) {   // all tiles of genome g are out: its level-1 segments can be partitioned while the rest still arrives
+                    const u32 capg = g ? pl.cap1g[1] : pl.cap1g[0];
+                    bkf_scatter2_kernel<<<dim3((unsigned)div_up(capg, BK_TILE), nb1), BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(
+                        s.bk_a.as<u64>(), pl, cursor1, cursor2, s.bk_b.as<u64>(), ovf, (u32)g);
+                    s.launches++;
+                    scatter2_done = true;
+                }
             }
         s.up_chunks = 0;
     } else if (nb1) scatter1(0, tiles1);
@@ -1269,9 +1367,9 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     MCU_CUDA(cudaEventRecord(s.kev[2], st));
     bkf_total_kernel<<<1, 256, 0, st>>>(cursor1, pl, meta);
     MCU_CUDA(cudaEventRecord(s.kev[3], st));
-    if (nb1) {
-        const dim3 grid2((unsigned)div_up(pl.cap1, BK_TILE), nb1);
-        bkf_scatter2_kernel<<<grid2, BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(s.bk_a.as<u64>(), pl, cursor1, cursor2, s.bk_b.as<u64>(), ovf);
+    if (nb1 && !scatter2_done) {
+        const dim3 grid2((unsigned)div_up(pl.cap1, BK_TILE), 2 * nb1);
+        bkf_scatter2_kernel<<<grid2, BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(s.bk_a.as<u64>(), pl, cursor1, cursor2, s.bk_b.as<u64>(), ovf, 2u);
     }
     MCU_CUDA(cudaEventRecord(ev_scatter2, st));
     MCU_CUDA(cudaEventRecord(s.kev[4], st));
@@ -1281,9 +1379,9 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     ga.cand = s.cand.as<u64>(); ga.cand_cap = pair_cap;
     ga.cnt2 = cursor2; ga.dirty = dirty; ga.nfinal = nfinal;
     // bk_group3 keeps <= 28 key bits that differ inside a final bucket next to four flag bits; wider keys (not reached by the seed
-    // tables at sizes that take this path) keep bk_group.  MAUVE_CUDA_GROUP_V1 / MAUVE_CUDA_GROUP_S11: A/B switches.
+    // tables at sizes that take this path) keep bk_group.  MAUVE_CUDA_GROUP_V1 / MAUVE_CUDA_GROUP_VARIANT: A/B switches.
     static const bool group_v1_env = getenv("MAUVE_CUDA_GROUP_V1") != nullptr;
-    static const bool group_s11 = getenv("MAUVE_CUDA_GROUP_S11") != nullptr;
+    static const int variant = getenv("MAUVE_CUDA_GROUP_VARIANT") ? atoi(getenv("MAUVE_CUDA_GROUP_VARIANT")) : 0;
     const bool group_v1 = group_v1_env || pl.rem1 - pl.d2 > G3_MAX_KEY_BITS;
     if (nfinal && group_v1) bk_group_kernel<<<(unsigned)nfinal, BK_THREADS, 0, st>>>(ga, pl);
     else if (nfinal) {
@@ -1291,16 +1389,15 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
         if (!attr3_done) {
             MCU_CUDA(cudaFuncSetAttribute(bk_group3_kernel<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G3Smem<12>)));
             MCU_CUDA(cudaFuncSetAttribute(bk_group3_kernel<11, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G3Smem<11>)));
+            MCU_CUDA(cudaFuncSetAttribute(bk_group3_kernel<11, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G3Smem<11>)));
             attr3_done = true;
         }
         // persistent: as many CTAs as fit, each walks the buckets with stride gridDim.x
-        if (group_s11) {
-            const u64 want = (u64)sm_count() * 4;
-            bk_group3_kernel<11, 4><<<(unsigned)(nfinal < want ? nfinal : want), BK_THREADS, sizeof(G3Smem<11>), st>>>(ga, pl);
-        } else {
-            const u64 want = (u64)sm_count() * 3;
-            bk_group3_kernel<12, 3><<<(unsigned)(nfinal < want ? nfinal : want), BK_THREADS, sizeof(G3Smem<12>), st>>>(ga, pl);
-        }
+        const u64 want = (u64)sm_count() * (variant == 1 ? 3 : variant == 2 ? 5 : 4);
+        const unsigned grid = (unsigned)(nfinal < want ? nfinal : want);
+        if (variant == 1) bk_group3_kernel<12, 3><<<grid, BK_THREADS, sizeof(G3Smem<12>), st>>>(ga, pl);
+        else if (variant == 2) bk_group3_kernel<11, 5><<<grid, BK_THREADS, sizeof(G3Smem<11>), st>>>(ga, pl);
+        else bk_group3_kernel<11, 4><<<grid, BK_THREADS, sizeof(G3Smem<11>), st>>>(ga, pl);
     }
     MCU_CUDA(cudaEventRecord(s.kev[5], st));
     s.launches += 3;

@@ -121,15 +121,19 @@ __device__ __forceinline__ u64 revcomp_seed(u64 f, int w)
     return x >> (64 - 2 * w);
 }
 
-// Which rank of a sharded run owns a seed: a hash of forward ^ reverse-complement, which is the same for a mer and its
-// reverse complement, so the decision needs neither the canonical form nor the bucket of the mer -- the non-owners'
-// whole cost per position is the rolling update of the two words and this test.  Every enumeration path uses it, so
-// ranks that end up on different paths (bucket overflow fallback) still agree on the partition.
+// Which rank of a sharded run owns a seed: a hash of the low words of forward ^ reverse-complement, which is the same for a mer and
+// its reverse complement, so the decision needs neither the canonical form nor the bucket of the mer.  The low word of the forward
+// seed is its last min(16, w) bases, the low word of the reverse complement comes from its first min(16, w) bases: a scan over
+// consecutive positions gets both from two sliding windows (bkf_scatter1_kernel's sharded path) -- the non-owners' whole cost.
+// Every enumeration path uses it, so ranks that end up on different paths (bucket overflow fallback) still agree on the partition.
+__device__ __forceinline__ bool seed_owned_x(u32 x, u32 shard, u32 nshard)   // x = (u32)forward ^ (u32)reverse complement
+{
+    return __umulhi(x * 0x9E3779B1u, nshard) == shard;
+}
 __device__ __forceinline__ bool seed_owned(u64 f, u64 rc, u32 shard, u32 nshard)
 {
     if (nshard <= 1) return true;
-    const u32 h = (u32)(((f ^ rc) * 0xD6E8FEB86659FD93ull) >> 32);
-    return (u32)(((u64)h * nshard) >> 32) == shard;
+    return seed_owned_x((u32)f ^ (u32)rc, shard, nshard);
 }
 
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }

@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(128) nwf_traceback_kernel(NwfTbArgs g)
     for (;;) {
         *--out = edge;
         ++n;
-        const u32 here = edge == 'M' ? 0u : nwf_nibble(tb, T, pa, pb);
+        const u32 here = (edge == 'M' || pa == 0 || pb == 0) ? 0u : nwf_nibble(tb, T, pa, pb);   // first row / column: the gap runs to the corner
         const u32 dg = (edge == 'M' && pa >= 2 && pb >= 2) ? nwf_nibble(tb, T, pa - 1, pb - 1) : 0u;
         const char next = nwf_prev_edge(edge, pa, pb, here, dg);
         if (edge != 'I') --pa;

@@ -102,9 +102,9 @@ int mcu_nw_batch_wild(uint64_t n, const char* a, const uint64_t* a_off, const ch
     uint64_t i;
     const double t0 = stub_now();
     g_nwf_problems += n;
-    for (i = 0; i < n; ++i) {   /* the argument checks of nw_batch_wild (csrc/dpwild.cu): empty region, more than 2^24 cells */
+    for (i = 0; i < n; ++i) {   /* the argument checks of nw_batch_wild (csrc/dpwild.cu): empty region, sequence too long */
         const uint64_t la = a_off[i + 1] - a_off[i], lb = b_off[i + 1] - b_off[i];
-        if (a_off[i + 1] <= a_off[i] || b_off[i + 1] <= b_off[i] || la * lb > (16ull << 20)) return -3;   /* MCU_EINVAL */
+        if (a_off[i + 1] <= a_off[i] || b_off[i + 1] <= b_off[i] || la > 0x3FFFFFFull || lb > 0x3FFFFFFull) return -3;   /* MCU_EINVAL */
     }
     for (i = 0; i < n; ++i) {
         long long r = orc_nw_align_f(a + a_off[i], (unsigned)(a_off[i + 1] - a_off[i]), b + b_off[i], (unsigned)(b_off[i + 1] - b_off[i]),

@@ -151,6 +151,26 @@ def test_buildindex_flow_with_the_oracle_list(tmp_path, monkeypatch, orc):
     got = B.buildIndex(fas[0], fas[1])
     assert np.array_equal(got, lut)
     assert not os.path.exists(fas[0] + ".sslist") and not os.path.exists(fas[1] + ".sslist")
+    # a mer beyond MER_REPEAT_LIMIT (stats[3] != 0): the anchors are NOT handed over (the reference's own list may then carry rows
+    # that depend on std::sort's tie order); the binary finds them itself from the lists written for it, and the LUT is still its own
+    seen = []
+    real_run = B.runMauve
+
+    def spy(files, flags):
+        seen.append(dict(flags))
+        return real_run(files, flags)
+
+    def flagged(a, b, seed, rule=0):
+        rows, stats = orc.find_mums(a, b, seed, rule)
+        stats = np.array(stats, dtype=np.uint64)
+        stats[3] = 1
+        return rows, stats
+
+    monkeypatch.setattr(B, "runMauve", spy)
+    monkeypatch.setattr(B.libmems, "find_mums", flagged)
+    got = B.buildIndex(fas[0], fas[1])
+    assert len(seen) == 1 and "--match-input" not in seen[0] and np.array_equal(got, lut)
+    monkeypatch.setattr(B, "runMauve", real_run)
     monkeypatch.delenv("MAUVE_DIR")
     with pytest.raises(IOError):
         B.buildIndex(fas[0], fas[1])
