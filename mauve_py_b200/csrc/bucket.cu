@@ -894,9 +894,9 @@ __global__ void __launch_bounds__(BK_THREADS, 6) bk_group_kernel(BkGroupArgs a, 
 // overflow its half) go to the radix-sort + join path like dirty / overfull buckets do.  Output is identical to
 // bk_group_kernel's (pair order inside the lists is unspecified in both).
 constexpr int G3_IPT = BK_HALF / BK_THREADS;   // records per thread and genome
-template <int LOGS>
+template <int LOGS, int NBUF>
 struct G3Smem {
-    u64 raw[2][BK_CAP];                   // TMA destinations: [buffer][genome 0: 0.., genome 1: BK_HALF..]
+    u64 raw[NBUF][BK_CAP];                // TMA destinations: [buffer][genome 0: 0.., genome 1: BK_HALF..]
     u32 tab[1 << LOGS];                   // key << 4 | flags; 0 = empty
     unsigned short idx1[1 << LOGS];       // index of the genome-1 record that claimed the slot
     unsigned long long bar[2];            // mbarriers of the two buffers
@@ -956,11 +956,14 @@ __device__ __forceinline__ u32 g3_classify(u64 r, u64 r1, bool aux, int auxshift
     return rev | direct;
 }
 
-template <int LOGS, int CTAS>
+// NBUF = 2: the next bucket is copied while this one is joined; NBUF = 1: the next bucket's copy starts when this one's records have
+// been read for the last time (it overlaps the reservation, the table clean-up and the previous bucket's write-out only, but the
+// smaller footprint lets more CTAs share an SM)
+template <int LOGS, int NBUF, int CTAS>
 __global__ void __launch_bounds__(BK_THREADS, CTAS) bk_group3_kernel(BkGroupArgs a, BkPlan pl)
 {
     extern __shared__ __align__(128) unsigned char g3_raw[];
-    typedef G3Smem<LOGS> Smem;
+    typedef G3Smem<LOGS, NBUF> Smem;
     Smem& sm = *reinterpret_cast<Smem*>(g3_raw);
     constexpr u32 SMASK = (1u << LOGS) - 1u;
     constexpr u32 NONE = 0xffffffffu;
@@ -979,7 +982,7 @@ __global__ void __launch_bounds__(BK_THREADS, CTAS) bk_group3_kernel(BkGroupArgs
 
     if (tid == 0) {
         g3_mbar_init(&sm.bar[0], 1);
-        g3_mbar_init(&sm.bar[1], 1);
+        if (NBUF == 2) g3_mbar_init(&sm.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sm.losers = 0;
     }
@@ -1064,8 +1067,8 @@ __global__ void __launch_bounds__(BK_THREADS, CTAS) bk_group3_kernel(BkGroupArgs
     };
 
     for (u32 k = 0; f < nfinal; ++k, f += stride) {
-        const int buf = (int)(k & 1);
-        if (tid == 0 && n0b && n1b && !spb) issue(buf ^ 1, f + stride, n0b, n1b);  // the other buffer was released by the barrier ending the previous round
+        const int buf = NBUF == 2 ? (int)(k & 1) : 0;
+        if (NBUF == 2 && tid == 0 && n0b && n1b && !spb) issue(buf ^ 1, f + stride, n0b, n1b);  // the other buffer was released by the barrier ending the previous round
         const Desc dn = fetch(f + 3 * stride);
         bool spill_it = spa;
         const u32 n0 = n0a, n1 = n1a;
@@ -1100,6 +1103,7 @@ __global__ void __launch_bounds__(BK_THREADS, CTAS) bk_group3_kernel(BkGroupArgs
                     if (o == 0) sm.idx1[s] = (unsigned short)i;
                     else { atomicOr(&sm.tab[s], G3_DUP1); ++losers; }
                 }
+                __syncwarp();   // the probing lanes rejoin here: without it the warp stays split for the records that follow
             }
         }
         if (pany && tid < 4) sm.base[tid] = resv;   // the previous bucket's reservations have had the build phase to arrive
@@ -1130,6 +1134,7 @@ __global__ void __launch_bounds__(BK_THREADS, CTAS) bk_group3_kernel(BkGroupArgs
                     if (o & G3_SEEN0) { atomicOr(&sm.tab[s], G3_DUP0); ++losers; }
                     slot[it] = s;
                 } else if (v != 0) ++losers;      // one of many copies in genome 1: counted like a duplicate
+                __syncwarp();
             }
             if (losers) atomicAdd(&sm.losers, losers);
         }
@@ -1168,6 +1173,7 @@ __global__ void __launch_bounds__(BK_THREADS, CTAS) bk_group3_kernel(BkGroupArgs
             pB = iB - cB;
         }
         __syncthreads();   // every read of the table and of raw[buf] is done
+        if (NBUF == 1 && tid == 0 && n0b && n1b && !spb) issue(0, f + stride, n0b, n1b);
         if (work) {
             {   // ---- empty the table for the next bucket ----
                 uint4* t = reinterpret_cast<uint4*>(sm.tab);
@@ -1385,19 +1391,21 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     const bool group_v1 = group_v1_env || pl.rem1 - pl.d2 > G3_MAX_KEY_BITS;
     if (nfinal && group_v1) bk_group_kernel<<<(unsigned)nfinal, BK_THREADS, 0, st>>>(ga, pl);
     else if (nfinal) {
-        static bool attr3_done = false;
-        if (!attr3_done) {
-            MCU_CUDA(cudaFuncSetAttribute(bk_group3_kernel<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G3Smem<12>)));
-            MCU_CUDA(cudaFuncSetAttribute(bk_group3_kernel<11, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G3Smem<11>)));
-            MCU_CUDA(cudaFuncSetAttribute(bk_group3_kernel<11, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G3Smem<11>)));
-            attr3_done = true;
-        }
         // persistent: as many CTAs as fit, each walks the buckets with stride gridDim.x
-        const u64 want = (u64)sm_count() * (variant == 1 ? 3 : variant == 2 ? 5 : 4);
-        const unsigned grid = (unsigned)(nfinal < want ? nfinal : want);
-        if (variant == 1) bk_group3_kernel<12, 3><<<grid, BK_THREADS, sizeof(G3Smem<12>), st>>>(ga, pl);
-        else if (variant == 2) bk_group3_kernel<11, 5><<<grid, BK_THREADS, sizeof(G3Smem<11>), st>>>(ga, pl);
-        else bk_group3_kernel<11, 4><<<grid, BK_THREADS, sizeof(G3Smem<11>), st>>>(ga, pl);
+        auto launch = [&](auto kernel, size_t smem, int ctas) -> int {
+            MCU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const u64 want = (u64)sm_count() * ctas;
+            kernel<<<(unsigned)(nfinal < want ? nfinal : want), BK_THREADS, smem, st>>>(ga, pl);
+            return MCU_OK;
+        };
+        switch (variant) {
+        case 1: MCU_TRY(launch(bk_group3_kernel<12, 2, 3>, sizeof(G3Smem<12, 2>), 3)); break;
+        case 2: MCU_TRY(launch(bk_group3_kernel<11, 2, 5>, sizeof(G3Smem<11, 2>), 5)); break;
+        case 3: MCU_TRY(launch(bk_group3_kernel<12, 1, 5>, sizeof(G3Smem<12, 1>), 5)); break;
+        case 4: MCU_TRY(launch(bk_group3_kernel<11, 1, 6>, sizeof(G3Smem<11, 1>), 6)); break;
+        case 5: MCU_TRY(launch(bk_group3_kernel<12, 1, 4>, sizeof(G3Smem<12, 1>), 4)); break;
+        default: MCU_TRY(launch(bk_group3_kernel<11, 2, 4>, sizeof(G3Smem<11, 2>), 4)); break;
+        }
     }
     MCU_CUDA(cudaEventRecord(s.kev[5], st));
     s.launches += 3;

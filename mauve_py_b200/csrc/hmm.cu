@@ -24,6 +24,7 @@
 namespace mcu {
 
 constexpr int HC = 64;  // columns per chunk
+constexpr int HMM_SPEC = 8;  // columns per speculative group of the exact chain (hmm_exact_chain_warp_kernel)
 
 struct HmmModel {
     double a[8][4];      // per symbol: {HH, UH, HU, UU} transition*emission, f' = (a0 h + a1 u, a2 h + a3 u)
@@ -407,10 +408,13 @@ __global__ void __launch_bounds__(32) hmm_exact_chain_warp_kernel(const u8* __re
         if (lane == 0) {
             // Common case, decided with integer tests on the high words of the four products: all of them positive and well
             // inside [1e-18, 1e18] (no renormalisation) and both states on the same exponent (aConversionLookup[0] = 1): the step
-            // is 2 float->double conversions, 4 double products, 4 double->float roundings and 2 float additions.  Anything
-            // else takes the operation-by-operation path.
+            // is 2 float->double conversions, 4 double products, 4 double->float roundings and 2 float additions.  Columns are
+            // taken in groups of HMM_SPEC: the group is evaluated in that form without a branch per column (the range tests only
+            // accumulate a flag, so the dependency chain of a column is conversion -> product -> rounding -> addition and nothing
+            // else), and a group in which any column left the common case is evaluated again, operation by operation, from the
+            // state it started with.
             const u32 w_lo = (u32)__double2hiint(lo) + 1u, w_span = (u32)__double2hiint(hi) - w_lo;
-            for (u32 j = 0; j < cnt; ++j) {
+            auto exact_step = [&](u32 j) {
                 const double4 c = coef[j];
                 const double du = (double)u.f, dh = (double)h.f;
                 // forward: U <- (c.x u) + (c.y h), H <- (c.z u) + (c.w h); backward: H <- (c.w h) + (c.y u), U <- (c.x u) + (c.z h)
@@ -438,7 +442,33 @@ __global__ void __launch_bounds__(32) hmm_exact_chain_warp_kernel(const u8* __re
                     u = nu;
                 }
                 res[j] = h;
+            };
+            u32 j0 = 0;
+            for (; j0 + HMM_SPEC <= cnt; j0 += HMM_SPEC) {
+                bool ok = u.e == h.e;
+                if (ok) {
+                    float uf = u.f, hf = h.f;
+                    u32 good = 1u;
+#pragma unroll
+                    for (int q = 0; q < HMM_SPEC; ++q) {
+                        const double4 c = coef[j0 + q];
+                        const double du = (double)uf, dh = (double)hf;
+                        const double p0 = __dmul_rn(fwd ? du : dh, fwd ? c.x : c.w), p1 = __dmul_rn(fwd ? dh : du, c.y);
+                        const double p2 = __dmul_rn(du, fwd ? c.z : c.x), p3 = __dmul_rn(dh, fwd ? c.w : c.z);
+                        good &= ((u32)__double2hiint(p0) - w_lo < w_span) & ((u32)__double2hiint(p1) - w_lo < w_span) &
+                                ((u32)__double2hiint(p2) - w_lo < w_span) & ((u32)__double2hiint(p3) - w_lo < w_span);
+                        const float a = __fadd_rn(__double2float_rn(p0), __double2float_rn(p1));
+                        const float b = __fadd_rn(__double2float_rn(p2), __double2float_rn(p3));
+                        if (fwd) { uf = a; hf = b; } else { hf = a; uf = b; }
+                        res[j0 + q] = BF{hf, h.e};
+                    }
+                    ok = good != 0u;
+                    if (ok) { u.f = uf; h.f = hf; }
+                }
+                if (!ok)
+                    for (u32 q = 0; q < HMM_SPEC; ++q) exact_step(j0 + q);
             }
+            for (; j0 < cnt; ++j0) exact_step(j0);
         }
         __syncwarp();
         if (lane < cnt) {
