@@ -269,6 +269,11 @@ int mcu_test_sort_pairs(void* keys, uint32_t* vals, uint64_t n, int key_bytes, i
  * per thread, register resident, one full-device launch timed with CUDA events.  *gops_out = thread-level integer instructions / s / 1e9
  * (ptxas fuses every add+max pair of the loop into one VIADDMNMX: one instruction, two operations). */
 int mcu_test_int32_peak(double* gops_out, float* ms_out);
+/* HomologyHMM, few long strings (one warp per chain, csrc/hmm.cu): of the last mcu_hmm_batch call, out3[0] = columns the chains
+ * stepped through (both directions), out3[1] = chain rounds (a round ends at a column whose exponents move or whose FP32 products are
+ * hazardous), out3[2] = columns that fell back from the FP32 form of the recurrence to the operation-by-operation FP64 form.
+ * MAUVE_CUDA_HMM_FP64=1 in the environment sends every column down the FP64 form (A/B in the tests). */
+int mcu_test_hmm_counters(uint64_t* out3);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

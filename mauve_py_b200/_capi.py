@@ -29,7 +29,7 @@ SYMBOLS = [
     "mcu_comm_unique_id", "mcu_comm_init", "mcu_comm_destroy", "mcu_comm_rank", "mcu_comm_world", "mcu_comm_barrier",
     "mcu_comm_allreduce_f64", "mcu_comm_gather_bytes", "mcu_device_synchronize",
     "mcu_session_upload_sharded", "mcu_session_run_sharded", "mcu_find_mums_sharded",
-    "mcu_test_sort_pairs", "mcu_test_int32_peak",
+    "mcu_test_sort_pairs", "mcu_test_int32_peak", "mcu_test_hmm_counters",
 ]
 
 
@@ -112,6 +112,7 @@ def lib():
     L.mcu_anchor_scores.argtypes = [vp, u64, vp, u64, u64, vp, vp, vp, u64, vp, u64, vp, i32, vp, vp]
     L.mcu_test_sort_pairs.argtypes = [vp, vp, u64, i32, i32]
     L.mcu_test_int32_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    L.mcu_test_hmm_counters.argtypes = [C.c_void_p]
     _lib = L
     return L
 

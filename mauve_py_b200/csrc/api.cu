@@ -516,6 +516,17 @@ int mcu_hmm_batch(uint64_t n, const char* sym, const uint64_t* off, const double
     return hmm_batch(n, sym, off, params, pred_out, post_out, device_ms);
 }
 
+int mcu_test_hmm_counters(uint64_t* out3)
+{
+    if (!out3) return MCU_EINVAL;
+    u64 c[3];
+    hmm_last_counters(c);
+    out3[0] = c[0];
+    out3[1] = c[1];
+    out3[2] = c[2];
+    return MCU_OK;
+}
+
 int mcu_nw_batch_wild(uint64_t n, const char* a, const uint64_t* a_off, const char* b, const uint64_t* b_off, const uint64_t* path_off,
                       char* path_out, uint32_t* path_len, float* score, float* device_ms)
 {

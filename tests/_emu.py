@@ -12,7 +12,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "mauve_py_b200", "csrc")
 OUT = os.path.join(ROOT, "tests", "_emu", "libmcu_emu.so")
-SOURCES = ["sol.cu", "dpwild.cu"]
+SOURCES = ["sol.cu", "dpwild.cu", "hmm.cu"]
 
 _lib = None
 
@@ -37,6 +37,12 @@ def emu():
     L.emu_anchor_scores.restype = None
     L.emu_nw_wild.argtypes = [C.c_char_p, C.c_uint, C.c_char_p, C.c_uint, vp, vp]
     L.emu_nw_wild.restype = C.c_longlong
+    L.emu_hmm_chain.argtypes = [vp, u64, vp, C.c_int, vp, vp, vp]
+    L.emu_hmm_chain.restype = None
+    L.emu_hmm_run.argtypes = [vp, u64, vp, vp, vp, vp]
+    L.emu_hmm_run.restype = C.c_int
+    L.emu_hmm_fprod.argtypes = [vp, vp, u64, vp]
+    L.emu_hmm_fprod.restype = None
     _lib = L
     return L
 

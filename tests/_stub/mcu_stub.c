@@ -96,6 +96,16 @@ int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out,
 /* regions with DNA wildcard columns (CudaGlobalAlign.h, seams with MAUVE_CUDA_WILD=1) */
 long long orc_nw_align_f(const char* a, unsigned la, const char* b, unsigned lb, char* path_out, float* score_out);
 static unsigned long long g_nwf_problems = 0;
+int orc_hmm_run(const char* sym, unsigned long long len, const double* p, char* pred_out, double* post_out);
+int mcu_hmm_batch(uint64_t n, const char* sym, const uint64_t* off, const double* params, char* pred_out, double* post_out, float* device_ms)
+{
+    uint64_t i;
+    for (i = 0; i < n; ++i)
+        if (orc_hmm_run(sym + off[i], off[i + 1] - off[i], params, pred_out + off[i], post_out ? post_out + off[i] : NULL) != 0) return -3;
+    if (device_ms) *device_ms = 1.0f;
+    return 0;
+}
+
 int mcu_nw_batch_wild(uint64_t n, const char* a, const uint64_t* a_off, const char* b, const uint64_t* b_off, const uint64_t* path_off, char* path_out,
                       uint32_t* path_len, float* score, float* device_ms)
 {

@@ -267,6 +267,35 @@ def test_hmm_batch_vs_oracle(mp, orc):
     assert e.value.code == _capi.MCU_EINVAL
 
 
+def test_hmm_long_string_fp32_chain(mp, orc, monkeypatch):
+    """ONE long string (what progressiveMauve really asks for): the warp chain's FP32 form of the recurrence (csrc/hmm.cu) gives the
+    posteriors of the operation-by-operation FP64 form bit for bit, takes the FP64 form at a handful of hazardous columns only, and
+    both equal the reference's run() on a prefix the oracle finishes quickly"""
+    import ctypes as C
+    params = mp.libmems.hmm_params(0.5, 0.0, 0.0, 0.0)
+    n = 2_000_000
+    s = synth.hmm_string(n, seed=77, block=2500)
+    c3 = np.zeros(3, dtype=np.uint64)
+    preds, posts, ms_fast = mp.run_batch([s], params, want_posterior=True)
+    assert mp.lib().mcu_test_hmm_counters(c3.ctypes.data) == 0
+    assert int(c3[0]) == 2 * (n - 1)
+    assert 0 < int(c3[2]) < n // 200           # hazardous columns exist and are rare
+    assert int(c3[1]) < n // 4                 # chain rounds: far fewer than columns
+    monkeypatch.setenv("MAUVE_CUDA_HMM_FP64", "1")
+    preds64, posts64, ms_64 = mp.run_batch([s], params, want_posterior=True)
+    assert mp.lib().mcu_test_hmm_counters(c3.ctypes.data) == 0
+    assert int(c3[2]) == 2 * (n - 1)
+    monkeypatch.delenv("MAUVE_CUDA_HMM_FP64")
+    assert preds[0] == preds64[0]
+    assert np.array_equal(posts[0].view(np.uint64), posts64[0].view(np.uint64))
+    print("hmm 2M columns: FP32 chain %.1f ms, FP64 chain %.1f ms" % (ms_fast, ms_64))
+    m = 300_000
+    preds, posts, _ = mp.run_batch([s[:m]], params, want_posterior=True)
+    opred, opost = orc.hmm_run(s[:m], params)
+    _check_hmm(preds[0], posts[0], opred, opost)
+    assert np.array_equal(posts[0].view(np.uint64), np.asarray(opost).view(np.uint64))
+
+
 def test_hmm_scan_mode_within_tolerance(mp, orc, monkeypatch):
     """MAUVE_CUDA_HMM_SCAN=1: the column-parallel evaluation in double stays within the 1e-5 bar for strings up to ~10 k columns"""
     monkeypatch.setenv("MAUVE_CUDA_HMM_SCAN", "1")
