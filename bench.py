@@ -556,12 +556,16 @@ def main():
         step_ms.append(1e3 * (time.perf_counter() - ts))
         stage += sess.stage_ms
         dev_ms_steps.append(float(sess.stage_ms[6]))
+    t_loop = time.perf_counter() - t0
     comm.barrier()
     dt = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
     launches = sess.launch_count() - launches0
     stats = sess.stats.copy()
-    dt = comm.allreduce([dt], mdist.MAX)[0]
+    dt, loop_max = comm.allreduce([dt, t_loop], mdist.MAX)
+    loop_min = comm.allreduce([t_loop], mdist.MIN)[0]
+    rank_loop_ms = {"max": 1e3 * loop_max / args.steps, "min": 1e3 * loop_min / args.steps,
+                    "closing_barrier_ms_total": 1e3 * (dt - loop_max)}   # per-step loop time of the slowest / fastest rank; what the closing barrier added to the K steps
     ms_per_step = 1e3 * dt / args.steps
     value = nbases / 1e6 / (dt / args.steps)
     stage /= args.steps
@@ -746,7 +750,7 @@ def main():
         "metric": "Mbp/s seed+match+extend", "value": value, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64" if kb == 8 else "u32",
         "data": "synthetic", "config": config_dict(args, weight, seed), "matches": int(nmatch), "seed_pairs": int(stats[0]),
-        "device_ms_per_step": dev_ms, "step_ms": spread(step_ms), "device_step_ms": spread(dev_ms_steps), "parity": parity,
+        "device_ms_per_step": dev_ms, "rank_loop_ms": rank_loop_ms, "step_ms": spread(step_ms), "device_step_ms": spread(dev_ms_steps), "parity": parity,
         "timing": "value/ms_per_step: K steps between barrier + device synchronisation on both sides, max over ranks (a step has host-visible "
                   "synchronisation points of its own, so this is the whole step); step_ms: host clock per step on rank 0; device_ms_per_step, roofline "
                   "launch_ms and kernel_ms: CUDA events recorded by the library on the stream it launches on (rank 0; at N > 1 the whole step incl. "

@@ -1387,7 +1387,7 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     // bk_group3 keeps <= 28 key bits that differ inside a final bucket next to four flag bits; wider keys (not reached by the seed
     // tables at sizes that take this path) keep bk_group.  MAUVE_CUDA_GROUP_V1 / MAUVE_CUDA_GROUP_VARIANT: A/B switches.
     static const bool group_v1_env = getenv("MAUVE_CUDA_GROUP_V1") != nullptr;
-    static const int variant = getenv("MAUVE_CUDA_GROUP_VARIANT") ? atoi(getenv("MAUVE_CUDA_GROUP_VARIANT")) : 0;
+    static const int variant = getenv("MAUVE_CUDA_GROUP_VARIANT") ? atoi(getenv("MAUVE_CUDA_GROUP_VARIANT")) : 3;   // measured (100 Mbp pair): 3: 1.64 ms, 5: 1.65, 1: 1.83, 4: 1.91, 0: 2.34
     const bool group_v1 = group_v1_env || pl.rem1 - pl.d2 > G3_MAX_KEY_BITS;
     if (nfinal && group_v1) bk_group_kernel<<<(unsigned)nfinal, BK_THREADS, 0, st>>>(ga, pl);
     else if (nfinal) {
@@ -1401,10 +1401,10 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
         switch (variant) {
         case 1: MCU_TRY(launch(bk_group3_kernel<12, 2, 3>, sizeof(G3Smem<12, 2>), 3)); break;
         case 2: MCU_TRY(launch(bk_group3_kernel<11, 2, 5>, sizeof(G3Smem<11, 2>), 5)); break;
-        case 3: MCU_TRY(launch(bk_group3_kernel<12, 1, 5>, sizeof(G3Smem<12, 1>), 5)); break;
+        case 0: MCU_TRY(launch(bk_group3_kernel<11, 2, 4>, sizeof(G3Smem<11, 2>), 4)); break;
         case 4: MCU_TRY(launch(bk_group3_kernel<11, 1, 6>, sizeof(G3Smem<11, 1>), 6)); break;
         case 5: MCU_TRY(launch(bk_group3_kernel<12, 1, 4>, sizeof(G3Smem<12, 1>), 4)); break;
-        default: MCU_TRY(launch(bk_group3_kernel<11, 2, 4>, sizeof(G3Smem<11, 2>), 4)); break;
+        default: MCU_TRY(launch(bk_group3_kernel<12, 1, 5>, sizeof(G3Smem<12, 1>), 5)); break;   // one buffer, 4096-slot table, 5 CTAs per SM
         }
     }
     MCU_CUDA(cudaEventRecord(s.kev[5], st));

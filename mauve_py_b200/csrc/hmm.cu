@@ -411,15 +411,21 @@ HMM_HD double hmm_posterior_value(BF a, BF b, BF p, const HmmExactModel& m)
 }
 
 // One column in FP32, any exponents.  c / l: high and low parts of the coefficients in role order (U' = c0 u + c1 h, H' = c2 u + c3 h;
-// the sum is symmetric, so Backward is Forward with c1 and c2 exchanged).  Returns false, leaving u and h alone, on a hazard.
-HMM_HD bool hmm_float_step(BF& u, BF& h, const float c[4], const float l[4])
+// the sum is symmetric, so Backward is Forward with c1 and c2 exchanged).  CHECK: returns false, leaving u and h alone, on a hazard.
+template <bool CHECK>
+HMM_HD bool hmm_float_step_t(BF& u, BF& h, const float c[4], const float l[4])
 {
     const float r0 = hmm_fprod(u.f, c[0], l[0]), r1 = hmm_fprod(h.f, c[1], l[1]);
     const float r2 = hmm_fprod(u.f, c[2], l[2]), r3 = hmm_fprod(h.f, c[3], l[3]);
     u32 w0, w1, w2, w3;
-    const u32 hz = hmm_prod_check(u.f, c[0], l[0], r0, w0) | hmm_prod_check(h.f, c[1], l[1], r1, w1) |
-                   hmm_prod_check(u.f, c[2], l[2], r2, w2) | hmm_prod_check(h.f, c[3], l[3], r3, w3);
-    if (hz) return false;
+    if (CHECK) {
+        const u32 hz = hmm_prod_check(u.f, c[0], l[0], r0, w0) | hmm_prod_check(h.f, c[1], l[1], r1, w1) |
+                       hmm_prod_check(u.f, c[2], l[2], r2, w2) | hmm_prod_check(h.f, c[3], l[3], r3, w3);
+        if (hz) return false;
+    } else {
+        w0 = (u32)(H_F2U(r0) < BF_LO_BITS); w1 = (u32)(H_F2U(r1) < BF_LO_BITS);
+        w2 = (u32)(H_F2U(r2) < BF_LO_BITS); w3 = (u32)(H_F2U(r3) < BF_LO_BITS);
+    }
     const int e0 = u.e - (int)w0, e1 = h.e - (int)w1, e2 = u.e - (int)w2, e3 = h.e - (int)w3;
     const int eu = e0 > e1 ? e0 : e1, eh = e2 > e3 ? e2 : e3;
     const float nu = H_FADD(H_FMUL(r0, hmm_mexp(u.e - eu)), H_FMUL(r1, hmm_mexp(h.e - eu)));
@@ -428,34 +434,40 @@ HMM_HD bool hmm_float_step(BF& u, BF& h, const float c[4], const float l[4])
     h = BF{nh, eh};
     return true;
 }
+HMM_HD bool hmm_float_step(BF& u, BF& h, const float c[4], const float l[4]) { return hmm_float_step_t<true>(u, h, c, l); }
 
-// The chain's form of the column: exponents assumed to STAY as they are (ue, he; d = ue - he in {-1, 0, 1}), which fixes the
-// multipliers of (3) to M(0), m1 = M(-d), m2 = M(d), M(0).  PLAIN: d = 0, no multiplications.  Dependency chain FMUL -> FFMA ->
-// (FMUL ->) FADD.  hmm_regime_ok says afterwards whether the assumption and every product held for the column.
-template <bool PLAIN>
-HMM_HD void hmm_regime_step(float& u, float& h, const float c[4], const float l[4], float m1, float m2)
+// The chain's form of the column: exponents assumed to STAY as they are (ue, he; D = ue - he in {-1, 0, 1}), which fixes the
+// multipliers of (3): U' = r0 + r1 M(-D), H' = r2 M(D) + r3.  Dependency chain FMUL -> FFMA -> (FMUL ->) FADD.  The assumption holds
+// for a column unless an exponent drops there; what the chain needs to notice that costs two min / max instructions beside the chain:
+//   D =  0: holds iff max(r0, r1) >= 1e-18 and max(r2, r3) >= 1e-18 (U drops iff r0 and r1 are both below; same for H)
+//   D = -1: holds iff r1 < 1e-18 <= r3          D = +1: holds iff r2 < 1e-18 <= r0
+// hmm_regime_metric folds that into one number per column (an event iff it is below 1e-18).  Products within 16 ulp of 1e-18 and every
+// rounding hazard are left to the re-examination of the column (hmm_float_step / hmm_exact_step).
+// the event metric of a column: the regime assumption holds for it iff the metric is >= 1e-18
+template <int D>
+HMM_HD float hmm_regime_metric(float r0, float r1, float r2, float r3)
 {
-    const float r0 = hmm_fprod(u, c[0], l[0]), r1 = hmm_fprod(h, c[1], l[1]);
-    const float r2 = hmm_fprod(u, c[2], l[2]), r3 = hmm_fprod(h, c[3], l[3]);
-    if (PLAIN) {
-        u = H_FADD(r0, r1);
-        h = H_FADD(r2, r3);
-    } else {
-        u = H_FADD(r0, H_FMUL(r1, m1));
-        h = H_FADD(H_FMUL(r2, m2), r3);
-    }
+    if (D == 0) return fminf(fmaxf(r0, r1), fmaxf(r2, r3));
+    if (D < 0) return r1 >= 1.0e-18f ? 0.f : r3;
+    return r2 >= 1.0e-18f ? 0.f : r0;
 }
 
-HMM_HD bool hmm_regime_ok(float u, float h, int ue, int he, const float c[4], const float l[4])
+template <int D>
+HMM_HD void hmm_regime_step(float& u, float& h, const float c[4], const float l[4], float& metric)
 {
     const float r0 = hmm_fprod(u, c[0], l[0]), r1 = hmm_fprod(h, c[1], l[1]);
     const float r2 = hmm_fprod(u, c[2], l[2]), r3 = hmm_fprod(h, c[3], l[3]);
-    u32 w0, w1, w2, w3;
-    const u32 hz = hmm_prod_check(u, c[0], l[0], r0, w0) | hmm_prod_check(h, c[1], l[1], r1, w1) |
-                   hmm_prod_check(u, c[2], l[2], r2, w2) | hmm_prod_check(h, c[3], l[3], r3, w3);
-    const int e0 = ue - (int)w0, e1 = he - (int)w1, e2 = ue - (int)w2, e3 = he - (int)w3;
-    const int eu = e0 > e1 ? e0 : e1, eh = e2 > e3 ? e2 : e3;
-    return hz == 0u && eu == ue && eh == he;
+    if (D == 0) {
+        u = H_FADD(r0, r1);
+        h = H_FADD(r2, r3);
+    } else if (D < 0) {
+        u = H_FADD(r0, H_FMUL(r1, 2.028240960365167e+31f));
+        h = H_FADD(H_FMUL(r2, 4.930380657631324e-32f), r3);
+    } else {
+        u = H_FADD(r0, H_FMUL(r1, 4.930380657631324e-32f));
+        h = H_FADD(H_FMUL(r2, 2.028240960365167e+31f), r3);
+    }
+    metric = hmm_regime_metric<D>(r0, r1, r2, r3);
 }
 
 // ---- tables shared by the kernels and the test-only host drivers ----
@@ -544,147 +556,266 @@ __global__ void __launch_bounds__(64) hmm_exact_chain_kernel(const u8* __restric
     if (bad) atomicOr(err, 1u);
 }
 
-// Few, long strings: one warp per (string, direction), a block of 32 columns at a time.  Lane 0 runs the serial recurrence in
-// its FP32 regime form (hmm_regime_step: 12 or 16 cycles of dependent latency per column) and parks the state after every column in
-// shared memory; then the 32 lanes each re-examine one column from the state it started with (hmm_regime_ok).  The first column that
-// did not hold (an exponent moves there, about once in 25 columns, or a product is hazardous) is evaluated by ITS lane with
-// hmm_float_step, or hmm_exact_step on a hazard, and the chain resumes behind it.  The other lanes also keep memory out of the
-// chain: symbols are fetched one block ahead with one coalesced load, the coefficients of every column are looked up into shared
-// memory, and the 32 results leave with one coalesced write.  MAUVE_CUDA_HMM_FP64=1 (tests): every column through hmm_exact_step.
-template <bool PLAIN>
-__device__ __forceinline__ void hmm_chain_run(const float4* __restrict__ chi, const float4* __restrict__ clo, float2* __restrict__ st, u32 j0, u32 cnt,
-                                              float uf, float hf, float m1, float m2)
+// Few, long strings: one CTA of two warps per (string, direction), a block of 32 columns at a time, three blocks in flight.
+//   warp 0, lane 0   runs the serial recurrence of block k in its FP32 regime form (hmm_regime_step: 12 or 16 cycles of dependent
+//                    latency per column), eight columns per group with their coefficients in registers, parking the state behind
+//                    every column in shared memory.  When a group's trackers report that an exponent dropped (about once in 19
+//                    columns) it finds the column, evaluates it with the general FP32 step and carries on behind it in the new regime.
+//   warp 1           meanwhile (a) re-examines block k - 1, one column per lane, from the state parked in front of it, with
+//                    hmm_float_step -- or hmm_exact_step when a product of it is hazardous --, (b) writes that block's 32 results
+//                    with one coalesced store, (c) looks up the coefficients of block k + 1 (symbols fetched two blocks ahead).
+// A column whose parked result is not what warp 1 gets (a hazard that mattered: about one column in a million) is corrected; the
+// chain is then taken up again behind it and block k, which started from the wrong state, is run again.
+// MAUVE_CUDA_HMM_FP64=1 (tests): every column through hmm_exact_step.
+struct HmmBlockBuf {
+    float4 chi[40], clo[40];  // coefficients of the block's columns, role order, high and low parts; rows 32.. and the rows past a short
+                              // block's end: identity (a group of eight may run past the end)
+    float4 st[41];            // st[j] = (u.f, h.f, bits of u.e, bits of h.e) in front of column j, st[j + 1] behind it
+    u8 xs[32];
+};
+struct HmmWarpSmem {
+    double te[8][4];          // role order
+    float4 chi_s[8], clo_s[8];
+    HmmBlockBuf b[3];
+    int bad;                  // first corrected column of the block re-examined in this iteration, or -1
+};
+
+// eight columns from column j on (rows past the block's end hold identity coefficients: nothing happens there); returns the first
+// of them (0..7) whose regime assumption failed -- what was computed from there on is void -- or 8.  Beside the chain the group costs
+// one min per column: for D = 0 an exponent can only drop where U' or H' comes out below 2e-18 (both products below 1e-18), for
+// D != 0 the metric is a product itself; the columns are looked at one by one only when that minimum says so.
+template <int D>
+__device__ __forceinline__ u32 hmm_chain_group(HmmBlockBuf& bb, u32 j, float uf, float hf, float eu, float eh)
 {
-    if (j0 == 0 && cnt == 32) {
+    float4 c[8], l[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float4 c = chi[j], l = clo[j];
-            const float cc[4] = {c.x, c.y, c.z, c.w}, ll[4] = {l.x, l.y, l.z, l.w};
-            hmm_regime_step<PLAIN>(uf, hf, cc, ll, m1, m2);
-            st[j + 1] = make_float2(uf, hf);
-        }
-    } else {
-        float4 c = chi[j0], l = clo[j0];
-        for (u32 j = j0; j < cnt; ++j) {
-            const float4 cn = chi[j + 1], ln = clo[j + 1];   // one column ahead (the arrays have a spare row)
-            const float cc[4] = {c.x, c.y, c.z, c.w}, ll[4] = {l.x, l.y, l.z, l.w};
-            hmm_regime_step<PLAIN>(uf, hf, cc, ll, m1, m2);
-            st[j + 1] = make_float2(uf, hf);
-            c = cn;
-            l = ln;
-        }
+    for (int q = 0; q < 8; ++q) {
+        c[q] = bb.chi[j + q];
+        l[q] = bb.clo[j + q];
+    }
+    float lo = 3.0e38f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float cc[4] = {c[q].x, c[q].y, c[q].z, c[q].w}, ll[4] = {l[q].x, l[q].y, l[q].z, l[q].w};
+        float metric;
+        hmm_regime_step<D>(uf, hf, cc, ll, metric);
+        bb.st[j + q + 1] = make_float4(uf, hf, eu, eh);
+        lo = D == 0 ? fminf(lo, fminf(uf, hf)) : fminf(lo, metric);
+    }
+    constexpr float two_l = 2.0f * 1.0e-18f;   // exactly twice the float 1e-18f: two products below 1e-18f sum to less than this
+    if (lo >= (D == 0 ? two_l : 1.0e-18f)) return 8u;
+    for (u32 q = 0; q < 8; ++q) {
+        const float4 v = bb.st[j + q], w = bb.st[j + q + 1];
+        if (D == 0 && w.x >= two_l && w.y >= two_l) continue;
+        const float4 cq = bb.chi[j + q], lq = bb.clo[j + q];
+        const float r0 = hmm_fprod(v.x, cq.x, lq.x), r1 = hmm_fprod(v.y, cq.y, lq.y), r2 = hmm_fprod(v.x, cq.z, lq.z), r3 = hmm_fprod(v.y, cq.w, lq.w);
+        if (hmm_regime_metric<D>(r0, r1, r2, r3) < 1.0e-18f) return q;
+    }
+    return 8u;
+}
+
+__device__ __forceinline__ void hmm_lane0_exact(HmmWarpSmem& sm, HmmBlockBuf& bb, u32 cnt, bool fwd, const HmmExactModel& m)
+{
+    const float4 s0 = bb.st[0];
+    BF u = BF{s0.x, __float_as_int(s0.z)}, h = BF{s0.y, __float_as_int(s0.w)};
+    for (u32 j = 0; j < cnt; ++j) {
+        hmm_exact_step(u, h, sm.te[bb.xs[j]], fwd, m);
+        bb.st[j + 1] = make_float4(u.f, h.f, __int_as_float(u.e), __int_as_float(h.e));
     }
 }
 
-__global__ void __launch_bounds__(32) hmm_exact_chain_warp_kernel(const u8* __restrict__ sym, const u64* __restrict__ off, u32 n, HmmExactModel m, HmmFastTab ft,
+// warp 0, lane 0: columns [start, cnt) of the block from the state parked at st[start]
+__device__ __forceinline__ void hmm_lane0_chain(HmmBlockBuf& bb, u32 start, u32 cnt)
+{
+    const float4 s0 = bb.st[start];
+    float uf = s0.x, hf = s0.y;
+    int ue = __float_as_int(s0.z), he = __float_as_int(s0.w);
+    u32 j = start;
+    while (j < cnt) {
+        const int d = ue - he;
+        if (d >= -1 && d <= 1) {
+            const float eu = __int_as_float(ue), eh = __int_as_float(he);
+            const u32 q = d == 0 ? hmm_chain_group<0>(bb, j, uf, hf, eu, eh) : (d < 0 ? hmm_chain_group<-1>(bb, j, uf, hf, eu, eh) : hmm_chain_group<1>(bb, j, uf, hf, eu, eh));
+            j += q;
+            const float4 v = bb.st[j];
+            uf = v.x;
+            hf = v.y;
+            if (q == 8u || j >= cnt) continue;   // the whole group stands
+        }
+        // this column on its own (an exponent moves here), from the state in front of it
+        BF u = BF{uf, ue}, h = BF{hf, he};
+        const float4 c = bb.chi[j], l = bb.clo[j];
+        const float cc[4] = {c.x, c.y, c.z, c.w}, ll[4] = {l.x, l.y, l.z, l.w};
+        hmm_float_step_t<false>(u, h, cc, ll);
+        uf = u.f; hf = h.f; ue = u.e; he = h.e;
+        ++j;
+        bb.st[j] = make_float4(uf, hf, __int_as_float(ue), __int_as_float(he));
+    }
+}
+
+// warp 1: columns [start, cnt) of a block, one per lane; returns the first column whose parked result had to be corrected (the lane
+// of that column has written its own), or 32
+__device__ __forceinline__ u32 hmm_reexamine(HmmWarpSmem& sm, HmmBlockBuf& bb, u32 lane, u32 start, u32 cnt, bool fwd, const HmmExactModel& m,
+                                             unsigned long long& n_exact)
+{
+    bool ok = true;
+    BF u, h;
+    if (lane >= start && lane < cnt) {
+        const float4 v = bb.st[lane], w = bb.st[lane + 1];
+        const float4 c = bb.chi[lane], l = bb.clo[lane];
+        const float cc[4] = {c.x, c.y, c.z, c.w}, ll[4] = {l.x, l.y, l.z, l.w};
+        u = BF{v.x, __float_as_int(v.z)};
+        h = BF{v.y, __float_as_int(v.w)};
+        if (!hmm_float_step(u, h, cc, ll)) {
+            hmm_exact_step(u, h, sm.te[bb.xs[lane]], fwd, m);
+            ++n_exact;
+        }
+        ok = __float_as_uint(u.f) == __float_as_uint(w.x) && __float_as_uint(h.f) == __float_as_uint(w.y) && u.e == __float_as_int(w.z) && h.e == __float_as_int(w.w);
+    }
+    const u32 badmask = __ballot_sync(0xffffffffu, !ok);
+    if (badmask == 0u) return 32u;
+    const u32 jb = (u32)__ffs((int)badmask) - 1u;
+    if (lane == jb) bb.st[jb + 1] = make_float4(u.f, h.f, __int_as_float(u.e), __int_as_float(h.e));
+    __syncwarp();
+    return jb;
+}
+
+__global__ void __launch_bounds__(64) hmm_exact_chain_warp_kernel(const u8* __restrict__ sym, const u64* __restrict__ off, u32 n, HmmExactModel m, HmmFastTab ft,
                                                                  int force_exact, BF* __restrict__ fh, BF* __restrict__ bh, BF* __restrict__ total,
                                                                  u32* __restrict__ err, unsigned long long* __restrict__ counters)
 {
-    __shared__ double te_s[8][4];          // role order
-    __shared__ float4 chi_s[8], clo_s[8];  // role order
-    __shared__ float4 chi[33], clo[33];    // per column of the block (+ a spare row for the look-ahead)
-    __shared__ u8 xs[32];
-    __shared__ float2 st[33];              // st[j] = (u, h) before column j of the block, st[j + 1] after it
-    __shared__ BF res[32];
-    const u32 lane = threadIdx.x;
+    __shared__ HmmWarpSmem sm;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 s = blockIdx.x >> 1;
     const bool fwd = (blockIdx.x & 1) == 0;
     const u64 beg = off[s], end = off[s + 1];
     if (end == beg) return;
-    {
+    if (warp == 0) {
         const u32 x = lane >> 2, k = lane & 3, src = (fwd || k == 0 || k == 3) ? k : 3 - k;
-        te_s[x][k] = m.te[x][src];
-        reinterpret_cast<float*>(chi_s)[lane] = ft.hi[x][src];
-        reinterpret_cast<float*>(clo_s)[lane] = ft.lo[x][src];
-        if (lane == 0) chi[32] = clo[32] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sm.te[x][k] = m.te[x][src];
+        reinterpret_cast<float*>(sm.chi_s)[lane] = ft.hi[x][src];
+        reinterpret_cast<float*>(sm.clo_s)[lane] = ft.lo[x][src];
     }
-    __syncwarp();
     const u64 len = end - beg;
     u32 bad = 0;
     const BF one = BF{1.0f, 0};
-    BF h, u;   // every lane carries the state; it moves in lockstep (shared memory / shuffles below)
-    if (fwd) {
-        const u32 x = sym_index(__ldg(sym + beg), bad);
-        u = bf_dprod(one, m.first[x][0], m);
-        h = bf_dprod(one, m.first[x][1], m);
-        if (lane == 0) fh[beg] = h;
-    } else {
-        h = bf_dprod(one, m.stop[1], m);
-        u = bf_dprod(one, m.stop[0], m);
-        if (lane == 0) bh[end - 1] = h;
+    if (threadIdx.x == 0) {
+        BF h, u;
+        if (fwd) {
+            const u32 x = sym_index(__ldg(sym + beg), bad);
+            u = bf_dprod(one, m.first[x][0], m);
+            h = bf_dprod(one, m.first[x][1], m);
+            fh[beg] = h;
+        } else {
+            h = bf_dprod(one, m.stop[1], m);
+            u = bf_dprod(one, m.stop[0], m);
+            bh[end - 1] = h;
+        }
+        sm.b[0].st[0] = make_float4(u.f, h.f, __int_as_float(u.e), __int_as_float(h.e));
+        sm.bad = -1;
     }
     const u64 steps = len - 1;
+    const u64 nb = (steps + 31) / 32;
     auto sym_of_step = [&](u64 k) -> u64 { return fwd ? beg + 1 + k : end - 1 - k; };  // index of the symbol step k consumes
+    auto cnt_of = [&](u64 k) -> u32 { return (u32)min((u64)32, steps - k * 32); };
+    __syncthreads();
+    // warp 1 stages block 0 and holds the symbols of block 1
     u32 xn = 0;
-    if (lane < steps) xn = sym_index(__ldg(sym + sym_of_step(lane)), bad);
-    unsigned long long n_rounds = 0, n_exact = 0;
-    for (u64 k0 = 0; k0 < steps; k0 += 32) {
-        const u32 cnt = (u32)min((u64)32, steps - k0);
-        const u32 x = xn;
-        if (k0 + 32 + lane < steps) xn = sym_index(__ldg(sym + sym_of_step(k0 + 32 + lane)), bad);  // next block, in flight during this one
-        chi[lane] = chi_s[x];
-        clo[lane] = clo_s[x];
-        xs[lane] = (u8)x;
-        __syncwarp();
-        u32 j0 = 0;
-        while (j0 < cnt) {
-            ++n_rounds;
-            const int d = u.e - h.e;
-            u32 jbad;   // first column of [j0, cnt) that needs its own evaluation
-            if (d >= -1 && d <= 1 && !force_exact) {
-                if (lane == 0) {
-                    st[j0] = make_float2(u.f, h.f);
-                    if (d == 0) hmm_chain_run<true>(chi, clo, st, j0, cnt, u.f, h.f, 1.f, 1.f);
-                    else hmm_chain_run<false>(chi, clo, st, j0, cnt, u.f, h.f, hmm_mexp(-d), hmm_mexp(d));
-                }
-                __syncwarp();
-                bool ok = true;
-                if (lane >= j0 && lane < cnt) {
-                    const float2 v = st[lane];
-                    const float4 c = chi[lane], l = clo[lane];
-                    const float cc[4] = {c.x, c.y, c.z, c.w}, ll[4] = {l.x, l.y, l.z, l.w};
-                    ok = hmm_regime_ok(v.x, v.y, u.e, h.e, cc, ll);
-                }
-                const u32 badmask = __ballot_sync(0xffffffffu, !ok);
-                jbad = badmask ? (u32)__ffs((int)badmask) - 1u : cnt;
-                if (lane >= j0 && lane < jbad) res[lane] = BF{st[lane + 1].y, h.e};
-                if (jbad > j0) {
-                    const float2 v = st[jbad];
-                    u.f = v.x;
-                    h.f = v.y;
-                }
-            } else
-                jbad = j0;
-            if (jbad < cnt) {   // the column's own lane evaluates it from the state in front of it, then everybody takes the result
-                if (lane == jbad) {
-                    const float4 c = chi[lane], l = clo[lane];
-                    const float cc[4] = {c.x, c.y, c.z, c.w}, ll[4] = {l.x, l.y, l.z, l.w};
-                    if (force_exact || !hmm_float_step(u, h, cc, ll)) {
-                        hmm_exact_step(u, h, te_s[xs[lane]], fwd, m);
-                        ++n_exact;
-                    }
-                    res[lane] = h;
-                }
-                u.f = __shfl_sync(0xffffffffu, u.f, jbad);
-                u.e = __shfl_sync(0xffffffffu, u.e, jbad);
-                h.f = __shfl_sync(0xffffffffu, h.f, jbad);
-                h.e = __shfl_sync(0xffffffffu, h.e, jbad);
+    if (warp == 1) {
+        u32 x0 = 0;
+        if (lane < steps) x0 = sym_index(__ldg(sym + sym_of_step(lane)), bad);
+        if (32 + lane < steps) xn = sym_index(__ldg(sym + sym_of_step(32 + lane)), bad);
+        const float4 ident = make_float4(1.f, 0.f, 0.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        sm.b[0].chi[lane] = lane < steps ? sm.chi_s[x0] : ident;
+        sm.b[0].clo[lane] = lane < steps ? sm.clo_s[x0] : zero;
+        sm.b[0].xs[lane] = (u8)x0;
+        if (lane < 8)
+            for (int i = 0; i < 3; ++i) {
+                sm.b[i].chi[32 + lane] = ident;
+                sm.b[i].clo[32 + lane] = zero;
             }
-            j0 = jbad + 1;
-        }
-        __syncwarp();
-        if (lane < cnt) {
-            if (fwd) fh[beg + 1 + k0 + lane] = res[lane];
-            else bh[end - 2 - k0 - lane] = res[lane];
-        }
-        __syncwarp();
     }
-    if (fwd && lane == 0) {
+    __syncthreads();
+    unsigned long long n_rounds = 0, n_exact = 0;
+    bool skip_reexam = false;
+    for (u64 k = 0; k <= nb;) {
+        // ---- chain block k | re-examine block k - 1, store its results, stage block k + 1 ----
+        if (warp == 0) {
+            if (lane == 0 && k < nb) {
+                if (k) sm.b[k % 3].st[0] = sm.b[(k - 1) % 3].st[cnt_of(k - 1)];
+                if (force_exact) hmm_lane0_exact(sm, sm.b[k % 3], cnt_of(k), fwd, m);
+                else hmm_lane0_chain(sm.b[k % 3], 0, cnt_of(k));
+            }
+        } else {
+            ++n_rounds;
+            if (k >= 1 && !skip_reexam) {
+                HmmBlockBuf& pb = sm.b[(k - 1) % 3];
+                const u32 pc = cnt_of(k - 1);
+                u32 jb = 32u;
+                if (!force_exact) jb = hmm_reexamine(sm, pb, lane, 0, pc, fwd, m, n_exact);
+                else n_exact += lane < pc ? 1u : 0u;
+                if (jb < 32u) {
+                    if (lane == 0) sm.bad = (int)jb;
+                } else if (lane < pc) {
+                    const float4 r = pb.st[lane + 1];
+                    const BF out = BF{r.y, __float_as_int(r.w)};
+                    if (fwd) fh[beg + 1 + (k - 1) * 32 + lane] = out;
+                    else bh[end - 2 - (k - 1) * 32 - lane] = out;
+                }
+            }
+            if (k + 1 < nb && !skip_reexam) {   // (after a repair block k + 1 is staged already)
+                HmmBlockBuf& nbuf = sm.b[(k + 1) % 3];
+                const u32 x = xn;
+                if ((k + 2) * 32 + lane < steps) xn = sym_index(__ldg(sym + sym_of_step((k + 2) * 32 + lane)), bad);  // in flight during the next iteration
+                const bool live = (k + 1) * 32 + lane < steps;
+                nbuf.chi[lane] = live ? sm.chi_s[x] : make_float4(1.f, 0.f, 0.f, 1.f);
+                nbuf.clo[lane] = live ? sm.clo_s[x] : make_float4(0.f, 0.f, 0.f, 0.f);
+                nbuf.xs[lane] = (u8)x;
+            }
+        }
+        __syncthreads();
+        skip_reexam = false;
+        int jb = sm.bad;
+        if (jb >= 0) {
+            // ---- repair block k - 1 behind column jb: chain and re-examination take turns until the block stands ----
+            HmmBlockBuf& pb = sm.b[(k - 1) % 3];
+            const u32 pc = cnt_of(k - 1);
+            __syncthreads();
+            if (threadIdx.x == 0) sm.bad = -1;
+            while (jb >= 0) {
+                const u32 vstart = (u32)jb + 1u;
+                if (threadIdx.x == 0) hmm_lane0_chain(pb, vstart, pc);
+                __syncthreads();
+                if (warp == 1) {
+                    ++n_rounds;
+                    const u32 j2 = hmm_reexamine(sm, pb, lane, vstart, pc, fwd, m, n_exact);
+                    if (lane == 0) sm.bad = j2 < 32u ? (int)j2 : -1;
+                }
+                __syncthreads();
+                jb = sm.bad;
+                __syncthreads();
+                if (threadIdx.x == 0) sm.bad = -1;
+            }
+            if (warp == 1 && lane < pc) {
+                const float4 r = pb.st[lane + 1];
+                const BF out = BF{r.y, __float_as_int(r.w)};
+                if (fwd) fh[beg + 1 + (k - 1) * 32 + lane] = out;
+                else bh[end - 2 - (k - 1) * 32 - lane] = out;
+            }
+            __syncthreads();
+            skip_reexam = true;   // block k starts again from the corrected state; k - 1 is done and k + 1 is staged
+            continue;
+        }
+        ++k;
+    }
+    if (fwd && threadIdx.x == 0) {
+        const float4 r = nb ? sm.b[(nb - 1) % 3].st[cnt_of(nb - 1)] : sm.b[0].st[0];
+        BF u = BF{r.x, __float_as_int(r.z)}, h = BF{r.y, __float_as_int(r.w)};
         BF p = bf_dprod(u, m.stop[0], m);
         bf_sum_accum(p, bf_dprod(h, m.stop[1], m));
         total[s] = p;
     }
-    if (counters) {
+    if (counters && warp == 1) {
         n_exact += __shfl_xor_sync(0xffffffffu, n_exact, 16);
         n_exact += __shfl_xor_sync(0xffffffffu, n_exact, 8);
         n_exact += __shfl_xor_sync(0xffffffffu, n_exact, 4);
@@ -790,7 +921,7 @@ int hmm_batch(u64 n, const char* sym, const u64* off, const double* params, char
         MCU_CUDA(cudaMemsetAsync(st.err.as<u32>() + 2, 0, 24, s));
         // few chains: a warp each (latency-optimised); many chains: a thread each (throughput)
         if (2 * n <= (u64)sm_count() * 64)
-            hmm_exact_chain_warp_kernel<<<(unsigned)(2 * n), 32, 0, s>>>(st.sym.as<u8>(), st.off.as<u64>(), (u32)n, xm, ft, force_exact, st.fh.as<BF>(),
+            hmm_exact_chain_warp_kernel<<<(unsigned)(2 * n), 64, 0, s>>>(st.sym.as<u8>(), st.off.as<u64>(), (u32)n, xm, ft, force_exact, st.fh.as<BF>(),
                                                                          st.bh.as<BF>(), st.total.as<BF>(), st.err.as<u32>(),
                                                                          reinterpret_cast<unsigned long long*>(st.err.as<u32>() + 2));
         else
@@ -832,7 +963,8 @@ void hmm_last_counters(u64* out3)
 // while hmm_regime_ok lets it stand, hmm_float_step at the columns where it does not, hmm_exact_step at hazardous ones -- and,
 // beside it, hmm_exact_step at EVERY column from the same state (the truth).  out_f / out_e: the homologous-state bfloat after every
 // step (steps = n - 1, chain order).  counts[0] = columns carried by the regime step, counts[1] = columns evaluated by hmm_float_step,
-// counts[2] = columns where an accepted FP32 form (either) differs from the truth (must be 0), counts[3] = hazardous columns.
+// counts[2] = columns where an accepted FP32 form differs from the truth or the chain's two event tests disagree (must be 0),
+// counts[3] = hazardous columns, counts[4] = exponent drops the chain's trackers miss (the re-examination corrects them).
 extern "C" void emu_hmm_chain(const unsigned char* sym, unsigned long long n, const double* params21, int fwd, float* out_f, int* out_e,
                               unsigned long long* counts)
 {
@@ -841,7 +973,7 @@ extern "C" void emu_hmm_chain(const unsigned char* sym, unsigned long long n, co
     build_exact_model(params21, &m);
     HmmFastTab ft;
     build_fast_tab(m, &ft);
-    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    counts[0] = counts[1] = counts[2] = counts[3] = counts[4] = 0;
     if (n == 0) return;
     const BF one = BF{1.0f, 0};
     BF u, h;
@@ -870,11 +1002,18 @@ extern "C" void emu_hmm_chain(const unsigned char* sym, unsigned long long n, co
         BF gu = u, gh = h;
         const bool float_ok = hmm_float_step(gu, gh, ch, cl);
         if (float_ok && !same(gu, gh)) ++counts[2];
-        if (d >= -1 && d <= 1 && hmm_regime_ok(u.f, h.f, u.e, h.e, ch, cl)) {
-            float uf = u.f, hf = h.f;
-            if (d == 0) hmm_regime_step<true>(uf, hf, ch, cl, 1.f, 1.f);
-            else hmm_regime_step<false>(uf, hf, ch, cl, hmm_mexp(-d), hmm_mexp(d));
-            if (!same(BF{uf, u.e}, BF{hf, h.e})) ++counts[2];
+        bool regime = false;
+        if (d >= -1 && d <= 1) {   // the chain's step and its trackers, as lane 0 evaluates them
+            float uf = u.f, hf = h.f, metric = 0.f;
+            if (d == 0) hmm_regime_step<0>(uf, hf, ch, cl, metric);
+            else if (d < 0) hmm_regime_step<-1>(uf, hf, ch, cl, metric);
+            else hmm_regime_step<1>(uf, hf, ch, cl, metric);
+            const bool ev = metric < 1.0e-18f;
+            // kept by the chain when no event fired; the re-examination (hmm_float_step, or the exact step on a hazard) then has to agree
+            regime = !ev && same(BF{uf, u.e}, BF{hf, h.e});
+            if (!ev && !regime && float_ok) ++counts[4];   // a drop the trackers missed: corrected by the re-examination, costs a round
+        }
+        if (regime) {
             ++counts[0];
         } else if (float_ok)
             ++counts[1];
@@ -900,7 +1039,7 @@ extern "C" int emu_hmm_run(const unsigned char* sym, unsigned long long n, const
     int* fe = (int*)malloc(n * 4), *be = (int*)malloc(n * 4);
     if (!ff || !bf_ || !fe || !be) { free(ff); free(bf_); free(fe); free(be); return -1; }
     const BF one = BF{1.0f, 0};
-    unsigned long long c4[4];
+    unsigned long long c4[5];
     // column 0 of the forward values and column n - 1 of the backward values are the chains' starting states
     {
         const u32 x = (u32)(sym[0] - '1') & 7u;

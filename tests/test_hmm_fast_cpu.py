@@ -17,7 +17,7 @@ import _oracle
 
 
 def _counts():
-    return np.zeros(4, dtype=np.uint64)
+    return np.zeros(8, dtype=np.uint64)
 
 
 def _fprod(v, c):
@@ -96,12 +96,13 @@ def test_chain_hybrid_equals_exact_chain(fwd):
     e = np.zeros(n, dtype=np.int32)
     k = _counts()
     _emu.emu().emu_hmm_chain(sym.ctypes.data, n, p.ctypes.data, fwd, f.ctypes.data, e.ctypes.data, k.ctypes.data)
-    print("regime", int(k[0]), "float_step", int(k[1]), "mismatch", int(k[2]), "exact", int(k[3]))
+    print("regime", int(k[0]), "float_step", int(k[1]), "mismatch", int(k[2]), "exact", int(k[3]), "missed drops", int(k[4]))
     assert int(k[2]) == 0, "an accepted FP32 step differs from the operation-by-operation step"
     assert int(k[0]) + int(k[1]) + int(k[3]) == n - 1
     assert int(k[0]) > 0.9 * (n - 1)         # the regime form carries the chain
     assert 0 < int(k[1]) < n // 10           # exponents move (the string renormalises thousands of times): those columns take hmm_float_step
     assert 0 < int(k[3]) < n // 300          # hazards exist and are rare
+    assert int(k[4]) < n // 10000            # drops the chain's own trackers miss cost a round each
     assert e.min() < -1000
 
 
