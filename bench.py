@@ -395,6 +395,56 @@ def measure_sml(mp, synth, args, a, pa, peak):
     return out
 
 
+def measure_config4(mp, synth, args, peak):
+    """BASELINE config 4 at its stated size: a synthetic 1 Gbp pair (uniform random ancestor + a 1 % SNP copy, seed 20261019).  (a) the
+    sorted-mer-list build of one genome (DNAMemorySML::Create = mcu_sml_build, pageable host sequence in, sorted list left in HBM) for
+    seed weights 11 / 15 / 19 / 21 at rank 0 and rank 3, with the onesweep passes against the HBM roofline (2 x (Kb + 4) bytes per pair
+    and pass); (b) one seed + match + extend pass over the pair at the default weight (genomes resident)."""
+    lib = mp.lib()
+    n = int(args.config4_gbp * 1e9)
+    rng = np.random.default_rng(20261019)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    step = 100_000_000
+    a = np.concatenate([lut[rng.integers(0, 4, min(step, n - o), dtype=np.uint8)] for o in range(0, n, step)])
+    out = {"metric": "Mbp/s sorted-mer-list build + seed+match+extend, BASELINE config 4", "genome_bp": n, "rows": []}
+    for w in (11, 15, 19, 21):
+        for r in (0, 3):
+            seed = mp.getSeed(w, r)
+            n_out = C.c_uint64(0)
+            walls = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                mp._capi.check(lib.mcu_sml_build(a.ctypes.data, a.size, seed, None, None, None, C.byref(n_out)))
+                walls.append(time.perf_counter() - t0)
+            st = np.zeros(6, dtype=np.float32)
+            lib.mcu_sml_last_stats(st.ctypes.data)
+            passes, kb, npos = int(st[3]), int(st[4]), float(n_out.value)
+            sort_bytes = passes * 2.0 * (kb + 4) * npos
+            dev_ms = float(st[0] + st[1] + st[2])
+            out["rows"].append({"weight_requested": w, "rank": r, "seed": hex(seed), "seed_length": mp.getSeedLength(seed), "seed_weight": mp.getSeedWeight(seed),
+                                "wall_ms": 1e3 * min(walls), "mbp_s": n / 1e6 / min(walls), "device_ms": dev_ms, "device_mbp_s": n / 1e6 / (dev_ms * 1e-3),
+                                "seedgen_ms": float(st[1]), "sort_ms": float(st[2]), "radix_passes": passes, "key_bytes": kb,
+                                "onesweep_gbs": sort_bytes / (float(st[2]) * 1e-3) / 1e9 if st[2] > 0 else None,
+                                "onesweep_frac": sort_bytes / (float(st[2]) * 1e-3) / 1e9 / peak if st[2] > 0 else None})
+    b = np.concatenate([synth.snps(a[o:o + step], 0.01, rng) for o in range(0, n, step)])
+    weight = mp.getDefaultSeedWeight((a.size + b.size) // 2)
+    seed = mp.getSeed(weight, mp.CODING_SEED)
+    sess = mp.AnchorSession()
+    sess.upload(a, b)
+    sess.run(seed)
+    ms = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        nm = sess.run(seed)
+        ms.append(1e3 * (time.perf_counter() - t0))
+    out["pair_step"] = {"seed_weight": weight, "seed": hex(seed), "matches": int(nm), "ms": min(ms), "device_ms": float(sess.stage_ms[6]),
+                        "mbp_s": 2 * n / 1e6 / (min(ms) * 1e-3), "bucketed": bool(sess.stage_ms[7] < 0), "repeat_limit_flag": int(sess.stats[3]),
+                        "parity": "size-independent properties only at this size (tests/test_zz_fullsize_gpu.py); the reference needs ~1.5 h and 40 GB for this pair"}
+    sess.close()
+    out["value"] = out["rows"][-3]["mbp_s"]
+    return out
+
+
 def measure_buildindex(mp, args):
     """BASELINE config 0 end to end: mauve.buildIndex on the MDS42 pair.  Reference arm = the reference's own progressiveMauve binary
     (oracle/_ref, unmodified sources) + the LUT construction, on the box's host cores; ours = mauve_py_b200.buildIndex (sorted mer
@@ -496,6 +546,7 @@ def main():
     ap.add_argument("--dp-cpu-regions", type=int, default=1000, help="stratified sample of the regions aligned by the reference's NWSmall")
     ap.add_argument("--hmm-single-columns", type=int, default=4000000)
     ap.add_argument("--sml-headline-weight", type=int, default=19)
+    ap.add_argument("--config4-gbp", type=float, default=1.0, help="genome size (Gbp) of the BASELINE config 4 measurement at N = 1; 0 skips it")
     ap.add_argument("--no-dp", action="store_true")
     ap.add_argument("--no-sml", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -741,6 +792,13 @@ def main():
             sml = measure_sml(mp, synth, args, a, pa, peak)
         except Exception as e:  # noqa: BLE001
             sml = {"error": "%s: %s" % (type(e).__name__, e)}
+    config4 = None
+    if world == 1 and not args.no_sml and args.config4_gbp > 0:
+        try:
+            sess.close()   # its buffers (3.7 GB at 100 Mbp) are not needed any more; the 1 Gbp pair takes ~60 GB
+            config4 = measure_config4(mp, synth, args, peak)
+        except Exception as e:  # noqa: BLE001
+            config4 = {"error": "%s: %s" % (type(e).__name__, e)}
     bidx = None
     if world == 1 and not args.no_cpu and not args.no_buildindex:
         # in a child process with a time limit: it drives external binaries, and nothing there may cost the headline line
@@ -765,7 +823,7 @@ def main():
                 "api": "mcu_find_mums_into(pinned host sequences -> pinned host rows): chunked H2D on a copy stream overlapped with pack + the level-1 "
                        "partition" if world == 1 else "mcu_find_mums_sharded (collective): every rank uploads 1/N of both genomes, packs it, ncclAllGather of "
                        "the packed words; rows to rank 0's pinned buffer (h2d_bytes_per_step is per rank)"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "sml": sml, "dp": dp, "hmm": hmm, "buildindex": bidx,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "sml": sml, "config4": config4, "dp": dp, "hmm": hmm, "buildindex": bidx,
     }
     emit(line)
     comm.barrier()

@@ -793,7 +793,7 @@ static int run_finish(Session& s, bool uniq_is_global, float* stage_ms, u64* sta
         MCU_TRY(s.matches.reserve((nmatch + 1) * sizeof(mcu_match)));
         if (nmatch) MCU_CUDA(cudaMemcpyAsync(s.matches.p, s.raw_matches.p, nmatch * sizeof(mcu_match), cudaMemcpyDeviceToDevice, s.stream));
     } else {
-        MCU_TRY(order_matches(s, s.raw_matches.as<mcu_match>(), nmatch));
+        MCU_TRY(order_matches(s, s.raw_matches.as<mcu_match>(), nmatch, s.n[0]));
         MCU_TRY(replay_unclean(s, &sp, !sharded, &unclean, &dup_rows));  // sharded runs replay after the merge
         nmatch = s.match_count;
     }
@@ -831,7 +831,39 @@ int join_sorted_u64(Session& s, const u64* keys, const u32* vals, u64 n, u64 pai
     return MCU_OK;
 }
 
-int order_matches(Session& s, const mcu_match* rows_dev, u64 n)
+// rows with equal primary key (same hash bucket AND same genome-0 start: next to never, duplicates of the order-dependent buckets
+// apart) are adjacent after the stable sort, still in their original order: the head of such a run orders it by the secondary key
+// (stable insertion: what a second LSD sort underneath would have given)
+__global__ void order_ties_kernel(const u64* __restrict__ pk, u32* __restrict__ idx, const u64* __restrict__ secondary, u64 n)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64 k = pk[i];
+        if (i > 0 && pk[i - 1] == k) continue;
+        if (i + 1 >= n || pk[i + 1] != k) continue;
+        u64 j = i + 2;
+        while (j < n && pk[j] == k) ++j;
+        for (u64 a = i + 1; a < j; ++a) {
+            const u32 v = idx[a];
+            const u64 kv = secondary[v];
+            u64 b = a;
+            while (b > i && secondary[idx[b - 1]] > kv) {
+                idx[b] = idx[b - 1];
+                --b;
+            }
+            idx[b] = v;
+        }
+    }
+}
+
+static int bits_for(u64 v)
+{
+    int b = 1;
+    while (b < 64 && (v >> b) != 0) ++b;
+    return b;
+}
+
+// max_start0: an upper bound of the rows' genome-0 starts (the genome's length) when the caller knows one, else 0
+int order_matches(Session& s, const mcu_match* rows_dev, u64 n, u64 max_start0)
 {
     s.match_count = n;
     MCU_TRY(s.matches.reserve((n + 1) * sizeof(mcu_match)));
@@ -842,26 +874,22 @@ int order_matches(Session& s, const mcu_match* rows_dev, u64 n)
     MCU_TRY(s.ord_vals_a.reserve(n * sizeof(u32)));
     MCU_TRY(s.ord_vals_b.reserve(n * sizeof(u32)));
     MCU_TRY(s.ord_primary.reserve(n * sizeof(u64)));
-    u64* primary = s.ord_primary.as<u64>();
-    u64* sec = s.ord_keys_a.as<u64>();
-    const int s0_bits = 33, s1_bits = 36;  // starts < 2^32 (+ length), sign bit
+    u64* secondary = s.ord_primary.as<u64>();
+    u64* primary = s.ord_keys_a.as<u64>();
+    const int s0_bits = max_start0 ? bits_for(max_start0 + 1) : 33;  // starts < 2^32 (+ length)
     const int g = grid_for(n, 256, 8);
-    order_keys_kernel<<<g, 256, 0, s.stream>>>(rows_dev, n, s0_bits, primary, sec, s.ord_vals_a.as<u32>());
+    order_keys_kernel<<<g, 256, 0, s.stream>>>(rows_dev, n, s0_bits, primary, secondary, s.ord_vals_a.as<u32>());
     s.launches++;
     bool in_a = true;
     u64 before = s.radix.launches;
+    // ONE stable sort on bucket | start0 (16 + s0_bits bits); the secondary key only decides between rows that tie on it
     MCU_TRY(radix_sort_pairs<u64>(s.radix, s.ord_keys_a.as<u64>(), s.ord_vals_a.as<u32>(), s.ord_keys_b.as<u64>(), s.ord_vals_b.as<u32>(), n,
-                                  s1_bits, false, s.stream, &in_a, nullptr));
-    u32* idx1 = in_a ? s.ord_vals_a.as<u32>() : s.ord_vals_b.as<u32>();
-    u32* idx_other = in_a ? s.ord_vals_b.as<u32>() : s.ord_vals_a.as<u32>();
-    // gather primary keys in secondary order, then sort on them (stable)
-    u64* pk = s.ord_keys_a.as<u64>();
-    u64* pk_other = s.ord_keys_b.as<u64>();
-    gather_u64_kernel<<<g, 256, 0, s.stream>>>(primary, idx1, n, pk);
-    s.launches++;
-    MCU_TRY(radix_sort_pairs<u64>(s.radix, pk, idx1, pk_other, idx_other, n, s0_bits + 16, false, s.stream, &in_a, nullptr));
+                                  s0_bits + 16, false, s.stream, &in_a, nullptr));
     s.launches += s.radix.launches - before;
-    const u32* idx_final = in_a ? idx1 : idx_other;
+    u32* idx_final = in_a ? s.ord_vals_a.as<u32>() : s.ord_vals_b.as<u32>();
+    const u64* pk = in_a ? s.ord_keys_a.as<u64>() : s.ord_keys_b.as<u64>();
+    order_ties_kernel<<<g, 256, 0, s.stream>>>(pk, idx_final, secondary, n);
+    s.launches++;
     gather_rows_kernel<<<g, 256, 0, s.stream>>>(rows_dev, idx_final, n, s.matches.as<mcu_match>());
     s.launches++;
     MCU_CUDA(cudaGetLastError());
@@ -891,7 +919,7 @@ int session_merge(Session& s, const mcu_match* rows_dev, u64 n, u64* unclean, u6
 {
     *unclean = 0;
     *dup_rows = 0;
-    MCU_TRY(order_matches(s, rows_dev, n));
+    MCU_TRY(order_matches(s, rows_dev, n, s.n[0]));
     MCU_TRY(replay_unclean(s, &s.run.sp, s.run.uniq_global, unclean, dup_rows));
     MCU_CUDA(cudaStreamSynchronize(s.stream));
     return MCU_OK;

@@ -83,7 +83,7 @@ int session_enumerate(Session& s, u64 seed, int shard_index, int shard_count);
 int session_finish(Session& s, bool uniq_is_global, float* stage_ms, u64* stats);
 int session_merge(Session& s, const mcu_match* rows_dev, u64 n, u64* unclean, u64* dup_rows);
 // sorts rows (device, n of them) into reference list order; result in s.matches (device)
-int order_matches(Session& s, const mcu_match* rows_dev, u64 n);
+int order_matches(Session& s, const mcu_match* rows_dev, u64 n, u64 max_start0);
 // join of an already sorted (key, position) array of 64-bit keys: appends to s.uniq / s.pairs / counters (anchor.cu)
 int join_sorted_u64(Session& s, const u64* keys, const u32* vals, u64 n, u64 pair_cap);
 // bucketed seed-match enumeration (bucket.cu); *used == false when the plan does not apply (caller sorts instead)

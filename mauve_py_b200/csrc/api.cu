@@ -461,7 +461,7 @@ int mcu_merge_matches(const mcu_match* rows, uint64_t n, int in_device, mcu_matc
         MCU_CUDA(cudaMemcpyAsync(s->raw_matches.p, rows, n * sizeof(mcu_match), cudaMemcpyHostToDevice, s->stream));
         dev_rows = s->raw_matches.as<mcu_match>();
     }
-    MCU_TRY(order_matches(*s, dev_rows, n));
+    MCU_TRY(order_matches(*s, dev_rows, n, 0));
     mcu_match* r = (mcu_match*)malloc((n ? n : 1) * sizeof(mcu_match));
     if (!r) { set_error("out of host memory"); return MCU_ENOMEM; }
     if (n) {

@@ -620,6 +620,108 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* 
     }
 }
 
+// Sharded runs with solid seeds (nshard > 1): a rank owns 1 / nshard of the seeds, so a 4096-position tile yields a fraction of a tile of
+// records while the per-tile costs (clearing and scanning the bin counters, one reservation per non-empty bin, the barriers) stay.
+// Here a CTA walks `sub` consecutive tiles of one genome (sub ~ 0.875 nshard: the expected yield stays eight standard deviations below
+// one tile) and parks what it owns -- the ownership scan, the record format and the output are bkf_scatter1_kernel's -- in shared
+// memory as (record, bin << 16 | rank in bin) in arrival order, reserves once, and writes every record to its reserved slot.  A
+// record that finds the parking area full (never, statistically) takes the overflow route like a record whose bucket is full.
+constexpr size_t bkf_multi_smem_bytes(u32 bins) { return (size_t)BK_TILE * 8 + (size_t)bins * 16 + 32 + (size_t)BK_TILE * 4 + 16; }
+
+__global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_multi_kernel(const u32* __restrict__ g0, const u32* __restrict__ g1, BkPlan pl, SeedParams sp,
+                                                                          unsigned long long* __restrict__ cursor1, u64* __restrict__ recs, BkOvf ovf,
+                                                                          u32 tiles0, u32 tiles_total, u32 sub, u32 ctas0)
+{
+    extern __shared__ __align__(16) unsigned char raw[];
+    const BkScatterSmem s = bk_carve(raw, pl.B1);
+    u32* sbr = (u32*)(raw + (size_t)BK_TILE * 8 + (size_t)pl.B1 * 16 + 32);   // [BK_TILE] bin << 16 | rank (takes the place of sbin)
+    u32* fill = sbr + BK_TILE;
+    const u32 tid = threadIdx.x, lane = tid & 31;
+    const u32 b_lo = pl.b_lo;
+    for (u32 i = tid; i < pl.B1; i += BK_THREADS) s.cnt[i] = 0;
+    if (tid == 0) *fill = 0;
+    __syncthreads();
+    const u32 gt = blockIdx.x >= ctas0 ? 1u : 0u;
+    const u32 first = gt ? tiles0 + (blockIdx.x - ctas0) * sub : blockIdx.x * sub;
+    const u32 last = min(first + sub, gt ? tiles_total : tiles0);
+    const int kbits = 2 * sp.w;
+    const u64 kmask = (1ull << kbits) - 1;   // kbits <= 62
+    const int mshift = kbits / 2 + 1;
+    const int m = sp.w < 16 ? sp.w : 16, skip = sp.w - m;                       // skip <= 15
+    const u32 xmask = m == 16 ? 0xffffffffu : (1u << (2 * m)) - 1u;
+    const u32* __restrict__ gp = gt ? g1 : g0;
+    const u64 npos = gt ? pl.npos1 : pl.npos0;
+    const u32 lt = lanemask_lt();
+    for (u32 tile = first; tile < last; ++tile) {
+        const u64 idx0 = (u64)tile * BK_TILE + (u64)tid * BK_IPT;
+        u32 own_mask = 0, own_nx = 0, own_prev = 0;
+        u64 own_pos = 0;
+        BkWindow w;
+        w.hi = 0; w.lo = 0;
+        if (idx0 < pl.nidx) {
+            const u64 pos = gt ? idx0 - pl.npad0 : idx0;
+            w.load(gp, pos);
+            // ownership of the 16 seeds from two sliding windows (seed_owned_x, common.cuh): see bkf_scatter1_kernel
+            const u32 hi_h = (u32)(w.hi >> 32), hi_l = (u32)w.hi;
+            own_nx = kbits < 32 ? __funnelshift_l(hi_l, hi_h, kbits) : __funnelshift_l(w.lo, hi_l, kbits - 32);
+            const u64 lastb = skip ? (w.hi << (2 * skip)) | ((u64)w.lo >> (32 - 2 * skip)) : w.hi;
+            const u64 tail = lastb >> (34 - 2 * m);
+            u64 head = __brevll(~w.hi);
+            head = ((head & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((head & 0x5555555555555555ull) << 1);
+            const u32 nvalid = pos >= npos ? 0u : (npos - pos >= 16 ? 16u : (u32)(npos - pos));
+#pragma unroll
+            for (int it = 0; it < BK_IPT; ++it) {
+                const u32 x = ((u32)(tail >> (30 - 2 * it)) ^ (u32)(head >> (2 * it))) & xmask;
+                if (seed_owned_x(x, pl.shard, pl.nshard)) own_mask |= 1u << it;
+            }
+            own_mask &= (1u << nvalid) - 1u;
+            own_pos = pos;
+            if (pl.aux && pos > 0) own_prev = base_at(gp, (i64)pos - 1);
+        }
+        // as many rounds as the busiest lane of the warp owns seeds (mean 16 / nshard)
+        for (int k = 0; k < BK_IPT; ++k) {
+            const u32 have = __ballot_sync(0xffffffffu, own_mask != 0);
+            if (!have) break;   // uniform
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(fill, (u32)__popc(have));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (own_mask) {
+                const int it = __ffs(own_mask) - 1;
+                own_mask &= own_mask - 1;
+                const u64 mer = it ? (w.hi << (2 * it)) | ((u64)w.lo >> (32 - 2 * it)) : w.hi;
+                const u64 ff = mer >> (64 - kbits), rr = revcomp_seed(ff, sp.w);
+                const u32 strand = rr < ff;
+                u64 x = strand ? rr : ff;
+                x ^= x >> mshift;
+                const u64 canon = (x * 0x9E3779B97F4A7C15ull) & kmask;  // == bk_mix
+                const u32 b = (u32)(canon >> pl.rem1);
+                const u64 keyrem = canon & ((1ull << pl.rem1) - 1);
+                u64 aux = 0;
+                if (pl.aux) {
+                    const u32 prev = it ? (u32)(w.hi >> (64 - 2 * it)) & 3u : own_prev;
+                    aux = prev | (((own_nx >> (30 - 2 * it)) & 3u) << 2);
+                }
+                const u64 rec = (keyrem << pl.kshift) | (aux << (pl.pbits + 2)) | ((own_pos + it) << 2) | ((u64)strand << 1) | (u64)gt;
+                const u32 p = base + (u32)__popc(have & lt);
+                if (p < (u32)BK_TILE) {
+                    s.stage[p] = rec;
+                    sbr[p] = (b << 16) | atomicAdd(&s.cnt[b], 1u);
+                } else
+                    bk_overflow(ovf.keys, ovf.vals, ovf.cap, ovf.cursor, ovf.dirty, rec, b, b - b_lo, pl.rem1, pl.kshift, pl.pbits, pl.d2);
+            }
+        }
+    }
+    __syncthreads();
+    const u64 cap1 = gt ? pl.cap1g[1] : pl.cap1g[0], segw = (u64)pl.cap1g[0] + pl.cap1g[1], goff = gt ? pl.cap1g[0] : 0;
+    bkf_reserve(s, pl.B1, cursor1 + (size_t)gt * pl.B1, 1, cap1, [=](u32 b) { return (u64)(b - b_lo) * segw + goff; });
+    const u32 ntile = min(*fill, (u32)BK_TILE);
+    for (u32 j = tid; j < ntile; j += BK_THREADS) {
+        const u32 b = sbr[j] >> 16, k = sbr[j] & 0xffffu;
+        if (k < s.cnt[b]) recs[s.gbase[b] + k] = s.stage[j];
+        else bk_overflow(ovf.keys, ovf.vals, ovf.cap, ovf.cursor, ovf.dirty, s.stage[j], b, b - b_lo, pl.rem1, pl.kshift, pl.pbits, pl.d2);
+    }
+}
+
 // level-2 partition of one tile of level-1 bucket b_lo + blockIdx.y into its B2 final buckets
 __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter2_kernel(const u64* __restrict__ src, BkPlan pl, const unsigned long long* __restrict__ cursor1,
                                                                     unsigned long long* __restrict__ cursor2, u64* __restrict__ dst, BkOvf ovf, u32 gsel)
@@ -1330,8 +1432,22 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     const unsigned tiles1 = (unsigned)div_up(pl.nidx, BK_TILE);
     MCU_CUDA(cudaEventRecord(s.kev[0], st));
     MCU_CUDA(cudaEventRecord(s.kev[1], st));
+    const u32 multi_sub = (solid_pattern && shard_count > 1 && getenv("MAUVE_CUDA_NO_MULTI") == nullptr) ? (u32)((7 * shard_count) / 8) : 0;
     auto scatter1 = [&](unsigned t0, unsigned t1) {
         if (t1 <= t0) return;
+        if (multi_sub > 1 && t0 == 0 && t1 == tiles1) {   // the whole scan in one launch: `multi_sub` tiles of one genome per CTA
+            static bool attr_multi = false;
+            if (!attr_multi) {
+                cudaFuncSetAttribute(bkf_scatter1_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bkf_multi_smem_bytes(BK_MAXB));
+                attr_multi = true;
+            }
+            const u32 tiles0 = (u32)(pl.npad0 / BK_TILE);
+            const u32 ctas0 = (tiles0 + multi_sub - 1) / multi_sub, ctas1 = (tiles1 - tiles0 + multi_sub - 1) / multi_sub;
+            bkf_scatter1_multi_kernel<<<ctas0 + ctas1, BK_THREADS, bkf_multi_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf, tiles0,
+                                                                                                        tiles1, multi_sub, ctas0);
+            s.launches++;
+            return;
+        }
         if (solid_pattern) bkf_scatter1_kernel<true><<<t1 - t0, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf, t0);
         else bkf_scatter1_kernel<false><<<t1 - t0, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf, t0);
         s.launches++;

@@ -96,7 +96,7 @@ int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out,
 /* regions with DNA wildcard columns (CudaGlobalAlign.h, seams with MAUVE_CUDA_WILD=1) */
 long long orc_nw_align_f(const char* a, unsigned la, const char* b, unsigned lb, char* path_out, float* score_out);
 static unsigned long long g_nwf_problems = 0;
-int orc_hmm_run(const char* sym, unsigned long long len, const double* p, char* pred_out, double* post_out);
+int orc_hmm_run(const char* sym, uint64_t len, const double* p, char* pred_out, double* post_out);
 int mcu_hmm_batch(uint64_t n, const char* sym, const uint64_t* off, const double* params, char* pred_out, double* post_out, float* device_ms)
 {
     uint64_t i;

@@ -42,7 +42,7 @@ def run_bench(argv, stub=True, timeout=600):
 
 def test_bench_main_line_dry_run():
     line, err = run_bench(["--mbp", "0.3", "--cpu-sample-mbp", "0.1", "--dp-regions", "6", "--dp-cpu-regions", "3", "--hmm-single-columns", "3000", "--steps", "2",
-                           "--warmup", "1", "--no-buildindex"])
+                           "--warmup", "1", "--no-buildindex", "--config4-gbp", "0.0002"])
     for k in REQUIRED:
         assert k in line, k
     assert line["metric"] == "Mbp/s seed+match+extend" and line["unit"] == "Mbp/s" and line["n_gpus"] == 1
@@ -71,6 +71,9 @@ def test_bench_main_line_dry_run():
     assert "error" not in line["hmm"], line["hmm"]
     assert line["hmm"]["value"] > 0 and line["hmm"]["strings"] == 6 and line["hmm"]["single_string"]["columns"] == 3000
     assert line["clocks"] is not None and "reasons" in line["clocks"]
+    assert "error" not in line["config4"], line["config4"]
+    assert len(line["config4"]["rows"]) == 8 and line["config4"]["pair_step"]["matches"] > 0 and line["config4"]["genome_bp"] == 200000
+    assert line["hmm"]["wall_ms_with_posteriors_back"] > 0 and line["rank_loop_ms"]["max"] > 0
     assert line["buildindex"] is None
 
 
