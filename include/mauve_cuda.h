@@ -262,6 +262,21 @@ int mcu_anchor_scores(const char* seq0, uint64_t n0, const char* seq1, uint64_t 
                       const mcu_match* rows, uint64_t n_rows, const uint64_t* lcb_off, uint64_t n_lcb, const int32_t* matrix,
                       int penalize_repeats, double* lcb_score_out, int64_t* match_score_out);
 
+/* ---- the step after the match list, two genomes.  Rows are (len > 0, start0 > 0, start1 != 0 signed).
+ *      mcu_eliminate_overlaps replaces mems::EliminateOverlaps_v2(ml, eliminate_both) (LM/ProgressiveAligner.h:300-406) followed, when
+ *      min_length > 0, by ml.LengthFilter(min_length) (LM/MatchList.h:680-692): the sequence pairwiseAnchorSearch runs after every gap
+ *      search (LM/ProgressiveAligner.cpp:656-660) and, with eliminate_both, the pairwise LCB set-up after the initial anchoring
+ *      (:3408-3410).  rows_out (n rows of room): what the reference's list holds afterwards, in its order.
+ *      mcu_lcbs replaces mems::IdentifyBreakpoints + ComputeLCBs_v2 (LM/GreedyBreakpointElimination.h:161-250): sorted_out = the list
+ *      ordered on genome 0, breakpoints_out (n entries of room) = index of the last match of every LCB, ascending: LCB l is
+ *      sorted_out[breakpoints[l-1] + 1 .. breakpoints[l]].
+ *      The reference orders its lists with std::sort on one start coordinate; where starts tie, the outcome depends on where
+ *      libstdc++'s introsort leaves the tied rows, and that algorithm is what runs here then (csrc/lcb.cu).  ties_out (optional): how
+ *      many adjacent ties the orderings met (0: any correct sort gives this result). */
+int mcu_eliminate_overlaps(const mcu_match* rows, uint64_t n, int eliminate_both, uint64_t min_length, mcu_match* rows_out, uint64_t* n_out,
+                           uint64_t* ties_out);
+int mcu_lcbs(const mcu_match* rows, uint64_t n, mcu_match* sorted_out, uint64_t* breakpoints_out, uint64_t* n_breakpoints_out, uint64_t* ties_out);
+
 /* ---- test hooks (exercise single kernels through the ABI) -------------------------------- */
 /* stable LSD radix sort of (key,val) pairs on the low `bits` bits; key_bytes is 4 or 8 */
 int mcu_test_sort_pairs(void* keys, uint32_t* vals, uint64_t n, int key_bytes, int bits);

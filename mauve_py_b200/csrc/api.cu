@@ -11,6 +11,7 @@
 #include "anchor.cuh"
 #include "dp.cuh"
 #include "hmm.cuh"
+#include "lcb.cuh"
 #include "sol.cuh"
 
 namespace mcu {
@@ -514,6 +515,31 @@ int mcu_hmm_batch(uint64_t n, const char* sym, const uint64_t* off, const double
     std::lock_guard<std::mutex> lk(g_mu);
     MCU_TRY(ensure_device());
     return hmm_batch(n, sym, off, params, pred_out, post_out, device_ms);
+}
+
+int mcu_eliminate_overlaps(const mcu_match* rows, uint64_t n, int eliminate_both, uint64_t min_length, mcu_match* rows_out, uint64_t* n_out,
+                           uint64_t* ties_out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    if (!n_out || (n && (!rows || !rows_out))) { set_error("mcu_eliminate_overlaps: NULL pointer"); return MCU_EINVAL; }
+    u64 cnt = 0, ties = 0;
+    MCU_TRY(lcb_eliminate_overlaps(rows, n, eliminate_both, min_length, rows_out, &cnt, &ties));
+    *n_out = cnt;
+    if (ties_out) *ties_out = ties;
+    return MCU_OK;
+}
+
+int mcu_lcbs(const mcu_match* rows, uint64_t n, mcu_match* sorted_out, uint64_t* breakpoints_out, uint64_t* n_breakpoints_out, uint64_t* ties_out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    if (!n_breakpoints_out || (n && (!rows || !sorted_out || !breakpoints_out))) { set_error("mcu_lcbs: NULL pointer"); return MCU_EINVAL; }
+    u64 nb = 0, ties = 0;
+    MCU_TRY(lcb_breakpoints(rows, n, sorted_out, (u64*)breakpoints_out, &nb, &ties));
+    *n_breakpoints_out = nb;
+    if (ties_out) *ties_out = ties;
+    return MCU_OK;
 }
 
 int mcu_test_hmm_counters(uint64_t* out3)

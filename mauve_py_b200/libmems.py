@@ -26,6 +26,7 @@ __all__ = [
     "bmer", "DNAMemorySML", "read_sslist", "write_sslist", "Match", "MatchList", "MemHash", "PairwiseMatchFinder", "AnchorSession", "merge_matches",
     "PWPath", "GlobalAlign", "GlobalAlignBatch", "GlobalAlignBatchWild", "Params", "hmm_params", "getAdaptedHoxdMatrixParameters", "adaptToPercentIdentity",
     "run", "run_batch", "sort_pairs", "SeedOccurrenceList", "GetPairwiseAnchorScore", "anchor_scores", "hoxd_matrix",
+    "EliminateOverlaps_v2", "IdentifyBreakpoints", "ComputeLCBs_v2",
 ]
 
 
@@ -596,6 +597,39 @@ def merge_matches(rows, in_device=False, n=None, return_unclean=False):
     res = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_int64)), shape=(k, 3)).copy() if k else np.zeros((0, 3), dtype=np.int64)
     lib().mcu_free(out)
     return (res, int(unclean.value)) if return_unclean else res
+
+
+# ---- LM/ProgressiveAligner.h:300-406, LM/MatchList.h:680-692, LM/GreedyBreakpointElimination.h:161-250 -------------
+def EliminateOverlaps_v2(rows, eliminate_both=False, min_length=0, return_ties=False):
+    """mems::EliminateOverlaps_v2(ml, eliminate_both) on a two-genome match list (rows: len, start0 > 0, start1 signed), followed by
+    ml.LengthFilter(min_length) when min_length > 0 -> the rows the reference's list holds afterwards, in its order."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3)
+    out = np.zeros_like(rows)
+    n_out, ties = C.c_uint64(0), C.c_uint64(0)
+    check(lib().mcu_eliminate_overlaps(rows.ctypes.data, rows.shape[0], 1 if eliminate_both else 0, int(min_length), out.ctypes.data, C.byref(n_out),
+                                       C.byref(ties)))
+    res = out[:int(n_out.value)].copy()
+    return (res, int(ties.value)) if return_ties else res
+
+
+def IdentifyBreakpoints(rows, return_ties=False):
+    """mems::IdentifyBreakpoints -> (the list ordered on genome 0, breakpoints = index of the last match of every LCB)"""
+    rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3)
+    out = np.zeros_like(rows)
+    bp = np.zeros(rows.shape[0] + 1, dtype=np.uint64)
+    n_bp, ties = C.c_uint64(0), C.c_uint64(0)
+    check(lib().mcu_lcbs(rows.ctypes.data, rows.shape[0], out.ctypes.data, bp.ctypes.data, C.byref(n_bp), C.byref(ties)))
+    res = (out, bp[:int(n_bp.value)].copy())
+    return res + (int(ties.value),) if return_ties else res
+
+
+def ComputeLCBs_v2(sorted_rows, breakpoints):
+    """mems::ComputeLCBs_v2: the LCBs as a list of row blocks (views of sorted_rows)"""
+    out, prev = [], 0
+    for b in np.asarray(breakpoints, dtype=np.int64).tolist():
+        out.append(sorted_rows[prev:b + 1])
+        prev = b + 1
+    return out
 
 
 # ---- MU/pwpath.h, MU/glbalign.cpp ------------------------------------------------------------------

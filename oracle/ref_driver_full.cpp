@@ -6,6 +6,8 @@
 //   ref_sol_build      -> mems::SeedOccurrenceList::construct            (LM/SeedOccurrenceList.h:22-78)
 //   ref_anchor_scores  -> mems::GetPairwiseAnchorScore                   (LM/GreedyBreakpointElimination.h:403-476)
 //   ref_anchor_cols    -> muscle::FindAnchorColsPP                       (MU/anchoredpp.cpp:354-409)
+//   ref_eliminate_overlaps -> mems::EliminateOverlaps_v2 + LengthFilter  (LM/ProgressiveAligner.h:300-406, LM/MatchList.h:680-692)
+//   ref_lcbs           -> mems::IdentifyBreakpoints + ComputeLCBs_v2     (LM/GreedyBreakpointElimination.h:161-250)
 //
 // Only the glue below is ours; every algorithmic step runs reference code.
 #include <cstdint>
@@ -21,6 +23,7 @@
 #include "libMems/SeedOccurrenceList.h"
 #include "libMems/SubstitutionMatrix.h"
 #include "libMems/GreedyBreakpointElimination.h"
+#include "libMems/ProgressiveAligner.h"
 using namespace std;  // LM/Scoring.h names std types unqualified
 #include "libMems/Scoring.h"
 
@@ -91,6 +94,63 @@ int ref_anchor_scores(const char* seq0, uint64_t n0, const char* seq1, uint64_t 
 		delete seq_table[0];
 		delete seq_table[1];
 		return 0;
+	} catch (...) { return -1; }
+}
+
+static void rows_to_list(const ref_match* rows, uint64_t n, MatchList& ml)
+{
+	Match mm(2);
+	for (uint64_t k = 0; k < n; ++k) {
+		Match* m = mm.Copy();
+		m->SetStart(0, rows[k].start0);
+		m->SetStart(1, rows[k].start1);
+		m->SetLength(rows[k].len);
+		ml.push_back(m);
+	}
+}
+
+// EliminateOverlaps_v2(ml, eliminate_both) followed (min_length > 0) by ml.LengthFilter(min_length): the sequence of
+// pairwiseAnchorSearch (LM/ProgressiveAligner.cpp:656-660) and, with eliminate_both, of the pairwise LCB set-up (:3408-3410).
+// out: what the list holds afterwards, in its order.  Returns the count or -1.
+long long ref_eliminate_overlaps(const ref_match* rows, uint64_t n, int eliminate_both, uint64_t min_length, ref_match* out)
+{
+	try {
+		MatchList ml;
+		rows_to_list(rows, n, ml);
+		EliminateOverlaps_v2(ml, eliminate_both != 0);
+		if (min_length) ml.LengthFilter(min_length);
+		for (size_t i = 0; i < ml.size(); ++i) {
+			out[i].len = (int64_t)ml[i]->Length();
+			out[i].start0 = ml[i]->Start(0);
+			out[i].start1 = ml[i]->Start(1);
+			ml[i]->Free();
+		}
+		return (long long)ml.size();
+	} catch (...) { return -1; }
+}
+
+// IdentifyBreakpoints + ComputeLCBs_v2 on the list: sorted_out = the list afterwards (sorted on genome 0), bp_out = the breakpoints
+// (index of the last match of every LCB).  Returns their number or -1.
+long long ref_lcbs(const ref_match* rows, uint64_t n, ref_match* sorted_out, uint64_t* bp_out)
+{
+	try {
+		MatchList ml;
+		rows_to_list(rows, n, ml);
+		vector<gnSeqI> breakpoints;
+		IdentifyBreakpoints(ml, breakpoints);
+		vector<MatchList> lcbs;
+		ComputeLCBs_v2(ml, breakpoints, lcbs);
+		size_t k = 0;
+		for (size_t l = 0; l < lcbs.size(); ++l) k += lcbs[l].size();
+		if (k != ml.size()) return -2;
+		for (size_t i = 0; i < ml.size(); ++i) {
+			sorted_out[i].len = (int64_t)ml[i]->Length();
+			sorted_out[i].start0 = ml[i]->Start(0);
+			sorted_out[i].start1 = ml[i]->Start(1);
+		}
+		for (size_t i = 0; i < breakpoints.size(); ++i) bp_out[i] = breakpoints[i];
+		for (size_t i = 0; i < ml.size(); ++i) ml[i]->Free();
+		return (long long)breakpoints.size();
 	} catch (...) { return -1; }
 }
 

@@ -100,8 +100,51 @@ def ref_full():
         lib.ref_sol_build.restype = C.c_longlong
         lib.ref_sol_build.argtypes = [C.c_char_p, u64, u64, p]
         lib.ref_anchor_scores.argtypes = [C.c_char_p, u64, C.c_char_p, u64, u64, p, u64, p, u64, C.c_int, p]
+        lib.ref_eliminate_overlaps.restype = C.c_longlong
+        lib.ref_eliminate_overlaps.argtypes = [p, u64, C.c_int, u64, p]
+        lib.ref_lcbs.restype = C.c_longlong
+        lib.ref_lcbs.argtypes = [p, u64, p, p]
         _cache["rf"] = lib
     return _cache["rf"]
+
+
+def eliminate_overlaps(rows, eliminate_both=False, min_length=0, use_ref=False):
+    """EliminateOverlaps_v2 (+ LengthFilter) on a two-genome match list -> (rows afterwards in the reference's order, ties or None)"""
+    rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3)
+    out = np.zeros_like(rows)
+    if use_ref:
+        n = ref_full().ref_eliminate_overlaps(rows.ctypes.data, rows.shape[0], int(eliminate_both), int(min_length), out.ctypes.data)
+        ties = None
+    else:
+        lib = oracle()
+        lib.orc_eliminate_overlaps.restype = C.c_longlong
+        lib.orc_eliminate_overlaps.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+        t = C.c_uint64(0)
+        n = lib.orc_eliminate_overlaps(rows.ctypes.data, rows.shape[0], int(eliminate_both), int(min_length), out.ctypes.data, C.byref(t))
+        ties = int(t.value)
+    if n < 0:
+        raise RuntimeError("eliminate_overlaps failed")
+    return out[:n].copy(), ties
+
+
+def lcbs(rows, use_ref=False):
+    """IdentifyBreakpoints + ComputeLCBs_v2 -> (rows sorted on genome 0, breakpoints = index of the last match of every LCB, ties or None)"""
+    rows = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3)
+    out = np.zeros_like(rows)
+    bp = np.zeros(rows.shape[0] + 1, dtype=np.uint64)
+    if use_ref:
+        n = ref_full().ref_lcbs(rows.ctypes.data, rows.shape[0], out.ctypes.data, bp.ctypes.data)
+        ties = None
+    else:
+        lib = oracle()
+        lib.orc_lcbs.restype = C.c_longlong
+        lib.orc_lcbs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        t = C.c_uint64(0)
+        n = lib.orc_lcbs(rows.ctypes.data, rows.shape[0], out.ctypes.data, bp.ctypes.data, C.byref(t))
+        ties = int(t.value)
+    if n < 0:
+        raise RuntimeError("lcbs failed")
+    return out, bp[:n].copy(), ties
 
 
 def sol_build(seq: bytes, seed: int, use_ref=False):

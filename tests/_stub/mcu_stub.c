@@ -94,6 +94,23 @@ int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out,
 }
 
 /* regions with DNA wildcard columns (CudaGlobalAlign.h, seams with MAUVE_CUDA_WILD=1) */
+long long orc_eliminate_overlaps(const mcu_match* rows, uint64_t n, int eliminate_both, uint64_t min_length, mcu_match* out, uint64_t* ties);
+long long orc_lcbs(const mcu_match* rows, uint64_t n, mcu_match* sorted_out, uint64_t* bp_out, uint64_t* ties);
+int mcu_eliminate_overlaps(const mcu_match* rows, uint64_t n, int eliminate_both, uint64_t min_length, mcu_match* rows_out, uint64_t* n_out, uint64_t* ties_out)
+{
+    long long k = orc_eliminate_overlaps(rows, n, eliminate_both, min_length, rows_out, ties_out);
+    if (k < 0) return -3;
+    *n_out = (uint64_t)k;
+    return 0;
+}
+int mcu_lcbs(const mcu_match* rows, uint64_t n, mcu_match* sorted_out, uint64_t* bp_out, uint64_t* n_bp_out, uint64_t* ties_out)
+{
+    long long k = orc_lcbs(rows, n, sorted_out, bp_out, ties_out);
+    if (k < 0) return -3;
+    *n_bp_out = (uint64_t)k;
+    return 0;
+}
+
 long long orc_nw_align_f(const char* a, unsigned la, const char* b, unsigned lb, char* path_out, float* score_out);
 static unsigned long long g_nwf_problems = 0;
 int orc_hmm_run(const char* sym, uint64_t len, const double* p, char* pred_out, double* post_out);

@@ -340,6 +340,8 @@ def _seam_counts(stderr):
     for l in stderr.splitlines():
         if l.split(" seam:")[0] in ("AnchoredProfileProfile", "MemHash::FindMatches", "RefineW", "SeedOccurrenceList::construct", "FileSML::Create"):
             out[l.split(" seam:")[0]] = [int(x) for x in l.replace(",", "").split() if x.isdigit()]
+        if l.startswith("EliminateOverlaps_v2 seam:") or l.startswith("IdentifyBreakpoints seam:"):
+            out[l.split(" seam:")[0]] = [int(x) for x in l.replace(",", "").replace("(", " ").split() if x.isdigit()]
         if l.startswith("run() seam (HomologyHMM):"):   # strings on the device, their columns, strings left to the reference's run()
             out["run"] = [int(x) for x in l.replace(",", "").replace("(", " ").split() if x.isdigit()]
     return out
@@ -400,6 +402,9 @@ def test_seams_host_code_inside_the_reference_binary(tmp_path):
     assert c["SeedOccurrenceList::construct"] == [2, 0]       # both genomes' seed occurrence lists (adapters/seams/sol_seam.cpp)
     assert c["FileSML::Create"] == [2, 0]                     # both `.sslist` files (adapters/seams/filesml_seam.cpp)
     assert c["run"][0] >= 1 and c["run"][1] > 3_900_000 and c["run"][2] == 0   # the backbone HMM: one string as long as the alignment (adapters/seams/hmm_seam.cpp)
+    # the step after every match list (adapters/seams/lcb_seam.cpp): overlaps of the initial list (25 tied keys) and of the gap lists that hold two matches or more, the LCBs
+    assert c["EliminateOverlaps_v2"][0] > 50 and c["EliminateOverlaps_v2"][1] >= 25 and c["EliminateOverlaps_v2"][2] == 0
+    assert c["IdentifyBreakpoints"][0] >= 1 and c["IdentifyBreakpoints"][1] == 0
 
 
 @needs_cuda_bin
@@ -505,6 +510,7 @@ def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, 
         assert c["SeedOccurrenceList::construct"] == ([2, 0] if sol_seam == "1" else [0, 2])
         assert c["FileSML::Create"] == [2, 0]
         assert c["run"][0] >= 1 and c["run"][1] > 3_900_000 and c["run"][2] == 0
+        assert c["EliminateOverlaps_v2"][0] > (50 if gap_seam == "1" else 0) and c["EliminateOverlaps_v2"][2] == 0 and c["IdentifyBreakpoints"] == [1, 0]
     # a pair with N columns: part of the DP falls back to the reference's code, the alignment stays the reference's
     d2 = os.path.join(str(tmp_path), "spiked")
     os.makedirs(d2)

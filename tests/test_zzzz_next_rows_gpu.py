@@ -195,3 +195,62 @@ def test_sml_accessors_on_a_device_built_list(mp, orc):
             assert found and int(sml.mers()[at]) == b.mer
         assert sml.FindMer(int(sml.mers()[-1]) + 2)[0] is False or int(sml.mers()[-1]) + 2 in sml.mers()
         assert sml.Clone().SMLLength() == sml.SMLLength() and sml.GetHeader()["seed"] == seed
+
+
+# ---- EliminateOverlaps_v2 + LengthFilter, IdentifyBreakpoints + ComputeLCBs_v2 (csrc/lcb.cu) --------------------------
+def _lcb_cases(z):
+    for nm in ["mds42", "syn"] + ["rand%d" % i for i in range(int(z["rand_count"]))]:
+        rows = _golden.npz("mums_mds42.npz")["rows_w15_r3"] if nm == "mds42" else z[nm + "_rows"]
+        yield nm, np.ascontiguousarray(rows, dtype=np.int64)
+
+
+def test_eliminate_overlaps_and_lcbs_golden(mp):
+    """the device pipeline against what the reference's own functions returned (tests/golden/lcb.npz): rows, their order, the LCB
+    boundaries -- including the MDS42 list, whose second pass orders 25 tied rows the way libstdc++'s introsort leaves them"""
+    z = _golden.npz("lcb.npz")
+    for nm, rows in _lcb_cases(z):
+        for key, both, ml in (("elim0", False, 0), ("elim0_min", False, 12), ("elim1", True, 0)):
+            got, ties = mp.EliminateOverlaps_v2(rows, both, ml, return_ties=True)
+            assert np.array_equal(got, z["%s_%s" % (nm, key)]), (nm, key, ties)
+            if nm == "mds42" and key == "elim1":
+                assert ties == 25
+        e1 = z[nm + "_elim1"]
+        if e1.shape[0]:
+            so, bp = mp.IdentifyBreakpoints(e1)
+            assert np.array_equal(so, z[nm + "_lcb_sorted"]) and np.array_equal(bp, z[nm + "_lcb_bp"]), nm
+            lcbs = mp.ComputeLCBs_v2(so, bp)
+            assert sum(len(l) for l in lcbs) == so.shape[0] and len(lcbs) == bp.size
+    assert mp.EliminateOverlaps_v2(np.zeros((0, 3), dtype=np.int64)).shape == (0, 3)
+    with pytest.raises(mp.McuError):
+        mp.EliminateOverlaps_v2(np.array([[10, 0, 5]], dtype=np.int64))   # not a two-genome match
+
+
+def test_eliminate_overlaps_and_lcbs_vs_oracle(mp, orc):
+    """fresh random lists (dense overlaps on both strands, ties) and the match list of a real run: device == C restatement"""
+    rng = np.random.default_rng(4242)
+    lists = []
+    for it in range(60):
+        n = int(rng.integers(1, 3000))
+        G = int(rng.integers(2000, 2000000))
+        s0 = rng.integers(1, G, n)
+        ln = rng.integers(5, 400, n)
+        s1 = rng.integers(1, G, n) * rng.choice([1, -1], n)
+        k = n // 2
+        s0[:k] = np.sort(rng.integers(1, max(G // 10, 2), k))
+        s1[:k] = s0[:k] + rng.integers(-3, 4, k)
+        s1[s1 == 0] = 1
+        lists.append(np.stack([ln, s0, s1], 1).astype(np.int64))
+    a, b = synth.small_pair(2_000_000, seed=808, snp=0.02, n_inv=6)
+    rows, _ = mp.libmems.find_mums(a, b, mp.getSeed(13, 0))
+    lists.append(np.ascontiguousarray(rows, dtype=np.int64))
+    for i, r in enumerate(lists):
+        for both in (False, True):
+            for ml in (0, 12):
+                want, wt = _oracle.eliminate_overlaps(r, both, ml)
+                got, gt = mp.EliminateOverlaps_v2(r, both, ml, return_ties=True)
+                assert np.array_equal(got, want) and gt == wt, (i, both, ml)
+        e1, _ = _oracle.eliminate_overlaps(r, True, 0)
+        if e1.shape[0]:
+            so, bp, t = _oracle.lcbs(e1)
+            gso, gbp, gt = mp.IdentifyBreakpoints(e1, return_ties=True)
+            assert np.array_equal(gso, so) and np.array_equal(gbp, bp) and gt == t, i
