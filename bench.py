@@ -692,6 +692,27 @@ def main():
             print("rank %d: HMM measurement failed: %s: %s" % (rank, type(e).__name__, e), file=sys.stderr)
             hmm = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    # ---- sorted mer list of genome 0, sharded by mer range over the N ranks (collective; at N = 1 the plain build) ----
+    sml_sharded = None
+    if not args.no_sml:
+        try:
+            walls, devs = [], []
+            for _ in range(3):
+                comm.barrier()
+                t0 = time.perf_counter()
+                spos, dms = mp.libmems.sml_build_sharded(a, seed)
+                walls.append(time.perf_counter() - t0)
+                devs.append(dms)
+            w = comm.allreduce([min(walls)], mdist.MAX)[0]
+            d = comm.allreduce([min(devs)], mdist.MAX)[0]
+            sml_sharded = {"metric": "Mbp/s sorted-mer-list build sharded by mer range (positions gathered on rank 0)", "unit": "Mbp/s", "n_gpus": world,
+                           "genome_bp": int(a.size), "seed": hex(seed), "wall_ms": 1e3 * w, "device_ms": d, "value": a.size / 1e6 / w,
+                           "device_mbp_s": a.size / 1e6 / (d * 1e-3), "list_length": int(spos.size) if rank == 0 else None,
+                           "note": "every rank uploads and scans the genome, sorts the seeds of its mer range, ncclSend/Recv of the 4-byte positions to "
+                                   "rank 0; pageable host sequence in, positions back to host on rank 0 (wall) / CUDA events around upload .. gather (device)"}
+        except Exception as e:  # noqa: BLE001
+            sml_sharded = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if rank != 0:
         comm.barrier()
         comm.close()
@@ -823,7 +844,7 @@ def main():
                 "api": "mcu_find_mums_into(pinned host sequences -> pinned host rows): chunked H2D on a copy stream overlapped with pack + the level-1 "
                        "partition" if world == 1 else "mcu_find_mums_sharded (collective): every rank uploads 1/N of both genomes, packs it, ncclAllGather of "
                        "the packed words; rows to rank 0's pinned buffer (h2d_bytes_per_step is per rank)"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "sml": sml, "config4": config4, "dp": dp, "hmm": hmm, "buildindex": bidx,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "sml": sml, "sml_sharded": sml_sharded, "config4": config4, "dp": dp, "hmm": hmm, "buildindex": bidx,
     }
     emit(line)
     comm.barrier()

@@ -73,6 +73,17 @@ int mcu_seed_weight(uint64_t seed);
 int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed,
                   uint32_t* pos_out, uint64_t* mer_out, uint32_t* packed_out, uint64_t* sml_len_out);
 
+/* One shard of the sorted mer list (the materialised position array sharded by mer range): the seeds whose key
+ * (canonical mer) lies in range `shard` of `n_shards` (<= 16) ranges that tile the key space in order, so that the shards' lists,
+ * one after the other, are the list mcu_sml_build returns -- except that equal mers come in unspecified order inside their run
+ * (the reference's own order there is std::sort's).  *shard_len_out = this shard's length; pos_out / mer_out need that much room
+ * (n - L + 1 always suffices).  mcu_sml_build_sharded is the collective form over the communicator of mcu_comm_init: every rank
+ * passes the same sequence and builds its shard, the positions are gathered on rank 0 (pos_out, n - L + 1 entries, used there only);
+ * ms_out (optional): device ms of the call on this rank, CUDA events around upload, scan, sort and gather. */
+int mcu_sml_build_shard(const char* seq, uint64_t n, uint64_t seed, int shard, int n_shards, uint32_t* pos_out, uint64_t* mer_out,
+                        uint64_t* shard_len_out);
+int mcu_sml_build_sharded(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out, uint64_t* sml_len_out, float* ms_out);
+
 /* device times of the last mcu_sml_build call (6 floats): [0] pack ms, [1] seed generation ms, [2] radix sort ms (CUDA events
  * on the launching stream), [3] radix passes, [4] key bytes (4 or 8), [5] list length */
 void mcu_sml_last_stats(float* out6);

@@ -29,7 +29,7 @@ SYMBOLS = [
     "mcu_comm_unique_id", "mcu_comm_init", "mcu_comm_destroy", "mcu_comm_rank", "mcu_comm_world", "mcu_comm_barrier",
     "mcu_comm_allreduce_f64", "mcu_comm_gather_bytes", "mcu_device_synchronize",
     "mcu_session_upload_sharded", "mcu_session_run_sharded", "mcu_find_mums_sharded",
-    "mcu_test_sort_pairs", "mcu_test_int32_peak", "mcu_test_hmm_counters", "mcu_eliminate_overlaps", "mcu_lcbs",
+    "mcu_test_sort_pairs", "mcu_test_int32_peak", "mcu_test_hmm_counters", "mcu_eliminate_overlaps", "mcu_lcbs", "mcu_sml_build_shard", "mcu_sml_build_sharded",
 ]
 
 
@@ -115,6 +115,8 @@ def lib():
     L.mcu_test_hmm_counters.argtypes = [C.c_void_p]
     L.mcu_eliminate_overlaps.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcu_lcbs.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcu_sml_build_shard.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcu_sml_build_sharded.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

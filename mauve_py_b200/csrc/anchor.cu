@@ -62,11 +62,21 @@ __global__ void __launch_bounds__(256) pack_kernel(const u8* __restrict__ seq, u
 // the keys for counting).  Coalesced: thread t of a block handles position base+t.
 // HBM traffic: 0.25 B/base packed read (L1/L2 served) + sizeof(K)+4 written.
 // =========================================================================================
+// Sharded sorted-mer-list build: rank r owns the seeds whose key lies in the r-th of n RANGES of the key space, so
+// that the ranks' sorted lists, one after the other, are the sorted list.  The key is the canonical mer = min(forward, reverse
+// complement), whose density over the key range is ~2 (1 - x) rather than flat: the splitters sit at the quantiles
+// 1 - sqrt(1 - k / n) of that density (top 16 key bits), which balances random sequence to a few percent.
+struct SmlSplit {
+    u32 n = 0;       // 0: ownership by hash (match finding)
+    int shift = 0;   // key >> shift = the bits the splitters are compared with
+    u32 s[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+};
+
 template <typename K>
 __global__ void __launch_bounds__(256) seedgen_kernel(const u32* __restrict__ packed, u64 npos, SeedParams sp, u32 genome,
                                                      K* __restrict__ keys, u32* __restrict__ vals, u64 out_base,
                                                      u64* __restrict__ hist, int passes, u32 shard, u32 nshard,
-                                                     unsigned long long* __restrict__ out_counter)
+                                                     unsigned long long* __restrict__ out_counter, SmlSplit split = SmlSplit())
 {
     extern __shared__ u32 sh_hist[];  // passes*256
     for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) sh_hist[i] = 0;
@@ -85,7 +95,13 @@ __global__ void __launch_bounds__(256) seedgen_kernel(const u32* __restrict__ pa
             u32 strand = rc < f;  // GetDnaSeedMer: forward wins ties (f < rc|1)
             u64 canon = strand ? rc : f;
             key = (canon << 2) | (genome << 1) | strand;
-            live = seed_owned(f, rc, shard, nshard);
+            if (split.n) {   // sorted-mer-list shards: ranges of the key, so that the ranks' sorted lists concatenate
+                const u32 top = (u32)(key >> split.shift);
+                u32 owner = 0;
+                for (u32 k = 0; k + 1 < split.n; ++k) owner += top >= split.s[k];
+                live = owner == shard;
+            } else
+                live = seed_owned(f, rc, shard, nshard);
         }
         u64 slot = out_base + p;
         if (sharded) {  // unordered compaction (tie order is irrelevant for match finding)
@@ -927,10 +943,19 @@ int session_merge(Session& s, const mcu_match* rows_dev, u64 n, u64* unclean, u6
 
 // ---- single-genome SML --------------------------------------------------------------------
 template <typename K>
-static int sml_build_t(Session& s, const SeedParams& sp, u32* pos_out, u64* mer_out, u32* packed_out, u64* len_out)
+static int sml_build_t(Session& s, const SeedParams& sp, u32* pos_out, u64* mer_out, u32* packed_out, u64* len_out, int shard = 0, int nshard = 1)
 {
     const u64 n = s.n[0];
-    const u64 npos = n >= (u64)sp.L ? n - sp.L + 1 : 0;
+    const u64 npos_all = n >= (u64)sp.L ? n - sp.L + 1 : 0;
+    u64 npos = npos_all;
+    SmlSplit split;
+    if (nshard > 1) {
+        const int kb = 2 * sp.w + 2;
+        const int tb = kb < 16 ? kb : 16;
+        split.n = (u32)nshard;
+        split.shift = kb - tb;
+        for (int k = 1; k < nshard; ++k) split.s[k - 1] = (u32)((double)(1u << tb) * (1.0 - sqrt(1.0 - (double)k / nshard)));
+    }
     const int key_bits = 2 * sp.w + 2;
     const int passes = (key_bits + 7) / 8;
     unsigned long long* ctr = s.counters.as<unsigned long long>();
@@ -946,8 +971,14 @@ static int sml_build_t(Session& s, const SeedParams& sp, u32* pos_out, u64* mer_
     bool in_a = true;
     if (npos) {
         seedgen_kernel<K><<<grid_for(npos, 256, 8), 256, passes * 256 * sizeof(u32), s.stream>>>(
-            s.packed[0].as<u32>(), npos, sp, 0u, s.keys_a.as<K>(), s.vals_a.as<u32>(), 0, s.radix.hist.as<u64>(), passes, 0u, 1u, ctr + 5);
+            s.packed[0].as<u32>(), npos, sp, 0u, s.keys_a.as<K>(), s.vals_a.as<u32>(), 0, s.radix.hist.as<u64>(), passes, (u32)shard, (u32)nshard, ctr + 5,
+            split);
         s.launches++;
+        if (nshard > 1) {   // how many seeds this shard owns: sizes the sort
+            MCU_CUDA(cudaMemcpyAsync(s.h_counters, ctr, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+            MCU_CUDA(cudaStreamSynchronize(s.stream));
+            npos = s.h_counters[5];
+        }
         MCU_CUDA(cudaEventRecord(s.ev[2], s.stream));
         u64 before = s.radix.launches;
         MCU_TRY(radix_sort_pairs<K>(s.radix, s.keys_a.as<K>(), s.vals_a.as<u32>(), s.keys_b.as<K>(), s.vals_b.as<u32>(), npos, key_bits, true,
@@ -981,13 +1012,14 @@ static int sml_build_t(Session& s, const SeedParams& sp, u32* pos_out, u64* mer_
     return MCU_OK;
 }
 
-int sml_build_device(Session& s, const char* seq, u64 n, u64 seed, u32* pos_out, u64* mer_out, u32* packed_out, u64* len_out)
+int sml_build_device(Session& s, const char* seq, u64 n, u64 seed, u32* pos_out, u64* mer_out, u32* packed_out, u64* len_out, int shard, int nshard)
 {
     SeedParams sp;
     MCU_TRY(make_seed_params(seed, &sp));
+    if (nshard < 1 || nshard > 16 || shard < 0 || shard >= nshard) { set_error("sorted mer list: bad shard %d of %d (at most 16)", shard, nshard); return MCU_EINVAL; }
     MCU_TRY(session_upload(s, seq, n, nullptr, 0));
-    if (2 * sp.w + 2 <= 32) return sml_build_t<u32>(s, sp, pos_out, mer_out, packed_out, len_out);
-    return sml_build_t<u64>(s, sp, pos_out, mer_out, packed_out, len_out);
+    if (2 * sp.w + 2 <= 32) return sml_build_t<u32>(s, sp, pos_out, mer_out, packed_out, len_out, shard, nshard);
+    return sml_build_t<u64>(s, sp, pos_out, mer_out, packed_out, len_out, shard, nshard);
 }
 
 }  // namespace mcu

@@ -105,7 +105,7 @@ int run_pack_piece(Session& s, int g, int c, u32* err_flag, u64* bases_ready);
 bool bucket_plan_applies(const SeedParams& sp, u64 npos0, u64 npos1, int shard_count);
 
 // single-genome SML (stable): outputs on device in s.keys_*/vals_* ; returns which buffer
-int sml_build_device(Session& s, const char* seq, u64 n, u64 seed, u32* pos_out, u64* mer_out, u32* packed_out, u64* len_out);
+int sml_build_device(Session& s, const char* seq, u64 n, u64 seed, u32* pos_out, u64* mer_out, u32* packed_out, u64* len_out, int shard = 0, int nshard = 1);
 
 #ifdef __CUDACC__
 // ---- probing one diagonal of the two packed genomes (shared by join/extend and the bucket replay) ----

@@ -213,6 +213,16 @@ int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out,
     return sml_build_device(*s, seq, n, seed, pos_out, mer_out, packed_out, sml_len_out);
 }
 
+int mcu_sml_build_shard(const char* seq, uint64_t n, uint64_t seed, int shard, int n_shards, uint32_t* pos_out, uint64_t* mer_out, uint64_t* shard_len_out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    if (n && !seq) { set_error("mcu_sml_build_shard: NULL sequence"); return MCU_EINVAL; }
+    Session* s;
+    MCU_TRY(default_session(&s));
+    return sml_build_device(*s, seq, n, seed, pos_out, mer_out, nullptr, shard_len_out, shard, n_shards);
+}
+
 void mcu_sml_last_stats(float* out6)
 {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -372,4 +372,66 @@ int mcu_find_mums_sharded(const char* seq0, uint64_t n0, const char* seq1, uint6
     return MCU_OK;
 }
 
+// Sorted-mer-list build sharded by key range (the materialised position array): every rank scans the genome, keeps the
+// seeds of its range (anchor.cu SmlSplit), sorts them; the ranks' lists, one after the other, are the sorted list.  One
+// ncclAllGather of the lengths, one group of ncclSend / ncclRecv of the 4-byte positions to rank 0.  pos_out (rank 0): n - L + 1
+// positions; equal mers come in unspecified order inside their run (the reference's own order there is std::sort's).
+int mcu_sml_build_sharded(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out, uint64_t* sml_len_out, float* ms_out)
+{
+    std::lock_guard<std::mutex> lk(api_mutex());
+    MCU_TRY(comm_ready());
+    if (n && !seq) { set_error("mcu_sml_build_sharded: NULL sequence"); return MCU_EINVAL; }
+    Session* s;
+    MCU_TRY(default_session(&s));
+    Comm& c = g_comm;
+    const int W = c.world;
+    u64 mine = 0;
+    cudaEvent_t e0 = s->kev[10], e1 = s->kev[11];   // (kev 9..11 are not used by the enumeration)
+    MCU_CUDA(cudaEventRecord(e0, s->stream));
+    if (W == 1) {
+        MCU_TRY(sml_build_device(*s, seq, n, seed, pos_out, nullptr, nullptr, &mine));
+        if (sml_len_out) *sml_len_out = mine;
+        MCU_CUDA(cudaEventRecord(e1, s->stream));
+        MCU_CUDA(cudaStreamSynchronize(s->stream));
+        if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+        return MCU_OK;
+    }
+    MCU_TRY(sml_build_device(*s, seq, n, seed, nullptr, nullptr, nullptr, &mine, c.rank, W));
+    if (!s->h_comm) MCU_CUDA(cudaHostAlloc((void**)&s->h_comm, (size_t)(W + 1) * 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    MCU_TRY(s->comm_small.reserve((size_t)(W + 1) * 8 * sizeof(unsigned long long)));
+    unsigned long long* h_send = s->h_comm;
+    unsigned long long* h_all = s->h_comm + 8;
+    unsigned long long* d_send = s->comm_small.as<unsigned long long>();
+    unsigned long long* d_all = d_send + 8;
+    h_send[0] = mine;
+    MCU_CUDA(cudaMemcpyAsync(d_send, h_send, 8, cudaMemcpyHostToDevice, s->stream));
+    MCU_NCCL(g_nccl.AllGather(d_send, d_all, 1, ncclUint64, c.comm, s->stream));
+    MCU_CUDA(cudaMemcpyAsync(h_all, d_all, (size_t)W * 8, cudaMemcpyDeviceToHost, s->stream));
+    MCU_CUDA(cudaStreamSynchronize(s->stream));
+    u64 total = 0;
+    for (int k = 0; k < W; ++k) total += h_all[k];
+    if (c.rank == 0) MCU_TRY(s->gathered.reserve((total + 1) * sizeof(u32)));
+    MCU_NCCL(g_nccl.GroupStart());
+    if (c.rank == 0) {
+        u64 off = h_all[0];
+        for (int k = 1; k < W; ++k) {
+            if (h_all[k]) MCU_NCCL(g_nccl.Recv(s->gathered.as<u32>() + off, h_all[k], ncclUint32, k, c.comm, s->stream));
+            off += h_all[k];
+        }
+    } else if (mine)
+        MCU_NCCL(g_nccl.Send(s->sml_vals, mine, ncclUint32, 0, c.comm, s->stream));
+    MCU_NCCL(g_nccl.GroupEnd());
+    if (c.rank == 0) {
+        if (mine) MCU_CUDA(cudaMemcpyAsync(s->gathered.p, s->sml_vals, mine * sizeof(u32), cudaMemcpyDeviceToDevice, s->stream));
+        MCU_CUDA(cudaEventRecord(e1, s->stream));
+        if (pos_out && total) MCU_CUDA(cudaMemcpyAsync(pos_out, s->gathered.p, total * sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
+    } else
+        MCU_CUDA(cudaEventRecord(e1, s->stream));
+    MCU_CUDA(cudaStreamSynchronize(s->stream));
+    MCU_CUDA(cudaGetLastError());
+    if (sml_len_out) *sml_len_out = total;
+    if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+    return MCU_OK;
+}
+
 }  // extern "C"

@@ -26,7 +26,7 @@ __all__ = [
     "bmer", "DNAMemorySML", "read_sslist", "write_sslist", "Match", "MatchList", "MemHash", "PairwiseMatchFinder", "AnchorSession", "merge_matches",
     "PWPath", "GlobalAlign", "GlobalAlignBatch", "GlobalAlignBatchWild", "Params", "hmm_params", "getAdaptedHoxdMatrixParameters", "adaptToPercentIdentity",
     "run", "run_batch", "sort_pairs", "SeedOccurrenceList", "GetPairwiseAnchorScore", "anchor_scores", "hoxd_matrix",
-    "EliminateOverlaps_v2", "IdentifyBreakpoints", "ComputeLCBs_v2",
+    "EliminateOverlaps_v2", "IdentifyBreakpoints", "ComputeLCBs_v2", "sml_build_shard", "sml_build_sharded",
 ]
 
 
@@ -597,6 +597,33 @@ def merge_matches(rows, in_device=False, n=None, return_unclean=False):
     res = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_int64)), shape=(k, 3)).copy() if k else np.zeros((0, 3), dtype=np.int64)
     lib().mcu_free(out)
     return (res, int(unclean.value)) if return_unclean else res
+
+
+# ---- sorted mer list sharded by mer range -------------------------------------------------------------------------
+def sml_build_shard(seq, seed, shard, n_shards, want_mers=True):
+    """shard `shard` of `n_shards` of DNAMemorySML::Create's sorted list: (positions, mers) of the seeds whose canonical mer lies in the
+    shard's range; the shards' lists, one after the other, are the whole list (equal mers in unspecified order inside their run)"""
+    addr, n, keep = _buf(seq)
+    L = getSeedLength(seed)
+    m = max(n - L + 1, 1)
+    pos = np.zeros(m, dtype=np.uint32)
+    mer = np.zeros(m, dtype=np.uint64) if want_mers else None
+    out_len = C.c_uint64(0)
+    check(lib().mcu_sml_build_shard(addr, n, seed, int(shard), int(n_shards), pos.ctypes.data, mer.ctypes.data if want_mers else None, C.byref(out_len)))
+    k = int(out_len.value)
+    return (pos[:k].copy(), mer[:k].copy()) if want_mers else pos[:k].copy()
+
+
+def sml_build_sharded(seq, seed):
+    """collective over the communicator of dist.init_from_env(): every rank passes the same sequence; rank 0 gets the positions of the
+    whole sorted list (others: None).  Returns (positions or None, device ms on this rank)."""
+    addr, n, keep = _buf(seq)
+    L = getSeedLength(seed)
+    pos = np.zeros(max(n - L + 1, 1), dtype=np.uint32)
+    out_len = C.c_uint64(0)
+    ms = C.c_float(0)
+    check(lib().mcu_sml_build_sharded(addr, n, seed, pos.ctypes.data, C.byref(out_len), C.byref(ms)))
+    return pos[:int(out_len.value)], float(ms.value)
 
 
 # ---- LM/ProgressiveAligner.h:300-406, LM/MatchList.h:680-692, LM/GreedyBreakpointElimination.h:161-250 (SURVEY.md 8f-1) -------------

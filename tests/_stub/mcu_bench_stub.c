@@ -165,6 +165,16 @@ void mcu_nw_last_stats(uint64_t* out5)
 int mcu_hmm_params(double gc, double go_h, double go_u, double pct, double* out) { orc_hmm_params(gc, go_h, go_u, pct, out); return 0; }
 int mcu_test_sort_pairs(void* k, void* v, uint64_t n, int bits, int kb) { (void)k; (void)v; (void)n; (void)bits; (void)kb; return -1; }
 int mcu_test_int32_peak(double* gops, float* ms) { if (gops) *gops = 1000.0; if (ms) *ms = 1.0f; return 0; }
+int mcu_sml_build_shard(const char* seq, uint64_t n, uint64_t seed, int shard, int n_shards, uint32_t* pos_out, uint64_t* mer_out, uint64_t* len_out)
+{
+    (void)shard; (void)n_shards;   /* the stand-in has one shard */
+    return mcu_sml_build(seq, n, seed, pos_out, mer_out, NULL, len_out);
+}
+int mcu_sml_build_sharded(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out, uint64_t* len_out, float* ms_out)
+{
+    if (ms_out) *ms_out = 1.0f;
+    return mcu_sml_build(seq, n, seed, pos_out, NULL, NULL, len_out);
+}
 int mcu_test_hmm_counters(uint64_t* out3) { if (out3) out3[0] = out3[1] = out3[2] = 0; return 0; }
 
 /* ---- round 2 entry points: caller-buffer form, chunked upload, the library's own communicator ------------------------------------ */

@@ -71,6 +71,8 @@ def test_bench_main_line_dry_run():
     assert "error" not in line["hmm"], line["hmm"]
     assert line["hmm"]["value"] > 0 and line["hmm"]["strings"] == 6 and line["hmm"]["single_string"]["columns"] == 3000
     assert line["clocks"] is not None and "reasons" in line["clocks"]
+    assert "error" not in line["sml_sharded"], line["sml_sharded"]
+    assert line["sml_sharded"]["n_gpus"] == 1 and line["sml_sharded"]["value"] > 0 and line["sml_sharded"]["list_length"] > 0
     assert "error" not in line["config4"], line["config4"]
     assert len(line["config4"]["rows"]) == 8 and line["config4"]["pair_step"]["matches"] > 0 and line["config4"]["genome_bp"] == 200000
     assert line["hmm"]["wall_ms_with_posteriors_back"] > 0 and line["rank_loop_ms"]["max"] > 0

@@ -227,6 +227,31 @@ def test_nw_errors(mp):
     assert mp.GlobalAlignBatch([]) == []
 
 
+def test_sml_shards_concatenate_to_the_sorted_list(mp):
+    """SURVEY 8e, sorted mer list sharded by mer range: the shards' lists, one after the other, carry the mer sequence of the
+    unsharded list and, run by run, the same positions; the ranges are balanced"""
+    g = synth.random_genome(3_000_000, 0.47, synth.rng_for(17)).tobytes()
+    for w, r in ((15, 3), (19, 3), (11, 0), (21, 0)):
+        seed = mp.getSeed(w, r)
+        sml = mp.DNAMemorySML()
+        sml.Create(g, seed)
+        pos_u, mer_u = sml.positions(), sml.mers()
+        for world in (2, 5, 8):
+            parts = [mp.libmems.sml_build_shard(g, seed, k, world) for k in range(world)]
+            pos_s = np.concatenate([p for p, _ in parts])
+            mer_s = np.concatenate([m for _, m in parts])
+            assert np.array_equal(mer_s, mer_u), (w, r, world)
+            assert np.array_equal(np.sort(pos_s), np.arange(pos_u.size, dtype=np.uint32))
+            # run by run the same positions: sorting (mer, position) pairs makes the order inside runs comparable
+            a = np.lexsort((pos_s, mer_s))
+            b = np.lexsort((pos_u, mer_u))
+            assert np.array_equal(pos_s[a], pos_u[b]), (w, r, world)
+            sizes = np.array([p.size for p, _ in parts], dtype=np.float64)
+            assert sizes.max() / sizes.mean() < 1.25, (w, r, world, sizes.tolist())
+    with pytest.raises(mp.McuError):
+        mp.libmems.sml_build_shard(g, mp.getSeed(15, 3), 3, 3)
+
+
 # ---- HMM ------------------------------------------------------------------------------------------
 def _check_hmm(pred, post, ref_pred, ref_post, exact=True):
     """north_star bar: 1e-5 relative on the posterior.  The default (bfloat-faithful) path is held to more: the reference's

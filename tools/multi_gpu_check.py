@@ -69,8 +69,26 @@ def worker(args):
         t0 = time.perf_counter()
         check(lib.mcu_find_mums_sharded(ab, len(ab), bb, len(bb), seed, 0, buf.ctypes.data, cap, C.byref(n_out), None))
         e2e.append(comm.allreduce([1e3 * (time.perf_counter() - t0)], mdist.MAX)[0])
+    # sorted mer list of genome 0 sharded by mer range (mcu_sml_build_sharded): positions gathered on rank 0
+    sml_ms = []
+    for i in range(3):
+        comm.barrier()
+        t0 = time.perf_counter()
+        spos, dev_ms = mp.libmems.sml_build_sharded(ab, seed)
+        sml_ms.append((comm.allreduce([1e3 * (time.perf_counter() - t0)], mdist.MAX)[0], comm.allreduce([dev_ms], mdist.MAX)[0]))
     ok = True
     if rank == 0:
+        sml = mp.DNAMemorySML()
+        t0 = time.perf_counter()
+        sml.Create(ab, seed)
+        t1 = 1e3 * (time.perf_counter() - t0)
+        pos_u, mer_u = sml.positions(), sml.mers()
+        mer_by_pos = np.empty_like(mer_u)
+        mer_by_pos[pos_u] = mer_u
+        out["sml_sharded"] = {"wall_ms": min(x[0] for x in sml_ms), "device_ms": min(x[1] for x in sml_ms), "single_gpu_wall_ms_with_mers_back": t1,
+                              "same_mer_sequence": bool(spos.size == pos_u.size and np.array_equal(mer_by_pos[spos], mer_u)),
+                              "a_permutation": bool(np.array_equal(np.sort(spos), np.arange(pos_u.size, dtype=np.uint32)))}
+        ok = out["sml_sharded"]["same_mer_sequence"] and out["sml_sharded"]["a_permutation"]
         out.update(rows=int(rows.shape[0]), sharded_ms=sorted(ms), device_ms_rank0=sorted(dev), e2e_ms=sorted(e2e), sha1=sha(rows),
                    stage_ms_per_rank=[np.frombuffer(x, dtype=np.float64).tolist() for x in all_stage])
         out["e2e_same"] = int(n_out.value) == rows.shape[0] and sha(buf[:int(n_out.value)]) == out["sha1"]
@@ -85,7 +103,7 @@ def worker(args):
         srows = single.download().copy()
         out["single_rows"] = int(n1)
         out["same_as_single_gpu"] = bool(srows.shape == rows.shape and sha(srows) == out["sha1"])
-        ok = out["same_as_single_gpu"] and out["e2e_same"]
+        ok = ok and out["same_as_single_gpu"] and out["e2e_same"]
         gp = os.path.join(ROOT, "tests", "golden", "config3_rows.json")
         if args.mbp == 100 and os.path.exists(gp) and not args.weight:
             g = json.load(open(gp))
