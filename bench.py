@@ -709,7 +709,7 @@ def main():
                            "genome_bp": int(a.size), "seed": hex(seed), "wall_ms": 1e3 * w, "device_ms": d, "value": a.size / 1e6 / w,
                            "device_mbp_s": a.size / 1e6 / (d * 1e-3), "list_length": int(spos.size) if rank == 0 else None,
                            "note": "every rank uploads and scans the genome, sorts the seeds of its mer range, ncclSend/Recv of the 4-byte positions to "
-                                   "rank 0; pageable host sequence in, positions back to host on rank 0 (wall) / CUDA events around upload .. gather (device)"}
+                                   "rank 0; wall: pageable host sequence in, positions back to pageable host memory on rank 0 (400 MB: that copy is most of it); device: CUDA events from the genome being in HBM to the gathered list being in rank 0's HBM (pack, scan, sort, gather)"}
         except Exception as e:  # noqa: BLE001
             sml_sharded = {"error": "%s: %s" % (type(e).__name__, e)}
 

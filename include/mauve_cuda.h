@@ -79,7 +79,8 @@ int mcu_sml_build(const char* seq, uint64_t n, uint64_t seed,
  * (the reference's own order there is std::sort's).  *shard_len_out = this shard's length; pos_out / mer_out need that much room
  * (n - L + 1 always suffices).  mcu_sml_build_sharded is the collective form over the communicator of mcu_comm_init: every rank
  * passes the same sequence and builds its shard, the positions are gathered on rank 0 (pos_out, n - L + 1 entries, used there only);
- * ms_out (optional): device ms of the call on this rank, CUDA events around upload, scan, sort and gather. */
+ * ms_out (optional): device ms on this rank from the genome being in HBM to the gathered list being in rank 0's HBM (pack, scan,
+ * sort, gather; CUDA events). */
 int mcu_sml_build_shard(const char* seq, uint64_t n, uint64_t seed, int shard, int n_shards, uint32_t* pos_out, uint64_t* mer_out,
                         uint64_t* shard_len_out);
 int mcu_sml_build_sharded(const char* seq, uint64_t n, uint64_t seed, uint32_t* pos_out, uint64_t* sml_len_out, float* ms_out);

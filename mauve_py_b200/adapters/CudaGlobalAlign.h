@@ -109,7 +109,90 @@ inline void EdgesToPath(const char* e, uint32_t len, PWPath& P)
 	}
 }
 
+// The same check on the GLOBALS the profile columns are derived from (ProfileFromMSA, MU/profilefrommsa.cpp:283-297: a column of a
+// one-sequence alignment without gaps gets gap open = close = g_scoreGapOpen / 2 and the substitution matrix row of its letter), for
+// callers that hold the sequences themselves and never build the profiles.
+inline bool DefaultScoringGlobals()
+{
+	static const SCORE nuc[4][4] = {{151, -54, 29, -63}, {-54, 160, -65, 29}, {29, -65, 160, -54}, {-63, 29, -54, 151}};
+	if (g_scoreGapExtend.get() != 0 || g_PPScore.get() != PPSCORE_SPN || g_scoreGapOpen.get() != (SCORE)-400) return false;
+	if (g_Alpha.get() != ALPHA_DNA) return false;
+	for (unsigned i = 0; i < 4; ++i)
+		for (unsigned j = 0; j < 4; ++j)
+			if ((*g_ptrScoreMatrix.get())[i][j] != nuc[i][j]) return false;
+	return true;
+}
+
+// the device letter of a character of a one-sequence DNA alignment row (MU/alpha.cpp:123-141, case folded as CharToLetterEx does):
+// A C G T, 'X', 'N' for the other wildcards (same classes as SingleLetterOrWildcard); 0 for anything else
+inline char DeviceLetterOfChar(char ch)
+{
+	switch (ch) {
+	case 'A': case 'a': return 'A';
+	case 'C': case 'c': return 'C';
+	case 'G': case 'g': return 'G';
+	case 'T': case 't': return 'T';
+	case 'X': case 'x': return 'X';
+	case 'M': case 'R': case 'W': case 'S': case 'Y': case 'K': case 'V': case 'H': case 'D': case 'B': case 'N':
+	case 'm': case 'r': case 'w': case 's': case 'y': case 'k': case 'v': case 'h': case 'd': case 'b': case 'n': return 'N';
+	default: return 0;
+	}
+}
+
+// row 0 of a one-sequence alignment without gap columns as a device string; false when a character is outside the DNA alphabet
+inline bool MsaRowToString(const MSA& msa, std::string& out, bool* has_wildcard)
+{
+	const unsigned n = msa.GetColCount();
+	out.resize(n);
+	*has_wildcard = false;
+	for (unsigned i = 0; i < n; ++i) {
+		const char c = DeviceLetterOfChar(msa.GetChar(0, i));
+		if (!c) return false;
+		if (c == 'N' || c == 'X') *has_wildcard = true;
+		out[i] = c;
+	}
+	return n > 0;
+}
+
 }  // namespace cuda_detail
+
+// what the two device entries take: the ranges whose columns are all A/C/G/T (integer wavefront kernels, mcu_nw_batch) and the ranges
+// with N / X columns (float wavefront kernel with the reference's arithmetic, mcu_nw_batch_wild)
+struct CudaDPGroups {
+	struct Group {
+		std::string a, b;
+		std::vector<uint64_t> a_off, b_off, p_off;
+		std::vector<size_t> index;
+		Group() : a_off(1, 0), b_off(1, 0), p_off(1, 0) {}
+	} g[2];
+	void Add(size_t index, const std::string& sa, const std::string& sb, bool wildcard)
+	{
+		Group& x = g[wildcard ? 1 : 0];
+		x.a += sa; x.b += sb;
+		x.a_off.push_back(x.a.size()); x.b_off.push_back(x.b.size()); x.p_off.push_back(x.p_off.back() + sa.size() + sb.size());
+		x.index.push_back(index);
+	}
+	void Run(PWPath* paths, std::vector<bool>& handled, std::vector<long long>* scores)
+	{
+		for (int k = 0; k < 2; ++k) {
+			const size_t m = g[k].index.size();
+			if (!m) continue;
+			std::vector<char> path(g[k].p_off.back());
+			std::vector<uint32_t> plen(m);
+			std::vector<int64_t> score(m);
+			std::vector<float> fscore(m);
+			const int rc = k == 0
+				? mcu_nw_batch(m, g[k].a.data(), &g[k].a_off[0], g[k].b.data(), &g[k].b_off[0], &g[k].p_off[0], &path[0], &plen[0], &score[0], NULL)
+				: mcu_nw_batch_wild(m, g[k].a.data(), &g[k].a_off[0], g[k].b.data(), &g[k].b_off[0], &g[k].p_off[0], &path[0], &plen[0], &fscore[0], NULL);
+			if (rc != MCU_OK) throw std::runtime_error(std::string("CudaGlobalAlignBatch: ") + mcu_last_error());
+			for (size_t j = 0; j < m; ++j) {
+				cuda_detail::EdgesToPath(&path[g[k].p_off[j]], plen[j], paths[g[k].index[j]]);
+				handled[g[k].index[j]] = true;
+				if (scores) (*scores)[g[k].index[j]] = k == 0 ? score[j] : (long long)fscore[j];
+			}
+		}
+	}
+};
 
 // Aligns every range on the device; paths (ranges.size() caller-owned objects: PWPath is not copyable) is filled for
 // handled[i] == true.
@@ -120,43 +203,40 @@ inline void CudaGlobalAlignBatch(const std::vector<CudaDPRange>& ranges, PWPath*
 	for (size_t i = 0; i < n; ++i) paths[i].Clear();
 	handled.assign(n, false);
 	if (scores) scores->assign(n, 0);
-	// two groups: columns that are all A/C/G/T (integer wavefront kernels, mcu_nw_batch) and ranges with N / X columns (float wavefront
-	// kernel with the reference's arithmetic, mcu_nw_batch_wild; `wildcards` = false leaves those to the caller)
-	struct Group {
-		std::string a, b;
-		std::vector<uint64_t> a_off, b_off, p_off;
-		std::vector<size_t> index;
-		Group() : a_off(1, 0), b_off(1, 0), p_off(1, 0) {}
-	} g[2];
+	CudaDPGroups groups;
 	std::string sa, sb;
 	for (size_t i = 0; i < n; ++i) {
 		bool wa = false, wb = false;
 		if (!cuda_detail::ProfileToStringWild(ranges[i].PA, ranges[i].uLengthA, sa, &wa) || !cuda_detail::ProfileToStringWild(ranges[i].PB, ranges[i].uLengthB, sb, &wb))
 			continue;
-		const int k = (wa || wb) ? 1 : 0;
-		if (k == 1 && !wildcards) continue;
+		if ((wa || wb) && !wildcards) continue;
 		if (!cuda_detail::DefaultScoring(ranges[i].PA, ranges[i].uLengthA) || !cuda_detail::DefaultScoring(ranges[i].PB, ranges[i].uLengthB)) continue;
-		g[k].a += sa; g[k].b += sb;
-		g[k].a_off.push_back(g[k].a.size()); g[k].b_off.push_back(g[k].b.size()); g[k].p_off.push_back(g[k].p_off.back() + sa.size() + sb.size());
-		g[k].index.push_back(i);
+		groups.Add(i, sa, sb, wa || wb);
 	}
-	for (int k = 0; k < 2; ++k) {
-		const size_t m = g[k].index.size();
-		if (!m) continue;
-		std::vector<char> path(g[k].p_off.back());
-		std::vector<uint32_t> plen(m);
-		std::vector<int64_t> score(m);
-		std::vector<float> fscore(m);
-		const int rc = k == 0
-			? mcu_nw_batch(m, g[k].a.data(), &g[k].a_off[0], g[k].b.data(), &g[k].b_off[0], &g[k].p_off[0], &path[0], &plen[0], &score[0], NULL)
-			: mcu_nw_batch_wild(m, g[k].a.data(), &g[k].a_off[0], g[k].b.data(), &g[k].b_off[0], &g[k].p_off[0], &path[0], &plen[0], &fscore[0], NULL);
-		if (rc != MCU_OK) throw std::runtime_error(std::string("CudaGlobalAlignBatch: ") + mcu_last_error());
-		for (size_t j = 0; j < m; ++j) {
-			cuda_detail::EdgesToPath(&path[g[k].p_off[j]], plen[j], paths[g[k].index[j]]);
-			handled[g[k].index[j]] = true;
-			if (scores) (*scores)[g[k].index[j]] = k == 0 ? score[j] : (long long)fscore[j];
-		}
+	groups.Run(paths, handled, scores);
+}
+
+// The same for pairs of ONE-SEQUENCE alignments without gap columns (what AnchoredProfileProfile's ranges are for two genomes): the
+// letters are read from the alignment rows and the profiles (ProfileFromMSA: counts, SortCounts, score rows per column -- 1.4 s of the
+// MDS42 run's host time) are never built.  A pair is left to the caller (handled[i] == false) when a row holds a character outside the
+// DNA alphabet or MUSCLE's scoring globals are not the defaults the kernels have built in.
+inline void CudaGlobalAlignBatchRows(const std::vector<std::pair<const MSA*, const MSA*> >& pairs, PWPath* paths, std::vector<bool>& handled,
+                                     bool wildcards = true)
+{
+	const size_t n = pairs.size();
+	for (size_t i = 0; i < n; ++i) paths[i].Clear();
+	handled.assign(n, false);
+	if (!cuda_detail::DefaultScoringGlobals()) return;
+	CudaDPGroups groups;
+	std::string sa, sb;
+	for (size_t i = 0; i < n; ++i) {
+		bool wa = false, wb = false;
+		if (pairs[i].first->GetSeqCount() != 1 || pairs[i].second->GetSeqCount() != 1) continue;
+		if (!cuda_detail::MsaRowToString(*pairs[i].first, sa, &wa) || !cuda_detail::MsaRowToString(*pairs[i].second, sb, &wb)) continue;
+		if ((wa || wb) && !wildcards) continue;
+		groups.Add(i, sa, sb, wa || wb);
 	}
+	groups.Run(paths, handled, NULL);
 }
 
 }  // namespace muscle

@@ -92,12 +92,16 @@ void AnchoredProfileProfile(MSA& msa1, MSA& msa2, MSA& msaOut)
 		msaOut.SetSeqId(uSeqIndex, uSeqIndex);
 	}
 
-	// :504-549, phase 1: the sub-alignments and profiles of every non-empty range, in range order
+	// :504-549, phase 1: the sub-alignments of every non-empty range, in range order.  For two genomes both are one-sequence alignments
+	// without gap columns: their letters go to the device as they are -- no profile is built for them (MAUVE_CUDA_DP_PROFILES=1 takes
+	// the round-1 route through ProfileFromMSA and the per-column check of the scoring, for A/B runs)
+	static const bool via_profiles = getenv("MAUVE_CUDA_DP_PROFILES") && getenv("MAUVE_CUDA_DP_PROFILES")[0] == '1';
 	struct Job {
 		MSA* m1; MSA* m2; ProfPos* P1; ProfPos* P2; bool device;
 	};
 	std::vector<Job> jobs;
 	std::vector<CudaDPRange> dp;
+	std::vector<std::pair<const MSA*, const MSA*> > rows;
 	std::vector<size_t> dp_job;
 	for (unsigned uRangeIndex = 0; uRangeIndex < uRangeCount; ++uRangeIndex) {
 		const Range& r = Ranges[uRangeIndex];
@@ -114,13 +118,16 @@ void AnchoredProfileProfile(MSA& msa1, MSA& msa2, MSA& msaOut)
 		StripGapColumns(*j.m1);
 		StripGapColumns(*j.m2);
 		const unsigned l1 = j.m1->GetColCount(), l2 = j.m2->GetColCount();
-		if (l1 > 0 && l2 > 0 && j.m1->GetSeqCount() == 1 && j.m2->GetSeqCount() == 1) {   // the two-genome form the integer kernel covers
-			Tree tree1, tree2;
-			j.P1 = ProfileOf(*j.m1, tree1);
-			j.P2 = ProfileOf(*j.m2, tree2);
-			CudaDPRange d;
-			d.PA = j.P1; d.uLengthA = l1; d.PB = j.P2; d.uLengthB = l2;
-			dp.push_back(d);
+		if (l1 > 0 && l2 > 0 && j.m1->GetSeqCount() == 1 && j.m2->GetSeqCount() == 1) {   // the two-genome form the kernels cover
+			if (via_profiles) {
+				Tree tree1, tree2;
+				j.P1 = ProfileOf(*j.m1, tree1);
+				j.P2 = ProfileOf(*j.m2, tree2);
+				CudaDPRange d;
+				d.PA = j.P1; d.uLengthA = l1; d.PB = j.P2; d.uLengthB = l2;
+				dp.push_back(d);
+			} else
+				rows.push_back(std::make_pair((const MSA*)j.m1, (const MSA*)j.m2));
 			dp_job.push_back(jobs.size());
 		}
 		jobs.push_back(j);
@@ -128,13 +135,15 @@ void AnchoredProfileProfile(MSA& msa1, MSA& msa2, MSA& msaOut)
 	g_seam_ranges += jobs.size();
 
 	// phase 2: every DP of this window in one device call
-	PWPath* paths = dp.empty() ? 0 : new PWPath[dp.size()];
+	const size_t n_dp = dp_job.size();
+	PWPath* paths = n_dp == 0 ? 0 : new PWPath[n_dp];
 	std::vector<bool> handled;
-	if (!dp.empty()) {
+	if (n_dp) {
 		try {
-			// MAUVE_CUDA_WILD=1: ranges with N / X columns go to mcu_nw_batch_wild instead of the reference's NWSmall
+			// ranges with N / X columns go to mcu_nw_batch_wild (MAUVE_CUDA_WILD=0: to the reference's NWSmall, for A/B runs)
 			static const bool wild = !(getenv("MAUVE_CUDA_WILD") && getenv("MAUVE_CUDA_WILD")[0] == '0');
-			CudaGlobalAlignBatch(dp, paths, handled, NULL, wild);
+			if (via_profiles) CudaGlobalAlignBatch(dp, paths, handled, NULL, wild);
+			else CudaGlobalAlignBatchRows(rows, paths, handled, wild);
 		} catch (std::exception& e) {
 			// MuscleInterface::ProfileAlignFast swallows every exception (LM/MuscleInterface.cpp:1155-1159) and the aligner would go on
 			// without this window: a device failure must stop the run, the way MUSCLE's own Quit() does
@@ -143,7 +152,7 @@ void AnchoredProfileProfile(MSA& msa1, MSA& msa2, MSA& msaOut)
 		}
 	}
 	std::vector<long> path_of(jobs.size(), -1);
-	for (size_t k = 0; k < dp.size(); ++k)
+	for (size_t k = 0; k < n_dp; ++k)
 		if (handled[k]) { jobs[dp_job[k]].device = true; path_of[dp_job[k]] = (long)k; ++g_seam_device; }
 
 	// phase 3: output blocks in range order

@@ -386,8 +386,7 @@ int mcu_sml_build_sharded(const char* seq, uint64_t n, uint64_t seed, uint32_t* 
     Comm& c = g_comm;
     const int W = c.world;
     u64 mine = 0;
-    cudaEvent_t e0 = s->kev[10], e1 = s->kev[11];   // (kev 9..11 are not used by the enumeration)
-    MCU_CUDA(cudaEventRecord(e0, s->stream));
+    cudaEvent_t e0 = s->ev[0], e1 = s->kev[11];   // ev[0]: recorded by the build once the genome is in HBM; (kev 9..11 are not used by the enumeration)
     if (W == 1) {
         MCU_TRY(sml_build_device(*s, seq, n, seed, pos_out, nullptr, nullptr, &mine));
         if (sml_len_out) *sml_len_out = mine;
