@@ -470,8 +470,8 @@ __device__ __forceinline__ u32 bkf_reserve(const BkScatterSmem& s, u32 bins, uns
     return total;
 }
 
-template <bool SOLID>
-__global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_kernel(const u32* __restrict__ g0, const u32* __restrict__ g1, BkPlan pl, SeedParams sp,
+template <bool SOLID, int MINB>
+__global__ void __launch_bounds__(BK_THREADS, MINB) bkf_scatter1_kernel(const u32* __restrict__ g0, const u32* __restrict__ g1, BkPlan pl, SeedParams sp,
                                                                     unsigned long long* __restrict__ cursor1, u64* __restrict__ recs, BkOvf ovf, u32 tile_base)
 {
     extern __shared__ __align__(16) unsigned char raw[];
@@ -723,7 +723,8 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_multi_kernel(const
 }
 
 // level-2 partition of one tile of level-1 bucket b_lo + blockIdx.y into its B2 final buckets
-__global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter2_kernel(const u64* __restrict__ src, BkPlan pl, const unsigned long long* __restrict__ cursor1,
+template <int MINB>
+__global__ void __launch_bounds__(BK_THREADS, MINB) bkf_scatter2_kernel(const u64* __restrict__ src, BkPlan pl, const unsigned long long* __restrict__ cursor1,
                                                                     unsigned long long* __restrict__ cursor2, u64* __restrict__ dst, BkOvf ovf, u32 gsel)
 {
     extern __shared__ __align__(16) unsigned char raw[];
@@ -1421,9 +1422,12 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     const u32* g1 = s.packed[1].as<u32>();
     static bool attr_done = false;
     if (!attr_done) {
-        MCU_CUDA(cudaFuncSetAttribute(bkf_scatter1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
-        MCU_CUDA(cudaFuncSetAttribute(bkf_scatter1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
-        MCU_CUDA(cudaFuncSetAttribute(bkf_scatter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
+        MCU_CUDA(cudaFuncSetAttribute(bkf_scatter1_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
+        MCU_CUDA(cudaFuncSetAttribute(bkf_scatter1_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
+        MCU_CUDA(cudaFuncSetAttribute(bkf_scatter1_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
+        MCU_CUDA(cudaFuncSetAttribute(bkf_scatter2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
+        MCU_CUDA(cudaFuncSetAttribute(bkf_scatter2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
+        MCU_CUDA(cudaFuncSetAttribute(bkf_scatter2_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem_bytes(BK_MAXB)));
         attr_done = true;
     }
     BkOvf ovf;
@@ -1448,8 +1452,10 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
             s.launches++;
             return;
         }
-        if (solid_pattern) bkf_scatter1_kernel<true><<<t1 - t0, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf, t0);
-        else bkf_scatter1_kernel<false><<<t1 - t0, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf, t0);
+        static const int s1_minb = getenv("MAUVE_CUDA_S1_MINB") ? atoi(getenv("MAUVE_CUDA_S1_MINB")) : 3;   // A/B: registers vs occupancy
+        if (solid_pattern && s1_minb == 4) bkf_scatter1_kernel<true, 4><<<t1 - t0, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf, t0);
+        else if (solid_pattern) bkf_scatter1_kernel<true, 3><<<t1 - t0, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf, t0);
+        else bkf_scatter1_kernel<false, 3><<<t1 - t0, BK_THREADS, bk_scatter_smem_bytes(pl.B1), st>>>(g0, g1, pl, sp, cursor1, s.bk_a.as<u64>(), ovf, t0);
         s.launches++;
     };
     bool scatter2_done = false;
@@ -1477,7 +1483,7 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
                 if (upto > done) done = upto;
                 if (nb1 && last) {   // all tiles of genome g are out: its level-1 segments can be partitioned while the rest still arrives
                     const u32 capg = g ? pl.cap1g[1] : pl.cap1g[0];
-                    bkf_scatter2_kernel<<<dim3((unsigned)div_up(capg, BK_TILE), nb1), BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(
+                    bkf_scatter2_kernel<3><<<dim3((unsigned)div_up(capg, BK_TILE), nb1), BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(
                         s.bk_a.as<u64>(), pl, cursor1, cursor2, s.bk_b.as<u64>(), ovf, (u32)g);
                     s.launches++;
                     scatter2_done = true;
@@ -1491,7 +1497,10 @@ static int bucket_group_fixed(Session& s, const SeedParams& sp, BkPlan pl, int s
     MCU_CUDA(cudaEventRecord(s.kev[3], st));
     if (nb1 && !scatter2_done) {
         const dim3 grid2((unsigned)div_up(pl.cap1, BK_TILE), 2 * nb1);
-        bkf_scatter2_kernel<<<grid2, BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(s.bk_a.as<u64>(), pl, cursor1, cursor2, s.bk_b.as<u64>(), ovf, 2u);
+        static const int s2_minb = getenv("MAUVE_CUDA_S2_MINB") ? atoi(getenv("MAUVE_CUDA_S2_MINB")) : 4;   // measured (100 Mbp pair): 3 CTAs/SM (72 registers) 0.986 ms, 4 (64) 0.945
+        if (s2_minb == 5) bkf_scatter2_kernel<5><<<grid2, BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(s.bk_a.as<u64>(), pl, cursor1, cursor2, s.bk_b.as<u64>(), ovf, 2u);
+        else if (s2_minb == 4) bkf_scatter2_kernel<4><<<grid2, BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(s.bk_a.as<u64>(), pl, cursor1, cursor2, s.bk_b.as<u64>(), ovf, 2u);
+        else bkf_scatter2_kernel<3><<<grid2, BK_THREADS, bk_scatter_smem_bytes(pl.B2), st>>>(s.bk_a.as<u64>(), pl, cursor1, cursor2, s.bk_b.as<u64>(), ovf, 2u);
     }
     MCU_CUDA(cudaEventRecord(ev_scatter2, st));
     MCU_CUDA(cudaEventRecord(s.kev[4], st));
