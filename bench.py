@@ -816,7 +816,8 @@ def main():
     config4 = None
     if world == 1 and not args.no_sml and args.config4_gbp > 0:
         try:
-            sess.close()   # its buffers (3.7 GB at 100 Mbp) are not needed any more; the 1 Gbp pair takes ~60 GB
+            sess.close()
+            lib.mcu_shutdown()   # every cached device buffer of this process goes back (the DP batch alone keeps tens of GB): the 1 Gbp pair takes ~80 GB
             config4 = measure_config4(mp, synth, args, peak)
         except Exception as e:  # noqa: BLE001
             config4 = {"error": "%s: %s" % (type(e).__name__, e)}

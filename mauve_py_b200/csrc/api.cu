@@ -157,6 +157,11 @@ void mcu_shutdown(void)
         delete g_default_session;
         g_default_session = nullptr;
     }
+    // the gapped-DP, HMM and LCB entries keep their device buffers between calls: give them back too
+    nw_release();
+    nwf_release();
+    hmm_release();
+    lcb_release();
 }
 
 const char* mcu_last_error(void) { return get_error(); }

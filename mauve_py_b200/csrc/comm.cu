@@ -390,9 +390,7 @@ int mcu_sml_build_sharded(const char* seq, uint64_t n, uint64_t seed, uint32_t* 
     if (W == 1) {
         MCU_TRY(sml_build_device(*s, seq, n, seed, pos_out, nullptr, nullptr, &mine));
         if (sml_len_out) *sml_len_out = mine;
-        MCU_CUDA(cudaEventRecord(e1, s->stream));
-        MCU_CUDA(cudaStreamSynchronize(s->stream));
-        if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+        if (ms_out) cudaEventElapsedTime(ms_out, e0, s->ev[3]);   // ev[3]: the sort is done (the copy of the positions to the host follows it)
         return MCU_OK;
     }
     MCU_TRY(sml_build_device(*s, seq, n, seed, nullptr, nullptr, nullptr, &mine, c.rank, W));

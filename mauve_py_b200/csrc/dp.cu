@@ -381,6 +381,13 @@ struct NwState {
 };
 static NwState g_nw;
 
+void nw_release()   // mcu_shutdown: give the cached device buffers back
+{
+    DevBuf* bufs[] = {&g_nw.a, &g_nw.b, &g_nw.a_off, &g_nw.b_off, &g_nw.order, &g_nw.tb, &g_nw.tb_off, &g_nw.boundary, &g_nw.result, &g_nw.counter,
+                      &g_nw.path_off, &g_nw.path, &g_nw.path_len, &g_nw.path_start, &g_nw.score, &g_nw.units};
+    for (DevBuf* b : bufs) b->release();
+}
+
 void nw_last_stats(u64* out5)
 {
     for (int i = 0; i < 5; ++i) out5[i] = g_nw.stats[i];

@@ -18,4 +18,7 @@ int nw_batch_wild(u64 n, const char* a, const u64* a_off, const char* b, const u
 // register-resident add/max microbenchmark: Gops/s of thread-level INT32 instructions the device sustains (DP roofline denominator)
 int int32_peak(double* gops_out, float* ms_out);
 
+void nw_release();
+void nwf_release();
+
 }  // namespace mcu

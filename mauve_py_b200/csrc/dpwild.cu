@@ -354,6 +354,12 @@ __global__ void __launch_bounds__(256) nwf_shift_kernel(u32 count, const u64* pa
 }
 
 static DevBuf w_a, w_b, w_aoff, w_boff, w_tboff, w_pathoff, w_tb, w_bnd, w_res, w_path, w_plen, w_pstart, w_score, w_ctr;
+
+void nwf_release()
+{
+    DevBuf* bufs[] = {&w_a, &w_b, &w_aoff, &w_boff, &w_tboff, &w_pathoff, &w_tb, &w_bnd, &w_res, &w_path, &w_plen, &w_pstart, &w_score, &w_ctr};
+    for (DevBuf* b : bufs) b->release();
+}
 static cudaStream_t w_stream = nullptr;
 
 // regions [i0, i1) of the caller's batch (offsets rebased by the caller's arrays themselves: absolute offsets are used)

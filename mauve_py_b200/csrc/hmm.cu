@@ -946,6 +946,13 @@ int hmm_batch(u64 n, const char* sym, const u64* off, const double* params, char
 }
 
 
+void hmm_release()
+{
+    HmmState& st = g_hmm;
+    DevBuf* bufs[] = {&st.sym, &st.off, &st.chunk_first, &st.prod, &st.fin, &st.bin, &st.scratch, &st.pred, &st.post, &st.err, &st.fh, &st.bh, &st.total};
+    for (DevBuf* b : bufs) b->release();
+}
+
 void hmm_last_counters(u64* out3)
 {
     out3[0] = g_hmm.counters[0];

@@ -349,6 +349,15 @@ struct LcbState {
 };
 static LcbState g_lcb;
 
+void lcb_release()
+{
+    LcbState& st = g_lcb;
+    DevBuf* bufs[] = {&st.rows_a, &st.rows_b, &st.keys_a, &st.keys_b, &st.idx_a, &st.idx_b, &st.words, &st.head, &st.alive, &st.counters, &st.bp,
+                      &st.radix.hist, &st.radix.status, &st.radix.counters};
+    for (DevBuf* b : bufs) b->release();
+    st.radix.epoch = 0;
+}
+
 static int lcb_grid(u64 n)
 {
     u64 g = div_up(n, 256);
