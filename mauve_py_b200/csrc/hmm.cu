@@ -470,6 +470,47 @@ HMM_HD void hmm_regime_step(float& u, float& h, const float c[4], const float l[
     metric = hmm_regime_metric<D>(r0, r1, r2, r3);
 }
 
+// ---- the chain in a VIRTUAL mantissa domain ---------------------------------------------------------------------------------------
+// Every scaling the bfloat operations perform is by a power of two (2^+-104) and commutes with both roundings; a term that the
+// reference multiplies by aConversionLookup[>= 2] = 0, or by 2^-104 into the denormals, is far below half an ulp of the term it is
+// added to (that one is >= 1e-18) and leaves the sum unchanged either way.  So the VALUES of the recursion do not depend on how the
+// reference happens to split them into mantissa and exponent: with both states on ONE running scale (u', h' plain floats,
+// value = x' * 2^(104 sc)) the step is U' = fl(r0 + r1), H' = fl(r2 + r3) in every regime -- no exponents in the chain at all, as long
+// as u' and h' stay normal floats.  The scale follows the larger state (both are multiplied by 2^104 when it falls below 1e6, so it
+// lives in [1e-13, 2e37] and a state up to 25 decades smaller is still normal); values never grow (every coefficient sum is < 1).
+// What the reference's split IS needed for is the output -- BFloat::Value's table is filled with expf, so (f, e) and (f 2^104, e - 1)
+// print as different doubles -- and it is recovered column by column when the block is re-examined: hmm_canon maps a virtual value to
+// the form a value takes when it has only ever been renormalised downwards (mantissa in [1e-18, 1e-18 * 2^104)); the reference's own
+// form differs from it only where a sum of two just-renormalised terms lands within a factor 2 above that window (about one column in
+// 400), which the re-examination sees as "same value, other form" and hands on to the next column.
+HMM_HD void hmm_vstep(float& u, float& h, const float c[4], const float l[4])
+{
+    const float r0 = hmm_fprod(u, c[0], l[0]), r1 = hmm_fprod(h, c[1], l[1]);
+    const float r2 = hmm_fprod(u, c[2], l[2]), r3 = hmm_fprod(h, c[3], l[3]);
+    u = H_FADD(r0, r1);
+    h = H_FADD(r2, r3);
+}
+
+HMM_HD BF hmm_canon(float v, int e)
+{
+    const float L = 1.0e-18f, TOP = 1.0e-18f * 2.028240960365167e+31f;   // exact: a power-of-two multiple of the float 1e-18f
+    if (!(v > 0.0f)) return BF{0.f, -BF_INF};
+    while (v >= TOP) { v = H_FMUL(v, 4.930380657631324e-32f); ++e; }
+    while (v < L) { v = H_FMUL(v, 2.028240960365167e+31f); --e; }
+    return BF{v, e};
+}
+
+HMM_HD bool hmm_bf_same(BF a, BF b) { return H_F2U(a.f) == H_F2U(b.f) && a.e == b.e; }
+
+// a bfloat pair on one scale: sc = the larger exponent, the other mantissa multiplied by M(its exponent - sc) (0 when two or more
+// exponents below: such a state is invisible in every sum until it has been replaced)
+HMM_HD void hmm_to_virtual(BF u, BF h, float& vu, float& vh, int& sc)
+{
+    sc = u.e > h.e ? u.e : h.e;
+    vu = H_FMUL(u.f, hmm_mexp(u.e - sc));
+    vh = H_FMUL(h.f, hmm_mexp(h.e - sc));
+}
+
 // ---- tables shared by the kernels and the test-only host drivers ----
 static void build_exact_model(const double* p, HmmExactModel* m)
 {
@@ -557,20 +598,24 @@ __global__ void __launch_bounds__(64) hmm_exact_chain_kernel(const u8* __restric
 }
 
 // Few, long strings: one CTA of two warps per (string, direction), a block of 32 columns at a time, three blocks in flight.
-//   warp 0, lane 0   runs the serial recurrence of block k in its FP32 regime form (hmm_regime_step: 12 or 16 cycles of dependent
-//                    latency per column), eight columns per group with their coefficients in registers, parking the state behind
-//                    every column in shared memory.  When a group's trackers report that an exponent dropped (about once in 19
-//                    columns) it finds the column, evaluates it with the general FP32 step and carries on behind it in the new regime.
-//   warp 1           meanwhile (a) re-examines block k - 1, one column per lane, from the state parked in front of it, with
-//                    hmm_float_step -- or hmm_exact_step when a product of it is hazardous --, (b) writes that block's 32 results
-//                    with one coalesced store, (c) looks up the coefficients of block k + 1 (symbols fetched two blocks ahead).
-// A column whose parked result is not what warp 1 gets (a hazard that mattered: about one column in a million) is corrected; the
-// chain is then taken up again behind it and block k, which started from the wrong state, is run again.
+//   warp 0, lane 0   runs the serial recurrence of block k in the VIRTUAL mantissa domain (hmm_vstep: 4 FMUL + 4 FFMA + 2 FADD per
+//                    column, dependency chain FMUL -> FFMA -> FADD, no exponents, no regimes), eight columns per group with their
+//                    coefficients in registers, parking (u', h', scale) behind every column in shared memory; once per group it
+//                    looks at the scale (both states times 2^104 when the larger one has fallen below 1e6).
+//   warp 1           meanwhile (a) re-examines block k - 1, one column per lane: the state parked in front of the column in the
+//                    reference's form (hmm_canon; the lane behind a "same value, other form" column takes its neighbour's true
+//                    form), one exact column from there (hmm_float_step, or hmm_exact_step when a product of it is hazardous), and
+//                    the comparison with what is parked behind the column; (b) writes that block's 32 results -- the reference's
+//                    (mantissa, exponent) pairs -- with one coalesced store; (c) looks up the coefficients of block k + 1 (symbols
+//                    fetched two blocks ahead).
+// A column whose parked VALUE is not what warp 1 gets (a rounding hazard that mattered: about one column in 20 million) is corrected;
+// the chain is then taken up again behind it and block k, which started from the wrong state, is run again.
 // MAUVE_CUDA_HMM_FP64=1 (tests): every column through hmm_exact_step.
 struct HmmBlockBuf {
     float4 chi[40], clo[40];  // coefficients of the block's columns, role order, high and low parts; rows 32.. and the rows past a short
                               // block's end: identity (a group of eight may run past the end)
-    float4 st[41];            // st[j] = (u.f, h.f, bits of u.e, bits of h.e) in front of column j, st[j + 1] behind it
+    float4 st[41];            // st[j] = the state in front of column j as a bfloat pair (u.f, h.f, bits of u.e, bits of h.e): the
+                              // chain parks both mantissas on its running scale, a repair writes the reference's own form
     u8 xs[32];
 };
 struct HmmWarpSmem {
@@ -579,40 +624,6 @@ struct HmmWarpSmem {
     HmmBlockBuf b[3];
     int bad;                  // first corrected column of the block re-examined in this iteration, or -1
 };
-
-// eight columns from column j on (rows past the block's end hold identity coefficients: nothing happens there); returns the first
-// of them (0..7) whose regime assumption failed -- what was computed from there on is void -- or 8.  Beside the chain the group costs
-// one min per column: for D = 0 an exponent can only drop where U' or H' comes out below 2e-18 (both products below 1e-18), for
-// D != 0 the metric is a product itself; the columns are looked at one by one only when that minimum says so.
-template <int D>
-__device__ __forceinline__ u32 hmm_chain_group(HmmBlockBuf& bb, u32 j, float uf, float hf, float eu, float eh)
-{
-    float4 c[8], l[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        c[q] = bb.chi[j + q];
-        l[q] = bb.clo[j + q];
-    }
-    float lo = 3.0e38f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const float cc[4] = {c[q].x, c[q].y, c[q].z, c[q].w}, ll[4] = {l[q].x, l[q].y, l[q].z, l[q].w};
-        float metric;
-        hmm_regime_step<D>(uf, hf, cc, ll, metric);
-        bb.st[j + q + 1] = make_float4(uf, hf, eu, eh);
-        lo = D == 0 ? fminf(lo, fminf(uf, hf)) : fminf(lo, metric);
-    }
-    constexpr float two_l = 2.0f * 1.0e-18f;   // exactly twice the float 1e-18f: two products below 1e-18f sum to less than this
-    if (lo >= (D == 0 ? two_l : 1.0e-18f)) return 8u;
-    for (u32 q = 0; q < 8; ++q) {
-        const float4 v = bb.st[j + q], w = bb.st[j + q + 1];
-        if (D == 0 && w.x >= two_l && w.y >= two_l) continue;
-        const float4 cq = bb.chi[j + q], lq = bb.clo[j + q];
-        const float r0 = hmm_fprod(v.x, cq.x, lq.x), r1 = hmm_fprod(v.y, cq.y, lq.y), r2 = hmm_fprod(v.x, cq.z, lq.z), r3 = hmm_fprod(v.y, cq.w, lq.w);
-        if (hmm_regime_metric<D>(r0, r1, r2, r3) < 1.0e-18f) return q;
-    }
-    return 8u;
-}
 
 __device__ __forceinline__ void hmm_lane0_exact(HmmWarpSmem& sm, HmmBlockBuf& bb, u32 cnt, bool fwd, const HmmExactModel& m)
 {
@@ -624,58 +635,95 @@ __device__ __forceinline__ void hmm_lane0_exact(HmmWarpSmem& sm, HmmBlockBuf& bb
     }
 }
 
-// warp 0, lane 0: columns [start, cnt) of the block from the state parked at st[start]
+// warp 0, lane 0: columns [start, cnt) of the block from the state parked at st[start], in groups of eight (rows past the block's end
+// hold identity coefficients: nothing happens there)
 __device__ __forceinline__ void hmm_lane0_chain(HmmBlockBuf& bb, u32 start, u32 cnt)
 {
     const float4 s0 = bb.st[start];
-    float uf = s0.x, hf = s0.y;
-    int ue = __float_as_int(s0.z), he = __float_as_int(s0.w);
-    u32 j = start;
-    while (j < cnt) {
-        const int d = ue - he;
-        if (d >= -1 && d <= 1) {
-            const float eu = __int_as_float(ue), eh = __int_as_float(he);
-            const u32 q = d == 0 ? hmm_chain_group<0>(bb, j, uf, hf, eu, eh) : (d < 0 ? hmm_chain_group<-1>(bb, j, uf, hf, eu, eh) : hmm_chain_group<1>(bb, j, uf, hf, eu, eh));
-            j += q;
-            const float4 v = bb.st[j];
-            uf = v.x;
-            hf = v.y;
-            if (q == 8u || j >= cnt) continue;   // the whole group stands
+    float u, h;
+    int sc;
+    hmm_to_virtual(BF{s0.x, __float_as_int(s0.z)}, BF{s0.y, __float_as_int(s0.w)}, u, h, sc);
+    for (u32 j = start; j < cnt; j += 8) {
+        float4 c[8], l[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            c[q] = bb.chi[j + q];
+            l[q] = bb.clo[j + q];
         }
-        // this column on its own (an exponent moves here), from the state in front of it
-        BF u = BF{uf, ue}, h = BF{hf, he};
-        const float4 c = bb.chi[j], l = bb.clo[j];
-        const float cc[4] = {c.x, c.y, c.z, c.w}, ll[4] = {l.x, l.y, l.z, l.w};
-        hmm_float_step_t<false>(u, h, cc, ll);
-        uf = u.f; hf = h.f; ue = u.e; he = h.e;
-        ++j;
-        bb.st[j] = make_float4(uf, hf, __int_as_float(ue), __int_as_float(he));
+        if (fmaxf(u, h) < 1.0e6f) {   // the scale follows the larger state (exact: a power of two; neither state can overflow)
+            u = __fmul_rn(u, 2.028240960365167e+31f);
+            h = __fmul_rn(h, 2.028240960365167e+31f);
+            --sc;
+        }
+        const float scf = __int_as_float(sc);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float cc[4] = {c[q].x, c[q].y, c[q].z, c[q].w}, ll[4] = {l[q].x, l[q].y, l[q].z, l[q].w};
+            hmm_vstep(u, h, cc, ll);
+            bb.st[j + q + 1] = make_float4(u, h, scf, scf);
+        }
     }
 }
 
-// warp 1: columns [start, cnt) of a block, one per lane; returns the first column whose parked result had to be corrected (the lane
-// of that column has written its own), or 32
-__device__ __forceinline__ u32 hmm_reexamine(HmmWarpSmem& sm, HmmBlockBuf& bb, u32 lane, u32 start, u32 cnt, bool fwd, const HmmExactModel& m,
-                                             unsigned long long& n_exact)
+// warp 1: columns [start, cnt) of a block, one per lane.  `first` = the reference's form of the state in front of column `start`.
+// out_u / out_h: the reference's state behind this lane's column (valid for start <= lane < cnt when the call returns 32 or for
+// lanes up to the returned column).  Returns the first column whose parked VALUE had to be corrected (its lane has written the
+// reference's state behind it to st), or 32.
+__device__ __forceinline__ u32 hmm_reexamine(HmmWarpSmem& sm, HmmBlockBuf& bb, u32 lane, u32 start, u32 cnt, BF first_u, BF first_h, bool fwd,
+                                             const HmmExactModel& m, BF& out_u, BF& out_h, unsigned long long& n_exact)
 {
-    bool ok = true;
-    BF u, h;
-    if (lane >= start && lane < cnt) {
+    const bool mine = lane >= start && lane < cnt;
+    BF in_u = first_u, in_h = first_h, want_u = first_u, want_h = first_h;
+    float cc[4] = {1.f, 0.f, 0.f, 1.f}, ll[4] = {0.f, 0.f, 0.f, 0.f};
+    if (mine) {
         const float4 v = bb.st[lane], w = bb.st[lane + 1];
         const float4 c = bb.chi[lane], l = bb.clo[lane];
-        const float cc[4] = {c.x, c.y, c.z, c.w}, ll[4] = {l.x, l.y, l.z, l.w};
-        u = BF{v.x, __float_as_int(v.z)};
-        h = BF{v.y, __float_as_int(v.w)};
-        if (!hmm_float_step(u, h, cc, ll)) {
-            hmm_exact_step(u, h, sm.te[bb.xs[lane]], fwd, m);
-            ++n_exact;
+        cc[0] = c.x; cc[1] = c.y; cc[2] = c.z; cc[3] = c.w;
+        ll[0] = l.x; ll[1] = l.y; ll[2] = l.z; ll[3] = l.w;
+        if (lane != start) {
+            in_u = hmm_canon(v.x, __float_as_int(v.z));
+            in_h = hmm_canon(v.y, __float_as_int(v.w));
         }
-        ok = __float_as_uint(u.f) == __float_as_uint(w.x) && __float_as_uint(h.f) == __float_as_uint(w.y) && u.e == __float_as_int(w.z) && h.e == __float_as_int(w.w);
+        want_u = hmm_canon(w.x, __float_as_int(w.z));
+        want_h = hmm_canon(w.y, __float_as_int(w.w));
     }
-    const u32 badmask = __ballot_sync(0xffffffffu, !ok);
+    const BF guess_u = in_u, guess_h = in_h;   // hmm_canon of what the chain parked (the given state for the first column)
+    bool value_bad = false;
+    for (int pass = 0; pass < 34; ++pass) {
+        bool other_form = false;
+        value_bad = false;
+        if (mine) {
+            out_u = in_u;
+            out_h = in_h;
+            if (!hmm_float_step(out_u, out_h, cc, ll)) {
+                hmm_exact_step(out_u, out_h, sm.te[bb.xs[lane]], fwd, m);
+                if (pass == 0) ++n_exact;
+            }
+            if (!(hmm_bf_same(out_u, want_u) && hmm_bf_same(out_h, want_h))) {
+                const bool same_value = hmm_bf_same(hmm_canon(out_u.f, out_u.e), want_u) && hmm_bf_same(hmm_canon(out_h.f, out_h.e), want_h);
+                other_form = same_value;
+                value_bad = !same_value;
+            }
+        }
+        // the lane behind a column that came out in another form than hmm_canon gives takes that form as its input
+        const float puf = __shfl_up_sync(0xffffffffu, out_u.f, 1), phf = __shfl_up_sync(0xffffffffu, out_h.f, 1);
+        const int pue = __shfl_up_sync(0xffffffffu, out_u.e, 1), phe = __shfl_up_sync(0xffffffffu, out_h.e, 1);
+        const bool pform = __shfl_up_sync(0xffffffffu, other_form ? 1 : 0, 1) != 0;
+        bool changed = false;
+        if (mine && lane > start) {
+            const BF nu = pform ? BF{puf, pue} : guess_u, nh = pform ? BF{phf, phe} : guess_h;
+            if (!(hmm_bf_same(nu, in_u) && hmm_bf_same(nh, in_h))) {
+                in_u = nu;
+                in_h = nh;
+                changed = true;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, changed) == 0u) break;
+    }
+    const u32 badmask = __ballot_sync(0xffffffffu, value_bad);
     if (badmask == 0u) return 32u;
     const u32 jb = (u32)__ffs((int)badmask) - 1u;
-    if (lane == jb) bb.st[jb + 1] = make_float4(u.f, h.f, __int_as_float(u.e), __int_as_float(h.e));
+    if (lane == jb) bb.st[jb + 1] = make_float4(out_u.f, out_h.f, __int_as_float(out_u.e), __int_as_float(out_h.e));
     __syncwarp();
     return jb;
 }
@@ -699,19 +747,18 @@ __global__ void __launch_bounds__(64) hmm_exact_chain_warp_kernel(const u8* __re
     const u64 len = end - beg;
     u32 bad = 0;
     const BF one = BF{1.0f, 0};
+    BF ent_u, ent_h;   // warp 1: the reference's state in front of the block it re-examines next (every thread computes the start)
+    if (fwd) {
+        const u32 x = sym_index(__ldg(sym + beg), bad);
+        ent_u = bf_dprod(one, m.first[x][0], m);
+        ent_h = bf_dprod(one, m.first[x][1], m);
+    } else {
+        ent_h = bf_dprod(one, m.stop[1], m);
+        ent_u = bf_dprod(one, m.stop[0], m);
+    }
     if (threadIdx.x == 0) {
-        BF h, u;
-        if (fwd) {
-            const u32 x = sym_index(__ldg(sym + beg), bad);
-            u = bf_dprod(one, m.first[x][0], m);
-            h = bf_dprod(one, m.first[x][1], m);
-            fh[beg] = h;
-        } else {
-            h = bf_dprod(one, m.stop[1], m);
-            u = bf_dprod(one, m.stop[0], m);
-            bh[end - 1] = h;
-        }
-        sm.b[0].st[0] = make_float4(u.f, h.f, __int_as_float(u.e), __int_as_float(h.e));
+        if (fwd) fh[beg] = ent_h; else bh[end - 1] = ent_h;
+        sm.b[0].st[0] = make_float4(ent_u.f, ent_h.f, __int_as_float(ent_u.e), __int_as_float(ent_h.e));
         sm.bad = -1;
     }
     const u64 steps = len - 1;
@@ -738,6 +785,12 @@ __global__ void __launch_bounds__(64) hmm_exact_chain_warp_kernel(const u8* __re
     __syncthreads();
     unsigned long long n_rounds = 0, n_exact = 0;
     bool skip_reexam = false;
+    auto store_results = [&](u64 blk, u32 pc, BF oh) {
+        if (lane < pc) {
+            if (fwd) fh[beg + 1 + blk * 32 + lane] = oh;
+            else bh[end - 2 - blk * 32 - lane] = oh;
+        }
+    };
     for (u64 k = 0; k <= nb;) {
         // ---- chain block k | re-examine block k - 1, store its results, stage block k + 1 ----
         if (warp == 0) {
@@ -751,16 +804,27 @@ __global__ void __launch_bounds__(64) hmm_exact_chain_warp_kernel(const u8* __re
             if (k >= 1 && !skip_reexam) {
                 HmmBlockBuf& pb = sm.b[(k - 1) % 3];
                 const u32 pc = cnt_of(k - 1);
+                BF ou = ent_u, oh = ent_h;
                 u32 jb = 32u;
-                if (!force_exact) jb = hmm_reexamine(sm, pb, lane, 0, pc, fwd, m, n_exact);
-                else n_exact += lane < pc ? 1u : 0u;
+                if (!force_exact) jb = hmm_reexamine(sm, pb, lane, 0, pc, ent_u, ent_h, fwd, m, ou, oh, n_exact);
+                else {
+                    n_exact += lane < pc ? 1u : 0u;
+                    if (lane < pc) {
+                        const float4 r = pb.st[lane + 1];
+                        ou = BF{r.x, __float_as_int(r.z)};
+                        oh = BF{r.y, __float_as_int(r.w)};
+                    }
+                }
                 if (jb < 32u) {
                     if (lane == 0) sm.bad = (int)jb;
-                } else if (lane < pc) {
-                    const float4 r = pb.st[lane + 1];
-                    const BF out = BF{r.y, __float_as_int(r.w)};
-                    if (fwd) fh[beg + 1 + (k - 1) * 32 + lane] = out;
-                    else bh[end - 2 - (k - 1) * 32 - lane] = out;
+                    // what stands so far: the columns in front of the corrected one and that one itself (kept across the repair)
+                    if (lane <= jb) store_results(k - 1, pc, oh);
+                    ent_u.f = __shfl_sync(0xffffffffu, ou.f, jb); ent_u.e = __shfl_sync(0xffffffffu, ou.e, jb);
+                    ent_h.f = __shfl_sync(0xffffffffu, oh.f, jb); ent_h.e = __shfl_sync(0xffffffffu, oh.e, jb);
+                } else {
+                    store_results(k - 1, pc, oh);
+                    ent_u.f = __shfl_sync(0xffffffffu, ou.f, pc - 1); ent_u.e = __shfl_sync(0xffffffffu, ou.e, pc - 1);
+                    ent_h.f = __shfl_sync(0xffffffffu, oh.f, pc - 1); ent_h.e = __shfl_sync(0xffffffffu, oh.e, pc - 1);
                 }
             }
             if (k + 1 < nb && !skip_reexam) {   // (after a repair block k + 1 is staged already)
@@ -784,11 +848,17 @@ __global__ void __launch_bounds__(64) hmm_exact_chain_warp_kernel(const u8* __re
             if (threadIdx.x == 0) sm.bad = -1;
             while (jb >= 0) {
                 const u32 vstart = (u32)jb + 1u;
+                if (vstart >= pc) break;   // the corrected column was the block's last
                 if (threadIdx.x == 0) hmm_lane0_chain(pb, vstart, pc);
                 __syncthreads();
                 if (warp == 1) {
                     ++n_rounds;
-                    const u32 j2 = hmm_reexamine(sm, pb, lane, vstart, pc, fwd, m, n_exact);
+                    BF ou = ent_u, oh = ent_h;   // ent = the reference's state behind the corrected column = in front of vstart
+                    const u32 j2 = hmm_reexamine(sm, pb, lane, vstart, pc, ent_u, ent_h, fwd, m, ou, oh, n_exact);
+                    const u32 upto = j2 < 32u ? j2 : pc - 1;
+                    if (lane >= vstart && lane <= upto) store_results(k - 1, pc, oh);
+                    ent_u.f = __shfl_sync(0xffffffffu, ou.f, upto); ent_u.e = __shfl_sync(0xffffffffu, ou.e, upto);
+                    ent_h.f = __shfl_sync(0xffffffffu, oh.f, upto); ent_h.e = __shfl_sync(0xffffffffu, oh.e, upto);
                     if (lane == 0) sm.bad = j2 < 32u ? (int)j2 : -1;
                 }
                 __syncthreads();
@@ -796,21 +866,21 @@ __global__ void __launch_bounds__(64) hmm_exact_chain_warp_kernel(const u8* __re
                 __syncthreads();
                 if (threadIdx.x == 0) sm.bad = -1;
             }
-            if (warp == 1 && lane < pc) {
-                const float4 r = pb.st[lane + 1];
-                const BF out = BF{r.y, __float_as_int(r.w)};
-                if (fwd) fh[beg + 1 + (k - 1) * 32 + lane] = out;
-                else bh[end - 2 - (k - 1) * 32 - lane] = out;
-            }
+            // the state block k starts from: the reference's state behind the last column of block k - 1
+            if (warp == 1 && lane == 0) pb.st[pc] = make_float4(ent_u.f, ent_h.f, __int_as_float(ent_u.e), __int_as_float(ent_h.e));
             __syncthreads();
             skip_reexam = true;   // block k starts again from the corrected state; k - 1 is done and k + 1 is staged
             continue;
         }
         ++k;
     }
-    if (fwd && threadIdx.x == 0) {
-        const float4 r = nb ? sm.b[(nb - 1) % 3].st[cnt_of(nb - 1)] : sm.b[0].st[0];
-        BF u = BF{r.x, __float_as_int(r.z)}, h = BF{r.y, __float_as_int(r.w)};
+    if (fwd && warp == 1 && lane == 0) {
+        BF u = ent_u, h = ent_h;   // the reference's state behind the last column
+        if (force_exact && nb) {
+            const float4 r = sm.b[(nb - 1) % 3].st[cnt_of(nb - 1)];
+            u = BF{r.x, __float_as_int(r.z)};
+            h = BF{r.y, __float_as_int(r.w)};
+        }
         BF p = bf_dprod(u, m.stop[0], m);
         bf_sum_accum(p, bf_dprod(h, m.stop[1], m));
         total[s] = p;
@@ -1085,6 +1155,61 @@ extern "C" int emu_hmm_run(const unsigned char* sym, unsigned long long n, const
     }
     free(ff); free(bf_); free(fe); free(be); free(tf); free(te);
     return 0;
+}
+
+// emu_hmm_vchain: the virtual-domain chain (hmm_vstep + the rescaling rule of the kernel) over a whole string, beside the exact chain.
+// counts[0] = columns where hmm_canon(virtual) is the reference's very form, counts[1] = columns with the same value in another form
+// (handed on by the re-examination), counts[2] = columns whose VALUE differs (the chain would be repaired there: hazards),
+// counts[3] = rescalings, counts[4] = columns where a virtual state was below 1e-30 (close to the denormals).
+extern "C" void emu_hmm_vchain(const unsigned char* sym, unsigned long long n, const double* params21, int fwd, unsigned long long* counts)
+{
+    using namespace mcu;
+    HmmExactModel m;
+    build_exact_model(params21, &m);
+    HmmFastTab ft;
+    build_fast_tab(m, &ft);
+    for (int i = 0; i < 5; ++i) counts[i] = 0;
+    if (n == 0) return;
+    const BF one = BF{1.0f, 0};
+    BF u, h;
+    if (fwd) {
+        const u32 x = (u32)(sym[0] - '1') & 7u;
+        u = bf_dprod(one, m.first[x][0], m);
+        h = bf_dprod(one, m.first[x][1], m);
+    } else {
+        h = bf_dprod(one, m.stop[1], m);
+        u = bf_dprod(one, m.stop[0], m);
+    }
+    float vu, vh;
+    int sc;
+    hmm_to_virtual(u, h, vu, vh, sc);
+    for (unsigned long long k = 1; k < n; ++k) {
+        const u32 x = (u32)(sym[fwd ? k : n - k] - '1') & 7u;
+        double c[4];
+        float ch[4], cl[4];
+        for (int r = 0; r < 4; ++r) {
+            const int src = (fwd || r == 0 || r == 3) ? r : 3 - r;
+            c[r] = m.te[x][src];
+            ch[r] = ft.hi[x][src];
+            cl[r] = ft.lo[x][src];
+        }
+        hmm_exact_step(u, h, c, fwd != 0, m);   // the truth
+        if (((k - 1) & 7) == 0 && fmaxf(vu, vh) < 1.0e6f) {   // the kernel looks at the scale once per group of eight columns
+            vu = H_FMUL(vu, 2.028240960365167e+31f);
+            vh = H_FMUL(vh, 2.028240960365167e+31f);
+            --sc;
+            ++counts[3];
+        }
+        hmm_vstep(vu, vh, ch, cl);
+        if (vu < 1.0e-30f || vh < 1.0e-30f) ++counts[4];
+        const BF cu = hmm_canon(vu, sc), chh = hmm_canon(vh, sc);
+        if (hmm_bf_same(cu, u) && hmm_bf_same(chh, h)) ++counts[0];
+        else if (hmm_bf_same(cu, hmm_canon(u.f, u.e)) && hmm_bf_same(chh, hmm_canon(h.f, h.e))) ++counts[1];
+        else {
+            ++counts[2];
+            hmm_to_virtual(u, h, vu, vh, sc);   // what the repair does: the chain goes on from the true state
+        }
+    }
 }
 
 // emu_hmm_fprod: y = (float)((double)v * c) for n pairs against the FP32 form; counts[0] = accepted, counts[1] = hazardous,

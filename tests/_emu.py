@@ -41,6 +41,8 @@ def emu():
     L.emu_hmm_chain.restype = None
     L.emu_hmm_run.argtypes = [vp, u64, vp, vp, vp, vp]
     L.emu_hmm_run.restype = C.c_int
+    L.emu_hmm_vchain.argtypes = [vp, u64, vp, C.c_int, vp]
+    L.emu_hmm_vchain.restype = None
     L.emu_hmm_fprod.argtypes = [vp, vp, u64, vp]
     L.emu_hmm_fprod.restype = None
     _lib = L
