@@ -665,29 +665,40 @@ __device__ __forceinline__ void hmm_lane0_chain(HmmBlockBuf& bb, u32 start, u32 
     }
 }
 
-// warp 1: columns [start, cnt) of a block, one per lane.  `first` = the reference's form of the state in front of column `start`.
-// out_u / out_h: the reference's state behind this lane's column (valid for start <= lane < cnt when the call returns 32 or for
-// lanes up to the returned column).  Returns the first column whose parked VALUE had to be corrected (its lane has written the
-// reference's state behind it to st), or 32.
+// hmm_canon for a state the chain parked: one step either way covers its range (the scale keeps the larger state in [1e-13, 2e37])
+__device__ __forceinline__ BF hmm_canon_parked(float v, int e)
+{
+    const float L = 1.0e-18f, TOP = 1.0e-18f * 2.028240960365167e+31f;
+    if (v >= TOP) { v = __fmul_rn(v, 4.930380657631324e-32f); ++e; }
+    else if (v < L) { v = __fmul_rn(v, 2.028240960365167e+31f); --e; }
+    if (!(v >= L && v < TOP)) return hmm_canon(v, e);   // (zero, or a repair's state far from the scale)
+    return BF{v, e};
+}
+
+// a verifier warp: columns [start, cnt) of a block, one per lane.  `first` = the state in front of column `start` in the reference's
+// form (or the best guess at it: the caller compares and comes back).  out_u / out_h: the reference's state behind this lane's column
+// (valid for start <= lane < cnt up to the returned column).  Returns the first column whose parked VALUE is not the reference's (its
+// lane has written the reference's state behind it to st), or 32.
 __device__ __forceinline__ u32 hmm_reexamine(HmmWarpSmem& sm, HmmBlockBuf& bb, u32 lane, u32 start, u32 cnt, BF first_u, BF first_h, bool fwd,
                                              const HmmExactModel& m, BF& out_u, BF& out_h, unsigned long long& n_exact)
 {
     const bool mine = lane >= start && lane < cnt;
-    BF in_u = first_u, in_h = first_h, want_u = first_u, want_h = first_h;
+    BF want_u = first_u, want_h = first_h;
     float cc[4] = {1.f, 0.f, 0.f, 1.f}, ll[4] = {0.f, 0.f, 0.f, 0.f};
     if (mine) {
-        const float4 v = bb.st[lane], w = bb.st[lane + 1];
+        const float4 w = bb.st[lane + 1];
         const float4 c = bb.chi[lane], l = bb.clo[lane];
         cc[0] = c.x; cc[1] = c.y; cc[2] = c.z; cc[3] = c.w;
         ll[0] = l.x; ll[1] = l.y; ll[2] = l.z; ll[3] = l.w;
-        if (lane != start) {
-            in_u = hmm_canon(v.x, __float_as_int(v.z));
-            in_h = hmm_canon(v.y, __float_as_int(v.w));
-        }
-        want_u = hmm_canon(w.x, __float_as_int(w.z));
-        want_h = hmm_canon(w.y, __float_as_int(w.w));
+        want_u = hmm_canon_parked(w.x, __float_as_int(w.z));
+        want_h = hmm_canon_parked(w.y, __float_as_int(w.w));
     }
-    const BF guess_u = in_u, guess_h = in_h;   // hmm_canon of what the chain parked (the given state for the first column)
+    // the state in front of a column = what is parked behind the column before it
+    BF guess_u, guess_h;
+    guess_u.f = __shfl_up_sync(0xffffffffu, want_u.f, 1); guess_u.e = __shfl_up_sync(0xffffffffu, want_u.e, 1);
+    guess_h.f = __shfl_up_sync(0xffffffffu, want_h.f, 1); guess_h.e = __shfl_up_sync(0xffffffffu, want_h.e, 1);
+    if (lane <= start) { guess_u = first_u; guess_h = first_h; }
+    BF in_u = guess_u, in_h = guess_h;
     bool value_bad = false;
     for (int pass = 0; pass < 34; ++pass) {
         bool other_form = false;
@@ -705,6 +716,7 @@ __device__ __forceinline__ u32 hmm_reexamine(HmmWarpSmem& sm, HmmBlockBuf& bb, u
                 value_bad = !same_value;
             }
         }
+        if (__ballot_sync(0xffffffffu, other_form) == 0u) break;   // (the common case: nothing to hand on)
         // the lane behind a column that came out in another form than hmm_canon gives takes that form as its input
         const float puf = __shfl_up_sync(0xffffffffu, out_u.f, 1), phf = __shfl_up_sync(0xffffffffu, out_h.f, 1);
         const int pue = __shfl_up_sync(0xffffffffu, out_u.e, 1), phe = __shfl_up_sync(0xffffffffu, out_h.e, 1);
@@ -728,11 +740,31 @@ __device__ __forceinline__ u32 hmm_reexamine(HmmWarpSmem& sm, HmmBlockBuf& bb, u
     return jb;
 }
 
-__global__ void __launch_bounds__(64) hmm_exact_chain_warp_kernel(const u8* __restrict__ sym, const u64* __restrict__ off, u32 n, HmmExactModel m, HmmFastTab ft,
-                                                                 int force_exact, BF* __restrict__ fh, BF* __restrict__ bh, BF* __restrict__ total,
-                                                                 u32* __restrict__ err, unsigned long long* __restrict__ counters)
+constexpr int HV = 4;        // verifier warps = blocks per iteration
+constexpr int HR = 3 * HV;   // block buffers: the blocks being re-examined, chained and staged
+struct HmmWarpSmem2 {
+    HmmWarpSmem base;        // te, chi_s, clo_s, bad (b[0..2] of it are the first three buffers)
+    HmmBlockBuf more[HR - 3];
+    float4 exit_st[HV + 1];  // the reference's state behind block i of the ones re-examined in this iteration ([0]: behind the block before them)
+    int bad_blk, bad_col;    // first column of this iteration whose parked value was not the reference's
+};
+
+__device__ __forceinline__ void hmm_bar_verifiers()
 {
-    __shared__ HmmWarpSmem sm;
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * HV) : "memory");
+}
+
+__global__ void __launch_bounds__(32 * (1 + HV)) hmm_exact_chain_warp_kernel(const u8* __restrict__ sym, const u64* __restrict__ off, u32 n, HmmExactModel m,
+                                                                            HmmFastTab ft, int force_exact, BF* __restrict__ fh, BF* __restrict__ bh,
+                                                                            BF* __restrict__ total, u32* __restrict__ err,
+                                                                            unsigned long long* __restrict__ counters)
+{
+    __shared__ HmmWarpSmem2 sm2;
+    HmmWarpSmem& sm = sm2.base;
+    auto buf = [&](u64 blk) -> HmmBlockBuf& {
+        const u32 i = (u32)(blk % HR);
+        return i < 3 ? sm.b[i] : sm2.more[i - 3];
+    };
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 s = blockIdx.x >> 1;
     const bool fwd = (blockIdx.x & 1) == 0;
@@ -747,7 +779,7 @@ __global__ void __launch_bounds__(64) hmm_exact_chain_warp_kernel(const u8* __re
     const u64 len = end - beg;
     u32 bad = 0;
     const BF one = BF{1.0f, 0};
-    BF ent_u, ent_h;   // warp 1: the reference's state in front of the block it re-examines next (every thread computes the start)
+    BF ent_u, ent_h;
     if (fwd) {
         const u32 x = sym_index(__ldg(sym + beg), bad);
         ent_u = bf_dprod(one, m.first[x][0], m);
@@ -759,104 +791,152 @@ __global__ void __launch_bounds__(64) hmm_exact_chain_warp_kernel(const u8* __re
     if (threadIdx.x == 0) {
         if (fwd) fh[beg] = ent_h; else bh[end - 1] = ent_h;
         sm.b[0].st[0] = make_float4(ent_u.f, ent_h.f, __int_as_float(ent_u.e), __int_as_float(ent_h.e));
-        sm.bad = -1;
+        sm2.exit_st[0] = sm.b[0].st[0];
+        sm2.bad_blk = 0x7fffffff;
+        sm2.bad_col = 0;
     }
     const u64 steps = len - 1;
     const u64 nb = (steps + 31) / 32;
     auto sym_of_step = [&](u64 k) -> u64 { return fwd ? beg + 1 + k : end - 1 - k; };  // index of the symbol step k consumes
     auto cnt_of = [&](u64 k) -> u32 { return (u32)min((u64)32, steps - k * 32); };
-    __syncthreads();
-    // warp 1 stages block 0 and holds the symbols of block 1
-    u32 xn = 0;
-    if (warp == 1) {
-        u32 x0 = 0;
-        if (lane < steps) x0 = sym_index(__ldg(sym + sym_of_step(lane)), bad);
-        if (32 + lane < steps) xn = sym_index(__ldg(sym + sym_of_step(32 + lane)), bad);
-        const float4 ident = make_float4(1.f, 0.f, 0.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        sm.b[0].chi[lane] = lane < steps ? sm.chi_s[x0] : ident;
-        sm.b[0].clo[lane] = lane < steps ? sm.clo_s[x0] : zero;
-        sm.b[0].xs[lane] = (u8)x0;
-        if (lane < 8)
-            for (int i = 0; i < 3; ++i) {
-                sm.b[i].chi[32 + lane] = ident;
-                sm.b[i].clo[32 + lane] = zero;
-            }
-    }
-    __syncthreads();
-    unsigned long long n_rounds = 0, n_exact = 0;
-    bool skip_reexam = false;
-    auto store_results = [&](u64 blk, u32 pc, BF oh) {
-        if (lane < pc) {
+    auto stage = [&](u64 blk, u32 x) {   // a verifier warp: the coefficient rows of a block (x: this lane's symbol index)
+        HmmBlockBuf& nbuf = buf(blk);
+        const bool live = blk * 32 + lane < steps;
+        nbuf.chi[lane] = live ? sm.chi_s[x] : make_float4(1.f, 0.f, 0.f, 1.f);
+        nbuf.clo[lane] = live ? sm.clo_s[x] : make_float4(0.f, 0.f, 0.f, 0.f);
+        nbuf.xs[lane] = (u8)x;
+        if (lane < 8) {
+            nbuf.chi[32 + lane] = make_float4(1.f, 0.f, 0.f, 1.f);
+            nbuf.clo[32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto load_sym = [&](u64 blk) -> u32 {
+        return (blk < nb && blk * 32 + lane < steps) ? sym_index(__ldg(sym + sym_of_step(blk * 32 + lane)), bad) : 0u;
+    };
+    auto store_results = [&](u64 blk, u32 upto_lane, BF oh) {   // lanes 0 .. upto_lane of the block
+        if (lane <= upto_lane && lane < cnt_of(blk)) {
             if (fwd) fh[beg + 1 + blk * 32 + lane] = oh;
             else bh[end - 2 - blk * 32 - lane] = oh;
         }
     };
-    for (u64 k = 0; k <= nb;) {
-        // ---- chain block k | re-examine block k - 1, store its results, stage block k + 1 ----
+    __syncthreads();
+    if (warp >= 1) {   // the rows of the first 2 HV blocks
+        for (int r = 0; r < 2; ++r) {
+            const u64 blk = (u64)r * HV + (warp - 1);
+            if (blk < nb) stage(blk, load_sym(blk));
+        }
+    }
+    __syncthreads();
+    unsigned long long n_rounds = 0, n_exact = 0;
+    u64 k = 0;       // first block the chain takes in this iteration
+    u64 vk = 0;      // first block to re-examine, nv of them
+    u32 nv = 0;
+    while (k < nb || nv) {
         if (warp == 0) {
-            if (lane == 0 && k < nb) {
-                if (k) sm.b[k % 3].st[0] = sm.b[(k - 1) % 3].st[cnt_of(k - 1)];
-                if (force_exact) hmm_lane0_exact(sm, sm.b[k % 3], cnt_of(k), fwd, m);
-                else hmm_lane0_chain(sm.b[k % 3], 0, cnt_of(k));
+            // ---- the chain: blocks k .. k + HV - 1 ----
+            if (lane == 0) {
+                for (u32 i = 0; i < (u32)HV && k + i < nb; ++i) {
+                    const u64 blk = k + i;
+                    HmmBlockBuf& bb = buf(blk);
+                    if (blk) bb.st[0] = buf(blk - 1).st[cnt_of(blk - 1)];
+                    if (force_exact) hmm_lane0_exact(sm, bb, cnt_of(blk), fwd, m);
+                    else hmm_lane0_chain(bb, 0, cnt_of(blk));
+                }
             }
         } else {
-            ++n_rounds;
-            if (k >= 1 && !skip_reexam) {
-                HmmBlockBuf& pb = sm.b[(k - 1) % 3];
-                const u32 pc = cnt_of(k - 1);
-                BF ou = ent_u, oh = ent_h;
-                u32 jb = 32u;
-                if (!force_exact) jb = hmm_reexamine(sm, pb, lane, 0, pc, ent_u, ent_h, fwd, m, ou, oh, n_exact);
-                else {
+            // ---- verifier warp w: re-examine block vk + w, store its results, stage block k + HV + w ----
+            const u32 w = warp - 1;
+            const u64 sb = k + HV + w;
+            const u32 sx = load_sym(sb);   // in flight during the re-examination
+            const bool have = w < nv;
+            const u64 vb = vk + w;
+            BF ou = BF{0.f, 0}, oh = BF{0.f, 0};
+            u32 jb = 32u, pc = 0;
+            BF used_u = BF{0.f, 0}, used_h = BF{0.f, 0};
+            if (have) {
+                ++n_rounds;
+                HmmBlockBuf& pb = buf(vb);
+                pc = cnt_of(vb);
+                if (force_exact) {
                     n_exact += lane < pc ? 1u : 0u;
                     if (lane < pc) {
                         const float4 r = pb.st[lane + 1];
                         ou = BF{r.x, __float_as_int(r.z)};
                         oh = BF{r.y, __float_as_int(r.w)};
                     }
-                }
-                if (jb < 32u) {
-                    if (lane == 0) sm.bad = (int)jb;
-                    // what stands so far: the columns in front of the corrected one and that one itself (kept across the repair)
-                    if (lane <= jb) store_results(k - 1, pc, oh);
-                    ent_u.f = __shfl_sync(0xffffffffu, ou.f, jb); ent_u.e = __shfl_sync(0xffffffffu, ou.e, jb);
-                    ent_h.f = __shfl_sync(0xffffffffu, oh.f, jb); ent_h.e = __shfl_sync(0xffffffffu, oh.e, jb);
                 } else {
-                    store_results(k - 1, pc, oh);
-                    ent_u.f = __shfl_sync(0xffffffffu, ou.f, pc - 1); ent_u.e = __shfl_sync(0xffffffffu, ou.e, pc - 1);
-                    ent_h.f = __shfl_sync(0xffffffffu, oh.f, pc - 1); ent_h.e = __shfl_sync(0xffffffffu, oh.e, pc - 1);
+                    // the state in front of the block: known for the first verifier, for the others the form hmm_canon gives what the
+                    // chain parked there (checked against the neighbour's result below)
+                    const float4 e0 = w == 0 ? sm2.exit_st[0] : pb.st[0];
+                    used_u = w == 0 ? BF{e0.x, __float_as_int(e0.z)} : hmm_canon_parked(e0.x, __float_as_int(e0.z));
+                    used_h = w == 0 ? BF{e0.y, __float_as_int(e0.w)} : hmm_canon_parked(e0.y, __float_as_int(e0.w));
+                    jb = hmm_reexamine(sm, pb, lane, 0, pc, used_u, used_h, fwd, m, ou, oh, n_exact);
+                }
+                const u32 lastl = jb < 32u ? jb : pc - 1;
+                const float xuf = __shfl_sync(0xffffffffu, ou.f, lastl), xhf = __shfl_sync(0xffffffffu, oh.f, lastl);
+                const int xue = __shfl_sync(0xffffffffu, ou.e, lastl), xhe = __shfl_sync(0xffffffffu, oh.e, lastl);
+                if (lane == 0) sm2.exit_st[w + 1] = make_float4(xuf, xhf, __int_as_float(xue), __int_as_float(xhe));
+            }
+            // the blocks' entry states, in order: verifier w waits for w - 1 (w rounds), comes back when its guess was another form
+            for (u32 r = 1; r < (u32)HV; ++r) {
+                hmm_bar_verifiers();
+                if (have && w == r && !force_exact) {
+                    const float4 e0 = sm2.exit_st[w];
+                    const BF tu = BF{e0.x, __float_as_int(e0.z)}, th = BF{e0.y, __float_as_int(e0.w)};
+                    if (!(hmm_bf_same(tu, used_u) && hmm_bf_same(th, used_h))) {
+                        HmmBlockBuf& pb = buf(vb);
+                        jb = hmm_reexamine(sm, pb, lane, 0, pc, tu, th, fwd, m, ou, oh, n_exact);
+                        const u32 lastl = jb < 32u ? jb : pc - 1;
+                        const float xuf = __shfl_sync(0xffffffffu, ou.f, lastl), xhf = __shfl_sync(0xffffffffu, oh.f, lastl);
+                        const int xue = __shfl_sync(0xffffffffu, ou.e, lastl), xhe = __shfl_sync(0xffffffffu, oh.e, lastl);
+                        if (lane == 0) sm2.exit_st[w + 1] = make_float4(xuf, xhf, __int_as_float(xue), __int_as_float(xhe));
+                    }
                 }
             }
-            if (k + 1 < nb && !skip_reexam) {   // (after a repair block k + 1 is staged already)
-                HmmBlockBuf& nbuf = sm.b[(k + 1) % 3];
-                const u32 x = xn;
-                if ((k + 2) * 32 + lane < steps) xn = sym_index(__ldg(sym + sym_of_step((k + 2) * 32 + lane)), bad);  // in flight during the next iteration
-                const bool live = (k + 1) * 32 + lane < steps;
-                nbuf.chi[lane] = live ? sm.chi_s[x] : make_float4(1.f, 0.f, 0.f, 1.f);
-                nbuf.clo[lane] = live ? sm.clo_s[x] : make_float4(0.f, 0.f, 0.f, 0.f);
-                nbuf.xs[lane] = (u8)x;
+            if (have && jb < 32u && lane == 0) {
+                const int prev = atomicMin(&sm2.bad_blk, (int)(vb & 0x3fffffff));
+                (void)prev;
             }
+            hmm_bar_verifiers();
+            if (have && jb < 32u && lane == 0 && sm2.bad_blk == (int)(vb & 0x3fffffff)) sm2.bad_col = (int)jb;
+            // what stands: every block in front of the first corrected column, and that block up to the column
+            if (have) {
+                const int bb_ = sm2.bad_blk;
+                const int me = (int)(vb & 0x3fffffff);
+                if (me < bb_) store_results(vb, 31u, oh);
+                else if (me == bb_) store_results(vb, jb, oh);
+            }
+            if (sb < nb) stage(sb, sx);
         }
         __syncthreads();
-        skip_reexam = false;
-        int jb = sm.bad;
-        if (jb >= 0) {
-            // ---- repair block k - 1 behind column jb: chain and re-examination take turns until the block stands ----
-            HmmBlockBuf& pb = sm.b[(k - 1) % 3];
-            const u32 pc = cnt_of(k - 1);
+        if (sm2.bad_blk != 0x7fffffff) {
+            // ---- a parked value was not the reference's: repair that block behind the column (chain lane and verifier 0 take turns),
+            //      then the chain starts again behind the block ----
+            const u64 rb = (vk & ~(u64)0x3fffffff) | (u64)sm2.bad_blk;
+            int jb = sm2.bad_col;
+            HmmBlockBuf& pb = buf(rb);
+            const u32 pc = cnt_of(rb);
+            // the reference's state behind the corrected column: verifier (rb - vk) left it in exit_st
+            if (warp == 1) {
+                const float4 e0 = sm2.exit_st[(u32)(rb - vk) + 1];
+                ent_u = BF{e0.x, __float_as_int(e0.z)};
+                ent_h = BF{e0.y, __float_as_int(e0.w)};
+            }
             __syncthreads();
-            if (threadIdx.x == 0) sm.bad = -1;
             while (jb >= 0) {
                 const u32 vstart = (u32)jb + 1u;
                 if (vstart >= pc) break;   // the corrected column was the block's last
-                if (threadIdx.x == 0) hmm_lane0_chain(pb, vstart, pc);
+                if (threadIdx.x == 0) {
+                    sm.bad = -1;
+                    hmm_lane0_chain(pb, vstart, pc);
+                }
                 __syncthreads();
                 if (warp == 1) {
                     ++n_rounds;
-                    BF ou = ent_u, oh = ent_h;   // ent = the reference's state behind the corrected column = in front of vstart
+                    BF ou = ent_u, oh = ent_h;
                     const u32 j2 = hmm_reexamine(sm, pb, lane, vstart, pc, ent_u, ent_h, fwd, m, ou, oh, n_exact);
                     const u32 upto = j2 < 32u ? j2 : pc - 1;
-                    if (lane >= vstart && lane <= upto) store_results(k - 1, pc, oh);
+                    if (lane >= vstart) store_results(rb, upto, oh);
                     ent_u.f = __shfl_sync(0xffffffffu, ou.f, upto); ent_u.e = __shfl_sync(0xffffffffu, ou.e, upto);
                     ent_h.f = __shfl_sync(0xffffffffu, oh.f, upto); ent_h.e = __shfl_sync(0xffffffffu, oh.e, upto);
                     if (lane == 0) sm.bad = j2 < 32u ? (int)j2 : -1;
@@ -864,35 +944,43 @@ __global__ void __launch_bounds__(64) hmm_exact_chain_warp_kernel(const u8* __re
                 __syncthreads();
                 jb = sm.bad;
                 __syncthreads();
-                if (threadIdx.x == 0) sm.bad = -1;
             }
-            // the state block k starts from: the reference's state behind the last column of block k - 1
-            if (warp == 1 && lane == 0) pb.st[pc] = make_float4(ent_u.f, ent_h.f, __int_as_float(ent_u.e), __int_as_float(ent_h.e));
+            if (warp == 1 && lane == 0) {
+                const float4 e = make_float4(ent_u.f, ent_h.f, __int_as_float(ent_u.e), __int_as_float(ent_h.e));
+                pb.st[pc] = e;          // the state the chain starts the next block from
+                sm2.exit_st[0] = e;     // and the state the next re-examination starts from
+                sm2.bad_blk = 0x7fffffff;
+                sm2.bad_col = 0;
+            }
             __syncthreads();
-            skip_reexam = true;   // block k starts again from the corrected state; k - 1 is done and k + 1 is staged
+            k = rb + 1;
+            vk = rb + 1;
+            nv = 0;
             continue;
         }
-        ++k;
+        // ---- next iteration: re-examine what was just chained ----
+        if (threadIdx.x == 32 && nv) sm2.exit_st[0] = sm2.exit_st[nv];
+        vk = k;
+        nv = (u32)min((u64)HV, nb > k ? nb - k : 0);
+        k = min(nb, k + HV);
+        __syncthreads();
     }
-    if (fwd && warp == 1 && lane == 0) {
-        BF u = ent_u, h = ent_h;   // the reference's state behind the last column
-        if (force_exact && nb) {
-            const float4 r = sm.b[(nb - 1) % 3].st[cnt_of(nb - 1)];
-            u = BF{r.x, __float_as_int(r.z)};
-            h = BF{r.y, __float_as_int(r.w)};
-        }
+    if (fwd && threadIdx.x == 32) {
+        float4 r = sm2.exit_st[0];   // the reference's state behind the last column
+        if (force_exact && nb) r = buf(nb - 1).st[cnt_of(nb - 1)];
+        BF u = BF{r.x, __float_as_int(r.z)}, h = BF{r.y, __float_as_int(r.w)};
         BF p = bf_dprod(u, m.stop[0], m);
         bf_sum_accum(p, bf_dprod(h, m.stop[1], m));
         total[s] = p;
     }
-    if (counters && warp == 1) {
+    if (counters && warp >= 1) {
         n_exact += __shfl_xor_sync(0xffffffffu, n_exact, 16);
         n_exact += __shfl_xor_sync(0xffffffffu, n_exact, 8);
         n_exact += __shfl_xor_sync(0xffffffffu, n_exact, 4);
         n_exact += __shfl_xor_sync(0xffffffffu, n_exact, 2);
         n_exact += __shfl_xor_sync(0xffffffffu, n_exact, 1);
         if (lane == 0) {
-            atomicAdd(counters, steps);
+            if (warp == 1) atomicAdd(counters, steps);
             atomicAdd(counters + 1, n_rounds);
             atomicAdd(counters + 2, n_exact);
         }
@@ -991,7 +1079,7 @@ int hmm_batch(u64 n, const char* sym, const u64* off, const double* params, char
         MCU_CUDA(cudaMemsetAsync(st.err.as<u32>() + 2, 0, 24, s));
         // few chains: a warp each (latency-optimised); many chains: a thread each (throughput)
         if (2 * n <= (u64)sm_count() * 64)
-            hmm_exact_chain_warp_kernel<<<(unsigned)(2 * n), 64, 0, s>>>(st.sym.as<u8>(), st.off.as<u64>(), (u32)n, xm, ft, force_exact, st.fh.as<BF>(),
+            hmm_exact_chain_warp_kernel<<<(unsigned)(2 * n), 32 * (1 + HV), 0, s>>>(st.sym.as<u8>(), st.off.as<u64>(), (u32)n, xm, ft, force_exact, st.fh.as<BF>(),
                                                                          st.bh.as<BF>(), st.total.as<BF>(), st.err.as<u32>(),
                                                                          reinterpret_cast<unsigned long long*>(st.err.as<u32>() + 2));
         else
