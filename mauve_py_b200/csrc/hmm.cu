@@ -436,40 +436,6 @@ HMM_HD bool hmm_float_step_t(BF& u, BF& h, const float c[4], const float l[4])
 }
 HMM_HD bool hmm_float_step(BF& u, BF& h, const float c[4], const float l[4]) { return hmm_float_step_t<true>(u, h, c, l); }
 
-// The chain's form of the column: exponents assumed to STAY as they are (ue, he; D = ue - he in {-1, 0, 1}), which fixes the
-// multipliers of (3): U' = r0 + r1 M(-D), H' = r2 M(D) + r3.  Dependency chain FMUL -> FFMA -> (FMUL ->) FADD.  The assumption holds
-// for a column unless an exponent drops there; what the chain needs to notice that costs two min / max instructions beside the chain:
-//   D =  0: holds iff max(r0, r1) >= 1e-18 and max(r2, r3) >= 1e-18 (U drops iff r0 and r1 are both below; same for H)
-//   D = -1: holds iff r1 < 1e-18 <= r3          D = +1: holds iff r2 < 1e-18 <= r0
-// hmm_regime_metric folds that into one number per column (an event iff it is below 1e-18).  Products within 16 ulp of 1e-18 and every
-// rounding hazard are left to the re-examination of the column (hmm_float_step / hmm_exact_step).
-// the event metric of a column: the regime assumption holds for it iff the metric is >= 1e-18
-template <int D>
-HMM_HD float hmm_regime_metric(float r0, float r1, float r2, float r3)
-{
-    if (D == 0) return fminf(fmaxf(r0, r1), fmaxf(r2, r3));
-    if (D < 0) return r1 >= 1.0e-18f ? 0.f : r3;
-    return r2 >= 1.0e-18f ? 0.f : r0;
-}
-
-template <int D>
-HMM_HD void hmm_regime_step(float& u, float& h, const float c[4], const float l[4], float& metric)
-{
-    const float r0 = hmm_fprod(u, c[0], l[0]), r1 = hmm_fprod(h, c[1], l[1]);
-    const float r2 = hmm_fprod(u, c[2], l[2]), r3 = hmm_fprod(h, c[3], l[3]);
-    if (D == 0) {
-        u = H_FADD(r0, r1);
-        h = H_FADD(r2, r3);
-    } else if (D < 0) {
-        u = H_FADD(r0, H_FMUL(r1, 2.028240960365167e+31f));
-        h = H_FADD(H_FMUL(r2, 4.930380657631324e-32f), r3);
-    } else {
-        u = H_FADD(r0, H_FMUL(r1, 4.930380657631324e-32f));
-        h = H_FADD(H_FMUL(r2, 2.028240960365167e+31f), r3);
-    }
-    metric = hmm_regime_metric<D>(r0, r1, r2, r3);
-}
-
 // ---- the chain in a VIRTUAL mantissa domain ---------------------------------------------------------------------------------------
 // Every scaling the bfloat operations perform is by a power of two (2^+-104) and commutes with both roundings; a term that the
 // reference multiplies by aConversionLookup[>= 2] = 0, or by 2^-104 into the denormals, is far below half an ulp of the term it is
@@ -1144,12 +1110,10 @@ void hmm_last_counters(u64* out3)
 // TEST-ONLY host drivers of the value functions above (tests/_emu.py builds this file with -DMCU_HOST_EMU into
 // tests/_emu/libmcu_emu.so; they are not part of libmauve_cuda.so).
 //
-// emu_hmm_chain: one chain (forward or backward) of one string, evaluated the way hmm_exact_chain_warp_kernel does: the regime step
-// while hmm_regime_ok lets it stand, hmm_float_step at the columns where it does not, hmm_exact_step at hazardous ones -- and,
-// beside it, hmm_exact_step at EVERY column from the same state (the truth).  out_f / out_e: the homologous-state bfloat after every
-// step (steps = n - 1, chain order).  counts[0] = columns carried by the regime step, counts[1] = columns evaluated by hmm_float_step,
-// counts[2] = columns where an accepted FP32 form differs from the truth or the chain's two event tests disagree (must be 0),
-// counts[3] = hazardous columns, counts[4] = exponent drops the chain's trackers miss (the re-examination corrects them).
+// emu_hmm_chain: one chain (forward or backward) of one string the way the re-examination and the thread-per-string kernel evaluate a
+// column: hmm_float_step, hmm_exact_step at hazardous ones -- and, beside it, hmm_exact_step at EVERY column from the same state (the
+// truth).  out_f / out_e: the homologous-state bfloat after every step (steps = n - 1, chain order).  counts[1] = columns evaluated by
+// hmm_float_step, counts[2] = columns where it differs from the truth (must be 0), counts[3] = hazardous columns.
 extern "C" void emu_hmm_chain(const unsigned char* sym, unsigned long long n, const double* params21, int fwd, float* out_f, int* out_e,
                               unsigned long long* counts)
 {
@@ -1183,27 +1147,11 @@ extern "C" void emu_hmm_chain(const unsigned char* sym, unsigned long long n, co
         BF tu = u, th = h;
         hmm_exact_step(tu, th, c, fwd != 0, m);
         auto same = [&](BF a, BF b) { return a.e == tu.e && b.e == th.e && memcmp(&a.f, &tu.f, 4) == 0 && memcmp(&b.f, &th.f, 4) == 0; };
-        const int d = u.e - h.e;
         BF gu = u, gh = h;
         const bool float_ok = hmm_float_step(gu, gh, ch, cl);
         if (float_ok && !same(gu, gh)) ++counts[2];
-        bool regime = false;
-        if (d >= -1 && d <= 1) {   // the chain's step and its trackers, as lane 0 evaluates them
-            float uf = u.f, hf = h.f, metric = 0.f;
-            if (d == 0) hmm_regime_step<0>(uf, hf, ch, cl, metric);
-            else if (d < 0) hmm_regime_step<-1>(uf, hf, ch, cl, metric);
-            else hmm_regime_step<1>(uf, hf, ch, cl, metric);
-            const bool ev = metric < 1.0e-18f;
-            // kept by the chain when no event fired; the re-examination (hmm_float_step, or the exact step on a hazard) then has to agree
-            regime = !ev && same(BF{uf, u.e}, BF{hf, h.e});
-            if (!ev && !regime && float_ok) ++counts[4];   // a drop the trackers missed: corrected by the re-examination, costs a round
-        }
-        if (regime) {
-            ++counts[0];
-        } else if (float_ok)
-            ++counts[1];
-        else
-            ++counts[3];
+        if (float_ok) ++counts[1];
+        else ++counts[3];
         u = tu;
         h = th;
         out_f[k - 1] = h.f;
