@@ -1,9 +1,9 @@
 #!/bin/bash
-# Round-2 GPU session 6 (one B200): the FP32 form of the HMM chains (parity tests, timing of one long string), the single-buffer
+# HMM session (one B200): the -m gpu HMM tests, timing of one long string (default and MAUVE_CUDA_HMM_FP64=1), optional A/B of bk_group3 variants, one ncu capture of the chain kernel
 # variants of bk_group3 on the headline workload
 set -u
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
-O=gpurun_out/${TAG:-s7}
+O=gpurun_out/${TAG:-hmm}
 mkdir -p $O
 export PYTHONUNBUFFERED=1
 timeout 600 python -m pytest tests -m gpu -q -x -p no:cacheprovider --timeout 300 -k "hmm" -s > $O/pytest_hmm.log 2>&1
