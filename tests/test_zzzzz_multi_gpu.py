@@ -28,3 +28,5 @@ def test_sharded_rows_equal_single_gpu_rows(world):
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert line["same_as_single_gpu"] and line["e2e_same"] and line["rows"] == line["single_rows"] > 10000
+    # the sorted mer list sharded by mer range over the same ranks: the mer sequence of the single-GPU list, every position once
+    assert line["sml_sharded"]["same_mer_sequence"] and line["sml_sharded"]["a_permutation"]
