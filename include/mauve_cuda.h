@@ -299,7 +299,9 @@ int mcu_test_int32_peak(double* gops_out, float* ms_out);
 /* HomologyHMM, few long strings (one warp per chain, csrc/hmm.cu): of the last mcu_hmm_batch call, out3[0] = columns the chains
  * stepped through (both directions), out3[1] = chain rounds (a round ends at a column whose exponents move or whose FP32 products are
  * hazardous), out3[2] = columns that fell back from the FP32 form of the recurrence to the operation-by-operation FP64 form.
- * MAUVE_CUDA_HMM_FP64=1 in the environment sends every column down the FP64 form (A/B in the tests). */
+ * MAUVE_CUDA_HMM_FP64=1 in the environment sends every column down the FP64 form (A/B in the tests); MAUVE_CUDA_HMM_TEST_FAULT=N flips
+ * the last mantissa bit of the chain's state at the end of every N-th group of eight columns, so that the tests can watch the kernel
+ * repair its chain (the result stays bit-identical). */
 int mcu_test_hmm_counters(uint64_t* out3);
 
 #if defined(__GNUC__)

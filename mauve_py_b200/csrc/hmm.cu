@@ -603,7 +603,9 @@ __device__ __forceinline__ void hmm_lane0_exact(HmmWarpSmem& sm, HmmBlockBuf& bb
 
 // warp 0, lane 0: columns [start, cnt) of the block in groups of eight (rows past the block's end hold identity coefficients: nothing
 // happens there), from the virtual state (u, h, sc), which it carries on
-__device__ __forceinline__ void hmm_lane0_run(HmmBlockBuf& bb, u32 start, u32 cnt, float& u, float& h, int& sc)
+// fault_every (tests only, MAUVE_CUDA_HMM_TEST_FAULT): every fault_every-th group ends with the last mantissa bit of u' flipped -- in the
+// parked state and in the chain -- which is what a rounding hazard that mattered looks like to the re-examination
+__device__ __forceinline__ void hmm_lane0_run(HmmBlockBuf& bb, u32 start, u32 cnt, float& u, float& h, int& sc, u32 fault_every = 0, u32* fault_ctr = nullptr)
 {
     for (u32 j = start; j < cnt; j += 8) {
         float4 c[8], l[8];
@@ -623,6 +625,10 @@ __device__ __forceinline__ void hmm_lane0_run(HmmBlockBuf& bb, u32 start, u32 cn
             const float cc[4] = {c[q].x, c[q].y, c[q].z, c[q].w}, ll[4] = {l[q].x, l[q].y, l[q].z, l[q].w};
             hmm_vstep(u, h, cc, ll);
             bb.st[j + q + 1] = make_float4(u, h, scf, scf);
+        }
+        if (fault_every && j + 8 <= cnt && ++*fault_ctr % fault_every == 0) {
+            u = __uint_as_float(__float_as_uint(u) ^ 1u);
+            bb.st[j + 8] = make_float4(u, h, scf, scf);
         }
     }
     const float4 e = bb.st[cnt];   // the state behind column cnt - 1 (the last group may have run past it)
@@ -731,7 +737,7 @@ __device__ __forceinline__ void hmm_bar_verifiers()
 }
 
 __global__ void __launch_bounds__(32 * (1 + HV)) hmm_exact_chain_warp_kernel(const u8* __restrict__ sym, const u64* __restrict__ off, u32 n, HmmExactModel m,
-                                                                            HmmFastTab ft, int force_exact, BF* __restrict__ fh, BF* __restrict__ bh,
+                                                                            HmmFastTab ft, int force_exact, int fault_every, BF* __restrict__ fh, BF* __restrict__ bh,
                                                                             BF* __restrict__ total, u32* __restrict__ err,
                                                                             unsigned long long* __restrict__ counters)
 {
@@ -804,6 +810,7 @@ __global__ void __launch_bounds__(32 * (1 + HV)) hmm_exact_chain_warp_kernel(con
     }
     __syncthreads();
     unsigned long long n_rounds = 0, n_exact = 0;
+    u32 fault_ctr = 0;
     u64 k = 0;       // first block the chain takes in this iteration
     u64 vk = 0;      // first block to re-examine, nv of them
     u32 nv = 0;
@@ -825,7 +832,7 @@ __global__ void __launch_bounds__(32 * (1 + HV)) hmm_exact_chain_warp_kernel(con
                             hmm_to_virtual(BF{s0.x, __float_as_int(s0.z)}, BF{s0.y, __float_as_int(s0.w)}, cu, ch, csc);
                         }
                         bb.st[0] = make_float4(cu, ch, __int_as_float(csc), __int_as_float(csc));
-                        hmm_lane0_run(bb, 0, cnt_of(blk), cu, ch, csc);
+                        hmm_lane0_run(bb, 0, cnt_of(blk), cu, ch, csc, (u32)fault_every, &fault_ctr);
                     }
                 }
             }
@@ -1062,10 +1069,11 @@ int hmm_batch(u64 n, const char* sym, const u64* off, const double* params, char
         HmmFastTab ft;
         build_fast_tab(xm, &ft);
         const int force_exact = getenv("MAUVE_CUDA_HMM_FP64") != nullptr;   // tests: every column operation by operation
+        const int fault_every = getenv("MAUVE_CUDA_HMM_TEST_FAULT") ? atoi(getenv("MAUVE_CUDA_HMM_TEST_FAULT")) : 0;   // tests: see hmm_lane0_run
         MCU_CUDA(cudaMemsetAsync(st.err.as<u32>() + 2, 0, 24, s));
         // few chains: a warp each (latency-optimised); many chains: a thread each (throughput)
         if (2 * n <= (u64)sm_count() * 64)
-            hmm_exact_chain_warp_kernel<<<(unsigned)(2 * n), 32 * (1 + HV), 0, s>>>(st.sym.as<u8>(), st.off.as<u64>(), (u32)n, xm, ft, force_exact, st.fh.as<BF>(),
+            hmm_exact_chain_warp_kernel<<<(unsigned)(2 * n), 32 * (1 + HV), 0, s>>>(st.sym.as<u8>(), st.off.as<u64>(), (u32)n, xm, ft, force_exact, fault_every > 0 ? fault_every : 0, st.fh.as<BF>(),
                                                                          st.bh.as<BF>(), st.total.as<BF>(), st.err.as<u32>(),
                                                                          reinterpret_cast<unsigned long long*>(st.err.as<u32>() + 2));
         else

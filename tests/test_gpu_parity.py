@@ -321,6 +321,27 @@ def test_hmm_long_string_fp32_chain(mp, orc, monkeypatch):
     assert np.array_equal(posts[0].view(np.uint64), np.asarray(opost).view(np.uint64))
 
 
+@pytest.mark.parametrize("every", [1, 3, 37, 1000])
+def test_hmm_chain_repair_protocol(mp, orc, monkeypatch, every):
+    """the long-string kernel repairs its chain when a parked value is not the reference's (a rounding hazard that mattered: about
+    one column in 20 million, so real inputs hardly ever get there).  MAUVE_CUDA_HMM_TEST_FAULT=N flips the last mantissa bit of the
+    chain's state at the end of every N-th group of eight columns -- in the parked value and in the chain itself; the re-examination
+    has to notice, correct the column, have the block redone behind it and the chain restarted: posteriors still bit-identical"""
+    params = mp.libmems.hmm_params(0.5, 0.0, 0.0, 0.0)
+    n = 200_003
+    s = synth.hmm_string(n, seed=5150 + every, block=700)
+    opred, opost = orc.hmm_run(s, params)
+    monkeypatch.setenv("MAUVE_CUDA_HMM_TEST_FAULT", str(every))
+    preds, posts, _ = mp.run_batch([s], params, want_posterior=True)
+    c3 = np.zeros(3, dtype=np.uint64)
+    assert mp.lib().mcu_test_hmm_counters(c3.ctypes.data) == 0
+    monkeypatch.delenv("MAUVE_CUDA_HMM_TEST_FAULT")
+    assert preds[0] == opred
+    assert np.array_equal(posts[0].view(np.uint64), np.asarray(opost).view(np.uint64))
+    blocks = 2 * ((n - 1 + 31) // 32)
+    assert int(c3[1]) > blocks            # re-examination rounds: one per block plus the repairs
+
+
 def test_hmm_scan_mode_within_tolerance(mp, orc, monkeypatch):
     """MAUVE_CUDA_HMM_SCAN=1: the column-parallel evaluation in double stays within the 1e-5 bar for strings up to ~10 k columns"""
     monkeypatch.setenv("MAUVE_CUDA_HMM_SCAN", "1")
