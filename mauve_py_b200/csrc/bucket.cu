@@ -652,24 +652,15 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bkf_scatter1_multi_kernel(const
     const u32* __restrict__ gp = gt ? g1 : g0;
     const u64 npos = gt ? pl.npos1 : pl.npos0;
     const u32 lt = lanemask_lt();
-    // the window of the NEXT tile is fetched while this tile's records are built (the loads are the only global reads of the scan)
-    BkWindow wn;
-    wn.hi = 0; wn.lo = 0;
-    {
-        const u64 idx0 = (u64)first * BK_TILE + (u64)tid * BK_IPT;
-        if (first < last && idx0 < pl.nidx) wn.load(gp, gt ? idx0 - pl.npad0 : idx0);
-    }
     for (u32 tile = first; tile < last; ++tile) {
         const u64 idx0 = (u64)tile * BK_TILE + (u64)tid * BK_IPT;
         u32 own_mask = 0, own_nx = 0, own_prev = 0;
         u64 own_pos = 0;
-        const BkWindow w = wn;
-        {
-            const u64 idxn = idx0 + BK_TILE;
-            if (tile + 1 < last && idxn < pl.nidx) wn.load(gp, gt ? idxn - pl.npad0 : idxn);
-        }
+        BkWindow w;
+        w.hi = 0; w.lo = 0;
         if (idx0 < pl.nidx) {
             const u64 pos = gt ? idx0 - pl.npad0 : idx0;
+            w.load(gp, pos);
             // ownership of the 16 seeds from two sliding windows (seed_owned_x, common.cuh): see bkf_scatter1_kernel
             const u32 hi_h = (u32)(w.hi >> 32), hi_l = (u32)w.hi;
             own_nx = kbits < 32 ? __funnelshift_l(hi_l, hi_h, kbits) : __funnelshift_l(w.lo, hi_l, kbits - 32);

@@ -605,6 +605,7 @@ __device__ __forceinline__ void hmm_lane0_exact(HmmWarpSmem& sm, HmmBlockBuf& bb
 // happens there), from the virtual state (u, h, sc), which it carries on
 // fault_every (tests only, MAUVE_CUDA_HMM_TEST_FAULT): every fault_every-th group ends with the last mantissa bit of u' flipped -- in the
 // parked state and in the chain -- which is what a rounding hazard that mattered looks like to the re-examination
+template <bool FAULT>
 __device__ __forceinline__ void hmm_lane0_run(HmmBlockBuf& bb, u32 start, u32 cnt, float& u, float& h, int& sc, u32 fault_every = 0, u32* fault_ctr = nullptr)
 {
     for (u32 j = start; j < cnt; j += 8) {
@@ -626,7 +627,7 @@ __device__ __forceinline__ void hmm_lane0_run(HmmBlockBuf& bb, u32 start, u32 cn
             hmm_vstep(u, h, cc, ll);
             bb.st[j + q + 1] = make_float4(u, h, scf, scf);
         }
-        if (fault_every && j + 8 <= cnt && ++*fault_ctr % fault_every == 0) {
+        if (FAULT && j + 8 <= cnt && ++*fault_ctr % fault_every == 0) {
             u = __uint_as_float(__float_as_uint(u) ^ 1u);
             bb.st[j + 8] = make_float4(u, h, scf, scf);
         }
@@ -644,7 +645,7 @@ __device__ __forceinline__ void hmm_lane0_chain(HmmBlockBuf& bb, u32 start, u32 
     float u, h;
     int sc;
     hmm_to_virtual(BF{s0.x, __float_as_int(s0.z)}, BF{s0.y, __float_as_int(s0.w)}, u, h, sc);
-    hmm_lane0_run(bb, start, cnt, u, h, sc);
+    hmm_lane0_run<false>(bb, start, cnt, u, h, sc);
 }
 
 // hmm_canon for a state the chain parked: one step either way covers its range (the scale keeps the larger state in [1e-13, 2e37])
@@ -832,7 +833,8 @@ __global__ void __launch_bounds__(32 * (1 + HV)) hmm_exact_chain_warp_kernel(con
                             hmm_to_virtual(BF{s0.x, __float_as_int(s0.z)}, BF{s0.y, __float_as_int(s0.w)}, cu, ch, csc);
                         }
                         bb.st[0] = make_float4(cu, ch, __int_as_float(csc), __int_as_float(csc));
-                        hmm_lane0_run(bb, 0, cnt_of(blk), cu, ch, csc, (u32)fault_every, &fault_ctr);
+                        if (fault_every) hmm_lane0_run<true>(bb, 0, cnt_of(blk), cu, ch, csc, (u32)fault_every, &fault_ctr);
+                        else hmm_lane0_run<false>(bb, 0, cnt_of(blk), cu, ch, csc);
                     }
                 }
             }
