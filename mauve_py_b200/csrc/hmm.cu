@@ -737,6 +737,7 @@ __device__ __forceinline__ void hmm_bar_verifiers()
     asm volatile("bar.sync 1, %0;" ::"r"(32 * HV) : "memory");
 }
 
+template <bool FAULT>
 __global__ void __launch_bounds__(32 * (1 + HV)) hmm_exact_chain_warp_kernel(const u8* __restrict__ sym, const u64* __restrict__ off, u32 n, HmmExactModel m,
                                                                             HmmFastTab ft, int force_exact, int fault_every, BF* __restrict__ fh, BF* __restrict__ bh,
                                                                             BF* __restrict__ total, u32* __restrict__ err,
@@ -833,8 +834,7 @@ __global__ void __launch_bounds__(32 * (1 + HV)) hmm_exact_chain_warp_kernel(con
                             hmm_to_virtual(BF{s0.x, __float_as_int(s0.z)}, BF{s0.y, __float_as_int(s0.w)}, cu, ch, csc);
                         }
                         bb.st[0] = make_float4(cu, ch, __int_as_float(csc), __int_as_float(csc));
-                        if (fault_every) hmm_lane0_run<true>(bb, 0, cnt_of(blk), cu, ch, csc, (u32)fault_every, &fault_ctr);
-                        else hmm_lane0_run<false>(bb, 0, cnt_of(blk), cu, ch, csc);
+                        hmm_lane0_run<FAULT>(bb, 0, cnt_of(blk), cu, ch, csc, (u32)fault_every, &fault_ctr);
                     }
                 }
             }
@@ -1074,11 +1074,16 @@ int hmm_batch(u64 n, const char* sym, const u64* off, const double* params, char
         const int fault_every = getenv("MAUVE_CUDA_HMM_TEST_FAULT") ? atoi(getenv("MAUVE_CUDA_HMM_TEST_FAULT")) : 0;   // tests: see hmm_lane0_run
         MCU_CUDA(cudaMemsetAsync(st.err.as<u32>() + 2, 0, 24, s));
         // few chains: a warp each (latency-optimised); many chains: a thread each (throughput)
-        if (2 * n <= (u64)sm_count() * 64)
-            hmm_exact_chain_warp_kernel<<<(unsigned)(2 * n), 32 * (1 + HV), 0, s>>>(st.sym.as<u8>(), st.off.as<u64>(), (u32)n, xm, ft, force_exact, fault_every > 0 ? fault_every : 0, st.fh.as<BF>(),
+        if (2 * n <= (u64)sm_count() * 64) {
+            if (fault_every > 0)
+                hmm_exact_chain_warp_kernel<true><<<(unsigned)(2 * n), 32 * (1 + HV), 0, s>>>(st.sym.as<u8>(), st.off.as<u64>(), (u32)n, xm, ft, force_exact, fault_every > 0 ? fault_every : 0, st.fh.as<BF>(),
                                                                          st.bh.as<BF>(), st.total.as<BF>(), st.err.as<u32>(),
                                                                          reinterpret_cast<unsigned long long*>(st.err.as<u32>() + 2));
-        else
+            else
+                hmm_exact_chain_warp_kernel<false><<<(unsigned)(2 * n), 32 * (1 + HV), 0, s>>>(st.sym.as<u8>(), st.off.as<u64>(), (u32)n, xm, ft, force_exact, fault_every > 0 ? fault_every : 0, st.fh.as<BF>(),
+                                                                         st.bh.as<BF>(), st.total.as<BF>(), st.err.as<u32>(),
+                                                                         reinterpret_cast<unsigned long long*>(st.err.as<u32>() + 2));
+        } else
             hmm_exact_chain_kernel<<<(unsigned)div_up(2 * n, 64), 64, 0, s>>>(st.sym.as<u8>(), st.off.as<u64>(), (u32)n, xm, ft, st.fh.as<BF>(), st.bh.as<BF>(),
                                                                               st.total.as<BF>(), st.err.as<u32>());
         hmm_exact_posterior_kernel<<<(unsigned)div_up(total, 256), 256, 0, s>>>(st.off.as<u64>(), (u32)n, total, xm, st.fh.as<BF>(), st.bh.as<BF>(),
