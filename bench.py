@@ -359,6 +359,58 @@ def measure_hmm(mp, synth, args, rank=0, comm=None):
     return out
 
 
+def measure_anchor_cols(mp, synth, args, rank=0):
+    """anchor columns of alignment windows (SURVEY 8f-4, muscle::FindAnchorColsPP): a batch of two-genome windows of 20,000 columns
+    (the aligner's window size) in one mcu_anchor_cols_batch call -- one CTA per window -- and the aligner's own case, ONE window
+    per call, with the CPU restatement beside both (checked equal on the spot)."""
+    nwin, ncol = args.anchor_windows, 20000
+    base = [synth.alignment_window(ncol, seed=900 + i + 64 * rank) for i in range(min(nwin, 64))]
+    wins = [(base[i % len(base)], 1) for i in range(nwin)]
+    lib = mp.lib()
+    blob = np.concatenate([w[0].reshape(-1) for w in wins])
+    n = len(wins)
+    row_off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(2 * ncol))
+    col_off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(ncol))
+    ncols = np.full(n, ncol, dtype=np.uint32)
+    ones = np.ones(n, dtype=np.uint32)
+    cols = np.zeros(n * ncol, dtype=np.uint32)
+    counts = np.zeros(n, dtype=np.uint32)
+    ms = C.c_float(0)
+
+    def call(k):
+        rc = lib.mcu_anchor_cols_batch(k, blob.ctypes.data, row_off.ctypes.data, ncols.ctypes.data, ones.ctypes.data, ones.ctypes.data, None, None,
+                                       col_off.ctypes.data, cols.ctypes.data, counts.ctypes.data, None, None, C.byref(ms))
+        if rc != 0:
+            raise RuntimeError("mcu_anchor_cols_batch: %s" % lib.mcu_last_error().decode())
+    call(n)
+    t0 = time.perf_counter()
+    call(n)
+    wall = time.perf_counter() - t0
+    dev = float(ms.value)
+    call(1)
+    t0 = time.perf_counter()
+    call(1)
+    wall1 = time.perf_counter() - t0
+    dev1 = float(ms.value)
+    out = {"metric": "alignment columns/s through FindAnchorColsPP (per-column SP score, smoothing, best columns, merging; floats identical to the reference)",
+           "windows": n, "columns_per_window": ncol, "value": n * ncol / wall, "unit": "columns/s", "wall_ms": 1e3 * wall, "device_ms": dev,
+           "kernel_only_columns_s": n * ncol / (dev * 1e-3),
+           "single_window": {"columns": ncol, "wall_ms": 1e3 * wall1, "device_ms": dev1},
+           "timing": "wall clock around mcu_anchor_cols_batch with HOST buffers (rows in, anchor columns back); device_ms = the kernel alone"}
+    if not args.no_cpu and rank == 0:
+        import _oracle
+        k = min(len(base), 16)
+        t0 = time.perf_counter()
+        want = [_oracle.anchor_cols(base[i], 1)[0] for i in range(k)]
+        cpu = (time.perf_counter() - t0) / k
+        call(n)
+        same = all(np.array_equal(cols[i * ncol:i * ncol + int(counts[i])], want[i % len(base)]) for i in range(n) if i % len(base) < k)
+        out["cpu_ms_per_window"] = 1e3 * cpu
+        out["cpu_kind"] = "port (oracle/mauve_oracle.c: orc_anchor_cols, pinned on the reference's FindAnchorColsPP by tests/golden/anchor_cols.npz), 1 core"
+        out["parity"] = "anchor columns identical to the CPU restatement on %d windows" % sum(1 for i in range(n) if i % len(base) < k) if same else "MISMATCH"
+    return out
+
+
 def measure_sml(mp, synth, args, a, pa, peak):
     """BASELINE config 4's stage at the size of this run: DNAMemorySML::Create = mcu_sml_build of genome 0 of the pair (pinned host
     sequence in, sorted list left on the device), for seed weights 11..21 at rank 0 and rank 3 (CODING_SEED).  Wall clock per call;
@@ -545,6 +597,7 @@ def main():
     ap.add_argument("--dp-regions", type=int, default=100000, help="BASELINE config 5 regions per GPU")
     ap.add_argument("--dp-cpu-regions", type=int, default=1000, help="stratified sample of the regions aligned by the reference's NWSmall")
     ap.add_argument("--hmm-single-columns", type=int, default=4000000)
+    ap.add_argument("--anchor-windows", type=int, default=1184, help="windows of 20,000 columns in the FindAnchorColsPP batch (8 per SM)")
     ap.add_argument("--sml-headline-weight", type=int, default=19)
     ap.add_argument("--config4-gbp", type=float, default=1.0, help="genome size (Gbp) of the BASELINE config 4 measurement at N = 1; 0 skips it")
     ap.add_argument("--no-dp", action="store_true")
@@ -679,7 +732,7 @@ def main():
     h2d = nbases if world == 1 else slice_bases(int(a.size)) + slice_bases(int(b.size))
 
     # ---- secondary metrics: every rank takes part at N > 1 (weak scaling: --dp-regions per GPU) ----
-    dp = hmm = sml = None
+    dp = hmm = sml = anchor_cols = None
     if not args.no_dp:
         try:
             dp = measure_dp(mp, synth, args, rank, comm)
@@ -691,6 +744,12 @@ def main():
         except Exception as e:  # noqa: BLE001
             print("rank %d: HMM measurement failed: %s: %s" % (rank, type(e).__name__, e), file=sys.stderr)
             hmm = {"error": "%s: %s" % (type(e).__name__, e)}
+        if rank == 0:
+            try:
+                anchor_cols = measure_anchor_cols(mp, synth, args, rank)
+            except Exception as e:  # noqa: BLE001
+                print("anchor column measurement failed: %s: %s" % (type(e).__name__, e), file=sys.stderr)
+                anchor_cols = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # ---- sorted mer list of genome 0, sharded by mer range over the N ranks (collective; at N = 1 the plain build) ----
     sml_sharded = None
@@ -845,7 +904,7 @@ def main():
                 "api": "mcu_find_mums_into(pinned host sequences -> pinned host rows): chunked H2D on a copy stream overlapped with pack + the level-1 "
                        "partition" if world == 1 else "mcu_find_mums_sharded (collective): every rank uploads 1/N of both genomes, packs it, ncclAllGather of "
                        "the packed words; rows to rank 0's pinned buffer (h2d_bytes_per_step is per rank)"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "sml": sml, "sml_sharded": sml_sharded, "config4": config4, "dp": dp, "hmm": hmm, "buildindex": bidx,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "sml": sml, "sml_sharded": sml_sharded, "config4": config4, "dp": dp, "hmm": hmm, "anchor_cols": anchor_cols, "buildindex": bidx,
     }
     emit(line)
     comm.barrier()

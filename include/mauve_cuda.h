@@ -289,6 +289,39 @@ int mcu_eliminate_overlaps(const mcu_match* rows, uint64_t n, int eliminate_both
                            uint64_t* ties_out);
 int mcu_lcbs(const mcu_match* rows, uint64_t n, mcu_match* sorted_out, uint64_t* breakpoints_out, uint64_t* n_breakpoints_out, uint64_t* ties_out);
 
+/* ---- anchor columns of alignment windows: replaces muscle::FindAnchorColsPP (MU/anchoredpp.cpp:354-409), the step
+ *      of AnchoredProfileProfile (:443-552) that decides which ranges of a window the gapped DP re-aligns:
+ *      LetterObjScoreXP (:256-329: ScoreSeqPairLetters :19-93 and the per-site ScoreSeqPairGaps :96-250 for every pair of rows, summed
+ *      with the rows' weights), WindowSmooth (MU/anchors.cpp:9-47), FindBestColsComboPP (:335-351), MergeBestCols (MU/anchors.cpp:137-186).
+ *      All scores are the reference's floats, every sum in the reference's order: columns, scores and smoothed scores are identical.
+ *      The settings are MUSCLE's globals at the time of the call (mcu_anchor_default_params: what MuscleInterface::ProfileAlignFast
+ *      leaves in force for DNA, LM/MuscleInterface.cpp:1086-1106).                                                              */
+#define MCU_AC_GAP 255u
+typedef struct {
+    float subst[4][4];        /* (*g_ptrScoreMatrix)[a][b] on the four residues (g_AlphaSize = 4)               */
+    float gap_open;           /* g_scoreGapOpen                                                                 */
+    float gap_extend;         /* g_scoreGapExtend                                                               */
+    float term_gap;           /* TermGapScore(true), MU/objscore2.cpp:22-40                                     */
+    float smooth_ceil;        /* g_dSmoothScoreCeil                                                             */
+    float min_best_col;       /* g_dMinBestColScore                                                             */
+    float min_smooth;         /* g_dMinSmoothScore                                                              */
+    uint32_t smooth_window;   /* g_uSmoothWindowLength as FindAnchorColsPP sets it: 21 (odd, MCU_EINVAL if not) */
+    uint32_t anchor_spacing;  /* g_uAnchorSpacing as FindAnchorColsPP sets it: 96                               */
+    uint8_t letter_of_char[256]; /* CharToLetterEx per character: 0..3 residues, MCU_AC_GAP where IsGapChar,
+                                    any other value = a letter outside the alphabet (wildcards: scored 0)      */
+} mcu_anchor_params;
+void mcu_anchor_default_params(mcu_anchor_params* p);
+/* n windows.  Window i is two alignments of ncol[i] columns with n1[i] and n2[i] rows: its (n1 + n2) rows of ncol characters lie
+ * one after the other from rows + row_off[i], the first alignment's rows first (characters as the MSA holds them after FixAlpha).
+ * weights: MSA::GetSeqWeight of every row, window after window in row order (NULL: all 1, the two-genome case).
+ * params NULL = mcu_anchor_default_params.  col_off (n + 1 offsets, col_off[i+1] - col_off[i] >= ncol[i]): where window i's outputs
+ * go in cols_out (its anchor columns, ascending; n_cols_out[i] of them), score_out and smooth_out (optional: MatchScore[] and
+ * SmoothScore[] of FindAnchorColsPP, ncol[i] floats).  device_ms (optional): the kernel's time.
+ * A window whose alignments differ in length has no anchor columns in the reference (:358-362): the caller answers that itself. */
+int mcu_anchor_cols_batch(uint64_t n, const char* rows, const uint64_t* row_off, const uint32_t* ncol, const uint32_t* n1, const uint32_t* n2,
+                          const float* weights, const mcu_anchor_params* params, const uint64_t* col_off, uint32_t* cols_out,
+                          uint32_t* n_cols_out, float* score_out, float* smooth_out, float* device_ms);
+
 /* ---- test hooks (exercise single kernels through the ABI) -------------------------------- */
 /* stable LSD radix sort of (key,val) pairs on the low `bits` bits; key_bytes is 4 or 8 */
 int mcu_test_sort_pairs(void* keys, uint32_t* vals, uint64_t n, int key_bytes, int bits);

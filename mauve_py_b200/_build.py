@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmauve_cuda.so")
-SOURCES = ["api.cu", "radix.cu", "anchor.cu", "bucket.cu", "replay.cu", "batch.cu", "dp.cu", "hmm.cu", "sol.cu", "dpwild.cu", "comm.cu", "lcb.cu"]
+SOURCES = ["api.cu", "radix.cu", "anchor.cu", "bucket.cu", "replay.cu", "batch.cu", "dp.cu", "hmm.cu", "sol.cu", "dpwild.cu", "comm.cu", "lcb.cu", "anchorcols.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "-diag-suppress", "177"]
 

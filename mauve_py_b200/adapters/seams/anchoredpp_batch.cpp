@@ -24,6 +24,7 @@
 #include "libMUSCLE/refine.h"
 
 #include "CudaGlobalAlign.h"
+#include "CudaAnchorCols.h"
 
 namespace muscle {
 
@@ -47,12 +48,15 @@ static ProfPos* ProfileOf(MSA& msa, Tree& tree)
 	return ProfileFromMSA(msa);
 }
 
-static unsigned long long g_seam_calls = 0, g_seam_ranges = 0, g_seam_device = 0;
+static unsigned long long g_seam_calls = 0, g_seam_ranges = 0, g_seam_device = 0, g_seam_cols_device = 0, g_seam_cols = 0;
 struct SeamReport {
 	~SeamReport()
 	{
 		if (getenv("MAUVE_CUDA_SEAM_REPORT"))
+		{
 			fprintf(stderr, "AnchoredProfileProfile seam: %llu calls, %llu ranges, %llu aligned on the device\n", g_seam_calls, g_seam_ranges, g_seam_device);
+			fprintf(stderr, "FindAnchorColsPP seam: %llu windows on the device, %llu anchor columns\n", g_seam_cols_device, g_seam_cols);
+		}
 	}
 };
 static SeamReport g_seam_report;
@@ -70,7 +74,19 @@ void AnchoredProfileProfile(MSA& msa1, MSA& msa2, MSA& msaOut)
 	unsigned uAnchorColCount;
 	PrepareMSAforScoring(msa1);
 	PrepareMSAforScoring(msa2);
-	FindAnchorColsPP(msa1, msa2, AnchorCols, &uAnchorColCount);
+	// the anchor columns of the window on the device (mcu_anchor_cols_batch; MAUVE_CUDA_COLS_SEAM=0: the reference's FindAnchorColsPP)
+	static const bool cols_off = getenv("MAUVE_CUDA_COLS_SEAM") && getenv("MAUVE_CUDA_COLS_SEAM")[0] == '0';
+	bool cols_done = false;
+	if (!cols_off) {
+		try {
+			cols_done = CudaFindAnchorColsPP(msa1, msa2, AnchorCols, &uAnchorColCount);
+		} catch (std::exception& e) {
+			fprintf(stderr, "\n*** FATAL: %s\n", e.what());   // see below: the caller would swallow the exception
+			exit(3);
+		}
+		if (cols_done) { ++g_seam_cols_device; g_seam_cols += uAnchorColCount; }
+	}
+	if (!cols_done) FindAnchorColsPP(msa1, msa2, AnchorCols, &uAnchorColCount);
 	const unsigned uRangeCount = uAnchorColCount + 1;
 	Range* Ranges = new Range[uRangeCount];
 	ColsToRanges(AnchorCols, uAnchorColCount, uColCountIn, Ranges);

@@ -12,6 +12,7 @@
 #include "dp.cuh"
 #include "hmm.cuh"
 #include "lcb.cuh"
+#include "anchorcols.cuh"
 #include "sol.cuh"
 
 namespace mcu {
@@ -162,6 +163,7 @@ void mcu_shutdown(void)
     nwf_release();
     hmm_release();
     lcb_release();
+    ac_release();
 }
 
 const char* mcu_last_error(void) { return get_error(); }
@@ -555,6 +557,24 @@ int mcu_lcbs(const mcu_match* rows, uint64_t n, mcu_match* sorted_out, uint64_t*
     *n_breakpoints_out = nb;
     if (ties_out) *ties_out = ties;
     return MCU_OK;
+}
+
+void mcu_anchor_default_params(mcu_anchor_params* p)
+{
+    if (p) ac_default_params(p);
+}
+
+int mcu_anchor_cols_batch(uint64_t n, const char* rows, const uint64_t* row_off, const uint32_t* ncol, const uint32_t* n1, const uint32_t* n2,
+                          const float* weights, const mcu_anchor_params* params, const uint64_t* col_off, uint32_t* cols_out,
+                          uint32_t* n_cols_out, float* score_out, float* smooth_out, float* device_ms)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MCU_TRY(ensure_device());
+    if (n && (!rows || !row_off || !ncol || !n1 || !n2 || !col_off || !cols_out || !n_cols_out)) {
+        set_error("mcu_anchor_cols_batch: NULL pointer");
+        return MCU_EINVAL;
+    }
+    return ac_batch(n, rows, (const u64*)row_off, ncol, n1, n2, weights, params, (const u64*)col_off, cols_out, n_cols_out, score_out, smooth_out, device_ms);
 }
 
 int mcu_test_hmm_counters(uint64_t* out3)

@@ -27,6 +27,7 @@ __all__ = [
     "PWPath", "GlobalAlign", "GlobalAlignBatch", "GlobalAlignBatchWild", "Params", "hmm_params", "getAdaptedHoxdMatrixParameters", "adaptToPercentIdentity",
     "run", "run_batch", "sort_pairs", "SeedOccurrenceList", "GetPairwiseAnchorScore", "anchor_scores", "hoxd_matrix",
     "EliminateOverlaps_v2", "IdentifyBreakpoints", "ComputeLCBs_v2", "sml_build_shard", "sml_build_sharded",
+    "AnchorParams", "FindAnchorColsPP", "FindAnchorColsPP_batch",
 ]
 
 
@@ -657,6 +658,78 @@ def ComputeLCBs_v2(sorted_rows, breakpoints):
         out.append(sorted_rows[prev:b + 1])
         prev = b + 1
     return out
+
+
+# ---- MU/anchoredpp.cpp:256-409, MU/anchors.cpp:9-186 ----------------------------------------------------------------
+class AnchorParams(C.Structure):
+    """mcu_anchor_params (include/mauve_cuda.h): the MUSCLE globals the column scoring reads.  AnchorParams.default() = the DNA
+    settings MuscleInterface::ProfileAlignFast leaves in force (LM/MuscleInterface.cpp:1086-1106)."""
+    _fields_ = [("subst", C.c_float * 16), ("gap_open", C.c_float), ("gap_extend", C.c_float), ("term_gap", C.c_float),
+                ("smooth_ceil", C.c_float), ("min_best_col", C.c_float), ("min_smooth", C.c_float),
+                ("smooth_window", C.c_uint32), ("anchor_spacing", C.c_uint32), ("letter_of_char", C.c_uint8 * 256)]
+
+    @classmethod
+    def default(cls):
+        p = cls()
+        lib().mcu_anchor_default_params(C.addressof(p))
+        return p
+
+
+def FindAnchorColsPP_batch(windows, params=None, return_scores=False):
+    """muscle::FindAnchorColsPP for many windows in one device call.  windows: sequence of (rows, n1[, weights]) with rows =
+    uint8[(n1 + n2), ncol] characters ('-' / '.' gaps; the first alignment's n1 rows first) and weights = MSA::GetSeqWeight per row
+    (None: all 1).  -> list of uint32 arrays of anchor columns (with return_scores: (cols, MatchScore, SmoothScore) per window)"""
+    n = len(windows)
+    if n == 0:
+        return []
+    mats, n1s, n2s, ws, any_w = [], [], [], [], False
+    for win in windows:
+        rows, n1 = win[0], int(win[1])
+        w = win[2] if len(win) > 2 else None
+        rows = np.ascontiguousarray(rows, dtype=np.uint8)
+        if rows.ndim != 2 or not (0 < n1 < rows.shape[0]):
+            raise ValueError("a window is uint8[(n1 + n2), ncol] with both alignments non-empty")
+        mats.append(rows)
+        n1s.append(n1)
+        n2s.append(rows.shape[0] - n1)
+        any_w = any_w or w is not None
+        ws.append(np.ones(rows.shape[0], dtype=np.float32) if w is None else np.ascontiguousarray(w, dtype=np.float32))
+        if ws[-1].size != rows.shape[0]:
+            raise ValueError("one weight per row")
+    ncol = np.array([m.shape[1] for m in mats], dtype=np.uint32)
+    row_off = np.zeros(n + 1, dtype=np.uint64)
+    row_off[1:] = np.cumsum([m.size for m in mats])
+    col_off = np.zeros(n + 1, dtype=np.uint64)
+    col_off[1:] = np.cumsum(ncol.astype(np.uint64))
+    blob = np.concatenate([m.reshape(-1) for m in mats]) if int(row_off[-1]) else np.zeros(1, dtype=np.uint8)
+    weights = np.concatenate(ws) if any_w else None
+    total = max(int(col_off[-1]), 1)
+    cols = np.zeros(total, dtype=np.uint32)
+    counts = np.zeros(n, dtype=np.uint32)
+    score = np.zeros(total, dtype=np.float32) if return_scores else None
+    smooth = np.zeros(total, dtype=np.float32) if return_scores else None
+    n1a, n2a = np.array(n1s, dtype=np.uint32), np.array(n2s, dtype=np.uint32)
+    check(lib().mcu_anchor_cols_batch(n, blob.ctypes.data, row_off.ctypes.data, ncol.ctypes.data, n1a.ctypes.data, n2a.ctypes.data,
+                                      weights.ctypes.data if weights is not None else None, C.addressof(params) if params is not None else None,
+                                      col_off.ctypes.data, cols.ctypes.data, counts.ctypes.data,
+                                      score.ctypes.data if return_scores else None, smooth.ctypes.data if return_scores else None, None))
+    out = []
+    for i in range(n):
+        a, b = int(col_off[i]), int(col_off[i + 1])
+        c = cols[a:a + int(counts[i])].copy()
+        out.append((c, score[a:b].copy(), smooth[a:b].copy()) if return_scores else c)
+    return out
+
+
+def FindAnchorColsPP(msa1, msa2, weights=None, params=None, return_scores=False):
+    """muscle::FindAnchorColsPP(msa1, msa2, AnchorCols, &count): msa1 / msa2 = the two alignments of a window as uint8[rows, ncol]
+    (or one bytes row each) -> the anchor columns.  Alignments of different lengths have none (MU/anchoredpp.cpp:358-362)."""
+    a = np.atleast_2d(np.frombuffer(msa1, dtype=np.uint8) if isinstance(msa1, (bytes, bytearray)) else np.asarray(msa1, dtype=np.uint8))
+    b = np.atleast_2d(np.frombuffer(msa2, dtype=np.uint8) if isinstance(msa2, (bytes, bytearray)) else np.asarray(msa2, dtype=np.uint8))
+    if a.shape[1] != b.shape[1]:
+        z = np.zeros(0, dtype=np.uint32)
+        return (z, np.zeros(0, np.float32), np.zeros(0, np.float32)) if return_scores else z
+    return FindAnchorColsPP_batch([(np.concatenate([a, b]), a.shape[0], weights)], params=params, return_scores=return_scores)[0]
 
 
 # ---- MU/pwpath.h, MU/glbalign.cpp ------------------------------------------------------------------

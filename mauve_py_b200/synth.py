@@ -229,3 +229,47 @@ def repeat_rich_pair(n=300_000, unit=61, copies=3000, seed=11, snp=0.01):
         a[p:p + 400] = elem
     b = snps(a, snp, rng)
     return a.tobytes(), b.tobytes()
+
+
+def alignment_window(ncol, seed=1, n_rows=2, snp=0.1, gap_rate=0.01, gap_mean=12, both_gap=0.002, wildcards=0.002, term_gaps=True,
+                     diverged_blocks=True):
+    """an alignment window as MUSCLE's anchor-column search sees it: uint8[n_rows, ncol] of ACGT with '-' runs, a few
+    columns where all rows have a gap, IUPAC wildcards and lower case, stretches that are well conserved and stretches that are not"""
+    rng = rng_for(seed)
+    base = random_genome(ncol, 0.5, rng)
+    rows = np.empty((n_rows, ncol), dtype=np.uint8)
+    for r in range(n_rows):
+        row = base.copy()
+        rate = np.full(ncol, snp if r else snp / 4, dtype=np.float32)
+        if diverged_blocks:
+            pos = 0
+            while pos < ncol:
+                ln = int(rng.integers(30, 400))
+                if rng.random() < 0.3:
+                    rate[pos:pos + ln] = 0.6
+                pos += ln
+        hit = rng.random(ncol, dtype=np.float32) < rate
+        row[hit] = ACGT[rng.integers(0, 4, int(hit.sum()))]
+        n_gaps = int(rng.poisson(gap_rate * ncol))
+        for _ in range(n_gaps):
+            ln = int(rng.geometric(1.0 / gap_mean))
+            at = int(rng.integers(0, max(ncol - 1, 1)))
+            row[at:at + ln] = ord("-")
+        if wildcards > 0:
+            w = rng.random(ncol, dtype=np.float32) < wildcards
+            keep = row != ord("-")
+            row[w & keep] = np.frombuffer(b"NNNRYKMSWn", dtype=np.uint8)[rng.integers(0, 10, int((w & keep).sum()))]
+            low = (rng.random(ncol, dtype=np.float32) < wildcards) & keep & ~w
+            row[low] = row[low] | 0x20
+        if term_gaps and ncol > 8 and rng.random() < 0.5:
+            k = int(rng.integers(1, max(ncol // 8, 2)))
+            if rng.random() < 0.5:
+                row[:k] = ord("-")
+            else:
+                row[ncol - k:] = ord("-")
+        rows[r] = row
+    if both_gap > 0 and ncol:
+        g = rng.random(ncol, dtype=np.float32) < both_gap
+        for s in np.nonzero(g)[0]:
+            rows[:, s:s + int(rng.integers(1, 6))] = ord("-")
+    return rows

@@ -31,6 +31,7 @@ using namespace std;  // LM/Scoring.h names std types unqualified
 #include "libMUSCLE/msa.h"
 #include "libMUSCLE/params.h"
 #include "libMUSCLE/alpha.h"
+#include "libMUSCLE/profile.h"
 
 using namespace std;
 using namespace genome;
@@ -39,6 +40,8 @@ using namespace mems;
 namespace muscle {
 void FindAnchorColsPP(const MSA& msa1, const MSA& msa2, unsigned AnchorCols[], unsigned* ptruAnchorColCount);
 SCORE LetterObjScoreXP(const MSA& msa1, const MSA& msa2, SCORE MatchScore[]);
+void PrepareMSAforScoring(MSA& msa);
+SCORE TermGapScore(bool Gap);
 }
 
 extern "C" {
@@ -152,6 +155,109 @@ long long ref_lcbs(const ref_match* rows, uint64_t n, ref_match* sorted_out, uin
 		for (size_t i = 0; i < ml.size(); ++i) ml[i]->Free();
 		return (long long)breakpoints.size();
 	} catch (...) { return -1; }
+}
+
+// ---- anchor columns of a window ------------------------------------------------------------------------------------------------
+// Global settings exactly as MuscleInterface::ProfileAlignFast (LM/MuscleInterface.cpp:1086-1106).
+static void ref_muscle_globals(unsigned nseq)
+{
+	using namespace muscle;
+	g_SeqType.get() = SEQTYPE_DNA;
+	g_uMaxIters.get() = 1;
+	g_bStable.get() = true;
+	g_bQuiet.get() = true;
+	g_SeqWeight1.get() = SEQWEIGHT_ClustalW;
+	SetMaxIters(g_uMaxIters.get());
+	SetSeqWeightMethod(g_SeqWeight1.get());
+	MSA::SetIdCount(nseq);
+	SetAlpha(ALPHA_DNA);
+	SetPPScore(PPSCORE_SPN);
+}
+
+static void ref_msa_from_rows(muscle::MSA& msa, const char* rows, unsigned nrows, unsigned ncol, unsigned first_id)
+{
+	msa.SetSize(nrows, ncol);
+	for (unsigned r = 0; r < nrows; ++r) {
+		char name[32];
+		snprintf(name, sizeof name, "seq%u", first_id + r);
+		msa.SetSeqName(r, name);
+		msa.SetSeqId(r, first_id + r);
+		for (unsigned c = 0; c < ncol; ++c) msa.SetChar(r, c, rows[(size_t)r * ncol + c]);
+	}
+}
+
+// rows: (n1 + n2) rows of ncol characters ('-' = gap), the first alignment's rows first.  prepare != 0: the rows' weights come from
+// PrepareMSAforScoring, as in AnchoredProfileProfile (MU/anchoredpp.cpp:454-455), and are written to weights; prepare == 0: weights
+// are given.  cols_out: FindAnchorColsPP's columns; score_out / smooth_out (optional): LetterObjScoreXP's per-column scores and
+// WindowSmooth of them with the settings FindAnchorColsPP uses.  fixed_rows_out (optional): the characters after MSA::FixAlpha.
+// Returns the number of anchor columns or -1.
+long long ref_anchor_cols(const char* rows, unsigned n1, unsigned n2, unsigned ncol, float* weights, int prepare, unsigned* cols_out,
+                          float* score_out, float* smooth_out, char* fixed_rows_out)
+{
+	using namespace muscle;
+	try {
+		ref_muscle_globals(n1 + n2);
+		MSA msa1, msa2;
+		ref_msa_from_rows(msa1, rows, n1, ncol, 0);
+		ref_msa_from_rows(msa2, rows + (size_t)n1 * ncol, n2, ncol, n1);
+		msa1.FixAlpha();
+		msa2.FixAlpha();
+		SetPPScore(PPSCORE_SPN);
+		if (prepare) {
+			PrepareMSAforScoring(msa1);
+			PrepareMSAforScoring(msa2);
+			for (unsigned r = 0; r < n1; ++r) weights[r] = msa1.GetSeqWeight(r);
+			for (unsigned r = 0; r < n2; ++r) weights[n1 + r] = msa2.GetSeqWeight(r);
+		} else {
+			for (unsigned r = 0; r < n1; ++r) msa1.SetSeqWeight(r, weights[r]);
+			for (unsigned r = 0; r < n2; ++r) msa2.SetSeqWeight(r, weights[n1 + r]);
+		}
+		if (fixed_rows_out) {
+			for (unsigned r = 0; r < n1; ++r)
+				for (unsigned c = 0; c < ncol; ++c) fixed_rows_out[(size_t)r * ncol + c] = msa1.GetChar(r, c);
+			for (unsigned r = 0; r < n2; ++r)
+				for (unsigned c = 0; c < ncol; ++c) fixed_rows_out[(size_t)(n1 + r) * ncol + c] = msa2.GetChar(r, c);
+		}
+		unsigned count = 0;
+		vector<unsigned> cols(ncol + 1);
+		FindAnchorColsPP(msa1, msa2, &cols[0], &count);
+		for (unsigned i = 0; i < count; ++i) cols_out[i] = cols[i];
+		if (score_out || smooth_out) {
+			vector<SCORE> score(ncol + 1), smooth(ncol + 1);
+			LetterObjScoreXP(msa1, msa2, &score[0]);
+			WindowSmooth(&score[0], ncol, g_uSmoothWindowLength.get(), &smooth[0], g_dSmoothScoreCeil.get());
+			for (unsigned c = 0; c < ncol; ++c) {
+				if (score_out) score_out[c] = score[c];
+				if (smooth_out) smooth_out[c] = smooth[c];
+			}
+		}
+		return (long long)count;
+	} catch (...) { return -1; }
+}
+
+// the settings the column scoring reads, after the set-up above (for the oracle's / the product's default parameters):
+// out[0..15] the score matrix on A C G T, [16] g_scoreGapOpen, [17] g_scoreGapExtend, [18] TermGapScore(true), [19] g_dSmoothScoreCeil,
+// [20] g_dMinBestColScore, [21] g_dMinSmoothScore, [22] g_uSmoothWindowLength, [23] g_uAnchorSpacing (both as FindAnchorColsPP sets
+// them), [24] g_AlphaSize; letters_out[256]: CharToLetterEx per character (255 where IsGapChar)
+void ref_anchor_settings(float* out, unsigned char* letters_out)
+{
+	using namespace muscle;
+	ref_muscle_globals(2);
+	for (int a = 0; a < 4; ++a)
+		for (int b = 0; b < 4; ++b) out[a * 4 + b] = (*g_ptrScoreMatrix.get())[a][b];
+	out[16] = g_scoreGapOpen.get();
+	out[17] = g_scoreGapExtend.get();
+	out[18] = TermGapScore(true);
+	out[19] = g_dSmoothScoreCeil.get();
+	out[20] = g_dMinBestColScore.get();
+	out[21] = g_dMinSmoothScore.get();
+	out[22] = 21;
+	out[23] = 96;
+	out[24] = (float)g_AlphaSize.get();
+	for (int c = 0; c < 256; ++c) {
+		unsigned l = CharToLetterEx((char)c);
+		letters_out[c] = IsGapChar((char)c) ? 255 : (unsigned char)(l > 254 ? 254 : l);
+	}
 }
 
 }  // extern "C"

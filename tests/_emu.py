@@ -12,7 +12,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "mauve_py_b200", "csrc")
 OUT = os.path.join(ROOT, "tests", "_emu", "libmcu_emu.so")
-SOURCES = ["sol.cu", "dpwild.cu", "hmm.cu"]
+SOURCES = ["sol.cu", "dpwild.cu", "hmm.cu", "anchorcols.cu"]
 
 _lib = None
 
@@ -45,6 +45,8 @@ def emu():
     L.emu_hmm_vchain.restype = None
     L.emu_hmm_fprod.argtypes = [vp, vp, u64, vp]
     L.emu_hmm_fprod.restype = None
+    L.emu_anchor_cols.argtypes = [vp, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp, vp, vp]
+    L.emu_anchor_cols.restype = C.c_longlong
     _lib = L
     return L
 

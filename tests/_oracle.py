@@ -104,6 +104,10 @@ def ref_full():
         lib.ref_eliminate_overlaps.argtypes = [p, u64, C.c_int, u64, p]
         lib.ref_lcbs.restype = C.c_longlong
         lib.ref_lcbs.argtypes = [p, u64, p, p]
+        lib.ref_anchor_cols.restype = C.c_longlong
+        lib.ref_anchor_cols.argtypes = [p, C.c_uint, C.c_uint, C.c_uint, p, C.c_int, p, p, p, p]
+        lib.ref_anchor_settings.restype = None
+        lib.ref_anchor_settings.argtypes = [p, p]
         _cache["rf"] = lib
     return _cache["rf"]
 
@@ -145,6 +149,58 @@ def lcbs(rows, use_ref=False):
     if n < 0:
         raise RuntimeError("lcbs failed")
     return out, bp[:n].copy(), ties
+
+
+class AnchorParams(C.Structure):
+    """orc_anchor_params == mcu_anchor_params (include/mauve_cuda.h)"""
+    _fields_ = [("subst", C.c_float * 16), ("gap_open", C.c_float), ("gap_extend", C.c_float), ("term_gap", C.c_float),
+                ("smooth_ceil", C.c_float), ("min_best_col", C.c_float), ("min_smooth", C.c_float),
+                ("smooth_window", C.c_uint), ("anchor_spacing", C.c_uint), ("letter_of_char", C.c_uint8 * 256)]
+
+
+def anchor_default_params():
+    p = AnchorParams()
+    lib = oracle()
+    lib.orc_anchor_default_params.restype = None
+    lib.orc_anchor_default_params.argtypes = [C.c_void_p]
+    lib.orc_anchor_default_params(C.byref(p))
+    return p
+
+
+def anchor_settings_ref():
+    """the settings the reference's column scoring reads after MuscleInterface's set-up -> (25 floats, 256 letters)"""
+    out = np.zeros(25, dtype=np.float32)
+    letters = np.zeros(256, dtype=np.uint8)
+    ref_full().ref_anchor_settings(out.ctypes.data, letters.ctypes.data)
+    return out, letters
+
+
+def anchor_cols(rows, n1, weights=None, use_ref=False, params=None):
+    """FindAnchorColsPP on a window: rows = uint8[(n1 + n2), ncol] characters ('-' gaps), the first alignment's n1 rows first.
+    -> (anchor columns uint32, per-column score float32, smoothed score float32, weights float32, rows as scored).
+    use_ref: the reference's own functions; weights None there = PrepareMSAforScoring computes them (as AnchoredProfileProfile does)"""
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    nr, ncol = rows.shape
+    n2 = nr - n1
+    cols = np.zeros(ncol + 1, dtype=np.uint32)
+    score = np.zeros(ncol + 1, dtype=np.float32)
+    smooth = np.zeros(ncol + 1, dtype=np.float32)
+    if use_ref:
+        w = np.ones(nr, dtype=np.float32) if weights is None else np.ascontiguousarray(weights, dtype=np.float32).copy()
+        fixed = np.zeros_like(rows)
+        n = ref_full().ref_anchor_cols(rows.ctypes.data, n1, n2, ncol, w.ctypes.data, 1 if weights is None else 0, cols.ctypes.data,
+                                       score.ctypes.data, smooth.ctypes.data, fixed.ctypes.data)
+        rows = fixed
+    else:
+        w = np.ones(nr, dtype=np.float32) if weights is None else np.ascontiguousarray(weights, dtype=np.float32)
+        lib = oracle()
+        lib.orc_anchor_cols.restype = C.c_longlong
+        lib.orc_anchor_cols.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        pr = params if params is not None else anchor_default_params()
+        n = lib.orc_anchor_cols(rows.ctypes.data, n1, n2, ncol, w.ctypes.data, C.byref(pr), cols.ctypes.data, score.ctypes.data, smooth.ctypes.data)
+    if n < 0:
+        raise RuntimeError("anchor_cols failed")
+    return cols[:n].copy(), score[:ncol].copy(), smooth[:ncol].copy(), w, rows
 
 
 def sol_build(seq: bytes, seed: int, use_ref=False):

@@ -111,6 +111,30 @@ int mcu_lcbs(const mcu_match* rows, uint64_t n, mcu_match* sorted_out, uint64_t*
     return 0;
 }
 
+/* anchor columns of windows (CudaAnchorCols.h, the AnchoredProfileProfile seam): mcu_anchor_params == orc_anchor_params */
+typedef struct { float subst[4][4]; float gap_open, gap_extend, term_gap, smooth_ceil, min_best_col, min_smooth; unsigned smooth_window, anchor_spacing; unsigned char letter_of_char[256]; } mcu_anchor_params;
+void orc_anchor_default_params(mcu_anchor_params* p);
+long long orc_anchor_cols(const unsigned char* rows, unsigned n1, unsigned n2, unsigned ncol, const float* w, const mcu_anchor_params* p,
+                          unsigned* cols_out, float* score_out, float* smooth_out);
+void mcu_anchor_default_params(mcu_anchor_params* p) { orc_anchor_default_params(p); }
+int mcu_anchor_cols_batch(uint64_t n, const char* rows, const uint64_t* row_off, const uint32_t* ncol, const uint32_t* n1, const uint32_t* n2,
+                          const float* weights, const mcu_anchor_params* params, const uint64_t* col_off, uint32_t* cols_out,
+                          uint32_t* n_cols_out, float* score_out, float* smooth_out, float* device_ms)
+{
+    mcu_anchor_params dflt;
+    uint64_t i, woff = 0;
+    if (!params) { orc_anchor_default_params(&dflt); params = &dflt; }
+    for (i = 0; i < n; ++i) {
+        long long k = orc_anchor_cols((const unsigned char*)rows + row_off[i], n1[i], n2[i], ncol[i], weights ? weights + woff : NULL, params,
+                                      cols_out + col_off[i], score_out ? score_out + col_off[i] : NULL, smooth_out ? smooth_out + col_off[i] : NULL);
+        if (k < 0) return -3;
+        n_cols_out[i] = (uint32_t)k;
+        woff += (uint64_t)n1[i] + n2[i];
+    }
+    if (device_ms) *device_ms = 1.0f;
+    return 0;
+}
+
 long long orc_nw_align_f(const char* a, unsigned la, const char* b, unsigned lb, char* path_out, float* score_out);
 static unsigned long long g_nwf_problems = 0;
 int orc_hmm_run(const char* sym, uint64_t len, const double* p, char* pred_out, double* post_out);

@@ -1,0 +1,105 @@
+"""Anchor columns of alignment windows (muscle::FindAnchorColsPP, MU/anchoredpp.cpp:354-409) on the CPU:
+
+  * the restatement (oracle/mauve_oracle.c: orc_anchor_cols) against the goldens the REFERENCE's own functions produced
+    (tests/golden/anchor_cols.npz, minted by tests/golden/make_golden_anchor_cols.py): anchor columns, per-column scores and smoothed
+    scores, float for float -- and against the reference itself on fresh random windows where oracle/_ref is present;
+  * the value path of the CUDA source (csrc/anchorcols.cu: ac_window compiled for the host by tests/_emu.py, one thread standing in
+    for the CTA) against the same goldens.  The parallel form proper is checked on the GPU (tests/test_zzzz_next_rows_gpu.py).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import _emu
+import _oracle
+from mauve_py_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "anchor_cols.npz")
+
+
+def _windows():
+    z = np.load(GOLDEN)
+    for k in range(int(z["n_windows"])):
+        yield k, z["w%d_rows" % k], int(z["w%d_n1" % k]), z["w%d_weights" % k], z["w%d_cols" % k], z["w%d_score" % k], z["w%d_smooth" % k]
+
+
+def _same_floats(a, b):
+    return np.array_equal(np.asarray(a, dtype=np.float32).view(np.uint32), np.asarray(b, dtype=np.float32).view(np.uint32))
+
+
+def test_default_parameters_are_the_references_settings():
+    z = np.load(GOLDEN)
+    s, letters = z["settings"], z["letters"]
+    p = _oracle.anchor_default_params()
+    assert _same_floats(np.array(p.subst[:]), s[:16])
+    assert (p.gap_open, p.gap_extend, p.term_gap, p.smooth_ceil, p.min_best_col, p.min_smooth) == tuple(float(x) for x in s[16:22])
+    assert (p.smooth_window, p.anchor_spacing) == (int(s[22]), int(s[23])) and int(s[24]) == 4
+    mine = np.array(p.letter_of_char[:], dtype=np.uint8)
+    # residues and gaps agree exactly; everything else only has to lie outside the alphabet on both sides
+    assert np.array_equal(mine < 4, letters < 4) and np.array_equal(mine[mine < 4], letters[letters < 4])
+    assert np.array_equal(mine == 255, letters == 255)
+
+
+def test_oracle_equals_golden():
+    n = 0
+    for k, rows, n1, w, cols, score, smooth in _windows():
+        c2, s2, m2, _, _ = _oracle.anchor_cols(rows, n1, weights=w)
+        assert np.array_equal(c2, cols), k
+        assert _same_floats(s2, score) and _same_floats(m2, smooth), k
+        n += cols.size
+    assert n > 300
+
+
+def _emu_cols(rows, n1, w):
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    nr, ncol = rows.shape
+    cols = np.zeros(ncol + 1, dtype=np.uint32)
+    score = np.zeros(ncol + 1, dtype=np.float32)
+    smooth = np.zeros(ncol + 1, dtype=np.float32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    p = _oracle.anchor_default_params()
+    n = _emu.emu().emu_anchor_cols(rows.ctypes.data, n1, nr - n1, ncol, w.ctypes.data, C.addressof(p), cols.ctypes.data, score.ctypes.data, smooth.ctypes.data)
+    assert n >= 0
+    return cols[:n], score[:ncol], smooth[:ncol]
+
+
+def test_kernel_value_path_equals_golden():
+    for k, rows, n1, w, cols, score, smooth in _windows():
+        c2, s2, m2 = _emu_cols(rows, n1, w)
+        assert np.array_equal(c2, cols), k
+        assert _same_floats(s2, score) and _same_floats(m2, smooth), k
+
+
+def test_kernel_value_path_equals_oracle_on_random_windows():
+    rng = np.random.default_rng(5)
+    for it in range(60):
+        ncol = int(rng.integers(1, 9000))
+        n1, n2 = (1, 1) if it % 3 else (int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+        rows = synth.alignment_window(ncol, seed=1000 + it, n_rows=n1 + n2, snp=float(rng.choice([0.02, 0.1, 0.3])),
+                                      gap_rate=float(rng.choice([0.002, 0.01, 0.06])), gap_mean=int(rng.choice([2, 12, 150])),
+                                      both_gap=float(rng.choice([0.0, 0.002, 0.03])))
+        w = rng.random(n1 + n2).astype(np.float32) if it % 3 == 0 else np.ones(n1 + n2, dtype=np.float32)
+        c1, s1, m1, _, _ = _oracle.anchor_cols(rows, n1, weights=w)
+        c2, s2, m2 = _emu_cols(rows, n1, w)
+        assert np.array_equal(c1, c2), it
+        assert _same_floats(s1, s2) and _same_floats(m1, m2), it
+
+
+@pytest.mark.skipif(not _oracle.have_ref_full(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_equals_reference_on_random_windows():
+    rng = np.random.default_rng(9)
+    total = 0
+    for it in range(40):
+        ncol = int(rng.integers(1, 6000))
+        n1, n2 = (1, 1) if it % 4 else (int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+        rows = synth.alignment_window(ncol, seed=2000 + it, n_rows=n1 + n2, snp=float(rng.choice([0.02, 0.1, 0.3])),
+                                      gap_rate=float(rng.choice([0.002, 0.01, 0.06])), gap_mean=int(rng.choice([2, 12, 150])),
+                                      both_gap=float(rng.choice([0.0, 0.002, 0.03])))
+        cols, score, smooth, w, fixed = _oracle.anchor_cols(rows, n1, use_ref=True)
+        c2, s2, m2, _, _ = _oracle.anchor_cols(fixed, n1, weights=w)
+        assert np.array_equal(cols, c2), it
+        assert _same_floats(score, s2) and _same_floats(smooth, m2), it
+        total += cols.size
+    assert total > 200

@@ -42,7 +42,7 @@ def run_bench(argv, stub=True, timeout=600):
 
 def test_bench_main_line_dry_run():
     line, err = run_bench(["--mbp", "0.3", "--cpu-sample-mbp", "0.1", "--dp-regions", "6", "--dp-cpu-regions", "3", "--hmm-single-columns", "3000", "--steps", "2",
-                           "--warmup", "1", "--no-buildindex", "--config4-gbp", "0.0002"])
+                           "--warmup", "1", "--no-buildindex", "--config4-gbp", "0.0002", "--anchor-windows", "3"])
     for k in REQUIRED:
         assert k in line, k
     assert line["metric"] == "Mbp/s seed+match+extend" and line["unit"] == "Mbp/s" and line["n_gpus"] == 1
@@ -70,6 +70,8 @@ def test_bench_main_line_dry_run():
     assert line["dp"]["value"] > 0 and line["dp"]["roofline"]["frac"] > 0 and line["dp"]["cpu_baseline"]["value"] > 0
     assert "error" not in line["hmm"], line["hmm"]
     assert line["hmm"]["value"] > 0 and line["hmm"]["strings"] == 6 and line["hmm"]["single_string"]["columns"] == 3000
+    assert "error" not in line["anchor_cols"], line["anchor_cols"]
+    assert line["anchor_cols"]["windows"] == 3 and line["anchor_cols"]["value"] > 0 and line["anchor_cols"]["parity"].startswith("anchor columns identical")
     assert line["clocks"] is not None and "reasons" in line["clocks"]
     assert "error" not in line["sml_sharded"], line["sml_sharded"]
     assert line["sml_sharded"]["n_gpus"] == 1 and line["sml_sharded"]["value"] > 0 and line["sml_sharded"]["list_length"] > 0

@@ -338,7 +338,7 @@ def _spiked_pair(d):
 def _seam_counts(stderr):
     out = {}
     for l in stderr.splitlines():
-        if l.split(" seam:")[0] in ("AnchoredProfileProfile", "MemHash::FindMatches", "RefineW", "SeedOccurrenceList::construct", "FileSML::Create"):
+        if l.split(" seam:")[0] in ("AnchoredProfileProfile", "FindAnchorColsPP", "MemHash::FindMatches", "RefineW", "SeedOccurrenceList::construct", "FileSML::Create"):
             out[l.split(" seam:")[0]] = [int(x) for x in l.replace(",", "").split() if x.isdigit()]
         if l.startswith("EliminateOverlaps_v2 seam:") or l.startswith("IdentifyBreakpoints seam:"):
             out[l.split(" seam:")[0]] = [int(x) for x in l.replace(",", "").replace("(", " ").split() if x.isdigit()]
@@ -405,6 +405,9 @@ def test_seams_host_code_inside_the_reference_binary(tmp_path):
     # the step after every match list (adapters/seams/lcb_seam.cpp): overlaps of the initial list (25 tied keys) and of the gap lists that hold two matches or more, the LCBs
     assert c["EliminateOverlaps_v2"][0] > 50 and c["EliminateOverlaps_v2"][1] >= 25 and c["EliminateOverlaps_v2"][2] == 0
     assert c["IdentifyBreakpoints"][0] >= 1 and c["IdentifyBreakpoints"][1] == 0
+    # the anchor columns of every window (adapters/CudaAnchorCols.h inside the AnchoredProfileProfile seam): all 165 windows, and the
+    # ranges between the columns are the 41,806 above
+    assert c["FindAnchorColsPP"][0] == c["AnchoredProfileProfile"][0] and c["FindAnchorColsPP"][1] > 40000
 
 
 @needs_cuda_bin
@@ -503,6 +506,7 @@ def test_buildindex_with_the_seam_binaries_mds42(tmp_path, monkeypatch, binary, 
     assert _xmfa_body_sha1(os.path.join(str(tmp_path), "cuda.xmfa")) == meta["xmfa_body_sha1"]
     c = _seam_counts(r.stderr)
     assert c["AnchoredProfileProfile"][1] == c["AnchoredProfileProfile"][2] > 40000
+    assert c["FindAnchorColsPP"][0] == c["AnchoredProfileProfile"][0] and c["FindAnchorColsPP"][1] > 40000   # every window's anchor columns on the device
     if binary != CUDA_BINARY:
         assert c["MemHash::FindMatches"][0] >= (300 if gap_seam == "1" else 1)
     if binary == CUDA_ALL_BINARY:

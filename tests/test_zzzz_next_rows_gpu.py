@@ -254,3 +254,77 @@ def test_eliminate_overlaps_and_lcbs_vs_oracle(mp, orc):
             so, bp, t = _oracle.lcbs(e1)
             gso, gbp, gt = mp.IdentifyBreakpoints(e1, return_ties=True)
             assert np.array_equal(gso, so) and np.array_equal(gbp, bp) and gt == t, i
+
+
+# ---- anchor columns of alignment windows (muscle::FindAnchorColsPP) ------------------------------------------------
+def _bits(a):
+    return np.asarray(a, dtype=np.float32).view(np.uint32)
+
+
+def test_anchor_cols_golden(mp):
+    """mcu_anchor_cols_batch against what the REFERENCE's FindAnchorColsPP / LetterObjScoreXP / WindowSmooth gave for the same windows
+    (tests/golden/anchor_cols.npz): anchor columns, per-column scores and smoothed scores, float for float -- every window in one
+    call (one CTA each), and each window on its own"""
+    z = _golden.npz("anchor_cols.npz")
+    n = int(z["n_windows"])
+    wins = [(z["w%d_rows" % k], int(z["w%d_n1" % k]), z["w%d_weights" % k]) for k in range(n)]
+    got = mp.libmems.FindAnchorColsPP_batch(wins, return_scores=True)
+    total = 0
+    for k in range(n):
+        cols, score, smooth = got[k]
+        assert np.array_equal(cols, z["w%d_cols" % k]), k
+        assert np.array_equal(_bits(score), _bits(z["w%d_score" % k])) and np.array_equal(_bits(smooth), _bits(z["w%d_smooth" % k])), k
+        total += cols.size
+    assert total > 300
+    for k in (0, 5, 13, 21, 29):
+        rows, n1, w = wins[k]
+        cols = mp.libmems.FindAnchorColsPP(rows[:n1], rows[n1:], weights=w)
+        assert np.array_equal(cols, z["w%d_cols" % k]), k
+    # two-genome windows need no weights; the default parameters are the settings the reference had in force
+    assert np.array_equal(mp.libmems.FindAnchorColsPP(wins[13][0][:1], wins[13][0][1:]), z["w13_cols"])
+    p = mp.libmems.AnchorParams.default()
+    assert np.array_equal(_bits(np.array(p.subst[:])), _bits(z["settings"][:16])) and p.gap_open == float(z["settings"][16])
+    assert mp.libmems.FindAnchorColsPP(b"ACGT" * 30, b"ACGT" * 31).size == 0      # different lengths: no anchor columns (MU/anchoredpp.cpp:358-362)
+
+
+def test_anchor_cols_vs_oracle(mp):
+    """fresh windows beside the oracle: 150 of the pipeline's two-row form and of alignments with more rows (random weights) in one
+    batch, a window far longer than the kernel's tiles, other thresholds"""
+    rng = np.random.default_rng(31)
+    wins = []
+    for it in range(150):
+        ncol = int(rng.integers(1, 12000))
+        n1, n2 = (1, 1) if it % 3 else (int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+        rows = synth.alignment_window(ncol, seed=5000 + it, n_rows=n1 + n2, snp=float(rng.choice([0.02, 0.1, 0.3])),
+                                      gap_rate=float(rng.choice([0.002, 0.01, 0.06])), gap_mean=int(rng.choice([2, 12, 150])),
+                                      both_gap=float(rng.choice([0.0, 0.002, 0.03])))
+        wins.append((rows, n1, rng.random(n1 + n2).astype(np.float32) if it % 3 == 0 else None))
+    wins.append((synth.alignment_window(1_000_000, seed=77, snp=0.05, gap_rate=0.005), 1, None))
+    got = mp.libmems.FindAnchorColsPP_batch(wins, return_scores=True)
+    n_cols = 0
+    for k, (rows, n1, w) in enumerate(wins):
+        c, s, m, _, _ = _oracle.anchor_cols(rows, n1, weights=w)
+        assert np.array_equal(got[k][0], c), k
+        assert np.array_equal(_bits(got[k][1]), _bits(s)) and np.array_equal(_bits(got[k][2]), _bits(m)), k
+        n_cols += c.size
+    assert n_cols > 5000
+    p = mp.libmems.AnchorParams.default()
+    p.smooth_ceil, p.min_best_col, p.min_smooth, p.smooth_window, p.anchor_spacing, p.gap_extend = 120.0, 100.0, 60.0, 7, 32, -5.0
+    po = _oracle.anchor_default_params()
+    po.smooth_ceil, po.min_best_col, po.min_smooth, po.smooth_window, po.anchor_spacing, po.gap_extend = 120.0, 100.0, 60.0, 7, 32, -5.0
+    for k in (1, 2, 3, 30, 31):
+        rows, n1, w = wins[k]
+        c, s, m, _, _ = _oracle.anchor_cols(rows, n1, weights=w, params=po)
+        g = mp.libmems.FindAnchorColsPP_batch([(rows, n1, w)], params=p, return_scores=True)[0]
+        assert np.array_equal(g[0], c) and np.array_equal(_bits(g[1]), _bits(s)) and np.array_equal(_bits(g[2]), _bits(m)), k
+
+
+def test_anchor_cols_argument_errors(mp):
+    rows = synth.alignment_window(100, seed=1)
+    p = mp.libmems.AnchorParams.default()
+    p.smooth_window = 20                      # WindowSmooth quits on an even window (MU/anchors.cpp:14-15)
+    with pytest.raises(mp.McuError):
+        mp.libmems.FindAnchorColsPP_batch([(rows, 1)], params=p)
+    with pytest.raises(ValueError):
+        mp.libmems.FindAnchorColsPP_batch([(rows, 2)])      # an alignment without rows
+    assert mp.libmems.FindAnchorColsPP_batch([]) == []
