@@ -336,6 +336,11 @@ int mcu_test_int32_peak(double* gops_out, float* ms_out);
  * the last mantissa bit of the chain's state at the end of every N-th group of eight columns, so that the tests can watch the kernel
  * repair its chain (the result stays bit-identical). */
 int mcu_test_hmm_counters(uint64_t* out3);
+/* counters of the last mcu_anchor_cols_batch call (8 x uint64): [0] 32-column segments of the smoothing chain that were finished in
+ * exact arithmetic by 32 lanes at once, [1] segments that ran as the serial float chain (csrc/anchorcols.cu), [2..7] SM cycles the
+ * first window spent scoring the columns, smoothing, selecting the best columns, searching the groups' ends, walking the groups,
+ * picking the anchor of every group */
+int mcu_test_anchor_counters(uint64_t* out8);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

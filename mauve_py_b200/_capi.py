@@ -30,7 +30,7 @@ SYMBOLS = [
     "mcu_comm_allreduce_f64", "mcu_comm_gather_bytes", "mcu_device_synchronize",
     "mcu_session_upload_sharded", "mcu_session_run_sharded", "mcu_find_mums_sharded",
     "mcu_test_sort_pairs", "mcu_test_int32_peak", "mcu_test_hmm_counters", "mcu_eliminate_overlaps", "mcu_lcbs", "mcu_sml_build_shard", "mcu_sml_build_sharded",
-    "mcu_anchor_default_params", "mcu_anchor_cols_batch",
+    "mcu_anchor_default_params", "mcu_anchor_cols_batch", "mcu_test_anchor_counters",
 ]
 
 
@@ -121,6 +121,7 @@ def lib():
     L.mcu_anchor_default_params.argtypes = [C.c_void_p]
     L.mcu_anchor_default_params.restype = None
     L.mcu_anchor_cols_batch.argtypes = [C.c_uint64] + [C.c_void_p] * 13
+    L.mcu_test_anchor_counters.argtypes = [C.c_void_p]
     _lib = L
     return L
 

@@ -8,8 +8,14 @@
 //   * gap penalties: the reference's running state (bGapping1/2, gap_left_col, cur_gap_score) is reset by every column that holds two
 //     letters, so the columns between two such columns form a run that is scored on its own: one thread walks each run with the
 //     reference's state machine and spreads the penalty, all runs at once;
-//   * smoothing: ONE running float sum per window whose roundings depend on the order -- kept as the serial chain it is (two FADDs per
-//     column on one lane), fed from shared memory tile by tile, everything around it in parallel;
+//   * smoothing: ONE running float sum per window whose roundings depend on the order.  Where no addition of the chain rounds, the
+//     chain is plain arithmetic and any order gives its values: per segment of 32 columns the prefix sums of (add - sub) are formed by
+//     a warp scan in which every addition is tested for exactness (the error term of TwoSum is zero), then total + prefix, - sub,
+//     + add are tested the same way, column by column, 32 lanes at once -- FP32 additions only.  All segments of a tile are tested
+//     at once against the totals they would start from if nothing before them rounded; the first one that fails is run as the
+//     serial chain it always was (two dependent FADDs per column on one lane), which gives the true total behind it, and the
+//     segments after it are tested again.  A tile full of rounding columns (gap penalties like -400/3 in the window) is the serial
+//     chain outright, and so are the two tiles after it.  Operands come through shared memory tile by tile, loaded one tile ahead;
 //   * best columns: flag + ordered block-wide compaction;
 //   * merging: `next group head` is a function of the head alone (a binary search per best column, in parallel), the groups are then the
 //     walk head -> next head (one lane, a few hundred steps), the pick per group in parallel.
@@ -29,6 +35,10 @@ namespace mcu {
 #define AC_FSUB(a, b) ((float)((float)(a) - (float)(b)))
 #define AC_FMUL(a, b) ((float)((float)(a) * (float)(b)))
 #define AC_FDIV(a, b) ((float)((float)(a) / (float)(b)))
+#define AC_SYNC_OR(x) (x)
+#define AC_ATOMIC_MIN(ptr, v) (*(ptr) = *(ptr) < (v) ? *(ptr) : (v))
+#define AC_ATOMIC_INC(ptr) ((*(ptr))++)
+#define AC_CLOCK() 0ull
 #else
 #define AC_HD __device__ __forceinline__
 #define AC_TID threadIdx.x
@@ -38,10 +48,15 @@ namespace mcu {
 #define AC_FSUB(a, b) __fsub_rn(a, b)
 #define AC_FMUL(a, b) __fmul_rn(a, b)
 #define AC_FDIV(a, b) __fdiv_rn(a, b)
+#define AC_SYNC_OR(x) __syncthreads_or(x)
+#define AC_ATOMIC_MIN(ptr, v) atomicMin(ptr, v)
+#define AC_ATOMIC_INC(ptr) atomicAdd(ptr, 1u)
+#define AC_CLOCK() ((unsigned long long)clock64())
 #endif
 
-#define AC_BLOCK 512
-#define AC_TILE 2048
+#define AC_BLOCK 1024
+#define AC_TILE 1024   // columns per smoothing tile: 32 segments of 32
+#define AC_PHASES 6
 
 struct AcWindow {
     u64 row_off;   // first character of the window's first row
@@ -52,15 +67,26 @@ struct AcWindow {
 
 struct AcShared {
     u8 letter[256];
-    float sub[AC_TILE], add[AC_TILE], out[AC_TILE];
+    float sub[AC_TILE], add[AC_TILE], out[AC_TILE];   // (also, as one array: a chunk of `nxt` for the walk over the groups)
+    float pre[AC_TILE];                    // per segment: inclusive prefix sums of add - sub
+    u32 seg_ok[AC_TILE / 32];              // ... every one of them formed without rounding
+    u32 seg_pass[AC_TILE / 32];            // 1: with the total it was tested against, no addition of the segment's chain rounds; 0: one
+                                           // does; 2: not tested, the sums in front of it were not exact
+    float seg_tot[AC_TILE / 32];           // what the segment adds to the running total
+    float seg_end[AC_TILE / 32];           // the chain's value behind a segment that passed
+    u32 walk_n;
+    u32 scan_w[3][AC_BLOCK / 32 + 1];      // ac_scan_min3: the warps' minima
+    unsigned long long clk[AC_PHASES + 1];
+    u32 spec_hold;                         // tiles left to run as the plain chain after a tile full of rounding columns
+    u32 seg_fast, seg_chain;               // segments finished without / with the serial chain (reported by mcu_test_anchor_counters)
     float total;
     int first, last;
-    u32 warp_sum[AC_BLOCK / 32];
-    u32 base, nbest, nanchor;
+    u32 warp_sum[AC_BLOCK / 32 + 1];
+    u32 nanchor;
 };
 
 // the gap penalties of one run of columns that starts at c0 (the first column of the pair's range, or the column after one with two
-// letters) and ends before the next column with two letters: ScoreSeqPairGaps :155-250 with its state as it is at a run's start
+// letters) and ends before the next column with two letters: ScoreSeqPairGaps :155-250 with its state as it is at a run's start.
 AC_HD void ac_gap_run(const u8* r1, const u8* r2, const u8* letter, u32 c0, u32 first, u32 last, u32 ncol, const mcu_anchor_params& p, float* gg)
 {
     bool in1 = false, in2 = false;
@@ -69,13 +95,13 @@ AC_HD void ac_gap_run(const u8* r1, const u8* r2, const u8* letter, u32 c0, u32 
     u32 c = c0;
     for (; c <= last; ++c) {
         const bool g1 = letter[r1[c]] == MCU_AC_GAP, g2 = letter[r2[c]] == MCU_AC_GAP;
-        if (g1 && g2) continue;
         if (!g1 && !g2) break;
-        bool& in = g1 ? in1 : in2;
-        if (!in) {
+        if (g1 && g2) continue;
+        if (!(g1 ? in1 : in2)) {
             left = c;
             cur = AC_FADD(cur, c == first ? p.term_gap : p.gap_open);
-            in = true;
+            if (g1) in1 = true;
+            else in2 = true;
         } else
             cur = AC_FADD(cur, p.gap_extend);
     }
@@ -91,6 +117,15 @@ AC_HD void ac_gap_run(const u8* r1, const u8* r2, const u8* letter, u32 c0, u32 
 }
 
 AC_HD float ac_ceil(float x, float ceil_at) { return x > ceil_at ? ceil_at : x; }   // Ceil() of WindowSmooth: both sides are floats widened to double
+
+// s = fl(a + b); true when the addition did not round (the error term of Knuth's TwoSum is zero; overflow gives NaN != 0)
+AC_HD bool ac_add_exact(float a, float b, float& s)
+{
+    s = AC_FADD(a, b);
+    const float bv = AC_FSUB(s, a);
+    const float err = AC_FADD(AC_FSUB(a, AC_FSUB(s, bv)), AC_FSUB(b, bv));
+    return err == 0.0f;
+}
 
 #ifndef MCU_HOST_EMU
 __device__ __forceinline__ void ac_block_minmax(AcShared& sm, int lo, int hi)
@@ -108,37 +143,512 @@ __device__ __forceinline__ void ac_block_minmax(AcShared& sm, int lo, int hi)
 __device__ __forceinline__ u32 ac_block_rank(AcShared& sm, bool flag, u32& total)
 {
     const u32 b = __ballot_sync(0xffffffffu, flag);
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     if (lane == 0) sm.warp_sum[warp] = __popc(b);
     __syncthreads();
-    u32 before = 0, all = 0;
-    for (u32 w = 0; w < AC_BLOCK / 32; ++w) {
-        const u32 v = sm.warp_sum[w];
-        before += w < warp ? v : 0;
-        all += v;
+    if (warp == 0) {   // the warps' counts -> exclusive prefixes, entry 32 = the total
+        const u32 v = lane < nwarps ? sm.warp_sum[lane] : 0;
+        u32 inc = v;
+        for (u32 o = 1; o < 32; o <<= 1) {
+            const u32 up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+        }
+        sm.warp_sum[lane] = inc - v;
+        if (lane == 31) sm.warp_sum[32] = inc;
     }
     __syncthreads();
-    total = all;
-    return before + __popc(b & ((1u << lane) - 1));
+    total = sm.warp_sum[32];
+    return sm.warp_sum[warp] + __popc(b & ((1u << lane) - 1));
 }
 #endif
 
+// the serial chain over columns [k0, k1) of the tile, starting from t: WindowSmooth's loop body (MU/anchors.cpp:38-46), two dependent
+// additions per column.  The operands of the next eight columns are in registers before the current eight are added.
+AC_HD float ac_chain(AcShared& sm, float t, u32 k0, u32 k1)
+{
+    u32 k = k0;
+#ifndef MCU_HOST_EMU
+    if (k + 8 <= k1) {
+        float a[8], b[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] = sm.sub[k + j];
+            b[j] = sm.add[k + j];
+        }
+        for (; k + 16 <= k1; k += 8) {
+            float na[8], nb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                na[j] = sm.sub[k + 8 + j];
+                nb[j] = sm.add[k + 8 + j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sm.out[k + j] = t;
+                t = AC_FSUB(t, a[j]);
+                t = AC_FADD(t, b[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a[j] = na[j];
+                b[j] = nb[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sm.out[k + j] = t;
+            t = AC_FSUB(t, a[j]);
+            t = AC_FADD(t, b[j]);
+        }
+        k += 8;
+    }
+#endif
+    for (; k < k1; ++k) {
+        sm.out[k] = t;
+        t = AC_FSUB(t, sm.sub[k]);
+        t = AC_FADD(t, sm.add[k]);   // (after the window's last column: a value nobody reads)
+    }
+    return t;
+}
+
+// One segment against the total t0 it would start from: true, its 32 outputs written and the chain's value behind it in seg_end, when
+// no addition of the chain -- t - sub, then + add, column after column -- rounds.  With exact prefix sums s_k (seg_ok) the chain's value in
+// front of column k is t0 + s_(k-1) provided that sum, the subtraction and the addition that follow are all exact: by induction over k.
+// Device: the calling warp, one column per lane.
+AC_HD bool ac_verify_segment(AcShared& sm, u32 seg, u32 n, float t0)
+{
+    const u32 base = seg * 32, cnt = n - base < 32 ? n - base : 32;
+#ifdef MCU_HOST_EMU
+    bool ok = sm.seg_ok[seg] != 0;
+    float end = t0;
+    for (u32 lane = 0; lane < cnt && ok; ++lane) {
+        float P, Q, R;
+        ok = ac_add_exact(t0, lane ? sm.pre[base + lane - 1] : 0.0f, P) && ac_add_exact(P, -sm.sub[base + lane], Q) && ac_add_exact(Q, sm.add[base + lane], R);
+        end = R;
+    }
+    if (ok) {
+        for (u32 lane = 0; lane < cnt; ++lane) sm.out[base + lane] = AC_FADD(t0, lane ? sm.pre[base + lane - 1] : 0.0f);
+        sm.seg_end[seg] = end;
+    }
+    return ok;
+#else
+    const u32 lane = threadIdx.x & 31;
+    const float mine_pre = sm.pre[base + lane];
+    float before = __shfl_up_sync(0xffffffffu, mine_pre, 1);
+    if (lane == 0) before = 0.0f;
+    float P, Q, R;
+    const bool mine = ac_add_exact(t0, before, P) & ac_add_exact(P, -sm.sub[base + lane], Q) & ac_add_exact(Q, sm.add[base + lane], R);
+    const bool ok = __all_sync(0xffffffffu, mine || lane >= cnt) && sm.seg_ok[seg] != 0;
+    if (ok) {
+        if (lane < cnt) sm.out[base + lane] = P;
+        if (lane == cnt - 1) sm.seg_end[seg] = R;
+    }
+    return ok;
+#endif
+}
+
+// The running sum over one tile (n columns, operands in sm.sub / sm.add, results to sm.out, sm.total carried).
+AC_HD void ac_smooth_tile(AcShared& sm, u32 n, u32 nseg)
+{
+    const u32 tid = AC_TID, nt = AC_NT;
+    if (sm.spec_hold) {   // the tile before was full of rounding columns: do not look for exact segments here
+        AC_SYNC();
+        if (tid == 0) {
+            sm.total = ac_chain(sm, sm.total, 0, n);
+            sm.seg_chain += nseg;
+            --sm.spec_hold;
+        }
+        AC_SYNC();
+        return;
+    }
+    // the segments' prefix sums of add - sub and their totals, every addition tested
+#ifdef MCU_HOST_EMU
+    for (u32 seg = 0; seg < nseg; ++seg) {
+        bool ok = true;
+        float run = 0.0f;
+        for (u32 lane = 0; lane < 32; ++lane) {
+            const u32 k = seg * 32 + lane;
+            float d = 0.0f;
+            if (k < n) ok = ac_add_exact(sm.add[k], -sm.sub[k], d) && ok;
+            ok = ac_add_exact(run, d, run) && ok;
+            if (k < AC_TILE) sm.pre[k] = run;
+        }
+        sm.seg_ok[seg] = ok;
+        sm.seg_tot[seg] = run;
+    }
+#else
+    for (u32 seg = tid >> 5; seg < nseg; seg += nt >> 5) {
+        const u32 lane = tid & 31, k = seg * 32 + lane;
+        float run = 0.0f;
+        bool ok = true;
+        if (k < n) ok = ac_add_exact(sm.add[k], -sm.sub[k], run);
+        for (u32 o = 1; o < 32; o <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, run, o);
+            float sum;
+            const bool e = ac_add_exact(run, up, sum);
+            if (lane >= o) {
+                run = sum;
+                ok = ok && e;
+            }
+        }
+        sm.pre[k] = run;
+        const bool all = __all_sync(0xffffffffu, ok);
+        if (lane == 31) sm.seg_tot[seg] = run;
+        if (lane == 0) sm.seg_ok[seg] = all;
+    }
+#endif
+    AC_SYNC();
+    {   // segments whose own sums round (a gap penalty like -400/3 among their operands): more than a few, and the tile is the chain
+        u32 nbad = 0;
+#ifdef MCU_HOST_EMU
+        for (u32 seg = 0; seg < nseg; ++seg) nbad += sm.seg_ok[seg] ? 0u : 1u;
+#else
+        nbad = __popc(__ballot_sync(0xffffffffu, (tid & 31) < nseg && !sm.seg_ok[tid & 31]));
+#endif
+        if (nbad > 3) {
+            if (tid == 0) {
+                sm.total = ac_chain(sm, sm.total, 0, n);
+                sm.seg_chain += nseg;
+                if (nbad > nseg / 2) sm.spec_hold = 2;
+            }
+            AC_SYNC();
+            return;
+        }
+    }
+    u32 seg0 = 0;
+    for (u32 round = 0; seg0 < nseg; ++round) {
+        const float t = sm.total;   // the chain's value in front of segment seg0
+        if (round >= 6) {
+            AC_SYNC();   // (everybody has read sm.total)
+            if (tid == 0) {
+                sm.total = ac_chain(sm, t, seg0 * 32, n);
+                sm.seg_chain += nseg - seg0;
+            }
+            AC_SYNC();
+            return;
+        }
+        // every segment from seg0 on against the total it would start from if none before it rounded
+#ifdef MCU_HOST_EMU
+        {
+            float ts = t;
+            bool ts_ok = true;
+            for (u32 seg = seg0; seg < nseg; ++seg) {
+                sm.seg_pass[seg] = !ts_ok ? 2u : ac_verify_segment(sm, seg, n, ts) ? 1u : 0u;
+                ts_ok = ac_add_exact(ts, sm.seg_tot[seg], ts) && ts_ok;
+            }
+        }
+#else
+        for (u32 seg = seg0 + (tid >> 5); seg < nseg; seg += nt >> 5) {
+            const u32 lane = tid & 31;
+            float part = seg0 + lane < seg ? sm.seg_tot[seg0 + lane] : 0.0f;   // nseg <= 32: one lane per earlier segment
+            bool exact = true;
+            for (u32 o = 16; o; o >>= 1) {
+                float sum;
+                exact = ac_add_exact(part, __shfl_xor_sync(0xffffffffu, part, o), sum) && exact;
+                part = sum;
+            }
+            float ts;
+            exact = ac_add_exact(t, part, ts) && exact;
+            const u32 verdict = !__all_sync(0xffffffffu, exact) ? 2u : ac_verify_segment(sm, seg, n, ts) ? 1u : 0u;
+            if (lane == 0) sm.seg_pass[seg] = verdict;
+        }
+#endif
+        AC_SYNC();
+        u32 f = nseg, nfail = 0;
+#ifdef MCU_HOST_EMU
+        for (u32 seg = seg0; seg < nseg; ++seg) {
+            if (sm.seg_pass[seg] != 1u && f == nseg) f = seg;
+            if (sm.seg_pass[seg] == 0u) ++nfail;
+        }
+#else
+        {   // every warp for itself: lane l looks at segment seg0 + l
+            const u32 seg = seg0 + (tid & 31);
+            const u32 verdict = seg < nseg ? sm.seg_pass[seg] : 1u;
+            const u32 open = __ballot_sync(0xffffffffu, verdict != 1u);
+            nfail = __popc(__ballot_sync(0xffffffffu, verdict == 0u));
+            if (open) f = seg0 + (__ffs(open) - 1);
+        }
+#endif
+        if (tid == 0) {   // (everybody read sm.total before the barrier above; the flags are written again only after the one below)
+            const float tf = f == seg0 ? t : sm.seg_end[f - 1];   // the chain's true value in front of segment f
+            sm.seg_fast += f - seg0;
+            if (f == nseg)
+                sm.total = tf;
+            else if (round == 0 && nfail > 3) {   // many: the chain from the first one to the end of the tile
+                sm.total = ac_chain(sm, tf, f * 32, n);
+                sm.seg_chain += nseg - f;
+                if (nfail > nseg / 2) sm.spec_hold = 2;
+            } else {
+                const u32 k1 = (f + 1) * 32 < n ? (f + 1) * 32 : n;
+                sm.total = ac_chain(sm, tf, f * 32, k1);
+                sm.seg_chain += 1;
+            }
+        }
+        AC_SYNC();
+        if (f == nseg || (round == 0 && nfail > 3)) return;
+        seg0 = f + 1;
+    }
+}
+
 // One window, start to end.  score / smooth / gg / best / nxt / heads: ncol entries each at the window's col_off.
-AC_HD void ac_window(AcShared& sm, const AcWindow w, const u8* rows_all, const float* weights, const mcu_anchor_params& p, float* score, float* smooth,
-                     float* gg, u32* best, u32* nxt, u32* heads, u32* cols_out, u32* count_out)
+// inclusive prefix minimum over the CTA's threads (thread order) of three values at once, continued from the minima of the chunks
+// before (carry, kept by every thread).  Every thread calls it.
+AC_HD void ac_scan_min3(AcShared& sm, u32& a, u32& b, u32& c, u32 carry[3])
+{
+#ifdef MCU_HOST_EMU
+    a = a < carry[0] ? a : carry[0];
+    b = b < carry[1] ? b : carry[1];
+    c = c < carry[2] ? c : carry[2];
+    carry[0] = a;
+    carry[1] = b;
+    carry[2] = c;
+#else
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (u32 o = 1; o < 32; o <<= 1) {
+        const u32 ua = __shfl_up_sync(0xffffffffu, a, o), ub = __shfl_up_sync(0xffffffffu, b, o), uc = __shfl_up_sync(0xffffffffu, c, o);
+        if (lane >= o) {
+            a = min(a, ua);
+            b = min(b, ub);
+            c = min(c, uc);
+        }
+    }
+    if (lane == 31) {
+        sm.scan_w[0][warp] = a;
+        sm.scan_w[1][warp] = b;
+        sm.scan_w[2][warp] = c;
+    }
+    __syncthreads();
+    if (warp < 3) {   // warp v: the minima of the warps in front of every warp for value v; entry 32 = the chunk's minimum
+        const u32 mine = lane < nwarps ? sm.scan_w[warp][lane] : 0xffffffffu;
+        u32 inc = mine;
+        for (u32 o = 1; o < 32; o <<= 1) {
+            const u32 up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc = min(inc, up);
+        }
+        u32 exc = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) exc = 0xffffffffu;
+        sm.scan_w[warp][lane] = exc;
+        if (lane == 31) sm.scan_w[warp][32] = inc;
+    }
+    __syncthreads();
+    a = min(min(a, sm.scan_w[0][warp]), carry[0]);
+    b = min(min(b, sm.scan_w[1][warp]), carry[1]);
+    c = min(min(c, sm.scan_w[2][warp]), carry[2]);
+    carry[0] = min(carry[0], sm.scan_w[0][32]);
+    carry[1] = min(carry[1], sm.scan_w[1][32]);
+    carry[2] = min(carry[2], sm.scan_w[2][32]);
+    __syncthreads();
+#endif
+}
+
+// first / last column where not both rows have a gap (MU/anchoredpp.cpp:46-74); the whole window when there is none
+AC_HD void ac_pair_range(AcShared& sm, const u8* code, u32 L, u32& first, u32& last)
+{
+    const u32 tid = AC_TID, nt = AC_NT;
+    if (tid == 0) {
+        sm.first = (int)L;
+        sm.last = -1;
+    }
+    AC_SYNC();
+    int lo = (int)L, hi = -1;
+    for (u32 c = tid; c < L; c += nt)
+        if (code[c] != 0x2d) {   // not gap | gap
+            lo = lo < (int)c ? lo : (int)c;
+            hi = (int)c;
+        }
+#ifdef MCU_HOST_EMU
+    sm.first = lo;
+    sm.last = hi;
+#else
+    ac_block_minmax(sm, lo, hi);
+#endif
+    AC_SYNC();
+    first = sm.last < 0 ? 0u : (u32)sm.first;
+    last = sm.last < 0 ? L - 1 : (u32)sm.last;
+}
+
+#define AC_NONE 0xffffffffu
+// a column's pair of letters in six bits: 0..3 residues, 4 a letter outside the alphabet, 5 a gap; row 2 in bits 3..5
+AC_HD u32 ac_code(const u8* letter, u8 c1, u8 c2)
+{
+    const u32 a = letter[c1], b = letter[c2];
+    return (a < 4 ? a : a == MCU_AC_GAP ? 5u : 4u) | ((b < 4 ? b : b == MCU_AC_GAP ? 5u : 4u) << 3);
+}
+#define AC_G1(k) (((k) & 7u) == 5u)
+#define AC_G2(k) (((k) >> 3) == 5u)
+
+// One pair of rows, no extension penalty (the setting in force for DNA): score[c] += ww * (letters + gap penalties), with the reference's
+// gap state machine (:155-250) in closed form.  Its state is reset by every column with two letters, so a run of columns between two such
+// columns is scored on its own: each row's FIRST gap column of the run opens a gap -- the first column of the pair's range at the
+// terminal price, :172 / :198 --, every other gap column adds gap_extend = 0, and the penalty is spread from the LATER of the two opening
+// columns (gap_left_col is overwritten, :170 / :196) to the run's end, or to the end of the window when the run is still open at the
+// pair's last column (:228-248).  Two scans over the columns do it whatever the runs look like: backwards, the next column with two
+// letters / with a gap in row 1 only / in row 2 only (at a run's first column that is the whole run: its three numbers go to
+// d_left / d_end / d_per there); forwards, the run a column belongs to.
+// code: one byte per column (scratch); d_left, d_end, d_per: one word per column (scratch, only the runs' first columns are used)
+AC_HD void ac_score_pair_scans(AcShared& sm, const u8* __restrict__ r1, const u8* __restrict__ r2, u32 L, float ww, const mcu_anchor_params& p,
+                               float* score, u8* code, u32* __restrict__ d_left, u32* __restrict__ d_end, u32* __restrict__ d_per)
+{
+    const u32 tid = AC_TID, nt = AC_NT;
+    const u8* letter = sm.letter;
+#pragma unroll 4
+    for (u32 c = tid; c < L; c += nt) code[c] = (u8)ac_code(letter, r1[c], r2[c]);
+    AC_SYNC();
+    u32 first, last;
+    ac_pair_range(sm, code, L, first, last);
+    // backwards: thread t of a chunk looks at column hi - 1 - t, so that a prefix minimum over the threads is a suffix minimum over columns
+    {
+        u32 carry[3] = {AC_NONE, AC_NONE, AC_NONE};
+        for (u32 hi = last + 1; hi > first; hi = hi > nt ? hi - nt : 0) {
+            const bool valid = tid < hi && hi - 1 - tid >= first;
+            const u32 c = valid ? hi - 1 - tid : 0;
+            const u32 k = valid ? code[c] : 0;
+            const bool g1 = AC_G1(k), g2 = AC_G2(k), two = !g1 && !g2;
+            u32 n_two = valid && two ? c : AC_NONE, n_g1 = valid && g1 && !g2 ? c : AC_NONE, n_g2 = valid && g2 && !g1 ? c : AC_NONE;
+            ac_scan_min3(sm, n_two, n_g1, n_g2, carry);
+            bool head = valid && !two;
+            if (head && c != first) {
+                const u32 kb = code[c - 1];
+                head = !AC_G1(kb) && !AC_G2(kb);
+            }
+            if (head) {
+                const u32 e = n_two < last + 1 ? n_two : last + 1;
+                const u32 f1 = n_g1 < e ? n_g1 : AC_NONE, f2 = n_g2 < e ? n_g2 : AC_NONE;
+                u32 left = AC_NONE, end = e;
+                float per_site = 0.0f;
+                if (f1 != AC_NONE || f2 != AC_NONE) {
+                    const u32 fa = f1 < f2 ? f1 : f2, fb = f1 < f2 ? f2 : f1;   // fb none: only one row has gaps in this run
+                    float cur = AC_FADD(0.0f, fa == first ? p.term_gap : p.gap_open);
+                    left = fa;
+                    if (fb != AC_NONE) {
+                        cur = AC_FADD(cur, p.gap_open);
+                        left = fb;
+                    }
+                    if (e > last) {
+                        cur = AC_FSUB(cur, p.gap_open);
+                        cur = AC_FADD(cur, p.term_gap);
+                        end = L;
+                    }
+                    per_site = AC_FDIV(cur, (float)(end - left));
+                }
+                d_left[c] = left;
+                d_end[c] = end;
+#ifdef MCU_HOST_EMU
+                memcpy(&d_per[c], &per_site, 4);
+#else
+                d_per[c] = __float_as_uint(per_site);
+#endif
+            }
+            if (hi <= nt) break;
+        }
+    }
+    AC_SYNC();
+    // forwards: the run's first column in front of (or at) every column, then the column's share of the run's penalty
+    {
+        u32 carry[3] = {AC_NONE, AC_NONE, AC_NONE};
+        for (u32 c0 = 0; c0 < L; c0 += nt) {
+            const u32 c = c0 + tid;
+            const bool valid = c < L;
+            const u32 k = valid ? code[c] : 0;
+            const bool g1 = AC_G1(k), g2 = AC_G2(k), two = !g1 && !g2;
+            bool head = valid && !two && c >= first && c <= last;
+            if (head && c != first) {
+                const u32 kb = code[c - 1];
+                head = !AC_G1(kb) && !AC_G2(kb);
+            }
+            // (the latest first-column-of-a-run at or in front of c: the largest one, as a minimum of complements.  A column that lies
+            //  behind that run's end -- one with two letters, or all-gap columns behind the pair's range -- gets nothing from it)
+            u32 h = head ? ~(c + 1) : AC_NONE, x1 = AC_NONE, x2 = AC_NONE;
+            ac_scan_min3(sm, h, x1, x2, carry);
+            if (valid) {
+                float g = 0.0f;
+                if (h != AC_NONE) {
+                    const u32 hc = ~h - 1;
+                    const u32 left = d_left[hc];
+                    if (left != AC_NONE && c >= left && c < d_end[hc]) {
+#ifdef MCU_HOST_EMU
+                        memcpy(&g, &d_per[hc], 4);
+#else
+                        g = __uint_as_float(d_per[hc]);
+#endif
+                    }
+                }
+                const u32 a = k & 7u, b = k >> 3;
+                const float mm = (a < 4 && b < 4) ? p.subst[a][b] : 0.0f;
+                score[c] = AC_FADD(score[c], AC_FMUL(ww, AC_FADD(mm, g)));
+            }
+        }
+    }
+    AC_SYNC();
+}
+
+// One pair of rows with an extension penalty: every run's penalty is a float sum in column order, walked by the thread that owns the
+// run's first column (ac_gap_run).  gg: one float per column, zero on entry and on exit.
+AC_HD void ac_score_pair_walks(AcShared& sm, const u8* __restrict__ r1, const u8* __restrict__ r2, u32 L, float ww, const mcu_anchor_params& p,
+                               float* score, float* gg)
+{
+    const u32 tid = AC_TID, nt = AC_NT;
+    const u8* letter = sm.letter;
+    if (tid == 0) {
+        sm.first = (int)L;
+        sm.last = -1;
+    }
+    AC_SYNC();
+    {
+        int lo = (int)L, hi = -1;
+        for (u32 c = tid; c < L; c += nt)
+            if (letter[r1[c]] != MCU_AC_GAP || letter[r2[c]] != MCU_AC_GAP) {
+                lo = lo < (int)c ? lo : (int)c;
+                hi = (int)c;
+            }
+#ifdef MCU_HOST_EMU
+        sm.first = lo;
+        sm.last = hi;
+#else
+        ac_block_minmax(sm, lo, hi);
+#endif
+    }
+    AC_SYNC();
+    const u32 first = sm.last < 0 ? 0u : (u32)sm.first, last = sm.last < 0 ? L - 1 : (u32)sm.last;
+    for (u32 c = first + tid; c <= last; c += nt) {
+        const bool two = letter[r1[c]] != MCU_AC_GAP && letter[r2[c]] != MCU_AC_GAP;
+        if (two) continue;
+        if (c != first) {
+            const bool two_before = letter[r1[c - 1]] != MCU_AC_GAP && letter[r2[c - 1]] != MCU_AC_GAP;
+            if (!two_before) continue;
+        }
+        ac_gap_run(r1, r2, letter, c, first, last, L, p, gg);
+    }
+    AC_SYNC();
+    for (u32 c = tid; c < L; c += nt) {
+        const u32 a = letter[r1[c]], b = letter[r2[c]];
+        const float mm = (a < 4 && b < 4) ? p.subst[a][b] : 0.0f;   // outside [first, last] both rows have gaps: 0 as well
+        score[c] = AC_FADD(score[c], AC_FMUL(ww, AC_FADD(mm, gg[c])));
+        gg[c] = 0.0f;
+    }
+    AC_SYNC();
+}
+
+// (smooth may be the same memory as gg: the gap penalties are dead when the smoothing starts; `before` must be neither)
+AC_HD void ac_window(AcShared& sm, const AcWindow w, const u8* __restrict__ rows_all, const float* __restrict__ weights, const mcu_anchor_params& p,
+                     float* score, float* smooth, float* gg, u32* before, u32* __restrict__ best, u32* __restrict__ nxt,
+                     u32* __restrict__ heads, u32* __restrict__ cols_out, u32* __restrict__ count_out)
 {
     const u32 tid = AC_TID, nt = AC_NT;
     const u32 L = w.ncol;
     const u8* rows = rows_all + w.row_off;
     for (u32 i = tid; i < 256; i += nt) sm.letter[i] = p.letter_of_char[i];
+#pragma unroll 4
     for (u32 c = tid; c < L; c += nt) {
         score[c] = 0.0f;
-        smooth[c] = 0.0f;
         gg[c] = 0.0f;
     }
     if (tid == 0) {
-        sm.base = 0;
         sm.nanchor = 0;
+        sm.seg_fast = 0;
+        sm.seg_chain = 0;
+        sm.spec_hold = 0;
+        sm.clk[0] = AC_CLOCK();
     }
     AC_SYNC();
     const u8* letter = sm.letter;
@@ -150,119 +660,131 @@ AC_HD void ac_window(AcShared& sm, const AcWindow w, const u8* rows_all, const f
             const u8* r2 = rows + (u64)(w.n1 + j) * L;
             const float w1 = weights ? weights[w.w_off + i] : 1.0f, w2 = weights ? weights[w.w_off + w.n1 + j] : 1.0f;
             const float ww = AC_FMUL(w1, w2);
-            // first / last column where not both rows have a gap (:46-74)
-            if (tid == 0) {
-                sm.first = (int)L;
-                sm.last = -1;
-            }
-            AC_SYNC();
-            {
-                int lo = (int)L, hi = -1;
-                for (u32 c = tid; c < L; c += nt)
-                    if (letter[r1[c]] != MCU_AC_GAP || letter[r2[c]] != MCU_AC_GAP) {
-                        lo = lo < (int)c ? lo : (int)c;
-                        hi = (int)c;
-                    }
-#ifdef MCU_HOST_EMU
-                sm.first = lo;
-                sm.last = hi;
-#else
-                ac_block_minmax(sm, lo, hi);
-#endif
-            }
-            AC_SYNC();
-            const u32 first = sm.last < 0 ? 0u : (u32)sm.first, last = sm.last < 0 ? L - 1 : (u32)sm.last;
-            // the runs of columns with a gap in one row, each by the thread that owns its first column
-            for (u32 c = first + tid; c <= last; c += nt) {
-                const bool two = letter[r1[c]] != MCU_AC_GAP && letter[r2[c]] != MCU_AC_GAP;
-                if (two) continue;
-                if (c != first) {
-                    const bool two_before = letter[r1[c - 1]] != MCU_AC_GAP && letter[r2[c - 1]] != MCU_AC_GAP;
-                    if (!two_before) continue;
-                }
-                ac_gap_run(r1, r2, letter, c, first, last, L, p, gg);
-            }
-            AC_SYNC();
-            for (u32 c = tid; c < L; c += nt) {
-                const u32 a = letter[r1[c]], b = letter[r2[c]];
-                const float mm = (a < 4 && b < 4) ? p.subst[a][b] : 0.0f;   // outside [first, last] both rows have gaps: 0 as well
-                score[c] = AC_FADD(score[c], AC_FMUL(ww, AC_FADD(mm, gg[c])));
-                gg[c] = 0.0f;
-            }
-            AC_SYNC();
+            if (p.gap_extend == 0.0f) ac_score_pair_scans(sm, r1, r2, L, ww, p, score, (u8*)gg, best, nxt, heads);
+            else ac_score_pair_walks(sm, r1, r2, L, ww, p, score, gg);
         }
 
-    // ---- WindowSmooth: the running sum is one serial chain (thread 0); its operands come through shared memory
+    if (tid == 0) sm.clk[1] = AC_CLOCK();
+
+    // ---- WindowSmooth
     const u32 W = p.smooth_window, w2 = W / 2;
-    if (L > W) {
+    if (L <= W) {
+        for (u32 c = tid; c < L; c += nt) smooth[c] = 0.0f;
+    } else {
+        for (u32 c = tid; c < w2; c += nt) {   // the window's edges (MU/anchors.cpp:25-29)
+            smooth[c] = 0.0f;
+            smooth[L - c - 1] = 0.0f;
+        }
         if (tid == 0) {
             float t = 0.0f;
             for (u32 i = 0; i < W; ++i) t = AC_FADD(t, ac_ceil(score[i], p.smooth_ceil));
             sm.total = t;
         }
         const u32 i_last = L - w2 - 1;
+        const float fw = (float)W;
+        // a tile's operands travel global -> registers while the tile before is being summed, registers -> shared memory afterwards
+        constexpr int PF = 4;   // columns per thread and tile (device: 256 threads or more)
+        float pa[PF], pb[PF];
+#define AC_PREFETCH(i0_, n_)                                                                               \
+    for (int q = 0; q < PF; ++q) {                                                                         \
+        const u32 k = tid + (u32)q * nt;                                                                   \
+        if (k < (n_)) {                                                                                    \
+            const u32 i = (i0_) + k;                                                                       \
+            pa[q] = score[i - w2];                                                                         \
+            pb[q] = i + w2 + 1 < L ? score[i + w2 + 1] : 0.0f; /* unused at i_last */                      \
+        }                                                                                                  \
+    }
+        u32 n = (i_last - w2 + 1) < AC_TILE ? (i_last - w2 + 1) : AC_TILE;
+#ifndef MCU_HOST_EMU
+        AC_PREFETCH(w2, n)
+#endif
         for (u32 i0 = w2; i0 <= i_last; i0 += AC_TILE) {
-            const u32 n = (i_last - i0 + 1) < AC_TILE ? (i_last - i0 + 1) : AC_TILE;
-            for (u32 k = tid; k < n; k += nt) {
+            n = (i_last - i0 + 1) < AC_TILE ? (i_last - i0 + 1) : AC_TILE;
+#ifdef MCU_HOST_EMU
+            for (u32 k = 0; k < n; ++k) {
                 const u32 i = i0 + k;
                 sm.sub[k] = ac_ceil(score[i - w2], p.smooth_ceil);
-                sm.add[k] = i + w2 + 1 < L ? ac_ceil(score[i + w2 + 1], p.smooth_ceil) : 0.0f;   // not used at i_last
+                sm.add[k] = i + w2 + 1 < L ? ac_ceil(score[i + w2 + 1], p.smooth_ceil) : 0.0f;
             }
-            AC_SYNC();
-            if (tid == 0) {
-                float t = sm.total;
-                const float fw = (float)W;
-                for (u32 k = 0; k < n; ++k) {
-                    sm.out[k] = AC_FDIV(t, fw);
-                    if (i0 + k == i_last) break;
-                    t = AC_FSUB(t, sm.sub[k]);
-                    t = AC_FADD(t, sm.add[k]);
+#else
+            for (int q = 0; q < PF; ++q) {
+                const u32 k = tid + (u32)q * nt;
+                if (k < n) {
+                    sm.sub[k] = ac_ceil(pa[q], p.smooth_ceil);
+                    sm.add[k] = ac_ceil(pb[q], p.smooth_ceil);
                 }
-                sm.total = t;
             }
+            if (i0 + AC_TILE <= i_last) {
+                const u32 n_next = (i_last - (i0 + AC_TILE) + 1) < AC_TILE ? (i_last - (i0 + AC_TILE) + 1) : AC_TILE;
+                AC_PREFETCH(i0 + AC_TILE, n_next)
+            }
+#endif
             AC_SYNC();
-            for (u32 k = tid; k < n; k += nt) smooth[i0 + k] = sm.out[k];
+            const u32 nseg = (n + 31) / 32;
+            ac_smooth_tile(sm, n, nseg);
+            for (u32 k = tid; k < n; k += nt) smooth[i0 + k] = AC_FDIV(sm.out[k], fw);
             AC_SYNC();
         }
+#undef AC_PREFETCH
     }
     AC_SYNC();
 
-    // ---- FindBestColsComboPP: the columns that pass both thresholds, in order
+    if (tid == 0) sm.clk[2] = AC_CLOCK();
+
+    // ---- FindBestColsComboPP: the columns that pass both thresholds, in order; before[c] = how many of them lie in front of column c
+    u32 nbest = 0;
     for (u32 c0 = 0; c0 < L; c0 += nt) {
         const u32 c = c0 + tid;
         const bool flag = c < L && !(score[c] < p.min_best_col) && !(smooth[c] < p.min_smooth);
 #ifdef MCU_HOST_EMU
-        if (flag) best[sm.base++] = c;
+        before[c] = nbest;
+        if (flag) best[nbest++] = c;
 #else
         u32 total;
-        const u32 rank = ac_block_rank(sm, flag, total);
-        if (flag) best[sm.base + rank] = c;
-        __syncthreads();
-        if (tid == 0) sm.base += total;
+        const u32 rank = nbest + ac_block_rank(sm, flag, total);
+        if (c < L) before[c] = rank;
+        if (flag) best[rank] = c;
+        nbest += total;
         __syncthreads();
 #endif
     }
     AC_SYNC();
-    const u32 nbest = sm.base;
 
-    // ---- MergeBestCols: groups of best columns closer to the group's first one than the spacing
-    for (u32 n = tid; n < nbest; n += nt) {   // where the group that starts at n ends: the first i > n with best[i] - best[n] >= spacing
-        const u32 head = best[n];
-        u32 lo = n + 1, hi = nbest;
-        while (lo < hi) {
-            const u32 mid = (lo + hi) >> 1;
-            if (best[mid] - head >= p.anchor_spacing) hi = mid;
-            else lo = mid + 1;
+    if (tid == 0) sm.clk[3] = AC_CLOCK();
+
+    // ---- MergeBestCols: groups of best columns closer to the group's first one than the spacing.  The group that starts at best[n]
+    //      ends in front of the first best column at or beyond best[n] + spacing
+    for (u32 n = tid; n < nbest; n += nt) {
+        const u64 stop = (u64)best[n] + p.anchor_spacing;
+        nxt[n] = stop < L ? before[stop] : nbest;
+    }
+    AC_SYNC();
+    if (tid == 0) sm.clk[4] = AC_CLOCK();
+    {   // the walk head -> next head, one lane, through chunks of `nxt` in shared memory
+        u32* s_nxt = (u32*)sm.sub;   // sub, add, out: one stretch of 3 * AC_TILE words
+        const u32 CH = 3u * AC_TILE;
+        if (tid == 0) sm.walk_n = 0;
+        AC_SYNC();
+        for (;;) {
+            const u32 c0 = sm.walk_n;
+            if (c0 >= nbest) break;
+            const u32 cn = nbest - c0 < CH ? nbest - c0 : CH;
+            for (u32 k = tid; k < cn; k += nt) s_nxt[k] = nxt[c0 + k];
+            AC_SYNC();
+            if (tid == 0) {
+                u32 n = c0, k = sm.nanchor;
+                while (n < c0 + cn) {
+                    heads[k++] = n;
+                    n = s_nxt[n - c0];
+                }
+                sm.nanchor = k;
+                sm.walk_n = n;
+            }
+            AC_SYNC();
         }
-        nxt[n] = lo;
     }
     AC_SYNC();
-    if (tid == 0) {
-        u32 k = 0;
-        for (u32 n = 0; n < nbest; n = nxt[n]) heads[k++] = n;
-        sm.nanchor = k;
-    }
-    AC_SYNC();
+    if (tid == 0) sm.clk[5] = AC_CLOCK();
     const u32 nanchor = sm.nanchor;
     for (u32 k = tid; k < nanchor; k += nt) {
         const u32 n = heads[k], within = nxt[n] - n - 1, head = best[n];
@@ -285,27 +807,64 @@ AC_HD void ac_window(AcShared& sm, const AcWindow w, const u8* rows_all, const f
         }
         cols_out[k] = pick;
     }
-    if (tid == 0) *count_out = nanchor;
+    if (tid == 0) {
+        *count_out = nanchor;
+        sm.clk[6] = AC_CLOCK();
+    }
 }
 
 #ifndef MCU_HOST_EMU
 
+// smem_cols > 0: a window of up to that many columns keeps its per-column scores and gap penalties / smoothed scores in (dynamic) shared
+// memory -- the latency form, one CTA per SM, for calls with few windows; they reach global memory only when the caller wants them.
 __global__ __launch_bounds__(AC_BLOCK) void anchor_cols_kernel(const AcWindow* __restrict__ windows, const u8* __restrict__ rows,
                                                                const float* __restrict__ weights, const mcu_anchor_params p, float* score, float* smooth,
-                                                               float* gg, u32* best, u32* nxt, u32* heads, u32* cols_out, u32* counts)
+                                                               float* gg, u32* best, u32* nxt, u32* heads, u32* cols_out, u32* counts,
+                                                               unsigned long long* seg_counters, u32 smem_cols, int want_scores)
 {
     __shared__ AcShared sm;
+    extern __shared__ float ac_dyn[];
     const AcWindow w = windows[blockIdx.x];
     if (w.ncol == 0) {
         if (threadIdx.x == 0) counts[blockIdx.x] = 0;
         return;
     }
-    ac_window(sm, w, rows, weights, p, score + w.col_off, smooth + w.col_off, gg + w.col_off, best + w.col_off, nxt + w.col_off, heads + w.col_off,
-              cols_out + w.col_off, counts + blockIdx.x);
+    const bool in_smem = w.ncol <= smem_cols;
+    float* my_score = in_smem ? ac_dyn : score + w.col_off;
+    float* my_gg = in_smem ? ac_dyn + smem_cols : gg + w.col_off;
+    float* my_smooth = in_smem ? my_gg : smooth + w.col_off;
+    u32* before = in_smem ? (u32*)(gg + w.col_off) : (u32*)my_gg;   // global mode: the gap penalties' memory once they are dead
+    ac_window(sm, w, rows, weights, p, my_score, my_smooth, my_gg, before, best + w.col_off, nxt + w.col_off, heads + w.col_off, cols_out + w.col_off,
+              counts + blockIdx.x);
+    if (in_smem && want_scores) {
+        __syncthreads();
+        for (u32 c = threadIdx.x; c < w.ncol; c += blockDim.x) {
+            score[w.col_off + c] = my_score[c];
+            smooth[w.col_off + c] = my_smooth[c];
+        }
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(seg_counters, (unsigned long long)sm.seg_fast);
+        atomicAdd(seg_counters + 1, (unsigned long long)sm.seg_chain);
+        if (blockIdx.x == 0)   // SM cycles of the first window's phases: scoring, smoothing, best columns, group search, group walk, picks
+            for (int i = 0; i < AC_PHASES; ++i) seg_counters[2 + i] = sm.clk[i + 1] - sm.clk[i];
+    }
+}
+
+// the anchor columns of all windows packed one after the other (a batch's result is a few columns per thousand: only those travel back)
+__global__ void anchor_cols_pack_kernel(const AcWindow* __restrict__ windows, const u32* __restrict__ cols, const u32* __restrict__ counts,
+                                        const u64* __restrict__ dense_off, u32* __restrict__ dense)
+{
+    const AcWindow w = windows[blockIdx.x];
+    const u32 n = counts[blockIdx.x];
+    const u64 to = dense_off[blockIdx.x];
+    for (u32 k = threadIdx.x; k < n; k += blockDim.x) dense[to + k] = cols[w.col_off + k];
 }
 
 struct AcState {
-    DevBuf windows, rows, weights, score, smooth, gg, best, nxt, heads, cols, counts;
+    DevBuf windows, rows, weights, score, smooth, gg, best, nxt, heads, cols, counts, dense, dense_off, seg_counters;
+    u64 last_counters[2 + AC_PHASES] = {0};
+    size_t max_dyn_smem = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -314,8 +873,14 @@ static AcState g_ac;
 void ac_release()
 {
     AcState& st = g_ac;
-    DevBuf* bufs[] = {&st.windows, &st.rows, &st.weights, &st.score, &st.smooth, &st.gg, &st.best, &st.nxt, &st.heads, &st.cols, &st.counts};
+    DevBuf* bufs[] = {&st.windows, &st.rows, &st.weights, &st.score, &st.smooth, &st.gg, &st.best, &st.nxt, &st.heads, &st.cols, &st.counts,
+                      &st.dense, &st.dense_off, &st.seg_counters};
     for (DevBuf* b : bufs) b->release();
+}
+
+void ac_last_counters(u64* out8)
+{
+    for (int i = 0; i < 2 + AC_PHASES; ++i) out8[i] = g_ac.last_counters[i];
 }
 
 void ac_default_params(mcu_anchor_params* p)
@@ -375,6 +940,14 @@ int ac_batch(u64 n, const char* rows, const u64* row_off, const u32* ncol, const
     }
     cols_total = col_off[n];
     if (!st.stream) {
+        int dev = 0, optin = 0;
+        MCU_CUDA(cudaGetDevice(&dev));
+        MCU_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        cudaFuncAttributes fa;
+        MCU_CUDA(cudaFuncGetAttributes(&fa, anchor_cols_kernel));
+        const long room = (long)optin - (long)fa.sharedSizeBytes - 1024;
+        st.max_dyn_smem = room > 0 ? (size_t)room : 0;
+        MCU_CUDA(cudaFuncSetAttribute(anchor_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st.max_dyn_smem));
         MCU_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
         MCU_CUDA(cudaEventCreate(&st.ev0));
         MCU_CUDA(cudaEventCreate(&st.ev1));
@@ -387,23 +960,58 @@ int ac_batch(u64 n, const char* rows, const u64* row_off, const u32* ncol, const
     MCU_TRY(st.score.reserve(ct * 4)); MCU_TRY(st.smooth.reserve(ct * 4)); MCU_TRY(st.gg.reserve(ct * 4));
     MCU_TRY(st.best.reserve(ct * 4)); MCU_TRY(st.nxt.reserve(ct * 4)); MCU_TRY(st.heads.reserve(ct * 4)); MCU_TRY(st.cols.reserve(ct * 4));
     MCU_TRY(st.counts.reserve(n * 4));
+    MCU_TRY(st.seg_counters.reserve(sizeof st.last_counters));
+    MCU_CUDA(cudaMemsetAsync(st.seg_counters.p, 0, sizeof st.last_counters, s));
     MCU_CUDA(cudaMemcpyAsync(st.windows.p, win.data(), n * sizeof(AcWindow), cudaMemcpyHostToDevice, s));
     if (rows_bytes) MCU_CUDA(cudaMemcpyAsync(st.rows.p, rows, rows_bytes, cudaMemcpyHostToDevice, s));
     if (weights) MCU_CUDA(cudaMemcpyAsync(st.weights.p, weights, n_weights * sizeof(float), cudaMemcpyHostToDevice, s));
     MCU_CUDA(cudaEventRecord(st.ev0, s));
-    anchor_cols_kernel<<<(unsigned)n, AC_BLOCK, 0, s>>>(st.windows.as<AcWindow>(), st.rows.as<u8>(), weights ? st.weights.as<float>() : nullptr, p,
-                                                         st.score.as<float>(), st.smooth.as<float>(), st.gg.as<float>(), st.best.as<u32>(),
-                                                         st.nxt.as<u32>(), st.heads.as<u32>(), st.cols.as<u32>(), st.counts.as<u32>());
+    // few windows: the latency form (1024 threads, per-column arrays in shared memory); a full batch: CTAs of 256 threads, several per
+    // SM, so that one window's serial stretches run under the others' parallel ones
+    const bool latency_form = n <= 2ull * (u64)sm_count();
+    u32 smem_cols = 0;
+    if (latency_form) {
+        u32 longest = 0;
+        for (u64 i = 0; i < n; ++i) longest = ncol[i] > longest ? ncol[i] : longest;
+        const u32 cap = (u32)((st.max_dyn_smem / 8) & ~31u);
+        smem_cols = ((longest < cap ? longest : cap) + 31u) & ~31u;
+        if (smem_cols > cap) smem_cols = cap;
+    }
+    anchor_cols_kernel<<<(unsigned)n, latency_form ? AC_BLOCK : 256, (size_t)smem_cols * 8, s>>>(
+        st.windows.as<AcWindow>(), st.rows.as<u8>(), weights ? st.weights.as<float>() : nullptr, p, st.score.as<float>(), st.smooth.as<float>(),
+        st.gg.as<float>(), st.best.as<u32>(), st.nxt.as<u32>(), st.heads.as<u32>(), st.cols.as<u32>(), st.counts.as<u32>(),
+        st.seg_counters.as<unsigned long long>(), smem_cols, (score_out || smooth_out) ? 1 : 0);
     MCU_CUDA(cudaGetLastError());
     MCU_CUDA(cudaEventRecord(st.ev1, s));
     MCU_CUDA(cudaMemcpyAsync(n_cols_out, st.counts.p, n * 4, cudaMemcpyDeviceToHost, s));
+    MCU_CUDA(cudaMemcpyAsync(st.last_counters, st.seg_counters.p, sizeof st.last_counters, cudaMemcpyDeviceToHost, s));
     if (cols_total) {
-        MCU_CUDA(cudaMemcpyAsync(cols_out, st.cols.p, cols_total * 4, cudaMemcpyDeviceToHost, s));
         if (score_out) MCU_CUDA(cudaMemcpyAsync(score_out, st.score.p, cols_total * 4, cudaMemcpyDeviceToHost, s));
         if (smooth_out) MCU_CUDA(cudaMemcpyAsync(smooth_out, st.smooth.p, cols_total * 4, cudaMemcpyDeviceToHost, s));
     }
+    const bool packed = n > 1 && cols_total * 4 > (1u << 20);   // one window, or a small batch: the column slots travel as they are
+    if (cols_total && !packed) MCU_CUDA(cudaMemcpyAsync(cols_out, st.cols.p, cols_total * 4, cudaMemcpyDeviceToHost, s));
     MCU_CUDA(cudaStreamSynchronize(s));
     if (device_ms) MCU_CUDA(cudaEventElapsedTime(device_ms, st.ev0, st.ev1));
+    if (cols_total && packed) {
+        std::vector<u64> off(n + 1);
+        off[0] = 0;
+        for (u64 i = 0; i < n; ++i) off[i + 1] = off[i] + n_cols_out[i];
+        const u64 total = off[n];
+        if (total) {
+            MCU_TRY(st.dense_off.reserve((n + 1) * 8));
+            MCU_TRY(st.dense.reserve(total * 4));
+            std::vector<u32> dense(total);
+            MCU_CUDA(cudaMemcpyAsync(st.dense_off.p, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, s));
+            anchor_cols_pack_kernel<<<(unsigned)n, 128, 0, s>>>(st.windows.as<AcWindow>(), st.cols.as<u32>(), st.counts.as<u32>(), st.dense_off.as<u64>(),
+                                                                 st.dense.as<u32>());
+            MCU_CUDA(cudaGetLastError());
+            MCU_CUDA(cudaMemcpyAsync(dense.data(), st.dense.p, total * 4, cudaMemcpyDeviceToHost, s));
+            MCU_CUDA(cudaStreamSynchronize(s));
+            for (u64 i = 0; i < n; ++i)
+                if (n_cols_out[i]) memcpy(cols_out + col_off[i], dense.data() + off[i], (size_t)n_cols_out[i] * 4);
+        }
+    }
     return MCU_OK;
 }
 
@@ -411,6 +1019,8 @@ int ac_batch(u64 n, const char* rows, const u64* row_off, const u32* ncol, const
 
 // TEST-ONLY host driver of ac_window (tests/_emu.py builds this file with -DMCU_HOST_EMU into tests/_emu/libmcu_emu.so): the CTA is
 // one thread, the barriers are nothing.  Returns the number of anchor columns.
+static u64 g_emu_seg[2] = {0, 0};
+extern "C" void emu_anchor_counters(u64* out2) { out2[0] = g_emu_seg[0]; out2[1] = g_emu_seg[1]; }
 extern "C" long long emu_anchor_cols(const u8* rows, u32 n1, u32 n2, u32 ncol, const float* weights, const mcu_anchor_params* p, u32* cols_out,
                                      float* score_out, float* smooth_out)
 {
@@ -421,7 +1031,11 @@ extern "C" long long emu_anchor_cols(const u8* rows, u32 n1, u32 n2, u32 ncol, c
     float* gg = new float[ncol];
     u32 *best = new u32[ncol], *nxt = new u32[ncol], *heads = new u32[ncol];
     u32 count = 0;
-    ac_window(*sm, w, rows, weights, *p, score_out, smooth_out, gg, best, nxt, heads, cols_out, &count);
+    u32* before = new u32[ncol];
+    ac_window(*sm, w, rows, weights, *p, score_out, smooth_out, gg, before, best, nxt, heads, cols_out, &count);
+    delete[] before;
+    g_emu_seg[0] += sm->seg_fast;
+    g_emu_seg[1] += sm->seg_chain;
     delete sm; delete[] gg; delete[] best; delete[] nxt; delete[] heads;
     return (long long)count;
 }

@@ -577,6 +577,13 @@ int mcu_anchor_cols_batch(uint64_t n, const char* rows, const uint64_t* row_off,
     return ac_batch(n, rows, (const u64*)row_off, ncol, n1, n2, weights, params, (const u64*)col_off, cols_out, n_cols_out, score_out, smooth_out, device_ms);
 }
 
+int mcu_test_anchor_counters(uint64_t* out8)
+{
+    if (!out8) return MCU_EINVAL;
+    ac_last_counters((u64*)out8);
+    return MCU_OK;
+}
+
 int mcu_test_hmm_counters(uint64_t* out3)
 {
     if (!out3) return MCU_EINVAL;

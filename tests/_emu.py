@@ -47,6 +47,8 @@ def emu():
     L.emu_hmm_fprod.restype = None
     L.emu_anchor_cols.argtypes = [vp, C.c_uint, C.c_uint, C.c_uint, vp, vp, vp, vp, vp]
     L.emu_anchor_cols.restype = C.c_longlong
+    L.emu_anchor_counters.argtypes = [vp]
+    L.emu_anchor_counters.restype = None
     _lib = L
     return L
 

@@ -176,6 +176,7 @@ int mcu_sml_build_sharded(const char* seq, uint64_t n, uint64_t seed, uint32_t* 
     return mcu_sml_build(seq, n, seed, pos_out, NULL, NULL, len_out);
 }
 int mcu_test_hmm_counters(uint64_t* out3) { if (out3) out3[0] = out3[1] = out3[2] = 0; return 0; }
+int mcu_test_anchor_counters(uint64_t* out8) { int i; if (out8) for (i = 0; i < 8; ++i) out8[i] = 0; return 0; }
 
 /* ---- round 2 entry points: caller-buffer form, chunked upload, the library's own communicator ------------------------------------ */
 #include <stdio.h>

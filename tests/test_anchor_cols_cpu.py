@@ -52,24 +52,48 @@ def test_oracle_equals_golden():
     assert n > 300
 
 
-def _emu_cols(rows, n1, w):
+def _emu_cols(rows, n1, w, p=None):
     rows = np.ascontiguousarray(rows, dtype=np.uint8)
     nr, ncol = rows.shape
     cols = np.zeros(ncol + 1, dtype=np.uint32)
     score = np.zeros(ncol + 1, dtype=np.float32)
     smooth = np.zeros(ncol + 1, dtype=np.float32)
     w = np.ascontiguousarray(w, dtype=np.float32)
-    p = _oracle.anchor_default_params()
+    p = p if p is not None else _oracle.anchor_default_params()
     n = _emu.emu().emu_anchor_cols(rows.ctypes.data, n1, nr - n1, ncol, w.ctypes.data, C.addressof(p), cols.ctypes.data, score.ctypes.data, smooth.ctypes.data)
     assert n >= 0
     return cols[:n], score[:ncol], smooth[:ncol]
 
 
+def _seg_counters():
+    c = np.zeros(2, dtype=np.uint64)
+    _emu.emu().emu_anchor_counters(c.ctypes.data)
+    return int(c[0]), int(c[1])
+
+
 def test_kernel_value_path_equals_golden():
+    f0, s0 = _seg_counters()
     for k, rows, n1, w, cols, score, smooth in _windows():
         c2, s2, m2 = _emu_cols(rows, n1, w)
         assert np.array_equal(c2, cols), k
         assert _same_floats(s2, score) and _same_floats(m2, smooth), k
+    # both forms of the smoothing chain were at work: segments finished in exact arithmetic, and segments run as the float chain
+    f1, s1 = _seg_counters()
+    assert f1 - f0 > 100 and s1 - s0 > 300, (f1 - f0, s1 - s0)
+
+
+def test_smoothing_segments_that_must_take_the_chain():
+    """totals that lose low bits on the way (a window sum crossing a power of two with a residue on board) and operands outside the
+    fixed-point range: the exact path has to refuse them, and the answer stays the oracle's"""
+    rng = np.random.default_rng(17)
+    p = _oracle.anchor_default_params()
+    for it in range(30):
+        ncol = 3000
+        rows = synth.alignment_window(ncol, seed=7000 + it, n_rows=4, snp=0.05, gap_rate=0.004, gap_mean=3)
+        w = (rng.random(4) * (10.0 ** rng.integers(-3, 4))).astype(np.float32)       # weights make every score a 24-bit float
+        c1, s1, m1, _, _ = _oracle.anchor_cols(rows, 2, weights=w)
+        c2, s2, m2 = _emu_cols(rows, 2, w)
+        assert np.array_equal(c1, c2) and _same_floats(s1, s2) and _same_floats(m1, m2), it
 
 
 def test_kernel_value_path_equals_oracle_on_random_windows():
@@ -103,3 +127,15 @@ def test_oracle_equals_reference_on_random_windows():
         assert _same_floats(score, s2) and _same_floats(smooth, m2), it
         total += cols.size
     assert total > 200
+
+
+def test_kernel_value_path_with_other_settings():
+    """an extension penalty (every gap run is then a float sum in column order: the owner thread's loop, whatever the run's length),
+    a smoothing ceiling that bites, other thresholds, window and spacing"""
+    p = _oracle.anchor_default_params()
+    p.smooth_ceil, p.min_best_col, p.min_smooth, p.smooth_window, p.anchor_spacing, p.gap_extend = 120.0, 100.0, 60.0, 7, 32, -5.0
+    for it in range(12):
+        rows = synth.alignment_window(2500, seed=8000 + it, gap_rate=0.01, gap_mean=int([3, 40, 200][it % 3]))
+        c1, s1, m1, _, _ = _oracle.anchor_cols(rows, 1, params=p)
+        c2, s2, m2 = _emu_cols(rows, 1, np.ones(2, dtype=np.float32), p)
+        assert np.array_equal(c1, c2) and _same_floats(s1, s2) and _same_floats(m1, m2), it

@@ -308,6 +308,16 @@ def test_anchor_cols_vs_oracle(mp):
         assert np.array_equal(_bits(got[k][1]), _bits(s)) and np.array_equal(_bits(got[k][2]), _bits(m)), k
         n_cols += c.size
     assert n_cols > 5000
+    # a batch beyond two windows per SM takes the other launch form (CTAs of 256 threads, per-column arrays in global memory)
+    many = [(synth.alignment_window(int(rng.integers(30, 3000)), seed=9000 + it, gap_rate=float(rng.choice([0.002, 0.02])),
+                                    gap_mean=int(rng.choice([4, 80]))), 1, None) for it in range(450)]
+    got = mp.libmems.FindAnchorColsPP_batch(many, return_scores=True)
+    for k, (rows, n1, w) in enumerate(many):
+        c, s, m, _, _ = _oracle.anchor_cols(rows, n1)
+        assert np.array_equal(got[k][0], c) and np.array_equal(_bits(got[k][1]), _bits(s)) and np.array_equal(_bits(got[k][2]), _bits(m)), k
+    counters = np.zeros(8, dtype=np.uint64)
+    mp.lib().mcu_test_anchor_counters(counters.ctypes.data)
+    assert int(counters[0]) > 0 and int(counters[1]) > 0      # segments of the smoothing chain finished in exact arithmetic / as the float chain
     p = mp.libmems.AnchorParams.default()
     p.smooth_ceil, p.min_best_col, p.min_smooth, p.smooth_window, p.anchor_spacing, p.gap_extend = 120.0, 100.0, 60.0, 7, 32, -5.0
     po = _oracle.anchor_default_params()

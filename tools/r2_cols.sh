@@ -23,3 +23,22 @@ for nw in (1, 148, 1184, 4736):
 PY
 tail -6 $OUT/time_cols.log
 timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; tail -2 $OUT/smoke.log
+cat > $OUT/_one.py <<'PY'
+import sys
+sys.path.insert(0, ".")
+import numpy as np
+import mauve_py_b200 as mp
+from mauve_py_b200 import synth
+from mauve_py_b200._capi import check
+check(mp.lib().mcu_init(0))
+clean = len(sys.argv) > 1 and sys.argv[1] == "clean"
+w = synth.alignment_window(20000, seed=900, **(dict(snp=0.02, gap_rate=0.0005, diverged_blocks=False) if clean else {}))
+for _ in range(3):
+    c = mp.FindAnchorColsPP(w[:1], w[1:])
+k = np.zeros(8, dtype=np.uint64)
+mp.lib().mcu_test_anchor_counters(k.ctypes.data)
+print(c.size, k.tolist())
+PY
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'anchor_cols_kernel' -s 2 -c 1 -o $OUT/one_window -f python $OUT/_one.py > $OUT/ncu_one.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'anchor_cols_kernel' -s 2 -c 1 -o $OUT/one_window_clean -f python $OUT/_one.py clean > $OUT/ncu_one_clean.log 2>&1
+tail -2 $OUT/ncu_one.log
