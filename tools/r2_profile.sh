@@ -42,5 +42,24 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'rs_
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'nw_forward_kernel' -c 2 -o $O/dp -f python tools/config5_dp.py --regions 1500 --chunk 1500 > $O/dp_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'hmm_exact_chain_warp_kernel' -c 1 -o $O/hmm_warp -f python tools/hmm_time.py --one 500000 > /dev/null 2> $O/hmm_ncu.err
 timeout 300 python tools/hmm_time.py > $O/hmm_time.log 2>&1
+# the anchor-column kernel (8f-4): ONE 20,000-column window per call -- the aligner's case -- captured, and its phase clocks on three kinds of window
+cat > $O/_cols_probe.py <<'PY'
+import sys
+sys.path.insert(0, ".")
+import numpy as np
+import mauve_py_b200 as mp
+from mauve_py_b200 import synth
+from mauve_py_b200._capi import check
+check(mp.lib().mcu_init(0))
+for name, kw in (("bench", {}), ("clean", dict(snp=0.02, gap_rate=0.0005, diverged_blocks=False)), ("gappy", dict(gap_rate=0.05))):
+    w = synth.alignment_window(20000, seed=900, **kw)
+    for _ in range(3):
+        c = mp.FindAnchorColsPP(w[:1], w[1:])
+    k = np.zeros(8, dtype=np.uint64)
+    mp.lib().mcu_test_anchor_counters(k.ctypes.data)
+    print(name, "anchor columns", c.size, "segments exact/chain", k[:2].tolist(), "SM cycles scoring/smoothing/best/ends/walk/picks", k[2:].tolist())
+PY
+timeout 300 python $O/_cols_probe.py > $O/cols_phases.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'anchor_cols_kernel' -s 2 -c 1 -o $O/anchor_cols -f python $O/_cols_probe.py > $O/cols_ncu.log 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $O/nvidia_smi.csv 2>&1
 echo done

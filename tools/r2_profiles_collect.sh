@@ -9,6 +9,11 @@ python tools/ncu_summary.py $T/partition.ncu-rep $T/finish.ncu-rep > $P/r02_ncu_
 python tools/ncu_summary.py $T/sml.ncu-rep > $P/r02_ncu_sml_build_summary.txt 2>&1
 python tools/ncu_summary.py $T/dp.ncu-rep > $P/r02_ncu_nw_forward_summary.txt 2>&1
 python tools/ncu_summary.py $T/hmm_warp.ncu-rep > $P/r02_ncu_hmm_warp_chain_summary.txt 2>&1
+if [ -f $T/anchor_cols.ncu-rep ]; then
+  python tools/ncu_summary.py $T/anchor_cols.ncu-rep > $P/r02_ncu_anchor_cols_summary.txt 2>&1
+  echo "# phase clocks of ONE 20,000-column window per call (mcu_test_anchor_counters), three kinds of window:" >> $P/r02_ncu_anchor_cols_summary.txt
+  grep -v "^==" $T/cols_phases.log >> $P/r02_ncu_anchor_cols_summary.txt
+fi
 grep -v "^==" $T/launches.csv > $P/r02_launches_bench_100mbp.csv
 python - "$T" <<'PY'
 import csv, json, sys, collections
