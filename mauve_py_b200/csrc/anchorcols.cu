@@ -65,19 +65,24 @@ struct AcWindow {
     u32 ncol, n1, n2, pad;
 };
 
+// one tile of the smoothing chain: its operands, results and what the exactness tests need (two of them: one is summed while the
+// next is being filled)
+struct AcTile {
+    float sub[AC_TILE], add[AC_TILE], out[AC_TILE];
+    float pre[AC_TILE];            // per segment: inclusive prefix sums of add - sub
+    u32 seg_ok[AC_TILE / 32];      // ... every one of them formed without rounding
+    float seg_tot[AC_TILE / 32];   // what the segment adds to the running total
+};
+
 struct AcShared {
     u8 letter[256];
-    float sub[AC_TILE], add[AC_TILE], out[AC_TILE];   // (also, as one array: a chunk of `nxt` for the walk over the groups)
-    float pre[AC_TILE];                    // per segment: inclusive prefix sums of add - sub
-    u32 seg_ok[AC_TILE / 32];              // ... every one of them formed without rounding
+    AcTile tile[2];                        // (tile[0].sub .. .add also serve as a chunk of `nxt` for the walk over the groups)
     u32 seg_pass[AC_TILE / 32];            // 1: with the total it was tested against, no addition of the segment's chain rounds; 0: one
                                            // does; 2: not tested, the sums in front of it were not exact
-    float seg_tot[AC_TILE / 32];           // what the segment adds to the running total
     float seg_end[AC_TILE / 32];           // the chain's value behind a segment that passed
     u32 walk_n;
     u32 scan_w[3][AC_BLOCK / 32 + 1];      // ac_scan_min3: the warps' minima
     unsigned long long clk[AC_PHASES + 1];
-    u32 spec_hold;                         // tiles left to run as the plain chain after a tile full of rounding columns
     u32 seg_fast, seg_chain;               // segments finished without / with the serial chain (reported by mcu_test_anchor_counters)
     float total;
     int first, last;
@@ -164,49 +169,43 @@ __device__ __forceinline__ u32 ac_block_rank(AcShared& sm, bool flag, u32& total
 
 // the serial chain over columns [k0, k1) of the tile, starting from t: WindowSmooth's loop body (MU/anchors.cpp:38-46), two dependent
 // additions per column.  The operands of the next eight columns are in registers before the current eight are added.
-AC_HD float ac_chain(AcShared& sm, float t, u32 k0, u32 k1)
+AC_HD float ac_chain(AcTile& tl, float t, u32 k0, u32 k1)
 {
     u32 k = k0;
 #ifndef MCU_HOST_EMU
+    // two register sets take turns (no copies between them: a register move costs the chain's pipe as much as an addition)
+#define AC_LOAD8(a_, b_, at_)                \
+    _Pragma("unroll") for (int j = 0; j < 8; ++j) \
+    {                                        \
+        a_[j] = tl.sub[(at_) + j];           \
+        b_[j] = tl.add[(at_) + j];           \
+    }
+#define AC_SUM8(a_, b_, at_)                 \
+    _Pragma("unroll") for (int j = 0; j < 8; ++j) \
+    {                                        \
+        tl.out[(at_) + j] = t;               \
+        t = AC_FSUB(t, a_[j]);               \
+        t = AC_FADD(t, b_[j]);               \
+    }
     if (k + 8 <= k1) {
-        float a[8], b[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            a[j] = sm.sub[k + j];
-            b[j] = sm.add[k + j];
+        float a0[8], b0[8], a1[8], b1[8];
+        AC_LOAD8(a0, b0, k)
+        for (; k + 24 <= k1; k += 16) {
+            AC_LOAD8(a1, b1, k + 8)
+            AC_SUM8(a0, b0, k)
+            AC_LOAD8(a0, b0, k + 16)
+            AC_SUM8(a1, b1, k + 8)
         }
-        for (; k + 16 <= k1; k += 8) {
-            float na[8], nb[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                na[j] = sm.sub[k + 8 + j];
-                nb[j] = sm.add[k + 8 + j];
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                sm.out[k + j] = t;
-                t = AC_FSUB(t, a[j]);
-                t = AC_FADD(t, b[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                a[j] = na[j];
-                b[j] = nb[j];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            sm.out[k + j] = t;
-            t = AC_FSUB(t, a[j]);
-            t = AC_FADD(t, b[j]);
-        }
+        AC_SUM8(a0, b0, k)
         k += 8;
     }
+#undef AC_LOAD8
+#undef AC_SUM8
 #endif
     for (; k < k1; ++k) {
-        sm.out[k] = t;
-        t = AC_FSUB(t, sm.sub[k]);
-        t = AC_FADD(t, sm.add[k]);   // (after the window's last column: a value nobody reads)
+        tl.out[k] = t;
+        t = AC_FSUB(t, tl.sub[k]);
+        t = AC_FADD(t, tl.add[k]);   // (after the window's last column: a value nobody reads)
     }
     return t;
 }
@@ -215,53 +214,42 @@ AC_HD float ac_chain(AcShared& sm, float t, u32 k0, u32 k1)
 // no addition of the chain -- t - sub, then + add, column after column -- rounds.  With exact prefix sums s_k (seg_ok) the chain's value in
 // front of column k is t0 + s_(k-1) provided that sum, the subtraction and the addition that follow are all exact: by induction over k.
 // Device: the calling warp, one column per lane.
-AC_HD bool ac_verify_segment(AcShared& sm, u32 seg, u32 n, float t0)
+AC_HD bool ac_verify_segment(AcShared& sm, AcTile& tl, u32 seg, u32 n, float t0)
 {
     const u32 base = seg * 32, cnt = n - base < 32 ? n - base : 32;
 #ifdef MCU_HOST_EMU
-    bool ok = sm.seg_ok[seg] != 0;
+    bool ok = tl.seg_ok[seg] != 0;
     float end = t0;
     for (u32 lane = 0; lane < cnt && ok; ++lane) {
         float P, Q, R;
-        ok = ac_add_exact(t0, lane ? sm.pre[base + lane - 1] : 0.0f, P) && ac_add_exact(P, -sm.sub[base + lane], Q) && ac_add_exact(Q, sm.add[base + lane], R);
+        ok = ac_add_exact(t0, lane ? tl.pre[base + lane - 1] : 0.0f, P) && ac_add_exact(P, -tl.sub[base + lane], Q) && ac_add_exact(Q, tl.add[base + lane], R);
         end = R;
     }
     if (ok) {
-        for (u32 lane = 0; lane < cnt; ++lane) sm.out[base + lane] = AC_FADD(t0, lane ? sm.pre[base + lane - 1] : 0.0f);
+        for (u32 lane = 0; lane < cnt; ++lane) tl.out[base + lane] = AC_FADD(t0, lane ? tl.pre[base + lane - 1] : 0.0f);
         sm.seg_end[seg] = end;
     }
     return ok;
 #else
     const u32 lane = threadIdx.x & 31;
-    const float mine_pre = sm.pre[base + lane];
+    const float mine_pre = tl.pre[base + lane];
     float before = __shfl_up_sync(0xffffffffu, mine_pre, 1);
     if (lane == 0) before = 0.0f;
     float P, Q, R;
-    const bool mine = ac_add_exact(t0, before, P) & ac_add_exact(P, -sm.sub[base + lane], Q) & ac_add_exact(Q, sm.add[base + lane], R);
-    const bool ok = __all_sync(0xffffffffu, mine || lane >= cnt) && sm.seg_ok[seg] != 0;
+    const bool mine = ac_add_exact(t0, before, P) & ac_add_exact(P, -tl.sub[base + lane], Q) & ac_add_exact(Q, tl.add[base + lane], R);
+    const bool ok = __all_sync(0xffffffffu, mine || lane >= cnt) && tl.seg_ok[seg] != 0;
     if (ok) {
-        if (lane < cnt) sm.out[base + lane] = P;
+        if (lane < cnt) tl.out[base + lane] = P;
         if (lane == cnt - 1) sm.seg_end[seg] = R;
     }
     return ok;
 #endif
 }
 
-// The running sum over one tile (n columns, operands in sm.sub / sm.add, results to sm.out, sm.total carried).
-AC_HD void ac_smooth_tile(AcShared& sm, u32 n, u32 nseg)
+// the segments' prefix sums of add - sub and their totals, every addition tested.  Device: warps wid, wid + nw, ... of the callers take
+// the segments (all warps of the CTA, or the helper warps while warp 0 is summing the tile before)
+AC_HD void ac_tile_prepare(AcTile& tl, u32 n, u32 nseg, u32 wid, u32 nw)
 {
-    const u32 tid = AC_TID, nt = AC_NT;
-    if (sm.spec_hold) {   // the tile before was full of rounding columns: do not look for exact segments here
-        AC_SYNC();
-        if (tid == 0) {
-            sm.total = ac_chain(sm, sm.total, 0, n);
-            sm.seg_chain += nseg;
-            --sm.spec_hold;
-        }
-        AC_SYNC();
-        return;
-    }
-    // the segments' prefix sums of add - sub and their totals, every addition tested
 #ifdef MCU_HOST_EMU
     for (u32 seg = 0; seg < nseg; ++seg) {
         bool ok = true;
@@ -269,19 +257,19 @@ AC_HD void ac_smooth_tile(AcShared& sm, u32 n, u32 nseg)
         for (u32 lane = 0; lane < 32; ++lane) {
             const u32 k = seg * 32 + lane;
             float d = 0.0f;
-            if (k < n) ok = ac_add_exact(sm.add[k], -sm.sub[k], d) && ok;
+            if (k < n) ok = ac_add_exact(tl.add[k], -tl.sub[k], d) && ok;
             ok = ac_add_exact(run, d, run) && ok;
-            if (k < AC_TILE) sm.pre[k] = run;
+            if (k < AC_TILE) tl.pre[k] = run;
         }
-        sm.seg_ok[seg] = ok;
-        sm.seg_tot[seg] = run;
+        tl.seg_ok[seg] = ok;
+        tl.seg_tot[seg] = run;
     }
 #else
-    for (u32 seg = tid >> 5; seg < nseg; seg += nt >> 5) {
-        const u32 lane = tid & 31, k = seg * 32 + lane;
+    for (u32 seg = wid; seg < nseg; seg += nw) {
+        const u32 lane = threadIdx.x & 31, k = seg * 32 + lane;
         float run = 0.0f;
         bool ok = true;
-        if (k < n) ok = ac_add_exact(sm.add[k], -sm.sub[k], run);
+        if (k < n) ok = ac_add_exact(tl.add[k], -tl.sub[k], run);
         for (u32 o = 1; o < 32; o <<= 1) {
             const float up = __shfl_up_sync(0xffffffffu, run, o);
             float sum;
@@ -291,41 +279,45 @@ AC_HD void ac_smooth_tile(AcShared& sm, u32 n, u32 nseg)
                 ok = ok && e;
             }
         }
-        sm.pre[k] = run;
+        tl.pre[k] = run;
         const bool all = __all_sync(0xffffffffu, ok);
-        if (lane == 31) sm.seg_tot[seg] = run;
-        if (lane == 0) sm.seg_ok[seg] = all;
+        if (lane == 31) tl.seg_tot[seg] = run;
+        if (lane == 0) tl.seg_ok[seg] = all;
     }
 #endif
-    AC_SYNC();
-    {   // segments whose own sums round (a gap penalty like -400/3 among their operands): more than a few, and the tile is the chain
-        u32 nbad = 0;
+}
+
+// segments whose own sums round (a gap penalty like -400/3 among their operands).  Every warp for itself.
+AC_HD u32 ac_tile_bad_segments(const AcTile& tl, u32 nseg)
+{
 #ifdef MCU_HOST_EMU
-        for (u32 seg = 0; seg < nseg; ++seg) nbad += sm.seg_ok[seg] ? 0u : 1u;
+    u32 nbad = 0;
+    for (u32 seg = 0; seg < nseg; ++seg) nbad += tl.seg_ok[seg] ? 0u : 1u;
+    return nbad;
 #else
-        nbad = __popc(__ballot_sync(0xffffffffu, (tid & 31) < nseg && !sm.seg_ok[tid & 31]));
+    const u32 lane = threadIdx.x & 31;
+    return __popc(__ballot_sync(0xffffffffu, lane < nseg && !tl.seg_ok[lane]));
 #endif
-        if (nbad > 3) {
-            if (tid == 0) {
-                sm.total = ac_chain(sm, sm.total, 0, n);
-                sm.seg_chain += nseg;
-                if (nbad > nseg / 2) sm.spec_hold = 2;
-            }
-            AC_SYNC();
-            return;
-        }
-    }
+}
+
+// The running sum over one prepared tile by the whole CTA (sm.total carried): all segments are tested at once against the totals they would
+// start from if nothing before them rounded; the first one that fails is run as the serial chain, which gives the true total behind it, and
+// the segments after it are tested again.  True when the tile turned out to be full of rounding columns after all (the caller then
+// takes the next tiles as the plain chain).  Every thread calls it; ends with a barrier.
+AC_HD bool ac_tile_resolve(AcShared& sm, AcTile& tl, u32 n, u32 nseg)
+{
+    const u32 tid = AC_TID, nt = AC_NT;
     u32 seg0 = 0;
     for (u32 round = 0; seg0 < nseg; ++round) {
         const float t = sm.total;   // the chain's value in front of segment seg0
         if (round >= 6) {
             AC_SYNC();   // (everybody has read sm.total)
             if (tid == 0) {
-                sm.total = ac_chain(sm, t, seg0 * 32, n);
+                sm.total = ac_chain(tl, t, seg0 * 32, n);
                 sm.seg_chain += nseg - seg0;
             }
             AC_SYNC();
-            return;
+            return false;
         }
         // every segment from seg0 on against the total it would start from if none before it rounded
 #ifdef MCU_HOST_EMU
@@ -333,14 +325,14 @@ AC_HD void ac_smooth_tile(AcShared& sm, u32 n, u32 nseg)
             float ts = t;
             bool ts_ok = true;
             for (u32 seg = seg0; seg < nseg; ++seg) {
-                sm.seg_pass[seg] = !ts_ok ? 2u : ac_verify_segment(sm, seg, n, ts) ? 1u : 0u;
-                ts_ok = ac_add_exact(ts, sm.seg_tot[seg], ts) && ts_ok;
+                sm.seg_pass[seg] = !ts_ok ? 2u : ac_verify_segment(sm, tl, seg, n, ts) ? 1u : 0u;
+                ts_ok = ac_add_exact(ts, tl.seg_tot[seg], ts) && ts_ok;
             }
         }
 #else
         for (u32 seg = seg0 + (tid >> 5); seg < nseg; seg += nt >> 5) {
             const u32 lane = tid & 31;
-            float part = seg0 + lane < seg ? sm.seg_tot[seg0 + lane] : 0.0f;   // nseg <= 32: one lane per earlier segment
+            float part = seg0 + lane < seg ? tl.seg_tot[seg0 + lane] : 0.0f;   // nseg <= 32: one lane per earlier segment
             bool exact = true;
             for (u32 o = 16; o; o >>= 1) {
                 float sum;
@@ -349,7 +341,7 @@ AC_HD void ac_smooth_tile(AcShared& sm, u32 n, u32 nseg)
             }
             float ts;
             exact = ac_add_exact(t, part, ts) && exact;
-            const u32 verdict = !__all_sync(0xffffffffu, exact) ? 2u : ac_verify_segment(sm, seg, n, ts) ? 1u : 0u;
+            const u32 verdict = !__all_sync(0xffffffffu, exact) ? 2u : ac_verify_segment(sm, tl, seg, n, ts) ? 1u : 0u;
             if (lane == 0) sm.seg_pass[seg] = verdict;
         }
 #endif
@@ -369,28 +361,29 @@ AC_HD void ac_smooth_tile(AcShared& sm, u32 n, u32 nseg)
             if (open) f = seg0 + (__ffs(open) - 1);
         }
 #endif
+        const bool give_up = f < nseg && round == 0 && nfail > 3;
         if (tid == 0) {   // (everybody read sm.total before the barrier above; the flags are written again only after the one below)
             const float tf = f == seg0 ? t : sm.seg_end[f - 1];   // the chain's true value in front of segment f
             sm.seg_fast += f - seg0;
             if (f == nseg)
                 sm.total = tf;
-            else if (round == 0 && nfail > 3) {   // many: the chain from the first one to the end of the tile
-                sm.total = ac_chain(sm, tf, f * 32, n);
+            else if (give_up) {   // many: the chain from the first one to the end of the tile
+                sm.total = ac_chain(tl, tf, f * 32, n);
                 sm.seg_chain += nseg - f;
-                if (nfail > nseg / 2) sm.spec_hold = 2;
             } else {
                 const u32 k1 = (f + 1) * 32 < n ? (f + 1) * 32 : n;
-                sm.total = ac_chain(sm, tf, f * 32, k1);
+                sm.total = ac_chain(tl, tf, f * 32, k1);
                 sm.seg_chain += 1;
             }
         }
         AC_SYNC();
-        if (f == nseg || (round == 0 && nfail > 3)) return;
+        if (give_up) return nfail > nseg / 2;
+        if (f == nseg) return false;
         seg0 = f + 1;
     }
+    return false;
 }
 
-// One window, start to end.  score / smooth / gg / best / nxt / heads: ncol entries each at the window's col_off.
 // inclusive prefix minimum over the CTA's threads (thread order) of three values at once, continued from the minima of the chunks
 // before (carry, kept by every thread).  Every thread calls it.
 AC_HD void ac_scan_min3(AcShared& sm, u32& a, u32& b, u32& c, u32 carry[3])
@@ -647,7 +640,6 @@ AC_HD void ac_window(AcShared& sm, const AcWindow w, const u8* __restrict__ rows
         sm.nanchor = 0;
         sm.seg_fast = 0;
         sm.seg_chain = 0;
-        sm.spec_hold = 0;
         sm.clk[0] = AC_CLOCK();
     }
     AC_SYNC();
@@ -682,50 +674,80 @@ AC_HD void ac_window(AcShared& sm, const AcWindow w, const u8* __restrict__ rows
         }
         const u32 i_last = L - w2 - 1;
         const float fw = (float)W;
-        // a tile's operands travel global -> registers while the tile before is being summed, registers -> shared memory afterwards
-        constexpr int PF = 4;   // columns per thread and tile (device: 256 threads or more)
-        float pa[PF], pb[PF];
-#define AC_PREFETCH(i0_, n_)                                                                               \
-    for (int q = 0; q < PF; ++q) {                                                                         \
-        const u32 k = tid + (u32)q * nt;                                                                   \
-        if (k < (n_)) {                                                                                    \
-            const u32 i = (i0_) + k;                                                                       \
-            pa[q] = score[i - w2];                                                                         \
-            pb[q] = i + w2 + 1 < L ? score[i + w2 + 1] : 0.0f; /* unused at i_last */                      \
-        }                                                                                                  \
-    }
-        u32 n = (i_last - w2 + 1) < AC_TILE ? (i_last - w2 + 1) : AC_TILE;
-#ifndef MCU_HOST_EMU
-        AC_PREFETCH(w2, n)
-#endif
-        for (u32 i0 = w2; i0 <= i_last; i0 += AC_TILE) {
-            n = (i_last - i0 + 1) < AC_TILE ? (i_last - i0 + 1) : AC_TILE;
+        const u32 ntiles = (i_last - w2 + 1 + AC_TILE - 1) / AC_TILE;
+        // Tiles of AC_TILE columns, two buffers.  While one lane sums tile k (the serial chain), the other warps divide and store tile
+        // k - 1 and fill and prepare tile k + 1: one barrier per tile, the chain is all that is left on the critical path.  A tile that
+        // may hold exact segments is resolved by the whole CTA instead (ac_tile_resolve).
 #ifdef MCU_HOST_EMU
-            for (u32 k = 0; k < n; ++k) {
-                const u32 i = i0 + k;
-                sm.sub[k] = ac_ceil(score[i - w2], p.smooth_ceil);
-                sm.add[k] = i + w2 + 1 < L ? ac_ceil(score[i + w2 + 1], p.smooth_ceil) : 0.0f;
-            }
+        const u32 hid = 0, nh = 1, hwid = 0, hnw = 1;
+        const bool chain_role = true, helper_role = true;
 #else
-            for (int q = 0; q < PF; ++q) {
-                const u32 k = tid + (u32)q * nt;
-                if (k < n) {
-                    sm.sub[k] = ac_ceil(pa[q], p.smooth_ceil);
-                    sm.add[k] = ac_ceil(pb[q], p.smooth_ceil);
-                }
-            }
-            if (i0 + AC_TILE <= i_last) {
-                const u32 n_next = (i_last - (i0 + AC_TILE) + 1) < AC_TILE ? (i_last - (i0 + AC_TILE) + 1) : AC_TILE;
-                AC_PREFETCH(i0 + AC_TILE, n_next)
-            }
+        const u32 hid = tid - 32, nh = nt - 32, hwid = (tid >> 5) - 1, hnw = (nt >> 5) - 1;   // helpers: every warp but the first
+        const bool chain_role = tid < 32, helper_role = tid >= 32;
 #endif
-            AC_SYNC();
-            const u32 nseg = (n + 31) / 32;
-            ac_smooth_tile(sm, n, nseg);
-            for (u32 k = tid; k < n; k += nt) smooth[i0 + k] = AC_FDIV(sm.out[k], fw);
-            AC_SYNC();
+#define AC_TILE_N(k_) ((i_last - (w2 + (k_) * AC_TILE) + 1) < AC_TILE ? (i_last - (w2 + (k_) * AC_TILE) + 1) : AC_TILE)
+#define AC_TILE_FILL(nx, k_, first_, step_)                                                        \
+    {                                                                                              \
+        const u32 i0_ = w2 + (k_) * AC_TILE, n_ = AC_TILE_N(k_);                                   \
+        for (u32 q = (first_); q < n_; q += (step_)) {                                             \
+            const u32 i = i0_ + q;                                                                 \
+            (nx).sub[q] = ac_ceil(score[i - w2], p.smooth_ceil);                                   \
+            (nx).add[q] = i + w2 + 1 < L ? ac_ceil(score[i + w2 + 1], p.smooth_ceil) : 0.0f; /* unused at i_last */ \
+        }                                                                                          \
+    }
+#define AC_TILE_STORE(pv, k_, first_, step_)                                                       \
+    {                                                                                              \
+        const u32 i0_ = w2 + (k_) * AC_TILE, n_ = AC_TILE_N(k_);                                   \
+        for (u32 q = (first_); q < n_; q += (step_)) smooth[i0_ + q] = AC_FDIV((pv).out[q], fw);   \
+    }
+        AC_TILE_FILL(sm.tile[0], 0u, tid, nt)
+        AC_SYNC();
+        ac_tile_prepare(sm.tile[0], AC_TILE_N(0u), (AC_TILE_N(0u) + 31) / 32, tid >> 5, nt >> 5 ? nt >> 5 : 1);
+        AC_SYNC();
+        u32 hold = 0;   // tiles left to take as the plain chain after a tile full of rounding columns (same value in every thread)
+        // tile k in `tl`; tiles k - 1 and k + 1 in `ot` (called with the two buffers by name, so that the chain's addresses are constants)
+        auto one_tile = [&](const u32 k, AcTile& tl, AcTile& ot) {
+            const u32 n = AC_TILE_N(k), nseg = (n + 31) / 32;
+            const u32 nbad = hold ? nseg : ac_tile_bad_segments(tl, nseg);
+            if (hold || nbad > 3) {
+                if (hold) --hold;
+                else if (nbad > nseg / 2) hold = 2;
+                if (chain_role && (tid & 31) == 0) {
+                    sm.total = ac_chain(tl, sm.total, 0, n);
+                    sm.seg_chain += nseg;
+                }
+                if (helper_role) {
+                    if (k > 0) AC_TILE_STORE(ot, k - 1, hid, nh)
+                    if (k + 1 < ntiles) {
+                        AC_TILE_FILL(ot, k + 1, hid, nh)
+                        if (!hold) {   // (a tile that will be taken as the chain anyway needs no preparation)
+#ifndef MCU_HOST_EMU
+                            asm volatile("bar.sync 1, %0;" ::"r"(nh) : "memory");   // the helpers among themselves: the tile is filled
+#endif
+                            ac_tile_prepare(ot, AC_TILE_N(k + 1), (AC_TILE_N(k + 1) + 31) / 32, hwid, hnw);
+                        }
+                    }
+                }
+                AC_SYNC();
+            } else {
+                if (k > 0) AC_TILE_STORE(ot, k - 1, tid, nt)
+                if (k + 1 < ntiles) {
+                    AC_TILE_FILL(ot, k + 1, tid, nt)
+                    AC_SYNC();
+                    ac_tile_prepare(ot, AC_TILE_N(k + 1), (AC_TILE_N(k + 1) + 31) / 32, tid >> 5, nt >> 5 ? nt >> 5 : 1);
+                }
+                if (ac_tile_resolve(sm, tl, n, nseg)) hold = 2;
+            }
+        };
+        for (u32 k = 0; k < ntiles; k += 2) {
+            one_tile(k, sm.tile[0], sm.tile[1]);
+            if (k + 1 < ntiles) one_tile(k + 1, sm.tile[1], sm.tile[0]);
         }
-#undef AC_PREFETCH
+        if ((ntiles - 1) & 1) AC_TILE_STORE(sm.tile[1], ntiles - 1, tid, nt)
+        else AC_TILE_STORE(sm.tile[0], ntiles - 1, tid, nt)
+#undef AC_TILE_N
+#undef AC_TILE_FILL
+#undef AC_TILE_STORE
     }
     AC_SYNC();
 
@@ -761,8 +783,8 @@ AC_HD void ac_window(AcShared& sm, const AcWindow w, const u8* __restrict__ rows
     AC_SYNC();
     if (tid == 0) sm.clk[4] = AC_CLOCK();
     {   // the walk head -> next head, one lane, through chunks of `nxt` in shared memory
-        u32* s_nxt = (u32*)sm.sub;   // sub, add, out: one stretch of 3 * AC_TILE words
-        const u32 CH = 3u * AC_TILE;
+        u32* s_nxt = (u32*)sm.tile[0].sub;   // sub, add: one stretch of 2 * AC_TILE words
+        const u32 CH = 2u * AC_TILE;
         if (tid == 0) sm.walk_n = 0;
         AC_SYNC();
         for (;;) {
