@@ -384,17 +384,19 @@ AC_HD bool ac_tile_resolve(AcShared& sm, AcTile& tl, u32 n, u32 nseg)
     return false;
 }
 
-// inclusive prefix minimum over the CTA's threads (thread order) of three values at once, continued from the minima of the chunks
-// before (carry, kept by every thread).  Every thread calls it.
+// exclusive prefix minimum over the CTA's threads (thread order) of three values at once, continued from the minima of the chunks
+// before (carry, kept by every thread): in go the threads' own minima, out come the minima of everything in front of the thread.
+// Every thread calls it.
 AC_HD void ac_scan_min3(AcShared& sm, u32& a, u32& b, u32& c, u32 carry[3])
 {
 #ifdef MCU_HOST_EMU
-    a = a < carry[0] ? a : carry[0];
-    b = b < carry[1] ? b : carry[1];
-    c = c < carry[2] ? c : carry[2];
-    carry[0] = a;
-    carry[1] = b;
-    carry[2] = c;
+    const u32 ia = a, ib = b, ic = c;
+    a = carry[0];
+    b = carry[1];
+    c = carry[2];
+    carry[0] = ia < carry[0] ? ia : carry[0];
+    carry[1] = ib < carry[1] ? ib : carry[1];
+    carry[2] = ic < carry[2] ? ic : carry[2];
 #else
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (u32 o = 1; o < 32; o <<= 1) {
@@ -410,6 +412,10 @@ AC_HD void ac_scan_min3(AcShared& sm, u32& a, u32& b, u32& c, u32 carry[3])
         sm.scan_w[1][warp] = b;
         sm.scan_w[2][warp] = c;
     }
+    a = __shfl_up_sync(0xffffffffu, a, 1);   // inclusive -> exclusive inside the warp
+    b = __shfl_up_sync(0xffffffffu, b, 1);
+    c = __shfl_up_sync(0xffffffffu, c, 1);
+    if (lane == 0) a = b = c = 0xffffffffu;
     __syncthreads();
     if (warp < 3) {   // warp v: the minima of the warps in front of every warp for value v; entry 32 = the chunk's minimum
         const u32 mine = lane < nwarps ? sm.scan_w[warp][lane] : 0xffffffffu;
@@ -461,6 +467,7 @@ AC_HD void ac_pair_range(AcShared& sm, const u8* code, u32 L, u32& first, u32& l
 }
 
 #define AC_NONE 0xffffffffu
+#define AC_V 4   // columns per thread and chunk in the two scans over a pair of rows
 // a column's pair of letters in six bits: 0..3 residues, 4 a letter outside the alphabet, 5 a gap; row 2 in bits 3..5
 AC_HD u32 ac_code(const u8* letter, u8 c1, u8 c2)
 {
@@ -489,22 +496,43 @@ AC_HD void ac_score_pair_scans(AcShared& sm, const u8* __restrict__ r1, const u8
     AC_SYNC();
     u32 first, last;
     ac_pair_range(sm, code, L, first, last);
-    // backwards: thread t of a chunk looks at column hi - 1 - t, so that a prefix minimum over the threads is a suffix minimum over columns
+    // Four columns per thread and chunk (AC_V): the thread's own columns are scanned in registers, the threads' minima by the CTA.
+    // backwards: thread t of a chunk looks at columns hi - 1 - (4 t + j), so that a prefix minimum in (t, j) order is a suffix minimum
+    // over columns
     {
         u32 carry[3] = {AC_NONE, AC_NONE, AC_NONE};
-        for (u32 hi = last + 1; hi > first; hi = hi > nt ? hi - nt : 0) {
-            const bool valid = tid < hi && hi - 1 - tid >= first;
-            const u32 c = valid ? hi - 1 - tid : 0;
-            const u32 k = valid ? code[c] : 0;
-            const bool g1 = AC_G1(k), g2 = AC_G2(k), two = !g1 && !g2;
-            u32 n_two = valid && two ? c : AC_NONE, n_g1 = valid && g1 && !g2 ? c : AC_NONE, n_g2 = valid && g2 && !g1 ? c : AC_NONE;
-            ac_scan_min3(sm, n_two, n_g1, n_g2, carry);
-            bool head = valid && !two;
-            if (head && c != first) {
-                const u32 kb = code[c - 1];
-                head = !AC_G1(kb) && !AC_G2(kb);
+        for (u32 hi = last + 1; hi > first; hi = hi > AC_V * nt ? hi - AC_V * nt : 0) {
+            u32 col[AC_V], kk[AC_V], m_two[AC_V], m_g1[AC_V], m_g2[AC_V];
+            u32 r_two = AC_NONE, r_g1 = AC_NONE, r_g2 = AC_NONE;
+#pragma unroll
+            for (int j = 0; j < AC_V; ++j) {
+                const u32 idx = AC_V * tid + j;
+                const bool valid = idx < hi && hi - 1 - idx >= first;
+                const u32 c = valid ? hi - 1 - idx : AC_NONE;
+                const u32 k = valid ? code[c] : 0;
+                const bool g1 = AC_G1(k), g2 = AC_G2(k);
+                col[j] = c;
+                kk[j] = k;
+                if (valid && !g1 && !g2) r_two = c;        // (columns descend: a later one is the smaller index)
+                if (valid && g1 && !g2) r_g1 = c;
+                if (valid && g2 && !g1) r_g2 = c;
+                m_two[j] = r_two;
+                m_g1[j] = r_g1;
+                m_g2[j] = r_g2;
             }
-            if (head) {
+            ac_scan_min3(sm, r_two, r_g1, r_g2, carry);   // now: the minima over everything behind this thread's columns
+#pragma unroll
+            for (int j = 0; j < AC_V; ++j) {
+                const u32 c = col[j];
+                if (c == AC_NONE) continue;
+                const u32 k = kk[j];
+                if (!AC_G1(k) && !AC_G2(k)) continue;
+                if (c != first) {   // a run starts behind a column with two letters
+                    const u32 kb = code[c - 1];
+                    if (AC_G1(kb) || AC_G2(kb)) continue;
+                }
+                const u32 n_two = m_two[j] < r_two ? m_two[j] : r_two, n_g1 = m_g1[j] < r_g1 ? m_g1[j] : r_g1,
+                          n_g2 = m_g2[j] < r_g2 ? m_g2[j] : r_g2;
                 const u32 e = n_two < last + 1 ? n_two : last + 1;
                 const u32 f1 = n_g1 < e ? n_g1 : AC_NONE, f2 = n_g2 < e ? n_g2 : AC_NONE;
                 u32 left = AC_NONE, end = e;
@@ -532,28 +560,38 @@ AC_HD void ac_score_pair_scans(AcShared& sm, const u8* __restrict__ r1, const u8
                 d_per[c] = __float_as_uint(per_site);
 #endif
             }
-            if (hi <= nt) break;
+            if (hi <= AC_V * nt) break;
         }
     }
     AC_SYNC();
     // forwards: the run's first column in front of (or at) every column, then the column's share of the run's penalty
     {
         u32 carry[3] = {AC_NONE, AC_NONE, AC_NONE};
-        for (u32 c0 = 0; c0 < L; c0 += nt) {
-            const u32 c = c0 + tid;
-            const bool valid = c < L;
-            const u32 k = valid ? code[c] : 0;
-            const bool g1 = AC_G1(k), g2 = AC_G2(k), two = !g1 && !g2;
-            bool head = valid && !two && c >= first && c <= last;
-            if (head && c != first) {
-                const u32 kb = code[c - 1];
-                head = !AC_G1(kb) && !AC_G2(kb);
+        for (u32 c0 = 0; c0 < L; c0 += AC_V * nt) {
+            u32 kk[AC_V], hh[AC_V];
+            u32 r_h = AC_NONE, x1 = AC_NONE, x2 = AC_NONE;
+#pragma unroll
+            for (int j = 0; j < AC_V; ++j) {
+                const u32 c = c0 + AC_V * tid + j;
+                const bool valid = c < L;
+                const u32 k = valid ? code[c] : 0;
+                kk[j] = k;
+                bool head = valid && (AC_G1(k) || AC_G2(k)) && c >= first && c <= last;
+                if (head && c != first) {
+                    const u32 kb = j ? kk[j - 1] : code[c - 1];
+                    head = !AC_G1(kb) && !AC_G2(kb);
+                }
+                // (the latest first-column-of-a-run at or in front of c: the largest one, as a minimum of complements.  A column that
+                //  lies behind that run's end -- one with two letters, or all-gap columns behind the pair's range -- gets nothing from it)
+                if (head) r_h = ~(c + 1);
+                hh[j] = r_h;
             }
-            // (the latest first-column-of-a-run at or in front of c: the largest one, as a minimum of complements.  A column that lies
-            //  behind that run's end -- one with two letters, or all-gap columns behind the pair's range -- gets nothing from it)
-            u32 h = head ? ~(c + 1) : AC_NONE, x1 = AC_NONE, x2 = AC_NONE;
-            ac_scan_min3(sm, h, x1, x2, carry);
-            if (valid) {
+            ac_scan_min3(sm, r_h, x1, x2, carry);
+#pragma unroll
+            for (int j = 0; j < AC_V; ++j) {
+                const u32 c = c0 + AC_V * tid + j;
+                if (c >= L) continue;
+                const u32 h = hh[j] < r_h ? hh[j] : r_h, k = kk[j];
                 float g = 0.0f;
                 if (h != AC_NONE) {
                     const u32 hc = ~h - 1;
