@@ -921,8 +921,11 @@ __global__ void anchor_cols_pack_kernel(const AcWindow* __restrict__ windows, co
     for (u32 k = threadIdx.x; k < n; k += blockDim.x) dense[to + k] = cols[w.col_off + k];
 }
 
+#define AC_STAGE_BYTES (1u << 20)
+#define AC_COUNTER_BYTES 64u
 struct AcState {
-    DevBuf windows, rows, weights, score, smooth, gg, best, nxt, heads, cols, counts, dense, dense_off, seg_counters;
+    DevBuf windows, rows, weights, score, smooth, gg, best, nxt, heads, cols, counts, dense, dense_off, seg_counters, in_blob, out_blob;
+    u8 *h_in = nullptr, *h_out = nullptr;   // pinned staging blocks of the small-call path
     u64 last_counters[2 + AC_PHASES] = {0};
     size_t max_dyn_smem = 0;
     cudaStream_t stream = nullptr;
@@ -934,8 +937,11 @@ void ac_release()
 {
     AcState& st = g_ac;
     DevBuf* bufs[] = {&st.windows, &st.rows, &st.weights, &st.score, &st.smooth, &st.gg, &st.best, &st.nxt, &st.heads, &st.cols, &st.counts,
-                      &st.dense, &st.dense_off, &st.seg_counters};
+                      &st.dense, &st.dense_off, &st.seg_counters, &st.in_blob, &st.out_blob};
     for (DevBuf* b : bufs) b->release();
+    if (st.h_in) cudaFreeHost(st.h_in);
+    if (st.h_out) cudaFreeHost(st.h_out);
+    st.h_in = st.h_out = nullptr;
 }
 
 void ac_last_counters(u64* out8)
@@ -1014,17 +1020,54 @@ int ac_batch(u64 n, const char* rows, const u64* row_off, const u32* ncol, const
     }
     cudaStream_t s = st.stream;
     const u64 ct = cols_total ? cols_total : 1;
-    MCU_TRY(st.windows.reserve(n * sizeof(AcWindow)));
-    MCU_TRY(st.rows.reserve(rows_bytes ? rows_bytes : 1));
-    MCU_TRY(st.weights.reserve((n_weights ? n_weights : 1) * sizeof(float)));
     MCU_TRY(st.score.reserve(ct * 4)); MCU_TRY(st.smooth.reserve(ct * 4)); MCU_TRY(st.gg.reserve(ct * 4));
-    MCU_TRY(st.best.reserve(ct * 4)); MCU_TRY(st.nxt.reserve(ct * 4)); MCU_TRY(st.heads.reserve(ct * 4)); MCU_TRY(st.cols.reserve(ct * 4));
-    MCU_TRY(st.counts.reserve(n * 4));
-    MCU_TRY(st.seg_counters.reserve(sizeof st.last_counters));
-    MCU_CUDA(cudaMemsetAsync(st.seg_counters.p, 0, sizeof st.last_counters, s));
-    MCU_CUDA(cudaMemcpyAsync(st.windows.p, win.data(), n * sizeof(AcWindow), cudaMemcpyHostToDevice, s));
-    if (rows_bytes) MCU_CUDA(cudaMemcpyAsync(st.rows.p, rows, rows_bytes, cudaMemcpyHostToDevice, s));
-    if (weights) MCU_CUDA(cudaMemcpyAsync(st.weights.p, weights, n_weights * sizeof(float), cudaMemcpyHostToDevice, s));
+    MCU_TRY(st.best.reserve(ct * 4)); MCU_TRY(st.nxt.reserve(ct * 4)); MCU_TRY(st.heads.reserve(ct * 4));
+    // One window per call is the aligner's case, and there every transfer counts: a call whose inputs and outputs are small goes through
+    // two pinned staging blocks -- windows, weights and rows down in ONE copy, counters, counts and columns back in ONE copy
+    const u64 in_w = (n * sizeof(AcWindow) + 15) & ~15ull, in_f = (n_weights * sizeof(float) + 15) & ~15ull;
+    const u64 in_bytes = in_w + in_f + rows_bytes;
+    const u64 out_c = (n * 4 + 15) & ~15ull, out_bytes = AC_COUNTER_BYTES + out_c + ct * 4;
+    const bool staged = in_bytes <= AC_STAGE_BYTES && out_bytes <= AC_STAGE_BYTES;
+    const AcWindow* d_windows;
+    const u8* d_rows;
+    const float* d_weights;
+    u32 *d_counts, *d_cols;
+    unsigned long long* d_counters;
+    if (staged) {
+        if (!st.h_in) {
+            MCU_CUDA(cudaMallocHost(&st.h_in, AC_STAGE_BYTES));
+            MCU_CUDA(cudaMallocHost(&st.h_out, AC_STAGE_BYTES));
+        }
+        MCU_TRY(st.in_blob.reserve(AC_STAGE_BYTES));
+        MCU_TRY(st.out_blob.reserve(AC_STAGE_BYTES));
+        memcpy(st.h_in, win.data(), n * sizeof(AcWindow));
+        if (weights) memcpy(st.h_in + in_w, weights, n_weights * sizeof(float));
+        if (rows_bytes) memcpy(st.h_in + in_w + in_f, rows, rows_bytes);
+        MCU_CUDA(cudaMemcpyAsync(st.in_blob.p, st.h_in, in_bytes, cudaMemcpyHostToDevice, s));
+        d_windows = st.in_blob.as<AcWindow>();
+        d_weights = (const float*)(st.in_blob.as<u8>() + in_w);
+        d_rows = st.in_blob.as<u8>() + in_w + in_f;
+        d_counters = st.out_blob.as<unsigned long long>();
+        d_counts = (u32*)(st.out_blob.as<u8>() + AC_COUNTER_BYTES);
+        d_cols = (u32*)(st.out_blob.as<u8>() + AC_COUNTER_BYTES + out_c);
+    } else {
+        MCU_TRY(st.windows.reserve(n * sizeof(AcWindow)));
+        MCU_TRY(st.rows.reserve(rows_bytes ? rows_bytes : 1));
+        MCU_TRY(st.weights.reserve((n_weights ? n_weights : 1) * sizeof(float)));
+        MCU_TRY(st.cols.reserve(ct * 4));
+        MCU_TRY(st.counts.reserve(n * 4));
+        MCU_TRY(st.seg_counters.reserve(AC_COUNTER_BYTES));
+        MCU_CUDA(cudaMemcpyAsync(st.windows.p, win.data(), n * sizeof(AcWindow), cudaMemcpyHostToDevice, s));
+        if (rows_bytes) MCU_CUDA(cudaMemcpyAsync(st.rows.p, rows, rows_bytes, cudaMemcpyHostToDevice, s));
+        if (weights) MCU_CUDA(cudaMemcpyAsync(st.weights.p, weights, n_weights * sizeof(float), cudaMemcpyHostToDevice, s));
+        d_windows = st.windows.as<AcWindow>();
+        d_weights = st.weights.as<float>();
+        d_rows = st.rows.as<u8>();
+        d_counters = st.seg_counters.as<unsigned long long>();
+        d_counts = st.counts.as<u32>();
+        d_cols = st.cols.as<u32>();
+    }
+    MCU_CUDA(cudaMemsetAsync(d_counters, 0, AC_COUNTER_BYTES, s));
     MCU_CUDA(cudaEventRecord(st.ev0, s));
     // few windows: the latency form (1024 threads, per-column arrays in shared memory); a full batch: CTAs of 256 threads, several per
     // SM, so that one window's serial stretches run under the others' parallel ones
@@ -1038,20 +1081,27 @@ int ac_batch(u64 n, const char* rows, const u64* row_off, const u32* ncol, const
         if (smem_cols > cap) smem_cols = cap;
     }
     anchor_cols_kernel<<<(unsigned)n, latency_form ? AC_BLOCK : 256, (size_t)smem_cols * 8, s>>>(
-        st.windows.as<AcWindow>(), st.rows.as<u8>(), weights ? st.weights.as<float>() : nullptr, p, st.score.as<float>(), st.smooth.as<float>(),
-        st.gg.as<float>(), st.best.as<u32>(), st.nxt.as<u32>(), st.heads.as<u32>(), st.cols.as<u32>(), st.counts.as<u32>(),
-        st.seg_counters.as<unsigned long long>(), smem_cols, (score_out || smooth_out) ? 1 : 0);
+        d_windows, d_rows, weights ? d_weights : nullptr, p, st.score.as<float>(), st.smooth.as<float>(), st.gg.as<float>(), st.best.as<u32>(),
+        st.nxt.as<u32>(), st.heads.as<u32>(), d_cols, d_counts, d_counters, smem_cols, (score_out || smooth_out) ? 1 : 0);
     MCU_CUDA(cudaGetLastError());
     MCU_CUDA(cudaEventRecord(st.ev1, s));
-    MCU_CUDA(cudaMemcpyAsync(n_cols_out, st.counts.p, n * 4, cudaMemcpyDeviceToHost, s));
-    MCU_CUDA(cudaMemcpyAsync(st.last_counters, st.seg_counters.p, sizeof st.last_counters, cudaMemcpyDeviceToHost, s));
     if (cols_total) {
         if (score_out) MCU_CUDA(cudaMemcpyAsync(score_out, st.score.p, cols_total * 4, cudaMemcpyDeviceToHost, s));
         if (smooth_out) MCU_CUDA(cudaMemcpyAsync(smooth_out, st.smooth.p, cols_total * 4, cudaMemcpyDeviceToHost, s));
     }
-    const bool packed = n > 1 && cols_total * 4 > (1u << 20);   // one window, or a small batch: the column slots travel as they are
-    if (cols_total && !packed) MCU_CUDA(cudaMemcpyAsync(cols_out, st.cols.p, cols_total * 4, cudaMemcpyDeviceToHost, s));
-    MCU_CUDA(cudaStreamSynchronize(s));
+    const bool packed = !staged && n > 1 && cols_total * 4 > (1u << 20);   // a batch's columns are packed on the device before they travel
+    if (staged) {
+        MCU_CUDA(cudaMemcpyAsync(st.h_out, st.out_blob.p, AC_COUNTER_BYTES + out_c + cols_total * 4, cudaMemcpyDeviceToHost, s));
+        MCU_CUDA(cudaStreamSynchronize(s));
+        memcpy(st.last_counters, st.h_out, sizeof st.last_counters);
+        memcpy(n_cols_out, st.h_out + AC_COUNTER_BYTES, n * 4);
+        if (cols_total) memcpy(cols_out, st.h_out + AC_COUNTER_BYTES + out_c, cols_total * 4);
+    } else {
+        MCU_CUDA(cudaMemcpyAsync(n_cols_out, d_counts, n * 4, cudaMemcpyDeviceToHost, s));
+        MCU_CUDA(cudaMemcpyAsync(st.last_counters, d_counters, sizeof st.last_counters, cudaMemcpyDeviceToHost, s));
+        if (cols_total && !packed) MCU_CUDA(cudaMemcpyAsync(cols_out, d_cols, cols_total * 4, cudaMemcpyDeviceToHost, s));
+        MCU_CUDA(cudaStreamSynchronize(s));
+    }
     if (device_ms) MCU_CUDA(cudaEventElapsedTime(device_ms, st.ev0, st.ev1));
     if (cols_total && packed) {
         std::vector<u64> off(n + 1);
