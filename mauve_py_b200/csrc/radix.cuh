@@ -89,8 +89,13 @@ __global__ void __launch_bounds__(RS_BLOCK, 2) rs_onesweep_kernel(const K* __res
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         u32 loc = chunk + i * 32 + lane;
-        key[i] = loc < tile_n ? kin[tile_base + loc] : (K)~(K)0;
+        key[i] = loc < tile_n ? __ldcs(kin + tile_base + loc) : (K)~(K)0;   // read once: streaming, so that the lines below stay in L1
     }
+    // the values are not touched before the keys are ranked and the tile's place is known: their lines are asked for now (one 128-byte
+    // line per warp and item, no register spent), and the loads of the placement step find them in L1
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+        if (lane == 0 && chunk + i * 32 < tile_n) asm volatile("prefetch.global.L1 [%0];" ::"l"(vin + tile_base + chunk + i * 32));
 
     // ---- rank inside the warp ----
     u32 rank[IPT];
