@@ -6,8 +6,9 @@
 // One CTA per window; the batch is the grid.  What the reference does column after column is split by what really depends on what:
 //   * letter scores: per column;
 //   * gap penalties: the reference's running state (bGapping1/2, gap_left_col, cur_gap_score) is reset by every column that holds two
-//     letters, so the columns between two such columns form a run that is scored on its own: one thread walks each run with the
-//     reference's state machine and spreads the penalty, all runs at once;
+//     letters, so the columns between two such columns form a run that is scored on its own, and without an extension penalty (the DNA
+//     setting) the state machine has a closed form per run: two block-wide scans over the columns (ac_score_pair_scans), in the same
+//     time whatever the runs look like.  With an extension penalty a run is a float sum in column order: one thread walks each run;
 //   * smoothing: ONE running float sum per window whose roundings depend on the order.  Where no addition of the chain rounds, the
 //     chain is plain arithmetic and any order gives its values: per segment of 32 columns the prefix sums of (add - sub) are formed by
 //     a warp scan in which every addition is tested for exactness (the error term of TwoSum is zero), then total + prefix, - sub,
@@ -15,10 +16,13 @@
 //     at once against the totals they would start from if nothing before them rounded; the first one that fails is run as the
 //     serial chain it always was (two dependent FADDs per column on one lane), which gives the true total behind it, and the
 //     segments after it are tested again.  A tile full of rounding columns (gap penalties like -400/3 in the window) is the serial
-//     chain outright, and so are the two tiles after it.  Operands come through shared memory tile by tile, loaded one tile ahead;
-//   * best columns: flag + ordered block-wide compaction;
-//   * merging: `next group head` is a function of the head alone (a binary search per best column, in parallel), the groups are then the
-//     walk head -> next head (one lane, a few hundred steps), the pick per group in parallel.
+//     chain outright, and so are the two tiles after it.  Two tile buffers: while one lane sums a tile the other warps store the tile
+//     before and fill and prepare the tile after;
+//   * best columns: flag + ordered block-wide compaction, which also leaves "best columns in front of column c" for every column;
+//   * merging: `next group head` is a function of the head alone (one look-up in that table), the groups are then the walk
+//     head -> next head (one lane, a few hundred steps through shared memory), the pick per group in parallel.
+// A call with few windows keeps the per-column arrays in dynamic shared memory (CTAs of 1,024 threads, one per SM); a batch runs CTAs of
+// 256 threads over global scratch, several per SM.
 // Every float operation is the reference's, in the reference's order, in round-to-nearest without contraction (__fadd_rn & co).
 // Everything that decides a value sits in functions that also compile for the host (-DMCU_HOST_EMU: the CTA becomes one thread;
 // tests/_emu.py, test-only -- the product library has no host path).
