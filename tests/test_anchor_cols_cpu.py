@@ -139,3 +139,26 @@ def test_kernel_value_path_with_other_settings():
         c1, s1, m1, _, _ = _oracle.anchor_cols(rows, 1, params=p)
         c2, s2, m2 = _emu_cols(rows, 1, np.ones(2, dtype=np.float32), p)
         assert np.array_equal(c1, c2) and _same_floats(s1, s2) and _same_floats(m1, m2), it
+
+
+def test_kernel_value_path_at_the_edges_of_the_exactness_tests():
+    """weights that push the scores to 1e8 and down to 1e-4 (sums that do / do not fit 24 bits, fractions of every size), rows of
+    wildcards only, lengths around the smoothing window and around the tile size of the kernel: the speculation in the smoothing
+    chain may take or refuse what it likes, the answer has to be the oracle's"""
+    rng = np.random.default_rng(23)
+    cases = []
+    for scale in (1e6, 3.0e5, 1024.0, 0.5, 1.0 / 3.0, 1e-4):
+        rows = synth.alignment_window(2600, seed=int(scale * 7) % 1000 + 1, snp=0.05, gap_rate=0.003)
+        cases.append((rows, 1, np.array([scale, 1.0], dtype=np.float32)))
+        cases.append((rows, 1, np.array([scale, scale], dtype=np.float32)))
+    for ncol in (21, 22, 23, 42, 43, 511 + 21, 512 + 21, 513 + 21, 1023 + 21, 1024 + 21, 1025 + 21, 2048 + 21, 2049 + 21):
+        cases.append((synth.alignment_window(ncol, seed=ncol, gap_rate=0.004), 1, np.ones(2, dtype=np.float32)))
+    wild = np.full((2, 900), ord("N"), dtype=np.uint8)
+    cases.append((wild, 1, np.ones(2, dtype=np.float32)))
+    half = synth.alignment_window(900, seed=3)
+    half[1, :450] = ord("N")
+    cases.append((half, 1, np.ones(2, dtype=np.float32)))
+    for rows, n1, w in cases:
+        c1, s1, m1, _, _ = _oracle.anchor_cols(rows, n1, weights=w)
+        c2, s2, m2 = _emu_cols(rows, n1, w)
+        assert np.array_equal(c1, c2) and _same_floats(s1, s2) and _same_floats(m1, m2), (rows.shape, w)

@@ -329,6 +329,29 @@ def test_anchor_cols_vs_oracle(mp):
         assert np.array_equal(g[0], c) and np.array_equal(_bits(g[1]), _bits(s)) and np.array_equal(_bits(g[2]), _bits(m)), k
 
 
+def test_anchor_cols_at_the_edges_of_the_exactness_tests(mp):
+    """weights that push the scores to 1e8 and down to 1e-4 (sums that do / do not fit 24 bits, fractions of every size), rows of
+    wildcards only, lengths around the smoothing window and around the tile size of the kernel, in one batch and one by one"""
+    cases = []
+    for scale in (1e6, 3.0e5, 1024.0, 0.5, 1.0 / 3.0, 1e-4):
+        rows = synth.alignment_window(2600, seed=int(scale * 7) % 1000 + 1, snp=0.05, gap_rate=0.003)
+        cases.append((rows, 1, np.array([scale, 1.0], dtype=np.float32)))
+        cases.append((rows, 1, np.array([scale, scale], dtype=np.float32)))
+    for ncol in (21, 22, 23, 42, 43, 511 + 21, 512 + 21, 513 + 21, 1023 + 21, 1024 + 21, 1025 + 21, 2048 + 21, 2049 + 21):
+        cases.append((synth.alignment_window(ncol, seed=ncol, gap_rate=0.004), 1, np.ones(2, dtype=np.float32)))
+    wild = np.full((2, 900), ord("N"), dtype=np.uint8)
+    cases.append((wild, 1, np.ones(2, dtype=np.float32)))
+    half = synth.alignment_window(900, seed=3)
+    half[1, :450] = ord("N")
+    cases.append((half, 1, np.ones(2, dtype=np.float32)))
+    batch = mp.libmems.FindAnchorColsPP_batch(cases, return_scores=True)
+    for k, (rows, n1, w) in enumerate(cases):
+        c, s, m, _, _ = _oracle.anchor_cols(rows, n1, weights=w)
+        one = mp.libmems.FindAnchorColsPP_batch([(rows, n1, w)], return_scores=True)[0]
+        for got in (batch[k], one):
+            assert np.array_equal(got[0], c) and np.array_equal(_bits(got[1]), _bits(s)) and np.array_equal(_bits(got[2]), _bits(m)), (k, rows.shape, w)
+
+
 def test_anchor_cols_argument_errors(mp):
     rows = synth.alignment_window(100, seed=1)
     p = mp.libmems.AnchorParams.default()
