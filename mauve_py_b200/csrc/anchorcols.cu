@@ -148,12 +148,17 @@ __device__ __forceinline__ void ac_block_minmax(AcShared& sm, int lo, int hi)
         atomicMax(&sm.last, hi);
     }
 }
-// exclusive rank of this thread's flag inside the CTA and the CTA's total (every thread calls it)
-__device__ __forceinline__ u32 ac_block_rank(AcShared& sm, bool flag, u32& total)
+// how many of the threads in front of this one raise, in total, `count` (exclusive prefix sum over the CTA's threads), and the CTA's total
+// (every thread calls it)
+__device__ __forceinline__ u32 ac_block_rank(AcShared& sm, u32 count, u32& total)
 {
-    const u32 b = __ballot_sync(0xffffffffu, flag);
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    if (lane == 0) sm.warp_sum[warp] = __popc(b);
+    u32 winc = count;
+    for (u32 o = 1; o < 32; o <<= 1) {
+        const u32 up = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += up;
+    }
+    if (lane == 31) sm.warp_sum[warp] = winc;
     __syncthreads();
     if (warp == 0) {   // the warps' counts -> exclusive prefixes, entry 32 = the total
         const u32 v = lane < nwarps ? sm.warp_sum[lane] : 0;
@@ -167,7 +172,7 @@ __device__ __forceinline__ u32 ac_block_rank(AcShared& sm, bool flag, u32& total
     }
     __syncthreads();
     total = sm.warp_sum[32];
-    return sm.warp_sum[warp] + __popc(b & ((1u << lane) - 1));
+    return sm.warp_sum[warp] + winc - count;
 }
 #endif
 
@@ -797,43 +802,68 @@ AC_HD void ac_window(AcShared& sm, const AcWindow w, const u8* __restrict__ rows
 
     // ---- FindBestColsComboPP: the columns that pass both thresholds, in order; before[c] = how many of them lie in front of column c
     u32 nbest = 0;
-    for (u32 c0 = 0; c0 < L; c0 += nt) {
-        const u32 c = c0 + tid;
-        const bool flag = c < L && !(score[c] < p.min_best_col) && !(smooth[c] < p.min_smooth);
 #ifdef MCU_HOST_EMU
+    for (u32 c = 0; c < L; ++c) {
         before[c] = nbest;
-        if (flag) best[nbest++] = c;
+        if (!(score[c] < p.min_best_col) && !(smooth[c] < p.min_smooth)) best[nbest++] = c;
+    }
 #else
+    for (u32 c0 = 0; c0 < L; c0 += AC_V * nt) {   // per step every warp takes 4 x 32 consecutive columns (one ballot per 32)
+        const u32 lane = tid & 31, wbase = c0 + (tid >> 5) * (AC_V * 32);
+        u32 b[AC_V], wtot = 0;
+#pragma unroll
+        for (int j = 0; j < AC_V; ++j) {
+            const u32 c = wbase + j * 32 + lane;
+            b[j] = __ballot_sync(0xffffffffu, c < L && !(score[c] < p.min_best_col) && !(smooth[c] < p.min_smooth));
+            wtot += __popc(b[j]);
+        }
         u32 total;
-        const u32 rank = nbest + ac_block_rank(sm, flag, total);
-        if (c < L) before[c] = rank;
-        if (flag) best[rank] = c;
+        u32 rank = ac_block_rank(sm, lane == 0 ? wtot : 0u, total);   // lane 0: the best columns of the warps in front
+        rank = nbest + __shfl_sync(0xffffffffu, rank, 0);
+#pragma unroll
+        for (int j = 0; j < AC_V; ++j) {
+            const u32 c = wbase + j * 32 + lane;
+            const u32 mine = rank + __popc(b[j] & ((1u << lane) - 1u));
+            if (c < L) before[c] = mine;
+            if (b[j] & (1u << lane)) best[mine] = c;
+            rank += __popc(b[j]);
+        }
         nbest += total;
         __syncthreads();
-#endif
     }
+#endif
     AC_SYNC();
 
     if (tid == 0) sm.clk[3] = AC_CLOCK();
 
     // ---- MergeBestCols: groups of best columns closer to the group's first one than the spacing.  The group that starts at best[n]
-    //      ends in front of the first best column at or beyond best[n] + spacing
-    for (u32 n = tid; n < nbest; n += nt) {
-        const u64 stop = (u64)best[n] + p.anchor_spacing;
-        nxt[n] = stop < L ? before[stop] : nbest;
-    }
-    AC_SYNC();
+    //      ends in front of the first best column at or beyond best[n] + spacing: one look-up in `before`
+#define AC_GROUP_END(n_) ((u64)best[n_] + p.anchor_spacing < L ? before[(u64)best[n_] + p.anchor_spacing] : nbest)
     if (tid == 0) sm.clk[4] = AC_CLOCK();
-    {   // the walk head -> next head, one lane, through chunks of `nxt` in shared memory
-        u32* s_nxt = (u32*)sm.tile[0].sub;   // sub, add: one stretch of 2 * AC_TILE words
-        const u32 CH = 2u * AC_TILE;
+    {   // the walk head -> next head, one lane, through chunks of group ends in shared memory (the two smoothing tiles' memory)
+        u32* s_nxt = (u32*)&sm.tile[0];
+        const u32 CH = (u32)(2 * sizeof(AcTile) / sizeof(u32));
         if (tid == 0) sm.walk_n = 0;
         AC_SYNC();
         for (;;) {
             const u32 c0 = sm.walk_n;
             if (c0 >= nbest) break;
             const u32 cn = nbest - c0 < CH ? nbest - c0 : CH;
-            for (u32 k = tid; k < cn; k += nt) s_nxt[k] = nxt[c0 + k];
+            for (u32 k0 = 0; k0 < cn; k0 += 8 * nt) {   // eight look-ups per thread in flight
+                u32 stop[8], end[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const u32 k = k0 + j * nt + tid;
+                    stop[j] = k < cn ? best[c0 + k] + p.anchor_spacing : 0xffffffffu;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) end[j] = stop[j] < L ? before[stop[j]] : nbest;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const u32 k = k0 + j * nt + tid;
+                    if (k < cn) s_nxt[k] = end[j];
+                }
+            }
             AC_SYNC();
             if (tid == 0) {
                 u32 n = c0, k = sm.nanchor;
@@ -851,23 +881,16 @@ AC_HD void ac_window(AcShared& sm, const AcWindow w, const u8* __restrict__ rows
     if (tid == 0) sm.clk[5] = AC_CLOCK();
     const u32 nanchor = sm.nanchor;
     for (u32 k = tid; k < nanchor; k += nt) {
-        const u32 n = heads[k], within = nxt[n] - n - 1, head = best[n];
+        const u32 n = heads[k], within = AC_GROUP_END(n) - n - 1, head = best[n];
         u32 pick = head;
         if (within == 1) {
             const u32 other = best[n + 1];
             pick = score[head] > score[other] ? head : other;
         } else if (within > 1) {
-            // "closest to the centre" as the reference computes it: the distance is taken from the group's first column, and the last
-            // member of the group is not looked at (MU/anchors.cpp:164-179)
-            int closest = (int)p.anchor_spacing;
-            for (u32 i = n + 1; i < n + within; ++i) {
-                int d = (int)(best[i] - head);
-                if (d < 0) d = -d;
-                if (d < closest) {
-                    pick = best[i];
-                    closest = d;
-                }
-            }
+            // "closest to the centre" as the reference computes it (MU/anchors.cpp:164-179): the distance is taken from the group's FIRST
+            // column, over the members but the first and the last, and the first smaller one wins -- in an ascending list that is the
+            // second member, whose distance is below the spacing by the definition of the group
+            pick = best[n + 1];
         }
         cols_out[k] = pick;
     }
@@ -875,6 +898,7 @@ AC_HD void ac_window(AcShared& sm, const AcWindow w, const u8* __restrict__ rows
         *count_out = nanchor;
         sm.clk[6] = AC_CLOCK();
     }
+#undef AC_GROUP_END
 }
 
 #ifndef MCU_HOST_EMU
