@@ -18,7 +18,8 @@
 //     segments after it are tested again.  A tile full of rounding columns (gap penalties like -400/3 in the window) is the serial
 //     chain outright, and so are the two tiles after it.  Two tile buffers: while one lane sums a tile the other warps store the tile
 //     before and fill and prepare the tile after;
-//   * best columns: flag + ordered block-wide compaction, which also leaves "best columns in front of column c" for every column;
+//   * best columns: ballots over 4 x 32 consecutive columns per warp and step + a block-wide scan of the warps' counts, which also leaves
+//     "best columns in front of column c" for every column;
 //   * merging: `next group head` is a function of the head alone (one look-up in that table), the groups are then the walk
 //     head -> next head (one lane, a few hundred steps through shared memory), the pick per group in parallel.
 // A call with few windows keeps the per-column arrays in dynamic shared memory (CTAs of 1,024 threads, one per SM); a batch runs CTAs of
