@@ -392,10 +392,15 @@ def measure_anchor_cols(mp, synth, args, rank=0):
     call(1)
     wall1 = time.perf_counter() - t0
     dev1 = float(ms.value)
+    ctr = np.zeros(8, dtype=np.uint64)
+    lib.mcu_test_anchor_counters(ctr.ctypes.data)
     out = {"metric": "alignment columns/s through FindAnchorColsPP (per-column SP score, smoothing, best columns, merging; floats identical to the reference)",
            "windows": n, "columns_per_window": ncol, "value": n * ncol / wall, "unit": "columns/s", "wall_ms": 1e3 * wall, "device_ms": dev,
            "kernel_only_columns_s": n * ncol / (dev * 1e-3),
-           "single_window": {"columns": ncol, "wall_ms": 1e3 * wall1, "device_ms": dev1},
+           "single_window": {"columns": ncol, "wall_ms": 1e3 * wall1, "device_ms": dev1,
+                             "smoothing_segments_exact_chain": [int(ctr[0]), int(ctr[1])],
+                             "sm_cycles": {"scoring": int(ctr[2]), "smoothing": int(ctr[3]), "best_columns": int(ctr[4]),
+                                           "group_walk": int(ctr[5]) + int(ctr[6]), "picks": int(ctr[7])}},
            "timing": "wall clock around mcu_anchor_cols_batch with HOST buffers (rows in, anchor columns back); device_ms = the kernel alone"}
     if not args.no_cpu and rank == 0:
         import _oracle
